@@ -1,0 +1,185 @@
+"""CPU restatement (numpy) of the reference's D=2 lattice form calculus.
+
+TEST INFRASTRUCTURE ONLY -- this module is the *checker* for the CUDA path.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
+
+Fields are plain ndarrays shaped (C, N, N) -- the reference's compact layout
+(supervillain/lattice/compact.py:665-716) with the component axis first -- or with any number
+of leading batch axes, (..., C, N, N).  Axis -2 is lattice direction 0, axis -1 is direction 1.
+
+Each function cites the reference lines it restates.  The arithmetic ORDER of the reference's
+numba kernels (supervillain/lattice/_kernels.py:19-46) is kept so float results are bit-equal.
+"""
+import numpy as np
+
+TWO_PI = 2 * np.pi
+
+
+def fft_coordinates(N):
+    """Index -> FFT-convention coordinate, [0, 1, ..., N//2, -(N-1)//2, ..., -1].
+
+    Restates supervillain/lattice/__init__.py:4-9 (`_dimension`).
+    """
+    idx = np.arange(N)
+    return np.where(idx <= N // 2, idx, idx - N)
+
+
+def colour_map(N):
+    """(N, N) int array: checkerboard colour of every site.
+
+    Restates supervillain/lattice/compact.py:192-239 for D=2: even N has two colours given by the
+    parity of the coordinate sum; odd N has four, enumerated as 2*b + parity where b=0 when the
+    two FFT coordinates fall in the same sign class (both >=0 or both <0) and b=1 otherwise
+    (`_hyperoctant_pair_mask`, compact.py:36-53).
+    """
+    c = fft_coordinates(N)
+    c0, c1 = np.meshgrid(c, c, indexing='ij')
+    parity = np.mod(c0 + c1, 2)
+    if N % 2 == 0:
+        return parity.astype(np.int64)
+    mixed = ((c0 >= 0) != (c1 >= 0)).astype(np.int64)
+    return 2 * mixed + parity
+
+
+def n_colours(N):
+    return 2 if N % 2 == 0 else 4
+
+
+def colour_sites(N):
+    """Tuple (one entry per colour) of (x0, x1) index arrays in row-major order.
+
+    Same content and order as `Lattice.checkerboarding` (compact.py:231-239), which is built from
+    `np.where` and therefore row-major within a colour.
+    """
+    cmap = colour_map(N)
+    return tuple(np.where(cmap == c) for c in range(n_colours(N)))
+
+
+# ---------------------------------------------------------------------------------------------
+# d, delta, face_sum, coface_sum.  Incidence rows for D=2 (compact.py:144-174):
+#   d,0:     (0,0,0,+) (1,0,1,+)          d,1:        (0,1,0,+) (0,0,1,-)
+#   delta,1: (0,0,0,+) (0,1,1,+)          delta,2:    (0,0,1,-) (1,0,0,+)
+#   face_sum / coface_sum: the same rows with sign +1.
+# Kernel bodies (_kernels.py:31-45):
+#   d:      res[out] += sign * (F[in][x+e] - F[in][x])
+#   delta:  res[out] -= sign * (F[in][x] - F[in][x-e])
+#   sums:   res[out] += F[in][x];  res[out] += F[in][x +/- e]      (two separate adds)
+# ---------------------------------------------------------------------------------------------
+
+def _fwd(a, axis):
+    """a[x + e_axis] (periodic); axis is 0 or 1 and refers to the last two array axes."""
+    return np.roll(a, -1, axis=axis - 2)
+
+
+def _bwd(a, axis):
+    """a[x - e_axis] (periodic)."""
+    return np.roll(a, +1, axis=axis - 2)
+
+
+def d0(phi):
+    """d of a 0-form (..., 1, N, N) -> 1-form (..., 2, N, N).  compact.py:973-1001."""
+    f = phi[..., 0, :, :]
+    out = np.zeros(phi.shape[:-3] + (2,) + phi.shape[-2:], dtype=phi.dtype)
+    out[..., 0, :, :] += (_fwd(f, 0) - f)
+    out[..., 1, :, :] += (_fwd(f, 1) - f)
+    return out
+
+
+def d1(n):
+    """d of a 1-form (..., 2, N, N) -> 2-form (..., 1, N, N).  Rows (0,1,0,+), (0,0,1,-)."""
+    n0 = n[..., 0, :, :]
+    n1 = n[..., 1, :, :]
+    out = np.zeros(n.shape[:-3] + (1,) + n.shape[-2:], dtype=n.dtype)
+    out[..., 0, :, :] += (_fwd(n1, 0) - n1)
+    out[..., 0, :, :] += -(_fwd(n0, 1) - n0)
+    return out
+
+
+def delta1(m):
+    """delta of a 1-form -> 0-form.  compact.py:1008-1037; rows (0,0,0,+), (0,1,1,+)."""
+    m0 = m[..., 0, :, :]
+    m1 = m[..., 1, :, :]
+    out = np.zeros(m.shape[:-3] + (1,) + m.shape[-2:], dtype=m.dtype)
+    out[..., 0, :, :] -= (m0 - _bwd(m0, 0))
+    out[..., 0, :, :] -= (m1 - _bwd(m1, 1))
+    return out
+
+
+def delta2(v):
+    """delta of a 2-form -> 1-form.  Rows (0,0,1,-), (1,0,0,+)."""
+    f = v[..., 0, :, :]
+    out = np.zeros(v.shape[:-3] + (2,) + v.shape[-2:], dtype=v.dtype)
+    out[..., 0, :, :] -= -(f - _bwd(f, 1))
+    out[..., 1, :, :] -= (f - _bwd(f, 0))
+    return out
+
+
+def face_sum1(F):
+    """face_sum of a 1-form -> 0-form.  compact.py:848-867; _kernels.py:37-45 (two adds per row)."""
+    F0 = F[..., 0, :, :]
+    F1 = F[..., 1, :, :]
+    out = np.zeros(F.shape[:-3] + (1,) + F.shape[-2:], dtype=F.dtype)
+    g = out[..., 0, :, :]
+    g += F0
+    g += _bwd(F0, 0)
+    g += F1
+    g += _bwd(F1, 1)
+    return out
+
+
+def face_sum2(F):
+    """face_sum of a 2-form -> 1-form.  Rows (0,0,1,+), (1,0,0,+)."""
+    f = F[..., 0, :, :]
+    out = np.zeros(F.shape[:-3] + (2,) + F.shape[-2:], dtype=F.dtype)
+    out[..., 0, :, :] += f
+    out[..., 0, :, :] += _bwd(f, 1)
+    out[..., 1, :, :] += f
+    out[..., 1, :, :] += _bwd(f, 0)
+    return out
+
+
+def coface_sum0(F):
+    """coface_sum of a 0-form -> 1-form.  compact.py:869-890; rows (0,0,0,+), (1,0,1,+)."""
+    f = F[..., 0, :, :]
+    out = np.zeros(F.shape[:-3] + (2,) + F.shape[-2:], dtype=F.dtype)
+    out[..., 0, :, :] += f
+    out[..., 0, :, :] += _fwd(f, 0)
+    out[..., 1, :, :] += f
+    out[..., 1, :, :] += _fwd(f, 1)
+    return out
+
+
+def coface_sum1(F):
+    """coface_sum of a 1-form -> 2-form.  Rows (0,1,0,+), (0,0,1,+)."""
+    F0 = F[..., 0, :, :]
+    F1 = F[..., 1, :, :]
+    out = np.zeros(F.shape[:-3] + (1,) + F.shape[-2:], dtype=F.dtype)
+    g = out[..., 0, :, :]
+    g += F1
+    g += _fwd(F1, 0)
+    g += F0
+    g += _fwd(F0, 1)
+    return out
+
+
+_OPS = {
+    ('d', 0): d0, ('d', 1): d1,
+    ('delta', 1): delta1, ('delta', 2): delta2,
+    ('face_sum', 1): face_sum1, ('face_sum', 2): face_sum2,
+    ('coface_sum', 0): coface_sum0, ('coface_sum', 1): coface_sum1,
+}
+
+
+def form_op(op, degree, F):
+    """Dispatch by (operator name, input degree); raises KeyError at the ends of the complex,
+    where the reference returns the scalar 0 (compact.py:999-1000, 1035-1036, 865-866, 888-889)."""
+    return _OPS[(op, degree)](np.asarray(F))
+
+
+def correlation(f, g):
+    """Translation-averaged cross-correlation, compact.py:465-536:
+    fft2(conj(fft2 f) * fft2 g, ortho) / sqrt(N^2), over the last two axes."""
+    N2 = f.shape[-1] * f.shape[-2]
+    Ff = np.fft.fftn(f, axes=(-2, -1), norm='ortho')
+    Fg = np.fft.fftn(g, axes=(-2, -1), norm='ortho')
+    return np.fft.fftn(Ff.conj() * Fg, axes=(-2, -1), norm='ortho') / np.sqrt(N2)

@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+The reference is imported through oracle/refimport.py (which stubs h5py/matplotlib when those
+are absent).  Every fixture stores the inputs, the random draws in dense per-site form, and the
+reference's outputs, so the tests that consume it need neither the reference nor numpy's PCG64
+stream to be reproducible.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refimport            # noqa: E402
+from oracle import villain_np           # noqa: E402
+
+sv = refimport.import_reference()
+Form = sv.lattice.Form
+
+
+def villain_neighborhood():
+    """NeighborhoodUpdate.step chains with rng = default_rng(99) (the reference's own seed in
+    test/test_vortex_sparse.py:31) from hot starts built like test/test_delta_s.py:20-27."""
+    cases = []
+    for (N, kappa, W, sweeps, cfg_seed) in [
+        (4, 0.5, 1, 12, 0), (4, 0.1, 2, 12, 1),
+        (5, 0.5, 1, 12, 2), (5, 0.1, 1, 12, 3), (5, 0.5, 3, 8, 4),
+        (8, 0.5, 1, 12, 5), (8, 0.1, 2, 12, 6), (7, 0.3, 1, 8, 7),
+        (6, 1.0, 1, 8, 8), (16, 0.2, 1, 6, 9),
+        (32, 0.5, 1, 4, 10), (32, 0.05, 1, 4, 11),
+    ]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Villain(L, kappa, W=W)
+        G = sv.generator.villain.NeighborhoodUpdate(S)
+        G.rng = np.random.default_rng(99)
+        replay = np.random.default_rng(99)
+        phi0, n0 = villain_np.hot_start(np.random.default_rng(cfg_seed), N)
+        n0 = n0 * W   # keeps dn = 0 mod W irrelevant here, but makes W>1 starts "valid-like"
+        cfg = {'phi': Form(phi0, degree=0, lattice=L), 'n': Form(n0, degree=1, lattice=L)}
+        rec = dict(N=N, kappa=kappa, W=W, sweeps=sweeps, phi0=phi0, n0=n0)
+        us, dphis, dnf, dnb, phis, ns, acc, accp, act = [], [], [], [], [], [], [], [], []
+        for s in range(sweeps):
+            draws = villain_np.draw_neighborhood(replay, N, W=W)
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            us.append(draws['u']); dphis.append(draws['dphi'])
+            dnf.append(draws['dn_fwd']); dnb.append(draws['dn_bwd'])
+            phis.append(np.asarray(cfg['phi']).copy()); ns.append(np.asarray(cfg['n']).copy())
+            acc.append(int(G.accepted - before[0]))
+            accp.append(float(G.acceptance - before[1]))      # mean acceptance probability of the sweep
+            act.append(float(S(cfg['phi'], cfg['n'])))
+        rec.update(u=np.array(us), dphi=np.array(dphis), dn_fwd=np.array(dnf), dn_bwd=np.array(dnb),
+                   phi=np.array(phis), n=np.array(ns), accepted=np.array(acc),
+                   acceptance=np.array(accp), action=np.array(act))
+        cases.append(rec)
+    out = {}
+    for i, rec in enumerate(cases):
+        for k, v in rec.items():
+            out[f'case{i}_{k}'] = np.asarray(v)
+    out['n_cases'] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(HERE, 'villain_neighborhood.npz'), **out)
+    print('villain_neighborhood.npz:', len(cases), 'cases; accepted per case:',
+          [int(r['accepted'].sum()) for r in cases])
+
+
+def villain_observables():
+    """Action and the named Villain observables on seeded hot configurations."""
+    out = {}
+    cases = [(4, 0.7, 0), (5, 0.5, 1), (8, 0.3, 2), (32, 0.5, 3)]
+    for i, (N, kappa, seed) in enumerate(cases):
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Villain(L, kappa)
+        phi, n = villain_np.hot_start(np.random.default_rng(seed), N)
+        fphi, fn = Form(phi, degree=0, lattice=L), Form(n, degree=1, lattice=L)
+        O = sv.observable
+        out[f'case{i}_N'] = np.asarray(N); out[f'case{i}_kappa'] = np.asarray(kappa)
+        out[f'case{i}_phi'] = phi; out[f'case{i}_n'] = n
+        out[f'case{i}_action'] = np.asarray(float(S(fphi, fn)))
+        out[f'case{i}_links'] = np.asarray(O.Links.Villain(S, fphi, fn))
+        out[f'case{i}_ActionDensity'] = np.asarray(float(O.ActionDensity.Villain(S, fphi, fn)))
+        out[f'case{i}_InternalEnergyDensity'] = np.asarray(float(O.InternalEnergyDensity.Villain(S, fphi, fn)))
+        out[f'case{i}_InternalEnergyDensitySquared'] = np.asarray(float(O.InternalEnergyDensitySquared.Villain(S, fphi, fn)))
+        out[f'case{i}_WindingSquared'] = np.asarray(float(O.WindingSquared.Villain(S, fn)))
+        tw = np.asarray(O.TorusWrapping.Villain(S, fphi, fn))
+        out[f'case{i}_TorusWrapping'] = tw
+        out[f'case{i}_WrappingSquared'] = np.asarray(float(O.WrappingSquared.default(S, tw)))
+        out[f'case{i}_Spin_Spin'] = np.asarray(O.Spin_Spin.Villain(S, fphi))
+        out[f'case{i}_Winding_Winding'] = np.asarray(O.Winding_Winding.Villain(S, fn))
+        out[f'case{i}_dn'] = np.asarray(sv.lattice.d(fn))
+    out['n_cases'] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(HERE, 'villain_observables.npz'), **out)
+    print('villain_observables.npz:', len(cases), 'cases')
+
+
+def lattice_forms():
+    """d, delta, face_sum, coface_sum of random float and int forms, plus the colour maps."""
+    out = {}
+    i = 0
+    for N in (3, 4, 5, 8):
+        L = sv.lattice.Lattice2D(N)
+        rng = np.random.default_rng(100 + N)
+        for p in (0, 1, 2):
+            for kind in ('f', 'i'):
+                C = (1, 2, 1)[p]
+                if kind == 'f':
+                    data = rng.uniform(-3, 3, (C, N, N))
+                else:
+                    data = rng.integers(-5, 6, (C, N, N))
+                F = Form(data, degree=p, lattice=L)
+                out[f'case{i}_N'] = np.asarray(N); out[f'case{i}_p'] = np.asarray(p)
+                out[f'case{i}_in'] = data
+                for name, fn in (('d', sv.lattice.d), ('delta', sv.lattice.delta),
+                                 ('face_sum', lambda f: f.face_sum()), ('coface_sum', lambda f: f.coface_sum())):
+                    res = fn(F)
+                    if isinstance(res, np.ndarray):
+                        out[f'case{i}_{name}'] = np.asarray(res)
+                i += 1
+        cmap = np.zeros((N, N), dtype=np.int64)
+        for c, color in enumerate(L.checkerboarding):
+            cmap[color] = c
+        out[f'colour_N{N}'] = cmap
+        out[f'colour_order_N{N}'] = np.concatenate([np.stack(color, 0) for color in L.checkerboarding], axis=1)
+    for N in (6, 7, 9, 32):
+        L = sv.lattice.Lattice2D(N)
+        cmap = np.zeros((N, N), dtype=np.int64)
+        for c, color in enumerate(L.checkerboarding):
+            cmap[color] = c
+        out[f'colour_N{N}'] = cmap
+        out[f'colour_order_N{N}'] = np.concatenate([np.stack(color, 0) for color in L.checkerboarding], axis=1)
+    out['n_cases'] = np.asarray(i)
+    np.savez_compressed(os.path.join(HERE, 'lattice_forms.npz'), **out)
+    print('lattice_forms.npz:', i, 'cases')
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms']
+    for name in which:
+        globals()[name]()

@@ -1,0 +1,107 @@
+"""The numpy oracle (oracle/villain_np.py, oracle/lattice_np.py) against golden vectors produced
+by the reference itself (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import lattice_np as lat
+from oracle import villain_np as V
+
+
+def test_colour_maps_match_reference(golden_lattice_forms):
+    _, extras = golden_lattice_forms
+    for N in (3, 4, 5, 6, 7, 8, 9, 32):
+        assert (lat.colour_map(N) == extras[f'colour_N{N}']).all()
+        order = np.concatenate([np.stack(c, 0) for c in lat.colour_sites(N)], axis=1)
+        assert (order == extras[f'colour_order_N{N}']).all()
+
+
+def test_colour_map_N5_ground_truth():
+    # SURVEY.md App. A.2 table
+    expect = np.array([[0, 1, 0, 2, 3], [1, 0, 1, 3, 2], [0, 1, 0, 2, 3], [2, 3, 2, 0, 1], [3, 2, 3, 1, 0]])
+    assert (lat.colour_map(5) == expect).all()
+
+
+def test_form_operators_bitexact(golden_lattice_forms):
+    cases, _ = golden_lattice_forms
+    checked = 0
+    for c in cases:
+        p = int(c['p'])
+        for op in ('d', 'delta', 'face_sum', 'coface_sum'):
+            if op in c:
+                got = lat.form_op(op, p, c['in'])
+                assert got.dtype == c[op].dtype          # dtype preserving, test/test_field_dtypes.py
+                assert (got == c[op]).all(), (op, p, int(c['N']))
+                checked += 1
+    assert checked == 4 * 2 * 8   # 4 sizes x {float,int} x (2 ops on 0-forms + 4 on 1-forms + 2 on 2-forms)
+
+
+def test_vectorised_step_reproduces_reference_chain(golden_villain_neighborhood):
+    for c in golden_villain_neighborhood:
+        rng = np.random.default_rng(99)
+        phi, n = c['phi0'], c['n0']
+        for s in range(int(c['sweeps'])):
+            stats = {}
+            phi, n = V.neighborhood_step(phi, n, float(c['kappa']), int(c['W']), rng, stats=stats)
+            assert (n == c['n'][s]).all()
+            assert (phi == c['phi'][s]).all()            # bitwise
+            assert stats['accepted'] == int(c['accepted'][s])
+            N = int(c['N'])
+            assert stats['acceptance'] / N**2 == pytest.approx(float(c['acceptance'][s]), rel=1e-13)
+
+
+def test_draw_replay_matches_golden_draws(golden_villain_neighborhood):
+    for c in golden_villain_neighborhood:
+        rng = np.random.default_rng(99)
+        for s in range(int(c['sweeps'])):
+            d = V.draw_neighborhood(rng, int(c['N']), W=int(c['W']))
+            assert (d['u'] == c['u'][s]).all() and (d['dphi'] == c['dphi'][s]).all()
+            assert (d['dn_fwd'] == c['dn_fwd'][s]).all() and (d['dn_bwd'] == c['dn_bwd'][s]).all()
+
+
+def test_dense_scalar_step_reproduces_reference_chain(golden_villain_neighborhood):
+    for c in golden_villain_neighborhood:
+        if int(c['N']) > 16:
+            continue
+        phi, n = c['phi0'], c['n0']
+        for s in range(int(c['sweeps'])):
+            draws = {k: c[k][s] for k in ('u', 'dphi', 'dn_fwd', 'dn_bwd')}
+            stats = {}
+            phi, n = V.neighborhood_step_dense(phi, n, float(c['kappa']), draws, stats=stats)
+            assert (n == c['n'][s]).all()
+            assert (phi == c['phi'][s]).all()
+            assert stats['accepted'] == int(c['accepted'][s])
+            assert V.action(phi, n, float(c['kappa'])) == pytest.approx(float(c['action'][s]), rel=1e-13)
+
+
+def test_observables_match_reference(golden_villain_observables):
+    for c in golden_villain_observables:
+        phi, n, kappa = c['phi'], c['n'], float(c['kappa'])
+        assert (V.links(phi, n) == c['links']).all()
+        assert V.action(phi, n, kappa) == pytest.approx(float(c['action']), rel=1e-14)
+        assert V.action_density(phi, n, kappa) == pytest.approx(float(c['ActionDensity']), rel=1e-14)
+        assert V.internal_energy_density(phi, n, kappa) == pytest.approx(float(c['InternalEnergyDensity']), rel=1e-14)
+        assert V.internal_energy_density(phi, n, kappa) ** 2 == pytest.approx(float(c['InternalEnergyDensitySquared']), rel=1e-13)
+        assert V.winding_squared(n) == pytest.approx(float(c['WindingSquared']), rel=1e-14)
+        assert (V.torus_wrapping(n) == c['TorusWrapping']).all()
+        assert V.wrapping_squared(n) == float(c['WrappingSquared'])
+        assert (lat.d1(n) == c['dn']).all()
+        np.testing.assert_allclose(V.spin_spin(phi), c['Spin_Spin'], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(V.winding_winding(n), c['Winding_Winding'], rtol=0, atol=1e-12)
+
+
+def test_delta_S_formula_equals_action_difference():
+    """Mirror of the reference's test/test_delta_s.py:115-144 on the oracle: the per-site fast
+    dS equals S(new) - S(old) to 1e-10."""
+    N, kappa = 4, 0.7
+    phi, n = V.hot_start(np.random.default_rng(0), N)
+    rng = np.random.default_rng(99)
+    draws = V.draw_neighborhood(rng, N)
+    dS = np.zeros((N, N))
+    V.neighborhood_step_dense(phi, n, kappa, draws | {'u': np.ones((N, N))}, dS_out=dS)  # u=1: nothing accepted
+    for x0 in range(N):
+        for x1 in range(N):
+            p2, n2 = phi.copy(), n.copy()
+            p2[0, x0, x1] += draws['dphi'][x0, x1]
+            n2[0, x0, x1] += draws['dn_fwd'][0, x0, x1]; n2[0, (x0 - 1) % N, x1] += draws['dn_bwd'][0, x0, x1]
+            n2[1, x0, x1] += draws['dn_fwd'][1, x0, x1]; n2[1, x0, (x1 - 1) % N] += draws['dn_bwd'][1, x0, x1]
+            assert abs(dS[x0, x1] - (V.action(p2, n2, kappa) - V.action(phi, n, kappa))) < 1e-10
