@@ -1,0 +1,193 @@
+/*
+ * svb200.h -- C ABI of libsvb200.so: B200-native (sm_100a) kernels for the batched Villain /
+ * worldline Metropolis hot path of evanberkowitz/supervillain.
+ *
+ * The reference has no FFI of its own for this path: the seam is the duck-typed Python protocol
+ * `generator.step(cfg)` / `generator.inline_observables(steps)` / `generator.report()` driven by
+ * supervillain/ensemble.py:74-98, plus the operator functions `d`, `delta`, `Form.face_sum`,
+ * `Form.coface_sum` of supervillain/lattice/compact.py.  The entry points below are what a
+ * ctypes/cffi binding on the reference side would call to replace the bodies of those Python
+ * functions; each one names the reference function it stands in for.  INTEGRATION.md shows the
+ * binding.
+ *
+ * Conventions
+ *  - every function returns int: 0 = ok, <0 = SVB_E_* (bad argument), >0 = a cudaError_t;
+ *    nothing throws; svb_last_error() returns a thread-local message for the last failure.
+ *  - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *    buffer; the library allocates nothing and keeps no global state besides kernel attributes.
+ *  - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL is the
+ *    legacy default stream); no implicit synchronisation.
+ *  - field layout is the reference's compact layout with a leading chain axis, C-contiguous:
+ *        phi (chains, 1, N, N)   n, m (chains, 2, N, N)   v (chains, 1, N, N)
+ *    (supervillain/lattice/compact.py:665-716, supervillain/action/villain.py:76-91,
+ *    supervillain/action/worldline.py:96-114).  Axis -2 is lattice direction 0.
+ *  - D = 2 only (every configuration named by BASELINE.json).
+ */
+#ifndef SVB200_H
+#define SVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_VERSION_MAJOR 0
+#define SVB_VERSION_MINOR 1
+
+/* error codes (negative); positive return values are cudaError_t */
+#define SVB_OK              0
+#define SVB_E_NULL         -1   /* a required pointer is NULL */
+#define SVB_E_SHAPE        -2   /* chains/N out of range */
+#define SVB_E_DTYPE        -3   /* unsupported dtype code */
+#define SVB_E_PARAM        -4   /* bad scalar parameter (kappa<=0, W<1, interval...) */
+#define SVB_E_UNSUPPORTED  -5   /* valid request this build cannot serve (e.g. odd N in a tiled path) */
+#define SVB_E_ALIGN        -6   /* pointer alignment */
+
+/* dtype codes */
+#define SVB_F64 0
+#define SVB_F32 1
+#define SVB_I32 2
+#define SVB_I64 3
+
+/* rng modes */
+#define SVB_RNG_PHILOX   0   /* in-kernel Philox4x32-10, counter = (site, chain, sweep) keyed by seed */
+#define SVB_RNG_INJECTED 1   /* proposals and uniforms read from caller-supplied dense arrays */
+
+/* arithmetic modes */
+#define SVB_ARITH_STRICT 0   /* the reference's operation order, no FMA contraction (bit-faithful dS) */
+#define SVB_ARITH_FAST   1   /* FMA-contracted dS (agrees with STRICT to ~1e-15 relative) */
+
+/* code paths for the sweeps (SVB_PATH_AUTO picks by N) */
+#define SVB_PATH_AUTO    0
+#define SVB_PATH_SMEM    1   /* whole lattice of a chain resident in shared memory, all colours and
+                                n_sweeps sweeps per launch: one HBM read + one write per launch */
+#define SVB_PATH_GLOBAL  2   /* one launch per colour pass straight out of HBM/L2 (any N) */
+
+/* per-chain observable record written by the sweep / observable entry points */
+#define SVB_VOBS_ACTION        0   /* S = kappa/2 sum (dphi - 2 pi n)^2       (action/villain.py:51-66) */
+#define SVB_VOBS_SUM_DN2       1   /* sum_p (dn)_p^2   -> WindingSquared = /N^2 (observable/winding.py:30-37) */
+#define SVB_VOBS_WRAP0         2   /* sum_x n_0[x]      TorusWrapping[0]        (observable/wrapping.py:17-25) */
+#define SVB_VOBS_WRAP1         3   /* sum_x n_1[x]      TorusWrapping[1] */
+#define SVB_VOBS_ACCEPTED      4   /* accepted proposals over the sweeps of this call (neighborhood.py:117,133) */
+#define SVB_VOBS_ACCEPTANCE    5   /* sum over proposals of min(1, e^-dS)         (neighborhood.py:118,132) */
+#define SVB_VOBS_COUNT         6
+
+#define SVB_WOBS_SUM_F2        0   /* sum_l (m - delta v / W)_l^2  (action/worldline.py:94; observable/action.py:35-47) */
+#define SVB_WOBS_SUM_DF2       1   /* sum_p (d(m - delta v/W))_p^2 (observable/winding.py:40-52) */
+#define SVB_WOBS_WRAP0         2   /* sum_x m_0[x]   (TorusWrapping = /N, observable/wrapping.py:28-39) */
+#define SVB_WOBS_WRAP1         3
+#define SVB_WOBS_ACCEPTED      4
+#define SVB_WOBS_ACCEPTANCE    5
+#define SVB_WOBS_DELTA_M_ABS   6   /* sum_x |(delta m)[x]|: 0 iff the constraint holds (action/worldline.py:54-70) */
+#define SVB_WOBS_COUNT         7
+
+/* worldline sweep modes */
+#define SVB_WL_JOINT    0   /* (dm, dv) jointly per plaquette: PlaquetteUpdate's move (worldline/plaquette.py:79-101) */
+#define SVB_WL_VORTEX   1   /* v only:  VortexUpdate  (worldline/vortex.py:51-136) */
+#define SVB_WL_COEXACT  2   /* m only (m += delta t): CoexactUpdate (worldline/coexact.py:53-128) */
+
+/* form operators */
+#define SVB_OP_D          0   /* supervillain.lattice.d            compact.py:973-1001  */
+#define SVB_OP_DELTA      1   /* supervillain.lattice.delta        compact.py:1008-1037 */
+#define SVB_OP_FACE_SUM   2   /* Form.face_sum                     compact.py:848-867   */
+#define SVB_OP_COFACE_SUM 3   /* Form.coface_sum                   compact.py:869-890   */
+
+int         svb_version(void);
+const char* svb_last_error(void);
+
+/*
+ * Replaces the body of NeighborhoodUpdate.step (supervillain/generator/villain/neighborhood.py:59-137)
+ * for `chains` independent chains at once, `n_sweeps` sweeps per call, IN PLACE.
+ *
+ *  phi            (chains,1,N,N) SVB_F64 or SVB_F32
+ *  n              (chains,2,N,N) SVB_I32
+ *  kappa          coupling used when kappa_chain == NULL
+ *  kappa_chain    optional (chains,) f64: one coupling per chain (kappa scans)
+ *  W              constraint integer (finite, >= 1): dn proposals are W * [-interval_n, interval_n]
+ *  seed, sweep0, chain0   Philox key / counter offsets: chain c of this call, sweep s of this call
+ *                 draws from counter (site, chain0 + c, sweep0 + s); results do not depend on
+ *                 how chains are split over calls or GPUs
+ *  rng_mode       SVB_RNG_PHILOX, or SVB_RNG_INJECTED with
+ *                   inj_u, inj_dphi  (n_sweeps, chains, N, N) f64
+ *                   inj_dn_fwd/bwd   (n_sweeps, chains, 2, N, N) i32, indexed by the PROPOSING site
+ *                                    and already multiplied by W  
+ *  obs            optional (chains, SVB_VOBS_COUNT) f64, state after the last sweep + counters
+ *  accept_mask    optional (chains, N, N) u8: accept decisions of the LAST sweep (parity tests)
+ *  dS_out         optional (chains, N, N) f64: dS of the LAST sweep's proposals (parity tests)
+ */
+int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n,
+                      int64_t chains, int N,
+                      double kappa, const double* kappa_chain, int W,
+                      double interval_phi, int interval_n,
+                      int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                      int rng_mode, int arith_mode, int path,
+                      const double* inj_u, const double* inj_dphi,
+                      const int32_t* inj_dn_fwd, const int32_t* inj_dn_bwd,
+                      double* obs, uint8_t* accept_mask, double* dS_out,
+                      void* stream);
+
+/*
+ * Villain.__call__ (action/villain.py:51-66) and the scalar observables of
+ * observable/{action,energy,winding,wrapping}.py for every chain: fills obs[:, ACTION..WRAP1]
+ * and zeroes the two counters.
+ */
+int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n,
+                            int64_t chains, int N, double kappa, const double* kappa_chain,
+                            double* obs, void* stream);
+
+/*
+ * The worldline checkerboard sweep: the PlaquetteUpdate move (worldline/plaquette.py:79-101) in
+ * the red/black order of VortexUpdate/CoexactUpdate (worldline/vortex.py:86-128,
+ * worldline/coexact.py:91-120), IN PLACE on m (chains,2,N,N) i32 and v (chains,1,N,N) i32.
+ *  mode           SVB_WL_JOINT / SVB_WL_VORTEX / SVB_WL_COEXACT
+ *  interval       proposals are drawn from [-interval, interval] \ {0} for dv (VORTEX) and t
+ *                 (COEXACT); JOINT is the reference's dm in {-1,+1}, dv in {-1,0,+1}
+ *  injected       inj_u (n_sweeps, chains, N, N) f64; inj_a (n_sweeps, chains, N, N) i32 = dm (JOINT),
+ *                 dv (VORTEX) or t (COEXACT); inj_b same shape = dv (JOINT only)
+ */
+int svb_worldline_sweep(int32_t* m, int32_t* v,
+                        int64_t chains, int N,
+                        double kappa, const double* kappa_chain, int W,
+                        int mode, int interval,
+                        int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                        int rng_mode, int path,
+                        const double* inj_u, const int32_t* inj_a, const int32_t* inj_b,
+                        double* obs, uint8_t* accept_mask, double* dS_out,
+                        void* stream);
+
+/* Worldline.__call__ ingredients and observables (action/worldline.py:72-94): obs (chains, SVB_WOBS_COUNT) */
+int svb_worldline_observables(const int32_t* m, const int32_t* v,
+                              int64_t chains, int N, int W,
+                              double* obs, void* stream);
+
+/*
+ * d / delta / face_sum / coface_sum on `chains` forms of input degree `degree`, dtype-preserving
+ * (compact.py:954-966 -> lattice/_kernels.py:19-46).  in (chains, C(2,degree), N, N) ->
+ * out (chains, C(2,degree +/- 1), N, N).  Returns SVB_E_PARAM at the ends of the complex, where
+ * the reference returns the scalar 0.
+ */
+int svb_form_op(int op, int degree, int dtype, const void* in, void* out,
+                int64_t chains, int N, void* stream);
+
+/*
+ * Spin_Spin.Villain (observable/spin.py:28-42): C[dx] = N^-2 sum_x e^{-i phi_x} e^{+i phi_{x-dx}},
+ * out (chains, N, N, 2) f64 (re, im).  Direct O(N^4) evaluation, intended for N <= 64.
+ */
+int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N,
+                          double* out, void* stream);
+
+/* Philox4x32-10 block, exposed for known-answer tests: out[4] = philox(ctr[4], key[2]) (host). */
+void svb_philox4x32_10_host(const uint32_t* ctr_host, const uint32_t* key_host, uint32_t* out_host);
+
+/* The draw mapping used in SVB_RNG_PHILOX mode, evaluated on the device for
+ * (chain0 + c, sweep, site) so tests can compare against the oracle's restatement:
+ * u, dphi (chains, N, N) f64;  dn (chains, 4, N, N) i32 ordered (fwd0, bwd0, fwd1, bwd1). */
+int svb_villain_draws(int64_t chains, int N, int W, double interval_phi, int interval_n,
+                      uint64_t seed, uint64_t sweep, uint64_t chain0,
+                      double* u, double* dphi, int32_t* dn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB200_H */

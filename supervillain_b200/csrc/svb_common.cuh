@@ -1,0 +1,180 @@
+// svb_common.cuh -- shared device/host helpers for libsvb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "svb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsvb200 is written for sm_100a (B200) only"
+#endif
+
+namespace svb {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SVB_CUDA_TRY(expr)                                             \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return ::svb::cuda_fail(_e, #expr);     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------
+// numpy's 2*np.pi as a double: 2 * 0x400921FB54442D18 (exact doubling)
+#define SVB_TWO_PI 6.283185307179586476925286766559
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Counter-based: the draw for
+// (site, chain, sweep) never depends on launch geometry, tiling, or the number of GPUs.
+// ------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+template <int ROUNDS = 10>
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// Stream ids folded into the top byte of counter word 3, so the generators never share draws.
+enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u };
+
+__host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t chain, uint64_t sweep,
+                                                         uint32_t site, uint32_t stream_id) {
+    // counter = (site, chain[31:0], sweep[31:0], stream<<24 | chain[39:32]<<16 | sweep[47:32])
+    uint32_t c3 = (stream_id << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) | (uint32_t)((sweep >> 32) & 0xFFFFu);
+    return philox4x32<10>(site, (uint32_t)chain, (uint32_t)sweep, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// ------------------------------------------------------------------------------------------
+// checkerboard colouring (supervillain/lattice/compact.py:192-239, D = 2)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int n_colours(int N) { return (N & 1) ? 4 : 2; }
+
+__host__ __device__ __forceinline__ int site_colour(int x0, int x1, int N) {
+    if ((N & 1) == 0) return (x0 + x1) & 1;
+    // FFT coordinates: index i -> i for i <= N/2, else i - N   (lattice/__init__.py:4-9)
+    int h = N >> 1;
+    int c0 = (x0 <= h) ? x0 : x0 - N;
+    int c1 = (x1 <= h) ? x1 : x1 - N;
+    int parity = (c0 + c1) & 1;                       // two's complement: correct for negatives
+    int mixed = ((c0 >= 0) != (c1 >= 0)) ? 1 : 0;     // compact.py:36-53 with D = 2
+    return 2 * mixed + parity;
+}
+
+// ------------------------------------------------------------------------------------------
+// warp / block reductions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum K doubles per thread across the block; result valid in thread 0.  scratch: K * 32 doubles.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    if (nwarps == 1) return;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double t = (lane < nwarps) ? scratch[k * 32 + lane] : 0.0;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier.  Sizes and addresses must be
+// multiples of 16 bytes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, completion tracked by the bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+}  // namespace svb

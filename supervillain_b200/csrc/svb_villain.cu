@@ -1,0 +1,635 @@
+// svb_villain.cu -- batched checkerboard Metropolis sweeps of the Villain action
+//   S = kappa/2 sum_l (d phi - 2 pi n)_l^2
+// replacing NeighborhoodUpdate.step (supervillain/generator/villain/neighborhood.py:59-137),
+// Villain.__call__ (supervillain/action/villain.py:51-66) and the scalar Villain observables
+// (supervillain/observable/{action,energy,winding,wrapping}.py).
+//
+// Per site x, with the four links touching x
+//   f0 = (0,x)  b0 = (0,x-e0)  f1 = (1,x)  b1 = (1,x-e1)
+//   r_l   = (phi[head] - phi[tail]) - 2 pi n_l
+//   dr_f  = (0 - dphi) - 2 pi dn_f          dr_b = (dphi - 0) - 2 pi dn_b
+//   dS    = 0 + s_f0 + s_b0 + s_f1 + s_b1,  s_l = ((kappa/2) dr_l) ((2 r_l) + dr_l)
+//   accept iff u < min(1, exp(-dS)); then phi[x] += dphi, n_l += dn_l.
+// Same-colour sites touch disjoint links and never neighbour each other, so one colour is
+// updated concurrently without atomics; colours are separated by a barrier.
+
+#include "svb_common.cuh"
+
+namespace svb {
+
+struct VillainArgs {
+    void* phi;
+    int32_t* n;
+    long long chains;
+    int N;
+    double kappa;
+    const double* kappa_chain;
+    int W;
+    double interval_phi;
+    int interval_n;
+    int n_sweeps;
+    unsigned long long seed, sweep0, chain0;
+    const double* inj_u;
+    const double* inj_dphi;
+    const int32_t* inj_dn_fwd;
+    const int32_t* inj_dn_bwd;
+    double* obs;
+    uint8_t* accept_mask;
+    double* dS_out;
+};
+
+// ------------------------------------------------------------------------------------------
+// arithmetic policies
+// ------------------------------------------------------------------------------------------
+template <typename T, bool STRICT>
+struct Arith;
+
+template <>
+struct Arith<double, true> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    // r = dphi - (2 pi) n          (neighborhood.py:91)
+    static __device__ __forceinline__ double resid(double dphi, double nn) { return __dsub_rn(dphi, __dmul_rn(SVB_TWO_PI, nn)); }
+    // s = ((kappa/2) dr) ((2 r) + dr)   (neighborhood.py:111)
+    static __device__ __forceinline__ double link(double hk, double dr, double r) {
+        return __dmul_rn(__dmul_rn(hk, dr), __dadd_rn(__dmul_rn(2.0, r), dr));
+    }
+    static __device__ __forceinline__ double expneg(double x) { return exp(-x); }
+};
+template <>
+struct Arith<double, false> {
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double resid(double dphi, double nn) { return fma(-SVB_TWO_PI, nn, dphi); }
+    static __device__ __forceinline__ double link(double hk, double dr, double r) { return (hk * dr) * fma(2.0, r, dr); }
+    static __device__ __forceinline__ double expneg(double x) { return exp(-x); }
+};
+template <>
+struct Arith<float, true> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float resid(float dphi, float nn) { return __fsub_rn(dphi, __fmul_rn((float)SVB_TWO_PI, nn)); }
+    static __device__ __forceinline__ float link(float hk, float dr, float r) {
+        return __fmul_rn(__fmul_rn(hk, dr), __fadd_rn(__fmul_rn(2.0f, r), dr));
+    }
+    static __device__ __forceinline__ float expneg(float x) { return expf(-x); }
+};
+template <>
+struct Arith<float, false> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float resid(float dphi, float nn) { return fmaf(-(float)SVB_TWO_PI, nn, dphi); }
+    static __device__ __forceinline__ float link(float hk, float dr, float r) { return (hk * dr) * fmaf(2.0f, r, dr); }
+    static __device__ __forceinline__ float expneg(float x) { return expf(-x); }
+};
+
+// ------------------------------------------------------------------------------------------
+// proposals
+// ------------------------------------------------------------------------------------------
+struct VillainDraw {
+    double u;      // Metropolis uniform in (0, 1)
+    double dphi;   // proposal for phi[x]
+    int dn[4];     // proposals for links f0, b0, f1, b1 (already multiplied by W)
+};
+
+// The Philox draw mapping.  128 bits per site per sweep, split 44 / 44 / 40:
+//   dphi = -I + (2 I) * ((k44 + 1/2) 2^-44)     [numpy: lo + (hi - lo) * U, no FMA]
+//   u    = (k44' + 1/2) 2^-44                   in (0,1): u = 0 can never force an accept
+//   dn   = four base-K digits (K = 2 interval_n + 1) of the 40-bit fraction k40 / 2^40
+__host__ __device__ __forceinline__ VillainDraw villain_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
+                                                                     uint32_t site, double interval_phi, int interval_n,
+                                                                     int W) {
+    Philox4 p = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD);
+    VillainDraw d;
+    const double two_m44 = 5.6843418860808015e-14;  // 2^-44
+    uint64_t kphi = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
+    uint64_t ku = ((uint64_t)(p.y & 0xFFFFFu) << 24) | (uint64_t)(p.z >> 8);
+    uint64_t kn = ((uint64_t)(p.z & 0xFFu) << 32) | (uint64_t)p.w;
+    double Uphi = ((double)(long long)kphi + 0.5) * two_m44;   // exact: 45 significant bits
+    d.u = ((double)(long long)ku + 0.5) * two_m44;
+#ifdef __CUDA_ARCH__
+    d.dphi = __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, Uphi));
+#else
+    {
+        volatile double prod = (2.0 * interval_phi) * Uphi;    // volatile: forbid FMA contraction on the host
+        d.dphi = -interval_phi + prod;
+    }
+#endif
+    const uint64_t K = (uint64_t)(2 * interval_n + 1);
+    const uint64_t mask40 = (1ull << 40) - 1ull;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        kn *= K;
+        int digit = (int)(kn >> 40);
+        kn &= mask40;
+        d.dn[i] = W * (digit - interval_n);
+    }
+    return d;
+}
+
+struct SiteOut {
+    double A;
+    bool ok;
+    double dS;
+};
+
+// One Metropolis proposal at site (x0, x1) of one chain, in place.  `phi`, `n0`, `n1` point at the
+// chain's fields (shared or global memory).
+template <typename real, bool STRICT>
+__device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, int32_t* __restrict__ n0,
+                                                       int32_t* __restrict__ n1, int N, int x0, int x1, real half_kappa,
+                                                       const VillainDraw& d) {
+    using A = Arith<real, STRICT>;
+    const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
+    const int xm0 = (x0 == 0) ? N - 1 : x0 - 1;
+    const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+    const int xm1 = (x1 == 0) ? N - 1 : x1 - 1;
+    const int row = x0 * N;
+    const int i_c = row + x1;
+    const int i_b0 = xm0 * N + x1;
+    const int i_b1 = row + xm1;
+
+    const real pc = phi[i_c];
+    const real pf0 = phi[xp0 * N + x1];
+    const real pb0 = phi[i_b0];
+    const real pf1 = phi[row + xp1];
+    const real pb1 = phi[i_b1];
+    const int nf0 = n0[i_c], nb0 = n0[i_b0], nf1 = n1[i_c], nb1 = n1[i_b1];
+
+    // residuals of the four links, recomputed from the current fields (neighborhood.py:91)
+    const real r_f0 = A::resid(A::sub(pf0, pc), (real)nf0);
+    const real r_b0 = A::resid(A::sub(pc, pb0), (real)nb0);
+    const real r_f1 = A::resid(A::sub(pf1, pc), (real)nf1);
+    const real r_b1 = A::resid(A::sub(pc, pb1), (real)nb1);
+
+    // change of the residuals (neighborhood.py:110): d(dphi) is -dphi on forward links, +dphi on backward links
+    const real dphi = (real)d.dphi;
+    const real dr_f0 = A::resid(-dphi, (real)d.dn[0]);
+    const real dr_b0 = A::resid(dphi, (real)d.dn[1]);
+    const real dr_f1 = A::resid(-dphi, (real)d.dn[2]);
+    const real dr_b1 = A::resid(dphi, (real)d.dn[3]);
+
+    // dS in the reference's face_sum order (neighborhood.py:111-112; lattice/_kernels.py:37-45)
+    real dS = A::link(half_kappa, dr_f0, r_f0);
+    dS = A::add(dS, A::link(half_kappa, dr_b0, r_b0));
+    dS = A::add(dS, A::link(half_kappa, dr_f1, r_f1));
+    dS = A::add(dS, A::link(half_kappa, dr_b1, r_b1));
+
+    const double acc = fmin((double)A::expneg(dS), 1.0);      // clip(exp(-dS), 0, 1)   (:115)
+    const bool ok = d.u < acc;                                  // (:116)
+    if (ok) {                                                   // (:121-128)
+        phi[i_c] = A::add(pc, dphi);
+        n0[i_c] = nf0 + d.dn[0];
+        n0[i_b0] = nb0 + d.dn[1];
+        n1[i_c] = nf1 + d.dn[2];
+        n1[i_b1] = nb1 + d.dn[3];
+    }
+    SiteOut o;
+    o.A = acc;
+    o.ok = ok;
+    o.dS = (double)dS;
+    return o;
+}
+
+template <bool INJECTED>
+__device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, long long chain, int sweep, int site) {
+    if (INJECTED) {
+        const long long V = (long long)a.N * a.N;
+        const long long base = ((long long)sweep * a.chains + chain) * V + site;
+        const long long lbase = ((long long)sweep * a.chains + chain) * 2 * V + site;
+        VillainDraw d;
+        d.u = a.inj_u[base];
+        d.dphi = a.inj_dphi[base];
+        d.dn[0] = a.inj_dn_fwd[lbase];
+        d.dn[1] = a.inj_dn_bwd[lbase];
+        d.dn[2] = a.inj_dn_fwd[lbase + V];
+        d.dn[3] = a.inj_dn_bwd[lbase + V];
+        return d;
+    } else {
+        return villain_draw_philox(a.seed, a.chain0 + (unsigned long long)chain, a.sweep0 + (unsigned long long)sweep,
+                                   (uint32_t)site, a.interval_phi, a.interval_n, a.W);
+    }
+}
+
+// Per-chain partial sums of the observables over the sites this thread strides over.
+template <typename real>
+__device__ __forceinline__ void villain_obs_partial(const real* __restrict__ phi, const int32_t* __restrict__ n0,
+                                                    const int32_t* __restrict__ n1, int N, int tid, int nthreads,
+                                                    double (&s)[4]) {
+    const int V = N * N;
+    for (int i = tid; i < V; i += nthreads) {
+        const int x0 = i / N, x1 = i - x0 * N;
+        const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
+        const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+        const int i0 = xp0 * N + x1, i1 = x0 * N + xp1;
+        const double pc = (double)phi[i];
+        const int a0 = n0[i], a1 = n1[i];
+        const double r0 = __dsub_rn(__dsub_rn((double)phi[i0], pc), __dmul_rn(SVB_TWO_PI, (double)a0));
+        const double r1 = __dsub_rn(__dsub_rn((double)phi[i1], pc), __dmul_rn(SVB_TWO_PI, (double)a1));
+        s[0] += r0 * r0 + r1 * r1;
+        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+        const int dn = (n1[i0] - a1) - (n0[i1] - a0);
+        s[1] += (double)dn * (double)dn;
+        s[2] += (double)a0;
+        s[3] += (double)a1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SMEM path: one CTA per chain (grid-stride over chains), whole lattice in shared memory.
+// ------------------------------------------------------------------------------------------
+template <typename real, bool INJECTED, bool STRICT>
+__global__ void __launch_bounds__(256) villain_smem_kernel(VillainArgs a, int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = a.N, V = N * N;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const size_t bytes_phi = (size_t)V * sizeof(real);
+    const size_t bytes_n = (size_t)2 * V * sizeof(int32_t);
+    const size_t off_n = (bytes_phi + 15) & ~(size_t)15;
+    const size_t off_scr = (off_n + bytes_n + 15) & ~(size_t)15;
+    real* sphi = reinterpret_cast<real*>(smem_raw);
+    int32_t* sn0 = reinterpret_cast<int32_t*>(smem_raw + off_n);
+    int32_t* sn1 = sn0 + V;
+    double* scratch = reinterpret_cast<double*>(smem_raw + off_scr);   // 6 * 32 doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_scr + 6 * 32 * sizeof(double));
+
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    uint32_t phase = 0;
+    const int ncol = n_colours(N);
+    const int halfN = N >> 1, nhalf = V >> 1;
+
+    for (long long chain = blockIdx.x; chain < a.chains; chain += gridDim.x) {
+        real* gphi = reinterpret_cast<real*>(a.phi) + chain * V;
+        int32_t* gn = a.n + chain * 2 * V;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const real half_kappa = (real)(kappa / 2);
+
+        // ---- load the chain: HBM -> shared ----
+        if (use_bulk) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, (uint32_t)(bytes_phi + bytes_n));
+                bulk_g2s(sphi, gphi, (uint32_t)bytes_phi, bar);
+                bulk_g2s(sn0, gn, (uint32_t)bytes_n, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < V; i += T) sphi[i] = gphi[i];
+            for (int i = tid; i < 2 * V; i += T) sn0[i] = gn[i];
+            __syncthreads();
+        }
+
+        double n_acc = 0.0, sum_A = 0.0;
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const bool last = (s == a.n_sweeps - 1);
+            for (int c = 0; c < ncol; ++c) {
+                if (ncol == 2) {
+                    for (int j = tid; j < nhalf; j += T) {
+                        const int x0 = j / halfN;
+                        const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
+                        const int site = x0 * N + x1;
+                        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
+                        const SiteOut o = villain_site_update<real, STRICT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        n_acc += o.ok ? 1.0 : 0.0;
+                        sum_A += o.A;
+                        if (last) {
+                            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                        }
+                    }
+                } else {
+                    for (int site = tid; site < V; site += T) {
+                        const int x0 = site / N, x1 = site - x0 * N;
+                        if (site_colour(x0, x1, N) != c) continue;
+                        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
+                        const SiteOut o = villain_site_update<real, STRICT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        n_acc += o.ok ? 1.0 : 0.0;
+                        sum_A += o.A;
+                        if (last) {
+                            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- fused observables of the final state ----
+        if (a.obs) {
+            double s[6] = {0, 0, 0, 0, n_acc, sum_A};
+            double part[4] = {0, 0, 0, 0};
+            villain_obs_partial<real>(sphi, sn0, sn1, N, tid, T, part);
+            s[0] = part[0]; s[1] = part[1]; s[2] = part[2]; s[3] = part[3];
+            block_sum<6>(s, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_VOBS_COUNT;
+                o[SVB_VOBS_ACTION] = (kappa / 2) * s[0];
+                o[SVB_VOBS_SUM_DN2] = s[1];
+                o[SVB_VOBS_WRAP0] = s[2];
+                o[SVB_VOBS_WRAP1] = s[3];
+                o[SVB_VOBS_ACCEPTED] = s[4];
+                o[SVB_VOBS_ACCEPTANCE] = s[5];
+            }
+        }
+
+        // ---- store the chain: shared -> HBM ----
+        if (use_bulk) {
+            fence_proxy_async();   // make this thread's generic-proxy smem writes visible to the bulk copy engine
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(gphi, sphi, (uint32_t)bytes_phi);
+                bulk_s2g(gn, sn0, (uint32_t)bytes_n);
+                bulk_commit();
+                bulk_wait_read0();  // smem may be overwritten by the next chain's load after this
+            }
+            __syncthreads();
+        } else {
+            for (int i = tid; i < V; i += T) gphi[i] = sphi[i];
+            for (int i = tid; i < 2 * V; i += T) gn[i] = sn0[i];
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GLOBAL path: one launch per colour pass, straight out of HBM / L2 (any N).
+// ------------------------------------------------------------------------------------------
+template <typename real, bool INJECTED, bool STRICT>
+__global__ void __launch_bounds__(256) villain_colour_pass_kernel(VillainArgs a, int sweep, int colour, int blocks_per_chain,
+                                                                  int write_debug) {
+    const int N = a.N, V = N * N;
+    const long long chain = blockIdx.x / blocks_per_chain;
+    const int blk = blockIdx.x - (int)(chain * blocks_per_chain);
+    real* gphi = reinterpret_cast<real*>(a.phi) + chain * V;
+    int32_t* gn0 = a.n + chain * 2 * V;
+    int32_t* gn1 = gn0 + V;
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    const real half_kappa = (real)(kappa / 2);
+    double n_acc = 0.0, sum_A = 0.0;
+
+    int site = -1, x0 = 0, x1 = 0;
+    if ((N & 1) == 0) {
+        const int j = blk * blockDim.x + threadIdx.x;
+        if (j < (V >> 1)) {
+            const int halfN = N >> 1;
+            x0 = j / halfN;
+            x1 = 2 * (j - x0 * halfN) + ((x0 + colour) & 1);
+            site = x0 * N + x1;
+        }
+    } else {
+        const int i = blk * blockDim.x + threadIdx.x;
+        if (i < V) {
+            x0 = i / N;
+            x1 = i - x0 * N;
+            if (site_colour(x0, x1, N) == colour) site = i;
+        }
+    }
+    if (site >= 0) {
+        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, sweep, site);
+        const SiteOut o = villain_site_update<real, STRICT>(gphi, gn0, gn1, N, x0, x1, half_kappa, d);
+        n_acc = o.ok ? 1.0 : 0.0;
+        sum_A = o.A;
+        if (write_debug) {
+            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+        }
+    }
+    if (a.obs) {
+        __shared__ double scratch[2 * 32];
+        double s[2] = {n_acc, sum_A};
+        block_sum<2>(s, scratch);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, s[0]);
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, s[1]);
+        }
+    }
+}
+
+// Observables of the current state, one CTA per chain.  keep_counters: leave ACCEPTED/ACCEPTANCE alone.
+template <typename real>
+__global__ void __launch_bounds__(256) villain_obs_kernel(const real* __restrict__ phi, const int32_t* __restrict__ n,
+                                                          long long chains, int N, double kappa_scalar,
+                                                          const double* __restrict__ kappa_chain, double* __restrict__ obs,
+                                                          int keep_counters) {
+    __shared__ double scratch[4 * 32];
+    const int V = N * N;
+    for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
+        const real* gphi = phi + chain * V;
+        const int32_t* gn0 = n + chain * 2 * V;
+        double s[4] = {0, 0, 0, 0};
+        villain_obs_partial<real>(gphi, gn0, gn0 + V, N, threadIdx.x, blockDim.x, s);
+        block_sum<4>(s, scratch);
+        if (threadIdx.x == 0) {
+            const double kappa = kappa_chain ? kappa_chain[chain] : kappa_scalar;
+            double* o = obs + chain * SVB_VOBS_COUNT;
+            o[SVB_VOBS_ACTION] = (kappa / 2) * s[0];
+            o[SVB_VOBS_SUM_DN2] = s[1];
+            o[SVB_VOBS_WRAP0] = s[2];
+            o[SVB_VOBS_WRAP1] = s[3];
+            if (!keep_counters) {
+                o[SVB_VOBS_ACCEPTED] = 0.0;
+                o[SVB_VOBS_ACCEPTANCE] = 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void villain_zero_counters_kernel(double* obs, long long chains) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < chains) {
+        obs[c * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED] = 0.0;
+        obs[c * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE] = 0.0;
+    }
+}
+
+__global__ void villain_draws_kernel(long long chains, int N, int W, double interval_phi, int interval_n,
+                                     unsigned long long seed, unsigned long long sweep, unsigned long long chain0,
+                                     double* u, double* dphi, int32_t* dn) {
+    const long long V = (long long)N * N;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= chains * V) return;
+    const long long chain = i / V;
+    const int site = (int)(i - chain * V);
+    const VillainDraw d = villain_draw_philox(seed, chain0 + chain, sweep, (uint32_t)site, interval_phi, interval_n, W);
+    u[i] = d.u;
+    dphi[i] = d.dphi;
+    for (int k = 0; k < 4; ++k) dn[(chain * 4 + k) * V + site] = d.dn[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static size_t villain_smem_bytes(int N, size_t real_size) {
+    const size_t V = (size_t)N * N;
+    const size_t off_n = (V * real_size + 15) & ~(size_t)15;
+    const size_t off_scr = (off_n + 2 * V * sizeof(int32_t) + 15) & ~(size_t)15;
+    return off_scr + 6 * 32 * sizeof(double) + 16;
+}
+
+static int villain_threads_for(int N) {
+    const int V = N * N;
+    int t = (V / 8 + 31) / 32 * 32;   // ~4 sites per colour per thread
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+static int get_device_info(DeviceInfo& info) {
+    int dev = 0;
+    SVB_CUDA_TRY(cudaGetDevice(&dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+template <typename real, bool INJECTED, bool STRICT>
+static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    auto kern = villain_smem_kernel<real, INJECTED, STRICT>;
+    const size_t smem = villain_smem_bytes(a.N, sizeof(real));
+    const int threads = villain_threads_for(a.N);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "villain smem kernel does not fit an SM at N=%d", a.N);
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > a.chains) grid = a.chains;
+    // bulk (TMA 1-D) copies need 16-byte sizes and addresses
+    const size_t bytes_phi = (size_t)a.N * a.N * sizeof(real);
+    const size_t bytes_n = (size_t)2 * a.N * a.N * sizeof(int32_t);
+    const int use_bulk = (bytes_phi % 16 == 0) && (bytes_n % 16 == 0) && ((uintptr_t)a.phi % 16 == 0) &&
+                         ((uintptr_t)a.n % 16 == 0);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(a, use_bulk);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename real, bool INJECTED, bool STRICT>
+static int launch_villain_global(const VillainArgs& a, cudaStream_t stream) {
+    const int N = a.N, V = N * N;
+    const int threads = 256;
+    const int work = (N & 1) ? V : V / 2;
+    const int bpc = (work + threads - 1) / threads;
+    const long long blocks = (long long)bpc * a.chains;
+    if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "too many blocks (%lld) for the global path", blocks);
+    if (a.obs) {
+        villain_zero_counters_kernel<<<(unsigned)((a.chains + 255) / 256), 256, 0, stream>>>(a.obs, a.chains);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    const int ncol = n_colours(N);
+    for (int s = 0; s < a.n_sweeps; ++s) {
+        for (int c = 0; c < ncol; ++c) {
+            villain_colour_pass_kernel<real, INJECTED, STRICT>
+                <<<(unsigned)blocks, threads, 0, stream>>>(a, s, c, bpc, s == a.n_sweeps - 1);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (a.obs) {
+        long long grid = a.chains < 148 * 8 ? a.chains : 148 * 8;
+        villain_obs_kernel<real><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const real*>(a.phi), a.n, a.chains,
+                                                                     N, a.kappa, a.kappa_chain, a.obs, 1);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <typename real>
+static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, int path, cudaStream_t stream) {
+    DeviceInfo info;
+    int rc = get_device_info(info);
+    if (rc) return rc;
+    if (path == SVB_PATH_AUTO) {
+        path = (villain_smem_bytes(a.N, sizeof(real)) <= (size_t)info.max_smem_optin) ? SVB_PATH_SMEM : SVB_PATH_GLOBAL;
+    }
+    if (path == SVB_PATH_SMEM) {
+        if (villain_smem_bytes(a.N, sizeof(real)) > (size_t)info.max_smem_optin)
+            return fail(SVB_E_UNSUPPORTED, "N=%d does not fit shared memory; use SVB_PATH_GLOBAL", a.N);
+        if (rng_mode == SVB_RNG_INJECTED) return launch_villain_smem<real, true, true>(a, stream, info);
+        if (arith_mode == SVB_ARITH_STRICT) return launch_villain_smem<real, false, true>(a, stream, info);
+        return launch_villain_smem<real, false, false>(a, stream, info);
+    }
+    if (rng_mode == SVB_RNG_INJECTED) return launch_villain_global<real, true, true>(a, stream);
+    if (arith_mode == SVB_ARITH_STRICT) return launch_villain_global<real, false, true>(a, stream);
+    return launch_villain_global<real, false, false>(a, stream);
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t chains, int N, double kappa,
+                                 const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
+                                 uint64_t seed, uint64_t sweep0, uint64_t chain0, int rng_mode, int arith_mode, int path,
+                                 const double* inj_u, const double* inj_dphi, const int32_t* inj_dn_fwd,
+                                 const int32_t* inj_dn_bwd, double* obs, uint8_t* accept_mask, double* dS_out,
+                                 void* stream) {
+    if (!phi || !n) return fail(SVB_E_NULL, "svb_villain_sweep: phi and n are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_villain_sweep: chains=%lld N=%d", (long long)chains, N);
+    if (phi_dtype != SVB_F64 && phi_dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_villain_sweep: phi dtype %d", phi_dtype);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep: kappa must be positive");
+    if (W < 1) return fail(SVB_E_PARAM, "svb_villain_sweep: W must be a finite integer >= 1 (got %d)", W);
+    if (interval_n < 0 || interval_n > 31) return fail(SVB_E_PARAM, "svb_villain_sweep: interval_n must be in [0, 31]");
+    if (!(interval_phi >= 0)) return fail(SVB_E_PARAM, "svb_villain_sweep: interval_phi must be >= 0");
+    if (n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_sweep: n_sweeps < 0");
+    if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_villain_sweep: rng_mode");
+    if (rng_mode == SVB_RNG_INJECTED && (!inj_u || !inj_dphi || !inj_dn_fwd || !inj_dn_bwd))
+        return fail(SVB_E_NULL, "svb_villain_sweep: injected mode needs inj_u, inj_dphi, inj_dn_fwd, inj_dn_bwd");
+    if (arith_mode != SVB_ARITH_STRICT && arith_mode != SVB_ARITH_FAST) return fail(SVB_E_PARAM, "svb_villain_sweep: arith_mode");
+    if (path < SVB_PATH_AUTO || path > SVB_PATH_GLOBAL) return fail(SVB_E_PARAM, "svb_villain_sweep: path");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
+    a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
+    a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (phi_dtype == SVB_F64) return dispatch_villain<double>(a, rng_mode, arith_mode, path, st);
+    return dispatch_villain<float>(a, rng_mode, arith_mode, path, st);
+}
+
+extern "C" int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n, int64_t chains, int N, double kappa,
+                                       const double* kappa_chain, double* obs, void* stream) {
+    if (!phi || !n || !obs) return fail(SVB_E_NULL, "svb_villain_observables: phi, n, obs are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_villain_observables: chains=%lld N=%d", (long long)chains, N);
+    if (phi_dtype != SVB_F64 && phi_dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_villain_observables: phi dtype %d", phi_dtype);
+    if (chains == 0) return SVB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long grid = chains < 148 * 8 ? chains : 148 * 8;
+    if (phi_dtype == SVB_F64)
+        villain_obs_kernel<double><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const double*>(phi), n, chains, N, kappa,
+                                                                   kappa_chain, obs, 0);
+    else
+        villain_obs_kernel<float><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float*>(phi), n, chains, N, kappa,
+                                                                  kappa_chain, obs, 0);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_villain_draws(int64_t chains, int N, int W, double interval_phi, int interval_n, uint64_t seed,
+                                 uint64_t sweep, uint64_t chain0, double* u, double* dphi, int32_t* dn, void* stream) {
+    if (!u || !dphi || !dn) return fail(SVB_E_NULL, "svb_villain_draws: outputs required");
+    if (chains <= 0 || N < 1) return fail(SVB_E_SHAPE, "svb_villain_draws: shape");
+    if (interval_n < 0 || interval_n > 31) return fail(SVB_E_PARAM, "svb_villain_draws: interval_n");
+    const long long total = (long long)chains * N * N;
+    villain_draws_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        chains, N, W, interval_phi, interval_n, seed, sweep, chain0, u, dphi, dn);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}

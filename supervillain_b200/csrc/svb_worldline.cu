@@ -1,0 +1,514 @@
+// svb_worldline.cu -- batched checkerboard Metropolis sweeps of the worldline action
+//   S = 1/(2 kappa) sum_l (m - delta v / W)_l^2 + const,   delta m = 0
+// The move is PlaquetteUpdate's (supervillain/generator/worldline/plaquette.py:79-101): the four
+// boundary links of the plaquette based at x change by +dm, +dm, -dm, -dm and v[x] by dv.  The
+// sweep order is the red/black order of the reference's own checkerboard generators
+// VortexUpdate / CoexactUpdate (worldline/vortex.py:86-128, worldline/coexact.py:91-120), whose
+// v-only and m-only moves are the VORTEX and COEXACT modes here.
+//
+// Boundary links of the plaquette at x and the sign of delta(unit 2-form at x) on them:
+//   (0,x): +1    (0,x+e1): -1    (1,x): -1    (1,x+e0): +1
+// f_l = m_l - (delta v)_l / W with (delta v)_0[x] = v[x] - v[x-e1], (delta v)_1[x] = -(v[x] - v[x-e0])
+// (compact.py delta,2 rows).  Plaquettes whose base sites share a colour have disjoint
+// boundaries, so a colour is updated concurrently without atomics.
+
+#include "svb_common.cuh"
+
+namespace svb {
+
+struct WorldlineArgs {
+    int32_t* m;
+    int32_t* v;
+    long long chains;
+    int N;
+    double kappa;
+    const double* kappa_chain;
+    int W;
+    int interval;
+    int n_sweeps;
+    unsigned long long seed, sweep0, chain0;
+    const double* inj_u;
+    const int32_t* inj_a;
+    const int32_t* inj_b;
+    double* obs;
+    uint8_t* accept_mask;
+    double* dS_out;
+};
+
+struct WlDraw {
+    double u;
+    int a;   // dm (JOINT), dv (VORTEX), t (COEXACT)
+    int b;   // dv (JOINT)
+};
+
+// Philox draw mapping for one plaquette: 44 bits -> u in (0,1); 1 bit -> dm sign (JOINT);
+// a 40-bit fraction -> one choice among K values.
+template <int MODE>
+__host__ __device__ __forceinline__ WlDraw worldline_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
+                                                                 uint32_t site, int interval) {
+    Philox4 p = philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE);
+    WlDraw d;
+    const double two_m44 = 5.6843418860808015e-14;  // 2^-44
+    uint64_t ku = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
+    d.u = ((double)(long long)ku + 0.5) * two_m44;
+    uint64_t k40 = ((uint64_t)(p.z & 0xFFu) << 32) | (uint64_t)p.w;
+    if (MODE == SVB_WL_JOINT) {
+        d.a = ((p.y >> 19) & 1u) ? +1 : -1;           // rng.choice([-1,+1])   (plaquette.py:58)
+        d.b = (int)((k40 * 3ull) >> 40) - 1;          // rng.choice([-1,0,+1]) (plaquette.py:59)
+    } else {
+        // choice over [-I..-1, 1..I]  (vortex.py:39, coexact.py:40)
+        int idx = (int)((k40 * (uint64_t)(2 * interval)) >> 40);
+        d.a = (idx < interval) ? idx - interval : idx - interval + 1;
+        d.b = 0;
+    }
+    return d;
+}
+
+template <int MODE, bool INJECTED>
+__device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, long long chain, int sweep, int site) {
+    if (INJECTED) {
+        const long long V = (long long)a.N * a.N;
+        const long long base = ((long long)sweep * a.chains + chain) * V + site;
+        WlDraw d;
+        d.u = a.inj_u[base];
+        d.a = a.inj_a[base];
+        d.b = (MODE == SVB_WL_JOINT) ? a.inj_b[base] : 0;
+        return d;
+    } else {
+        return worldline_draw_philox<MODE>(a.seed, a.chain0 + (unsigned long long)chain,
+                                           a.sweep0 + (unsigned long long)sweep, (uint32_t)site, a.interval);
+    }
+}
+
+struct PlaqOut {
+    double A;
+    bool ok;
+    double dS;
+};
+
+template <int MODE>
+__device__ __forceinline__ PlaqOut worldline_plaquette_update(int32_t* __restrict__ m0, int32_t* __restrict__ m1,
+                                                              int32_t* __restrict__ v, int N, int x0, int x1, double kappa,
+                                                              double Wd, const WlDraw& d) {
+    const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
+    const int xm0 = (x0 == 0) ? N - 1 : x0 - 1;
+    const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+    const int xm1 = (x1 == 0) ? N - 1 : x1 - 1;
+    const int i_c = x0 * N + x1;
+    const int i_p0 = xp0 * N + x1, i_m0 = xm0 * N + x1;
+    const int i_p1 = x0 * N + xp1, i_m1 = x0 * N + xm1;
+
+    const int vc = v[i_c], vp0 = v[i_p0], vm0 = v[i_m0], vp1 = v[i_p1], vm1 = v[i_m1];
+    const int m_0x = m0[i_c];      // link (0, x)
+    const int m_0p = m0[i_p1];     // link (0, x + e1)
+    const int m_1x = m1[i_c];      // link (1, x)
+    const int m_1p = m1[i_p0];     // link (1, x + e0)
+
+    // f = m - delta(v) / W     (plaquette.py:53, vortex.py:111, coexact.py:104)
+    const double f_0x = __dsub_rn((double)m_0x, __ddiv_rn((double)(vc - vm1), Wd));
+    const double f_0p = __dsub_rn((double)m_0p, __ddiv_rn((double)(vp1 - vc), Wd));
+    const double f_1x = __dsub_rn((double)m_1x, __ddiv_rn((double)(vm0 - vc), Wd));
+    const double f_1p = __dsub_rn((double)m_1p, __ddiv_rn((double)(vc - vp0), Wd));
+
+    double dS;
+    if (MODE == SVB_WL_JOINT) {
+        // delta_f = dm - dv / W ;  dS = delta_f / kappa * (f1 + f2 - f3 - f4 + 2 delta_f)   (plaquette.py:84-85)
+        const double df = __dsub_rn((double)d.a, __ddiv_rn((double)d.b, Wd));
+        double s = __dadd_rn(f_0x, f_1p);            // f1 + f2
+        s = __dsub_rn(s, f_0p);                      // - f3
+        s = __dsub_rn(s, f_1x);                      // - f4
+        s = __dadd_rn(s, __dmul_rn(2.0, df));
+        dS = __dmul_rn(__ddiv_rn(df, kappa), s);
+    } else {
+        const double hk = __ddiv_rn(0.5, kappa);
+        double t_1x, t_1p, t_0x, t_0p;
+        if (MODE == SVB_WL_VORTEX) {
+            // c_l = sign_l a / W ;  T_l = ((0.5/kappa)(-c_l)) ((2 f_l) - c_l)   (vortex.py:108-112)
+            const double c_pos = __ddiv_rn((double)d.a, Wd), c_neg = __ddiv_rn((double)(-d.a), Wd);
+            t_1x = __dmul_rn(__dmul_rn(hk, -c_neg), __dsub_rn(__dmul_rn(2.0, f_1x), c_neg));
+            t_1p = __dmul_rn(__dmul_rn(hk, -c_pos), __dsub_rn(__dmul_rn(2.0, f_1p), c_pos));
+            t_0x = __dmul_rn(__dmul_rn(hk, -c_pos), __dsub_rn(__dmul_rn(2.0, f_0x), c_pos));
+            t_0p = __dmul_rn(__dmul_rn(hk, -c_neg), __dsub_rn(__dmul_rn(2.0, f_0p), c_neg));
+        } else {
+            // c_l = sign_l t ;  T_l = ((0.5/kappa) c_l) ((2 f_l) + c_l)           (coexact.py:102-106)
+            const double c_pos = (double)d.a, c_neg = (double)(-d.a);
+            t_1x = __dmul_rn(__dmul_rn(hk, c_neg), __dadd_rn(__dmul_rn(2.0, f_1x), c_neg));
+            t_1p = __dmul_rn(__dmul_rn(hk, c_pos), __dadd_rn(__dmul_rn(2.0, f_1p), c_pos));
+            t_0x = __dmul_rn(__dmul_rn(hk, c_pos), __dadd_rn(__dmul_rn(2.0, f_0x), c_pos));
+            t_0p = __dmul_rn(__dmul_rn(hk, c_neg), __dadd_rn(__dmul_rn(2.0, f_0p), c_neg));
+        }
+        // coface_sum order: 0 + T(1,x) + T(1,x+e0) + T(0,x) + T(0,x+e1)   (compact.py coface_sum,1 rows)
+        dS = __dadd_rn(t_1x, t_1p);
+        dS = __dadd_rn(dS, t_0x);
+        dS = __dadd_rn(dS, t_0p);
+    }
+    const double acc = fmin(exp(-dS), 1.0);
+    const bool ok = d.u < acc;
+    if (ok) {
+        if (MODE == SVB_WL_JOINT) {
+            m0[i_c] = m_0x + d.a;      // plaquette.py:91-95
+            m1[i_p0] = m_1p + d.a;
+            m0[i_p1] = m_0p - d.a;
+            m1[i_c] = m_1x - d.a;
+            v[i_c] = vc + d.b;
+        } else if (MODE == SVB_WL_VORTEX) {
+            v[i_c] = vc + d.a;         // vortex.py:125-127
+        } else {
+            m0[i_c] = m_0x + d.a;      // m += delta t, coexact.py:119-120
+            m1[i_p0] = m_1p + d.a;
+            m0[i_p1] = m_0p - d.a;
+            m1[i_c] = m_1x - d.a;
+        }
+    }
+    PlaqOut o;
+    o.A = acc;
+    o.ok = ok;
+    o.dS = dS;
+    return o;
+}
+
+__device__ __forceinline__ void worldline_obs_partial(const int32_t* __restrict__ m0, const int32_t* __restrict__ m1,
+                                                      const int32_t* __restrict__ v, int N, double Wd, int tid, int nthreads,
+                                                      double (&s)[5]) {
+    const int V = N * N;
+    for (int i = tid; i < V; i += nthreads) {
+        const int x0 = i / N, x1 = i - x0 * N;
+        const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1, xm0 = (x0 == 0) ? N - 1 : x0 - 1;
+        const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1, xm1 = (x1 == 0) ? N - 1 : x1 - 1;
+        const int i_p0 = xp0 * N + x1, i_m0 = xm0 * N + x1, i_p1 = x0 * N + xp1, i_m1 = x0 * N + xm1;
+        const int vc = v[i], a0 = m0[i], a1 = m1[i];
+        // f at (0,x), (1,x), (1,x+e0), (0,x+e1)
+        const double f0 = (double)a0 - (double)(vc - v[i_m1]) / Wd;
+        const double f1 = (double)a1 - (double)(v[i_m0] - vc) / Wd;
+        const double f1p = (double)m1[i_p0] - (double)(vc - v[i_p0]) / Wd;
+        const double f0p = (double)m0[i_p1] - (double)(v[i_p1] - vc) / Wd;
+        s[0] += f0 * f0 + f1 * f1;
+        const double df = (f1p - f1) - (f0p - f0);                  // (d f)[x], compact.py d,1 rows
+        s[1] += df * df;
+        s[2] += (double)a0;
+        s[3] += (double)a1;
+        // (delta m)[x] = -(m0[x] - m0[x-e0]) - (m1[x] - m1[x-e1])   (compact.py delta,1 rows)
+        const int dm = -(a0 - m0[i_m0]) - (a1 - m1[i_m1]);
+        s[4] += (double)(dm < 0 ? -dm : dm);
+    }
+}
+
+template <int MODE, bool INJECTED>
+__global__ void __launch_bounds__(256) worldline_smem_kernel(WorldlineArgs a, int use_bulk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int N = a.N, V = N * N;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const size_t bytes_m = (size_t)2 * V * sizeof(int32_t);
+    const size_t bytes_v = (size_t)V * sizeof(int32_t);
+    const size_t off_v = (bytes_m + 15) & ~(size_t)15;
+    const size_t off_scr = (off_v + bytes_v + 15) & ~(size_t)15;
+    int32_t* sm0 = reinterpret_cast<int32_t*>(smem_raw);
+    int32_t* sm1 = sm0 + V;
+    int32_t* sv = reinterpret_cast<int32_t*>(smem_raw + off_v);
+    double* scratch = reinterpret_cast<double*>(smem_raw + off_scr);   // 7 * 32 doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off_scr + 7 * 32 * sizeof(double));
+
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    uint32_t phase = 0;
+    const int ncol = n_colours(N);
+    const int halfN = N >> 1, nhalf = V >> 1;
+    const double Wd = (double)a.W;
+
+    for (long long chain = blockIdx.x; chain < a.chains; chain += gridDim.x) {
+        int32_t* gm = a.m + chain * 2 * V;
+        int32_t* gv = a.v + chain * V;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+
+        if (use_bulk) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, (uint32_t)(bytes_m + bytes_v));
+                bulk_g2s(sm0, gm, (uint32_t)bytes_m, bar);
+                bulk_g2s(sv, gv, (uint32_t)bytes_v, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = tid; i < 2 * V; i += T) sm0[i] = gm[i];
+            for (int i = tid; i < V; i += T) sv[i] = gv[i];
+            __syncthreads();
+        }
+
+        double n_acc = 0.0, sum_A = 0.0;
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const bool last = (s == a.n_sweeps - 1);
+            for (int c = 0; c < ncol; ++c) {
+                if (ncol == 2) {
+                    for (int j = tid; j < nhalf; j += T) {
+                        const int x0 = j / halfN;
+                        const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
+                        const int site = x0 * N + x1;
+                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, site);
+                        const PlaqOut o = worldline_plaquette_update<MODE>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d);
+                        n_acc += o.ok ? 1.0 : 0.0;
+                        sum_A += o.A;
+                        if (last) {
+                            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                        }
+                    }
+                } else {
+                    for (int site = tid; site < V; site += T) {
+                        const int x0 = site / N, x1 = site - x0 * N;
+                        if (site_colour(x0, x1, N) != c) continue;
+                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, site);
+                        const PlaqOut o = worldline_plaquette_update<MODE>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d);
+                        n_acc += o.ok ? 1.0 : 0.0;
+                        sum_A += o.A;
+                        if (last) {
+                            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        if (a.obs) {
+            double part[5] = {0, 0, 0, 0, 0};
+            worldline_obs_partial(sm0, sm1, sv, N, Wd, tid, T, part);
+            double s[7] = {part[0], part[1], part[2], part[3], n_acc, sum_A, part[4]};
+            block_sum<7>(s, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_WOBS_COUNT;
+                for (int k = 0; k < SVB_WOBS_COUNT; ++k) o[k] = s[k];
+            }
+        }
+
+        if (use_bulk) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                if (MODE != SVB_WL_VORTEX) bulk_s2g(gm, sm0, (uint32_t)bytes_m);
+                if (MODE != SVB_WL_COEXACT) bulk_s2g(gv, sv, (uint32_t)bytes_v);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+            __syncthreads();
+        } else {
+            if (MODE != SVB_WL_VORTEX)
+                for (int i = tid; i < 2 * V; i += T) gm[i] = sm0[i];
+            if (MODE != SVB_WL_COEXACT)
+                for (int i = tid; i < V; i += T) gv[i] = sv[i];
+            __syncthreads();
+        }
+    }
+}
+
+template <int MODE, bool INJECTED>
+__global__ void __launch_bounds__(256) worldline_colour_pass_kernel(WorldlineArgs a, int sweep, int colour, int blocks_per_chain,
+                                                                    int write_debug) {
+    const int N = a.N, V = N * N;
+    const long long chain = blockIdx.x / blocks_per_chain;
+    const int blk = blockIdx.x - (int)(chain * blocks_per_chain);
+    int32_t* gm0 = a.m + chain * 2 * V;
+    int32_t* gm1 = gm0 + V;
+    int32_t* gv = a.v + chain * V;
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    double n_acc = 0.0, sum_A = 0.0;
+
+    int site = -1, x0 = 0, x1 = 0;
+    if ((N & 1) == 0) {
+        const int j = blk * blockDim.x + threadIdx.x;
+        if (j < (V >> 1)) {
+            const int halfN = N >> 1;
+            x0 = j / halfN;
+            x1 = 2 * (j - x0 * halfN) + ((x0 + colour) & 1);
+            site = x0 * N + x1;
+        }
+    } else {
+        const int i = blk * blockDim.x + threadIdx.x;
+        if (i < V) {
+            x0 = i / N;
+            x1 = i - x0 * N;
+            if (site_colour(x0, x1, N) == colour) site = i;
+        }
+    }
+    if (site >= 0) {
+        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, sweep, site);
+        const PlaqOut o = worldline_plaquette_update<MODE>(gm0, gm1, gv, N, x0, x1, kappa, (double)a.W, d);
+        n_acc = o.ok ? 1.0 : 0.0;
+        sum_A = o.A;
+        if (write_debug) {
+            if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+            if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+        }
+    }
+    if (a.obs) {
+        __shared__ double scratch[2 * 32];
+        double s[2] = {n_acc, sum_A};
+        block_sum<2>(s, scratch);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.obs + chain * SVB_WOBS_COUNT + SVB_WOBS_ACCEPTED, s[0]);
+            atomicAdd(a.obs + chain * SVB_WOBS_COUNT + SVB_WOBS_ACCEPTANCE, s[1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) worldline_obs_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ v,
+                                                            long long chains, int N, int W, double* __restrict__ obs,
+                                                            int keep_counters) {
+    __shared__ double scratch[5 * 32];
+    const int V = N * N;
+    for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
+        const int32_t* gm0 = m + chain * 2 * V;
+        double s[5] = {0, 0, 0, 0, 0};
+        worldline_obs_partial(gm0, gm0 + V, v + chain * V, N, (double)W, threadIdx.x, blockDim.x, s);
+        block_sum<5>(s, scratch);
+        if (threadIdx.x == 0) {
+            double* o = obs + chain * SVB_WOBS_COUNT;
+            o[SVB_WOBS_SUM_F2] = s[0];
+            o[SVB_WOBS_SUM_DF2] = s[1];
+            o[SVB_WOBS_WRAP0] = s[2];
+            o[SVB_WOBS_WRAP1] = s[3];
+            o[SVB_WOBS_DELTA_M_ABS] = s[4];
+            if (!keep_counters) {
+                o[SVB_WOBS_ACCEPTED] = 0.0;
+                o[SVB_WOBS_ACCEPTANCE] = 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void worldline_zero_counters_kernel(double* obs, long long chains) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < chains) {
+        obs[c * SVB_WOBS_COUNT + SVB_WOBS_ACCEPTED] = 0.0;
+        obs[c * SVB_WOBS_COUNT + SVB_WOBS_ACCEPTANCE] = 0.0;
+    }
+}
+
+static size_t worldline_smem_bytes(int N) {
+    const size_t V = (size_t)N * N;
+    const size_t off_v = (2 * V * sizeof(int32_t) + 15) & ~(size_t)15;
+    const size_t off_scr = (off_v + V * sizeof(int32_t) + 15) & ~(size_t)15;
+    return off_scr + 7 * 32 * sizeof(double) + 16;
+}
+
+static int worldline_threads_for(int N) {
+    const int V = N * N;
+    int t = (V / 8 + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+template <int MODE, bool INJECTED>
+static int launch_worldline_smem(const WorldlineArgs& a, cudaStream_t stream, int sm_count) {
+    auto kern = worldline_smem_kernel<MODE, INJECTED>;
+    const size_t smem = worldline_smem_bytes(a.N);
+    const int threads = worldline_threads_for(a.N);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "worldline smem kernel does not fit an SM at N=%d", a.N);
+    long long grid = (long long)per_sm * sm_count;
+    if (grid > a.chains) grid = a.chains;
+    const size_t bytes_v = (size_t)a.N * a.N * sizeof(int32_t);
+    const int use_bulk = (bytes_v % 16 == 0) && ((uintptr_t)a.m % 16 == 0) && ((uintptr_t)a.v % 16 == 0);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(a, use_bulk);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int MODE, bool INJECTED>
+static int launch_worldline_global(const WorldlineArgs& a, cudaStream_t stream) {
+    const int N = a.N, V = N * N;
+    const int threads = 256;
+    const int work = (N & 1) ? V : V / 2;
+    const int bpc = (work + threads - 1) / threads;
+    const long long blocks = (long long)bpc * a.chains;
+    if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "too many blocks (%lld) for the global path", blocks);
+    if (a.obs) {
+        worldline_zero_counters_kernel<<<(unsigned)((a.chains + 255) / 256), 256, 0, stream>>>(a.obs, a.chains);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    const int ncol = n_colours(N);
+    for (int s = 0; s < a.n_sweeps; ++s) {
+        for (int c = 0; c < ncol; ++c) {
+            worldline_colour_pass_kernel<MODE, INJECTED>
+                <<<(unsigned)blocks, threads, 0, stream>>>(a, s, c, bpc, s == a.n_sweeps - 1);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (a.obs) {
+        long long grid = a.chains < 148 * 8 ? a.chains : 148 * 8;
+        worldline_obs_kernel<<<(unsigned)grid, 256, 0, stream>>>(a.m, a.v, a.chains, N, a.W, a.obs, 1);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int MODE>
+static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cudaStream_t stream) {
+    int dev = 0, sm_count = 0, max_smem = 0;
+    SVB_CUDA_TRY(cudaGetDevice(&dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (path == SVB_PATH_AUTO) path = (worldline_smem_bytes(a.N) <= (size_t)max_smem) ? SVB_PATH_SMEM : SVB_PATH_GLOBAL;
+    if (path == SVB_PATH_SMEM) {
+        if (worldline_smem_bytes(a.N) > (size_t)max_smem)
+            return fail(SVB_E_UNSUPPORTED, "N=%d does not fit shared memory; use SVB_PATH_GLOBAL", a.N);
+        return rng_mode == SVB_RNG_INJECTED ? launch_worldline_smem<MODE, true>(a, stream, sm_count)
+                                            : launch_worldline_smem<MODE, false>(a, stream, sm_count);
+    }
+    return rng_mode == SVB_RNG_INJECTED ? launch_worldline_global<MODE, true>(a, stream)
+                                        : launch_worldline_global<MODE, false>(a, stream);
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                   int W, int mode, int interval, int n_sweeps, uint64_t seed, uint64_t sweep0,
+                                   uint64_t chain0, int rng_mode, int path, const double* inj_u, const int32_t* inj_a,
+                                   const int32_t* inj_b, double* obs, uint8_t* accept_mask, double* dS_out, void* stream) {
+    if (!m || !v) return fail(SVB_E_NULL, "svb_worldline_sweep: m and v are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_worldline_sweep: chains=%lld N=%d", (long long)chains, N);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_sweep: kappa must be positive");
+    if (W < 1) return fail(SVB_E_PARAM, "svb_worldline_sweep: W must be a finite integer >= 1 (got %d)", W);
+    if (mode < SVB_WL_JOINT || mode > SVB_WL_COEXACT) return fail(SVB_E_PARAM, "svb_worldline_sweep: mode %d", mode);
+    if (mode != SVB_WL_JOINT && (interval < 1 || interval > 1024)) return fail(SVB_E_PARAM, "svb_worldline_sweep: interval");
+    if (n_sweeps < 0) return fail(SVB_E_PARAM, "svb_worldline_sweep: n_sweeps < 0");
+    if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_worldline_sweep: rng_mode");
+    if (rng_mode == SVB_RNG_INJECTED && (!inj_u || !inj_a || (mode == SVB_WL_JOINT && !inj_b)))
+        return fail(SVB_E_NULL, "svb_worldline_sweep: injected mode needs inj_u, inj_a (and inj_b for JOINT)");
+    if (path < SVB_PATH_AUTO || path > SVB_PATH_GLOBAL) return fail(SVB_E_PARAM, "svb_worldline_sweep: path");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+
+    WorldlineArgs a;
+    a.m = m; a.v = v; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval = interval; a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    a.inj_u = inj_u; a.inj_a = inj_a; a.inj_b = inj_b; a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (mode) {
+        case SVB_WL_JOINT: return dispatch_worldline<SVB_WL_JOINT>(a, rng_mode, path, st);
+        case SVB_WL_VORTEX: return dispatch_worldline<SVB_WL_VORTEX>(a, rng_mode, path, st);
+        default: return dispatch_worldline<SVB_WL_COEXACT>(a, rng_mode, path, st);
+    }
+}
+
+extern "C" int svb_worldline_observables(const int32_t* m, const int32_t* v, int64_t chains, int N, int W, double* obs,
+                                         void* stream) {
+    if (!m || !v || !obs) return fail(SVB_E_NULL, "svb_worldline_observables: m, v, obs are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_worldline_observables: shape");
+    if (W < 1) return fail(SVB_E_PARAM, "svb_worldline_observables: W");
+    if (chains == 0) return SVB_OK;
+    long long grid = chains < 148 * 8 ? chains : 148 * 8;
+    worldline_obs_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(m, v, chains, N, W, obs, 0);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}

@@ -1,0 +1,202 @@
+"""Thin, validated Python wrappers over the C ABI of libsvb200.so.
+
+Arguments are `torch` CUDA tensors used purely as device storage (`data_ptr()` + the current
+stream); every function enqueues work on `torch.cuda.current_stream()` and returns immediately.
+Nothing here computes on the CPU -- a missing library or device raises.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ARITH_FAST, ARITH_STRICT, PATH_AUTO, PATH_GLOBAL, PATH_SMEM, RNG_INJECTED, RNG_PHILOX,  # noqa: F401
+                   VOBS_COUNT, WOBS_COUNT, WL_COEXACT, WL_JOINT, WL_VORTEX)
+
+_PATHS = {'auto': PATH_AUTO, 'smem': PATH_SMEM, 'global': PATH_GLOBAL}
+_ARITH = {'strict': ARITH_STRICT, 'fast': ARITH_FAST}
+_WL_MODES = {'joint': WL_JOINT, 'vortex': WL_VORTEX, 'coexact': WL_COEXACT}
+_OPS = {'d': _lib.OP_D, 'delta': _lib.OP_DELTA, 'face_sum': _lib.OP_FACE_SUM, 'coface_sum': _lib.OP_COFACE_SUM}
+_DTYPES = {torch.float64: _lib.F64, torch.float32: _lib.F32, torch.int32: _lib.I32, torch.int64: _lib.I64}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t, name, dtypes, shape=None):
+    """Validate a device tensor argument and return its pointer."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor on a CUDA device, got {type(t).__name__}')
+    if not t.is_cuda:
+        raise ValueError(f'{name} must live on a CUDA device (supervillain_b200 has no CPU path)')
+    if t.dtype not in dtypes:
+        raise TypeError(f'{name} has dtype {t.dtype}; expected one of {dtypes}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be C-contiguous')
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f'{name} has shape {tuple(t.shape)}; expected {tuple(shape)}')
+    return t.data_ptr()
+
+
+def _opt(t, name, dtypes, shape):
+    return None if t is None else _dev(t, name, dtypes, shape)
+
+
+def _fields_shape(t, name, comps):
+    if t.dim() != 4 or t.shape[1] != comps or t.shape[2] != t.shape[3]:
+        raise ValueError(f'{name} must have shape (chains, {comps}, N, N); got {tuple(t.shape)}')
+    return int(t.shape[0]), int(t.shape[2])
+
+
+def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_sweeps=1, seed=0, sweep0=0,
+                  chain0=0, injected=None, arithmetic='fast', path='auto', kappa_chain=None, obs=None,
+                  accept_mask=None, dS_out=None):
+    """`n_sweeps` NeighborhoodUpdate sweeps on every chain, in place (svb_villain_sweep).
+
+    phi (chains,1,N,N) float64|float32, n (chains,2,N,N) int32.  `injected` is None (in-kernel
+    Philox) or a dict of device tensors u, dphi (n_sweeps,chains,N,N) f64 and dn_fwd, dn_bwd
+    (n_sweeps,chains,2,N,N) int32 -- the reference's own draws, see generator.villain.
+    """
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    p_phi = _dev(phi, 'phi', (torch.float64, torch.float32))
+    p_n = _dev(n, 'n', (torch.int32,), (chains, 2, N, N))
+    if W != W or W == float('inf') or int(W) != W:
+        raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W (the reference yields nan for W=inf, '
+                         'neighborhood.py:105)')
+    if injected is None:
+        rng_mode, pu, pd, pf, pb = RNG_PHILOX, None, None, None, None
+    else:
+        rng_mode = RNG_INJECTED
+        arithmetic = 'strict'
+        pu = _dev(injected['u'], 'injected[u]', (torch.float64,), (n_sweeps, chains, N, N))
+        pd = _dev(injected['dphi'], 'injected[dphi]', (torch.float64,), (n_sweeps, chains, N, N))
+        pf = _dev(injected['dn_fwd'], 'injected[dn_fwd]', (torch.int32,), (n_sweeps, chains, 2, N, N))
+        pb = _dev(injected['dn_bwd'], 'injected[dn_bwd]', (torch.int32,), (n_sweeps, chains, 2, N, N))
+    code = lib.svb_villain_sweep(
+        p_phi, _DTYPES[phi.dtype], p_n, chains, N, float(kappa),
+        _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(W),
+        float(interval_phi), int(interval_n), int(n_sweeps), int(seed) & (2**64 - 1), int(sweep0), int(chain0),
+        rng_mode, _ARITH[arithmetic], _PATHS[path], pu, pd, pf, pb,
+        _opt(obs, 'obs', (torch.float64,), (chains, VOBS_COUNT)),
+        _opt(accept_mask, 'accept_mask', (torch.uint8,), (chains, N, N)),
+        _opt(dS_out, 'dS_out', (torch.float64,), (chains, N, N)),
+        _stream())
+    _lib.check(code)
+
+
+def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
+    """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    if obs is None:
+        obs = torch.empty((chains, VOBS_COUNT), dtype=torch.float64, device=phi.device)
+    code = lib.svb_villain_observables(
+        _dev(phi, 'phi', (torch.float64, torch.float32)), _DTYPES[phi.dtype],
+        _dev(n, 'n', (torch.int32,), (chains, 2, N, N)), chains, N, float(kappa),
+        _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)),
+        _dev(obs, 'obs', (torch.float64,), (chains, VOBS_COUNT)), _stream())
+    _lib.check(code)
+    return obs
+
+
+def worldline_sweep(m, v, kappa, *, W=1, mode='joint', interval=1, n_sweeps=1, seed=0, sweep0=0, chain0=0,
+                    injected=None, path='auto', kappa_chain=None, obs=None, accept_mask=None, dS_out=None):
+    """`n_sweeps` checkerboard plaquette sweeps on every chain, in place (svb_worldline_sweep).
+
+    m (chains,2,N,N) int32, v (chains,1,N,N) int32.  mode: 'joint' (PlaquetteUpdate's move),
+    'vortex' (v only) or 'coexact' (m only).  `injected`: dict of u (n_sweeps,chains,N,N) f64,
+    a (same shape) int32 and, for 'joint', b.
+    """
+    lib = _lib.load()
+    chains, N = _fields_shape(m, 'm', 2)
+    p_m = _dev(m, 'm', (torch.int32,))
+    p_v = _dev(v, 'v', (torch.int32,), (chains, 1, N, N))
+    if W != W or W == float('inf') or int(W) != W:
+        raise ValueError('the GPU worldline sweep needs a finite integer W (integer-valued v)')
+    if injected is None:
+        rng_mode, pu, pa, pb = RNG_PHILOX, None, None, None
+    else:
+        rng_mode = RNG_INJECTED
+        pu = _dev(injected['u'], 'injected[u]', (torch.float64,), (n_sweeps, chains, N, N))
+        pa = _dev(injected['a'], 'injected[a]', (torch.int32,), (n_sweeps, chains, N, N))
+        pb = _opt(injected.get('b'), 'injected[b]', (torch.int32,), (n_sweeps, chains, N, N))
+    code = lib.svb_worldline_sweep(
+        p_m, p_v, chains, N, float(kappa), _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(W),
+        _WL_MODES[mode], int(interval), int(n_sweeps), int(seed) & (2**64 - 1), int(sweep0), int(chain0),
+        rng_mode, _PATHS[path], pu, pa, pb,
+        _opt(obs, 'obs', (torch.float64,), (chains, WOBS_COUNT)),
+        _opt(accept_mask, 'accept_mask', (torch.uint8,), (chains, N, N)),
+        _opt(dS_out, 'dS_out', (torch.float64,), (chains, N, N)),
+        _stream())
+    _lib.check(code)
+
+
+def worldline_observables(m, v, *, W=1, obs=None):
+    lib = _lib.load()
+    chains, N = _fields_shape(m, 'm', 2)
+    if obs is None:
+        obs = torch.empty((chains, WOBS_COUNT), dtype=torch.float64, device=m.device)
+    code = lib.svb_worldline_observables(
+        _dev(m, 'm', (torch.int32,)), _dev(v, 'v', (torch.int32,), (chains, 1, N, N)), chains, N, int(W),
+        _dev(obs, 'obs', (torch.float64,), (chains, WOBS_COUNT)), _stream())
+    _lib.check(code)
+    return obs
+
+
+_OUT_COMPS = {('d', 0): 2, ('d', 1): 1, ('coface_sum', 0): 2, ('coface_sum', 1): 1,
+              ('delta', 1): 1, ('delta', 2): 2, ('face_sum', 1): 1, ('face_sum', 2): 2}
+_IN_COMPS = {0: 1, 1: 2, 2: 1}
+
+
+def form_op(op, degree, f, out=None):
+    """d / delta / face_sum / coface_sum of a batch of forms f (chains, C, N, N), dtype-preserving.
+
+    Returns None at the ends of the complex where the reference returns the scalar 0
+    (compact.py:999-1000, 1035-1036, 865-866, 888-889).
+    """
+    lib = _lib.load()
+    if op not in _OPS:
+        raise ValueError(f'unknown form operator {op!r}')
+    if (op, degree) not in _OUT_COMPS:
+        return None
+    chains, N = _fields_shape(f, 'f', _IN_COMPS[degree])
+    p_in = _dev(f, 'f', tuple(_DTYPES))
+    if out is None:
+        out = torch.empty((chains, _OUT_COMPS[(op, degree)], N, N), dtype=f.dtype, device=f.device)
+    p_out = _dev(out, 'out', (f.dtype,), (chains, _OUT_COMPS[(op, degree)], N, N))
+    _lib.check(lib.svb_form_op(_OPS[op], int(degree), _DTYPES[f.dtype], p_in, p_out, chains, N, _stream()))
+    return out
+
+
+def villain_spin_spin(phi, out=None):
+    """Spin_Spin.Villain for every chain -> complex128 (chains, N, N)."""
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    if out is None:
+        out = torch.empty((chains, N, N, 2), dtype=torch.float64, device=phi.device)
+    _lib.check(lib.svb_villain_spin_spin(_dev(phi, 'phi', (torch.float64, torch.float32)), _DTYPES[phi.dtype],
+                                         chains, N, _dev(out, 'out', (torch.float64,), (chains, N, N, 2)), _stream()))
+    return torch.view_as_complex(out)
+
+
+def villain_draws(chains, N, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, sweep=0, chain0=0, device='cuda'):
+    """The Philox draw mapping evaluated on the device (for tests): u, dphi (chains,N,N), dn (chains,4,N,N)."""
+    lib = _lib.load()
+    u = torch.empty((chains, N, N), dtype=torch.float64, device=device)
+    dphi = torch.empty_like(u)
+    dn = torch.empty((chains, 4, N, N), dtype=torch.int32, device=device)
+    _lib.check(lib.svb_villain_draws(chains, N, int(W), float(interval_phi), int(interval_n), int(seed) & (2**64 - 1),
+                                     int(sweep), int(chain0), u.data_ptr(), dphi.data_ptr(), dn.data_ptr(), _stream()))
+    return u, dphi, dn
+
+
+def philox4x32_10(ctr, key):
+    """One Philox4x32-10 block on the host (known-answer tests)."""
+    lib = _lib.load()
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib.svb_philox4x32_10_host(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out

@@ -45,3 +45,18 @@ def golden_villain_observables():
 @pytest.fixture(scope='session')
 def golden_lattice_forms():
     return load_golden('lattice_forms')
+
+
+@pytest.fixture(scope='session')
+def golden_worldline_checkerboard():
+    return load_golden('worldline_checkerboard')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_worldline_plaquette():
+    return load_golden('worldline_plaquette')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_worldline_observables():
+    return load_golden('worldline_observables')[0]

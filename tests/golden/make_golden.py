@@ -21,6 +21,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import refimport            # noqa: E402
 from oracle import villain_np           # noqa: E402
+from oracle import worldline_np         # noqa: E402
 
 sv = refimport.import_reference()
 Form = sv.lattice.Form
@@ -140,7 +141,106 @@ def lattice_forms():
     print('lattice_forms.npz:', i, 'cases')
 
 
+def _pack(cases, name):
+    out = {}
+    for i, rec in enumerate(cases):
+        for k, v in rec.items():
+            out[f'case{i}_{k}'] = np.asarray(v)
+    out['n_cases'] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(f'{name}.npz:', len(cases), 'cases')
+
+
+def _wl_random_cfg(L, seed):
+    """The construction of test/test_vortex_sparse.py:15-19 (m is NOT constrained there)."""
+    rng = np.random.default_rng(seed)
+    m = rng.integers(-3, 4, (2,) + L.dims)
+    v = rng.integers(-3, 4, (1,) + L.dims)
+    return m, v
+
+
+def worldline_checkerboard():
+    """VortexUpdate / CoexactUpdate chains: `step_reference` with rng = default_rng(99), 5 chained
+    steps, exactly the pattern of test/test_vortex_sparse.py:22-39 and test/test_coexact_sparse.py:25-39
+    (which also assert step == step_reference; re-checked here)."""
+    cases = []
+    for kind in ('vortex', 'coexact'):
+        for (N, W, kappa, interval) in [(4, 1, 0.5, 1), (5, 1, 0.5, 1), (5, 3, 0.5, 1), (8, 1, 0.5, 1), (8, 3, 0.3, 2),
+                                        (6, 2, 1.0, 1), (7, 2, 0.5, 1), (16, 1, 0.5, 1)]:
+            L = sv.lattice.Lattice2D(N)
+            S = sv.action.Worldline(L, kappa, W=W)
+            Gen = sv.generator.worldline.VortexUpdate if kind == 'vortex' else sv.generator.worldline.CoexactUpdate
+            dense, sparse = Gen(S, interval), Gen(S, interval)
+            dense.rng = np.random.default_rng(99); sparse.rng = np.random.default_rng(99)
+            replay = np.random.default_rng(99)
+            if kind == 'vortex':
+                m0, v0 = _wl_random_cfg(L, 10 * 2 + W)
+            else:
+                m0, v0 = worldline_np.hot_start(np.random.default_rng(N + W), N)
+            cfg = {'m': Form(m0, degree=1, lattice=L), 'v': Form(v0, degree=2, lattice=L)}
+            cfg_s = cfg
+            us, aa, ms, vs, acc, accp = [], [], [], [], [], []
+            for s in range(5):
+                draws = worldline_np.draw_checkerboard(replay, N, kind, interval)
+                before = (dense.accepted, dense.acceptance)
+                cfg = cfg | dense.step_reference(cfg)
+                cfg_s = cfg_s | sparse.step(cfg_s)
+                assert (np.asarray(cfg['m']) == np.asarray(cfg_s['m'])).all() and (np.asarray(cfg['v']) == np.asarray(cfg_s['v'])).all()
+                us.append(draws['u']); aa.append(draws['a'])
+                ms.append(np.asarray(cfg['m']).copy()); vs.append(np.asarray(cfg['v']).copy())
+                acc.append(int(dense.accepted - before[0])); accp.append(float(dense.acceptance - before[1]))
+            cases.append(dict(kind=kind, N=N, W=W, kappa=kappa, interval=interval, sweeps=5, m0=m0, v0=v0,
+                              u=np.array(us), a=np.array(aa), m=np.array(ms), v=np.array(vs),
+                              accepted=np.array(acc), acceptance=np.array(accp)))
+    _pack(cases, 'worldline_checkerboard')
+
+
+def worldline_plaquette():
+    """PlaquetteUpdate.step chains: np.random.seed(7) for the site permutation
+    (test/test_plaquette_update.py:31) and rng = default_rng(99) for the proposals."""
+    cases = []
+    for (N, W, kappa) in [(4, 1, 0.5), (5, 1, 0.5), (5, 2, 0.4), (8, 1, 0.5), (8, 3, 0.6)]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Worldline(L, kappa, W=W)
+        G = sv.generator.worldline.PlaquetteUpdate(S)
+        G.rng = np.random.default_rng(99)
+        np.random.seed(7)
+        m0, v0 = worldline_np.hot_start(np.random.default_rng(N * 10 + W), N)
+        cfg = {'m': Form(m0, degree=1, lattice=L), 'v': Form(v0, degree=2, lattice=L)}
+        ms, vs, acc, accp, act = [], [], [], [], []
+        for s in range(4):
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            assert S.valid(cfg)
+            ms.append(np.asarray(cfg['m']).copy()); vs.append(np.asarray(cfg['v']).copy())
+            acc.append(int(G.accepted - before[0])); accp.append(float(G.acceptance - before[1]))
+            act.append(float(S(cfg['m'], cfg['v'])))
+        cases.append(dict(N=N, W=W, kappa=kappa, sweeps=4, m0=m0, v0=v0, m=np.array(ms), v=np.array(vs),
+                          accepted=np.array(acc), acceptance=np.array(accp), action=np.array(act)))
+    _pack(cases, 'worldline_plaquette')
+
+
+def worldline_observables():
+    cases = []
+    for (N, kappa, W, seed) in [(4, 0.7, 1, 0), (5, 0.5, 2, 1), (8, 0.3, 3, 2), (32, 0.5, 1, 3), (64, 0.5, 1, 4)]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Worldline(L, kappa, W=W)
+        m, v = worldline_np.hot_start(np.random.default_rng(seed), N)
+        fm, fv = Form(m, degree=1, lattice=L), Form(v, degree=2, lattice=L)
+        O = sv.observable
+        lk = O.Links.Worldline(S, fm, fv)
+        cases.append(dict(N=N, kappa=kappa, W=W, m=m, v=v, action=float(S(fm, fv)), links=np.asarray(lk),
+                          ActionDensity=float(O.ActionDensity.Worldline(S, lk)),
+                          InternalEnergyDensity=float(O.InternalEnergyDensity.Worldline(S, lk)),
+                          InternalEnergyDensitySquared=float(O.InternalEnergyDensitySquared.Worldline(S, lk)),
+                          WindingSquared=float(O.WindingSquared.Worldline(S, lk)),
+                          TorusWrapping=np.asarray(O.TorusWrapping.Worldline(S, fm)),
+                          Vortex_Vortex=np.asarray(O.Vortex_Vortex.Worldline(S, fv))))
+    _pack(cases, 'worldline_observables')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms']
+    which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
+                             'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables']
     for name in which:
         globals()[name]()
