@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- site-updates/s of batched Villain Metropolis sweeps (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (N=1): BASELINE config 2 -- Villain (phi, n), L=32, kappa=0.5, 4096 independent chains on
+one B200, one checkerboard NeighborhoodUpdate sweep per step with the action / winding / wrapping
+reductions fused in.  With N GPUs every rank runs that workload on its own 4096 chains (weak
+scaling; chains are independent, there is no collective on the hot path; a final all_gather of
+the observable records runs outside the timed region).
+
+A step is ONE kernel launch.  The chain state (64 MiB) would fit the 126 MB L2, so the timed loop
+rotates over 4 independent chain sets (256 MiB): every step streams its set from HBM.
+
+One JSON line on stdout; see the task contract for the keys.  `--impl reference` times the CPU
+restatement of the reference's numpy algorithm (oracle/villain_np.py) on all host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'site-updates/sec (batched Villain Metropolis sweeps)'
+UNIT = 'site-updates/s'
+L, KAPPA, W_CONSTRAINT, CHAINS = 32, 0.5, 1, 4096
+BYTES_PER_SITE_UPDATE = 32          # fp64 phi + 2 x int32 n, one read + one write
+ROTATE = 4                           # chain sets rotated through so every step comes from HBM, not L2
+WORKLOAD = 'config2: Villain (phi,n) L=32 kappa=0.5 W=1, 4096 chains/GPU, NeighborhoodUpdate checkerboard sweep + action/winding/wrapping'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md, 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's port of the reference's numpy NeighborhoodUpdate, one chain per process
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, sweeps = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from oracle import villain_np as V
+    rng = np.random.default_rng(seed)
+    phi, n = V.hot_start(np.random.default_rng(1000 + seed), L)
+    phi, n = V.neighborhood_step(phi, n, KAPPA, W_CONSTRAINT, rng)       # untimed first sweep (imports, caches)
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        phi, n = V.neighborhood_step(phi, n, KAPPA, W_CONSTRAINT, rng)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(procs, sweeps):
+    """site-updates/s of `procs` processes each sweeping its own L=32 chain `sweeps` times (wall clock)."""
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(i, 1) for i in range(procs)])            # warm the pool
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i, sweeps) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    return procs * sweeps * L * L / wall, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    per_step = []
+    sweeps = 60
+    for _ in range(args.warmup):
+        cpu_reference_rate(cores, 5)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        rate, wall = cpu_reference_rate(cores, sweeps)
+        per_step.append((rate, wall))
+    total_wall = time.perf_counter() - t_all
+    value = float(np.mean([r for r, _ in per_step]))
+    sample = f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each per step (numpy port of neighborhood.py:59-137)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_wall / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'L': L, 'kappa': KAPPA, 'chains_per_gpu': CHAINS},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(self.samples[0][1]),
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import supervillain_b200 as svb
+    from supervillain_b200._lib import VOBS_COUNT
+    from supervillain_b200.generator.villain import NeighborhoodUpdate
+    from supervillain_b200.hostpath import HostStepper
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    S = svb.Villain(svb.Lattice2D(L), KAPPA, W=W_CONSTRAINT)
+    G = NeighborhoodUpdate(S, seed=20260101)
+    chain0 = rank * CHAINS                       # global chain ids: results do not depend on the GPU count
+    sets = []
+    for r in range(ROTATE):
+        E = svb.BatchedEnsemble(S, CHAINS, chain0=chain0)
+        sets.append(E._start('hot', 20260101 + 7919 * (rank * ROTATE + r)))
+    obs = torch.zeros((CHAINS, VOBS_COUNT), dtype=torch.float64, device=dev)
+
+    def step(k):
+        phi, n = sets[k % ROTATE]
+        G.sweep_device(phi, n, args.sweeps_per_step, obs=obs, chain0=chain0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    stop.record()
+    barrier()
+    ms = start.elapsed_time(stop)
+    if args.steps * (ms / max(args.steps, 1)) < 300:          # keep the sampler alive long enough to see the load
+        t_end = time.time() + 0.5
+        k = 0
+        while time.time() < t_end:
+            step(k); k += 1
+        torch.cuda.synchronize()
+    sampler.stop_flag.set()
+    sampler.join()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    updates_per_step = CHAINS * L * L * args.sweeps_per_step
+    value = world * updates_per_step * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the step IS one launch of villain_smem_kernel) ----
+    peak, peak_src = measured_peaks()
+    launch_s = (ms * 1e-3) / args.steps
+    achieved = BYTES_PER_SITE_UPDATE * CHAINS * L * L * args.sweeps_per_step / launch_s / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': args.traffic, 'kernel': 'villain_smem_kernel<double,false,false>',
+                'algorithmic_bytes_per_launch': BYTES_PER_SITE_UPDATE * CHAINS * L * L,
+                'peak_source': peak_src, 'sweeps_per_launch': args.sweeps_per_step}
+
+    # ---- end to end through the host-buffer API: H2D of the fields, sweep, D2H of fields + observables ----
+    stepper = HostStepper(G, CHAINS, chain0=chain0)
+    host_sets = [stepper.pinned_fields(from_device=s) for s in sets[:2]]
+    for k in range(2):
+        stepper.step(*host_sets[k % 2], n_sweeps=args.sweeps_per_step)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        stepper.step(*host_sets[k % 2], n_sweeps=args.sweeps_per_step)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * updates_per_step * e2e_steps / float(t.item())
+    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': stepper.h2d_bytes, 'd2h_bytes_per_step': stepper.d2h_bytes,
+           'steps': e2e_steps, 'api': 'HostStepper.step(phi_host, n_host): pinned host fields in and out + observables'}
+
+    # ---- final gather of observables (outside the timed region; the only inter-GPU traffic) ----
+    final = obs[:, 0].mean().reshape(1)
+    if world > 1:
+        gathered = [torch.zeros_like(final) for _ in range(world)]
+        dist.all_gather(gathered, final)
+        final = torch.cat(gathered)
+    mean_action_density = float(final.mean().item()) / (L * L)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            sweeps = 120
+            rate, wall = cpu_reference_rate(cores, sweeps)
+            cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each, {wall:.1f} s wall '
+                             f'(oracle/villain_np.py port of neighborhood.py:59-137)'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'L': L, 'kappa': KAPPA, 'W': W_CONSTRAINT, 'chains_per_gpu': CHAINS,
+                       'sweeps_per_step': args.sweeps_per_step, 'start': 'hot', 'rng': 'philox4x32-10 in-kernel',
+                       'l2': f'inputs larger than L2: {ROTATE} chain sets ({ROTATE * CHAINS * L * L * 16 >> 20} MiB) rotated',
+                       'parallelism': f'chains sharded over {world} GPU(s), no hot-path collective'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
+            'clocks': sampler.summary(), 'check': {'mean_action_density': mean_action_density},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='svb200', choices=['svb200', 'reference'])
+    ap.add_argument('--sweeps-per-step', type=int, default=1)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--traffic', type=float, default=None,
+                    help='dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun when asked for several GPUs directly
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

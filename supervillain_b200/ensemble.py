@@ -1,0 +1,224 @@
+"""`Ensemble` (the reference's per-chain driver) and `BatchedEnsemble` (thousands of resident chains).
+
+`Ensemble` mirrors supervillain/ensemble.py:17-336 for the calls on the hot path: `generate`,
+`continue_from`, `cut`, `every`, field access by attribute.  It advances ONE chain through the
+generator protocol, so any generator of this package -- or of the reference -- can drive it.
+
+`BatchedEnsemble` is the fast path the reference does not have: a chain
+axis.  All chains live in HBM for the whole run; one kernel launch advances every chain by
+`sweeps_per_step` sweeps and reduces the observables; only the per-chain observable record (a few
+doubles per chain) crosses PCIe per step, and configurations only at the stride asked for.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import VOBS_COUNT, WOBS_COUNT
+from .batch import Batch, Configurations
+from .generator.combining import KeepEvery
+from .generator.villain import villain_inline_values
+from .generator.worldline import worldline_inline_values
+from .lattice import Form
+
+
+def _no_op(x, **kwargs):
+    return x
+
+
+class Ensemble:
+    """An ensemble of configurations of one Markov chain, importance-sampled according to `action`."""
+
+    def __init__(self, action):
+        self.Action = action
+
+    def from_configurations(self, configurations):
+        self.configuration = configurations
+        return self
+
+    def generate(self, steps, generator, start='cold', progress=_no_op, starting_index=0, index_stride=1):
+        self.configuration = self.Action.configurations(steps)
+        self.configuration |= generator.inline_observables(steps)
+        self.index_stride = index_stride
+        self.index = Batch(starting_index + index_stride * np.arange(steps))
+        self.weight = Batch(np.ones(steps))
+        if isinstance(start, str) and start == 'cold':
+            seed = self.Action.configurations(1)[0]
+        elif type(start) is dict:
+            seed = start
+        else:
+            raise ValueError(f'Not sure how to transform a {type(start)} into a starting configuration.')
+        self.configuration[0] = generator.step(seed)
+        for k in progress(range(1, steps), desc='Generation'):
+            self.configuration[k] = generator.step(self.configuration[k - 1])
+        self.start = start
+        self.generator = generator
+        return self
+
+    @classmethod
+    def continue_from(cls, ensemble, steps, progress=_no_op):
+        if not isinstance(ensemble, Ensemble):
+            raise ValueError('ensemble should be a supervillain_b200.Ensemble.')
+        try:
+            generator, action = ensemble.generator, ensemble.Action
+            last = ensemble.configuration[-1]
+            index = ensemble.index[-1] + ensemble.index_stride
+        except Exception:
+            raise ValueError('The ensemble must provide a generator, an Action, and at least one configuration.')
+        return Ensemble(action).generate(steps, generator, last, progress=progress, starting_index=index,
+                                         index_stride=ensemble.index_stride)
+
+    def __len__(self):
+        return len(self.configuration)
+
+    def _sub(self, sl, stride=1):
+        e = Ensemble(self.Action).from_configurations(self.configuration[sl])
+        e.index = self.index[sl]
+        e.index_stride = self.index_stride * stride
+        e.weight = self.weight[sl]
+        return e
+
+    def cut(self, start):
+        e = self._sub(slice(start, None))
+        e.generator = self.generator
+        return e
+
+    def every(self, stride):
+        e = self._sub(slice(None, None, stride), stride)
+        e.generator = KeepEvery(stride, self.generator, blocked_inline=False)
+        return e
+
+    def __getattr__(self, name):
+        if name in ('configuration', 'Action'):
+            raise AttributeError(name)
+        try:
+            return getattr(self.configuration, name)
+        except AttributeError:
+            raise AttributeError(name) from None
+
+
+class BatchedEnsemble:
+    """`chains` independent Markov chains of one action, resident on one GPU.
+
+    >>> S = Villain(Lattice2D(32), kappa=0.5)
+    >>> E = BatchedEnsemble(S, chains=4096).generate(1000, NeighborhoodUpdate(S), start='cold', sweeps_per_step=10)
+    >>> E.ActionDensity.shape      # (chains, steps)
+    """
+
+    def __init__(self, action, chains, *, device=None, dtype=torch.float64, chain0=0):
+        self.Action = action
+        self.chains = int(chains)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = dtype
+        self.chain0 = int(chain0)      # global id of the first chain: shards of one job draw disjoint Philox streams
+        self.kind = type(action).__name__
+        if self.kind not in ('Villain', 'Worldline'):
+            raise ValueError('BatchedEnsemble needs a Villain or Worldline action')
+        self.fields = None
+
+    # -- starting configurations ---------------------------------------------------------------
+    def _start(self, start, seed):
+        N, C = self.Action.Lattice.N, self.chains
+        dev = self.device
+        if isinstance(start, dict):
+            keys = ('phi', 'n') if self.kind == 'Villain' else ('m', 'v')
+            comps = (1, 2) if self.kind == 'Villain' else (2, 1)
+            out = []
+            for key, comp in zip(keys, comps):
+                dt = self.dtype if key == 'phi' else torch.int32
+                t = start[key] if isinstance(start[key], torch.Tensor) else torch.from_numpy(np.ascontiguousarray(start[key]))
+                if t.dim() == 3:
+                    t = t[None].expand(C, comp, N, N)
+                if tuple(t.shape) != (C, comp, N, N):
+                    raise ValueError(f'start[{key!r}] must have shape ({C}, {comp}, {N}, {N}) or ({comp}, {N}, {N})')
+                out.append(t.to(device=dev, dtype=dt).contiguous().clone())
+            return tuple(out)
+        if start == 'cold':
+            if self.kind == 'Villain':
+                return (torch.zeros((C, 1, N, N), dtype=self.dtype, device=dev),
+                        torch.zeros((C, 2, N, N), dtype=torch.int32, device=dev))
+            return (torch.zeros((C, 2, N, N), dtype=torch.int32, device=dev),
+                    torch.zeros((C, 1, N, N), dtype=torch.int32, device=dev))
+        if start == 'hot':
+            # synthetic hot start of SURVEY.md 8(d): phi ~ U(-pi, pi), n ~ integers(-2, 3);
+            # worldline: m = delta t with t ~ integers(-2, 3) (so delta m = 0), v ~ integers(-2, 3)
+            g = torch.Generator(device=dev)
+            g.manual_seed(int(seed))
+            if self.kind == 'Villain':
+                phi = (torch.rand((C, 1, N, N), generator=g, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+                n = torch.randint(-2, 3, (C, 2, N, N), generator=g, device=dev, dtype=torch.int32)
+                return phi.to(self.dtype), n
+            t = torch.randint(-2, 3, (C, 1, N, N), generator=g, device=dev, dtype=torch.int32)
+            m = ops.form_op('delta', 2, t)
+            v = torch.randint(-2, 3, (C, 1, N, N), generator=g, device=dev, dtype=torch.int32)
+            return m, v
+        raise ValueError(f'Not sure how to transform {start!r} into a starting configuration.')
+
+    # -- generation ----------------------------------------------------------------------------
+    def generate(self, steps, generator, start='cold', *, sweeps_per_step=1, keep_every=0, start_seed=0,
+                 kappa_chain=None, progress=_no_op):
+        """Advance every chain `steps` times by `sweeps_per_step` sweeps.
+
+        keep_every: 0 keeps no configurations (observables only); k > 0 copies the fields to the host
+        every k-th step into reference-layout columns `(chain, draw, C, N, N)`.
+        kappa_chain: optional per-chain couplings (kappa scans), device or host array of length `chains`.
+        """
+        if self.fields is None or start != 'continue':
+            self.fields = self._start(start, start_seed)
+        if kappa_chain is not None and not isinstance(kappa_chain, torch.Tensor):
+            kappa_chain = torch.as_tensor(np.asarray(kappa_chain, dtype=np.float64))
+        if kappa_chain is not None:
+            kappa_chain = kappa_chain.to(device=self.device, dtype=torch.float64).contiguous()
+        self.kappa_chain = kappa_chain
+        nobs = VOBS_COUNT if self.kind == 'Villain' else WOBS_COUNT
+        record = torch.empty((steps, self.chains, nobs), dtype=torch.float64, device=self.device)
+        kept = []
+        a, b = self.fields
+        for k in progress(range(steps), desc='Generation'):
+            generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
+            if keep_every and (k + 1) % keep_every == 0:
+                kept.append((a.cpu().numpy(), b.cpu().numpy()))
+        self.record = record.cpu().numpy().transpose(1, 0, 2)          # (chains, steps, nobs): ONE D2H
+        self.steps = steps
+        self.sweeps_per_step = sweeps_per_step
+        self.generator = generator
+        self.index = sweeps_per_step * (1 + np.arange(steps))
+        if kept:
+            names = ('phi', 'n') if self.kind == 'Villain' else ('m', 'v')
+            self.configuration = {
+                names[0]: np.stack([x[0] for x in kept], axis=1),
+                names[1]: np.stack([x[1] for x in kept], axis=1).astype(np.int64),
+            }
+        N = self.Action.Lattice.N
+        kappa = self.Action.kappa if kappa_chain is None else kappa_chain.cpu().numpy()[:, None]
+        values = villain_inline_values if self.kind == 'Villain' else worldline_inline_values
+        self.observables = values(self.record, N, kappa)
+        sites = N * N
+        generator.sweeps += steps * sweeps_per_step * self.chains
+        generator.proposed += sites * steps * sweeps_per_step * self.chains
+        generator.accepted += int(round(float(self.record[..., 4].sum())))
+        generator.acceptance += float(self.record[..., 5].sum()) / (1 if str(generator) == 'PlaquetteUpdate' else sites)
+        return self
+
+    def __getattr__(self, name):
+        obs = self.__dict__.get('observables')
+        if obs is not None and name in obs:
+            return obs[name]
+        raise AttributeError(name)
+
+    def chain(self, c):
+        """Chain `c` as a reference-layout `Ensemble` (needs keep_every > 0): fields `(draw, C, N, N)` Batches
+        plus the inline observable columns, exactly what `Ensemble.generate` would have stored."""
+        if 'configuration' not in self.__dict__:
+            raise ValueError('no configurations were kept; call generate(..., keep_every=k)')
+        L = self.Action.Lattice
+        degree = {'phi': 0, 'n': 1, 'm': 1, 'v': 2}
+        cols = {k: Batch(v[c], cls=Form, degree=degree[k], lattice=L) for k, v in self.configuration.items()}
+        stride = self.steps // len(next(iter(cols.values())))
+        for name, v in self.observables.items():
+            cols[name] = Batch(v[c][stride - 1::stride])
+        e = Ensemble(self.Action).from_configurations(Configurations(cols))
+        e.index = Batch(self.index[stride - 1::stride])
+        e.index_stride = stride * self.sweeps_per_step
+        e.weight = Batch(np.ones(len(e.index)))
+        e.generator = self.generator
+        return e

@@ -1,0 +1,48 @@
+"""Replay of the reference generators' numpy RNG call sequences into dense per-site arrays.
+
+When a user assigns `generator.rng = np.random.default_rng(seed)` -- the reference's own seam,
+test/test_vortex_sparse.py:31-32 -- the GPU generators draw from that numpy Generator with exactly
+the calls, in exactly the order, the reference makes, scatter the 1-D draw vectors to the sites
+that consume them, and hand the dense arrays to the kernels (SVB_RNG_INJECTED).  The chain
+produced is then the reference's chain.  This is host bookkeeping of random numbers, not a
+compute path: dS, accept/reject and the field updates all happen in the kernels.
+"""
+import numpy as np
+
+
+def villain_neighborhood(rng, lattice, W, interval_phi, interval_n):
+    """One sweep of NeighborhoodUpdate draws (neighborhood.py:87, 98, 104-107)."""
+    N = lattice.N
+    n_changes = np.arange(-interval_n, 1 + interval_n)
+    u = rng.uniform(0, 1, (N,) * 2)
+    dphi = np.zeros((N, N))
+    dn_fwd = np.zeros((2, N, N), dtype=np.int32)
+    dn_bwd = np.zeros((2, N, N), dtype=np.int32)
+    for color in lattice.checkerboarding:
+        count = len(color[0])
+        dphi[color] = rng.uniform(-interval_phi, +interval_phi, count)
+        for mu in range(2):
+            dn_fwd[mu][color] = W * rng.choice(n_changes, count)
+            dn_bwd[mu][color] = W * rng.choice(n_changes, count)
+    return u, dphi, dn_fwd, dn_bwd
+
+
+def _nonzero_choices(interval):
+    return tuple(range(-interval, 0)) + tuple(range(1, interval + 1))
+
+
+def worldline_checkerboard(rng, lattice, mode, interval=1):
+    """One sweep of VortexUpdate (vortex.py:84, 98-105) or CoexactUpdate (coexact.py:89, 96-99) draws;
+    for 'joint' (no reference counterpart in checkerboard order): u, then per colour dm, dv."""
+    N = lattice.N
+    u = rng.uniform(0, 1, (1, N, N))[0]
+    a = np.zeros((N, N), dtype=np.int32)
+    b = np.zeros((N, N), dtype=np.int32)
+    for color in lattice.checkerboarding:
+        count = len(color[0])
+        if mode == 'joint':
+            a[color] = rng.choice([-1, +1], count)
+            b[color] = rng.choice([-1, 0, +1], count)
+        else:
+            a[color] = rng.choice(_nonzero_choices(interval), count)
+    return u, a, b

@@ -1,0 +1,153 @@
+"""`NeighborhoodUpdate` on the GPU, drop-in for supervillain.generator.villain.NeighborhoodUpdate
+(supervillain/generator/villain/neighborhood.py:12-150)."""
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import VOBS_ACCEPTANCE, VOBS_ACCEPTED, VOBS_ACTION, VOBS_COUNT, VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1
+from ..action import to_device
+from ..batch import Batch
+from ..lattice import Form
+from . import _replay
+from .generator import Generator, fresh_seed
+
+INLINE_NAMES = ('ActionDensity', 'InternalEnergyDensity', 'InternalEnergyDensitySquared', 'WindingSquared',
+                'TorusWrapping', 'WrappingSquared')
+
+
+def _is_villain(action):
+    return type(action).__name__ == 'Villain' and all(hasattr(action, a) for a in ('Lattice', 'kappa', 'W'))
+
+
+def villain_inline_values(rec, N, kappa):
+    """Reference observables (observable/{action,energy,winding,wrapping}.py) from a per-chain device record."""
+    sites = N * N
+    S = rec[..., VOBS_ACTION]
+    wrap = np.stack([rec[..., VOBS_WRAP0], rec[..., VOBS_WRAP1]], axis=-1)
+    return {
+        'ActionDensity': S / sites,
+        'InternalEnergyDensity': S / (sites * kappa),
+        'InternalEnergyDensitySquared': (S / (sites * kappa)) ** 2,
+        'WindingSquared': rec[..., VOBS_SUM_DN2] / sites,
+        'TorusWrapping': np.rint(wrap).astype(np.int64),
+        'WrappingSquared': (wrap ** 2).sum(axis=-1),
+    }
+
+
+class NeighborhoodUpdate(Generator):
+    r"""Checkerboard Metropolis on (phi_x, the four n touching x), every chain of a batch at once.
+
+    Same constructor, attributes and `step`/`report` contract as the reference class.  Extras:
+
+    rng
+        `None` (default): proposals come from the in-kernel Philox4x32-10 stream keyed by `seed`.
+        Assign a `numpy.random.Generator` -- as the reference's tests do -- and the numpy draws are
+        replayed in the reference's order and injected, reproducing the reference chain bit for bit.
+    inline
+        names from `INLINE_NAMES` to return as inline observables (observable/observable.py:49-54).
+    """
+
+    def __init__(self, action, interval_phi=np.pi, interval_n=1, *, seed=None, inline=(), arithmetic='fast',
+                 path='auto', dtype=torch.float64):
+        if not _is_villain(action):
+            raise ValueError('The Neighborhood Metropolis update requires the Villain action.')
+        self.Action = action
+        self.Lattice = action.Lattice
+        self.kappa = action.kappa
+        self.interval_phi = interval_phi
+        self.interval_n = interval_n
+        self.rng = None
+        self.seed = fresh_seed() if seed is None else int(seed)
+        self.counter = 0               # Philox sweep counter: resume = (seed, counter)
+        self.arithmetic = arithmetic
+        self.path = path
+        self.dtype = dtype
+        unknown = set(inline) - set(INLINE_NAMES)
+        if unknown:
+            raise ValueError(f'unknown inline observables {sorted(unknown)}')
+        self.inline = tuple(inline)
+        self.n_changes = np.arange(-interval_n, 1 + interval_n)
+        self.accepted = 0
+        self.proposed = 0
+        self.acceptance = 0.
+        self.sweeps = 0
+
+    def __str__(self):
+        return 'NeighborhoodUpdate'
+
+    # -- device API -------------------------------------------------------------------------
+    def sweep_device(self, phi, n, n_sweeps=1, *, obs=None, chain0=0, kappa_chain=None, injected=None,
+                     accept_mask=None, dS_out=None):
+        """`n_sweeps` sweeps in place on device tensors phi (chains,1,N,N), n (chains,2,N,N) int32."""
+        ops.villain_sweep(phi, n, self.kappa, W=self.Action.W, interval_phi=self.interval_phi,
+                          interval_n=self.interval_n, n_sweeps=n_sweeps, seed=self.seed, sweep0=self.counter,
+                          chain0=chain0, injected=injected, arithmetic=self.arithmetic, path=self.path,
+                          kappa_chain=kappa_chain, obs=obs, accept_mask=accept_mask, dS_out=dS_out)
+        if injected is None:
+            self.counter += n_sweeps
+
+    def _injected_draws(self, chains, n_sweeps):
+        L, W = self.Lattice, self.Action.W
+        N = L.N
+        u = np.empty((n_sweeps, chains, N, N)); dphi = np.empty_like(u)
+        dn_fwd = np.empty((n_sweeps, chains, 2, N, N), dtype=np.int32); dn_bwd = np.empty_like(dn_fwd)
+        for c in range(chains):              # chain-major: chain c consumes its n_sweeps sweeps consecutively
+            for s in range(n_sweeps):
+                u[s, c], dphi[s, c], dn_fwd[s, c], dn_bwd[s, c] = _replay.villain_neighborhood(
+                    self.rng, L, W, self.interval_phi, self.interval_n)
+        return {k: torch.from_numpy(v).cuda() for k, v in
+                dict(u=u, dphi=dphi, dn_fwd=dn_fwd, dn_bwd=dn_bwd).items()}
+
+    def _count(self, rec, chains, n_sweeps):
+        sites = self.Lattice.sites
+        self.sweeps += n_sweeps * chains
+        self.proposed += sites * n_sweeps * chains
+        self.accepted += int(round(float(rec[:, VOBS_ACCEPTED].sum())))
+        self.acceptance += float(rec[:, VOBS_ACCEPTANCE].sum()) / sites
+
+    # -- reference protocol -----------------------------------------------------------------
+    def step(self, cfg, n_sweeps=1):
+        r"""A volume's worth of single-site updates (`n_sweeps` of them) on cfg['phi'], cfg['n'].
+
+        cfg holds one configuration -- phi (1,N,N), n (2,N,N) -- or a batch with a leading chain axis.
+        Returns `cfg | {'phi': ..., 'n': ...}` as float64 / int64 `Form`s like the reference (:137).
+        """
+        N = self.Lattice.N
+        phi, single = to_device(cfg['phi'], self.dtype, 1, N)
+        n, _ = to_device(cfg['n'], torch.int32, 2, N)
+        if not isinstance(cfg['phi'], torch.Tensor):
+            pass
+        else:
+            phi, n = phi.clone(), n.clone()     # reference copy semantics (:84-85)
+        chains = phi.shape[0]
+        injected = self._injected_draws(chains, n_sweeps) if self.rng is not None else None
+        obs = torch.empty((chains, VOBS_COUNT), dtype=torch.float64, device=phi.device)
+        self.sweep_device(phi, n, n_sweeps, obs=obs, injected=injected)
+        rec = obs.cpu().numpy()
+        self._count(rec, chains, n_sweeps)
+        out_phi = phi.to(torch.float64).cpu().numpy()
+        out_n = n.cpu().numpy().astype(np.int64)
+        L = self.Lattice
+        if single:
+            result = {'phi': Form(out_phi[0], degree=0, lattice=L), 'n': Form(out_n[0], degree=1, lattice=L)}
+        else:
+            result = {'phi': out_phi, 'n': out_n}
+        if self.inline:
+            vals = villain_inline_values(rec, N, self.kappa)
+            for name in self.inline:
+                result[name] = vals[name][0] if single else vals[name]
+        return cfg | result
+
+    def inline_observables(self, steps):
+        shapes = {'TorusWrapping': (2,)}
+        dtypes = {'TorusWrapping': int}
+        return {name: Batch(steps, shape=shapes.get(name, ()), dtype=dtypes.get(name, float)) for name in self.inline}
+
+    def report(self):
+        return (
+            f'There were {self.accepted} neighborhood proposals accepted of {self.proposed} proposed updates.'
+            + '\n' +
+            f'    {self.accepted/self.proposed:.6f} acceptance rate'
+            + '\n' +
+            f'    {self.acceptance / self.sweeps:.6f} average Metropolis acceptance probability.'
+        )

@@ -1,0 +1,115 @@
+"""Form operators, action and observables on the GPU against the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lattice_np as lat
+from oracle import villain_np as V
+
+pytestmark = pytest.mark.gpu
+
+import supervillain_b200 as svb                      # noqa: E402
+from supervillain_b200 import ops                    # noqa: E402
+from supervillain_b200.generator.villain import villain_inline_values   # noqa: E402
+
+
+def test_form_operators_bitexact_vs_reference(golden_lattice_forms):
+    """d, delta, face_sum, coface_sum == the reference's results with `==` (test/test_lattice_kernels.py:17-34),
+    dtype preserved (test/test_field_dtypes.py:11-31), scalar 0 at the ends of the complex (:37-42)."""
+    cases, _ = golden_lattice_forms
+    for c in cases:
+        N, p = int(c['N']), int(c['p'])
+        L = svb.Lattice2D(N)
+        F = svb.Form(c['in'], degree=p, lattice=L)
+        for name, fn in (('d', svb.d), ('delta', svb.delta), ('face_sum', lambda f: f.face_sum()),
+                         ('coface_sum', lambda f: f.coface_sum())):
+            got = fn(F)
+            if name in c:
+                assert isinstance(got, svb.Form) and got.dtype == c[name].dtype
+                assert (np.asarray(got) == c[name]).all(), (name, p, N)
+            else:
+                assert isinstance(got, int) and got == 0
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32, torch.int32, torch.int64])
+def test_form_operators_batched_all_dtypes(dtype):
+    N, chains = 12, 5
+    rng = np.random.default_rng(0)
+    for p, C in ((0, 1), (1, 2), (2, 1)):
+        if dtype.is_floating_point:
+            a = rng.uniform(-3, 3, (chains, C, N, N))
+        else:
+            a = rng.integers(-9, 10, (chains, C, N, N))
+        t = torch.from_numpy(a).to(dtype).cuda()
+        for op in ('d', 'delta', 'face_sum', 'coface_sum'):
+            out = ops.form_op(op, p, t)
+            if (op, p) in lat._OPS:
+                ref = lat.form_op(op, p, t.cpu().numpy())
+                assert out.dtype == dtype and (out.cpu().numpy() == ref).all(), (op, p, dtype)
+            else:
+                assert out is None
+
+
+def test_exterior_calculus_identities():
+    """d^2 = 0, delta^2 = 0, <d a, b> = <a, delta b> (test/test_lattice.py) on integer forms, exactly."""
+    N, chains = 16, 8
+    rng = np.random.default_rng(1)
+    a = torch.from_numpy(rng.integers(-5, 6, (chains, 1, N, N))).cuda()
+    b = torch.from_numpy(rng.integers(-5, 6, (chains, 2, N, N))).cuda()
+    v = torch.from_numpy(rng.integers(-5, 6, (chains, 1, N, N))).cuda()
+    assert (ops.form_op('d', 1, ops.form_op('d', 0, a)) == 0).all()
+    assert (ops.form_op('delta', 1, ops.form_op('delta', 2, v)) == 0).all()
+    assert ((ops.form_op('d', 0, a) * b).sum() == (a * ops.form_op('delta', 1, b)).sum()).item()
+    assert ((ops.form_op('d', 1, b) * v).sum() == (b * ops.form_op('delta', 2, v)).sum()).item()
+
+
+def test_villain_action_and_observables_match_reference(golden_villain_observables):
+    for c in golden_villain_observables:
+        N, kappa = int(c['N']), float(c['kappa'])
+        S = svb.Villain(svb.Lattice2D(N), kappa)
+        assert S(c['phi'], c['n']) == pytest.approx(float(c['action']), rel=1e-12)
+        assert (np.asarray(S.links(svb.Form(c['phi'], degree=0, lattice=S.Lattice), c['n'])) == c['links']).all()
+        vals = villain_inline_values(S.observables(c['phi'], c['n']).cpu().numpy()[0], N, kappa)
+        for name in ('ActionDensity', 'InternalEnergyDensity', 'InternalEnergyDensitySquared', 'WindingSquared',
+                     'WrappingSquared'):
+            assert vals[name] == pytest.approx(float(c[name]), rel=1e-12), name
+        assert (vals['TorusWrapping'] == c['TorusWrapping']).all()
+        phi = torch.from_numpy(c['phi'][None]).cuda()
+        C = ops.villain_spin_spin(phi).cpu().numpy()[0]
+        np.testing.assert_allclose(C, c['Spin_Spin'], rtol=0, atol=1e-12)
+        dn = ops.form_op('d', 1, torch.from_numpy(c['n'][None]).cuda()).cpu().numpy()[0]
+        assert (dn == c['dn']).all()
+
+
+def test_gauge_invariance_of_observables():
+    """phi -> phi + 2 pi k, n -> n + dk leaves every observable unchanged to 1e-12 (test/test_gauge-invariance.py)."""
+    N, kappa, chains = 16, 0.6, 4
+    rng = np.random.default_rng(3)
+    phi, n = V.hot_start(rng, N, chains)
+    k = rng.integers(-3, 4, (chains, 1, N, N))
+    phi2, n2 = phi + 2 * np.pi * k, n + lat.d0(k)
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    r1, r2 = S.observables(phi, n).cpu().numpy(), S.observables(phi2, n2).cpu().numpy()
+    np.testing.assert_allclose(r1[:, :2], r2[:, :2], rtol=1e-11)
+    assert (r1[:, 2:4] == r2[:, 2:4]).all()              # sum of dk vanishes on the torus
+    C1 = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    C2 = ops.villain_spin_spin(torch.from_numpy(phi2).cuda()).cpu().numpy()
+    np.testing.assert_allclose(C1, C2, atol=1e-12)
+
+
+def test_ensemble_reference_protocol_config1():
+    """BASELINE config 1: L=5 (odd: four colours), kappa=0.5, one chain, cold start, the call of test/end-to-end.py:53."""
+    S = svb.Villain(svb.Lattice2D(5), 0.5, W=1)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=5, inline=('ActionDensity', 'WindingSquared', 'TorusWrapping'))
+    E = svb.Ensemble(S).generate(200, G, 'cold')
+    assert np.asarray(E.phi).shape == (200, 1, 5, 5) and np.asarray(E.n).dtype == np.int64
+    assert len(E) == 200 and E.configuration.ActionDensity.shape == (200,)
+    k = 137
+    assert E.configuration.ActionDensity[k] == pytest.approx(float(V.action_density(np.asarray(E.phi[k]), np.asarray(E.n[k]), 0.5)), rel=1e-12)
+    assert E.configuration.WindingSquared[k] == pytest.approx(float(V.winding_squared(np.asarray(E.n[k]))), rel=1e-12)
+    assert (E.configuration.TorusWrapping[k] == V.torus_wrapping(np.asarray(E.n[k]))).all()
+    assert 'neighborhood proposals accepted of 5000 proposed updates' in G.report()
+    cut = E.cut(50).every(10)
+    assert len(cut) == 15 and cut.index_stride == 10
+    more = svb.Ensemble.continue_from(cut, 5)
+    assert len(more) == 5 and more.index[0] == cut.index[-1] + 10

@@ -1,0 +1,195 @@
+"""Parity of the CUDA Villain path (through the C ABI) with the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox_np as P
+from oracle import villain_np as V
+
+pytestmark = pytest.mark.gpu
+
+import supervillain_b200 as svb                      # noqa: E402
+from supervillain_b200 import ops                    # noqa: E402
+from supervillain_b200._lib import (VOBS_ACCEPTANCE, VOBS_ACCEPTED, VOBS_ACTION, VOBS_COUNT, VOBS_SUM_DN2,  # noqa: E402
+                                    VOBS_WRAP0, VOBS_WRAP1)
+from supervillain_b200.generator.villain import NeighborhoodUpdate   # noqa: E402
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+@pytest.mark.parametrize('path', ['smem', 'global'])
+def test_injected_rng_reproduces_reference_chain(golden_villain_neighborhood, path):
+    """Level 1: the reference's own numpy draws injected -> n, phi and accept counts identical to the
+    reference's NeighborhoodUpdate.step, sweep after sweep (golden generated with rng=default_rng(99))."""
+    for c in golden_villain_neighborhood:
+        N, kappa, W = int(c['N']), float(c['kappa']), int(c['W'])
+        S = svb.Villain(svb.Lattice2D(N), kappa, W=W)
+        G = NeighborhoodUpdate(S, path=path)
+        G.rng = np.random.default_rng(99)
+        cfg = {'phi': c['phi0'], 'n': c['n0']}
+        for s in range(int(c['sweeps'])):
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            assert np.asarray(cfg['n']).dtype == np.int64 and np.asarray(cfg['phi']).dtype == np.float64
+            assert (np.asarray(cfg['n']) == c['n'][s]).all(), (N, kappa, W, s)
+            assert (np.asarray(cfg['phi']) == c['phi'][s]).all(), (N, kappa, W, s)      # bitwise
+            assert G.accepted - before[0] == int(c['accepted'][s])
+            assert G.acceptance - before[1] == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
+            assert float(S(cfg['phi'], cfg['n'])) == pytest.approx(float(c['action'][s]), rel=1e-12)
+
+
+def test_dS_and_accept_mask_match_oracle(golden_villain_neighborhood):
+    """Level 2: dS of every proposal within 1e-12 (relative, fp64) of the oracle, same accept mask."""
+    for c in golden_villain_neighborhood[:9]:
+        N, kappa, W = int(c['N']), float(c['kappa']), int(c['W'])
+        draws = {k: c[k][0] for k in ('u', 'dphi', 'dn_fwd', 'dn_bwd')}
+        dS_ref = np.zeros((N, N)); mask_ref = np.zeros((N, N), dtype=bool)
+        V.neighborhood_step_dense(c['phi0'], c['n0'], kappa, draws, accept_mask=mask_ref, dS_out=dS_ref)
+        phi, n = dev(c['phi0'][None]), dev(c['n0'][None], torch.int32)
+        inj = {'u': dev(draws['u'][None, None]), 'dphi': dev(draws['dphi'][None, None]),
+               'dn_fwd': dev(draws['dn_fwd'][None, None], torch.int32), 'dn_bwd': dev(draws['dn_bwd'][None, None], torch.int32)}
+        mask = torch.zeros((1, N, N), dtype=torch.uint8, device='cuda')
+        dS = torch.zeros((1, N, N), dtype=torch.float64, device='cuda')
+        ops.villain_sweep(phi, n, kappa, W=W, injected=inj, accept_mask=mask, dS_out=dS)
+        assert (mask.cpu().numpy()[0].astype(bool) == mask_ref).all()
+        # the kernel recomputes r from the current fields where the reference carries it incrementally
+        # (neighborhood.py:129): identical up to a few ulp of r, i.e. ~1e-15 of the terms of dS
+        np.testing.assert_allclose(dS.cpu().numpy()[0], dS_ref, rtol=1e-12, atol=1e-12)
+
+
+def oracle_philox_chain(phi, n, kappa, W, seed, chain, sweep0, sweeps, interval_phi=np.pi, interval_n=1):
+    stats_all = []
+    for s in range(sweeps):
+        draws = P.villain_draws(seed, chain, sweep0 + s, phi.shape[-1], W=W, interval_phi=interval_phi, interval_n=interval_n)
+        st = {}
+        phi, n = V.neighborhood_step_dense(phi, n, kappa, draws, stats=st)
+        stats_all.append(st)
+    return phi, n, stats_all
+
+
+def test_philox_draw_mapping_matches_oracle():
+    for (N, W, I, seed, sweep, chain0) in [(8, 1, 1, 1, 0, 0), (5, 2, 1, 2**40 + 17, 3, 5), (16, 1, 3, 99, 2**33 + 1, 2**32 + 3)]:
+        u, dphi, dn = ops.villain_draws(3, N, W=W, interval_n=I, seed=seed, sweep=sweep, chain0=chain0)
+        for c in range(3):
+            ref = P.villain_draws(seed, chain0 + c, sweep, N, W=W, interval_n=I)
+            assert (u[c].cpu().numpy() == ref['u']).all()
+            assert (dphi[c].cpu().numpy() == ref['dphi']).all()
+            got = dn[c].cpu().numpy()
+            assert (got[0] == ref['dn_fwd'][0]).all() and (got[1] == ref['dn_bwd'][0]).all()
+            assert (got[2] == ref['dn_fwd'][1]).all() and (got[3] == ref['dn_bwd'][1]).all()
+
+
+@pytest.mark.parametrize('path', ['smem', 'global'])
+@pytest.mark.parametrize('arith', ['strict', 'fast'])
+@pytest.mark.parametrize('N,W,kappa', [(4, 1, 0.5), (5, 1, 0.3), (8, 2, 0.2), (7, 1, 0.1), (16, 1, 0.05), (32, 1, 0.5)])
+def test_philox_mode_matches_oracle_replay(path, arith, N, W, kappa):
+    """The production RNG path: regenerate the kernel's Philox draws with the oracle's independent
+    Philox, run the restated reference algorithm on them, demand identical fields."""
+    chains, sweeps, seed, chain0, sweep0 = 3, 3, 20260101, 11, 5
+    phi0, n0 = V.hot_start(np.random.default_rng(N), N, chains)
+    n0 = n0 * W
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, W=W, n_sweeps=sweeps, seed=seed, sweep0=sweep0, chain0=chain0,
+                      arithmetic=arith, path=path, obs=obs)
+    rec = obs.cpu().numpy()
+    for c in range(chains):
+        p_ref, n_ref, st = oracle_philox_chain(phi0[c], n0[c], kappa, W, seed, chain0 + c, sweep0, sweeps)
+        assert (n[c].cpu().numpy() == n_ref).all()
+        assert (phi[c].cpu().numpy() == p_ref).all()
+        assert rec[c, VOBS_ACCEPTED] == sum(s['accepted'] for s in st)
+        assert rec[c, VOBS_ACCEPTANCE] == pytest.approx(sum(s['acceptance'] for s in st), rel=1e-12)
+        assert rec[c, VOBS_ACTION] == pytest.approx(float(V.action(p_ref, n_ref, kappa)), rel=1e-12)
+        assert rec[c, VOBS_SUM_DN2] == float(V.winding_squared(n_ref) * N * N)
+        assert (rec[c, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()
+
+
+def test_fused_sweeps_equal_repeated_single_sweeps():
+    N, chains, kappa = 32, 64, 0.5
+    phi0, n0 = V.hot_start(np.random.default_rng(1), N, chains)
+    a_phi, a_n = dev(phi0), dev(n0, torch.int32)
+    b_phi, b_n = dev(phi0), dev(n0, torch.int32)
+    ops.villain_sweep(a_phi, a_n, kappa, n_sweeps=6, seed=7, sweep0=100)
+    for s in range(6):
+        ops.villain_sweep(b_phi, b_n, kappa, n_sweeps=1, seed=7, sweep0=100 + s, path='global' if s % 2 else 'smem')
+    assert torch.equal(a_n, b_n) and torch.equal(a_phi, b_phi)
+
+
+def test_chain_offset_makes_shards_independent_of_partition():
+    """Chains [0,8) in one call == chains [0,4) and [4,8) in two calls with chain0 offsets (multi-GPU sharding)."""
+    N, kappa = 16, 0.4
+    phi0, n0 = V.hot_start(np.random.default_rng(2), N, 8)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    ops.villain_sweep(phi, n, kappa, n_sweeps=3, seed=5)
+    for lo in (0, 4):
+        p, q = dev(phi0[lo:lo + 4]), dev(n0[lo:lo + 4], torch.int32)
+        ops.villain_sweep(p, q, kappa, n_sweeps=3, seed=5, chain0=lo)
+        assert torch.equal(p, phi[lo:lo + 4]) and torch.equal(q, n[lo:lo + 4])
+
+
+def test_full_size_config2_smem_equals_global_and_is_sane():
+    """BASELINE config 2 (L=32, 4096 chains): the shared-memory path and the per-colour global path are
+    independent code paths that must agree bit for bit; dn stays a multiple of W; acceptance ~0.5 %."""
+    N, chains, kappa = 32, 4096, 0.5
+    g = torch.Generator(device='cuda'); g.manual_seed(3)
+    phi0 = (torch.rand((chains, 1, N, N), generator=g, device='cuda', dtype=torch.float64) * 2 - 1) * np.pi
+    n0 = torch.randint(-2, 3, (chains, 2, N, N), generator=g, device='cuda', dtype=torch.int32)
+    a_phi, a_n, b_phi, b_n = phi0.clone(), n0.clone(), phi0.clone(), n0.clone()
+    oa = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda'); ob = torch.zeros_like(oa)
+    ops.villain_sweep(a_phi, a_n, kappa, n_sweeps=4, seed=11, path='smem', obs=oa)
+    ops.villain_sweep(b_phi, b_n, kappa, n_sweeps=4, seed=11, path='global', obs=ob)
+    assert torch.equal(a_n, b_n) and torch.equal(a_phi, b_phi)
+    assert torch.equal(oa[:, VOBS_ACCEPTED], ob[:, VOBS_ACCEPTED])
+    torch.testing.assert_close(oa, ob, rtol=1e-12, atol=1e-9)
+    changed = (a_n != n0).any().item() and (a_phi != phi0).any().item()
+    assert changed
+    # every changed phi comes from an accepted proposal (a site may be accepted more than once in 4 sweeps)
+    assert int((a_phi != phi0).sum().item()) <= int(oa[:, VOBS_ACCEPTED].sum().item())
+
+
+def test_cold_start_acceptance_and_observables_are_consistent():
+    N, chains, kappa = 32, 256, 0.5
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    G = NeighborhoodUpdate(S, seed=1)
+    E = svb.BatchedEnsemble(S, chains).generate(20, G, 'cold', sweeps_per_step=5)
+    assert E.ActionDensity.shape == (chains, 20)
+    rate = G.accepted / G.proposed
+    assert 0.002 < rate < 0.02                     # ~0.4-0.5 % at kappa = 0.5
+    phi, n = E.fields
+    rec = ops.villain_observables(phi, n, kappa).cpu().numpy()
+    ref = V.action(phi.cpu().numpy(), n.cpu().numpy().astype(np.int64), kappa)
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], ref, rtol=1e-12)
+    np.testing.assert_allclose(E.ActionDensity[:, -1], ref / N**2, rtol=1e-12)
+
+
+def test_fp32_mode_tracks_fp64_within_stated_tolerance():
+    """fp32 phi: same Philox proposals; dS differs at float precision (stated tolerance: 2e-5 relative to
+    the scale of the terms), so nearly all decisions agree after one sweep."""
+    N, chains, kappa = 32, 32, 0.5
+    phi0, n0 = V.hot_start(np.random.default_rng(5), N, chains)
+    p64, n64 = dev(phi0), dev(n0, torch.int32)
+    p32, n32 = dev(phi0).to(torch.float32), dev(n0, torch.int32)
+    d64 = torch.zeros((chains, N, N), dtype=torch.float64, device='cuda'); d32 = torch.zeros_like(d64)
+    ops.villain_sweep(p64, n64, kappa, seed=3, dS_out=d64)
+    ops.villain_sweep(p32, n32, kappa, seed=3, dS_out=d32)
+    scale = 200.0     # |terms| of dS are O(kappa/2 * (3 pi)^2 * 4) ~ 10^2
+    assert (d64 - d32).abs().max().item() < 2e-5 * scale
+    assert (n64 != n32).float().mean().item() < 1e-3
+
+
+def test_argument_validation_maps_to_python_exceptions():
+    phi = torch.zeros((2, 1, 8, 8), dtype=torch.float64, device='cuda')
+    n = torch.zeros((2, 2, 8, 8), dtype=torch.int32, device='cuda')
+    with pytest.raises(ValueError):
+        ops.villain_sweep(phi, n, -1.0)
+    with pytest.raises(ValueError):
+        ops.villain_sweep(phi, n, 0.5, W=float('inf'))
+    with pytest.raises(TypeError):
+        ops.villain_sweep(phi, n.to(torch.int64), 0.5)
+    with pytest.raises(ValueError):
+        ops.villain_sweep(phi.cpu(), n, 0.5)
+    with pytest.raises(ValueError):
+        NeighborhoodUpdate(svb.Worldline(svb.Lattice2D(8), 0.5))

@@ -1,0 +1,134 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the RNG replay matches the oracle's, Batch/Configurations keep the reference's contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    from supervillain_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, 'include', 'svb200.h')).read()
+    declared = set(re.findall(r'\b(svb_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} is declared in svb200.h but missing from libsvb200.so'
+    from supervillain_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.load().svb_version() == 1
+
+
+def test_constants_mirror_header():
+    from supervillain_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'svb200.h')).read()
+    defs = dict(re.findall(r'#define\s+SVB_([A-Z0-9_]+)\s+(-?\d+)', header))
+    for py, c in (('VOBS_COUNT', 'VOBS_COUNT'), ('WOBS_COUNT', 'WOBS_COUNT'), ('RNG_INJECTED', 'RNG_INJECTED'),
+                  ('PATH_GLOBAL', 'PATH_GLOBAL'), ('WL_COEXACT', 'WL_COEXACT'), ('OP_COFACE_SUM', 'OP_COFACE_SUM'),
+                  ('I64', 'I64'), ('E_ALIGN', 'E_ALIGN'), ('WOBS_DELTA_M_ABS', 'WOBS_DELTA_M_ABS'),
+                  ('VOBS_ACCEPTANCE', 'VOBS_ACCEPTANCE'), ('ARITH_FAST', 'ARITH_FAST')):
+        assert getattr(_lib, py) == int(defs[c]), py
+
+
+def test_no_cpu_fallback_without_device():
+    """The product path must fail loudly when it cannot reach a GPU."""
+    import torch
+    from supervillain_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip('a device is present')
+    phi = torch.zeros((1, 1, 8, 8), dtype=torch.float64)
+    n = torch.zeros((1, 2, 8, 8), dtype=torch.int32)
+    with pytest.raises(ValueError):
+        ops.villain_sweep(phi, n, 0.5)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'supervillain_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), f
+                assert '/root/reference' not in text, f
+
+
+def test_replay_matches_oracle_draw_order():
+    from oracle import villain_np as V
+    from oracle import worldline_np as WL
+    import supervillain_b200 as svb
+    from supervillain_b200.generator import _replay
+    for N in (4, 5, 8):
+        L = svb.Lattice2D(N)
+        a, b = np.random.default_rng(99), np.random.default_rng(99)
+        for _ in range(3):
+            u, dphi, dn_fwd, dn_bwd = _replay.villain_neighborhood(a, L, 2, np.pi, 1)
+            ref = V.draw_neighborhood(b, N, W=2)
+            assert (u == ref['u']).all() and (dphi == ref['dphi']).all()
+            assert (dn_fwd == ref['dn_fwd']).all() and (dn_bwd == ref['dn_bwd']).all()
+        for mode in ('vortex', 'coexact', 'joint'):
+            a, b = np.random.default_rng(7), np.random.default_rng(7)
+            u, x, y = _replay.worldline_checkerboard(a, L, mode, 2)
+            ref = WL.draw_checkerboard(b, N, mode, 2)
+            assert (u == ref['u']).all() and (x == ref['a']).all() and (y == ref['b']).all()
+
+
+def test_lattice_colouring_matches_reference(golden_lattice_forms):
+    import supervillain_b200 as svb
+    _, extras = golden_lattice_forms
+    for N in (3, 4, 5, 6, 7, 8, 9, 32):
+        L = svb.Lattice2D(N)
+        assert (L.colour_map == extras[f'colour_N{N}']).all()
+        order = np.concatenate([np.stack(c, 0) for c in L.checkerboarding], axis=1)
+        assert (order == extras[f'colour_order_N{N}']).all()
+    with pytest.raises(NotImplementedError):
+        svb.Lattice(3, 4)
+
+
+def test_batch_contract():
+    """test/test_batch.py, test/test_batch_dtype.py: draw-major columns, Form wrapping, lossless casts only."""
+    import supervillain_b200 as svb
+    L = svb.Lattice2D(4)
+    S = svb.Villain(L, 0.5)
+    cfgs = S.configurations(3)
+    assert cfgs.phi.shape == (3, 1, 4, 4) and cfgs.n.shape == (3, 2, 4, 4)
+    assert cfgs.phi.dtype == np.float64 and cfgs.n.dtype == np.int64
+    one = cfgs[1]
+    assert isinstance(one['phi'], svb.Form) and one['phi'].degree == 0 and one['n'].degree == 1
+    cfgs[2] = {'phi': np.ones((1, 4, 4)), 'n': np.full((2, 4, 4), 3, dtype=np.int32)}     # widening is lossless
+    assert (cfgs.n[2] == 3).all()
+    cfgs[2] = {'n': np.full((2, 4, 4), 2.0)}                                              # integer-valued float is fine
+    with pytest.raises(TypeError):
+        cfgs[2] = {'n': np.full((2, 4, 4), 2.5)}
+    sub = cfgs[1:]
+    assert len(sub) == 2 and isinstance(sub.phi, svb.Batch)
+    W = svb.Worldline(L, 0.5, W=2).configurations(2)
+    assert W.m.shape == (2, 2, 4, 4) and W.v.shape == (2, 1, 4, 4) and W.v.dtype == np.int64
+
+
+def test_generators_reject_wrong_action_and_report_format():
+    import supervillain_b200 as svb
+    from supervillain_b200.generator.villain import NeighborhoodUpdate
+    from supervillain_b200.generator.worldline import PlaquetteUpdate, VortexUpdate, CoexactUpdate
+    L = svb.Lattice2D(4)
+    V, Wl = svb.Villain(L, 0.5), svb.Worldline(L, 0.5)
+    with pytest.raises(ValueError, match='requires the Villain action'):
+        NeighborhoodUpdate(Wl)
+    for G in (PlaquetteUpdate, VortexUpdate, CoexactUpdate):
+        with pytest.raises(ValueError):
+            G(V)
+    with pytest.raises(NotImplementedError):
+        PlaquetteUpdate(svb.Worldline(L, 0.5, W=float('inf')))
+    G = NeighborhoodUpdate(V)
+    assert str(G) == 'NeighborhoodUpdate' and G.rng is None and G.accepted == 0 and G.sweeps == 0
+    G.accepted, G.proposed, G.acceptance, G.sweeps = 3, 160, 0.2, 10
+    assert G.report() == ('There were 3 neighborhood proposals accepted of 160 proposed updates.\n'
+                          '    0.018750 acceptance rate\n    0.020000 average Metropolis acceptance probability.')
