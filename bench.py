@@ -63,15 +63,20 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(procs, sweeps):
-    """site-updates/s of `procs` processes each sweeping its own L=32 chain `sweeps` times (wall clock)."""
+def cpu_reference_rate(procs, seconds):
+    """site-updates/s of `procs` processes each sweeping its own L=32 chain for about `seconds` of wall clock.
+
+    Returns (rate, wall, sweeps_per_process).  The sweep count is calibrated on a short untimed run so
+    the timed sample is bounded."""
     ctx = mp.get_context('spawn')
     with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(i, 1) for i in range(procs)])            # warm the pool
+        pool.map(_cpu_worker, [(i, 1) for i in range(procs)])            # warm the pool (imports)
+        probe = max(pool.map(_cpu_worker, [(i, 20) for i in range(procs)])) / 20
+        sweeps = max(10, int(seconds / max(probe, 1e-6)))
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(i, sweeps) for i in range(procs)])
         wall = time.perf_counter() - t0
-    return procs * sweeps * L * L / wall, wall
+    return procs * sweeps * L * L / wall, wall, sweeps
 
 
 def host_cores():
@@ -87,16 +92,20 @@ def run_reference(args):
         return 0
     cores = host_cores()
     per_step = []
-    sweeps = 60
-    for _ in range(args.warmup):
-        cpu_reference_rate(cores, 5)
+    # bounded: the whole --steps/--warmup run stays within a few minutes whatever K and W are
+    steps, warmup = min(args.steps, 20), min(args.warmup, 3)
+    seconds = min(3.0, 60.0 / max(steps, 1))
+    for _ in range(warmup):
+        cpu_reference_rate(cores, 0.2)
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        rate, wall = cpu_reference_rate(cores, sweeps)
+    sweeps = 0
+    for _ in range(steps):
+        rate, wall, sweeps = cpu_reference_rate(cores, seconds)
         per_step.append((rate, wall))
     total_wall = time.perf_counter() - t_all
     value = float(np.mean([r for r, _ in per_step]))
-    sample = f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each per step (numpy port of neighborhood.py:59-137)'
+    sample = (f'{steps} timed steps; each step = {cores} processes x ~{sweeps} sweeps of one L=32 kappa=0.5 chain each '
+              f'(~{seconds:.1f} s; numpy port of neighborhood.py:59-137)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_wall / max(args.steps, 1),
@@ -251,8 +260,7 @@ def run_gpu(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
-            sweeps = 120
-            rate, wall = cpu_reference_rate(cores, sweeps)
+            rate, wall, sweeps = cpu_reference_rate(cores, 12.0)
             cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                    'sample': f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each, {wall:.1f} s wall '
                              f'(oracle/villain_np.py port of neighborhood.py:59-137)'}

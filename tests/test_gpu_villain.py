@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import lattice_np as lat
 from oracle import philox_np as P
 from oracle import villain_np as V
 
@@ -103,7 +104,7 @@ def test_philox_mode_matches_oracle_replay(path, arith, N, W, kappa):
         assert rec[c, VOBS_ACCEPTED] == sum(s['accepted'] for s in st)
         assert rec[c, VOBS_ACCEPTANCE] == pytest.approx(sum(s['acceptance'] for s in st), rel=1e-12)
         assert rec[c, VOBS_ACTION] == pytest.approx(float(V.action(p_ref, n_ref, kappa)), rel=1e-12)
-        assert rec[c, VOBS_SUM_DN2] == float(V.winding_squared(n_ref) * N * N)
+        assert rec[c, VOBS_SUM_DN2] == float((lat.d1(n_ref) ** 2).sum())
         assert (rec[c, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()
 
 
