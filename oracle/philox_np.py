@@ -46,29 +46,32 @@ def philox_site(seed, chain, sweep, site, stream_id):
 
 
 TWO_M44 = 2.0 ** -44
+TWO_M52 = 2.0 ** -52
 
 
 def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
     """Dense per-site proposals of one chain and sweep, in the layout of villain_np.draw_neighborhood.
 
-    128 Philox bits per site split 44/44/40: dphi = -I + (2I) * ((k+1/2) 2^-44); u = (k'+1/2) 2^-44;
-    the four dn are the leading base-K digits (K = 2 interval_n + 1) of a 40-bit fraction.
+    128 Philox bits (x, y, z, w) per site split 44 / 52 / 32:
+      dphi = -I + (2I) * ((k44 + 1/2) 2^-44),  k44 = x << 12 | y >> 20
+      u    = (k52 + 1/2) 2^-52,                k52 = (y & 0xFFFFF) << 32 | z
+      dn   = W * (digit_i - interval_n), digit_i = the four leading base-K digits (K = 2 interval_n + 1)
+             of the fraction w / 2^32, ordered (fwd 0, bwd 0, fwd 1, bwd 1)
     """
     site = np.arange(N * N, dtype=np.uint64)
     x, y, z, w = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD)
     kphi = (x << np.uint64(12)) | (y >> np.uint64(20))
-    ku = ((y & np.uint64(0xFFFFF)) << np.uint64(24)) | (z >> np.uint64(8))
-    kn = ((z & np.uint64(0xFF)) << np.uint64(32)) | w
+    ku = ((y & np.uint64(0xFFFFF)) << np.uint64(32)) | z
     Uphi = (kphi.astype(np.float64) + 0.5) * TWO_M44
-    u = (ku.astype(np.float64) + 0.5) * TWO_M44
+    u = (ku.astype(np.float64) + 0.5) * TWO_M52
     dphi = -interval_phi + (2.0 * interval_phi) * Uphi
     K = np.uint64(2 * interval_n + 1)
-    mask40 = np.uint64((1 << 40) - 1)
+    f = w
     digits = []
     for _ in range(4):
-        kn = kn * K
-        digits.append((kn >> np.uint64(40)).astype(np.int64) - interval_n)
-        kn = kn & mask40
+        prod = f * K
+        digits.append((prod >> np.uint64(32)).astype(np.int64) - interval_n)
+        f = prod & MASK32
     dn_fwd = np.stack([W * digits[0], W * digits[2]]).reshape(2, N, N)
     dn_bwd = np.stack([W * digits[1], W * digits[3]]).reshape(2, N, N)
     return {'u': u.reshape(N, N), 'dphi': dphi.reshape(N, N), 'dn_fwd': dn_fwd, 'dn_bwd': dn_bwd}

@@ -41,14 +41,9 @@ struct Philox4 {
 };
 
 __host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-    lo = a * b;
-    hi = __umulhi(a, b);
-#else
-    uint64_t p = (uint64_t)a * (uint64_t)b;
+    const uint64_t p = (uint64_t)a * (uint64_t)b;   // one IMAD.WIDE.U32 on the device
     lo = (uint32_t)p;
     hi = (uint32_t)(p >> 32);
-#endif
 }
 
 template <int ROUNDS = 10>

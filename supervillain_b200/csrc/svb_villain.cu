@@ -12,6 +12,11 @@
 //   accept iff u < min(1, exp(-dS)); then phi[x] += dphi, n_l += dn_l.
 // Same-colour sites touch disjoint links and never neighbour each other, so one colour is
 // updated concurrently without atomics; colours are separated by a barrier.
+//
+// The kernel is instruction-issue bound (Philox + fp64 dS + exp per site against 32 B of HBM
+// traffic), so the hot instantiations fix the lattice size and block size at compile time: all
+// index arithmetic folds to shifts/immediates, loops unroll, integer->double conversions go
+// through the fp64 adder instead of the conversion unit, and integer reductions use REDUX.
 
 #include "svb_common.cuh"
 
@@ -38,6 +43,11 @@ struct VillainArgs {
     double* dS_out;
 };
 
+// exact int32 -> double on the fp64 add pipe: (2^52 + 2^31 + n) - (2^52 + 2^31)
+__device__ __forceinline__ double int_to_double(int n) {
+    return __hiloint2double(0x43300000, n ^ 0x80000000) - 4503601774854144.0;
+}
+
 // ------------------------------------------------------------------------------------------
 // arithmetic policies
 // ------------------------------------------------------------------------------------------
@@ -46,7 +56,7 @@ struct Arith;
 
 template <>
 struct Arith<double, true> {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double cvt(int n) { return int_to_double(n); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     // r = dphi - (2 pi) n          (neighborhood.py:91)
@@ -59,7 +69,7 @@ struct Arith<double, true> {
 };
 template <>
 struct Arith<double, false> {
-    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double cvt(int n) { return int_to_double(n); }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
     static __device__ __forceinline__ double resid(double dphi, double nn) { return fma(-SVB_TWO_PI, nn, dphi); }
@@ -68,7 +78,7 @@ struct Arith<double, false> {
 };
 template <>
 struct Arith<float, true> {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float cvt(int n) { return (float)n; }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float resid(float dphi, float nn) { return __fsub_rn(dphi, __fmul_rn((float)SVB_TWO_PI, nn)); }
@@ -79,7 +89,7 @@ struct Arith<float, true> {
 };
 template <>
 struct Arith<float, false> {
-    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float cvt(int n) { return (float)n; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
     static __device__ __forceinline__ float resid(float dphi, float nn) { return fmaf(-(float)SVB_TWO_PI, nn, dphi); }
@@ -96,37 +106,29 @@ struct VillainDraw {
     int dn[4];     // proposals for links f0, b0, f1, b1 (already multiplied by W)
 };
 
-// The Philox draw mapping.  128 bits per site per sweep, split 44 / 44 / 40:
-//   dphi = -I + (2 I) * ((k44 + 1/2) 2^-44)     [numpy: lo + (hi - lo) * U, no FMA]
-//   u    = (k44' + 1/2) 2^-44                   in (0,1): u = 0 can never force an accept
-//   dn   = four base-K digits (K = 2 interval_n + 1) of the 40-bit fraction k40 / 2^40
-__host__ __device__ __forceinline__ VillainDraw villain_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
-                                                                     uint32_t site, double interval_phi, int interval_n,
-                                                                     int W) {
-    Philox4 p = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD);
+// The Philox draw mapping: 128 bits per site per sweep, split 44 / 52 / 32.
+//   dphi = -I + (2 I) * ((k44 + 1/2) 2^-44)     [numpy: lo + (hi - lo) * U, multiply then add, no FMA]
+//   u    = (k52 + 1/2) 2^-52                    in (0,1): u = 0 can never force an accept
+//   dn   = W * (digit_i - interval_n), digit_i the leading base-K digits (K = 2 interval_n + 1) of the
+//          32-bit fraction w3 / 2^32:  p = f * K;  digit = p >> 32;  f = p mod 2^32
+// Integers become doubles by planting them in the mantissa of 2^52 and subtracting (exact).
+__device__ __forceinline__ VillainDraw villain_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site,
+                                                           double interval_phi, int interval_n, int W) {
+    const Philox4 p = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD);
     VillainDraw d;
-    const double two_m44 = 5.6843418860808015e-14;  // 2^-44
-    uint64_t kphi = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
-    uint64_t ku = ((uint64_t)(p.y & 0xFFFFFu) << 24) | (uint64_t)(p.z >> 8);
-    uint64_t kn = ((uint64_t)(p.z & 0xFFu) << 32) | (uint64_t)p.w;
-    double Uphi = ((double)(long long)kphi + 0.5) * two_m44;   // exact: 45 significant bits
-    d.u = ((double)(long long)ku + 0.5) * two_m44;
-#ifdef __CUDA_ARCH__
+    const double bias = 4503599627370495.5;   // 2^52 - 1/2
+    const double kphi_half = __hiloint2double(0x43300000 | (int)(p.x >> 20), (int)((p.x << 12) | (p.y >> 20))) - bias;
+    const double ku_half = __hiloint2double(0x43300000 | (int)(p.y & 0xFFFFFu), (int)p.z) - bias;
+    const double Uphi = kphi_half * 5.6843418860808015e-14;          // 2^-44
+    d.u = ku_half * 2.220446049250313e-16;                            // 2^-52
     d.dphi = __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, Uphi));
-#else
-    {
-        volatile double prod = (2.0 * interval_phi) * Uphi;    // volatile: forbid FMA contraction on the host
-        d.dphi = -interval_phi + prod;
-    }
-#endif
-    const uint64_t K = (uint64_t)(2 * interval_n + 1);
-    const uint64_t mask40 = (1ull << 40) - 1ull;
+    const uint32_t K = (uint32_t)(2 * interval_n + 1);
+    uint32_t f = p.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        kn *= K;
-        int digit = (int)(kn >> 40);
-        kn &= mask40;
-        d.dn[i] = W * (digit - interval_n);
+        const uint64_t prod = (uint64_t)f * K;
+        f = (uint32_t)prod;
+        d.dn[i] = W * ((int)(prod >> 32) - interval_n);
     }
     return d;
 }
@@ -138,16 +140,21 @@ struct SiteOut {
 };
 
 // One Metropolis proposal at site (x0, x1) of one chain, in place.  `phi`, `n0`, `n1` point at the
-// chain's fields (shared or global memory).
-template <typename real, bool STRICT>
+// chain's fields (shared or global memory).  NT > 0: N == NT is a compile-time power of two.
+template <typename real, bool STRICT, int NT>
 __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, int32_t* __restrict__ n0,
-                                                       int32_t* __restrict__ n1, int N, int x0, int x1, real half_kappa,
+                                                       int32_t* __restrict__ n1, int Nrt, int x0, int x1, real half_kappa,
                                                        const VillainDraw& d) {
     using A = Arith<real, STRICT>;
-    const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
-    const int xm0 = (x0 == 0) ? N - 1 : x0 - 1;
-    const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
-    const int xm1 = (x1 == 0) ? N - 1 : x1 - 1;
+    const int N = NT ? NT : Nrt;
+    int xp0, xm0, xp1, xm1;
+    if (NT) {
+        xp0 = (x0 + 1) & (NT - 1); xm0 = (x0 - 1) & (NT - 1);
+        xp1 = (x1 + 1) & (NT - 1); xm1 = (x1 - 1) & (NT - 1);
+    } else {
+        xp0 = (x0 + 1 == N) ? 0 : x0 + 1; xm0 = (x0 == 0) ? N - 1 : x0 - 1;
+        xp1 = (x1 + 1 == N) ? 0 : x1 + 1; xm1 = (x1 == 0) ? N - 1 : x1 - 1;
+    }
     const int row = x0 * N;
     const int i_c = row + x1;
     const int i_b0 = xm0 * N + x1;
@@ -161,17 +168,17 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     const int nf0 = n0[i_c], nb0 = n0[i_b0], nf1 = n1[i_c], nb1 = n1[i_b1];
 
     // residuals of the four links, recomputed from the current fields (neighborhood.py:91)
-    const real r_f0 = A::resid(A::sub(pf0, pc), (real)nf0);
-    const real r_b0 = A::resid(A::sub(pc, pb0), (real)nb0);
-    const real r_f1 = A::resid(A::sub(pf1, pc), (real)nf1);
-    const real r_b1 = A::resid(A::sub(pc, pb1), (real)nb1);
+    const real r_f0 = A::resid(A::sub(pf0, pc), A::cvt(nf0));
+    const real r_b0 = A::resid(A::sub(pc, pb0), A::cvt(nb0));
+    const real r_f1 = A::resid(A::sub(pf1, pc), A::cvt(nf1));
+    const real r_b1 = A::resid(A::sub(pc, pb1), A::cvt(nb1));
 
     // change of the residuals (neighborhood.py:110): d(dphi) is -dphi on forward links, +dphi on backward links
     const real dphi = (real)d.dphi;
-    const real dr_f0 = A::resid(-dphi, (real)d.dn[0]);
-    const real dr_b0 = A::resid(dphi, (real)d.dn[1]);
-    const real dr_f1 = A::resid(-dphi, (real)d.dn[2]);
-    const real dr_b1 = A::resid(dphi, (real)d.dn[3]);
+    const real dr_f0 = A::resid(-dphi, A::cvt(d.dn[0]));
+    const real dr_b0 = A::resid(dphi, A::cvt(d.dn[1]));
+    const real dr_f1 = A::resid(-dphi, A::cvt(d.dn[2]));
+    const real dr_b1 = A::resid(dphi, A::cvt(d.dn[3]));
 
     // dS in the reference's face_sum order (neighborhood.py:111-112; lattice/_kernels.py:37-45)
     real dS = A::link(half_kappa, dr_f0, r_f0);
@@ -215,38 +222,84 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
     }
 }
 
-// Per-chain partial sums of the observables over the sites this thread strides over.
-template <typename real>
-__device__ __forceinline__ void villain_obs_partial(const real* __restrict__ phi, const int32_t* __restrict__ n0,
-                                                    const int32_t* __restrict__ n1, int N, int tid, int nthreads,
-                                                    double (&s)[4]) {
-    const int V = N * N;
-    for (int i = tid; i < V; i += nthreads) {
-        const int x0 = i / N, x1 = i - x0 * N;
-        const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
-        const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
-        const int i0 = xp0 * N + x1, i1 = x0 * N + xp1;
-        const double pc = (double)phi[i];
-        const int a0 = n0[i], a1 = n1[i];
-        const double r0 = __dsub_rn(__dsub_rn((double)phi[i0], pc), __dmul_rn(SVB_TWO_PI, (double)a0));
-        const double r1 = __dsub_rn(__dsub_rn((double)phi[i1], pc), __dmul_rn(SVB_TWO_PI, (double)a1));
-        s[0] += r0 * r0 + r1 * r1;
-        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
-        const int dn = (n1[i0] - a1) - (n0[i1] - a0);
-        s[1] += (double)dn * (double)dn;
-        s[2] += (double)a0;
-        s[3] += (double)a1;
+// Partial sums of the observables over the sites this thread strides over:
+//   s_action = sum r^2 (double);  i_dn2 = sum (dn)^2;  i_w0, i_w1 = sum n_0, sum n_1.
+template <typename real, int NT>
+__device__ __forceinline__ void villain_obs_site(const real* __restrict__ phi, const int32_t* __restrict__ n0,
+                                                 const int32_t* __restrict__ n1, int Nrt, int x0, int x1, double& s_action,
+                                                 long long& i_dn2, int& i_w0, int& i_w1) {
+    const int N = NT ? NT : Nrt;
+    int xp0, xp1;
+    if (NT) {
+        xp0 = (x0 + 1) & (NT - 1); xp1 = (x1 + 1) & (NT - 1);
+    } else {
+        xp0 = (x0 + 1 == N) ? 0 : x0 + 1; xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
     }
+    const int i = x0 * N + x1, i0 = xp0 * N + x1, i1 = x0 * N + xp1;
+    const double pc = (double)phi[i];
+    const int a0 = n0[i], a1 = n1[i];
+    const double r0 = __dsub_rn(__dsub_rn((double)phi[i0], pc), __dmul_rn(SVB_TWO_PI, int_to_double(a0)));
+    const double r1 = __dsub_rn(__dsub_rn((double)phi[i1], pc), __dmul_rn(SVB_TWO_PI, int_to_double(a1)));
+    s_action = fma(r0, r0, s_action);
+    s_action = fma(r1, r1, s_action);
+    // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+    const int dn = (n1[i0] - a1) - (n0[i1] - a0);
+    i_dn2 += (long long)dn * dn;
+    i_w0 += a0;
+    i_w1 += a1;
+}
+
+// Block reduction of the per-chain record.  Doubles go through shuffles, integers through REDUX.
+// in/out: v[0] action-sum, v[1] sum A;  ints: dn2 (64-bit, split), w0, w1, accepted.  Result in thread 0.
+struct ChainSums {
+    double action, sumA;
+    long long dn2;
+    int w0, w1, accepted;
+};
+
+__device__ __forceinline__ ChainSums block_reduce_chain(ChainSums s, double* scratch /* 6*32 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    s.action = warp_sum(s.action);
+    s.sumA = warp_sum(s.sumA);
+    unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(s.dn2 & 0xFFFFFF));
+    unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)((unsigned long long)s.dn2 >> 24));
+    s.dn2 = (long long)lo + ((long long)hi << 24);
+    s.w0 = __reduce_add_sync(0xffffffffu, s.w0);
+    s.w1 = __reduce_add_sync(0xffffffffu, s.w1);
+    s.accepted = __reduce_add_sync(0xffffffffu, s.accepted);
+    if (nwarps == 1) return s;
+    long long* iscr = reinterpret_cast<long long*>(scratch + 2 * 32);
+    __syncthreads();
+    if (lane == 0) {
+        scratch[warp] = s.action;
+        scratch[32 + warp] = s.sumA;
+        iscr[warp] = s.dn2;
+        iscr[32 + warp] = (long long)s.w0;
+        iscr[64 + warp] = (long long)s.w1;
+        iscr[96 + warp] = (long long)s.accepted;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const bool in = lane < nwarps;
+        s.action = warp_sum(in ? scratch[lane] : 0.0);
+        s.sumA = warp_sum(in ? scratch[32 + lane] : 0.0);
+        s.dn2 = warp_sum(in ? iscr[lane] : 0LL);
+        s.w0 = (int)warp_sum(in ? iscr[32 + lane] : 0LL);
+        s.w1 = (int)warp_sum(in ? iscr[64 + lane] : 0LL);
+        s.accepted = (int)warp_sum(in ? iscr[96 + lane] : 0LL);
+    }
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------
 // SMEM path: one CTA per chain (grid-stride over chains), whole lattice in shared memory.
+// NT/TT > 0 fix the lattice size (power of two) and the block size at compile time.
 // ------------------------------------------------------------------------------------------
-template <typename real, bool INJECTED, bool STRICT>
-__global__ void __launch_bounds__(256) villain_smem_kernel(VillainArgs a, int use_bulk) {
+template <typename real, bool INJECTED, bool STRICT, int NT, int TT>
+__global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs a, int use_bulk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int N = a.N, V = N * N;
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int N = NT ? NT : a.N, V = N * N;
+    const int tid = threadIdx.x, T = TT ? TT : (int)blockDim.x;
     const size_t bytes_phi = (size_t)V * sizeof(real);
     const size_t bytes_n = (size_t)2 * V * sizeof(int32_t);
     const size_t off_n = (bytes_phi + 15) & ~(size_t)15;
@@ -289,20 +342,23 @@ __global__ void __launch_bounds__(256) villain_smem_kernel(VillainArgs a, int us
             __syncthreads();
         }
 
-        double n_acc = 0.0, sum_A = 0.0;
+        int n_acc = 0;
+        double sum_A = 0.0;
         for (int s = 0; s < a.n_sweeps; ++s) {
             const bool last = (s == a.n_sweeps - 1);
+            const bool debug = last && (a.accept_mask != nullptr || a.dS_out != nullptr);
             for (int c = 0; c < ncol; ++c) {
                 if (ncol == 2) {
+#pragma unroll
                     for (int j = tid; j < nhalf; j += T) {
                         const int x0 = j / halfN;
                         const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                         const int site = x0 * N + x1;
                         const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
-                        const SiteOut o = villain_site_update<real, STRICT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
-                        n_acc += o.ok ? 1.0 : 0.0;
+                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
-                        if (last) {
+                        if (debug) {
                             if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
                             if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
                         }
@@ -312,10 +368,10 @@ __global__ void __launch_bounds__(256) villain_smem_kernel(VillainArgs a, int us
                         const int x0 = site / N, x1 = site - x0 * N;
                         if (site_colour(x0, x1, N) != c) continue;
                         const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
-                        const SiteOut o = villain_site_update<real, STRICT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
-                        n_acc += o.ok ? 1.0 : 0.0;
+                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
-                        if (last) {
+                        if (debug) {
                             if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
                             if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
                         }
@@ -327,19 +383,22 @@ __global__ void __launch_bounds__(256) villain_smem_kernel(VillainArgs a, int us
 
         // ---- fused observables of the final state ----
         if (a.obs) {
-            double s[6] = {0, 0, 0, 0, n_acc, sum_A};
-            double part[4] = {0, 0, 0, 0};
-            villain_obs_partial<real>(sphi, sn0, sn1, N, tid, T, part);
-            s[0] = part[0]; s[1] = part[1]; s[2] = part[2]; s[3] = part[3];
-            block_sum<6>(s, scratch);
+            ChainSums cs;
+            cs.action = 0.0; cs.sumA = sum_A; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = n_acc;
+#pragma unroll
+            for (int i = tid; i < V; i += T) {
+                const int x0 = i / N, x1 = i - x0 * N;
+                villain_obs_site<real, NT>(sphi, sn0, sn1, N, x0, x1, cs.action, cs.dn2, cs.w0, cs.w1);
+            }
+            cs = block_reduce_chain(cs, scratch);
             if (tid == 0) {
                 double* o = a.obs + chain * SVB_VOBS_COUNT;
-                o[SVB_VOBS_ACTION] = (kappa / 2) * s[0];
-                o[SVB_VOBS_SUM_DN2] = s[1];
-                o[SVB_VOBS_WRAP0] = s[2];
-                o[SVB_VOBS_WRAP1] = s[3];
-                o[SVB_VOBS_ACCEPTED] = s[4];
-                o[SVB_VOBS_ACCEPTANCE] = s[5];
+                o[SVB_VOBS_ACTION] = (kappa / 2) * cs.action;
+                o[SVB_VOBS_SUM_DN2] = (double)cs.dn2;
+                o[SVB_VOBS_WRAP0] = (double)cs.w0;
+                o[SVB_VOBS_WRAP1] = (double)cs.w1;
+                o[SVB_VOBS_ACCEPTED] = (double)cs.accepted;
+                o[SVB_VOBS_ACCEPTANCE] = cs.sumA;
             }
         }
 
@@ -397,7 +456,7 @@ __global__ void __launch_bounds__(256) villain_colour_pass_kernel(VillainArgs a,
     }
     if (site >= 0) {
         const VillainDraw d = villain_get_draw<INJECTED>(a, chain, sweep, site);
-        const SiteOut o = villain_site_update<real, STRICT>(gphi, gn0, gn1, N, x0, x1, half_kappa, d);
+        const SiteOut o = villain_site_update<real, STRICT, 0>(gphi, gn0, gn1, N, x0, x1, half_kappa, d);
         n_acc = o.ok ? 1.0 : 0.0;
         sum_A = o.A;
         if (write_debug) {
@@ -422,21 +481,25 @@ __global__ void __launch_bounds__(256) villain_obs_kernel(const real* __restrict
                                                           long long chains, int N, double kappa_scalar,
                                                           const double* __restrict__ kappa_chain, double* __restrict__ obs,
                                                           int keep_counters) {
-    __shared__ double scratch[4 * 32];
+    __shared__ double scratch[6 * 32];
     const int V = N * N;
     for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
         const real* gphi = phi + chain * V;
         const int32_t* gn0 = n + chain * 2 * V;
-        double s[4] = {0, 0, 0, 0};
-        villain_obs_partial<real>(gphi, gn0, gn0 + V, N, threadIdx.x, blockDim.x, s);
-        block_sum<4>(s, scratch);
+        ChainSums cs;
+        cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
+        for (int i = threadIdx.x; i < V; i += blockDim.x) {
+            const int x0 = i / N, x1 = i - x0 * N;
+            villain_obs_site<real, 0>(gphi, gn0, gn0 + V, N, x0, x1, cs.action, cs.dn2, cs.w0, cs.w1);
+        }
+        cs = block_reduce_chain(cs, scratch);
         if (threadIdx.x == 0) {
             const double kappa = kappa_chain ? kappa_chain[chain] : kappa_scalar;
             double* o = obs + chain * SVB_VOBS_COUNT;
-            o[SVB_VOBS_ACTION] = (kappa / 2) * s[0];
-            o[SVB_VOBS_SUM_DN2] = s[1];
-            o[SVB_VOBS_WRAP0] = s[2];
-            o[SVB_VOBS_WRAP1] = s[3];
+            o[SVB_VOBS_ACTION] = (kappa / 2) * cs.action;
+            o[SVB_VOBS_SUM_DN2] = (double)cs.dn2;
+            o[SVB_VOBS_WRAP0] = (double)cs.w0;
+            o[SVB_VOBS_WRAP1] = (double)cs.w1;
             if (!keep_counters) {
                 o[SVB_VOBS_ACCEPTED] = 0.0;
                 o[SVB_VOBS_ACCEPTANCE] = 0.0;
@@ -498,11 +561,11 @@ static int get_device_info(DeviceInfo& info) {
     return 0;
 }
 
-template <typename real, bool INJECTED, bool STRICT>
-static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
-    auto kern = villain_smem_kernel<real, INJECTED, STRICT>;
+template <typename real, bool INJECTED, bool STRICT, int NT, int TT>
+static int launch_villain_smem_inst(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    auto kern = villain_smem_kernel<real, INJECTED, STRICT, NT, TT>;
     const size_t smem = villain_smem_bytes(a.N, sizeof(real));
-    const int threads = villain_threads_for(a.N);
+    const int threads = TT ? TT : villain_threads_for(a.N);
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
@@ -517,6 +580,20 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
     kern<<<(unsigned)grid, threads, smem, stream>>>(a, use_bulk);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+template <typename real, bool INJECTED, bool STRICT>
+static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    // compile-time geometry for the production shapes (Philox mode); everything else takes the generic kernel
+    if (!INJECTED) {
+        switch (a.N) {
+            case 16: return launch_villain_smem_inst<real, INJECTED, STRICT, 16, 32>(a, stream, info);
+            case 32: return launch_villain_smem_inst<real, INJECTED, STRICT, 32, 128>(a, stream, info);
+            case 64: return launch_villain_smem_inst<real, INJECTED, STRICT, 64, 256>(a, stream, info);
+            default: break;
+        }
+    }
+    return launch_villain_smem_inst<real, INJECTED, STRICT, 0, 0>(a, stream, info);
 }
 
 template <typename real, bool INJECTED, bool STRICT>
