@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libsvb200.so')
+LIB_PATH = os.environ.get('SVB200_LIB') or os.path.join(HERE, 'libsvb200.so')   # override: kernel tuning experiments
 
 # mirrors include/svb200.h
 F64, F32, I32, I64 = 0, 1, 2, 3

@@ -75,6 +75,36 @@ __host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// min(1, exp(x)): the Metropolis acceptance probability.
+// Degree-11 near-minimax polynomial on [-ln2/2, ln2/2] (Chebyshev-node interpolation, 0.15 ulp
+// approximation error; tests/test_gpu_villain.py checks it against libm) after the usual
+// x = n ln2 + z reduction.  The coefficients live in constant memory so the FMAs read them as
+// constant-bank operands instead of rebuilding 64-bit immediates in registers per call.
+// Arguments are clamped to [-708, 0]: above 0 the clipped result is exactly 1; below -708 the true
+// value (< 4e-308) is far under the smallest uniform the generators can draw (2^-53), so such a
+// proposal is rejected either way and its contribution to acceptance statistics is negligible.
+// ------------------------------------------------------------------------------------------
+static __constant__ double SVB_EXP_C[12] = {
+    1.0, 1.0, 0.5000000000000019, 0.1666666666666668, 0.0416666666664881, 0.008333333333319601,
+    0.0013888888952314775, 0.00019841269890047113, 2.4801485482328494e-05, 2.755724091857897e-06,
+    2.763263963904103e-07, 2.5110037605963777e-08};
+
+__device__ __forceinline__ double exp_clipped(double x) {
+    x = fmin(fmax(x, -708.0), 0.0);
+    const double magic = 6755399441055744.0;                     // 1.5 * 2^52: rounds x log2(e) to an integer
+    double t = fma(x, 1.4426950408889634, magic);
+    const int n = __double2loint(t);
+    t -= magic;
+    double z = fma(t, -0.6931471805599453, x);
+    z = fma(t, -2.3190468138462996e-17, z);
+    double p = SVB_EXP_C[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) p = fma(p, z, SVB_EXP_C[k]);
+    // scale by 2^n (n in [-1022, 0], p in [0.70, 1.42]): add n to the exponent field
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// ------------------------------------------------------------------------------------------
 // checkerboard colouring (supervillain/lattice/compact.py:192-239, D = 2)
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int n_colours(int N) { return (N & 1) ? 4 : 2; }

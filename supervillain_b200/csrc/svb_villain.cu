@@ -20,7 +20,16 @@
 
 #include "svb_common.cuh"
 
+#ifndef SVB_SITE_UNROLL
+#define SVB_SITE_UNROLL 1
+#endif
+#ifndef SVB_MINB32
+#define SVB_MINB32 6
+#endif
+
 namespace svb {
+
+constexpr int kSiteUnroll = SVB_SITE_UNROLL;
 
 struct VillainArgs {
     void* phi;
@@ -34,6 +43,7 @@ struct VillainArgs {
     int interval_n;
     int n_sweeps;
     unsigned long long seed, sweep0, chain0;
+    uint32_t round_key[20];   // Philox key schedule (k0 + r W0, k1 + r W1), r = 0..9, precomputed on the host
     const double* inj_u;
     const double* inj_dphi;
     const int32_t* inj_dn_fwd;
@@ -54,67 +64,76 @@ __device__ __forceinline__ double int_to_double(int n) {
 template <typename T, bool STRICT>
 struct Arith;
 
+// STRICT: the reference's operation order, one rounding per numpy operation, no FMA contraction.
+// FAST:   the same expressions with multiply-adds fused (agrees to ~1e-15 relative).
 template <>
 struct Arith<double, true> {
-    static __device__ __forceinline__ double cvt(int n) { return int_to_double(n); }
+    static __device__ __forceinline__ double cvt(int n) { return (double)n; }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    // r = dphi - (2 pi) n          (neighborhood.py:91)
-    static __device__ __forceinline__ double resid(double dphi, double nn) { return __dsub_rn(dphi, __dmul_rn(SVB_TWO_PI, nn)); }
+    // x - c * t:  r = dphi - (2 pi) n  (neighborhood.py:91),  dr = d(dphi) - (2 pi) dn  (:110)
+    static __device__ __forceinline__ double resid(double x, double c, double t) { return __dsub_rn(x, __dmul_rn(c, t)); }
     // s = ((kappa/2) dr) ((2 r) + dr)   (neighborhood.py:111)
     static __device__ __forceinline__ double link(double hk, double dr, double r) {
         return __dmul_rn(__dmul_rn(hk, dr), __dadd_rn(__dmul_rn(2.0, r), dr));
     }
-    static __device__ __forceinline__ double expneg(double x) { return exp(-x); }
+    static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
 };
 template <>
 struct Arith<double, false> {
-    static __device__ __forceinline__ double cvt(int n) { return int_to_double(n); }
+    static __device__ __forceinline__ double cvt(int n) { return (double)n; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
-    static __device__ __forceinline__ double resid(double dphi, double nn) { return fma(-SVB_TWO_PI, nn, dphi); }
+    static __device__ __forceinline__ double resid(double x, double c, double t) { return fma(-c, t, x); }
     static __device__ __forceinline__ double link(double hk, double dr, double r) { return (hk * dr) * fma(2.0, r, dr); }
-    static __device__ __forceinline__ double expneg(double x) { return exp(-x); }
+    static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
 };
 template <>
 struct Arith<float, true> {
     static __device__ __forceinline__ float cvt(int n) { return (float)n; }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float resid(float dphi, float nn) { return __fsub_rn(dphi, __fmul_rn((float)SVB_TWO_PI, nn)); }
+    static __device__ __forceinline__ float resid(float x, float c, float t) { return __fsub_rn(x, __fmul_rn(c, t)); }
     static __device__ __forceinline__ float link(float hk, float dr, float r) {
         return __fmul_rn(__fmul_rn(hk, dr), __fadd_rn(__fmul_rn(2.0f, r), dr));
     }
-    static __device__ __forceinline__ float expneg(float x) { return expf(-x); }
+    static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
 };
 template <>
 struct Arith<float, false> {
     static __device__ __forceinline__ float cvt(int n) { return (float)n; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
-    static __device__ __forceinline__ float resid(float dphi, float nn) { return fmaf(-(float)SVB_TWO_PI, nn, dphi); }
+    static __device__ __forceinline__ float resid(float x, float c, float t) { return fmaf(-c, t, x); }
     static __device__ __forceinline__ float link(float hk, float dr, float r) { return (hk * dr) * fmaf(2.0f, r, dr); }
-    static __device__ __forceinline__ float expneg(float x) { return expf(-x); }
+    static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
 };
 
 // ------------------------------------------------------------------------------------------
 // proposals
 // ------------------------------------------------------------------------------------------
+// A proposal for one site: the Metropolis uniform, dphi, and the four link changes in UNITS
+// dg[i] (links f0, b0, f1, b1); the integer change of n is unit * dg[i] and its residual change is
+// c * dg[i], where (unit, c) = (W, fl(2 pi W)) for Philox draws in FAST arithmetic and (1, 2 pi)
+// otherwise (then dg already carries the factor W and 2 pi * dn is rounded exactly as numpy does).
 struct VillainDraw {
-    double u;      // Metropolis uniform in (0, 1)
-    double dphi;   // proposal for phi[x]
-    int dn[4];     // proposals for links f0, b0, f1, b1 (already multiplied by W)
+    double u;
+    double dphi;
+    int dg[4];
+};
+
+struct VillainConsts {
+    double c;        // residual change per unit of dg
+    int unit;        // integer change of n per unit of dg
 };
 
 // The Philox draw mapping: 128 bits per site per sweep, split 44 / 52 / 32.
 //   dphi = -I + (2 I) * ((k44 + 1/2) 2^-44)     [numpy: lo + (hi - lo) * U, multiply then add, no FMA]
 //   u    = (k52 + 1/2) 2^-52                    in (0,1): u = 0 can never force an accept
-//   dn   = W * (digit_i - interval_n), digit_i the leading base-K digits (K = 2 interval_n + 1) of the
+//   dg_i = digit_i - interval_n, digit_i the leading base-K digits (K = 2 interval_n + 1) of the
 //          32-bit fraction w3 / 2^32:  p = f * K;  digit = p >> 32;  f = p mod 2^32
-// Integers become doubles by planting them in the mantissa of 2^52 and subtracting (exact).
-__device__ __forceinline__ VillainDraw villain_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site,
-                                                           double interval_phi, int interval_n, int W) {
-    const Philox4 p = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD);
+// The 44- and 52-bit integers become doubles by planting them in the mantissa of 2^52 (exact).
+__device__ __forceinline__ VillainDraw villain_draw_from_bits(const Philox4& p, double interval_phi, int interval_n) {
     VillainDraw d;
     const double bias = 4503599627370495.5;   // 2^52 - 1/2
     const double kphi_half = __hiloint2double(0x43300000 | (int)(p.x >> 20), (int)((p.x << 12) | (p.y >> 20))) - bias;
@@ -128,9 +147,26 @@ __device__ __forceinline__ VillainDraw villain_draw_philox(uint64_t seed, uint64
     for (int i = 0; i < 4; ++i) {
         const uint64_t prod = (uint64_t)f * K;
         f = (uint32_t)prod;
-        d.dn[i] = W * ((int)(prod >> 32) - interval_n);
+        d.dg[i] = (int)(prod >> 32) - interval_n;
     }
     return d;
+}
+
+// Philox4x32-10 with the key schedule read from kernel parameters (constant bank operands).
+__device__ __forceinline__ Philox4 philox_site_keys(const VillainArgs& a, uint64_t chain, uint64_t sweep, uint32_t site) {
+    uint32_t c0 = site, c1 = (uint32_t)chain, c2 = (uint32_t)sweep;
+    uint32_t c3 = (STREAM_VILLAIN_NEIGHBORHOOD << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
+                  (uint32_t)((sweep >> 32) & 0xFFFFu);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(0xD2511F53u, c0, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ a.round_key[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ a.round_key[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
 }
 
 struct SiteOut {
@@ -139,12 +175,21 @@ struct SiteOut {
     double dS;
 };
 
+// Running sums of the observables that can be collected while the LAST colour of the last sweep is
+// processed: every link has exactly one end of that colour (even N), so summing the four links of
+// each of its sites covers each link once.
+struct LinkSums {
+    double r2;     // sum of final residuals squared
+    int w0, w1;    // sum of final n_0, n_1
+};
+
 // One Metropolis proposal at site (x0, x1) of one chain, in place.  `phi`, `n0`, `n1` point at the
 // chain's fields (shared or global memory).  NT > 0: N == NT is a compile-time power of two.
 template <typename real, bool STRICT, int NT>
 __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, int32_t* __restrict__ n0,
                                                        int32_t* __restrict__ n1, int Nrt, int x0, int x1, real half_kappa,
-                                                       const VillainDraw& d) {
+                                                       const VillainConsts& k, const VillainDraw& d, bool collect,
+                                                       LinkSums& sums) {
     using A = Arith<real, STRICT>;
     const int N = NT ? NT : Nrt;
     int xp0, xm0, xp1, xm1;
@@ -168,17 +213,19 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     const int nf0 = n0[i_c], nb0 = n0[i_b0], nf1 = n1[i_c], nb1 = n1[i_b1];
 
     // residuals of the four links, recomputed from the current fields (neighborhood.py:91)
-    const real r_f0 = A::resid(A::sub(pf0, pc), A::cvt(nf0));
-    const real r_b0 = A::resid(A::sub(pc, pb0), A::cvt(nb0));
-    const real r_f1 = A::resid(A::sub(pf1, pc), A::cvt(nf1));
-    const real r_b1 = A::resid(A::sub(pc, pb1), A::cvt(nb1));
+    const real two_pi = (real)SVB_TWO_PI;
+    const real r_f0 = A::resid(A::sub(pf0, pc), two_pi, A::cvt(nf0));
+    const real r_b0 = A::resid(A::sub(pc, pb0), two_pi, A::cvt(nb0));
+    const real r_f1 = A::resid(A::sub(pf1, pc), two_pi, A::cvt(nf1));
+    const real r_b1 = A::resid(A::sub(pc, pb1), two_pi, A::cvt(nb1));
 
     // change of the residuals (neighborhood.py:110): d(dphi) is -dphi on forward links, +dphi on backward links
     const real dphi = (real)d.dphi;
-    const real dr_f0 = A::resid(-dphi, A::cvt(d.dn[0]));
-    const real dr_b0 = A::resid(dphi, A::cvt(d.dn[1]));
-    const real dr_f1 = A::resid(-dphi, A::cvt(d.dn[2]));
-    const real dr_b1 = A::resid(dphi, A::cvt(d.dn[3]));
+    const real c = (real)k.c;
+    const real dr_f0 = A::resid(-dphi, c, A::cvt(d.dg[0]));
+    const real dr_b0 = A::resid(dphi, c, A::cvt(d.dg[1]));
+    const real dr_f1 = A::resid(-dphi, c, A::cvt(d.dg[2]));
+    const real dr_b1 = A::resid(dphi, c, A::cvt(d.dg[3]));
 
     // dS in the reference's face_sum order (neighborhood.py:111-112; lattice/_kernels.py:37-45)
     real dS = A::link(half_kappa, dr_f0, r_f0);
@@ -186,14 +233,26 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     dS = A::add(dS, A::link(half_kappa, dr_f1, r_f1));
     dS = A::add(dS, A::link(half_kappa, dr_b1, r_b1));
 
-    const double acc = fmin((double)A::expneg(dS), 1.0);      // clip(exp(-dS), 0, 1)   (:115)
+    const double acc = A::accept_prob(dS);                      // clip(exp(-dS), 0, 1)   (:115)
     const bool ok = d.u < acc;                                  // (:116)
     if (ok) {                                                   // (:121-128)
         phi[i_c] = A::add(pc, dphi);
-        n0[i_c] = nf0 + d.dn[0];
-        n0[i_b0] = nb0 + d.dn[1];
-        n1[i_c] = nf1 + d.dn[2];
-        n1[i_b1] = nb1 + d.dn[3];
+        n0[i_c] = nf0 + k.unit * d.dg[0];
+        n0[i_b0] = nb0 + k.unit * d.dg[1];
+        n1[i_c] = nf1 + k.unit * d.dg[2];
+        n1[i_b1] = nb1 + k.unit * d.dg[3];
+    }
+    if (collect) {
+        const double s = ok ? 1.0 : 0.0;
+        const double q0 = fma(s, (double)dr_f0, (double)r_f0), q1 = fma(s, (double)dr_b0, (double)r_b0);
+        const double q2 = fma(s, (double)dr_f1, (double)r_f1), q3 = fma(s, (double)dr_b1, (double)r_b1);
+        sums.r2 = fma(q0, q0, sums.r2);
+        sums.r2 = fma(q1, q1, sums.r2);
+        sums.r2 = fma(q2, q2, sums.r2);
+        sums.r2 = fma(q3, q3, sums.r2);
+        const int m = ok ? k.unit : 0;
+        sums.w0 += nf0 + nb0 + m * (d.dg[0] + d.dg[1]);
+        sums.w1 += nf1 + nb1 + m * (d.dg[2] + d.dg[3]);
     }
     SiteOut o;
     o.A = acc;
@@ -202,8 +261,9 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     return o;
 }
 
-template <bool INJECTED>
-__device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, long long chain, int sweep, int site) {
+template <bool INJECTED, bool KEYS>
+__device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, long long chain, int sweep, int site,
+                                                        int dg_scale) {
     if (INJECTED) {
         const long long V = (long long)a.N * a.N;
         const long long base = ((long long)sweep * a.chains + chain) * V + site;
@@ -211,19 +271,39 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
         VillainDraw d;
         d.u = a.inj_u[base];
         d.dphi = a.inj_dphi[base];
-        d.dn[0] = a.inj_dn_fwd[lbase];
-        d.dn[1] = a.inj_dn_bwd[lbase];
-        d.dn[2] = a.inj_dn_fwd[lbase + V];
-        d.dn[3] = a.inj_dn_bwd[lbase + V];
+        d.dg[0] = a.inj_dn_fwd[lbase];
+        d.dg[1] = a.inj_dn_bwd[lbase];
+        d.dg[2] = a.inj_dn_fwd[lbase + V];
+        d.dg[3] = a.inj_dn_bwd[lbase + V];
         return d;
     } else {
-        return villain_draw_philox(a.seed, a.chain0 + (unsigned long long)chain, a.sweep0 + (unsigned long long)sweep,
-                                   (uint32_t)site, a.interval_phi, a.interval_n, a.W);
+        const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
+        const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, (uint32_t)site)
+                               : philox_site(a.seed, gc, gs, (uint32_t)site, STREAM_VILLAIN_NEIGHBORHOOD);
+        VillainDraw d = villain_draw_from_bits(p, a.interval_phi, a.interval_n);
+        if (dg_scale != 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d.dg[i] *= dg_scale;
+        }
+        return d;
     }
 }
 
-// Partial sums of the observables over the sites this thread strides over:
-//   s_action = sum r^2 (double);  i_dn2 = sum (dn)^2;  i_w0, i_w1 = sum n_0, sum n_1.
+// (unit, c, dg_scale) for a launch: FAST Philox keeps dg in units of W; everything else folds W into dg
+template <bool INJECTED, bool STRICT>
+__device__ __forceinline__ void villain_consts(const VillainArgs& a, VillainConsts& k, int& dg_scale) {
+    if (!INJECTED && !STRICT) {
+        k.unit = a.W;
+        k.c = SVB_TWO_PI * (double)a.W;
+        dg_scale = 1;
+    } else {
+        k.unit = 1;
+        k.c = SVB_TWO_PI;
+        dg_scale = INJECTED ? 1 : a.W;
+    }
+}
+
+// Observables of one site's forward links and plaquette (full pass; used for odd N and by the obs kernel).
 template <typename real, int NT>
 __device__ __forceinline__ void villain_obs_site(const real* __restrict__ phi, const int32_t* __restrict__ n0,
                                                  const int32_t* __restrict__ n1, int Nrt, int x0, int x1, double& s_action,
@@ -238,8 +318,8 @@ __device__ __forceinline__ void villain_obs_site(const real* __restrict__ phi, c
     const int i = x0 * N + x1, i0 = xp0 * N + x1, i1 = x0 * N + xp1;
     const double pc = (double)phi[i];
     const int a0 = n0[i], a1 = n1[i];
-    const double r0 = __dsub_rn(__dsub_rn((double)phi[i0], pc), __dmul_rn(SVB_TWO_PI, int_to_double(a0)));
-    const double r1 = __dsub_rn(__dsub_rn((double)phi[i1], pc), __dmul_rn(SVB_TWO_PI, int_to_double(a1)));
+    const double r0 = __dsub_rn(__dsub_rn((double)phi[i0], pc), __dmul_rn(SVB_TWO_PI, (double)a0));
+    const double r1 = __dsub_rn(__dsub_rn((double)phi[i1], pc), __dmul_rn(SVB_TWO_PI, (double)a1));
     s_action = fma(r0, r0, s_action);
     s_action = fma(r1, r1, s_action);
     // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
@@ -249,8 +329,23 @@ __device__ __forceinline__ void villain_obs_site(const real* __restrict__ phi, c
     i_w1 += a1;
 }
 
+// (dn)^2 of the plaquette based at (x0, x1): the only observable that needs a pass after the last colour.
+template <int NT>
+__device__ __forceinline__ long long villain_dn2_site(const int32_t* __restrict__ n0, const int32_t* __restrict__ n1, int Nrt,
+                                                      int x0, int x1) {
+    const int N = NT ? NT : Nrt;
+    int xp0, xp1;
+    if (NT) {
+        xp0 = (x0 + 1) & (NT - 1); xp1 = (x1 + 1) & (NT - 1);
+    } else {
+        xp0 = (x0 + 1 == N) ? 0 : x0 + 1; xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+    }
+    const int i = x0 * N + x1;
+    const int dn = (n1[xp0 * N + x1] - n1[i]) - (n0[x0 * N + xp1] - n0[i]);
+    return (long long)dn * dn;
+}
+
 // Block reduction of the per-chain record.  Doubles go through shuffles, integers through REDUX.
-// in/out: v[0] action-sum, v[1] sum A;  ints: dn2 (64-bit, split), w0, w1, accepted.  Result in thread 0.
 struct ChainSums {
     double action, sumA;
     long long dn2;
@@ -293,10 +388,11 @@ __device__ __forceinline__ ChainSums block_reduce_chain(ChainSums s, double* scr
 
 // ------------------------------------------------------------------------------------------
 // SMEM path: one CTA per chain (grid-stride over chains), whole lattice in shared memory.
-// NT/TT > 0 fix the lattice size (power of two) and the block size at compile time.
+// NT/TT > 0 fix the lattice size (power of two) and the block size at compile time; MINB is the
+// occupancy the register allocation is held to.
 // ------------------------------------------------------------------------------------------
-template <typename real, bool INJECTED, bool STRICT, int NT, int TT>
-__global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs a, int use_bulk) {
+template <typename real, bool INJECTED, bool STRICT, int NT, int TT, int MINB>
+__global__ void __launch_bounds__(TT ? TT : 256, MINB) villain_smem_kernel(const __grid_constant__ VillainArgs a, int use_bulk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int N = NT ? NT : a.N, V = N * N;
     const int tid = threadIdx.x, T = TT ? TT : (int)blockDim.x;
@@ -320,6 +416,10 @@ __global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs
     uint32_t phase = 0;
     const int ncol = n_colours(N);
     const int halfN = N >> 1, nhalf = V >> 1;
+    VillainConsts kc;
+    int dg_scale;
+    villain_consts<INJECTED, STRICT>(a, kc, dg_scale);
+    const bool fuse_obs = (a.obs != nullptr) && (ncol == 2);
 
     for (long long chain = blockIdx.x; chain < a.chains; chain += gridDim.x) {
         real* gphi = reinterpret_cast<real*>(a.phi) + chain * V;
@@ -344,18 +444,22 @@ __global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs
 
         int n_acc = 0;
         double sum_A = 0.0;
+        LinkSums ls;
+        ls.r2 = 0.0; ls.w0 = 0; ls.w1 = 0;
         for (int s = 0; s < a.n_sweeps; ++s) {
             const bool last = (s == a.n_sweeps - 1);
             const bool debug = last && (a.accept_mask != nullptr || a.dS_out != nullptr);
             for (int c = 0; c < ncol; ++c) {
                 if (ncol == 2) {
-#pragma unroll
+                    const bool collect = fuse_obs && last && (c == 1);
+#pragma unroll kSiteUnroll
                     for (int j = tid; j < nhalf; j += T) {
                         const int x0 = j / halfN;
                         const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                         const int site = x0 * N + x1;
-                        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
-                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, site, dg_scale);
+                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                                collect, ls);
                         n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
                         if (debug) {
@@ -367,8 +471,9 @@ __global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs
                     for (int site = tid; site < V; site += T) {
                         const int x0 = site / N, x1 = site - x0 * N;
                         if (site_colour(x0, x1, N) != c) continue;
-                        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, s, site);
-                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, d);
+                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, site, dg_scale);
+                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                                false, ls);
                         n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
                         if (debug) {
@@ -381,14 +486,24 @@ __global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs
             }
         }
 
-        // ---- fused observables of the final state ----
+        // ---- observables of the final state ----
         if (a.obs) {
             ChainSums cs;
-            cs.action = 0.0; cs.sumA = sum_A; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = n_acc;
+            cs.sumA = sum_A; cs.accepted = n_acc; cs.dn2 = 0;
+            if (fuse_obs) {
+                // action and wrapping were collected link by link during the last colour pass
+                cs.action = ls.r2; cs.w0 = ls.w0; cs.w1 = ls.w1;
 #pragma unroll
-            for (int i = tid; i < V; i += T) {
-                const int x0 = i / N, x1 = i - x0 * N;
-                villain_obs_site<real, NT>(sphi, sn0, sn1, N, x0, x1, cs.action, cs.dn2, cs.w0, cs.w1);
+                for (int i = tid; i < V; i += T) {
+                    const int x0 = i / N, x1 = i - x0 * N;
+                    cs.dn2 += villain_dn2_site<NT>(sn0, sn1, N, x0, x1);
+                }
+            } else {
+                cs.action = 0.0; cs.w0 = 0; cs.w1 = 0;
+                for (int i = tid; i < V; i += T) {
+                    const int x0 = i / N, x1 = i - x0 * N;
+                    villain_obs_site<real, NT>(sphi, sn0, sn1, N, x0, x1, cs.action, cs.dn2, cs.w0, cs.w1);
+                }
             }
             cs = block_reduce_chain(cs, scratch);
             if (tid == 0) {
@@ -425,8 +540,8 @@ __global__ void __launch_bounds__(TT ? TT : 256) villain_smem_kernel(VillainArgs
 // GLOBAL path: one launch per colour pass, straight out of HBM / L2 (any N).
 // ------------------------------------------------------------------------------------------
 template <typename real, bool INJECTED, bool STRICT>
-__global__ void __launch_bounds__(256) villain_colour_pass_kernel(VillainArgs a, int sweep, int colour, int blocks_per_chain,
-                                                                  int write_debug) {
+__global__ void __launch_bounds__(256) villain_colour_pass_kernel(const __grid_constant__ VillainArgs a, int sweep, int colour,
+                                                                  int blocks_per_chain, int write_debug) {
     const int N = a.N, V = N * N;
     const long long chain = blockIdx.x / blocks_per_chain;
     const int blk = blockIdx.x - (int)(chain * blocks_per_chain);
@@ -455,8 +570,12 @@ __global__ void __launch_bounds__(256) villain_colour_pass_kernel(VillainArgs a,
         }
     }
     if (site >= 0) {
-        const VillainDraw d = villain_get_draw<INJECTED>(a, chain, sweep, site);
-        const SiteOut o = villain_site_update<real, STRICT, 0>(gphi, gn0, gn1, N, x0, x1, half_kappa, d);
+        VillainConsts kc;
+        int dg_scale;
+        villain_consts<INJECTED, STRICT>(a, kc, dg_scale);
+        LinkSums unused;
+        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, sweep, site, dg_scale);
+        const SiteOut o = villain_site_update<real, STRICT, 0>(gphi, gn0, gn1, N, x0, x1, half_kappa, kc, d, false, unused);
         n_acc = o.ok ? 1.0 : 0.0;
         sum_A = o.A;
         if (write_debug) {
@@ -525,10 +644,11 @@ __global__ void villain_draws_kernel(long long chains, int N, int W, double inte
     if (i >= chains * V) return;
     const long long chain = i / V;
     const int site = (int)(i - chain * V);
-    const VillainDraw d = villain_draw_philox(seed, chain0 + chain, sweep, (uint32_t)site, interval_phi, interval_n, W);
+    const Philox4 p = philox_site(seed, chain0 + chain, sweep, (uint32_t)site, STREAM_VILLAIN_NEIGHBORHOOD);
+    const VillainDraw d = villain_draw_from_bits(p, interval_phi, interval_n);
     u[i] = d.u;
     dphi[i] = d.dphi;
-    for (int k = 0; k < 4; ++k) dn[(chain * 4 + k) * V + site] = d.dn[k];
+    for (int k = 0; k < 4; ++k) dn[(chain * 4 + k) * V + site] = W * d.dg[k];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -561,12 +681,13 @@ static int get_device_info(DeviceInfo& info) {
     return 0;
 }
 
-template <typename real, bool INJECTED, bool STRICT, int NT, int TT>
+template <typename real, bool INJECTED, bool STRICT, int NT, int TT, int MINB>
 static int launch_villain_smem_inst(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
-    auto kern = villain_smem_kernel<real, INJECTED, STRICT, NT, TT>;
+    auto kern = villain_smem_kernel<real, INJECTED, STRICT, NT, TT, MINB>;
     const size_t smem = villain_smem_bytes(a.N, sizeof(real));
     const int threads = TT ? TT : villain_threads_for(a.N);
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "villain smem kernel does not fit an SM at N=%d", a.N);
@@ -587,13 +708,13 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
     // compile-time geometry for the production shapes (Philox mode); everything else takes the generic kernel
     if (!INJECTED) {
         switch (a.N) {
-            case 16: return launch_villain_smem_inst<real, INJECTED, STRICT, 16, 32>(a, stream, info);
-            case 32: return launch_villain_smem_inst<real, INJECTED, STRICT, 32, 128>(a, stream, info);
-            case 64: return launch_villain_smem_inst<real, INJECTED, STRICT, 64, 256>(a, stream, info);
+            case 16: return launch_villain_smem_inst<real, INJECTED, STRICT, 16, 32, 24>(a, stream, info);
+            case 32: return launch_villain_smem_inst<real, INJECTED, STRICT, 32, 128, SVB_MINB32>(a, stream, info);
+            case 64: return launch_villain_smem_inst<real, INJECTED, STRICT, 64, 256, 3>(a, stream, info);
             default: break;
         }
     }
-    return launch_villain_smem_inst<real, INJECTED, STRICT, 0, 0>(a, stream, info);
+    return launch_villain_smem_inst<real, INJECTED, STRICT, 0, 0, 1>(a, stream, info);
 }
 
 template <typename real, bool INJECTED, bool STRICT>
@@ -674,6 +795,10 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
     a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
     a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
     a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
