@@ -23,6 +23,14 @@
 #ifndef SVB_SITE_UNROLL
 #define SVB_SITE_UNROLL 1
 #endif
+#ifdef SVB_CVT_I2F
+#define SVB_CVT(n) ((double)(n))      /* I2F.F64 on the conversion unit: 16 lanes/clk/SM, measured 6 % slower */
+#else
+#define SVB_CVT(n) int_to_double(n)   /* LOP3 + DADD on the alu / fp64 pipes */
+#endif
+#ifndef SVB_PHILOX_ROUNDS
+#define SVB_PHILOX_ROUNDS 10
+#endif
 #ifndef SVB_MINB32
 #define SVB_MINB32 6
 #endif
@@ -78,15 +86,19 @@ struct Arith<double, true> {
         return __dmul_rn(__dmul_rn(hk, dr), __dadd_rn(__dmul_rn(2.0, r), dr));
     }
     static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
+    static __device__ __forceinline__ double twice_plus(double r, double dr) { return fma(2.0, r, dr); }
+    static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
 };
 template <>
 struct Arith<double, false> {
-    static __device__ __forceinline__ double cvt(int n) { return (double)n; }
+    static __device__ __forceinline__ double cvt(int n) { return SVB_CVT(n); }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
     static __device__ __forceinline__ double resid(double x, double c, double t) { return fma(-c, t, x); }
     static __device__ __forceinline__ double link(double hk, double dr, double r) { return (hk * dr) * fma(2.0, r, dr); }
     static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
+    static __device__ __forceinline__ double twice_plus(double r, double dr) { return fma(2.0, r, dr); }
+    static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
 };
 template <>
 struct Arith<float, true> {
@@ -98,6 +110,8 @@ struct Arith<float, true> {
         return __fmul_rn(__fmul_rn(hk, dr), __fadd_rn(__fmul_rn(2.0f, r), dr));
     }
     static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
+    static __device__ __forceinline__ float twice_plus(float r, float dr) { return fmaf(2.0f, r, dr); }
+    static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
 };
 template <>
 struct Arith<float, false> {
@@ -107,6 +121,8 @@ struct Arith<float, false> {
     static __device__ __forceinline__ float resid(float x, float c, float t) { return fmaf(-c, t, x); }
     static __device__ __forceinline__ float link(float hk, float dr, float r) { return (hk * dr) * fmaf(2.0f, r, dr); }
     static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
+    static __device__ __forceinline__ float twice_plus(float r, float dr) { return fmaf(2.0f, r, dr); }
+    static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -158,7 +174,7 @@ __device__ __forceinline__ Philox4 philox_site_keys(const VillainArgs& a, uint64
     uint32_t c3 = (STREAM_VILLAIN_NEIGHBORHOOD << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
                   (uint32_t)((sweep >> 32) & 0xFFFFu);
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < SVB_PHILOX_ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(0xD2511F53u, c0, hi0, lo0);
         mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
@@ -227,11 +243,21 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     const real dr_f1 = A::resid(-dphi, c, A::cvt(d.dg[2]));
     const real dr_b1 = A::resid(dphi, c, A::cvt(d.dg[3]));
 
-    // dS in the reference's face_sum order (neighborhood.py:111-112; lattice/_kernels.py:37-45)
-    real dS = A::link(half_kappa, dr_f0, r_f0);
-    dS = A::add(dS, A::link(half_kappa, dr_b0, r_b0));
-    dS = A::add(dS, A::link(half_kappa, dr_f1, r_f1));
-    dS = A::add(dS, A::link(half_kappa, dr_b1, r_b1));
+    real dS;
+    if (STRICT) {
+        // dS in the reference's face_sum order (neighborhood.py:111-112; lattice/_kernels.py:37-45)
+        dS = A::link(half_kappa, dr_f0, r_f0);
+        dS = A::add(dS, A::link(half_kappa, dr_b0, r_b0));
+        dS = A::add(dS, A::link(half_kappa, dr_f1, r_f1));
+        dS = A::add(dS, A::link(half_kappa, dr_b1, r_b1));
+    } else {
+        // same sum with kappa/2 factored out and the multiply-adds fused: 8 FMAs + 1 multiply
+        real acc2 = dr_f0 * A::twice_plus(r_f0, dr_f0);
+        acc2 = A::mad(dr_b0, A::twice_plus(r_b0, dr_b0), acc2);
+        acc2 = A::mad(dr_f1, A::twice_plus(r_f1, dr_f1), acc2);
+        acc2 = A::mad(dr_b1, A::twice_plus(r_b1, dr_b1), acc2);
+        dS = half_kappa * acc2;
+    }
 
     const double acc = A::accept_prob(dS);                      // clip(exp(-dS), 0, 1)   (:115)
     const bool ok = d.u < acc;                                  // (:116)
@@ -536,6 +562,151 @@ __global__ void __launch_bounds__(TT ? TT : 256, MINB) villain_smem_kernel(const
     }
 }
 
+// Sum of (dn)^2 over the plaquettes of PER consecutive sites of one row, with 128-bit shared loads.
+template <int NT, int TT>
+__device__ __forceinline__ long long villain_dn2_rows(const int32_t* __restrict__ n0, const int32_t* __restrict__ n1, int tid) {
+    constexpr int PER = NT * NT / TT;           // consecutive plaquettes per thread (a multiple of 4)
+    constexpr int SEGS = NT / PER;               // such segments per row
+    static_assert(PER % 4 == 0 && NT % PER == 0, "villain_dn2_rows: unsupported geometry");
+    const int x0 = tid / SEGS, seg = (tid % SEGS) * PER;
+    const int xp0 = (x0 + 1) & (NT - 1);
+    const int4* up = reinterpret_cast<const int4*>(n1 + xp0 * NT + seg);   // n1[x + e0]
+    const int4* me = reinterpret_cast<const int4*>(n1 + x0 * NT + seg);    // n1[x]
+    const int4* ho = reinterpret_cast<const int4*>(n0 + x0 * NT + seg);    // n0[x], n0[x + e1]
+    const int wrap = n0[x0 * NT + ((seg + PER) & (NT - 1))];
+    long long acc = 0;
+    int4 C = ho[0];
+#pragma unroll
+    for (int q = 0; q < PER / 4; ++q) {
+        const int4 A = up[q], B = me[q];
+        const int4 Cn = (q + 1 < PER / 4) ? ho[q + 1] : make_int4(wrap, 0, 0, 0);
+        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+        const int d0 = (A.x - B.x) - (C.y - C.x), d1 = (A.y - B.y) - (C.z - C.y);
+        const int d2 = (A.z - B.z) - (C.w - C.z), d3 = (A.w - B.w) - (Cn.x - C.w);
+        acc += (long long)d0 * d0;
+        acc += (long long)d1 * d1;
+        acc += (long long)d2 * d2;
+        acc += (long long)d3 * d3;
+        C = Cn;
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// SMEM path, production instantiation: Philox draws, compile-time geometry, and a two-stage
+// TMA pipeline per CTA.  While a CTA sweeps the chain in one shared-memory buffer, the bulk load
+// of its next chain lands in the other buffer and the bulk store of the previous chain drains,
+// so HBM latency never sits on the CTA's critical path.
+// ------------------------------------------------------------------------------------------
+template <typename real, bool STRICT, int NT, int TT, int MINB>
+__global__ void __launch_bounds__(TT, MINB) villain_smem_pipelined_kernel(const __grid_constant__ VillainArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = NT * NT, T = TT;
+    constexpr int halfN = N / 2, nhalf = V / 2;
+    constexpr uint32_t bytes_phi = V * sizeof(real);
+    constexpr uint32_t bytes_n = 2 * V * sizeof(int32_t);
+    constexpr uint32_t stage_bytes = bytes_phi + bytes_n;          // a multiple of 16
+    const int tid = threadIdx.x;
+    double* scratch = reinterpret_cast<double*>(smem_raw + 2 * stage_bytes);   // 6 * 32 doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * stage_bytes + 6 * 32 * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    VillainConsts kc;
+    int dg_scale;
+    villain_consts<false, STRICT>(a, kc, dg_scale);
+    const bool want_obs = a.obs != nullptr;
+
+    auto issue_load = [&](long long chain, int b) {
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        mbar_expect_tx(&bar[b], stage_bytes);
+        bulk_g2s(stage, reinterpret_cast<const real*>(a.phi) + chain * V, bytes_phi, &bar[b]);
+        bulk_g2s(stage + bytes_phi, a.n + chain * 2 * V, bytes_n, &bar[b]);
+    };
+
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0);
+
+    for (int it = 0; chain < a.chains; chain += gridDim.x, ++it) {
+        const int b = it & 1;
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        real* sphi = reinterpret_cast<real*>(stage);
+        int32_t* sn0 = reinterpret_cast<int32_t*>(stage + bytes_phi);
+        int32_t* sn1 = sn0 + V;
+        const long long next = chain + gridDim.x;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const real half_kappa = (real)(kappa / 2);
+
+        mbar_wait(&bar[b], (uint32_t)((it >> 1) & 1));
+
+        int n_acc = 0;
+        double sum_A = 0.0;
+        LinkSums ls;
+        ls.r2 = 0.0; ls.w0 = 0; ls.w1 = 0;
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const bool last = (s == a.n_sweeps - 1);
+            const bool debug = last && (a.accept_mask != nullptr || a.dS_out != nullptr);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const bool collect = want_obs && last && (c == 1);
+#pragma unroll kSiteUnroll
+                for (int j = tid; j < nhalf; j += T) {
+                    const int x0 = j / halfN;
+                    const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
+                    const int site = x0 * N + x1;
+                    const VillainDraw d = villain_get_draw<false, true>(a, chain, s, site, dg_scale);
+                    const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                            collect, ls);
+                    n_acc += o.ok ? 1 : 0;
+                    sum_A += o.A;
+                    if (debug) {
+                        if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                        if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                    }
+                }
+                __syncthreads();
+                if (s == 0 && c == 0 && tid == 0 && next < a.chains) {
+                    // The other buffer was stored from at the end of the previous iteration; once that bulk
+                    // store has finished reading shared memory the next chain can be fetched into it.
+                    bulk_wait_read0();
+                    issue_load(next, b ^ 1);
+                }
+            }
+        }
+
+        if (want_obs) {
+            ChainSums cs;
+            cs.sumA = sum_A; cs.accepted = n_acc;
+            cs.action = ls.r2; cs.w0 = ls.w0; cs.w1 = ls.w1;      // collected during the last colour pass
+            cs.dn2 = villain_dn2_rows<NT, TT>(sn0, sn1, tid);
+            cs = block_reduce_chain(cs, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_VOBS_COUNT;
+                o[SVB_VOBS_ACTION] = (kappa / 2) * cs.action;
+                o[SVB_VOBS_SUM_DN2] = (double)cs.dn2;
+                o[SVB_VOBS_WRAP0] = (double)cs.w0;
+                o[SVB_VOBS_WRAP1] = (double)cs.w1;
+                o[SVB_VOBS_ACCEPTED] = (double)cs.accepted;
+                o[SVB_VOBS_ACCEPTANCE] = cs.sumA;
+            }
+        }
+
+        fence_proxy_async();   // generic-proxy writes of this thread -> visible to the bulk copy engine
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(reinterpret_cast<real*>(a.phi) + chain * V, sphi, bytes_phi);
+            bulk_s2g(a.n + chain * 2 * V, sn0, bytes_n);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait0();   // all stores complete before the CTA (and its shared memory) retires
+}
+
 // ------------------------------------------------------------------------------------------
 // GLOBAL path: one launch per colour pass, straight out of HBM / L2 (any N).
 // ------------------------------------------------------------------------------------------
@@ -703,14 +874,31 @@ static int launch_villain_smem_inst(const VillainArgs& a, cudaStream_t stream, c
     return 0;
 }
 
+template <typename real, bool STRICT, int NT, int TT, int MINB>
+static int launch_villain_pipelined(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    auto kern = villain_smem_pipelined_kernel<real, STRICT, NT, TT, MINB>;
+    const size_t stage = (size_t)NT * NT * (sizeof(real) + 2 * sizeof(int32_t));
+    const size_t smem = 2 * stage + 6 * 32 * sizeof(double) + 16;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TT, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "pipelined villain kernel does not fit an SM at N=%d", NT);
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > a.chains) grid = a.chains;
+    kern<<<(unsigned)grid, TT, smem, stream>>>(a);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
-    // compile-time geometry for the production shapes (Philox mode); everything else takes the generic kernel
-    if (!INJECTED) {
+    const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
+    if (!INJECTED && aligned && sizeof(real) == 8) {
         switch (a.N) {
-            case 16: return launch_villain_smem_inst<real, INJECTED, STRICT, 16, 32, 24>(a, stream, info);
-            case 32: return launch_villain_smem_inst<real, INJECTED, STRICT, 32, 128, SVB_MINB32>(a, stream, info);
-            case 64: return launch_villain_smem_inst<real, INJECTED, STRICT, 64, 256, 3>(a, stream, info);
+            case 16: return launch_villain_pipelined<real, STRICT, 16, 32, 16>(a, stream, info);
+            case 32: return launch_villain_pipelined<real, STRICT, 32, 128, SVB_MINB32>(a, stream, info);
+            case 64: return launch_villain_pipelined<real, STRICT, 64, 256, 1>(a, stream, info);
             default: break;
         }
     }
