@@ -194,3 +194,77 @@ def test_argument_validation_maps_to_python_exceptions():
         ops.villain_sweep(phi.cpu(), n, 0.5)
     with pytest.raises(ValueError):
         NeighborhoodUpdate(svb.Worldline(svb.Lattice2D(8), 0.5))
+
+
+def test_full_size_config2_bit_exact_against_c_oracle():
+    """BASELINE config 2 at full size (L=32, 4096 chains, 3 sweeps): every phi and n of every chain identical
+    to the C oracle replaying the same Philox draws through the reference algorithm; counters too."""
+    from oracle import c_oracle as C
+    N, chains, kappa, sweeps, seed = 32, 4096, 0.5, 3, 20260101
+    phi0, n0 = V.hot_start(np.random.default_rng(42), N, chains)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps, seed=seed, sweep0=7, chain0=100, obs=obs)
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=sweeps, seed=seed, sweep0=7, chain0=100)
+    assert (n.cpu().numpy() == n_ref).all()
+    assert (phi.cpu().numpy() == p_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, VOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-12)
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, kappa), rtol=1e-12)
+    assert (rec[:, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum(axis=(-3, -2, -1))).all()
+    assert (rec[:, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()
+
+
+@pytest.mark.parametrize('N,chains', [(16, 512), (64, 128), (128, 8), (48, 16)])
+def test_other_shapes_bit_exact_against_c_oracle(N, chains):
+    """The other compile-time geometries (16, 64), the global path (128) and a generic even size (48)."""
+    from oracle import c_oracle as C
+    kappa, seed = 0.7, 5
+    phi0, n0 = V.hot_start(np.random.default_rng(N), N, chains)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=2, seed=seed, obs=obs)
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=2, seed=seed)
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, VOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, kappa), rtol=1e-12)
+    assert (rec[:, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum(axis=(-3, -2, -1))).all()
+
+
+def test_kappa_scan_per_chain_couplings():
+    """BASELINE config 4 in miniature: per-chain kappa (a scan across the BKT region) in one launch."""
+    from oracle import c_oracle as C
+    N, per, kappas = 16, 4, np.linspace(0.3, 1.2, 8)
+    chains = per * len(kappas)
+    kc = np.repeat(kappas, per)
+    phi0, n0 = V.hot_start(np.random.default_rng(9), N, chains)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, 1.0, n_sweeps=2, seed=3, kappa_chain=dev(kc), obs=obs)
+    for c in range(chains):
+        p_ref, n_ref, _, _ = C.villain_sweep_philox(phi0[c:c + 1], n0[c:c + 1], kc[c], n_sweeps=2, seed=3, chain0=c)
+        assert (n[c].cpu().numpy() == n_ref[0]).all() and (phi[c].cpu().numpy() == p_ref[0]).all()
+        assert obs[c, VOBS_ACTION].item() == pytest.approx(float(V.action(p_ref[0], n_ref[0], kc[c])), rel=1e-12)
+
+
+def test_exp_clipped_agrees_with_libm_through_acceptance():
+    """The kernel's own min(1, e^-dS) (degree-11 polynomial) against libm: sum of acceptance probabilities of a
+    sweep with all proposals rejected (u = 1) equals the oracle's to 1e-13 relative on a wide spread of dS."""
+    N, chains = 32, 8
+    phi0, n0 = V.hot_start(np.random.default_rng(11), N, chains)
+    for kappa in (0.01, 0.1, 1.0, 5.0):
+        u = np.ones((1, chains, N, N))
+        rng = np.random.default_rng(3)
+        dphi = rng.uniform(-np.pi, np.pi, (1, chains, N, N))
+        dnf = rng.integers(-1, 2, (1, chains, 2, N, N)); dnb = rng.integers(-1, 2, (1, chains, 2, N, N))
+        phi, n = dev(phi0), dev(n0, torch.int32)
+        obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+        ops.villain_sweep(phi, n, kappa, injected={'u': dev(u), 'dphi': dev(dphi), 'dn_fwd': dev(dnf, torch.int32),
+                                                    'dn_bwd': dev(dnb, torch.int32)}, obs=obs)
+        for c in range(chains):
+            st = {}
+            V.neighborhood_step_dense(phi0[c], n0[c], kappa, {'u': u[0, c], 'dphi': dphi[0, c], 'dn_fwd': dnf[0, c], 'dn_bwd': dnb[0, c]}, stats=st)
+            assert obs[c, VOBS_ACCEPTANCE].item() == pytest.approx(st['acceptance'], rel=1e-13)
+            assert obs[c, VOBS_ACCEPTED].item() == 0

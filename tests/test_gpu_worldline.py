@@ -130,3 +130,20 @@ def test_plaquette_update_generator_protocol():
     assert 'single-plaquette proposals accepted' in G.report()
     with pytest.raises(ValueError):
         PlaquetteUpdate(svb.Villain(svb.Lattice2D(8), 0.5))
+
+
+@pytest.mark.parametrize('mode', ['joint', 'vortex', 'coexact'])
+def test_full_size_config3_shard_bit_exact_against_c_oracle(mode):
+    """BASELINE config 3, one GPU's shard at full size (L=64, 1024 chains, 2 sweeps): m and v identical to the C oracle."""
+    from oracle import c_oracle as C
+    N, chains, kappa, W = 64, 1024, 0.5, 1
+    m0, v0 = WL.hot_start(np.random.default_rng(64), N, chains)
+    m, v = dev(m0, torch.int32), dev(v0, torch.int32)
+    obs = torch.zeros((chains, WOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.worldline_sweep(m, v, kappa, W=W, mode=mode, n_sweeps=2, seed=8, chain0=3072, obs=obs)
+    m_ref, v_ref, acc, accp = C.worldline_sweep_philox(m0, v0, kappa, W=W, mode=mode, n_sweeps=2, seed=8, chain0=3072)
+    assert (m.cpu().numpy() == m_ref).all() and (v.cpu().numpy() == v_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, WOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, WOBS_ACCEPTANCE], accp, rtol=1e-12)
+    assert (rec[:, WOBS_DELTA_M_ABS] == 0).all()
