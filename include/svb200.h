@@ -177,6 +177,18 @@ int svb_form_op(int op, int degree, int dtype, const void* in, void* out,
 int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N,
                           double* out, void* stream);
 
+/*
+ * Lattice.correlation (compact.py:465-536) of a per-site field derived from `field`:
+ *   SVB_CORR_SPIN     field = phi (chains,1,N,N) f64|f32, s = exp(i phi)          Spin_Spin.Villain
+ *   SVB_CORR_WINDING  field = n   (chains,2,N,N) i32,     s = dn                  Winding_Winding.Villain (winding.py:77-86)
+ *   SVB_CORR_VORTEX   field = v   (chains,1,N,N) i32,     s = exp(2 pi i v / W)   Vortex_Vortex.Worldline (vortex.py:22-37)
+ * out (chains, N, N, 2) f64 (re, im).  Direct evaluation, N <= 64.
+ */
+#define SVB_CORR_SPIN    0
+#define SVB_CORR_WINDING 1
+#define SVB_CORR_VORTEX  2
+int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int N, int W, double* out, void* stream);
+
 /* Philox4x32-10 block, exposed for known-answer tests: out[4] = philox(ctr[4], key[2]) (host). */
 void svb_philox4x32_10_host(const uint32_t* ctr_host, const uint32_t* key_host, uint32_t* out_host);
 

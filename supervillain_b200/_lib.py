@@ -18,6 +18,7 @@ VOBS_ACTION, VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1, VOBS_ACCEPTED, VOBS_ACCEPTANC
  WOBS_COUNT) = range(8)
 WL_JOINT, WL_VORTEX, WL_COEXACT = 0, 1, 2
 OP_D, OP_DELTA, OP_FACE_SUM, OP_COFACE_SUM = 0, 1, 2, 3
+CORR_SPIN, CORR_WINDING, CORR_VORTEX = 0, 1, 2
 
 E_NULL, E_SHAPE, E_DTYPE, E_PARAM, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4, -5, -6
 
@@ -34,6 +35,7 @@ SIGNATURES = {
     'svb_worldline_observables': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     'svb_form_op': (_i, [_i, _i, _i, _vp, _vp, _i64, _i, _vp]),
     'svb_villain_spin_spin': (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    'svb_correlation': (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp]),
     'svb_philox4x32_10_host': (None, [_vp, _vp, _vp]),
     'svb_villain_draws': (_i, [_i64, _i, _i, _d, _i, _u64, _u64, _u64, _vp, _vp, _vp, _vp]),
 }

@@ -1,8 +1,9 @@
 // svb_observables.cu -- two-point observables that are not simple per-chain scalars.
 //
-// Spin_Spin.Villain (supervillain/observable/spin.py:28-42) through Lattice.correlation
-// (supervillain/lattice/compact.py:465-536):
-//     C[r] = N^-2 sum_x conj(s[x]) s[x - r],   s = exp(i phi)
+// Lattice.correlation (supervillain/lattice/compact.py:465-536), C[r] = N^-2 sum_x conj(s[x]) s[x - r], for
+//   Spin_Spin.Villain        s = exp(i phi)             supervillain/observable/spin.py:28-42
+//   Winding_Winding.Villain  s = dn                     supervillain/observable/winding.py:77-86
+//   Vortex_Vortex.Worldline  s = exp(2 pi i v / W)      supervillain/observable/vortex.py:22-37
 // The reference evaluates it with three FFTs; here it is the direct O(N^4) sum out of shared
 // memory, which is exact to rounding and cheap for the lattices that fit an SM (N <= 64).
 
@@ -10,21 +11,34 @@
 
 namespace svb {
 
-template <typename real>
-__global__ void __launch_bounds__(256) villain_spin_spin_kernel(const real* __restrict__ phi, long long chains, int N,
-                                                                double* __restrict__ out) {
+// KIND: SVB_CORR_SPIN    s = exp(i phi)                       field = phi (chains,1,N,N)
+//       SVB_CORR_WINDING s = dn = d(n) (real)                  field = n   (chains,2,N,N) int32
+//       SVB_CORR_VORTEX  s = exp(2 pi i v / W)                 field = v   (chains,1,N,N) int32
+template <typename real, int KIND>
+__global__ void __launch_bounds__(256) correlation_kernel(const real* __restrict__ field, long long chains, int N, int W,
+                                                          double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int V = N * N;
     double* sre = reinterpret_cast<double*>(smem_raw);
     double* sim = sre + V;
     const double inv_V = 1.0 / (double)V;
     for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
-        const real* g = phi + chain * V;
+        const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
         for (int i = threadIdx.x; i < V; i += blockDim.x) {
-            double s, c;
-            sincos((double)g[i], &s, &c);
-            sre[i] = c;
-            sim[i] = s;
+            if (KIND == SVB_CORR_WINDING) {
+                const int x0 = i / N, x1 = i - x0 * N;
+                const int i0 = ((x0 + 1 == N) ? 0 : x0 + 1) * N + x1, i1 = x0 * N + ((x1 + 1 == N) ? 0 : x1 + 1);
+                // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])
+                sre[i] = (double)(((long long)g[V + i0] - (long long)g[V + i]) - ((long long)g[i1] - (long long)g[i]));
+                sim[i] = 0.0;
+            } else {
+                double s, c;
+                // np.exp(2j * np.pi * v / W): the phase is rounded as (2 pi v) / W   (observable/vortex.py:34)
+                const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[i]) / (double)W : (double)g[i];
+                sincos(ang, &s, &c);
+                sre[i] = c;
+                sim[i] = s;
+            }
         }
         __syncthreads();
         for (int r = threadIdx.x; r < V; r += blockDim.x) {
@@ -59,10 +73,22 @@ __global__ void __launch_bounds__(256) villain_spin_spin_kernel(const real* __re
 
 using namespace svb;
 
-extern "C" int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N, double* out, void* stream) {
-    if (!phi || !out) return fail(SVB_E_NULL, "svb_villain_spin_spin: phi and out are required");
-    if (chains < 0 || N < 1) return fail(SVB_E_SHAPE, "svb_villain_spin_spin: shape");
-    if (phi_dtype != SVB_F64 && phi_dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_villain_spin_spin: dtype %d", phi_dtype);
+template <typename real, int KIND>
+static int launch_correlation(const void* field, long long chains, int N, int W, double* out, size_t smem, long long grid,
+                              cudaStream_t st) {
+    auto kern = correlation_kernel<real, KIND>;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 256, smem, st>>>(reinterpret_cast<const real*>(field), chains, N, W, out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int N, int W, double* out, void* stream) {
+    if (!field || !out) return fail(SVB_E_NULL, "svb_correlation: field and out are required");
+    if (chains < 0 || N < 1) return fail(SVB_E_SHAPE, "svb_correlation: shape");
+    if (kind == SVB_CORR_SPIN && dtype != SVB_F64 && dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_correlation: phi dtype %d", dtype);
+    if (kind != SVB_CORR_SPIN && dtype != SVB_I32) return fail(SVB_E_DTYPE, "svb_correlation: integer fields must be int32");
+    if (kind == SVB_CORR_VORTEX && W < 1) return fail(SVB_E_PARAM, "svb_correlation: W");
     if (chains == 0) return SVB_OK;
     const size_t smem = (size_t)2 * N * N * sizeof(double);
     int dev = 0, max_smem = 0, sms = 0;
@@ -70,16 +96,19 @@ extern "C" int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t cha
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (smem > (size_t)max_smem)
-        return fail(SVB_E_UNSUPPORTED, "svb_villain_spin_spin: direct evaluation needs the lattice in shared memory (N=%d too large)", N);
+        return fail(SVB_E_UNSUPPORTED, "svb_correlation: direct evaluation needs the lattice in shared memory (N=%d too large)", N);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    long long grid = chains < (long long)sms * 4 ? chains : (long long)sms * 4;
-    if (phi_dtype == SVB_F64) {
-        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_spin_spin_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        villain_spin_spin_kernel<double><<<(unsigned)grid, 256, smem, st>>>(reinterpret_cast<const double*>(phi), chains, N, out);
-    } else {
-        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_spin_spin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        villain_spin_spin_kernel<float><<<(unsigned)grid, 256, smem, st>>>(reinterpret_cast<const float*>(phi), chains, N, out);
+    const long long grid = chains < (long long)sms * 4 ? chains : (long long)sms * 4;
+    switch (kind) {
+        case SVB_CORR_SPIN:
+            return dtype == SVB_F64 ? launch_correlation<double, SVB_CORR_SPIN>(field, chains, N, W, out, smem, grid, st)
+                                    : launch_correlation<float, SVB_CORR_SPIN>(field, chains, N, W, out, smem, grid, st);
+        case SVB_CORR_WINDING: return launch_correlation<int32_t, SVB_CORR_WINDING>(field, chains, N, W, out, smem, grid, st);
+        case SVB_CORR_VORTEX: return launch_correlation<int32_t, SVB_CORR_VORTEX>(field, chains, N, W, out, smem, grid, st);
+        default: return fail(SVB_E_PARAM, "svb_correlation: kind %d", kind);
     }
-    SVB_CUDA_TRY(cudaGetLastError());
-    return SVB_OK;
+}
+
+extern "C" int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N, double* out, void* stream) {
+    return svb_correlation(SVB_CORR_SPIN, phi, phi_dtype, chains, N, 1, out, stream);
 }

@@ -181,6 +181,25 @@ def villain_spin_spin(phi, out=None):
     return torch.view_as_complex(out)
 
 
+def correlation(kind, field, W=1, out=None):
+    """Translation-averaged correlator of every chain -> complex128 (chains, N, N).
+
+    kind 'spin' (field = phi), 'winding' (field = n, int32) or 'vortex' (field = v, int32; needs W).
+    """
+    lib = _lib.load()
+    kinds = {'spin': (_lib.CORR_SPIN, 1), 'winding': (_lib.CORR_WINDING, 2), 'vortex': (_lib.CORR_VORTEX, 1)}
+    if kind not in kinds:
+        raise ValueError(f'unknown correlator {kind!r}')
+    code, comps = kinds[kind]
+    chains, N = _fields_shape(field, 'field', comps)
+    dtypes = (torch.float64, torch.float32) if kind == 'spin' else (torch.int32,)
+    if out is None:
+        out = torch.empty((chains, N, N, 2), dtype=torch.float64, device=field.device)
+    _lib.check(lib.svb_correlation(code, _dev(field, 'field', dtypes), _DTYPES[field.dtype], chains, N, int(W),
+                                   _dev(out, 'out', (torch.float64,), (chains, N, N, 2)), _stream()))
+    return torch.view_as_complex(out)
+
+
 def villain_draws(chains, N, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, sweep=0, chain0=0, device='cuda'):
     """The Philox draw mapping evaluated on the device (for tests): u, dphi (chains,N,N), dn (chains,4,N,N)."""
     lib = _lib.load()

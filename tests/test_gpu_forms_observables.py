@@ -113,3 +113,17 @@ def test_ensemble_reference_protocol_config1():
     assert len(cut) == 15 and cut.index_stride == 10
     more = svb.Ensemble.continue_from(cut, 5)
     assert len(more) == 5 and more.index[0] == cut.index[-1] + 10
+
+
+def test_winding_and_vortex_correlators_match_reference(golden_villain_observables, golden_worldline_observables):
+    """Winding_Winding.Villain (winding.py:77-86) and Vortex_Vortex.Worldline (vortex.py:22-37) to 1e-12, and the
+    reference's identity Winding_Winding[origin] == WindingSquared (test/test_winding.py:21-43)."""
+    for c in golden_villain_observables:
+        n = torch.from_numpy(c['n'][None]).to(torch.int32).cuda()
+        C = ops.correlation('winding', n).cpu().numpy()[0]
+        np.testing.assert_allclose(C, c['Winding_Winding'], rtol=0, atol=1e-12)
+        assert C[0, 0].real == pytest.approx(float(c['WindingSquared']), rel=1e-12)
+    for c in golden_worldline_observables:
+        v = torch.from_numpy(c['v'][None]).to(torch.int32).cuda()
+        C = ops.correlation('vortex', v, W=int(c['W'])).cpu().numpy()[0]
+        np.testing.assert_allclose(C, c['Vortex_Vortex'], rtol=0, atol=1e-12)
