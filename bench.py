@@ -36,6 +36,7 @@ UNIT = 'site-updates/s'
 L, KAPPA, W_CONSTRAINT, CHAINS = 32, 0.5, 1, 4096
 BYTES_PER_SITE_UPDATE = 32          # fp64 phi + 2 x int32 n, one read + one write
 ROTATE = 4                           # chain sets rotated through so every step comes from HBM, not L2
+THERMALISE = 200                     # untimed sweeps applied to each synthetic hot start before the warm-up
 WORKLOAD = 'config2: Villain (phi,n) L=32 kappa=0.5 W=1, 4096 chains/GPU, NeighborhoodUpdate checkerboard sweep + action/winding/wrapping'
 
 
@@ -165,6 +166,7 @@ def run_gpu(args):
     from supervillain_b200._lib import VOBS_COUNT
     from supervillain_b200.generator.villain import NeighborhoodUpdate
     from supervillain_b200.hostpath import HostStepper
+    from supervillain_b200 import sharding
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -176,12 +178,16 @@ def run_gpu(args):
 
     S = svb.Villain(svb.Lattice2D(L), KAPPA, W=W_CONSTRAINT)
     G = NeighborhoodUpdate(S, seed=20260101)
-    chain0 = rank * CHAINS                       # global chain ids: results do not depend on the GPU count
+    # weak scaling: 4096 chains per GPU; global chain ids make the draws independent of the GPU count
+    chain0, n_chains = sharding.shard_chains(world * CHAINS, world, rank)
+    assert n_chains == CHAINS
     sets = []
     for r in range(ROTATE):
         E = svb.BatchedEnsemble(S, CHAINS, chain0=chain0)
         sets.append(E._start('hot', 20260101 + 7919 * (rank * ROTATE + r)))
     obs = torch.zeros((CHAINS, VOBS_COUNT), dtype=torch.float64, device=dev)
+    for phi, n in sets:                                       # untimed thermalisation of the synthetic hot starts
+        G.sweep_device(phi, n, THERMALISE, chain0=chain0)
 
     def step(k):
         phi, n = sets[k % ROTATE]
@@ -248,12 +254,8 @@ def run_gpu(args):
            'steps': e2e_steps, 'api': 'HostStepper.step(phi_host, n_host): pinned host fields in and out + observables'}
 
     # ---- final gather of observables (outside the timed region; the only inter-GPU traffic) ----
-    final = obs[:, 0].mean().reshape(1)
-    if world > 1:
-        gathered = [torch.zeros_like(final) for _ in range(world)]
-        dist.all_gather(gathered, final)
-        final = torch.cat(gathered)
-    mean_action_density = float(final.mean().item()) / (L * L)
+    all_obs = sharding.gather_columns(obs)                    # (world * CHAINS, VOBS_COUNT) on every rank
+    mean_action_density = float(all_obs[:, 0].mean().item()) / (L * L)
 
     line = None
     if rank == 0:
@@ -269,11 +271,12 @@ def run_gpu(args):
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'L': L, 'kappa': KAPPA, 'W': W_CONSTRAINT, 'chains_per_gpu': CHAINS,
-                       'sweeps_per_step': args.sweeps_per_step, 'start': 'hot', 'rng': 'philox4x32-10 in-kernel',
+                       'sweeps_per_step': args.sweeps_per_step, 'start': f'hot (phi~U(-pi,pi), n~integers(-2,3)) + {THERMALISE} untimed sweeps',
+                       'rng': 'philox4x32-10 in-kernel',
                        'l2': f'inputs larger than L2: {ROTATE} chain sets ({ROTATE * CHAINS * L * L * 16 >> 20} MiB) rotated',
                        'parallelism': f'chains sharded over {world} GPU(s), no hot-path collective'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
-            'clocks': sampler.summary(), 'check': {'mean_action_density': mean_action_density},
+            'clocks': sampler.summary(), 'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -12,6 +12,7 @@ from . import action
 from . import generator
 from . import batch
 from . import hostpath
+from . import sharding
 from .batch import Batch, Configurations
 from .ensemble import Ensemble, BatchedEnsemble
 from .lattice import Lattice, Lattice2D, Form, d, delta
