@@ -230,7 +230,7 @@ def run_gpu(args):
     launch_s = (ms * 1e-3) / args.steps
     achieved = BYTES_PER_SITE_UPDATE * CHAINS * L * L * args.sweeps_per_step / launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': args.traffic, 'kernel': 'villain_smem_kernel<double,false,false>',
+                'traffic': args.traffic, 'kernel': 'villain_smem_pipelined_kernel<double, STRICT=false, N=32, T=128>',
                 'algorithmic_bytes_per_launch': BYTES_PER_SITE_UPDATE * CHAINS * L * L,
                 'peak_source': peak_src, 'sweeps_per_launch': args.sweeps_per_step}
 

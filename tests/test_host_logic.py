@@ -132,3 +132,21 @@ def test_generators_reject_wrong_action_and_report_format():
     G.accepted, G.proposed, G.acceptance, G.sweeps = 3, 160, 0.2, 10
     assert G.report() == ('There were 3 neighborhood proposals accepted of 160 proposed updates.\n'
                           '    0.018750 acceptance rate\n    0.020000 average Metropolis acceptance probability.')
+
+
+def test_gpu_generators_accept_the_reference_action_objects():
+    """the generators are duck-typed on the action (needs the reference tree: build container only)."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip('reference tree not mounted')
+    sv = refimport.import_reference()
+    from supervillain_b200.generator.villain import NeighborhoodUpdate
+    from supervillain_b200.generator.worldline import PlaquetteUpdate
+    L = sv.lattice.Lattice2D(8)
+    G = NeighborhoodUpdate(sv.action.Villain(L, 0.5, W=2))
+    assert G.kappa == 0.5 and G.Lattice.N == 8 and G.Action.W == 2
+    P = PlaquetteUpdate(sv.action.Worldline(L, 0.5))
+    assert str(P) == 'PlaquetteUpdate'
+    with pytest.raises(ValueError):
+        NeighborhoodUpdate(sv.action.Worldline(L, 0.5))
+    assert len(G.Lattice.checkerboarding) == 2        # _replay uses the reference lattice's own colour lists
