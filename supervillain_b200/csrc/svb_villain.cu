@@ -799,6 +799,47 @@ __global__ void __launch_bounds__(256) villain_obs_kernel(const real* __restrict
     }
 }
 
+// Observables of large lattices: many CTAs per chain, block partials combined with atomics (the summation order of
+// the fp64 partials is then not fixed: results agree to ~1e-16 relative between runs, not bitwise).
+template <typename real>
+__global__ void __launch_bounds__(256) villain_obs_tiled_kernel(const real* __restrict__ phi, const int32_t* __restrict__ n,
+                                                                long long chains, int N, double kappa_scalar,
+                                                                const double* __restrict__ kappa_chain, double* __restrict__ obs,
+                                                                int blocks_per_chain, int sites_per_block) {
+    __shared__ double scratch[6 * 32];
+    const int V = N * N;
+    const long long chain = blockIdx.x / blocks_per_chain;
+    const int blk = blockIdx.x - (int)(chain * blocks_per_chain);
+    const real* gphi = phi + chain * V;
+    const int32_t* gn0 = n + chain * 2 * V;
+    ChainSums cs;
+    cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
+    const int lo = blk * sites_per_block;
+    const int hi = min(V, lo + sites_per_block);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int x0 = i / N, x1 = i - x0 * N;
+        villain_obs_site<real, 0>(gphi, gn0, gn0 + V, N, x0, x1, cs.action, cs.dn2, cs.w0, cs.w1);
+    }
+    cs = block_reduce_chain(cs, scratch);
+    if (threadIdx.x == 0) {
+        const double kappa = kappa_chain ? kappa_chain[chain] : kappa_scalar;
+        double* o = obs + chain * SVB_VOBS_COUNT;
+        atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * cs.action);
+        atomicAdd(o + SVB_VOBS_SUM_DN2, (double)cs.dn2);
+        atomicAdd(o + SVB_VOBS_WRAP0, (double)cs.w0);
+        atomicAdd(o + SVB_VOBS_WRAP1, (double)cs.w1);
+    }
+}
+
+__global__ void villain_zero_record_kernel(double* obs, long long chains, int keep_counters) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < chains) {
+        double* o = obs + c * SVB_VOBS_COUNT;
+        o[SVB_VOBS_ACTION] = 0.0; o[SVB_VOBS_SUM_DN2] = 0.0; o[SVB_VOBS_WRAP0] = 0.0; o[SVB_VOBS_WRAP1] = 0.0;
+        if (!keep_counters) { o[SVB_VOBS_ACCEPTED] = 0.0; o[SVB_VOBS_ACCEPTANCE] = 0.0; }
+    }
+}
+
 __global__ void villain_zero_counters_kernel(double* obs, long long chains) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < chains) {
@@ -905,6 +946,30 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
     return launch_villain_smem_inst<real, INJECTED, STRICT, 0, 0, 1>(a, stream, info);
 }
 
+// Observables of the current state.  Small lattices: one CTA per chain (deterministic order).  Large lattices with few
+// chains: several CTAs per chain + atomics, so a single L=4096 chain still fills the GPU.
+template <typename real>
+static int launch_villain_obs(const real* phi, const int32_t* n, long long chains, int N, double kappa, const double* kappa_chain,
+                              double* obs, int keep_counters, cudaStream_t stream) {
+    const long long V = (long long)N * N;
+    const long long want_ctas = 148LL * 8;
+    if (V <= 16384 || chains >= want_ctas) {
+        long long grid = chains < want_ctas ? chains : want_ctas;
+        villain_obs_kernel<real><<<(unsigned)grid, 256, 0, stream>>>(phi, n, chains, N, kappa, kappa_chain, obs, keep_counters);
+        SVB_CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    int bpc = (int)((want_ctas + chains - 1) / chains);
+    int spb = (int)((V + bpc - 1) / bpc);
+    if (spb < 2048) spb = 2048;
+    bpc = (int)((V + spb - 1) / spb);
+    villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, stream>>>(obs, chains, keep_counters);
+    SVB_CUDA_TRY(cudaGetLastError());
+    villain_obs_tiled_kernel<real><<<(unsigned)(bpc * chains), 256, 0, stream>>>(phi, n, chains, N, kappa, kappa_chain, obs, bpc, spb);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_global(const VillainArgs& a, cudaStream_t stream) {
     const int N = a.N, V = N * N;
@@ -925,12 +990,7 @@ static int launch_villain_global(const VillainArgs& a, cudaStream_t stream) {
             SVB_CUDA_TRY(cudaGetLastError());
         }
     }
-    if (a.obs) {
-        long long grid = a.chains < 148 * 8 ? a.chains : 148 * 8;
-        villain_obs_kernel<real><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<const real*>(a.phi), a.n, a.chains,
-                                                                     N, a.kappa, a.kappa_chain, a.obs, 1);
-        SVB_CUDA_TRY(cudaGetLastError());
-    }
+    if (a.obs) return launch_villain_obs<real>(reinterpret_cast<const real*>(a.phi), a.n, a.chains, N, a.kappa, a.kappa_chain, a.obs, 1, stream);
     return 0;
 }
 
@@ -1001,15 +1061,9 @@ extern "C" int svb_villain_observables(const void* phi, int phi_dtype, const int
     if (phi_dtype != SVB_F64 && phi_dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_villain_observables: phi dtype %d", phi_dtype);
     if (chains == 0) return SVB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    long long grid = chains < 148 * 8 ? chains : 148 * 8;
     if (phi_dtype == SVB_F64)
-        villain_obs_kernel<double><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const double*>(phi), n, chains, N, kappa,
-                                                                   kappa_chain, obs, 0);
-    else
-        villain_obs_kernel<float><<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float*>(phi), n, chains, N, kappa,
-                                                                  kappa_chain, obs, 0);
-    SVB_CUDA_TRY(cudaGetLastError());
-    return SVB_OK;
+        return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 0, st);
+    return launch_villain_obs<float>(reinterpret_cast<const float*>(phi), n, chains, N, kappa, kappa_chain, obs, 0, st);
 }
 
 extern "C" int svb_villain_draws(int64_t chains, int N, int W, double interval_phi, int interval_n, uint64_t seed,

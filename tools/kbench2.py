@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Timing of the other BASELINE shapes: worldline C3 shard, Villain C4 shard (L=128), C5 (L=4096), form ops."""
+import os
+import sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import supervillain_b200 as svb
+from supervillain_b200 import ops
+
+PEAK = 6538.6e9
+
+
+def timeit(fn, n=20, reps=3):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) / n)
+    return best * 1e-3
+
+
+def report(name, updates, bytes_per, t):
+    print(f'{name:58s} {t*1e6:9.1f} us  {updates/t:.3e} upd/s  {updates*bytes_per/t/PEAK*100:5.1f}% of HBM roofline ({bytes_per} B/upd)')
+
+
+which = sys.argv[1:] or ['c3', 'c4', 'c5', 'forms']
+if 'c3' in which:
+    N, CH = 64, 1024
+    S = svb.Worldline(svb.Lattice2D(N), 0.5)
+    sets = [svb.BatchedEnsemble(S, CH)._start('hot', r) for r in range(6)]      # 6 x 48 MiB > L2
+    obs = torch.zeros((CH, ops.WOBS_COUNT), dtype=torch.float64, device='cuda')
+    for mode in ('joint', 'vortex', 'coexact'):
+        k = [0]
+        def f():
+            m, v = sets[k[0] % 6]; k[0] += 1
+            ops.worldline_sweep(m, v, 0.5, mode=mode, seed=1, sweep0=k[0], obs=obs)
+        report(f'worldline {mode} L=64 x 1024 chains (C3 shard), smem path', CH * N * N, 24, timeit(f))
+if 'c4' in which:
+    N, CH = 128, 1024                                   # 1/8 of a GPU's C4 shard; 256 MiB of state
+    S = svb.Villain(svb.Lattice2D(N), 0.5)
+    phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
+    obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
+    kc = torch.linspace(0.3, 1.2, CH, dtype=torch.float64, device='cuda')
+    k = [0]
+    def f():
+        k[0] += 1
+        ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], kappa_chain=kc, obs=obs)
+    report('villain L=128 x 1024 chains (C4), auto path', CH * N * N, 32, timeit(f, n=5))
+if 'c5' in which:
+    N, CH = 4096, 1
+    S = svb.Villain(svb.Lattice2D(N), 0.5)
+    phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
+    obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
+    k = [0]
+    def f():
+        k[0] += 1
+        ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], obs=obs)
+    report('villain L=4096 x 1 chain (C5), auto path', CH * N * N, 32, timeit(f, n=5))
+if 'forms' in which:
+    N, CH = 32, 65536                                    # 512 MiB f64 0-forms
+    a = torch.randn((CH, 1, N, N), dtype=torch.float64, device='cuda')
+    out = torch.empty((CH, 2, N, N), dtype=torch.float64, device='cuda')
+    report('d(0-form f64) L=32 x 65536', CH * N * N, 24, timeit(lambda: ops.form_op('d', 0, a, out)))
+    b = torch.randint(-3, 4, (CH, 2, N, N), dtype=torch.int32, device='cuda')
+    out1 = torch.empty((CH, 1, N, N), dtype=torch.int32, device='cuda')
+    report('d(1-form i32) L=32 x 65536', CH * N * N, 12, timeit(lambda: ops.form_op('d', 1, b, out1)))
+    report('delta(1-form i32) L=32 x 65536', CH * N * N, 12, timeit(lambda: ops.form_op('delta', 1, b, out1)))
+    phi = a
+    n = b
+    obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
+    report('villain_observables L=32 x 65536', CH * N * N, 16, timeit(lambda: ops.villain_observables(phi, n, 0.5, obs=obs)))
