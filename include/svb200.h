@@ -79,7 +79,9 @@ extern "C" {
 #define SVB_WOBS_WRAP1         3
 #define SVB_WOBS_ACCEPTED      4
 #define SVB_WOBS_ACCEPTANCE    5
-#define SVB_WOBS_DELTA_M_ABS   6   /* sum_x |(delta m)[x]|: 0 iff the constraint holds (action/worldline.py:54-70) */
+#define SVB_WOBS_DELTA_M_ABS   6   /* sum_x |(delta m)[x]|: 0 iff the constraint holds (action/worldline.py:54-70);
+                                      evaluated by svb_worldline_observables; a sweep may report -1 = not evaluated
+                                      (the move preserves delta m identically) */
 #define SVB_WOBS_COUNT         7
 
 /* worldline sweep modes */

@@ -78,17 +78,18 @@ def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
 
 
 def worldline_draws(seed, chain, sweep, N, mode, interval=1):
-    """Dense per-plaquette proposals: u, a (dm | dv | t) and, for mode 'joint', b (dv)."""
+    """Dense per-plaquette proposals: u, a (dm | dv | t) and, for mode 'joint', b (dv).
+
+    u = (k44 + 1/2) 2^-44 with k44 = x << 12 | y >> 20; dm sign = bit 19 of y; choices = (w * K) >> 32."""
     site = np.arange(N * N, dtype=np.uint64)
     x, y, z, w = philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE)
     ku = (x << np.uint64(12)) | (y >> np.uint64(20))
     u = (ku.astype(np.float64) + 0.5) * TWO_M44
-    k40 = ((z & np.uint64(0xFF)) << np.uint64(32)) | w
     if mode == 'joint':
         a = np.where(((y >> np.uint64(19)) & np.uint64(1)) == 1, 1, -1).astype(np.int64)
-        b = ((k40 * np.uint64(3)) >> np.uint64(40)).astype(np.int64) - 1
+        b = ((w * np.uint64(3)) >> np.uint64(32)).astype(np.int64) - 1
     else:
-        idx = ((k40 * np.uint64(2 * interval)) >> np.uint64(40)).astype(np.int64)
+        idx = ((w * np.uint64(2 * interval)) >> np.uint64(32)).astype(np.int64)
         a = np.where(idx < interval, idx - interval, idx - interval + 1)
         b = np.zeros_like(a)
     return {'u': u.reshape(N, N), 'a': a.reshape(N, N), 'b': b.reshape(N, N)}

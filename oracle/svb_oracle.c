@@ -85,12 +85,11 @@ void svo_worldline_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t 
     philox_site(seed, chain, sweep, site, 2u, w);
     uint64_t ku = ((uint64_t)w[0] << 12) | (uint64_t)(w[1] >> 20);
     *u = ((double)ku + 0.5) * 0x1p-44;
-    uint64_t k40 = ((uint64_t)(w[2] & 0xFFu) << 32) | (uint64_t)w[3];
     if (mode == 0) {
         *a = ((w[1] >> 19) & 1u) ? +1 : -1;
-        *b = (int)((k40 * 3ull) >> 40) - 1;
+        *b = (int)(((uint64_t)w[3] * 3ull) >> 32) - 1;
     } else {
-        int idx = (int)((k40 * (uint64_t)(2 * interval)) >> 40);
+        int idx = (int)(((uint64_t)w[3] * (uint64_t)(2 * interval)) >> 32);
         *a = (idx < interval) ? idx - interval : idx - interval + 1;
         *b = 0;
     }

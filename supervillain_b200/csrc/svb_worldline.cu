@@ -27,6 +27,7 @@ struct WorldlineArgs {
     int interval;
     int n_sweeps;
     unsigned long long seed, sweep0, chain0;
+    uint32_t round_key[20];   // Philox key schedule precomputed on the host
     const double* inj_u;
     const int32_t* inj_a;
     const int32_t* inj_b;
@@ -41,27 +42,34 @@ struct WlDraw {
     int b;   // dv (JOINT)
 };
 
-// Philox draw mapping for one plaquette: 44 bits -> u in (0,1); 1 bit -> dm sign (JOINT);
-// a 40-bit fraction -> one choice among K values.
+// Philox draw mapping for one plaquette: 44 bits (x, top of y) -> u in (0,1); bit 19 of y -> dm sign
+// (JOINT); the 32-bit fraction w / 2^32 -> one choice among K values (choice = (w * K) >> 32).
 template <int MODE>
-__host__ __device__ __forceinline__ WlDraw worldline_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
-                                                                 uint32_t site, int interval) {
-    Philox4 p = philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE);
+__host__ __device__ __forceinline__ WlDraw worldline_draw_from_bits(const Philox4& p, int interval) {
     WlDraw d;
     const double two_m44 = 5.6843418860808015e-14;  // 2^-44
-    uint64_t ku = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
+    const uint64_t ku = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
+#ifdef __CUDA_ARCH__
+    d.u = (__hiloint2double(0x43300000 | (int)(ku >> 32), (int)(uint32_t)ku) - 4503599627370495.5) * two_m44;   // exact
+#else
     d.u = ((double)(long long)ku + 0.5) * two_m44;
-    uint64_t k40 = ((uint64_t)(p.z & 0xFFu) << 32) | (uint64_t)p.w;
+#endif
     if (MODE == SVB_WL_JOINT) {
-        d.a = ((p.y >> 19) & 1u) ? +1 : -1;           // rng.choice([-1,+1])   (plaquette.py:58)
-        d.b = (int)((k40 * 3ull) >> 40) - 1;          // rng.choice([-1,0,+1]) (plaquette.py:59)
+        d.a = ((p.y >> 19) & 1u) ? +1 : -1;                               // rng.choice([-1,+1])   (plaquette.py:58)
+        d.b = (int)(((uint64_t)p.w * 3ull) >> 32) - 1;                    // rng.choice([-1,0,+1]) (plaquette.py:59)
     } else {
         // choice over [-I..-1, 1..I]  (vortex.py:39, coexact.py:40)
-        int idx = (int)((k40 * (uint64_t)(2 * interval)) >> 40);
+        const int idx = (int)(((uint64_t)p.w * (uint64_t)(2 * interval)) >> 32);
         d.a = (idx < interval) ? idx - interval : idx - interval + 1;
         d.b = 0;
     }
     return d;
+}
+
+template <int MODE>
+__host__ __device__ __forceinline__ WlDraw worldline_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
+                                                                 uint32_t site, int interval) {
+    return worldline_draw_from_bits<MODE>(philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE), interval);
 }
 
 template <int MODE, bool INJECTED>
@@ -306,6 +314,245 @@ __global__ void __launch_bounds__(256) worldline_smem_kernel(WorldlineArgs a, in
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Production instantiation: W = 1, Philox draws, compile-time geometry, TMA bulk copies with
+// STAGES shared-memory stages per CTA.  With W = 1 every f = m - delta v is an integer, so the
+// whole neighbourhood arithmetic is int32 and only the final products are fp64 -- with exactly the
+// roundings of the reference's expressions (each product below has exact integer factors times one
+// rounded constant), so dS is bit-equal to the general path and to the oracle.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Philox4 philox_plaquette_keys(const WorldlineArgs& a, uint64_t chain, uint64_t sweep, uint32_t site) {
+    uint32_t c0 = site, c1 = (uint32_t)chain, c2 = (uint32_t)sweep;
+    uint32_t c3 = (STREAM_WORLDLINE_PLAQUETTE << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
+                  (uint32_t)((sweep >> 32) & 0xFFFFu);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(0xD2511F53u, c0, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ a.round_key[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ a.round_key[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ double wl_int_to_double(int n) {   // exact, on the fp64 adder
+    return __hiloint2double(0x43300000, n ^ 0x80000000) - 4503601774854144.0;
+}
+
+struct WlSums {
+    long long f2;      // sum of f^2 over links (an integer when W = 1)
+    long long df2;     // sum of (d f)^2 over plaquettes
+    int w0, w1;        // sum of m_0, m_1
+};
+
+template <int MODE, int NT>
+__device__ __forceinline__ PlaqOut worldline_plaquette_update_w1(int32_t* __restrict__ m0, int32_t* __restrict__ m1,
+                                                                 int32_t* __restrict__ v, int x0, int x1, double inv_kappa,
+                                                                 double half_inv_kappa, const WlDraw& d, bool collect,
+                                                                 WlSums& sums) {
+    const int xp0 = (x0 + 1) & (NT - 1), xm0 = (x0 - 1) & (NT - 1);
+    const int xp1 = (x1 + 1) & (NT - 1), xm1 = (x1 - 1) & (NT - 1);
+    const int i_c = x0 * NT + x1;
+    const int i_p0 = xp0 * NT + x1, i_m0 = xm0 * NT + x1;
+    const int i_p1 = x0 * NT + xp1, i_m1 = x0 * NT + xm1;
+    const int vc = v[i_c], vp0 = v[i_p0], vm0 = v[i_m0], vp1 = v[i_p1], vm1 = v[i_m1];
+    const int m_0x = m0[i_c], m_0p = m0[i_p1], m_1x = m1[i_c], m_1p = m1[i_p0];
+    // f = m - delta(v) on the four boundary links (W = 1: exact integers)
+    const int f_0x = m_0x - (vc - vm1);
+    const int f_0p = m_0p - (vp1 - vc);
+    const int f_1x = m_1x - (vm0 - vc);
+    const int f_1p = m_1p - (vc - vp0);
+    const int curl = (f_0x + f_1p) - f_0p - f_1x;        // f1 + f2 - f3 - f4 = (d f)[x]
+    double dS;
+    int df_int;                                          // change of f on the (+)-oriented links if accepted
+    if (MODE == SVB_WL_JOINT) {
+        df_int = d.a - d.b;                              // delta_f = dm - dv / 1
+        // (delta_f / kappa) * (f1 + f2 - f3 - f4 + 2 delta_f): |delta_f| <= 2, so delta_f / kappa == delta_f * fl(1/kappa)
+        dS = __dmul_rn(__dmul_rn(wl_int_to_double(df_int), inv_kappa), wl_int_to_double(curl + 2 * df_int));
+    } else {
+        const int a = d.a;
+        const double P = __dmul_rn(half_inv_kappa, wl_int_to_double(a));      // (0.5/kappa) * a
+        double t_1x, t_1p, t_0x, t_0p;
+        if (MODE == SVB_WL_VORTEX) {
+            df_int = -a;                                 // f changes by -sign * a
+            t_1x = __dmul_rn(P, wl_int_to_double(2 * f_1x + a));
+            t_1p = __dmul_rn(-P, wl_int_to_double(2 * f_1p - a));
+            t_0x = __dmul_rn(-P, wl_int_to_double(2 * f_0x - a));
+            t_0p = __dmul_rn(P, wl_int_to_double(2 * f_0p + a));
+        } else {
+            df_int = a;
+            t_1x = __dmul_rn(-P, wl_int_to_double(2 * f_1x - a));
+            t_1p = __dmul_rn(P, wl_int_to_double(2 * f_1p + a));
+            t_0x = __dmul_rn(P, wl_int_to_double(2 * f_0x + a));
+            t_0p = __dmul_rn(-P, wl_int_to_double(2 * f_0p - a));
+        }
+        dS = __dadd_rn(t_1x, t_1p);
+        dS = __dadd_rn(dS, t_0x);
+        dS = __dadd_rn(dS, t_0p);
+    }
+    const double acc = exp_clipped(-dS);
+    const bool ok = d.u < acc;
+    if (ok) {
+        if (MODE != SVB_WL_VORTEX) {
+            m0[i_c] = m_0x + d.a;
+            m1[i_p0] = m_1p + d.a;
+            m0[i_p1] = m_0p - d.a;
+            m1[i_c] = m_1x - d.a;
+        }
+        if (MODE == SVB_WL_JOINT) v[i_c] = vc + d.b;
+        if (MODE == SVB_WL_VORTEX) v[i_c] = vc + d.a;
+    }
+    if (collect) {
+        const int s = ok ? df_int : 0;
+        const int g0 = f_0x + s, g1 = f_1p + s, g2 = f_0p - s, g3 = f_1x - s;      // final f on the four links
+        sums.f2 += (long long)g0 * g0 + (long long)g1 * g1 + (long long)g2 * g2 + (long long)g3 * g3;
+        const int c2 = curl + 4 * s;
+        sums.df2 += (long long)c2 * c2;
+        sums.w0 += m_0x + m_0p;                                                    // dm cancels within a direction
+        sums.w1 += m_1x + m_1p;
+    }
+    PlaqOut o;
+    o.A = acc;
+    o.ok = ok;
+    o.dS = dS;
+    return o;
+}
+
+// (d f)^2 of the plaquette at (x0, x1) from the final fields (W = 1)
+template <int NT>
+__device__ __forceinline__ long long worldline_curl2_w1(const int32_t* __restrict__ m0, const int32_t* __restrict__ m1,
+                                                        const int32_t* __restrict__ v, int x0, int x1) {
+    const int xp0 = (x0 + 1) & (NT - 1), xm0 = (x0 - 1) & (NT - 1);
+    const int xp1 = (x1 + 1) & (NT - 1), xm1 = (x1 - 1) & (NT - 1);
+    const int i_c = x0 * NT + x1;
+    const int vc = v[i_c];
+    // curl of m minus curl of delta v:  (d delta v)[x] = 4 v[x] - v[x-e1] - v[x+e1] - v[x-e0] - v[x+e0]
+    const int cm = (m0[i_c] + m1[xp0 * NT + x1]) - m0[x0 * NT + xp1] - m1[i_c];
+    const int cv = 4 * vc - v[x0 * NT + xm1] - v[x0 * NT + xp1] - v[xm0 * NT + x1] - v[xp0 * NT + x1];
+    const int c = cm - cv;
+    return (long long)c * c;
+}
+
+template <int MODE, int NT, int TT, int MINB, int STAGES>
+__global__ void __launch_bounds__(TT, MINB) worldline_smem_fast_kernel(const __grid_constant__ WorldlineArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = NT * NT, T = TT;
+    constexpr int halfN = N / 2, nhalf = V / 2;
+    constexpr uint32_t bytes_m = 2 * V * sizeof(int32_t);
+    constexpr uint32_t bytes_v = V * sizeof(int32_t);
+    constexpr uint32_t stage_bytes = bytes_m + bytes_v;
+    const int tid = threadIdx.x;
+    double* scratch = reinterpret_cast<double*>(smem_raw + STAGES * stage_bytes);      // 7 * 32 doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + STAGES * stage_bytes + 7 * 32 * sizeof(double));
+
+    if (tid == 0) {
+        for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const bool want_obs = a.obs != nullptr;
+
+    auto issue_load = [&](long long chain, int b) {
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        mbar_expect_tx(&bar[b], stage_bytes);
+        bulk_g2s(stage, a.m + chain * 2 * V, bytes_m, &bar[b]);
+        bulk_g2s(stage + bytes_m, a.v + chain * V, bytes_v, &bar[b]);
+    };
+
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0);
+
+    for (int it = 0; chain < a.chains; chain += gridDim.x, ++it) {
+        const int b = (STAGES == 2) ? (it & 1) : 0;
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        int32_t* sm0 = reinterpret_cast<int32_t*>(stage);
+        int32_t* sm1 = sm0 + V;
+        int32_t* sv = reinterpret_cast<int32_t*>(stage + bytes_m);
+        const long long next = chain + gridDim.x;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double inv_kappa = __ddiv_rn(1.0, kappa), half_inv_kappa = __ddiv_rn(0.5, kappa);
+
+        mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
+
+        int n_acc = 0;
+        double sum_A = 0.0;
+        WlSums ws;
+        ws.f2 = 0; ws.df2 = 0; ws.w0 = 0; ws.w1 = 0;
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const bool last = (s == a.n_sweeps - 1);
+            const bool debug = last && (a.accept_mask != nullptr || a.dS_out != nullptr);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const bool collect = want_obs && last && (c == 1);
+#pragma unroll 1
+                for (int j = tid; j < nhalf; j += T) {
+                    const int x0 = j / halfN;
+                    const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
+                    const int site = x0 * N + x1;
+                    const Philox4 bits = philox_plaquette_keys(a, a.chain0 + (unsigned long long)chain,
+                                                               a.sweep0 + (unsigned long long)s, (uint32_t)site);
+                    const WlDraw d = worldline_draw_from_bits<MODE>(bits, a.interval);
+                    const PlaqOut o = worldline_plaquette_update_w1<MODE, NT>(sm0, sm1, sv, x0, x1, inv_kappa, half_inv_kappa, d,
+                                                                              collect, ws);
+                    n_acc += o.ok ? 1 : 0;
+                    sum_A += o.A;
+                    if (debug) {
+                        if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                        if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                    }
+                }
+                __syncthreads();
+                if (STAGES == 2 && s == 0 && c == 0 && tid == 0 && next < a.chains) {
+                    bulk_wait_read0();
+                    issue_load(next, b ^ 1);
+                }
+            }
+        }
+
+        if (want_obs) {
+            // links and colour-1 plaquettes were collected in the last pass; the colour-0 plaquettes' (d f)^2 needs the
+            // final fields of their neighbours, so it is evaluated here
+#pragma unroll 1
+            for (int j = tid; j < nhalf; j += T) {
+                const int x0 = j / halfN;
+                const int x1 = 2 * (j - x0 * halfN) + (x0 & 1);
+                ws.df2 += worldline_curl2_w1<NT>(sm0, sm1, sv, x0, x1);
+            }
+            double sred[7] = {0, 0, 0, 0, 0, sum_A, 0};
+            // integer sums: exact in double as long as they stay below 2^53
+            sred[0] = (double)ws.f2; sred[1] = (double)ws.df2; sred[2] = (double)ws.w0; sred[3] = (double)ws.w1;
+            sred[4] = (double)n_acc;
+            block_sum<7>(sred, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_WOBS_COUNT;
+                o[SVB_WOBS_SUM_F2] = sred[0];
+                o[SVB_WOBS_SUM_DF2] = sred[1];
+                o[SVB_WOBS_WRAP0] = sred[2];
+                o[SVB_WOBS_WRAP1] = sred[3];
+                o[SVB_WOBS_ACCEPTED] = sred[4];
+                o[SVB_WOBS_ACCEPTANCE] = sred[5];
+                o[SVB_WOBS_DELTA_M_ABS] = -1.0;       // not evaluated by the sweep (the move preserves delta m identically)
+            }
+        }
+
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            if (MODE != SVB_WL_VORTEX) bulk_s2g(a.m + chain * 2 * V, sm0, bytes_m);
+            if (MODE != SVB_WL_COEXACT) bulk_s2g(a.v + chain * V, sv, bytes_v);
+            bulk_commit();
+            if (STAGES == 1) {
+                bulk_wait_read0();
+                if (next < a.chains) issue_load(next, 0);
+            }
+        }
+        if (STAGES == 1) __syncthreads();
+    }
+    if (tid == 0) bulk_wait0();
+}
+
 template <int MODE, bool INJECTED>
 __global__ void __launch_bounds__(256) worldline_colour_pass_kernel(WorldlineArgs a, int sweep, int colour, int blocks_per_chain,
                                                                     int write_debug) {
@@ -451,6 +698,22 @@ static int launch_worldline_global(const WorldlineArgs& a, cudaStream_t stream) 
     return 0;
 }
 
+template <int MODE, int NT, int TT, int MINB, int STAGES>
+static int launch_worldline_fast(const WorldlineArgs& a, cudaStream_t stream, int sm_count) {
+    auto kern = worldline_smem_fast_kernel<MODE, NT, TT, MINB, STAGES>;
+    const size_t smem = (size_t)STAGES * NT * NT * 3 * sizeof(int32_t) + 7 * 32 * sizeof(double) + 16;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TT, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "fast worldline kernel does not fit an SM at N=%d", NT);
+    long long grid = (long long)per_sm * sm_count;
+    if (grid > a.chains) grid = a.chains;
+    kern<<<(unsigned)grid, TT, smem, stream>>>(a);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <int MODE>
 static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cudaStream_t stream) {
     int dev = 0, sm_count = 0, max_smem = 0;
@@ -461,6 +724,15 @@ static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cu
     if (path == SVB_PATH_SMEM) {
         if (worldline_smem_bytes(a.N) > (size_t)max_smem)
             return fail(SVB_E_UNSUPPORTED, "N=%d does not fit shared memory; use SVB_PATH_GLOBAL", a.N);
+        const bool aligned = ((uintptr_t)a.m % 16 == 0) && ((uintptr_t)a.v % 16 == 0);
+        if (rng_mode == SVB_RNG_PHILOX && a.W == 1 && aligned) {
+            switch (a.N) {
+                case 16: return launch_worldline_fast<MODE, 16, 32, 16, 2>(a, stream, sm_count);
+                case 32: return launch_worldline_fast<MODE, 32, 128, 6, 2>(a, stream, sm_count);
+                case 64: return launch_worldline_fast<MODE, 64, 256, 4, 1>(a, stream, sm_count);
+                default: break;
+            }
+        }
         return rng_mode == SVB_RNG_INJECTED ? launch_worldline_smem<MODE, true>(a, stream, sm_count)
                                             : launch_worldline_smem<MODE, false>(a, stream, sm_count);
     }
@@ -492,6 +764,10 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
     WorldlineArgs a;
     a.m = m; a.v = v; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
     a.interval = interval; a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     a.inj_u = inj_u; a.inj_a = inj_a; a.inj_b = inj_b; a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (mode) {
