@@ -708,6 +708,253 @@ __global__ void __launch_bounds__(TT, MINB) villain_smem_pipelined_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------
+// SMEM path with the residuals resident (production instantiation, Philox draws).
+//
+// The reference keeps r = d(phi) - 2 pi n as a field and patches it after every accepted colour
+// (neighborhood.py:91, :129).  Doing the same in shared memory removes, from every proposal, the five
+// phi loads, four n loads, four int->double conversions and eight fp64 operations that recomputing r
+// costs: a proposal reads four doubles of r, and phi / n are touched only when it is accepted.  In STRICT
+// arithmetic r is rebuilt at the start of every sweep and patched as (r + d(dphi)) - 2 pi dn, exactly the
+// reference's roundings, so dS is bit-equal to the reference; in FAST arithmetic r is carried across the
+// sweeps of a launch and patched with one add.  2 pi dn comes from a K-entry table in shared memory
+// (K = 2 interval_n + 1 distinct proposals), so no integer is converted to fp64 on the hot path.
+// ------------------------------------------------------------------------------------------
+struct VillainDigits {
+    double u;
+    double dphi;
+    int digit[4];      // proposal index in [0, K) for links f0, b0, f1, b1;  dn = W * (digit - interval_n)
+};
+
+__device__ __forceinline__ VillainDigits villain_digits_from_bits(const Philox4& p, double interval_phi, uint32_t K) {
+    VillainDigits d;
+    const double bias = 4503599627370495.5;   // 2^52 - 1/2
+    const double kphi_half = __hiloint2double(0x43300000 | (int)(p.x >> 20), (int)((p.x << 12) | (p.y >> 20))) - bias;
+    const double ku_half = __hiloint2double(0x43300000 | (int)(p.y & 0xFFFFFu), (int)p.z) - bias;
+    d.u = ku_half * 2.220446049250313e-16;                                                    // 2^-52
+    d.dphi = __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, kphi_half * 5.6843418860808015e-14));
+    uint32_t f = p.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t prod = (uint64_t)f * K;
+        f = (uint32_t)prod;
+        d.digit[i] = (int)(prod >> 32);
+    }
+    return d;
+}
+
+template <bool STRICT, int NT>
+__device__ __forceinline__ SiteOut villain_site_update_resid(double* __restrict__ phi, int32_t* __restrict__ n0,
+                                                             int32_t* __restrict__ n1, double* __restrict__ r0,
+                                                             double* __restrict__ r1, const double* __restrict__ tpdn, int x0,
+                                                             int x1, double half_kappa, int W, int interval_n,
+                                                             const VillainDigits& d) {
+    using A = Arith<double, STRICT>;
+    const int i_c = x0 * NT + x1;
+    const int i_b0 = ((x0 - 1) & (NT - 1)) * NT + x1;
+    const int i_b1 = x0 * NT + ((x1 - 1) & (NT - 1));
+    const double r_f0 = r0[i_c], r_b0 = r0[i_b0], r_f1 = r1[i_c], r_b1 = r1[i_b1];
+    const double t0 = tpdn[d.digit[0]], t1 = tpdn[d.digit[1]], t2 = tpdn[d.digit[2]], t3 = tpdn[d.digit[3]];   // 2 pi dn
+    const double dphi = d.dphi;
+    // dr = d(dphi) - 2 pi dn   (neighborhood.py:110)
+    const double dr_f0 = A::sub(-dphi, t0), dr_b0 = A::sub(dphi, t1), dr_f1 = A::sub(-dphi, t2), dr_b1 = A::sub(dphi, t3);
+    double dS;
+    if (STRICT) {
+        dS = A::link(half_kappa, dr_f0, r_f0);
+        dS = A::add(dS, A::link(half_kappa, dr_b0, r_b0));
+        dS = A::add(dS, A::link(half_kappa, dr_f1, r_f1));
+        dS = A::add(dS, A::link(half_kappa, dr_b1, r_b1));
+    } else {
+        double acc2 = dr_f0 * fma(2.0, r_f0, dr_f0);
+        acc2 = fma(dr_b0, fma(2.0, r_b0, dr_b0), acc2);
+        acc2 = fma(dr_f1, fma(2.0, r_f1, dr_f1), acc2);
+        acc2 = fma(dr_b1, fma(2.0, r_b1, dr_b1), acc2);
+        dS = half_kappa * acc2;
+    }
+    const double acc = exp_clipped(-dS);
+    const bool ok = d.u < acc;
+    if (ok) {
+        phi[i_c] = A::add(phi[i_c], dphi);
+        n0[i_c] += W * (d.digit[0] - interval_n);
+        n0[i_b0] += W * (d.digit[1] - interval_n);
+        n1[i_c] += W * (d.digit[2] - interval_n);
+        n1[i_b1] += W * (d.digit[3] - interval_n);
+        if (STRICT) {       // r = r + d(dphi) - 2 pi dn, left to right   (neighborhood.py:129)
+            r0[i_c] = __dsub_rn(__dadd_rn(r_f0, -dphi), t0);
+            r0[i_b0] = __dsub_rn(__dadd_rn(r_b0, dphi), t1);
+            r1[i_c] = __dsub_rn(__dadd_rn(r_f1, -dphi), t2);
+            r1[i_b1] = __dsub_rn(__dadd_rn(r_b1, dphi), t3);
+        } else {
+            r0[i_c] = r_f0 + dr_f0;
+            r0[i_b0] = r_b0 + dr_b0;
+            r1[i_c] = r_f1 + dr_f1;
+            r1[i_b1] = r_b1 + dr_b1;
+        }
+    }
+    SiteOut o;
+    o.A = acc;
+    o.ok = ok;
+    o.dS = dS;
+    return o;
+}
+
+template <bool STRICT, int NT, int TT, int MINB, int STAGES>
+__global__ void __launch_bounds__(TT, MINB) villain_smem_resid_kernel(const __grid_constant__ VillainArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = NT * NT, T = TT;
+    constexpr int halfN = N / 2, nhalf = V / 2;
+    constexpr uint32_t bytes_phi = V * sizeof(double);
+    constexpr uint32_t bytes_n = 2 * V * sizeof(int32_t);
+    constexpr uint32_t stage_bytes = bytes_phi + bytes_n;
+    static_assert(V % (2 * T) == 0, "unsupported geometry");
+    const int tid = threadIdx.x;
+    double* sr0 = reinterpret_cast<double*>(smem_raw + STAGES * stage_bytes);
+    double* sr1 = sr0 + V;
+    double* tpdn = sr1 + V;                                                   // 64 doubles: 2 pi W (k - interval_n)
+    double* scratch = tpdn + 64;                                              // 6 * 32 doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + 6 * 32);
+
+    if (tid == 0) {
+        for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
+        fence_mbar_init();
+    }
+    const uint32_t K = (uint32_t)(2 * a.interval_n + 1);
+    if (tid < (int)K) tpdn[tid] = __dmul_rn(SVB_TWO_PI, (double)(a.W * (tid - a.interval_n)));   // numpy: 2*np.pi*change_n
+    __syncthreads();
+    const bool want_obs = a.obs != nullptr;
+
+    auto issue_load = [&](long long chain, int b) {
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        mbar_expect_tx(&bar[b], stage_bytes);
+        bulk_g2s(stage, reinterpret_cast<const double*>(a.phi) + chain * V, bytes_phi, &bar[b]);
+        bulk_g2s(stage + bytes_phi, a.n + chain * 2 * V, bytes_n, &bar[b]);
+    };
+
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0);
+
+    for (int it = 0; chain < a.chains; chain += gridDim.x, ++it) {
+        const int b = (STAGES == 2) ? (it & 1) : 0;
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        double* sphi = reinterpret_cast<double*>(stage);
+        int32_t* sn0 = reinterpret_cast<int32_t*>(stage + bytes_phi);
+        int32_t* sn1 = sn0 + V;
+        const long long next = chain + gridDim.x;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double half_kappa = kappa / 2;
+
+        mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
+
+        int n_acc = 0;
+        double sum_A = 0.0;
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const bool last = (s == a.n_sweeps - 1);
+            const bool debug = last && (a.accept_mask != nullptr || a.dS_out != nullptr);
+            if (s == 0 || STRICT) {
+                // r = d(phi) - 2 pi n   (neighborhood.py:91), two horizontally adjacent sites per thread per step:
+                // consecutive threads touch consecutive 16-byte pairs, so every access is conflict-free
+#pragma unroll
+                for (int q = 0; q < V / (2 * T); ++q) {
+                    const int i = 2 * (tid + T * q);                       // sites i, i + 1 (same row)
+                    const int x0 = i / N, x1 = i - x0 * N;
+                    const int iup = ((x0 + 1) & (N - 1)) * N + x1;
+                    const double2 pc = *reinterpret_cast<const double2*>(sphi + i);
+                    const double2 pu = *reinterpret_cast<const double2*>(sphi + iup);
+                    const double pr = sphi[x0 * N + ((x1 + 2) & (N - 1))];
+                    const int2 a0 = *reinterpret_cast<const int2*>(sn0 + i);
+                    const int2 a1 = *reinterpret_cast<const int2*>(sn1 + i);
+                    double2 o0, o1;
+                    o0.x = __dsub_rn(__dsub_rn(pu.x, pc.x), __dmul_rn(SVB_TWO_PI, int_to_double(a0.x)));
+                    o0.y = __dsub_rn(__dsub_rn(pu.y, pc.y), __dmul_rn(SVB_TWO_PI, int_to_double(a0.y)));
+                    o1.x = __dsub_rn(__dsub_rn(pc.y, pc.x), __dmul_rn(SVB_TWO_PI, int_to_double(a1.x)));
+                    o1.y = __dsub_rn(__dsub_rn(pr, pc.y), __dmul_rn(SVB_TWO_PI, int_to_double(a1.y)));
+                    *reinterpret_cast<double2*>(sr0 + i) = o0;
+                    *reinterpret_cast<double2*>(sr1 + i) = o1;
+                }
+                __syncthreads();
+            }
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll kSiteUnroll
+                for (int j = tid; j < nhalf; j += T) {
+                    const int x0 = j / halfN;
+                    const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
+                    const int site = x0 * N + x1;
+                    const Philox4 bits = philox_site_keys(a, a.chain0 + (unsigned long long)chain,
+                                                          a.sweep0 + (unsigned long long)s, (uint32_t)site);
+                    const VillainDigits d = villain_digits_from_bits(bits, a.interval_phi, K);
+                    const SiteOut o = villain_site_update_resid<STRICT, NT>(sphi, sn0, sn1, sr0, sr1, tpdn, x0, x1, half_kappa,
+                                                                            a.W, a.interval_n, d);
+                    n_acc += o.ok ? 1 : 0;
+                    sum_A += o.A;
+                    if (debug) {
+                        if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                        if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+                    }
+                }
+                __syncthreads();
+                if (STAGES == 2 && s == 0 && c == 0 && tid == 0 && next < a.chains) {
+                    bulk_wait_read0();
+                    issue_load(next, b ^ 1);
+                }
+            }
+        }
+
+        if (want_obs) {
+            // one pass over site pairs: sum r^2 (the residuals are resident), sum n, sum (dn)^2; conflict-free vector loads
+            ChainSums cs;
+            cs.sumA = sum_A; cs.accepted = n_acc; cs.action = 0.0; cs.w0 = 0; cs.w1 = 0;
+            long long dn2 = 0;
+#pragma unroll
+            for (int q = 0; q < V / (2 * T); ++q) {
+                const int i = 2 * (tid + T * q);
+                const int x0 = i / N, x1 = i - x0 * N;
+                const int iup = ((x0 + 1) & (N - 1)) * N + x1;
+                const double2 A0 = *reinterpret_cast<const double2*>(sr0 + i);
+                const double2 A1 = *reinterpret_cast<const double2*>(sr1 + i);
+                cs.action = fma(A0.x, A0.x, cs.action);
+                cs.action = fma(A0.y, A0.y, cs.action);
+                cs.action = fma(A1.x, A1.x, cs.action);
+                cs.action = fma(A1.y, A1.y, cs.action);
+                const int2 h = *reinterpret_cast<const int2*>(sn0 + i);          // n0[x], n0[x + e1]
+                const int hr = sn0[x0 * N + ((x1 + 2) & (N - 1))];                // n0[x + 2 e1]
+                const int2 me = *reinterpret_cast<const int2*>(sn1 + i);         // n1[x]
+                const int2 up = *reinterpret_cast<const int2*>(sn1 + iup);       // n1[x + e0]
+                // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+                const int d0 = (up.x - me.x) - (h.y - h.x), d1 = (up.y - me.y) - (hr - h.y);
+                dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+                cs.w0 += h.x + h.y;
+                cs.w1 += me.x + me.y;
+            }
+            cs.dn2 = dn2;
+            cs = block_reduce_chain(cs, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_VOBS_COUNT;
+                o[SVB_VOBS_ACTION] = (kappa / 2) * cs.action;
+                o[SVB_VOBS_SUM_DN2] = (double)cs.dn2;
+                o[SVB_VOBS_WRAP0] = (double)cs.w0;
+                o[SVB_VOBS_WRAP1] = (double)cs.w1;
+                o[SVB_VOBS_ACCEPTED] = (double)cs.accepted;
+                o[SVB_VOBS_ACCEPTANCE] = cs.sumA;
+            }
+        }
+
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(reinterpret_cast<double*>(a.phi) + chain * V, sphi, bytes_phi);
+            bulk_s2g(a.n + chain * 2 * V, sn0, bytes_n);
+            bulk_commit();
+            if (STAGES == 1) {
+                bulk_wait_read0();
+                if (next < a.chains) issue_load(next, 0);
+            }
+        }
+        if (STAGES == 1) __syncthreads();
+    }
+    if (tid == 0) bulk_wait0();
+}
+
+// ------------------------------------------------------------------------------------------
 // GLOBAL path: one launch per colour pass, straight out of HBM / L2 (any N).
 // ------------------------------------------------------------------------------------------
 template <typename real, bool INJECTED, bool STRICT>
@@ -932,16 +1179,49 @@ static int launch_villain_pipelined(const VillainArgs& a, cudaStream_t stream, c
     return 0;
 }
 
+template <bool STRICT, int NT, int TT, int MINB, int STAGES>
+static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    auto kern = villain_smem_resid_kernel<STRICT, NT, TT, MINB, STAGES>;
+    const size_t V = (size_t)NT * NT;
+    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(double) + 64 * sizeof(double) + 6 * 32 * sizeof(double) + 16;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TT, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "resident-residual villain kernel does not fit an SM at N=%d", NT);
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > a.chains) grid = a.chains;
+    kern<<<(unsigned)grid, TT, smem, stream>>>(a);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+#ifndef SVB_RESID_STAGES
+#define SVB_RESID_STAGES 1
+#endif
+#ifndef SVB_RESID_T32
+#define SVB_RESID_T32 128
+#endif
+
 template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
     if (!INJECTED && aligned && sizeof(real) == 8) {
+#ifndef SVB_NO_RESID
+        switch (a.N) {
+            case 16: return launch_villain_resid<STRICT, 16, 32, 16, 2>(a, stream, info);
+            case 32: return launch_villain_resid<STRICT, 32, SVB_RESID_T32, SVB_MINB32 * 128 / SVB_RESID_T32, SVB_RESID_STAGES>(a, stream, info);
+            case 64: return launch_villain_resid<STRICT, 64, 256, 1, 1>(a, stream, info);
+            default: break;
+        }
+#else
         switch (a.N) {
             case 16: return launch_villain_pipelined<real, STRICT, 16, 32, 16>(a, stream, info);
             case 32: return launch_villain_pipelined<real, STRICT, 32, 128, SVB_MINB32>(a, stream, info);
             case 64: return launch_villain_pipelined<real, STRICT, 64, 256, 1>(a, stream, info);
             default: break;
         }
+#endif
     }
     return launch_villain_smem_inst<real, INJECTED, STRICT, 0, 0, 1>(a, stream, info);
 }
