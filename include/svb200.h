@@ -158,6 +158,20 @@ int svb_worldline_sweep(int32_t* m, int32_t* v,
                         double* obs, uint8_t* accept_mask, double* dS_out,
                         void* stream);
 
+/*
+ * WrappingUpdate.step (worldline/wrapping.py:43-90): one proposal per torus cycle (2N per chain), IN PLACE on m.
+ *  interval       proposals are drawn from [-interval, interval] \ {0}
+ *  sweep          Philox counter of this step (stream 3, counter word 0 = mu * N + k)
+ *  injected       inj_u (chains, 2, N) f64 and inj_c (chains, 2, N) i32: [mu, k] is the mu-direction cycle at
+ *                 perpendicular coordinate k (the reference's draw order: choices mu=0, mu=1, uniforms mu=0, mu=1)
+ *  counters       optional (chains, 2) f64: accepted, sum of min(1, e^-dS);  dS_out optional (chains, 2, N)
+ */
+int svb_worldline_wrapping(int32_t* m, const int32_t* v, int64_t chains, int N,
+                           double kappa, const double* kappa_chain, int W, int interval,
+                           uint64_t seed, uint64_t sweep, uint64_t chain0, int rng_mode,
+                           const double* inj_u, const int32_t* inj_c,
+                           double* counters, double* dS_out, void* stream);
+
 /* Worldline.__call__ ingredients and observables (action/worldline.py:72-94): obs (chains, SVB_WOBS_COUNT) */
 int svb_worldline_observables(const int32_t* m, const int32_t* v,
                               int64_t chains, int N, int W,

@@ -266,3 +266,66 @@ def hot_start(rng, N, chains=None):
     m = lat.delta2(t)
     v = rng.integers(-2, 3, lead + (1, N, N))
     return m, v
+
+
+def wrapping_step(m, v, kappa, W, rng, interval_w=1, stats=None):
+    """WrappingUpdate.step (supervillain/generator/worldline/wrapping.py:43-90): one proposal per torus cycle.
+
+    A mu-direction cycle changes m_mu by the same amount on all N links along direction mu at fixed
+    perpendicular coordinate; dS of a cycle is the sum of the link changes along it (:71).
+    """
+    N = m.shape[-1]
+    ws = _choices(interval_w)
+    change = np.zeros((2, N, N), dtype=np.int64)
+    change[0] = rng.choice(ws, N).reshape(1, N)                          # :59-60, mu = 0: one value per x1
+    change[1] = rng.choice(ws, N).reshape(N, 1)                          #          mu = 1: one value per x0
+    dS_link = 0.5 / kappa * change * (2 * (m - lat.delta2(v) / W) + change)    # :64
+    accepted, acceptance = 0, 0.0
+    for mu in range(2):
+        dS = dS_link[mu].sum(axis=mu)                                    # :71
+        A = np.clip(np.exp(-dS), 0, 1)
+        u = rng.uniform(0, 1, A.shape)                                   # :74
+        acc = u < A
+        change[mu] *= np.expand_dims(acc, axis=mu)                       # :77
+        acceptance += float(A.sum()); accepted += int(acc.sum())
+    if stats is not None:
+        stats['accepted'] = accepted; stats['acceptance'] = acceptance
+    return m + change, v.copy()
+
+
+def draw_wrapping(rng, N, interval_w=1):
+    """The reference's RNG call order for one WrappingUpdate step: choices for mu=0, mu=1, then uniforms for mu=0, mu=1."""
+    ws = _choices(interval_w)
+    cm = np.stack([rng.choice(ws, N), rng.choice(ws, N)])
+    u = np.stack([rng.uniform(0, 1, N), rng.uniform(0, 1, N)])
+    return {'cm': cm, 'u': u}
+
+
+def wrapping_step_dense(m, v, kappa, W, draws, stats=None, dS_out=None):
+    """The same step cycle by cycle with dense draws cm, u of shape (2, N): index [mu, k] is the mu-direction cycle
+    at perpendicular coordinate k.  Terms are accumulated sequentially along the cycle."""
+    N = m.shape[-1]
+    m = m.copy()
+    f = m - lat.delta2(v) / W
+    hk = 0.5 / kappa
+    accepted, acceptance = 0, 0.0
+    for mu in range(2):
+        for k in range(N):
+            c = int(draws['cm'][mu, k])
+            dS = 0.0
+            for j in range(N):
+                fl = f[0, j, k] if mu == 0 else f[1, k, j]
+                dS = dS + (hk * c) * (2 * fl + c)
+            A = min(max(float(np.exp(-dS)), 0.0), 1.0)
+            acceptance += A
+            if dS_out is not None:
+                dS_out[mu, k] = dS
+            if draws['u'][mu, k] < A:
+                accepted += 1
+                if mu == 0:
+                    m[0, :, k] += c
+                else:
+                    m[1, k, :] += c
+    if stats is not None:
+        stats['accepted'] = accepted; stats['acceptance'] = acceptance
+    return m, v.copy()

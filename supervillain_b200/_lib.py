@@ -33,6 +33,7 @@ SIGNATURES = {
     'svb_worldline_sweep': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _i, _i, _u64, _u64, _u64, _i, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'svb_worldline_observables': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    'svb_worldline_wrapping': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp, _vp]),
     'svb_form_op': (_i, [_i, _i, _i, _vp, _vp, _i64, _i, _vp]),
     'svb_villain_spin_spin': (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     'svb_correlation': (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp]),

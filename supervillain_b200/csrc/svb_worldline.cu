@@ -777,6 +777,127 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// WrappingUpdate (supervillain/generator/worldline/wrapping.py:43-90): one proposal per torus cycle.
+// The mu-direction cycle at perpendicular coordinate k changes m_mu by c on its N links;
+//   dS = sum_j ((0.5/kappa) c) ((2 f_j) + c),  f = m - delta v / W  (:64, :71)
+// All 2N cycles of a chain read the initial fields and touch disjoint links, so they are decided
+// concurrently: one thread per cycle out of shared memory.  2N proposals per chain against N^2 per
+// plaquette sweep -- this kernel is never the bottleneck.
+// ------------------------------------------------------------------------------------------
+namespace svb {
+
+struct WrappingArgs {
+    int32_t* m;
+    const int32_t* v;
+    long long chains;
+    int N;
+    double kappa;
+    const double* kappa_chain;
+    int W;
+    int interval;
+    unsigned long long seed, sweep, chain0;
+    const double* inj_u;       // (chains, 2, N)
+    const int32_t* inj_c;      // (chains, 2, N)
+    double* counters;          // (chains, 2): accepted, sum of min(1, e^-dS)
+    double* dS_out;            // (chains, 2, N) optional
+};
+
+template <bool INJECTED>
+__global__ void __launch_bounds__(128) worldline_wrapping_kernel(WrappingArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.N, V = N * N;
+    int32_t* sm = reinterpret_cast<int32_t*>(smem_raw);       // m: 2V
+    int32_t* sv = sm + 2 * V;                                  // v: V
+    __shared__ double red[2 * 4];
+    const double Wd = (double)a.W;
+    for (long long chain = blockIdx.x; chain < a.chains; chain += gridDim.x) {
+        int32_t* gm = a.m + chain * 2 * V;
+        const int32_t* gv = a.v + chain * V;
+        for (int i = threadIdx.x; i < 2 * V; i += blockDim.x) sm[i] = gm[i];
+        for (int i = threadIdx.x; i < V; i += blockDim.x) sv[i] = gv[i];
+        __syncthreads();
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double hk = __ddiv_rn(0.5, kappa);
+        double n_acc = 0.0, sum_A = 0.0;
+        for (int cyc = threadIdx.x; cyc < 2 * N; cyc += blockDim.x) {
+            const int mu = cyc / N, k = cyc - mu * N;
+            double u;
+            int c;
+            if (INJECTED) {
+                u = a.inj_u[chain * 2 * N + cyc];
+                c = a.inj_c[chain * 2 * N + cyc];
+            } else {
+                const Philox4 p = philox_site(a.seed, a.chain0 + (unsigned long long)chain, a.sweep, (uint32_t)cyc, STREAM_WORLDLINE_WRAPPING);
+                const uint64_t ku = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
+                u = ((double)(long long)ku + 0.5) * 5.6843418860808015e-14;
+                const int idx = (int)(((uint64_t)p.w * (uint64_t)(2 * a.interval)) >> 32);
+                c = (idx < a.interval) ? idx - a.interval : idx - a.interval + 1;
+            }
+            const double cd = (double)c;
+            const double hc = __dmul_rn(hk, cd);
+            double dS = 0.0;
+            for (int j = 0; j < N; ++j) {
+                // link (mu, x): mu = 0 -> x = (j, k);  mu = 1 -> x = (k, j)
+                const int x0 = (mu == 0) ? j : k, x1 = (mu == 0) ? k : j;
+                const int i = x0 * N + x1;
+                const int dv = (mu == 0) ? (sv[i] - sv[x0 * N + (x1 == 0 ? N - 1 : x1 - 1)])
+                                         : (sv[(x0 == 0 ? N - 1 : x0 - 1) * N + x1] - sv[i]);
+                const double f = __dsub_rn((double)sm[mu * V + i], __ddiv_rn((double)dv, Wd));
+                dS = __dadd_rn(dS, __dmul_rn(hc, __dadd_rn(__dmul_rn(2.0, f), cd)));
+            }
+            const double A = exp_clipped(-dS);
+            const bool ok = u < A;
+            sum_A += A;
+            if (a.dS_out) a.dS_out[chain * 2 * N + cyc] = dS;
+            if (ok) {
+                n_acc += 1.0;
+                for (int j = 0; j < N; ++j) {
+                    const int i = (mu == 0) ? (j * N + k) : (k * N + j);
+                    gm[mu * V + i] = sm[mu * V + i] + c;       // cycles touch disjoint links: write straight to HBM
+                }
+            }
+        }
+        if (a.counters) {
+            double s[2] = {n_acc, sum_A};
+            block_sum<2>(s, red);
+            if (threadIdx.x == 0) {
+                a.counters[chain * 2] = s[0];
+                a.counters[chain * 2 + 1] = s[1];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace svb
+
+extern "C" int svb_worldline_wrapping(int32_t* m, const int32_t* v, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                      int W, int interval, uint64_t seed, uint64_t sweep, uint64_t chain0, int rng_mode,
+                                      const double* inj_u, const int32_t* inj_c, double* counters, double* dS_out, void* stream) {
+    if (!m || !v) return fail(SVB_E_NULL, "svb_worldline_wrapping: m and v are required");
+    if (chains < 0 || N < 3 || N > 181) return fail(SVB_E_SHAPE, "svb_worldline_wrapping: chains=%lld N=%d (needs the lattice in shared memory)", (long long)chains, N);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_wrapping: kappa must be positive");
+    if (W < 1 || interval < 1 || interval > 1024) return fail(SVB_E_PARAM, "svb_worldline_wrapping: W / interval");
+    if (rng_mode == SVB_RNG_INJECTED && (!inj_u || !inj_c)) return fail(SVB_E_NULL, "svb_worldline_wrapping: injected mode needs inj_u and inj_c");
+    if (chains == 0) return SVB_OK;
+    WrappingArgs a;
+    a.m = m; a.v = v; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W; a.interval = interval;
+    a.seed = seed; a.sweep = sweep; a.chain0 = chain0; a.inj_u = inj_u; a.inj_c = inj_c; a.counters = counters; a.dS_out = dS_out;
+    const size_t smem = (size_t)3 * N * N * sizeof(int32_t);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long grid = chains < 148LL * 8 ? chains : 148LL * 8;
+    if (rng_mode == SVB_RNG_INJECTED) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(worldline_wrapping_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        worldline_wrapping_kernel<true><<<(unsigned)grid, 128, smem, st>>>(a);
+    } else {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(worldline_wrapping_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        worldline_wrapping_kernel<false><<<(unsigned)grid, 128, smem, st>>>(a);
+    }
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
 extern "C" int svb_worldline_observables(const int32_t* m, const int32_t* v, int64_t chains, int N, int W, double* obs,
                                          void* stream) {
     if (!m || !v || !obs) return fail(SVB_E_NULL, "svb_worldline_observables: m, v, obs are required");

@@ -192,11 +192,10 @@ class BatchedEnsemble:
         kappa = self.Action.kappa if kappa_chain is None else kappa_chain.cpu().numpy()[:, None]
         values = villain_inline_values if self.kind == 'Villain' else worldline_inline_values
         self.observables = values(self.record, N, kappa)
-        sites = N * N
-        generator.sweeps += steps * sweeps_per_step * self.chains
-        generator.proposed += sites * steps * sweeps_per_step * self.chains
-        generator.accepted += int(round(float(self.record[..., 4].sum())))
-        generator.acceptance += float(self.record[..., 5].sum()) / (1 if str(generator) == 'PlaquetteUpdate' else sites)
+        account = getattr(generator, '_count', None)       # single GPU generators keep the reference's counters
+        if account is not None:
+            flat = self.record.reshape(-1, self.record.shape[-1])
+            account(flat, self.chains, steps * sweeps_per_step)
         return self
 
     def __getattr__(self, name):

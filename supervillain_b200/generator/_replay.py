@@ -46,3 +46,12 @@ def worldline_checkerboard(rng, lattice, mode, interval=1):
         else:
             a[color] = rng.choice(_nonzero_choices(interval), count)
     return u, a, b
+
+
+def worldline_wrapping(rng, lattice, interval=1):
+    """One WrappingUpdate step's draws (wrapping.py:59-60, :74): choices for mu = 0, 1, then uniforms for mu = 0, 1."""
+    N = lattice.N
+    ws = _nonzero_choices(interval)
+    c = np.stack([rng.choice(ws, N), rng.choice(ws, N)]).astype(np.int32)
+    u = np.stack([rng.uniform(0, 1, N), rng.uniform(0, 1, N)])
+    return u, c

@@ -25,6 +25,15 @@ class Sequentially(Generator):
             combined |= g.inline_observables(steps)
         return combined
 
+    def sweep_device(self, a, b, n_sweeps=1, *, obs=None, chain0=0, kappa_chain=None):
+        """Device-resident counterpart of `step` for GPU generators (used by `BatchedEnsemble`): `n_sweeps` rounds of
+        every generator in order, in place; the observable record is written by the last generator of the last round."""
+        gens = list(self.generators)
+        for s in range(n_sweeps):
+            for k, g in enumerate(gens):
+                final = (s == n_sweeps - 1) and (k == len(gens) - 1)
+                g.sweep_device(a, b, 1, obs=obs if final else None, chain0=chain0, kappa_chain=kappa_chain)
+
     def report(self):
         return '\n\n'.join(g.report() for g in self.generators)
 

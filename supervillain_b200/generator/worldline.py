@@ -194,3 +194,78 @@ class CoexactUpdate(_CheckerboardWorldline):
 
     def __str__(self):
         return 'CoexactUpdate'
+
+
+class WrappingUpdate(Generator):
+    """Torus-cycle updates of m (supervillain/generator/worldline/wrapping.py:9-99); `WrappingUpdate(action, interval_w=1)`.
+
+    Needed next to `PlaquetteUpdate` for ergodicity: plaquette moves cannot change the wrapping sector
+    (plaquette.py:16-19; test/end-to-end.py:48-50 always pairs them).
+    """
+
+    def __init__(self, action, interval_w=1, *, seed=None):
+        if not _is_worldline(action):
+            raise ValueError('The WrappingUpdate requires the Worldline action.')
+        if not (action.W < float('inf')):
+            raise NotImplementedError('the GPU worldline generators implement finite W (integer v) only')
+        self.Action = action
+        self.Lattice = action.Lattice
+        self.kappa = action.kappa
+        self.interval_w = interval_w
+        self.w = _replay._nonzero_choices(interval_w)
+        self.rng = None
+        self.seed = fresh_seed() if seed is None else int(seed)
+        self.counter = 0
+        self.accepted = 0
+        self.proposed = 0
+        self.sweeps = 0
+        self.acceptance = 0.
+
+    def __str__(self):
+        return 'WrappingUpdate'
+
+    def sweep_device(self, m, v, n_sweeps=1, *, obs=None, chain0=0, kappa_chain=None, injected=None, counters=None,
+                     dS_out=None):
+        """`n_sweeps` wrapping steps in place on m (chains,2,N,N) int32; `obs`, if given, is refreshed from the final
+        state with svb_worldline_observables (a wrapping move changes every link observable)."""
+        for s in range(n_sweeps):
+            ops.worldline_wrapping(m, v, self.kappa, W=self.Action.W, interval=self.interval_w, seed=self.seed,
+                                   sweep=self.counter + s, chain0=chain0, injected=injected, kappa_chain=kappa_chain,
+                                   counters=counters, dS_out=dS_out)
+        if injected is None:
+            self.counter += n_sweeps
+        if obs is not None:
+            ops.worldline_observables(m, v, W=self.Action.W, obs=obs)
+
+    def step(self, cfg):
+        N = self.Lattice.N
+        m, single = to_device(cfg['m'], torch.int32, 2, N)
+        v, _ = to_device(cfg['v'], torch.int32, 1, N)
+        if isinstance(cfg['m'], torch.Tensor):
+            m = m.clone()
+        chains = m.shape[0]
+        injected = None
+        if self.rng is not None:
+            u = np.empty((chains, 2, N)); c = np.empty((chains, 2, N), dtype=np.int32)
+            for k in range(chains):
+                u[k], c[k] = _replay.worldline_wrapping(self.rng, self.Lattice, self.interval_w)
+            injected = {'u': torch.from_numpy(u).cuda(), 'c': torch.from_numpy(c).cuda()}
+        counters = torch.zeros((chains, 2), dtype=torch.float64, device=m.device)
+        self.sweep_device(m, v, 1, injected=injected, counters=counters)
+        rec = counters.cpu().numpy()
+        n_cycles = 2 * N
+        self.proposed += n_cycles * chains
+        self.accepted += int(round(float(rec[:, 0].sum())))
+        self.acceptance += float(rec[:, 1].sum()) / n_cycles
+        self.sweeps += chains
+        out_m = m.cpu().numpy().astype(np.int64)
+        return cfg | {'m': Form(out_m[0], degree=1, lattice=self.Lattice) if single else out_m}
+
+    def report(self):
+        return (
+            f'There were {self.accepted} single-wrapping proposals accepted of {self.proposed} proposed updates.'
+            + '\n' +
+            f'    {self.accepted / self.proposed:.6f} acceptance rate'
+            + '\n' +
+            f'    {self.acceptance / self.sweeps:.6f} average Metropolis acceptance probability.'
+        )

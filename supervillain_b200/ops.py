@@ -133,6 +133,29 @@ def worldline_sweep(m, v, kappa, *, W=1, mode='joint', interval=1, n_sweeps=1, s
     _lib.check(code)
 
 
+def worldline_wrapping(m, v, kappa, *, W=1, interval=1, seed=0, sweep=0, chain0=0, injected=None, kappa_chain=None,
+                       counters=None, dS_out=None):
+    """One WrappingUpdate step (2N torus-cycle proposals per chain), in place on m (svb_worldline_wrapping).
+
+    `injected`: dict of u (chains,2,N) f64 and c (chains,2,N) int32.  counters (chains,2): accepted, sum of acceptance.
+    """
+    lib = _lib.load()
+    chains, N = _fields_shape(m, 'm', 2)
+    p_m = _dev(m, 'm', (torch.int32,))
+    p_v = _dev(v, 'v', (torch.int32,), (chains, 1, N, N))
+    if injected is None:
+        rng_mode, pu, pc = RNG_PHILOX, None, None
+    else:
+        rng_mode = RNG_INJECTED
+        pu = _dev(injected['u'], 'injected[u]', (torch.float64,), (chains, 2, N))
+        pc = _dev(injected['c'], 'injected[c]', (torch.int32,), (chains, 2, N))
+    _lib.check(lib.svb_worldline_wrapping(
+        p_m, p_v, chains, N, float(kappa), _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(W), int(interval),
+        int(seed) & (2**64 - 1), int(sweep), int(chain0), rng_mode, pu, pc,
+        _opt(counters, 'counters', (torch.float64,), (chains, 2)), _opt(dS_out, 'dS_out', (torch.float64,), (chains, 2, N)),
+        _stream()))
+
+
 def worldline_observables(m, v, *, W=1, obs=None):
     lib = _lib.load()
     chains, N = _fields_shape(m, 'm', 2)

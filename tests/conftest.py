@@ -60,3 +60,8 @@ def golden_worldline_plaquette():
 @pytest.fixture(scope='session')
 def golden_worldline_observables():
     return load_golden('worldline_observables')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_worldline_wrapping():
+    return load_golden('worldline_wrapping')[0]

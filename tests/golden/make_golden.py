@@ -239,8 +239,31 @@ def worldline_observables():
     _pack(cases, 'worldline_observables')
 
 
+def worldline_wrapping():
+    """WrappingUpdate.step chains (worldline/wrapping.py:43-90) with rng = default_rng(99)."""
+    cases = []
+    for (N, W, kappa, interval) in [(4, 1, 0.5, 1), (5, 2, 0.4, 1), (8, 1, 0.3, 2), (8, 3, 0.6, 1), (16, 1, 0.25, 1)]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Worldline(L, kappa, W=W)
+        G = sv.generator.worldline.WrappingUpdate(S, interval)
+        G.rng = np.random.default_rng(99)
+        replay = np.random.default_rng(99)
+        m0, v0 = worldline_np.hot_start(np.random.default_rng(N + W), N)
+        cfg = {'m': Form(m0, degree=1, lattice=L), 'v': Form(v0, degree=2, lattice=L)}
+        us, cs, ms, acc = [], [], [], []
+        for s in range(6):
+            d = worldline_np.draw_wrapping(replay, N, interval)
+            before = G.accepted
+            cfg = G.step(cfg)
+            assert S.valid(cfg)
+            us.append(d['u']); cs.append(d['cm']); ms.append(np.asarray(cfg['m']).copy()); acc.append(int(G.accepted - before))
+        cases.append(dict(N=N, W=W, kappa=kappa, interval=interval, sweeps=6, m0=m0, v0=v0, u=np.array(us), cm=np.array(cs),
+                          m=np.array(ms), accepted=np.array(acc)))
+    _pack(cases, 'worldline_wrapping')
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
-                             'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables']
+                             'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping']
     for name in which:
         globals()[name]()

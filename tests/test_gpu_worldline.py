@@ -148,3 +148,62 @@ def test_full_size_config3_shard_bit_exact_against_c_oracle(mode):
     assert (rec[:, WOBS_ACCEPTED] == acc).all()
     np.testing.assert_allclose(rec[:, WOBS_ACCEPTANCE], accp, rtol=1e-12)
     assert (ops.worldline_observables(m, v, W=W)[:, WOBS_DELTA_M_ABS] == 0).all().item()
+
+
+def test_wrapping_update_reproduces_reference_chain(golden_worldline_wrapping):
+    """WrappingUpdate with rng=default_rng(99): identical m and accept counts to the reference (wrapping.py:43-90)."""
+    from supervillain_b200.generator.worldline import WrappingUpdate
+    for c in golden_worldline_wrapping:
+        N, W, kappa, I = int(c['N']), int(c['W']), float(c['kappa']), int(c['interval'])
+        S = svb.Worldline(svb.Lattice2D(N), kappa, W=W)
+        G = WrappingUpdate(S, I)
+        G.rng = np.random.default_rng(99)
+        cfg = {'m': c['m0'], 'v': c['v0']}
+        for s in range(int(c['sweeps'])):
+            before = G.accepted
+            cfg = G.step(cfg)
+            assert (np.asarray(cfg['m']) == c['m'][s]).all(), (N, W, s)
+            assert G.accepted - before == int(c['accepted'][s])
+            assert S.valid(cfg)
+    assert 'single-wrapping proposals accepted' in G.report()
+
+
+def test_wrapping_philox_matches_dense_oracle_and_changes_the_sector():
+    N, chains, kappa = 8, 64, 0.3
+    m0, v0 = WL.hot_start(np.random.default_rng(5), N, chains)
+    m, v = dev(m0, torch.int32), dev(v0, torch.int32)
+    dS = torch.zeros((chains, 2, N), dtype=torch.float64, device='cuda')
+    cnt = torch.zeros((chains, 2), dtype=torch.float64, device='cuda')
+    ops.worldline_wrapping(m, v, kappa, seed=3, sweep=1, chain0=10, counters=cnt, dS_out=dS)
+    got = m.cpu().numpy()
+    changed = 0
+    for c in range(chains):
+        # rebuild the kernel's draws: stream 3, counter word 0 = mu * N + k
+        x, y, z, w = P.philox_site(3, 10 + c, 1, np.arange(2 * N, dtype=np.uint64), 3)
+        ku = (x << np.uint64(12)) | (y >> np.uint64(20))
+        u = ((ku.astype(np.float64) + 0.5) * 2.0 ** -44).reshape(2, N)
+        idx = ((w * np.uint64(2)) >> np.uint64(32)).astype(np.int64)
+        cm = np.where(idx < 1, idx - 1, idx).reshape(2, N)
+        st = {}; dS_ref = np.zeros((2, N))
+        m_ref, _ = WL.wrapping_step_dense(m0[c], v0[c], kappa, 1, {'u': u, 'cm': cm}, stats=st, dS_out=dS_ref)
+        assert (got[c] == m_ref).all()
+        np.testing.assert_allclose(dS[c].cpu().numpy(), dS_ref, rtol=1e-13, atol=1e-13)
+        assert cnt[c, 0].item() == st['accepted']
+        assert WL.valid(m_ref)
+        changed += int((WL.torus_wrapping(m_ref) != WL.torus_wrapping(m0[c])).any())
+    assert changed > 0
+
+
+def test_sequentially_plaquette_and_wrapping_in_a_batched_ensemble():
+    """The ergodic pairing of test/end-to-end.py:48-50, device resident, many chains."""
+    from supervillain_b200.generator.combining import Sequentially
+    from supervillain_b200.generator.worldline import WrappingUpdate
+    S = svb.Worldline(svb.Lattice2D(8), 0.5)
+    G = Sequentially((PlaquetteUpdate(S, seed=1), WrappingUpdate(S, seed=2)))
+    E = svb.BatchedEnsemble(S, 128).generate(50, G, 'cold', sweeps_per_step=4)
+    m, v = E.fields
+    assert (ops.worldline_observables(m, v)[:, WOBS_DELTA_M_ABS] == 0).all().item()
+    assert E.ActionDensity.shape == (128, 50) and np.isfinite(E.ActionDensity).all()
+    assert (E.TorusWrapping != 0).any()                      # wrapping sectors are visited
+    ref = WL.action_density(m.cpu().numpy().astype(np.int64), v.cpu().numpy().astype(np.int64), 0.5, 1)
+    np.testing.assert_allclose(E.ActionDensity[:, -1], ref, rtol=1e-12, atol=1e-12)

@@ -105,3 +105,17 @@ def test_delta_S_equals_action_difference_and_constraint_kept(mode):
     # a full accepted sweep keeps the constraint
     m3, v3 = WL.checkerboard_step_dense(m, v, kappa, W, draws | {'u': np.zeros((N, N))}, mode)
     assert WL.valid(m3)
+
+
+def test_wrapping_oracle_reproduces_reference(golden_worldline_wrapping):
+    for c in golden_worldline_wrapping:
+        N, W, kappa, I = int(c['N']), int(c['W']), float(c['kappa']), int(c['interval'])
+        rng = np.random.default_rng(99)
+        m, v = c['m0'], c['v0']
+        md = c['m0']
+        for s in range(int(c['sweeps'])):
+            st = {}
+            m, v = WL.wrapping_step(m, v, kappa, W, rng, I, stats=st)
+            md, _ = WL.wrapping_step_dense(md, c['v0'], kappa, W, {'u': c['u'][s], 'cm': c['cm'][s]})
+            assert (m == c['m'][s]).all() and (md == c['m'][s]).all() and WL.valid(m)
+            assert st['accepted'] == int(c['accepted'][s])
