@@ -130,6 +130,19 @@ int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n,
                       void* stream);
 
 /*
+ * The same sweep with HOST buffers: the reference's `step(cfg)` contract (host arrays in, host arrays out,
+ * neighborhood.py:59-137) for a whole batch.  phi_host / n_host / obs_host are pinned HOST buffers updated in place;
+ * phi_dev / n_dev / obs_dev are caller-owned DEVICE staging buffers of the same shapes.  The chains are processed in
+ * `n_chunks` chunks round-robin over the `n_streams` streams (cudaStream_t[]), each chunk H2D -> sweep -> D2H, so copies
+ * in both directions overlap the kernels.  Philox mode only.  Asynchronous: the caller synchronises the streams.
+ */
+int svb_villain_sweep_host(void* phi_host, int phi_dtype, int32_t* n_host, double* obs_host,
+                           void* phi_dev, int32_t* n_dev, double* obs_dev,
+                           int64_t chains, int N, double kappa, int W, double interval_phi, int interval_n,
+                           int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode,
+                           int n_chunks, void* const* streams, int n_streams);
+
+/*
  * Villain.__call__ (action/villain.py:51-66) and the scalar observables of
  * observable/{action,energy,winding,wrapping}.py for every chain: fills obs[:, ACTION..WRAP1]
  * and zeroes the two counters.

@@ -1357,3 +1357,46 @@ extern "C" int svb_villain_draws(int64_t chains, int N, int W, double interval_p
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }
+
+
+// Host-buffer form of svb_villain_sweep: the reference's `step(cfg)` contract (host arrays in, host arrays out) at
+// batch scale.  The chains are cut into `n_chunks` chunks; chunk i is copied host->device, swept and copied back on
+// stream i % n_streams, so the H2D copy of one chunk, the sweep of another and the D2H copy of a third overlap
+// (PCIe is full duplex).  Host buffers must be pinned for the copies to be asynchronous.  Nothing is synchronised
+// here: the caller synchronises the streams it passed.
+extern "C" int svb_villain_sweep_host(void* phi_host, int phi_dtype, int32_t* n_host, double* obs_host,
+                                      void* phi_dev, int32_t* n_dev, double* obs_dev,
+                                      int64_t chains, int N, double kappa, int W, double interval_phi, int interval_n,
+                                      int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode,
+                                      int n_chunks, void* const* streams, int n_streams) {
+    if (!phi_host || !n_host || !phi_dev || !n_dev) return fail(SVB_E_NULL, "svb_villain_sweep_host: field buffers are required");
+    if (!streams || n_streams < 1 || n_chunks < 1) return fail(SVB_E_PARAM, "svb_villain_sweep_host: streams / chunks");
+    if ((obs_host == nullptr) != (obs_dev == nullptr)) return fail(SVB_E_NULL, "svb_villain_sweep_host: obs_host and obs_dev go together");
+    if (phi_dtype != SVB_F64 && phi_dtype != SVB_F32) return fail(SVB_E_DTYPE, "svb_villain_sweep_host: phi dtype %d", phi_dtype);
+    if (chains <= 0) return SVB_OK;
+    if (n_chunks > chains) n_chunks = (int)chains;
+    const size_t V = (size_t)N * N;
+    const size_t esz = (phi_dtype == SVB_F64) ? 8 : 4;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int64_t lo = chains * i / n_chunks, hi = chains * (i + 1) / n_chunks;
+        if (hi <= lo) continue;
+        const int64_t cnt = hi - lo;
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(streams[i % n_streams]);
+        char* ph = reinterpret_cast<char*>(phi_host) + lo * V * esz;
+        char* pd = reinterpret_cast<char*>(phi_dev) + lo * V * esz;
+        int32_t* nh = n_host + lo * 2 * V;
+        int32_t* nd = n_dev + lo * 2 * V;
+        SVB_CUDA_TRY(cudaMemcpyAsync(pd, ph, cnt * V * esz, cudaMemcpyHostToDevice, st));
+        SVB_CUDA_TRY(cudaMemcpyAsync(nd, nh, cnt * 2 * V * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        int rc = svb_villain_sweep(pd, phi_dtype, nd, cnt, N, kappa, nullptr, W, interval_phi, interval_n, n_sweeps, seed, sweep0,
+                                   chain0 + (uint64_t)lo, SVB_RNG_PHILOX, arith_mode, SVB_PATH_AUTO, nullptr, nullptr, nullptr,
+                                   nullptr, obs_dev ? obs_dev + lo * SVB_VOBS_COUNT : nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+        SVB_CUDA_TRY(cudaMemcpyAsync(ph, pd, cnt * V * esz, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA_TRY(cudaMemcpyAsync(nh, nd, cnt * 2 * V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (obs_dev)
+            SVB_CUDA_TRY(cudaMemcpyAsync(obs_host + lo * SVB_VOBS_COUNT, obs_dev + lo * SVB_VOBS_COUNT,
+                                         cnt * SVB_VOBS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    return SVB_OK;
+}

@@ -7,13 +7,16 @@ exactly that on pinned host buffers, split into chunks of chains pipelined over 
 H2D copy of chunk i+1, the sweep of chunk i and the D2H copy of chunk i-1 overlap (PCIe is
 full-duplex).  The kernels are the same ones the resident path uses.
 """
+import ctypes
+
 import torch
 
+from . import _lib
 from ._lib import VOBS_COUNT, WOBS_COUNT
 
 
 class HostStepper:
-    def __init__(self, generator, chains, *, chain0=0, chunks=8, streams=3, device=None):
+    def __init__(self, generator, chains, *, chain0=0, chunks=16, streams=4, device=None):
         self.generator = generator
         self.chains = int(chains)
         self.chain0 = int(chain0)
@@ -61,6 +64,21 @@ class HostStepper:
         current = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(current)
+        if self.kind == 'Villain' and getattr(G, 'rng', None) is None and getattr(G, 'path', 'auto') == 'auto':
+            # the whole chunked H2D -> sweep -> D2H pipeline is issued by one C call (svb_villain_sweep_host)
+            lib = _lib.load()
+            handles = (ctypes.c_void_p * len(self.streams))(*[s.cuda_stream for s in self.streams])
+            _lib.check(lib.svb_villain_sweep_host(
+                host_a.data_ptr(), _lib.F64 if self.dtypes[0] == torch.float64 else _lib.F32, host_b.data_ptr(),
+                self.host_obs.data_ptr(), self.dev_a.data_ptr(), self.dev_b.data_ptr(), self.dev_obs.data_ptr(),
+                self.chains, self.N, float(G.kappa), int(G.Action.W), float(G.interval_phi), int(G.interval_n),
+                int(n_sweeps), int(G.seed) & (2**64 - 1), int(sweep0), self.chain0,
+                _lib.ARITH_FAST if G.arithmetic == 'fast' else _lib.ARITH_STRICT,
+                len(self.bounds), handles, len(self.streams)))
+            G.counter = sweep0 + n_sweeps
+            for s in self.streams:
+                s.synchronize()
+            return self.host_obs
         for i, (lo, hi) in enumerate(self.bounds):
             st = self.streams[i % len(self.streams)]
             with torch.cuda.stream(st):
