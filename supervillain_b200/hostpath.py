@@ -16,7 +16,7 @@ from ._lib import VOBS_COUNT, WOBS_COUNT
 
 
 class HostStepper:
-    def __init__(self, generator, chains, *, chain0=0, chunks=16, streams=4, device=None):
+    def __init__(self, generator, chains, *, chain0=0, chunks=16, streams=8, device=None):
         self.generator = generator
         self.chains = int(chains)
         self.chain0 = int(chain0)
