@@ -216,16 +216,19 @@ def test_full_size_config2_bit_exact_against_c_oracle():
     assert (rec[:, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()
 
 
-@pytest.mark.parametrize('N,chains', [(16, 512), (64, 128), (128, 8), (48, 16)])
-def test_other_shapes_bit_exact_against_c_oracle(N, chains):
-    """The other compile-time geometries (16, 64), the global path (128) and a generic even size (48)."""
+@pytest.mark.parametrize('arith', ['fast', 'strict'])
+@pytest.mark.parametrize('sweeps', [1, 2])
+@pytest.mark.parametrize('N,chains', [(16, 512), (32, 256), (64, 128), (128, 8), (48, 16)])
+def test_other_shapes_bit_exact_against_c_oracle(N, chains, sweeps, arith):
+    """Every kernel behind SVB_PATH_AUTO: the pipelined recompute kernel (1 sweep, fast) and the resident-residual kernel
+    (fused sweeps, or strict) at the compile-time geometries 16 / 32 / 64, the global path (128), a generic even size (48)."""
     from oracle import c_oracle as C
     kappa, seed = 0.7, 5
     phi0, n0 = V.hot_start(np.random.default_rng(N), N, chains)
     phi, n = dev(phi0), dev(n0, torch.int32)
     obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
-    ops.villain_sweep(phi, n, kappa, n_sweeps=2, seed=seed, obs=obs)
-    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=2, seed=seed)
+    ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps, seed=seed, obs=obs, arithmetic=arith)
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=sweeps, seed=seed)
     assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
     rec = obs.cpu().numpy()
     assert (rec[:, VOBS_ACCEPTED] == acc).all()
