@@ -105,6 +105,31 @@ __device__ __forceinline__ double exp_clipped(double x) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The Metropolis test u < min(1, e^-dS) without evaluating the fp64 exponential for (almost) every proposal.
+// u < e^-dS  <=>  dS < -ln u.  -ln u is formed in fp32 (one MUFU.LG2); whenever dS is farther from it than a guard band
+// that covers every fp32 error in the comparison by a factor > 20, the decision is already certain.  Only inside the band
+// (probability ~1e-6 per proposal) is the exact fp64 test evaluated, so every decision equals the fp64 decision.
+// The acceptance probability itself, wanted only for the generator's report() statistic, comes from MUFU.EX2 in fp32
+// (relative accuracy ~1e-6); STRICT arithmetic keeps the fp64 exponential for both.
+// ------------------------------------------------------------------------------------------
+#ifndef SVB_NO_LOG_FILTER
+__device__ __forceinline__ bool metropolis_filtered(double dS, double u, double& prob) {
+    const float dSf = (float)dS, uf = (float)u;
+    prob = (double)fminf(exp2f(-1.4426950408889634f * dSf), 1.0f);
+    const float L = -0.6931471805599453f * __log2f(uf);
+    const float band = 1e-5f * (1.0f + L + fabsf(dSf));
+    if (dSf > L + band) return false;
+    if (dSf < L - band) return true;
+    return u < exp_clipped(-dS);
+}
+#else
+__device__ __forceinline__ bool metropolis_filtered(double dS, double u, double& prob) {
+    prob = exp_clipped(-dS);
+    return u < prob;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // checkerboard colouring (supervillain/lattice/compact.py:192-239, D = 2)
 // ------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int n_colours(int N) { return (N & 1) ? 4 : 2; }

@@ -86,6 +86,7 @@ struct Arith<double, true> {
         return __dmul_rn(__dmul_rn(hk, dr), __dadd_rn(__dmul_rn(2.0, r), dr));
     }
     static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
+    static __device__ __forceinline__ bool metropolis(double dS, double u, double& prob) { prob = exp_clipped(-dS); return u < prob; }
     static __device__ __forceinline__ double twice_plus(double r, double dr) { return fma(2.0, r, dr); }
     static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
 };
@@ -97,6 +98,7 @@ struct Arith<double, false> {
     static __device__ __forceinline__ double resid(double x, double c, double t) { return fma(-c, t, x); }
     static __device__ __forceinline__ double link(double hk, double dr, double r) { return (hk * dr) * fma(2.0, r, dr); }
     static __device__ __forceinline__ double accept_prob(double dS) { return exp_clipped(-dS); }
+    static __device__ __forceinline__ bool metropolis(double dS, double u, double& prob) { return metropolis_filtered(dS, u, prob); }
     static __device__ __forceinline__ double twice_plus(double r, double dr) { return fma(2.0, r, dr); }
     static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
 };
@@ -110,6 +112,7 @@ struct Arith<float, true> {
         return __fmul_rn(__fmul_rn(hk, dr), __fadd_rn(__fmul_rn(2.0f, r), dr));
     }
     static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
+    static __device__ __forceinline__ bool metropolis(float dS, double u, double& prob) { prob = fmin((double)expf(-dS), 1.0); return u < prob; }
     static __device__ __forceinline__ float twice_plus(float r, float dr) { return fmaf(2.0f, r, dr); }
     static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
 };
@@ -121,6 +124,7 @@ struct Arith<float, false> {
     static __device__ __forceinline__ float resid(float x, float c, float t) { return fmaf(-c, t, x); }
     static __device__ __forceinline__ float link(float hk, float dr, float r) { return (hk * dr) * fmaf(2.0f, r, dr); }
     static __device__ __forceinline__ double accept_prob(float dS) { return fmin((double)expf(-dS), 1.0); }
+    static __device__ __forceinline__ bool metropolis(float dS, double u, double& prob) { prob = fmin((double)expf(-dS), 1.0); return u < prob; }
     static __device__ __forceinline__ float twice_plus(float r, float dr) { return fmaf(2.0f, r, dr); }
     static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
 };
@@ -259,8 +263,8 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
         dS = half_kappa * acc2;
     }
 
-    const double acc = A::accept_prob(dS);                      // clip(exp(-dS), 0, 1)   (:115)
-    const bool ok = d.u < acc;                                  // (:116)
+    double acc;                                                 // clip(exp(-dS), 0, 1)   (:115)
+    const bool ok = A::metropolis(dS, d.u, acc);                // u < acc                (:116)
     if (ok) {                                                   // (:121-128)
         phi[i_c] = A::add(pc, dphi);
         n0[i_c] = nf0 + k.unit * d.dg[0];
@@ -770,8 +774,8 @@ __device__ __forceinline__ SiteOut villain_site_update_resid(double* __restrict_
         acc2 = fma(dr_b1, fma(2.0, r_b1, dr_b1), acc2);
         dS = half_kappa * acc2;
     }
-    const double acc = exp_clipped(-dS);
-    const bool ok = d.u < acc;
+    double acc;
+    const bool ok = A::metropolis(dS, d.u, acc);
     if (ok) {
         phi[i_c] = A::add(phi[i_c], dphi);
         n0[i_c] += W * (d.digit[0] - interval_n);

@@ -392,8 +392,8 @@ __device__ __forceinline__ PlaqOut worldline_plaquette_update_w1(int32_t* __rest
         dS = __dadd_rn(dS, t_0x);
         dS = __dadd_rn(dS, t_0p);
     }
-    const double acc = exp_clipped(-dS);
-    const bool ok = d.u < acc;
+    double acc;                                          // fp32-accurate statistic; the decision is the exact fp64 one
+    const bool ok = metropolis_filtered(dS, d.u, acc);
     if (ok) {
         if (MODE != SVB_WL_VORTEX) {
             m0[i_c] = m_0x + d.a;

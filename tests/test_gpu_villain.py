@@ -102,7 +102,7 @@ def test_philox_mode_matches_oracle_replay(path, arith, N, W, kappa):
         assert (n[c].cpu().numpy() == n_ref).all()
         assert (phi[c].cpu().numpy() == p_ref).all()
         assert rec[c, VOBS_ACCEPTED] == sum(s['accepted'] for s in st)
-        assert rec[c, VOBS_ACCEPTANCE] == pytest.approx(sum(s['acceptance'] for s in st), rel=1e-12)
+        assert rec[c, VOBS_ACCEPTANCE] == pytest.approx(sum(s['acceptance'] for s in st), rel=1e-12 if arith == 'strict' else 1e-5)
         assert rec[c, VOBS_ACTION] == pytest.approx(float(V.action(p_ref, n_ref, kappa)), rel=1e-12)
         assert rec[c, VOBS_SUM_DN2] == float((lat.d1(n_ref) ** 2).sum())
         assert (rec[c, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()
@@ -144,7 +144,7 @@ def test_full_size_config2_smem_equals_global_and_is_sane():
     ops.villain_sweep(b_phi, b_n, kappa, n_sweeps=4, seed=11, path='global', obs=ob)
     assert torch.equal(a_n, b_n) and torch.equal(a_phi, b_phi)
     assert torch.equal(oa[:, VOBS_ACCEPTED], ob[:, VOBS_ACCEPTED])
-    torch.testing.assert_close(oa, ob, rtol=1e-12, atol=1e-9)
+    torch.testing.assert_close(oa, ob, rtol=1e-5, atol=1e-9)
     changed = (a_n != n0).any().item() and (a_phi != phi0).any().item()
     assert changed
     # every changed phi comes from an accepted proposal (a site may be accepted more than once in 4 sweeps)
@@ -210,7 +210,7 @@ def test_full_size_config2_bit_exact_against_c_oracle():
     assert (phi.cpu().numpy() == p_ref).all()
     rec = obs.cpu().numpy()
     assert (rec[:, VOBS_ACCEPTED] == acc).all()
-    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-12)
+    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-5)      # FAST arithmetic: fp32 statistic
     np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, kappa), rtol=1e-12)
     assert (rec[:, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum(axis=(-3, -2, -1))).all()
     assert (rec[:, [VOBS_WRAP0, VOBS_WRAP1]] == V.torus_wrapping(n_ref)).all()

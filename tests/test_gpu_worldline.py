@@ -67,7 +67,7 @@ def test_philox_mode_matches_oracle_replay(mode, path, N, W, kappa):
         assert (dS[c].cpu().numpy() == dS_ref).all()               # strict arithmetic: bitwise
         assert (mask[c].cpu().numpy().astype(bool) == mask_ref).all()
         assert rec[c, WOBS_ACCEPTED] == acc
-        assert rec[c, WOBS_ACCEPTANCE] == pytest.approx(accp, rel=1e-12)
+        assert rec[c, WOBS_ACCEPTANCE] == pytest.approx(accp, rel=1e-5)      # fast W=1 kernel: fp32 statistic
         assert rec[c, WOBS_DELTA_M_ABS] in (0, -1) and WL.valid(mr)
         assert ops.worldline_observables(m, v, W=W)[c, WOBS_DELTA_M_ABS].item() == 0
         f = WL.links(mr, vr, W)
@@ -146,7 +146,7 @@ def test_full_size_config3_shard_bit_exact_against_c_oracle(mode):
     assert (m.cpu().numpy() == m_ref).all() and (v.cpu().numpy() == v_ref).all()
     rec = obs.cpu().numpy()
     assert (rec[:, WOBS_ACCEPTED] == acc).all()
-    np.testing.assert_allclose(rec[:, WOBS_ACCEPTANCE], accp, rtol=1e-12)
+    np.testing.assert_allclose(rec[:, WOBS_ACCEPTANCE], accp, rtol=1e-5)
     assert (ops.worldline_observables(m, v, W=W)[:, WOBS_DELTA_M_ABS] == 0).all().item()
 
 
