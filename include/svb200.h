@@ -130,6 +130,18 @@ int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n,
                       void* stream);
 
 /*
+ * The same sweeps for lattices too large for shared memory (N a multiple of 32, e.g. configs 4 and 5): one CTA per
+ * 32 x 32 tile with a ghost zone, one pass per sweep, ping-pong between (phi, n) and a caller-provided workspace
+ * (phi_ws, n_ws) of the same shapes.  The result always ends in (phi, n).  fp64 phi, Philox mode.
+ */
+#define SVB_PATH_TILED 3
+int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
+                            int64_t chains, int N, double kappa, const double* kappa_chain, int W,
+                            double interval_phi, int interval_n, int n_sweeps,
+                            uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode,
+                            double* obs, uint8_t* accept_mask, double* dS_out, void* stream);
+
+/*
  * The same sweep with HOST buffers: the reference's `step(cfg)` contract (host arrays in, host arrays out,
  * neighborhood.py:59-137) for a whole batch.  phi_host / n_host / obs_host are pinned HOST buffers updated in place;
  * phi_dev / n_dev / obs_dev are caller-owned DEVICE staging buffers of the same shapes.  The chains are processed in

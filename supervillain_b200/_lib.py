@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('SVB200_LIB') or os.path.join(HERE, 'libsvb200.so')   
 F64, F32, I32, I64 = 0, 1, 2, 3
 RNG_PHILOX, RNG_INJECTED = 0, 1
 ARITH_STRICT, ARITH_FAST = 0, 1
-PATH_AUTO, PATH_SMEM, PATH_GLOBAL = 0, 1, 2
+PATH_AUTO, PATH_SMEM, PATH_GLOBAL, PATH_TILED = 0, 1, 2, 3
 VOBS_ACTION, VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1, VOBS_ACCEPTED, VOBS_ACCEPTANCE, VOBS_COUNT = range(7)
 (WOBS_SUM_F2, WOBS_SUM_DF2, WOBS_WRAP0, WOBS_WRAP1, WOBS_ACCEPTED, WOBS_ACCEPTANCE, WOBS_DELTA_M_ABS,
  WOBS_COUNT) = range(8)
@@ -30,6 +30,7 @@ SIGNATURES = {
     'svb_villain_sweep': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'svb_villain_observables': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
+    'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),
     'svb_worldline_sweep': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _i, _i, _u64, _u64, _u64, _i, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

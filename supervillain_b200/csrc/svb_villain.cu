@@ -959,6 +959,114 @@ __global__ void __launch_bounds__(TT, MINB) villain_smem_resid_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------
+// TILED path: lattices that do not fit shared memory (config 4: L=128, config 5: L=4096).
+//
+// One CTA owns a 32 x 32 tile of one chain and produces its final state in ONE pass: it loads the tile plus a ghost
+// zone (2 sites on the low sides, 3 on the high sides: 37 x 38 with padding) from the INPUT buffers, runs the colour-0
+// updates on the tile grown by one ring more than the colour-1 updates need, then the colour-1 updates, and writes only
+// the sites and links it owns to the OUTPUT buffers (ping-pong: a neighbouring CTA may still be reading the inputs).
+// The Philox counter is keyed by the GLOBAL site and chain, so the redundant ghost updates are bit-identical in every
+// tile that computes them and the result does not depend on the tiling (tests: identical to the global path and to
+// the oracle).  HBM traffic: (37 x 38 / 1024) reads + 1 write of the state = 38 B per site-update instead of the
+// >= 56 B of the per-colour global path; compute redundancy (35^2 + 33^2) / (2 x 1024) = 1.13.
+// Why these sizes: a link (mu, x) owned by the tile is last touched by x or x + e_mu, so final decisions are needed
+// on the tile grown by +1 on the high sides (33 x 33, local [2, 35)); the colour-1 sites there read phi and links that
+// colour-0 sites one ring further out (35 x 35, local [1, 36)) may have changed; those read initial data one more
+// ring out (37 x 37, local [0, 37)).
+// ------------------------------------------------------------------------------------------
+constexpr int kTile = 32;
+constexpr int kRegRows = kTile + 5;      // 37
+constexpr int kRegCols = kTile + 6;      // 38: even, so rows are pairs of 16-byte aligned phi
+constexpr int kRegSize = kRegRows * kRegCols;
+
+template <bool STRICT>
+__global__ void __launch_bounds__(128, 8) villain_tiled_kernel(const __grid_constant__ VillainArgs a, const double* __restrict__ phi_in,
+                                                               const int32_t* __restrict__ n_in, double* __restrict__ phi_out,
+                                                               int32_t* __restrict__ n_out, int sweep, int tiles_per_side) {
+    __shared__ __align__(16) double sphi[kRegSize];
+    __shared__ __align__(16) int32_t sn0[kRegSize];
+    __shared__ __align__(16) int32_t sn1[kRegSize];
+    __shared__ double red[2 * 4];
+    const int N = a.N;
+    const long long V = (long long)N * N;
+    const int tiles = tiles_per_side * tiles_per_side;
+    const long long chain = blockIdx.x / tiles;
+    const int tile = blockIdx.x - (int)(chain * tiles);
+    const int a0 = (tile / tiles_per_side) * kTile, a1 = (tile % tiles_per_side) * kTile;
+    const int tid = threadIdx.x;
+    const double* gphi = phi_in + chain * V;
+    const int32_t* gn0 = n_in + chain * 2 * V;
+    const int32_t* gn1 = gn0 + V;
+
+    // ---- load the region, two sites at a time (N and the origins are even: a pair never straddles the wrap) ----
+    for (int p = tid; p < kRegRows * (kRegCols / 2); p += 128) {
+        const int i = p / (kRegCols / 2), jj = 2 * (p - i * (kRegCols / 2));
+        int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+        int x1 = a1 - 2 + jj; x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+        const long long g = (long long)x0 * N + x1;
+        const int l = i * kRegCols + jj;
+        *reinterpret_cast<double2*>(sphi + l) = *reinterpret_cast<const double2*>(gphi + g);
+        *reinterpret_cast<int2*>(sn0 + l) = *reinterpret_cast<const int2*>(gn0 + g);
+        *reinterpret_cast<int2*>(sn1 + l) = *reinterpret_cast<const int2*>(gn1 + g);
+    }
+    __syncthreads();
+
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    const double half_kappa = kappa / 2;
+    VillainConsts kc;
+    int dg_scale;
+    villain_consts<false, STRICT>(a, kc, dg_scale);
+    LinkSums unused;
+    double n_acc = 0.0, sum_A = 0.0;
+
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        const int lo = (c == 0) ? 1 : 2;                      // colour 0 on local [1, 36), colour 1 on local [2, 35)
+        const int side = (c == 0) ? kTile + 3 : kTile + 1;    // 35, 33
+        const int per_row = (side + 1) / 2;
+        for (int idx = tid; idx < side * per_row; idx += 128) {
+            const int i = lo + idx / per_row;
+            const int j = lo + 2 * (idx % per_row) + ((i + lo + c) & 1);       // (i + j) & 1 == c  (origins are even)
+            if (j >= lo + side) continue;
+            int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+            int x1 = a1 - 2 + j;  x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+            const int site = x0 * N + x1;
+            const VillainDraw d = villain_get_draw<false, true>(a, chain, sweep, site, dg_scale);
+            const SiteOut o = villain_site_update<double, STRICT, 0>(sphi, sn0, sn1, kRegCols, i, j, half_kappa, kc, d, false, unused);
+            const bool owned = (i >= 2) && (i < 2 + kTile) && (j >= 2) && (j < 2 + kTile);
+            if (owned) {
+                n_acc += o.ok ? 1.0 : 0.0;
+                sum_A += o.A;
+                if (a.accept_mask) a.accept_mask[chain * V + site] = o.ok ? 1 : 0;
+                if (a.dS_out) a.dS_out[chain * V + site] = o.dS;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write the owned tile ----
+    double* ophi = phi_out + chain * V;
+    int32_t* on0 = n_out + chain * 2 * V;
+    int32_t* on1 = on0 + V;
+    for (int p = tid; p < kTile * (kTile / 2); p += 128) {
+        const int i = p / (kTile / 2), jj = 2 * (p - i * (kTile / 2));
+        const long long g = (long long)(a0 + i) * N + (a1 + jj);
+        const int l = (i + 2) * kRegCols + (jj + 2);
+        *reinterpret_cast<double2*>(ophi + g) = *reinterpret_cast<const double2*>(sphi + l);
+        *reinterpret_cast<int2*>(on0 + g) = *reinterpret_cast<const int2*>(sn0 + l);
+        *reinterpret_cast<int2*>(on1 + g) = *reinterpret_cast<const int2*>(sn1 + l);
+    }
+    if (a.obs) {
+        double sred[2] = {n_acc, sum_A};
+        block_sum<2>(sred, red);
+        if (tid == 0) {
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, sred[0]);
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, sred[1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // GLOBAL path: one launch per colour pass, straight out of HBM / L2 (any N).
 // ------------------------------------------------------------------------------------------
 template <typename real, bool INJECTED, bool STRICT>
@@ -1406,5 +1514,57 @@ extern "C" int svb_villain_sweep_host(void* phi_host, int phi_dtype, int32_t* n_
             SVB_CUDA_TRY(cudaMemcpyAsync(obs_host + lo * SVB_VOBS_COUNT, obs_dev + lo * SVB_VOBS_COUNT,
                                          cnt * SVB_VOBS_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    return SVB_OK;
+}
+
+
+// Tiled single-pass sweeps for lattices too large for shared memory (N a multiple of 32): ping-pong between the fields
+// and a caller-provided workspace of the same size; the result always ends in (phi, n).
+extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws, int64_t chains, int N, double kappa,
+                                       const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
+                                       uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode, double* obs,
+                                       uint8_t* accept_mask, double* dS_out, void* stream) {
+    if (!phi || !n || !phi_ws || !n_ws) return fail(SVB_E_NULL, "svb_villain_sweep_tiled: fields and workspace are required");
+    if (chains < 0 || N < kTile || (N % kTile) != 0) return fail(SVB_E_SHAPE, "svb_villain_sweep_tiled: N=%d must be a multiple of %d", N, kTile);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_tiled: kappa must be positive");
+    if (W < 1 || interval_n < 0 || interval_n > 31 || n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_sweep_tiled: W / interval_n / n_sweeps");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+    const int tps = N / kTile;
+    const long long blocks = (long long)chains * tps * tps;
+    if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_sweep_tiled: too many tiles (%lld)", blocks);
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
+    a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
+    a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (obs) {
+        villain_zero_counters_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    double* bufp[2] = {reinterpret_cast<double*>(phi), reinterpret_cast<double*>(phi_ws)};
+    int32_t* bufn[2] = {n, n_ws};
+    for (int s = 0; s < n_sweeps; ++s) {
+        const int src = s & 1, dst = src ^ 1;
+        const bool last = (s == n_sweeps - 1);
+        a.accept_mask = last ? accept_mask : nullptr;
+        a.dS_out = last ? dS_out : nullptr;
+        if (arith_mode == SVB_ARITH_STRICT)
+            villain_tiled_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps);
+        else
+            villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    if (n_sweeps & 1) {     // the result sits in the workspace: bring it home
+        const size_t V = (size_t)N * N;
+        SVB_CUDA_TRY(cudaMemcpyAsync(phi, phi_ws, (size_t)chains * V * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        SVB_CUDA_TRY(cudaMemcpyAsync(n, n_ws, (size_t)chains * 2 * V * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
     return SVB_OK;
 }

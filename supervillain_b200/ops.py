@@ -14,6 +14,9 @@ from ._lib import (ARITH_FAST, ARITH_STRICT, PATH_AUTO, PATH_GLOBAL, PATH_SMEM, 
                    VOBS_COUNT, WOBS_COUNT, WL_COEXACT, WL_JOINT, WL_VORTEX)
 
 _PATHS = {'auto': PATH_AUTO, 'smem': PATH_SMEM, 'global': PATH_GLOBAL}
+_TILE = 32
+_SMEM_MAX_N = 96            # largest fp64 lattice whose chain fits one SM's shared memory
+_workspaces = {}            # (device, chains, N) -> (phi_ws, n_ws) for the tiled ping-pong path
 _ARITH = {'strict': ARITH_STRICT, 'fast': ARITH_FAST}
 _WL_MODES = {'joint': WL_JOINT, 'vortex': WL_VORTEX, 'coexact': WL_COEXACT}
 _OPS = {'d': _lib.OP_D, 'delta': _lib.OP_DELTA, 'face_sum': _lib.OP_FACE_SUM, 'coface_sum': _lib.OP_COFACE_SUM}
@@ -65,6 +68,23 @@ def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_s
     if W != W or W == float('inf') or int(W) != W:
         raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W (the reference yields nan for W=inf, '
                          'neighborhood.py:105)')
+    tiled_ok = injected is None and phi.dtype == torch.float64 and N % _TILE == 0
+    if path == 'tiled' and not tiled_ok:
+        raise NotImplementedError('the tiled path needs fp64 phi, Philox draws and N a multiple of 32')
+    if path == 'tiled' or (path == 'auto' and tiled_ok and N > _SMEM_MAX_N):
+        key = (phi.device, chains, N)
+        ws = _workspaces.get(key)
+        if ws is None:
+            _workspaces.clear()                      # one workspace at a time: these are the large lattices
+            ws = _workspaces[key] = (torch.empty_like(phi), torch.empty_like(n))
+        _lib.check(lib.svb_villain_sweep_tiled(
+            p_phi, p_n, ws[0].data_ptr(), ws[1].data_ptr(), chains, N, float(kappa),
+            _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(W), float(interval_phi), int(interval_n),
+            int(n_sweeps), int(seed) & (2**64 - 1), int(sweep0), int(chain0), _ARITH[arithmetic],
+            _opt(obs, 'obs', (torch.float64,), (chains, VOBS_COUNT)),
+            _opt(accept_mask, 'accept_mask', (torch.uint8,), (chains, N, N)),
+            _opt(dS_out, 'dS_out', (torch.float64,), (chains, N, N)), _stream()))
+        return
     if injected is None:
         rng_mode, pu, pd, pf, pb = RNG_PHILOX, None, None, None, None
     else:

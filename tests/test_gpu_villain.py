@@ -294,3 +294,30 @@ def test_host_stepper_equals_resident_path():
         assert torch.equal(a, ref_phi.cpu()) and torch.equal(b, ref_n.cpu())
         assert torch.equal(rec, ref_obs.cpu())
         assert G.counter == 4
+
+
+@pytest.mark.parametrize('arith', ['fast', 'strict'])
+@pytest.mark.parametrize('N,chains,sweeps', [(32, 8, 1), (64, 6, 2), (128, 4, 3), (256, 2, 2)])
+def test_tiled_path_equals_oracle_and_global_path(N, chains, sweeps, arith):
+    """The single-pass tiled kernel (ghost zones + ping-pong, configs 4 and 5): identical to the C oracle and to the
+    per-colour global path, independent of the tiling (N = 32 is a single tile whose ghost zone wraps onto itself)."""
+    from oracle import c_oracle as C
+    kappa, seed = 0.6, 31
+    phi0, n0 = V.hot_start(np.random.default_rng(N + 1), N, chains)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    mask = torch.zeros((chains, N, N), dtype=torch.uint8, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps, seed=seed, sweep0=3, chain0=7, obs=obs, arithmetic=arith, path='tiled',
+                      accept_mask=mask)
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=sweeps, seed=seed, sweep0=3, chain0=7)
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, VOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-12 if arith == 'strict' else 1e-5)
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, kappa), rtol=1e-12)
+    assert (rec[:, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum(axis=(-3, -2, -1))).all()
+    g_phi, g_n = dev(phi0), dev(n0, torch.int32)
+    g_mask = torch.zeros_like(mask)
+    ops.villain_sweep(g_phi, g_n, kappa, n_sweeps=sweeps, seed=seed, sweep0=3, chain0=7, arithmetic=arith, path='global',
+                      accept_mask=g_mask)
+    assert torch.equal(g_phi, phi) and torch.equal(g_n, n) and torch.equal(g_mask, mask)
