@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(128, 8) villain_tiled_kernel(const __grid_cons
     __shared__ __align__(16) double sphi[kRegSize];
     __shared__ __align__(16) int32_t sn0[kRegSize];
     __shared__ __align__(16) int32_t sn1[kRegSize];
-    __shared__ double red[2 * 4];
+    __shared__ double red[2 * 32];
     const int N = a.N;
     const long long V = (long long)N * N;
     const int tiles = tiles_per_side * tiles_per_side;

@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(128) worldline_wrapping_kernel(WrappingArgs a)
     const int N = a.N, V = N * N;
     int32_t* sm = reinterpret_cast<int32_t*>(smem_raw);       // m: 2V
     int32_t* sv = sm + 2 * V;                                  // v: V
-    __shared__ double red[2 * 4];
+    __shared__ double red[2 * 32];
     const double Wd = (double)a.W;
     for (long long chain = blockIdx.x; chain < a.chains; chain += gridDim.x) {
         int32_t* gm = a.m + chain * 2 * V;
