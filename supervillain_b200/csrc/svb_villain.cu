@@ -982,7 +982,8 @@ constexpr int kRegSize = kRegRows * kRegCols;
 template <bool STRICT>
 __global__ void __launch_bounds__(128, 8) villain_tiled_kernel(const __grid_constant__ VillainArgs a, const double* __restrict__ phi_in,
                                                                const int32_t* __restrict__ n_in, double* __restrict__ phi_out,
-                                                               int32_t* __restrict__ n_out, int sweep, int tiles_per_side) {
+                                                               int32_t* __restrict__ n_out, int sweep, int tiles_per_side,
+                                                               int fuse_obs) {
     __shared__ __align__(16) double sphi[kRegSize];
     __shared__ __align__(16) int32_t sn0[kRegSize];
     __shared__ __align__(16) int32_t sn1[kRegSize];
@@ -1062,6 +1063,27 @@ __global__ void __launch_bounds__(128, 8) villain_tiled_kernel(const __grid_cons
         if (tid == 0) {
             atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, sred[0]);
             atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, sred[1]);
+        }
+        if (fuse_obs) {
+            // Observables of the tile's owned sites from the final state in shared memory.  Every link an owned
+            // plaquette touches has both of its end sites inside the region where final decisions were made
+            // (local [2, 35)), so (dn)^2 is final here as well.  Partials are combined with atomics.
+            __syncthreads();
+            ChainSums cs;
+            cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
+            for (int p = tid; p < kTile * kTile; p += 128) {
+                const int i = 2 + p / kTile, j = 2 + (p % kTile);
+                villain_obs_site<double, 0>(sphi, sn0, sn1, kRegCols, i, j, cs.action, cs.dn2, cs.w0, cs.w1);
+            }
+            __shared__ double scratch[6 * 32];
+            cs = block_reduce_chain(cs, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_VOBS_COUNT;
+                atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * cs.action);
+                atomicAdd(o + SVB_VOBS_SUM_DN2, (double)cs.dn2);
+                atomicAdd(o + SVB_VOBS_WRAP0, (double)cs.w0);
+                atomicAdd(o + SVB_VOBS_WRAP1, (double)cs.w1);
+            }
         }
     }
 }
@@ -1543,28 +1565,43 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // An even number of ping-pong sweeps ends in (phi, n).  An odd count would end in the workspace, so the last sweep of
+    // an odd count is done in place by the per-colour global path instead (cheaper than copying the state back).
+    const int n_tiled = n_sweeps & ~1;
+    const bool tail_global = (n_sweeps & 1) != 0;
     if (obs) {
-        villain_zero_counters_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains);
+        villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains, 0);
         SVB_CUDA_TRY(cudaGetLastError());
     }
     double* bufp[2] = {reinterpret_cast<double*>(phi), reinterpret_cast<double*>(phi_ws)};
     int32_t* bufn[2] = {n, n_ws};
-    for (int s = 0; s < n_sweeps; ++s) {
+    for (int s = 0; s < n_tiled; ++s) {
         const int src = s & 1, dst = src ^ 1;
         const bool last = (s == n_sweeps - 1);
         a.accept_mask = last ? accept_mask : nullptr;
         a.dS_out = last ? dS_out : nullptr;
+        const int fuse = (obs && last) ? 1 : 0;
         if (arith_mode == SVB_ARITH_STRICT)
-            villain_tiled_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps);
+            villain_tiled_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
         else
-            villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps);
+            villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
         SVB_CUDA_TRY(cudaGetLastError());
     }
-    if (n_sweeps & 1) {     // the result sits in the workspace: bring it home
-        const size_t V = (size_t)N * N;
-        SVB_CUDA_TRY(cudaMemcpyAsync(phi, phi_ws, (size_t)chains * V * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        SVB_CUDA_TRY(cudaMemcpyAsync(n, n_ws, (size_t)chains * 2 * V * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (tail_global) {
+        const int V = N * N;
+        const int bpc = (V / 2 + 255) / 256;
+        const long long gblocks = (long long)bpc * chains;
+        if (gblocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_sweep_tiled: too many blocks");
+        a.accept_mask = accept_mask;
+        a.dS_out = dS_out;
+        for (int c = 0; c < 2; ++c) {
+            if (arith_mode == SVB_ARITH_STRICT)
+                villain_colour_pass_kernel<double, false, true><<<(unsigned)gblocks, 256, 0, st>>>(a, n_sweeps - 1, c, bpc, 1);
+            else
+                villain_colour_pass_kernel<double, false, false><<<(unsigned)gblocks, 256, 0, st>>>(a, n_sweeps - 1, c, bpc, 1);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+        if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
     }
-    if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
     return SVB_OK;
 }

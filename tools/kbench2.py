@@ -47,21 +47,23 @@ if 'c4' in which:
     phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
     obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
     kc = torch.linspace(0.3, 1.2, CH, dtype=torch.float64, device='cuda')
-    k = [0]
-    def f():
-        k[0] += 1
-        ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], kappa_chain=kc, obs=obs)
-    report('villain L=128 x 1024 chains (C4), auto path', CH * N * N, 32, timeit(f, n=5))
+    for path, sw in (('global', 1), ('tiled', 1), ('tiled', 2), ('tiled', 10)):
+        k = [0]
+        def f():
+            k[0] += sw
+            ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], kappa_chain=kc, obs=obs, path=path, n_sweeps=sw)
+        report(f'villain L=128 x 1024 chains (C4), {path}, {sw} sweep(s)/call', CH * N * N * sw, 32, timeit(f, n=5))
 if 'c5' in which:
     N, CH = 4096, 1
     S = svb.Villain(svb.Lattice2D(N), 0.5)
     phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
     obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
-    k = [0]
-    def f():
-        k[0] += 1
-        ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], obs=obs)
-    report('villain L=4096 x 1 chain (C5), auto path', CH * N * N, 32, timeit(f, n=5))
+    for path, sw in (('global', 1), ('tiled', 1), ('tiled', 2), ('tiled', 10)):
+        k = [0]
+        def f():
+            k[0] += sw
+            ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], obs=obs, path=path, n_sweeps=sw)
+        report(f'villain L=4096 x 1 chain (C5), {path}, {sw} sweep(s)/call', CH * N * N * sw, 32, timeit(f, n=5))
 if 'forms' in which:
     N, CH = 32, 65536                                    # 512 MiB f64 0-forms
     a = torch.randn((CH, 1, N, N), dtype=torch.float64, device='cuda')
