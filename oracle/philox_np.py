@@ -16,6 +16,7 @@ MASK32 = np.uint64(0xFFFFFFFF)
 
 STREAM_VILLAIN_NEIGHBORHOOD = 1
 STREAM_WORLDLINE_PLAQUETTE = 2
+STREAM_VILLAIN_REFINE = 4
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -47,31 +48,41 @@ def philox_site(seed, chain, sweep, site, stream_id):
 
 TWO_M44 = 2.0 ** -44
 TWO_M52 = 2.0 ** -52
+TWO_M32 = 2.0 ** -32
 
 
 def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
     """Dense per-site proposals of one chain and sweep, in the layout of villain_np.draw_neighborhood.
 
-    128 Philox bits (x, y, z, w) per site split 44 / 52 / 32:
-      dphi = -I + (2I) * ((k44 + 1/2) 2^-44),  k44 = x << 12 | y >> 20
-      u    = (k52 + 1/2) 2^-52,                k52 = (y & 0xFFFFF) << 32 | z
+    Draw mapping, version 2 (documented in supervillain_b200/csrc/svb_villain.cu): sites (x0, x1) and (x0 ^ 8, x1)
+    share the Philox block with counter word 0 = (x0 & ~8) N + x1; the site with bit 3 of x0 clear owns words
+    (A, B) = (0, 1), the other one words (2, 3):
+      dphi = -I + (2I) * ((A + 1/2) 2^-32)
       dn   = W * (digit_i - interval_n), digit_i = the four leading base-K digits (K = 2 interval_n + 1)
-             of the fraction w / 2^32, ordered (fwd 0, bwd 0, fwd 1, bwd 1)
+             of the fraction B / 2^32, ordered (fwd 0, bwd 0, fwd 1, bwd 1)
+      u    = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53), f = the remainder of B after the four digits,
+             e = word 0 or 2 (by half) of the block with the same counter in stream STREAM_VILLAIN_REFINE
+    (the kernels generate e only when u < A is not already decided by f; the decision is the same).
     """
-    site = np.arange(N * N, dtype=np.uint64)
-    x, y, z, w = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_NEIGHBORHOOD)
-    kphi = (x << np.uint64(12)) | (y >> np.uint64(20))
-    ku = ((y & np.uint64(0xFFFFF)) << np.uint64(32)) | z
-    Uphi = (kphi.astype(np.float64) + 0.5) * TWO_M44
-    u = (ku.astype(np.float64) + 0.5) * TWO_M52
+    x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
+    c0 = ((x0 & ~8) * N + x1).astype(np.uint64)
+    half = ((x0 >> 3) & 1).astype(bool)
+    w = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD)
+    r = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE)
+    A = np.where(half, w[2], w[0])
+    B = np.where(half, w[3], w[1])
+    e = np.where(half, r[2], r[0])
+    Uphi = (A.astype(np.float64) + 0.5) * TWO_M32
     dphi = -interval_phi + (2.0 * interval_phi) * Uphi
     K = np.uint64(2 * interval_n + 1)
-    f = w
+    f = B
     digits = []
     for _ in range(4):
         prod = f * K
         digits.append((prod >> np.uint64(32)).astype(np.int64) - interval_n)
         f = prod & MASK32
+    frac = (e.astype(np.float64) + 0.5) * TWO_M32
+    u = np.minimum((f.astype(np.float64) + frac) * TWO_M32, 1.0 - 2.0 ** -53)
     dn_fwd = np.stack([W * digits[0], W * digits[2]]).reshape(2, N, N)
     dn_bwd = np.stack([W * digits[1], W * digits[3]]).reshape(2, N, N)
     return {'u': u.reshape(N, N), 'dphi': dphi.reshape(N, N), 'dn_fwd': dn_fwd, 'dn_bwd': dn_bwd}

@@ -58,24 +58,30 @@ static void philox_site(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t 
     svo_philox4x32_10(ctr, key, out);
 }
 
-/* 128 bits -> (u, dphi, dn[4]); split 44 / 52 / 32 (see svb_villain.cu) */
-void svo_villain_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site, int W, double interval_phi,
+/* draw mapping version 2 (see svb_villain.cu): 64 bits per site from the Philox block its pair shares, and the
+ * trailing bits of the uniform from the refinement stream */
+void svo_villain_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site, int N, int W, double interval_phi,
                       int interval_n, double* u, double* dphi, int dn[4]) {
-    uint32_t w[4];
-    philox_site(seed, chain, sweep, site, 1u, w);
-    uint64_t kphi = ((uint64_t)w[0] << 12) | (uint64_t)(w[1] >> 20);
-    uint64_t ku = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | (uint64_t)w[2];
-    double Uphi = ((double)kphi + 0.5) * 0x1p-44;
-    *u = ((double)ku + 0.5) * 0x1p-52;
+    uint32_t w[4], r[4];
+    int x0 = (int)(site / (uint32_t)N), x1 = (int)(site % (uint32_t)N);
+    uint32_t c0 = (uint32_t)((x0 & ~8) * N + x1);
+    int half = (x0 >> 3) & 1;
+    philox_site(seed, chain, sweep, c0, 1u, w);
+    philox_site(seed, chain, sweep, c0, 4u, r);
+    uint32_t A = w[2 * half], B = w[2 * half + 1], e = r[2 * half];
+    double Uphi = ((double)A + 0.5) * 0x1p-32;
     double prod = (2.0 * interval_phi) * Uphi;
     *dphi = -interval_phi + prod;
     uint32_t K = (uint32_t)(2 * interval_n + 1);
-    uint32_t f = w[3];
+    uint32_t f = B;
     for (int i = 0; i < 4; ++i) {
         uint64_t p = (uint64_t)f * K;
         f = (uint32_t)p;
         dn[i] = W * ((int)(p >> 32) - interval_n);
     }
+    double frac = ((double)e + 0.5) * 0x1p-32;
+    double uu = ((double)f + frac) * 0x1p-32;
+    *u = uu < 0x1.fffffffffffffp-1 ? uu : 0x1.fffffffffffffp-1;
 }
 
 /* mode 0 joint: a = dm in {-1,+1}, b = dv in {-1,0,+1}; modes 1, 2: a in [-I..-1, 1..I] */
@@ -218,7 +224,7 @@ int svo_villain_sweep_philox(double* phi, int64_t* n, int64_t chains, int N, dou
         for (int s = 0; s < n_sweeps; ++s) {
             for (int i = 0; i < V; ++i) {
                 int dn[4];
-                svo_villain_draw(seed, chain0 + (uint64_t)c, sweep0 + (uint64_t)s, (uint32_t)i, W, interval_phi, interval_n,
+                svo_villain_draw(seed, chain0 + (uint64_t)c, sweep0 + (uint64_t)s, (uint32_t)i, N, W, interval_phi, interval_n,
                                  &u[i], &dphi[i], dn);
                 dnf[i] = dn[0]; dnb[i] = dn[1]; dnf[V + i] = dn[2]; dnb[V + i] = dn[3];
             }

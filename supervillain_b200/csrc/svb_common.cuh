@@ -65,7 +65,8 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1,
 }
 
 // Stream ids folded into the top byte of counter word 3, so the generators never share draws.
-enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u, STREAM_WORLDLINE_WRAPPING = 3u };
+enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u, STREAM_WORLDLINE_WRAPPING = 3u,
+                  STREAM_VILLAIN_REFINE = 4u };
 
 __host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t chain, uint64_t sweep,
                                                          uint32_t site, uint32_t stream_id) {
@@ -112,17 +113,28 @@ __device__ __forceinline__ double exp_clipped(double x) {
 // The acceptance probability itself, wanted only for the generator's report() statistic, comes from MUFU.EX2 in fp32
 // (relative accuracy ~1e-6); STRICT arithmetic keeps the fp64 exponential for both.
 // ------------------------------------------------------------------------------------------
+// Returns +1 (accept), 0 (reject) or -1 (undecided: evaluate exactly).  `u_mid` is the midpoint of a bracket of
+// half-width `u_halfwidth_rel` * u_mid (relative) that is known to contain u; pass 0 for an exactly known u.
 #ifndef SVB_NO_LOG_FILTER
-__device__ __forceinline__ bool metropolis_filtered(double dS, double u, double& prob) {
-    const float dSf = (float)dS, uf = (float)u;
+__device__ __forceinline__ int metropolis_log_filter(double dS, double u_mid, float u_halfwidth_rel, double& prob) {
+    const float dSf = (float)dS, uf = (float)u_mid;
     prob = (double)fminf(exp2f(-1.4426950408889634f * dSf), 1.0f);
     const float L = -0.6931471805599453f * __log2f(uf);
-    const float band = 1e-5f * (1.0f + L + fabsf(dSf));
-    if (dSf > L + band) return false;
-    if (dSf < L - band) return true;
+    const float band = 1e-5f * (1.0f + L + fabsf(dSf)) + 1.5f * u_halfwidth_rel;
+    if (dSf > L + band) return 0;
+    if (dSf < L - band) return 1;
+    return -1;
+}
+__device__ __forceinline__ bool metropolis_filtered(double dS, double u, double& prob) {
+    const int r = metropolis_log_filter(dS, u, 0.0f, prob);
+    if (r >= 0) return r != 0;
     return u < exp_clipped(-dS);
 }
 #else
+__device__ __forceinline__ int metropolis_log_filter(double dS, double u_mid, float u_halfwidth_rel, double& prob) {
+    prob = exp_clipped(-dS);
+    return -1;
+}
 __device__ __forceinline__ bool metropolis_filtered(double dS, double u, double& prob) {
     prob = exp_clipped(-dS);
     return u < prob;

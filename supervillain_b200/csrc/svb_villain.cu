@@ -137,9 +137,12 @@ struct Arith<float, false> {
 // c * dg[i], where (unit, c) = (W, fl(2 pi W)) for Philox draws in FAST arithmetic and (1, 2 pi)
 // otherwise (then dg already carries the factor W and 2 pi * dn is rounded exactly as numpy does).
 struct VillainDraw {
-    double u;
+    double u;          // INJECTED: the Metropolis uniform.  Philox: the midpoint (f + 1/2) 2^-32 of the known bracket
     double dphi;
     int dg[4];
+    uint32_t f;        // Philox: leading 32 bits of the uniform, u in [f, f + 1] 2^-32; the rest is drawn lazily
+    uint32_t c0;       // Philox: counter word 0 of the site's pair
+    uint32_t half;     // Philox: which half of the 128-bit block belongs to this site
 };
 
 struct VillainConsts {
@@ -147,29 +150,65 @@ struct VillainConsts {
     int unit;        // integer change of n per unit of dg
 };
 
-// The Philox draw mapping: 128 bits per site per sweep, split 44 / 52 / 32.
-//   dphi = -I + (2 I) * ((k44 + 1/2) 2^-44)     [numpy: lo + (hi - lo) * U, multiply then add, no FMA]
-//   u    = (k52 + 1/2) 2^-52                    in (0,1): u = 0 can never force an accept
-//   dg_i = digit_i - interval_n, digit_i the leading base-K digits (K = 2 interval_n + 1) of the
-//          32-bit fraction w3 / 2^32:  p = f * K;  digit = p >> 32;  f = p mod 2^32
-// The 44- and 52-bit integers become doubles by planting them in the mantissa of 2^52 (exact).
-__device__ __forceinline__ VillainDraw villain_draw_from_bits(const Philox4& p, double interval_phi, int interval_n) {
-    VillainDraw d;
+// The Philox draw mapping (version 2): 64 bits per site per sweep, and more only when a decision needs them.
+//   Sites (x0, x1) and (x0 ^ 8, x1) -- same colour -- share one Philox4x32-10 block with counter word 0
+//   c0 = (x0 & ~8) N + x1; the site with bit 3 of x0 clear owns words (0, 1), the other one words (2, 3):
+//   word A -> dphi = -I + (2 I) * ((A + 1/2) 2^-32)       [numpy: lo + (hi - lo) * U, multiply then add, no FMA]
+//   word B -> the four leading base-K digits (K = 2 interval_n + 1) of the fraction B / 2^32:
+//               p = f K;  digit = p >> 32;  f = p mod 2^32;   dg_i = digit_i - interval_n   (links f0, b0, f1, b1)
+//             and the remainder f after the fourth digit (uniform on [0, 2^32), independent of the digits) is the
+//             LEADING 32 bits of the Metropolis uniform:
+//               u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53),  e = word `2 half` of the block with the same
+//               counter in stream STREAM_VILLAIN_REFINE.
+//   u is known to lie in [f, f + 1] 2^-32 without e, which decides u < A unless A falls in that bracket
+//   (probability 2^-32 per proposal); only then is e generated.  Every kernel and the oracle implement exactly this
+//   rule, so decisions are those of the full 64-bit uniform.
+__host__ __device__ __forceinline__ uint32_t villain_pair_counter(int x0, int x1, int N) { return (uint32_t)((x0 & ~8) * N + x1); }
+__host__ __device__ __forceinline__ uint32_t villain_pair_half(int x0) { return (uint32_t)((x0 >> 3) & 1); }
+
+__device__ __forceinline__ double villain_dphi_from_word(uint32_t A, double interval_phi) {
     const double bias = 4503599627370495.5;   // 2^52 - 1/2
-    const double kphi_half = __hiloint2double(0x43300000 | (int)(p.x >> 20), (int)((p.x << 12) | (p.y >> 20))) - bias;
-    const double ku_half = __hiloint2double(0x43300000 | (int)(p.y & 0xFFFFFu), (int)p.z) - bias;
-    const double Uphi = kphi_half * 5.6843418860808015e-14;          // 2^-44
-    d.u = ku_half * 2.220446049250313e-16;                            // 2^-52
-    d.dphi = __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, Uphi));
+    const double U = (__hiloint2double(0x43300000, (int)A) - bias) * 2.3283064365386963e-10;   // (A + 1/2) 2^-32, exact
+    return __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, U));
+}
+
+__device__ __forceinline__ VillainDraw villain_draw_from_words(uint32_t A, uint32_t B, double interval_phi, int interval_n) {
+    VillainDraw d;
+    d.dphi = villain_dphi_from_word(A, interval_phi);
     const uint32_t K = (uint32_t)(2 * interval_n + 1);
-    uint32_t f = p.w;
+    uint32_t f = B;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint64_t prod = (uint64_t)f * K;
         f = (uint32_t)prod;
         d.dg[i] = (int)(prod >> 32) - interval_n;
     }
+    d.f = f;
+    d.u = (__hiloint2double(0x43300000, (int)f) - 4503599627370495.5) * 2.3283064365386963e-10;   // (f + 1/2) 2^-32
     return d;
+}
+
+// The trailing bits of the uniform, generated only when a decision needs them (cold path).
+__device__ __noinline__ double villain_refined_uniform(uint32_t f, uint32_t c0, uint32_t half, unsigned long long seed,
+                                                       unsigned long long chain, unsigned long long sweep) {
+    const Philox4 p = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE);
+    const uint32_t e = half ? p.z : p.x;
+    const double frac = __dmul_rn(__dadd_rn((double)e, 0.5), 2.3283064365386963e-10);          // (e + 1/2) 2^-32
+    const double u = __dmul_rn(__dadd_rn((double)f, frac), 2.3283064365386963e-10);
+    return fmin(u, 0.99999999999999988898);                                                     // 1 - 2^-53
+}
+
+struct RefineCtx {
+    unsigned long long seed, chain, sweep;
+};
+
+// u < A decided from the bracket [f, f + 1] 2^-32 of u, refining only when A falls inside it.
+__device__ __forceinline__ bool villain_decide_lazy(double A, const VillainDraw& d, const RefineCtx& rc) {
+    const double u_lo = __dmul_rn((double)d.f, 2.3283064365386963e-10);
+    const double u_hi = __dadd_rn(u_lo, 2.3283064365386963e-10);
+    if (A > u_hi) return true;
+    if (A <= u_lo) return false;
+    return villain_refined_uniform(d.f, d.c0, d.half, rc.seed, rc.chain, rc.sweep) < A;
 }
 
 // Philox4x32-10 with the key schedule read from kernel parameters (constant bank operands).
@@ -203,13 +242,29 @@ struct LinkSums {
     int w0, w1;    // sum of final n_0, n_1
 };
 
+// u < min(1, e^-dS) for a Philox draw: the fp32 log filter (FAST fp64 only) on the bracket of u, else the exact test.
+template <typename real, bool STRICT>
+__device__ __forceinline__ bool villain_metropolis_lazy(real dS, const VillainDraw& d, const RefineCtx& rc, double& prob) {
+    if (!STRICT && sizeof(real) == 8) {
+        if (d.f >= 65536u) {     // half-width of the bracket relative to u: 2^-33 / u <= 2^-17
+            const int r = metropolis_log_filter((double)dS, d.u, 7.62939453125e-06f, prob);
+            if (r >= 0) return r != 0;
+        }
+        prob = exp_clipped(-(double)dS);
+        return villain_decide_lazy(prob, d, rc);
+    }
+    prob = Arith<real, STRICT>::accept_prob(dS);
+    return villain_decide_lazy(prob, d, rc);
+}
+
 // One Metropolis proposal at site (x0, x1) of one chain, in place.  `phi`, `n0`, `n1` point at the
 // chain's fields (shared or global memory).  NT > 0: N == NT is a compile-time power of two.
-template <typename real, bool STRICT, int NT>
+// LAZY: the draw is a Philox draw whose uniform is known by its leading 32 bits (see villain_decide_lazy).
+template <typename real, bool STRICT, int NT, bool LAZY>
 __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, int32_t* __restrict__ n0,
                                                        int32_t* __restrict__ n1, int Nrt, int x0, int x1, real half_kappa,
                                                        const VillainConsts& k, const VillainDraw& d, bool collect,
-                                                       LinkSums& sums) {
+                                                       LinkSums& sums, const RefineCtx& rc) {
     using A = Arith<real, STRICT>;
     const int N = NT ? NT : Nrt;
     int xp0, xm0, xp1, xm1;
@@ -264,7 +319,8 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
     }
 
     double acc;                                                 // clip(exp(-dS), 0, 1)   (:115)
-    const bool ok = A::metropolis(dS, d.u, acc);                // u < acc                (:116)
+    const bool ok = LAZY ? villain_metropolis_lazy<real, STRICT>(dS, d, rc, acc)
+                         : A::metropolis(dS, d.u, acc);         // u < acc                (:116)
     if (ok) {                                                   // (:121-128)
         phi[i_c] = A::add(pc, dphi);
         n0[i_c] = nf0 + k.unit * d.dg[0];
@@ -292,8 +348,8 @@ __device__ __forceinline__ SiteOut villain_site_update(real* __restrict__ phi, i
 }
 
 template <bool INJECTED, bool KEYS>
-__device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, long long chain, int sweep, int site,
-                                                        int dg_scale) {
+__device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, long long chain, int sweep, int x0, int x1,
+                                                        int site, int dg_scale) {
     if (INJECTED) {
         const long long V = (long long)a.N * a.N;
         const long long base = ((long long)sweep * a.chains + chain) * V + site;
@@ -305,18 +361,26 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
         d.dg[1] = a.inj_dn_bwd[lbase];
         d.dg[2] = a.inj_dn_fwd[lbase + V];
         d.dg[3] = a.inj_dn_bwd[lbase + V];
+        d.f = 0; d.c0 = 0; d.half = 0;
         return d;
     } else {
         const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
-        const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, (uint32_t)site)
-                               : philox_site(a.seed, gc, gs, (uint32_t)site, STREAM_VILLAIN_NEIGHBORHOOD);
-        VillainDraw d = villain_draw_from_bits(p, a.interval_phi, a.interval_n);
+        const uint32_t c0 = villain_pair_counter(x0, x1, a.N), half = villain_pair_half(x0);
+        const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, c0) : philox_site(a.seed, gc, gs, c0, STREAM_VILLAIN_NEIGHBORHOOD);
+        VillainDraw d = villain_draw_from_words(half ? p.z : p.x, half ? p.w : p.y, a.interval_phi, a.interval_n);
+        d.c0 = c0; d.half = half;
         if (dg_scale != 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) d.dg[i] *= dg_scale;
         }
         return d;
     }
+}
+
+__device__ __forceinline__ RefineCtx villain_refine_ctx(const VillainArgs& a, long long chain, int sweep) {
+    RefineCtx rc;
+    rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain; rc.sweep = a.sweep0 + (unsigned long long)sweep;
+    return rc;
 }
 
 // (unit, c, dg_scale) for a launch: FAST Philox keeps dg in units of W; everything else folds W into dg
@@ -487,9 +551,9 @@ __global__ void __launch_bounds__(TT ? TT : 256, MINB) villain_smem_kernel(const
                         const int x0 = j / halfN;
                         const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                         const int site = x0 * N + x1;
-                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, site, dg_scale);
-                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
-                                                                                collect, ls);
+                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, x0, x1, site, dg_scale);
+                        const SiteOut o = villain_site_update<real, STRICT, NT, !INJECTED>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                                           collect, ls, villain_refine_ctx(a, chain, s));
                         n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
                         if (debug) {
@@ -501,9 +565,9 @@ __global__ void __launch_bounds__(TT ? TT : 256, MINB) villain_smem_kernel(const
                     for (int site = tid; site < V; site += T) {
                         const int x0 = site / N, x1 = site - x0 * N;
                         if (site_colour(x0, x1, N) != c) continue;
-                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, site, dg_scale);
-                        const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
-                                                                                false, ls);
+                        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, s, x0, x1, site, dg_scale);
+                        const SiteOut o = villain_site_update<real, STRICT, NT, !INJECTED>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                                           false, ls, villain_refine_ctx(a, chain, s));
                         n_acc += o.ok ? 1 : 0;
                         sum_A += o.A;
                         if (debug) {
@@ -663,9 +727,9 @@ __global__ void __launch_bounds__(TT, MINB) villain_smem_pipelined_kernel(const 
                     const int x0 = j / halfN;
                     const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                     const int site = x0 * N + x1;
-                    const VillainDraw d = villain_get_draw<false, true>(a, chain, s, site, dg_scale);
-                    const SiteOut o = villain_site_update<real, STRICT, NT>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
-                                                                            collect, ls);
+                    const VillainDraw d = villain_get_draw<false, true>(a, chain, s, x0, x1, site, dg_scale);
+                    const SiteOut o = villain_site_update<real, STRICT, NT, true>(sphi, sn0, sn1, N, x0, x1, half_kappa, kc, d,
+                                                                                  collect, ls, villain_refine_ctx(a, chain, s));
                     n_acc += o.ok ? 1 : 0;
                     sum_A += o.A;
                     if (debug) {
@@ -724,25 +788,22 @@ __global__ void __launch_bounds__(TT, MINB) villain_smem_pipelined_kernel(const 
 // (K = 2 interval_n + 1 distinct proposals), so no integer is converted to fp64 on the hot path.
 // ------------------------------------------------------------------------------------------
 struct VillainDigits {
-    double u;
-    double dphi;
+    VillainDraw d;     // u bracket, dphi; d.dg[] unused
     int digit[4];      // proposal index in [0, K) for links f0, b0, f1, b1;  dn = W * (digit - interval_n)
 };
 
-__device__ __forceinline__ VillainDigits villain_digits_from_bits(const Philox4& p, double interval_phi, uint32_t K) {
+__device__ __forceinline__ VillainDigits villain_digits_from_words(uint32_t A, uint32_t B, double interval_phi, uint32_t K) {
     VillainDigits d;
-    const double bias = 4503599627370495.5;   // 2^52 - 1/2
-    const double kphi_half = __hiloint2double(0x43300000 | (int)(p.x >> 20), (int)((p.x << 12) | (p.y >> 20))) - bias;
-    const double ku_half = __hiloint2double(0x43300000 | (int)(p.y & 0xFFFFFu), (int)p.z) - bias;
-    d.u = ku_half * 2.220446049250313e-16;                                                    // 2^-52
-    d.dphi = __dadd_rn(-interval_phi, __dmul_rn(2.0 * interval_phi, kphi_half * 5.6843418860808015e-14));
-    uint32_t f = p.w;
+    d.d.dphi = villain_dphi_from_word(A, interval_phi);
+    uint32_t f = B;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint64_t prod = (uint64_t)f * K;
         f = (uint32_t)prod;
         d.digit[i] = (int)(prod >> 32);
     }
+    d.d.f = f;
+    d.d.u = (__hiloint2double(0x43300000, (int)f) - 4503599627370495.5) * 2.3283064365386963e-10;
     return d;
 }
 
@@ -751,14 +812,14 @@ __device__ __forceinline__ SiteOut villain_site_update_resid(double* __restrict_
                                                              int32_t* __restrict__ n1, double* __restrict__ r0,
                                                              double* __restrict__ r1, const double* __restrict__ tpdn, int x0,
                                                              int x1, double half_kappa, int W, int interval_n,
-                                                             const VillainDigits& d) {
+                                                             const VillainDigits& d, const RefineCtx& rc) {
     using A = Arith<double, STRICT>;
     const int i_c = x0 * NT + x1;
     const int i_b0 = ((x0 - 1) & (NT - 1)) * NT + x1;
     const int i_b1 = x0 * NT + ((x1 - 1) & (NT - 1));
     const double r_f0 = r0[i_c], r_b0 = r0[i_b0], r_f1 = r1[i_c], r_b1 = r1[i_b1];
     const double t0 = tpdn[d.digit[0]], t1 = tpdn[d.digit[1]], t2 = tpdn[d.digit[2]], t3 = tpdn[d.digit[3]];   // 2 pi dn
-    const double dphi = d.dphi;
+    const double dphi = d.d.dphi;
     // dr = d(dphi) - 2 pi dn   (neighborhood.py:110)
     const double dr_f0 = A::sub(-dphi, t0), dr_b0 = A::sub(dphi, t1), dr_f1 = A::sub(-dphi, t2), dr_b1 = A::sub(dphi, t3);
     double dS;
@@ -775,7 +836,7 @@ __device__ __forceinline__ SiteOut villain_site_update_resid(double* __restrict_
         dS = half_kappa * acc2;
     }
     double acc;
-    const bool ok = A::metropolis(dS, d.u, acc);
+    const bool ok = villain_metropolis_lazy<double, STRICT>(dS, d.d, rc, acc);
     if (ok) {
         phi[i_c] = A::add(phi[i_c], dphi);
         n0[i_c] += W * (d.digit[0] - interval_n);
@@ -883,11 +944,13 @@ __global__ void __launch_bounds__(TT, MINB) villain_smem_resid_kernel(const __gr
                     const int x0 = j / halfN;
                     const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                     const int site = x0 * N + x1;
+                    const uint32_t pc0 = villain_pair_counter(x0, x1, N), phalf = villain_pair_half(x0);
                     const Philox4 bits = philox_site_keys(a, a.chain0 + (unsigned long long)chain,
-                                                          a.sweep0 + (unsigned long long)s, (uint32_t)site);
-                    const VillainDigits d = villain_digits_from_bits(bits, a.interval_phi, K);
+                                                          a.sweep0 + (unsigned long long)s, pc0);
+                    VillainDigits d = villain_digits_from_words(phalf ? bits.z : bits.x, phalf ? bits.w : bits.y, a.interval_phi, K);
+                    d.d.c0 = pc0; d.d.half = phalf;
                     const SiteOut o = villain_site_update_resid<STRICT, NT>(sphi, sn0, sn1, sr0, sr1, tpdn, x0, x1, half_kappa,
-                                                                            a.W, a.interval_n, d);
+                                                                            a.W, a.interval_n, d, villain_refine_ctx(a, chain, s));
                     n_acc += o.ok ? 1 : 0;
                     sum_A += o.A;
                     if (debug) {
@@ -1032,8 +1095,9 @@ __global__ void __launch_bounds__(128, 8) villain_tiled_kernel(const __grid_cons
             int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
             int x1 = a1 - 2 + j;  x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
             const int site = x0 * N + x1;
-            const VillainDraw d = villain_get_draw<false, true>(a, chain, sweep, site, dg_scale);
-            const SiteOut o = villain_site_update<double, STRICT, 0>(sphi, sn0, sn1, kRegCols, i, j, half_kappa, kc, d, false, unused);
+            const VillainDraw d = villain_get_draw<false, true>(a, chain, sweep, x0, x1, site, dg_scale);
+            const SiteOut o = villain_site_update<double, STRICT, 0, true>(sphi, sn0, sn1, kRegCols, i, j, half_kappa, kc, d, false, unused,
+                                                                           villain_refine_ctx(a, chain, sweep));
             const bool owned = (i >= 2) && (i < 2 + kTile) && (j >= 2) && (j < 2 + kTile);
             if (owned) {
                 n_acc += o.ok ? 1.0 : 0.0;
@@ -1126,8 +1190,9 @@ __global__ void __launch_bounds__(256) villain_colour_pass_kernel(const __grid_c
         int dg_scale;
         villain_consts<INJECTED, STRICT>(a, kc, dg_scale);
         LinkSums unused;
-        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, sweep, site, dg_scale);
-        const SiteOut o = villain_site_update<real, STRICT, 0>(gphi, gn0, gn1, N, x0, x1, half_kappa, kc, d, false, unused);
+        const VillainDraw d = villain_get_draw<INJECTED, true>(a, chain, sweep, x0, x1, site, dg_scale);
+        const SiteOut o = villain_site_update<real, STRICT, 0, !INJECTED>(gphi, gn0, gn1, N, x0, x1, half_kappa, kc, d, false, unused,
+                                                                          villain_refine_ctx(a, chain, sweep));
         n_acc = o.ok ? 1.0 : 0.0;
         sum_A = o.A;
         if (write_debug) {
@@ -1237,9 +1302,11 @@ __global__ void villain_draws_kernel(long long chains, int N, int W, double inte
     if (i >= chains * V) return;
     const long long chain = i / V;
     const int site = (int)(i - chain * V);
-    const Philox4 p = philox_site(seed, chain0 + chain, sweep, (uint32_t)site, STREAM_VILLAIN_NEIGHBORHOOD);
-    const VillainDraw d = villain_draw_from_bits(p, interval_phi, interval_n);
-    u[i] = d.u;
+    const int x0 = site / N, x1 = site - x0 * N;
+    const uint32_t c0 = villain_pair_counter(x0, x1, N), half = villain_pair_half(x0);
+    const Philox4 p = philox_site(seed, chain0 + chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD);
+    const VillainDraw d = villain_draw_from_words(half ? p.z : p.x, half ? p.w : p.y, interval_phi, interval_n);
+    u[i] = villain_refined_uniform(d.f, c0, half, seed, chain0 + chain, sweep);
     dphi[i] = d.dphi;
     for (int k = 0; k < 4; ++k) dn[(chain * 4 + k) * V + site] = W * d.dg[k];
 }
@@ -1330,6 +1397,14 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
     return 0;
 }
 
+#include "svb_villain_filtered.cuh"
+
+#ifndef SVB_FILT_MINB32
+#define SVB_FILT_MINB32 6
+#endif
+#ifndef SVB_FILT_STAGES
+#define SVB_FILT_STAGES 1
+#endif
 #ifndef SVB_RESID_STAGES
 #define SVB_RESID_STAGES 1
 #endif
@@ -1340,6 +1415,17 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
+#ifndef SVB_NO_FILTERED_KERNEL
+    if (!INJECTED && !STRICT && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out) {
+        // production path: fp32-filtered decisions on resident fp32 residuals (svb_villain_filtered.cuh)
+        switch (a.N) {
+            case 16: return launch_villain_filtered<16, 16, 2>(a, stream, info);
+            case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, stream, info);
+            case 64: return launch_villain_filtered<64, 2, 1>(a, stream, info);
+            default: break;
+        }
+    }
+#endif
     if (!INJECTED && aligned && sizeof(real) == 8) {
         // One sweep per launch in FAST arithmetic: recomputing the residuals is as cheap as building the resident copy,
         // and the two-stage pipeline hides the loads (52.0 vs 53.5 us at config 2).  Fused sweeps, and STRICT
