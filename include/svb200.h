@@ -142,6 +142,34 @@ int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
                             double* obs, uint8_t* accept_mask, double* dS_out, void* stream);
 
 /*
+ * The same sweeps as OVERLAPPED launches: a launch may begin while the previous launch in the stream is still running
+ * (programmatic dependent launch), so the ramp-up of one sweep hides under the tail of the one before -- at config 2 a
+ * quarter of a non-overlapped step.  Data dependencies are tracked per chain instead of per kernel:
+ *
+ *  epochs         (chains,) u32 device scratch owned by the caller, one word per chain of THIS chain set.  A launch loads
+ *                 chain c only once epochs[c] == wait_epoch, and sets epochs[c] = signal_epoch when its store of chain c
+ *                 and the chain's observable record are complete.  A sequence of steps on one chain set therefore passes
+ *                 (wait, signal) = (e, e + 1), (e + 1, e + 2), ...
+ *  flags          0: the launch first waits for ALL earlier work in the stream (griddepcontrol.wait) and ignores
+ *                 wait_epoch -- use it for the first launch of a sequence, whose inputs were produced by anything else.
+ *                 SVB_OVERLAP_PREDECESSOR: the caller vouches that everything this launch reads was written either
+ *                 before the last launch that passed flags = 0 on this stream, or by overlapped launches (whose chains
+ *                 the epochs order).  Only then does the launch skip the grid-wide wait and overlap its predecessor.
+ *                 Launches on different chain sets may be interleaved freely; each set has its own epochs.
+ *  obs            optional (chains, SVB_VOBS_COUNT); give consecutive launches DIFFERENT records (e.g. rows of a
+ *                 (steps, chains, SVB_VOBS_COUNT) column) if they may overlap.
+ * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64}; anything else returns SVB_E_UNSUPPORTED (use
+ * svb_villain_sweep).  A kernel launched normally after these waits for all of them, as usual.
+ */
+#define SVB_OVERLAP_PREDECESSOR 1
+int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N,
+                                 double kappa, const double* kappa_chain, int W,
+                                 double interval_phi, int interval_n,
+                                 int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                                 double* obs, uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch,
+                                 int flags, void* stream);
+
+/*
  * The same sweep with HOST buffers: the reference's `step(cfg)` contract (host arrays in, host arrays out,
  * neighborhood.py:59-137) for a whole batch.  phi_host / n_host / obs_host are pinned HOST buffers updated in place;
  * phi_dev / n_dev / obs_dev are caller-owned DEVICE staging buffers of the same shapes.  The chains are processed in

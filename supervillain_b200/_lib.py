@@ -19,6 +19,7 @@ VOBS_ACTION, VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1, VOBS_ACCEPTED, VOBS_ACCEPTANC
 WL_JOINT, WL_VORTEX, WL_COEXACT = 0, 1, 2
 OP_D, OP_DELTA, OP_FACE_SUM, OP_COFACE_SUM = 0, 1, 2, 3
 CORR_SPIN, CORR_WINDING, CORR_VORTEX = 0, 1, 2
+OVERLAP_PREDECESSOR = 1
 
 E_NULL, E_SHAPE, E_DTYPE, E_PARAM, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4, -5, -6
 
@@ -29,6 +30,8 @@ SIGNATURES = {
     'svb_last_error': (ctypes.c_char_p, []),
     'svb_villain_sweep': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'svb_villain_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp,
+                                          ctypes.c_uint32, ctypes.c_uint32, _i, _vp]),
     'svb_villain_observables': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),

@@ -59,6 +59,10 @@ struct VillainArgs {
     double* obs;
     uint8_t* accept_mask;
     double* dS_out;
+    // overlapped launches (svb_villain_sweep_overlapped); epochs == nullptr otherwise
+    uint32_t* epochs;
+    uint32_t wait_epoch, signal_epoch;
+    int grid_wait;
 };
 
 // exact int32 -> double on the fp64 add pipe: (2^52 + 2^31 + n) - (2^52 + 2^31)
@@ -1332,12 +1336,25 @@ static int villain_threads_for(int N) {
 struct DeviceInfo {
     int sm_count;
     int max_smem_optin;
+    int device;
 };
 static int get_device_info(DeviceInfo& info) {
+    // device attributes never change: cached per device (launch-bound loops call this every step)
+    static DeviceInfo cache[64];
+    static bool have[64];
     int dev = 0;
     SVB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && have[dev]) {
+        info = cache[dev];
+        return 0;
+    }
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev));
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    info.device = dev;
+    if (dev >= 0 && dev < 64) {
+        cache[dev] = info;
+        have[dev] = true;
+    }
     return 0;
 }
 
@@ -1553,9 +1570,48 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
     }
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
+    a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (phi_dtype == SVB_F64) return dispatch_villain<double>(a, rng_mode, arith_mode, path, st);
     return dispatch_villain<float>(a, rng_mode, arith_mode, path, st);
+}
+
+extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                            int W, double interval_phi, int interval_n, int n_sweeps, uint64_t seed,
+                                            uint64_t sweep0, uint64_t chain0, double* obs, uint32_t* epochs,
+                                            uint32_t wait_epoch, uint32_t signal_epoch, int flags, void* stream) {
+    if (!phi || !n || !epochs) return fail(SVB_E_NULL, "svb_villain_sweep_overlapped: phi, n and epochs are required");
+    if (chains < 0) return fail(SVB_E_SHAPE, "svb_villain_sweep_overlapped: chains=%lld", (long long)chains);
+    if (N != 16 && N != 32 && N != 64) return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_overlapped: N must be 16, 32 or 64 (got %d)", N);
+    if (((uintptr_t)phi % 16) || ((uintptr_t)n % 16)) return fail(SVB_E_ALIGN, "svb_villain_sweep_overlapped: fields must be 16-byte aligned");
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: kappa must be positive");
+    if (W < 1) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: W must be a finite integer >= 1 (got %d)", W);
+    if (interval_n < 0 || interval_n > 31) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: interval_n must be in [0, 31]");
+    if (!(interval_phi >= 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: interval_phi must be >= 0");
+    if (n_sweeps < 1) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: n_sweeps must be >= 1 (every launch signals its epoch)");
+    if (flags & ~SVB_OVERLAP_PREDECESSOR) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: flags");
+    if (chains == 0) return SVB_OK;
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
+    a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
+    a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.epochs = epochs; a.wait_epoch = wait_epoch; a.signal_epoch = signal_epoch;
+    a.grid_wait = (flags & SVB_OVERLAP_PREDECESSOR) ? 0 : 1;
+    DeviceInfo info;
+    int rc = get_device_info(info);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (N) {
+        case 16: return launch_villain_filtered<16, 16, 2>(a, st, info);
+        case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
+        default: return launch_villain_filtered<64, 2, 1>(a, st, info);
+    }
 }
 
 extern "C" int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n, int64_t chains, int N, double kappa,
@@ -1650,6 +1706,7 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     }
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // An even number of ping-pong sweeps ends in (phi, n).  An odd count would end in the workspace, so the last sweep of
     // an odd count is done in place by the per-colour global path instead (cheaper than copying the state back).

@@ -20,19 +20,21 @@
 #pragma once
 // (included inside namespace svb)
 
-// Band of the fp32 decision.  With D = interval_phi + 2 pi W interval_n >= |dr|, R = max |r| over the four links,
-// eps = 2^-24 and
-//   |dphi32 - dphi| <= 2 I 2^-24 (23 leading bits, centred) + rounding      -> |delta dr| <= 1.0e-6 (1 + D/10)
-//   |r32 - r| <= eps |r| + 1.2e-6 (one fp32 patch by an accepted neighbour of the other colour)
-// the error of one term dr (2 r + dr) is bounded by (|2r + dr| + |dr|) delta_dr + |dr| (2 delta_r) + 3 eps |dr||2r + dr|,
-// and four terms plus their accumulation give
-//   |dS32 - dS| <= (kappa/2) (bA R + bB),   bA = 8e-6 + 3.9e-6 D,   bB = 1.8e-5 D + 1.7e-6 D^2
-// (constants rounded up).  The kernel uses twice that, plus 2e-5 + 4e-6 L for the logarithm (MUFU.LG2: < 1e-6 (1 + L))
-// and for the bracket of u (relative half-width <= 2^-17 once f >= 2^16; smaller f always take the exact path).
+// Band of the fp32 decision (everything in units of ln 2 inside the kernel; natural units here).  With
+// D = interval_phi + 2 pi W interval_n >= |dr|, R = max |r| over the four links and eps = 2^-24, worst cases:
+//   delta_dr <= 2.9e-7 D    dphi32 from 23 centred bits (I 2^-23) + fp32 constants (2 pi, I) + the roundings of
+//                           c I_n -+ dphi and of the fused multiply-add
+//   delta_r  <= 3 eps R + delta_dr     rounding of r to fp32 + at most one fp32 patch by an accepted neighbour
+//   one term dr (2r + dr):  (|2r + dr| + |dr|) delta_dr + 2 |dr| delta_r + 4 eps |dr| |2r + dr|
+//   four terms, their accumulation and the final multiply:
+//       |dS32 - dS| <= (kappa/2) (7.6e-6 D R + 6.6e-6 D^2)
+// The kernel uses bA = 1.0e-5 D and bB = 9.0e-6 D^2 (1.3 x the worst case; typical errors are ~30 x smaller).  On the
+// other side, -log2 u is known to 2.2e-5 (bracket [f, f + 1] 2^-32 once f >= 2^16; smaller f always take the exact path)
+// + 2.4e-7 (1 + |lg2|) (MUFU.LG2) + 2e-6 (roundings): the kernel allows 3.7e-5 + 4e-6 L.
 struct FilterConsts {
     float I, two_I;          // interval_phi, 2 interval_phi
     float c;                 // 2 pi W
-    float bA, bB;            // band coefficients (already doubled)
+    float bA, bB;            // band coefficients
     float g_bias;            // 12582912 + interval_n: subtracting it from the planted digit gives dg as a float
 };
 
@@ -42,8 +44,8 @@ static FilterConsts make_filter_consts(double interval_phi, int W, int interval_
     fc.I = (float)interval_phi;
     fc.two_I = (float)(2.0 * interval_phi);
     fc.c = (float)(SVB_TWO_PI * W);
-    fc.bA = (float)(2.0 * (8e-6 + 3.9e-6 * D));
-    fc.bB = (float)(2.0 * (1.8e-5 * D + 1.7e-6 * D * D));
+    fc.bA = (float)(1.0e-5 * D);
+    fc.bB = (float)(9.0e-6 * D * D);
     fc.g_bias = 12582912.0f + (float)interval_n;
     return fc;
 }
@@ -78,63 +80,131 @@ __device__ __noinline__ bool villain_exact_decision(const ExactProposal& p) {
     return villain_decide_lazy(exp_clipped(-dS), p.d, p.rc);
 }
 
-// fp64 residuals of the forward links of the sites (x0, 2k) and (x0, 2k + 1); jj = x0 N/2 + k.
-template <int N>
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#ifdef SVB_FILT_CVT_I2F
+#define SVB_FILT_CVT(n) ((double)(n))
+#else
+#define SVB_FILT_CVT(n) int_to_double(n)
+#endif
+
+// fp64 residuals of the forward links of the sites (x0, 2k) and (x0, 2k + 1) and the integers they were built from.
 struct PairResiduals {
     double r0e, r0o, r1e, r1o;
     int2 a0, a1;
 };
-template <int N>
-__device__ __forceinline__ PairResiduals<N> villain_pair_residuals(const double* __restrict__ sphi, const int32_t* __restrict__ sn0,
-                                                                    const int32_t* __restrict__ sn1, int jj) {
-    constexpr int HN = N / 2;
-    const int i = 2 * jj;
-    const int x0 = jj / HN, x1 = 2 * (jj - x0 * HN);
-    const int iup = ((x0 + 1) & (N - 1)) * N + x1;
-    const double2 pc = *reinterpret_cast<const double2*>(sphi + i);
-    const double2 pu = *reinterpret_cast<const double2*>(sphi + iup);
-    const double pr = sphi[x0 * N + ((x1 + 2) & (N - 1))];
-    PairResiduals<N> o;
-    o.a0 = *reinterpret_cast<const int2*>(sn0 + i);
-    o.a1 = *reinterpret_cast<const int2*>(sn1 + i);
-    o.r0e = fma(-SVB_TWO_PI, int_to_double(o.a0.x), pu.x - pc.x);
-    o.r0o = fma(-SVB_TWO_PI, int_to_double(o.a0.y), pu.y - pc.y);
-    o.r1e = fma(-SVB_TWO_PI, int_to_double(o.a1.x), pc.y - pc.x);
-    o.r1o = fma(-SVB_TWO_PI, int_to_double(o.a1.y), pr - pc.y);
+// p_c: phi at (x0, 2k); p_u: phi at (x0 + 1, 2k); p_r: phi at (x0, 2k + 2); n0c / n1c: n at (x0, 2k)
+__device__ __forceinline__ PairResiduals villain_pair_residuals(const double* p_c, const double* p_u, const double* p_r,
+                                                                 const int32_t* n0c, const int32_t* n1c) {
+    const double2 pc = *reinterpret_cast<const double2*>(p_c);
+    const double2 pu = *reinterpret_cast<const double2*>(p_u);
+    const double pr = *p_r;
+    PairResiduals o;
+    o.a0 = *reinterpret_cast<const int2*>(n0c);
+    o.a1 = *reinterpret_cast<const int2*>(n1c);
+    o.r0e = fma(-SVB_TWO_PI, SVB_FILT_CVT(o.a0.x), pu.x - pc.x);
+    o.r0o = fma(-SVB_TWO_PI, SVB_FILT_CVT(o.a0.y), pu.y - pc.y);
+    o.r1e = fma(-SVB_TWO_PI, SVB_FILT_CVT(o.a1.x), pc.y - pc.x);
+    o.r1o = fma(-SVB_TWO_PI, SVB_FILT_CVT(o.a1.y), pr - pc.y);
     return o;
 }
 
-template <int NT, int MINB, int STAGES>
+// OVERLAP: the launch takes part in the overlapped-launch protocol of svb_villain_sweep_overlapped -- it may begin
+// while its predecessor in the stream is still running (programmatic dependent launch), and every chain is ordered
+// individually through `a.epochs`: a chain is loaded only once its epoch reads a.wait_epoch (written by the launch that
+// last stored it), and a CTA sets the epochs of its chains to a.signal_epoch once all its stores and records are complete.
+template <int NT, int MINB, int STAGES, bool OVERLAP>
 __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                              const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT;
+    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
     constexpr int PER = VH / T;                                  // sites per thread per colour (rows x0 + 8 q)
     static_assert(PER >= 2 && PER % 2 == 0, "villain_smem_filtered_kernel: unsupported geometry");
     constexpr uint32_t bytes_phi = V * sizeof(double);
     constexpr uint32_t bytes_n = 2 * V * sizeof(int32_t);
     constexpr uint32_t stage_bytes = bytes_phi + bytes_n;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* rc0 = reinterpret_cast<float*>(smem_raw + STAGES * stage_bytes);      // [colour][VH]: residual of link (0, x)
     float* rc1 = rc0 + V;                                                         // [colour][VH]: residual of link (1, x)
-    double* scratch = reinterpret_cast<double*>(rc1 + V);                         // 6 * 32 doubles
-    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + 6 * 32);
+    double* red = reinterpret_cast<double*>(rc1 + V);                             // [NW][6] per-warp partial sums
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 6 * 32);
+    unsigned* arrivals = reinterpret_cast<unsigned*>(bar + 2);
 
     if (tid == 0) {
         for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
+        *arrivals = 0;
         fence_mbar_init();
+    }
+    if (OVERLAP) {
+        // let the next launch in the stream start as soon as every CTA of this one is resident ...
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // ... and, unless the caller vouches for the predecessor, wait for everything before this launch
+        if (a.grid_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     __syncthreads();
     const bool want_obs = a.obs != nullptr;
     const uint32_t K = (uint32_t)(2 * a.interval_n + 1);
-    const int W = a.W, interval_n = a.interval_n;
+    const int W = a.W, mWI = -a.W * a.interval_n;
+    const float cIn = fc.c * (float)a.interval_n;
 
     // per-thread geometry: rows row8 + 8 q of the compact column k
     const int row8 = tid / HN, k = tid - row8 * HN;
     const int cc = row8 & 1;                                      // colour of the even-column site of this thread's pairs
     const int wrap0 = (row8 == 0) ? VH : 0;                       // backward-0 neighbour of row 0 is row N - 1
+    const int up_off = (row8 == 7) ? (N - V) : N;                 // row below the LAST of this thread's rows wraps to row 0
 
-    auto issue_load = [&](long long chain, int b) {
+    // The epochs of ALL of this CTA's chains are released together when the CTA is done: one gpu-scope release fence
+    // (a memory barrier that costs ~0.7 us on a busy SM -- per chain it would eat most of what overlapping wins)
+    // followed by one relaxed store per chain.  Call behind a block barrier before which thread 0 -- the thread whose
+    // bulk stores they were -- has seen the stores complete and the last warp has written the records.
+    auto publish_all = [&](int count) {
+#ifdef SVB_OV_NOPUB
+        return;
+#endif
+        if (OVERLAP) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (int i = lane; i < count; i += 32)
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.epochs + blockIdx.x + (long long)i * gridDim.x),
+                             "r"(a.signal_epoch)
+                             : "memory");
+        }
+    };
+    // `seen`: a value of the chain's epoch read earlier (peek_epoch), so that the common case -- the producer finished
+    // long ago -- costs no round trip to L2 at the point where the load is issued
+    auto peek_epoch = [&](long long chain) -> uint32_t {
+        uint32_t e = a.wait_epoch;
+#ifdef SVB_OV_NOWAIT
+        return e;
+#endif
+        if (OVERLAP && !a.grid_wait)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.epochs + chain) : "memory");
+        return e;
+    };
+    auto issue_load = [&](long long chain, int b, uint32_t seen) {
+        if (OVERLAP && !a.grid_wait) {
+            uint32_t e = seen;
+            unsigned ns = 32, naps = 0;
+            while (true) {
+                if (e == a.wait_epoch) break;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.epochs + chain) : "memory");
+                if (e == a.wait_epoch) break;
+                __nanosleep(ns);
+                if (ns < 1024) ns *= 2;
+                // a producer that never comes is a caller error (wrong epochs): fail the launch instead of hanging the GPU
+                if (++naps > (1u << 21)) __trap();          // > 2 s
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
         mbar_expect_tx(&bar[b], stage_bytes);
         bulk_g2s(stage, reinterpret_cast<const double*>(a.phi) + chain * V, bytes_phi, &bar[b]);
@@ -142,9 +212,10 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     };
 
     long long chain = blockIdx.x;
-    if (tid == 0 && chain < a.chains) issue_load(chain, 0);
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0, peek_epoch(chain));
 
-    for (int it = 0; chain < a.chains; chain += gridDim.x, ++it) {
+    int it = 0;
+    for (; chain < a.chains; chain += gridDim.x, ++it) {
         const int b = (STAGES == 2) ? (it & 1) : 0;
         unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
         double* sphi = reinterpret_cast<double*>(stage);
@@ -153,8 +224,13 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         const long long next = chain + gridDim.x;
         const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
         const double half_kappa = kappa / 2;
-        const float hk = (float)half_kappa;
-        const float hkA = 1.0001f * hk * fc.bA, hkB = 1.0001f * hk * fc.bB + 2e-5f;
+        const float hk2 = (float)(half_kappa * 1.4426950408889634);                 // decisions are taken in units of ln 2
+        const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+        // pair pointers: phi / n at (row8, 2k); rows advance by 8 N per q
+        const double* pp = sphi + row8 * N + 2 * k;
+        const double* pp_r = sphi + row8 * N + ((2 * k + 2) & (N - 1));
+        const int32_t* pn0 = sn0 + row8 * N + 2 * k;
+        const int32_t* pn1 = sn1 + row8 * N + 2 * k;
 
         mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
 
@@ -163,14 +239,21 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         for (int s = 0; s < a.n_sweeps; ++s) {
             float sum_A = 0.0f;
             // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) in fp64, stored rounded to fp32 ----
+            {
+                float* w0e = rc0 + cc * VH + tid;
+                float* w1e = rc1 + cc * VH + tid;
+                float* w0o = rc0 + (cc ^ 1) * VH + tid;
+                float* w1o = rc1 + (cc ^ 1) * VH + tid;
 #pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int jj = tid + T * q;
-                const PairResiduals<N> pr = villain_pair_residuals<N>(sphi, sn0, sn1, jj);
-                rc0[cc * VH + jj] = (float)pr.r0e;
-                rc1[cc * VH + jj] = (float)pr.r1e;
-                rc0[(cc ^ 1) * VH + jj] = (float)pr.r0o;
-                rc1[(cc ^ 1) * VH + jj] = (float)pr.r1o;
+                for (int q = 0; q < PER; ++q) {
+                    const int o = 8 * N * q;
+                    const PairResiduals pr = villain_pair_residuals(pp + o, pp + o + ((q == PER - 1) ? up_off : N), pp_r + o,
+                                                                    pn0 + o, pn1 + o);
+                    w0e[T * q] = (float)pr.r0e;
+                    w1e[T * q] = (float)pr.r1e;
+                    w0o[T * q] = (float)pr.r0o;
+                    w1o[T * q] = (float)pr.r1o;
+                }
             }
             __syncthreads();
 
@@ -179,12 +262,20 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
             for (int c = 0; c < 2; ++c) {
                 const int par = (row8 + c) & 1;                    // column parity of this thread's sites of colour c
                 const int x1 = 2 * k + par;
-                float* R0own = rc0 + c * VH;
-                float* R1own = rc1 + c * VH;
-                float* R0oth = rc0 + (c ^ 1) * VH;
-                float* R1oth = rc1 + (c ^ 1) * VH;
                 const int ob1 = par ? 0 : ((k == 0) ? (1 - HN) : 1);          // compact index of x - e1 is j - ob1
                 const int wrap1 = (x1 == 0) ? N : 0;
+                // q-independent bases; per q the offsets are compile-time immediates
+                float* R0own = rc0 + c * VH + tid;
+                float* R1own = rc1 + c * VH + tid;
+                float* R0b = rc0 + (c ^ 1) * VH + tid - HN;        // backward link (0, x - e0): row above, same compact column
+                float* R0b_q0 = R0b + wrap0;
+                float* R1b = rc1 + (c ^ 1) * VH + tid - ob1;       // backward link (1, x - e1)
+                double* Pc = sphi + 2 * tid + par;
+                int32_t* N0c = sn0 + 2 * tid + par;
+                int32_t* N1c = sn1 + 2 * tid + par;
+                int32_t* N0b = N0c - N;
+                int32_t* N0b_q0 = N0b + 2 * wrap0;
+                int32_t* N1b = N1c - 1 + wrap1;
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p) {
                     const uint32_t c0 = (uint32_t)((row8 + 16 * p) * N + x1);                 // villain_pair_counter
@@ -192,9 +283,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int q = 2 * p + h;
-                        const int j = tid + T * q;
-                        const int jb0 = j - HN + ((q == 0) ? wrap0 : 0);
-                        const int jb1 = j - ob1;
+                        float* r0b = (q == 0) ? R0b_q0 : R0b;
+                        int32_t* n0b = (q == 0) ? N0b_q0 : N0b;
                         const uint32_t wA = h ? bits.z : bits.x, wB = h ? bits.w : bits.y;
                         // proposal: four base-K digits, then the leading 32 bits of the uniform
                         uint32_t f = wB;
@@ -207,134 +297,179 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                         }
                         const float U = __uint_as_float(0x3F800000u | (wA >> 9)) - 0.99999994f;       // in (0, 1), 23 bits, centred
                         const float dphi = fmaf(fc.two_I, U, -fc.I);
-                        const float g0 = __int_as_float(0x4B400000 + dig[0]) - fc.g_bias;
-                        const float g1 = __int_as_float(0x4B400000 + dig[1]) - fc.g_bias;
-                        const float g2 = __int_as_float(0x4B400000 + dig[2]) - fc.g_bias;
-                        const float g3 = __int_as_float(0x4B400000 + dig[3]) - fc.g_bias;
-                        const float r_f0 = R0own[j], r_f1 = R1own[j], r_b0 = R0oth[jb0], r_b1 = R1oth[jb1];
-                        // dr = d(dphi) - 2 pi dn   (neighborhood.py:110)
-                        const float dr_f0 = fmaf(-fc.c, g0, -dphi), dr_b0 = fmaf(-fc.c, g1, dphi);
-                        const float dr_f1 = fmaf(-fc.c, g2, -dphi), dr_b1 = fmaf(-fc.c, g3, dphi);
+                        const float base_f = cIn - dphi, base_b = cIn + dphi;
+                        const float r_f0 = R0own[T * q], r_f1 = R1own[T * q], r_b0 = r0b[T * q], r_b1 = R1b[T * q];
+                        // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
+                        const float dr_f0 = fmaf(-fc.c, (float)dig[0], base_f), dr_b0 = fmaf(-fc.c, (float)dig[1], base_b);
+                        const float dr_f1 = fmaf(-fc.c, (float)dig[2], base_f), dr_b1 = fmaf(-fc.c, (float)dig[3], base_b);
                         float acc2 = dr_f0 * fmaf(2.0f, r_f0, dr_f0);
                         acc2 = fmaf(dr_b0, fmaf(2.0f, r_b0, dr_b0), acc2);
                         acc2 = fmaf(dr_f1, fmaf(2.0f, r_f1, dr_f1), acc2);
                         acc2 = fmaf(dr_b1, fmaf(2.0f, r_b1, dr_b1), acc2);
-                        const float dS = hk * acc2;
-                        const float L = fmaf(__log2f((float)f + 0.5f), -0.6931471805599453f, 22.18070977791825f);   // -ln((f + 1/2) 2^-32)
+                        const float dS2 = hk2 * acc2;                                   // dS / ln 2
+                        const float L2 = 32.0f - fast_lg2((float)f);                    // -log2(f 2^-32); u lies in [f, f + 1] 2^-32
                         const float Rmax = fmaxf(fmaxf(fabsf(r_f0), fabsf(r_b0)), fmaxf(fabsf(r_f1), fabsf(r_b1)));
-                        const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L, hkB));
-                        const float diff = dS - L;
+                        const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L2, hkB));
+                        const float diff = dS2 - L2;
                         bool ok = diff < 0.0f;
-                        sum_A += fminf(exp2f(-1.4426950408889634f * dS), 1.0f);
-                        const int i_c = 2 * j + par;
-                        const int i_b0 = i_c - N + ((q == 0) ? 2 * wrap0 : 0);
-                        const int i_b1 = i_c - 1 + wrap1;
+                        sum_A += fminf(fast_ex2(-dS2), 1.0f);
                         if (!(fabsf(diff) > band) || f < 65536u) {
                             ExactProposal ep;
                             ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1;
                             const int x0 = row8 + 8 * q;
-                            ep.i_c = i_c; ep.i_b0 = i_b0; ep.i_b1 = i_b1;
+                            ep.i_c = x0 * N + x1;
+                            ep.i_b0 = ((x0 - 1) & (N - 1)) * N + x1;
+                            ep.i_b1 = x0 * N + ((x1 - 1) & (N - 1));
                             ep.i_f0 = ((x0 + 1) & (N - 1)) * N + x1;
                             ep.i_f1 = x0 * N + ((x1 + 1) & (N - 1));
                             ep.half_kappa = half_kappa;
                             ep.c = SVB_TWO_PI * (double)W;
                             ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - a.interval_n;
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
                             ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
                             ok = villain_exact_decision(ep);
                         }
                         if (ok) {                                               // (:121-129)
-                            sphi[i_c] = __dadd_rn(sphi[i_c], villain_dphi_from_word(wA, a.interval_phi));
-                            sn0[i_c] += W * (dig[0] - interval_n);
-                            sn0[i_b0] += W * (dig[1] - interval_n);
-                            sn1[i_c] += W * (dig[2] - interval_n);
-                            sn1[i_b1] += W * (dig[3] - interval_n);
-                            R0own[j] = r_f0 + dr_f0;
-                            R0oth[jb0] = r_b0 + dr_b0;
-                            R1own[j] = r_f1 + dr_f1;
-                            R1oth[jb1] = r_b1 + dr_b1;
+                            Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], villain_dphi_from_word(wA, a.interval_phi));
+                            atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);      // only this thread touches these links in this pass
+                            atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
+                            atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
+                            atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
+                            R0own[T * q] = r_f0 + dr_f0;
+                            r0b[T * q] = r_b0 + dr_b0;
+                            R1own[T * q] = r_f1 + dr_f1;
+                            R1b[T * q] = r_b1 + dr_b1;
                             ++n_acc;
                         }
                     }
                 }
+                if (s == a.n_sweeps - 1 && c == 1) fence_proxy_async();      // this thread's phi / n writes -> visible to the bulk store
+                uint32_t seen = 0;
+                if (STAGES == 2 && s == 0 && c == 0 && tid == 0) {
+                    if (next < a.chains) seen = peek_epoch(next);
+                    bulk_wait_read0();                                      // the previous chain's store (issued a pass ago)
+                }
                 __syncthreads();
-                if (STAGES == 2 && s == 0 && c == 0 && tid == 0 && next < a.chains) {
-                    bulk_wait_read0();
-                    issue_load(next, b ^ 1);
+                if (STAGES == 2 && s == 0 && c == 0) {
+                    // every warp is past the previous chain's observable pass; its store has completed
+                    if (tid == 0 && next < a.chains) issue_load(next, b ^ 1, seen);
                 }
             }
             sum_A_all += (double)sum_A;
         }
 
-        if (want_obs) {
-            // one fp64 pass over site pairs: sum r^2, sum n, sum (dn)^2 of the final state
-            ChainSums cs;
-            cs.sumA = sum_A_all; cs.accepted = n_acc; cs.action = 0.0; cs.w0 = 0; cs.w1 = 0;
-            long long dn2 = 0;
-#pragma unroll
-            for (int q = 0; q < PER; ++q) {
-                const int jj = tid + T * q;
-                const PairResiduals<N> pr = villain_pair_residuals<N>(sphi, sn0, sn1, jj);
-                cs.action = fma(pr.r0e, pr.r0e, cs.action);
-                cs.action = fma(pr.r0o, pr.r0o, cs.action);
-                cs.action = fma(pr.r1e, pr.r1e, cs.action);
-                cs.action = fma(pr.r1o, pr.r1o, cs.action);
-                const int x0 = row8 + 8 * q;
-                const int iup = ((x0 + 1) & (N - 1)) * N + 2 * k;
-                const int hr = sn0[x0 * N + ((2 * k + 2) & (N - 1))];                // n0[x + 2 e1]
-                const int2 up = *reinterpret_cast<const int2*>(sn1 + iup);           // n1[x + e0]
-                // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
-                const int d0 = (up.x - pr.a1.x) - (pr.a0.y - pr.a0.x), d1 = (up.y - pr.a1.y) - (hr - pr.a0.y);
-                dn2 += (long long)d0 * d0 + (long long)d1 * d1;
-                cs.w0 += pr.a0.x + pr.a0.y;
-                cs.w1 += pr.a1.x + pr.a1.y;
-            }
-            cs.dn2 = dn2;
-            cs = block_reduce_chain(cs, scratch);
-            if (tid == 0) {
-                double* o = a.obs + chain * SVB_VOBS_COUNT;
-                o[SVB_VOBS_ACTION] = (kappa / 2) * cs.action;
-                o[SVB_VOBS_SUM_DN2] = (double)cs.dn2;
-                o[SVB_VOBS_WRAP0] = (double)cs.w0;
-                o[SVB_VOBS_WRAP1] = (double)cs.w1;
-                o[SVB_VOBS_ACCEPTED] = (double)cs.accepted;
-                o[SVB_VOBS_ACCEPTANCE] = cs.sumA;
-            }
-        }
-
-        fence_proxy_async();
-        __syncthreads();
+        // ---- store the chain (nothing below writes phi or n) ----
+        uint32_t seen_next = 0;
         if (tid == 0) {
             bulk_s2g(reinterpret_cast<double*>(a.phi) + chain * V, sphi, bytes_phi);
             bulk_s2g(a.n + chain * 2 * V, sn0, bytes_n);
             bulk_commit();
-            if (STAGES == 1) {
-                bulk_wait_read0();
-                if (next < a.chains) issue_load(next, 0);
+            if (STAGES == 1 && next < a.chains) seen_next = peek_epoch(next);     // lands during the observable pass
+        }
+
+        if (want_obs) {
+            // one fp64 pass over site pairs: sum r^2, sum n, sum (dn)^2 of the final state
+            double action = 0.0;
+            int w0 = 0, w1 = 0;
+            long long dn2 = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int o = 8 * N * q;
+                const int uo = (q == PER - 1) ? up_off : N;
+                const PairResiduals pr = villain_pair_residuals(pp + o, pp + o + uo, pp_r + o, pn0 + o, pn1 + o);
+                action = fma(pr.r0e, pr.r0e, action);
+                action = fma(pr.r0o, pr.r0o, action);
+                action = fma(pr.r1e, pr.r1e, action);
+                action = fma(pr.r1o, pr.r1o, action);
+                const int hr = sn0[(row8 + 8 * q) * N + ((2 * k + 2) & (N - 1))];            // n0[x + 2 e1]
+                const int2 up = *reinterpret_cast<const int2*>(pn1 + o + uo);                 // n1[x + e0]
+                // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+                const int d0 = (up.x - pr.a1.x) - (pr.a0.y - pr.a0.x), d1 = (up.y - pr.a1.y) - (hr - pr.a0.y);
+                dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+                w0 += pr.a0.x + pr.a0.y;
+                w1 += pr.a1.x + pr.a1.y;
+            }
+            // warp partials -> shared slots; the last warp to arrive adds them in warp order (deterministic) and writes
+            // the record.  No block barrier: the next use of the slots is behind the next chain's first barrier.
+            action = warp_sum(action);
+            sum_A_all = warp_sum(sum_A_all);
+            const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(dn2 & 0xFFFFFF));
+            const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)((unsigned long long)dn2 >> 24));
+            w0 = __reduce_add_sync(0xffffffffu, w0);
+            w1 = __reduce_add_sync(0xffffffffu, w1);
+            n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+            if (lane == 0) {
+                double* slot = red + 6 * warp;
+                slot[0] = action; slot[1] = sum_A_all;
+                slot[2] = (double)((long long)lo + ((long long)hi << 24));
+                slot[3] = (double)w0; slot[4] = (double)w1; slot[5] = (double)n_acc;
+                __threadfence_block();
+                if (atomicAdd(arrivals, 1u) == NW - 1) {
+                    __threadfence_block();
+                    double t[6] = {0, 0, 0, 0, 0, 0};
+                    for (int w = 0; w < NW; ++w)
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) t[i] += red[6 * w + i];
+                    double* o = a.obs + chain * SVB_VOBS_COUNT;
+                    o[SVB_VOBS_ACTION] = (kappa / 2) * t[0];
+                    o[SVB_VOBS_SUM_DN2] = t[2];
+                    o[SVB_VOBS_WRAP0] = t[3];
+                    o[SVB_VOBS_WRAP1] = t[4];
+                    o[SVB_VOBS_ACCEPTED] = t[5];
+                    o[SVB_VOBS_ACCEPTANCE] = t[1];
+                    *arrivals = 0;
+                }
             }
         }
-        if (STAGES == 1) __syncthreads();
+        if (STAGES == 1) {
+            __syncthreads();           // every warp has read the final state before the buffer is refilled
+            if (tid == 0) {
+                bulk_wait_read0();
+                if (next < a.chains) issue_load(next, 0, seen_next);
+            }
+        }
     }
     if (tid == 0) bulk_wait0();
+    if (OVERLAP) {
+        __syncthreads();                                   // every store has completed, every record is written
+        if (warp == 0) publish_all(it);
+    }
 }
 
 template <int NT, int MINB, int STAGES>
 static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
-    auto kern = villain_smem_filtered_kernel<NT, MINB, STAGES>;
+    const bool overlap = a.epochs != nullptr;
+    auto kern = overlap ? villain_smem_filtered_kernel<NT, MINB, STAGES, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, false>;
     const size_t V = (size_t)NT * NT;
-    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * 32 * sizeof(double) + 16;
-    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
-    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "filtered villain kernel does not fit an SM at N=%d", NT);
+    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * 32 * sizeof(double) + 32;
+    // kernel attributes and occupancy are set / queried once per (instantiation, device)
+    static int per_sm_cache[2][64];
+    int per_sm = (info.device < 64) ? per_sm_cache[overlap ? 1 : 0][info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "filtered villain kernel does not fit an SM at N=%d", NT);
+        if (info.device < 64) per_sm_cache[overlap ? 1 : 0][info.device] = per_sm;
+    }
     long long grid = (long long)per_sm * info.sm_count;
     if (grid > a.chains) grid = a.chains;
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    if (overlap) {
+        // programmatic dependent launch: this grid may start once every CTA of the previous kernel in the stream has
+        // executed griddepcontrol.launch_dependents (or exited); the per-chain epochs order the data
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, fc));
+        return 0;
+    }
     kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a, fc);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
-

@@ -173,10 +173,19 @@ class BatchedEnsemble:
         record = torch.empty((steps, self.chains, nobs), dtype=torch.float64, device=self.device)
         kept = []
         a, b = self.fields
+        overlapped = None
+        if hasattr(generator, 'overlapped_device'):
+            try:          # launches that overlap their predecessor; each step writes its own row of the record
+                overlapped = generator.overlapped_device(a, b, chain0=self.chain0, kappa_chain=kappa_chain)
+            except NotImplementedError:
+                overlapped = None
         for k in progress(range(steps), desc='Generation'):
-            generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
+            if overlapped is not None:
+                overlapped(sweeps_per_step, obs=record[k])
+            else:
+                generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
             if keep_every and (k + 1) % keep_every == 0:
-                kept.append((a.cpu().numpy(), b.cpu().numpy()))
+                kept.append((a.cpu().numpy(), b.cpu().numpy()))          # reads only: stream order suffices
         self.record = record.cpu().numpy().transpose(1, 0, 2)          # (chains, steps, nobs): ONE D2H
         self.steps = steps
         self.sweeps_per_step = sweeps_per_step

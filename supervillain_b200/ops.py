@@ -135,6 +135,63 @@ def villain_sweep_plan(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1
     return run
 
 
+OVERLAP_SIZES = (16, 32, 64)
+
+
+class VillainOverlappedSweeps:
+    """Back-to-back Philox sweeps of ONE chain set as overlapped launches (svb_villain_sweep_overlapped).
+
+    Each `step` is one kernel launch that may begin while the previous step's launch is still running; chains are
+    ordered individually through a per-chain epoch word, so results are identical to `villain_sweep` call by call.
+    The FIRST step after construction or `fence()` waits for all earlier work in the stream; call `fence()` whenever
+    something other than these steps has written phi, n or kappa_chain (anything that only READS them -- a normal
+    kernel or copy enqueued afterwards -- waits for the overlapped launches by ordinary stream order and needs nothing).
+    Steps of several instances (different chain sets) may be interleaved on one stream.
+    """
+
+    def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None):
+        self.lib = _lib.load()
+        self.chains, self.N = _fields_shape(phi, 'phi', 1)
+        if self.N not in OVERLAP_SIZES or phi.dtype != torch.float64:
+            raise NotImplementedError('overlapped sweeps need fp64 phi and N in (16, 32, 64)')
+        self.p_phi = _dev(phi, 'phi', (torch.float64,))
+        self.p_n = _dev(n, 'n', (torch.int32,), (self.chains, 2, self.N, self.N))
+        if W != W or W == float('inf') or int(W) != W:
+            raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W')
+        self.p_kc = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (self.chains,))
+        self.args = (float(kappa), self.p_kc, int(W), float(interval_phi), int(interval_n))
+        self.seed, self.chain0 = int(seed) & (2**64 - 1), int(chain0)
+        self.epochs = torch.zeros((self.chains,), dtype=torch.int32, device=phi.device)
+        self.p_epochs = self.epochs.data_ptr()
+        self.epoch = 0
+        self.fenced = True
+        self._keep = (phi, n, kappa_chain)
+        self._fn = self.lib.svb_villain_sweep_overlapped
+        self._stream = torch.cuda.current_stream
+        self._last_obs = self._last_p_obs = None
+
+    def fence(self):
+        """The next step waits for everything enqueued before it (use after foreign writes to the fields)."""
+        self.fenced = True
+
+    def step(self, sweep0, n_sweeps=1, obs=None):
+        if obs is None:
+            p_obs = None
+        elif obs is self._last_obs:
+            p_obs = self._last_p_obs               # validated before: tight loops pay nothing per launch
+        else:
+            p_obs = _dev(obs, 'obs', (torch.float64,), (self.chains, VOBS_COUNT))
+            self._last_obs, self._last_p_obs = obs, p_obs
+        e = self.epoch
+        code = self._fn(self.p_phi, self.p_n, self.chains, self.N, *self.args, int(n_sweeps), self.seed, int(sweep0), self.chain0,
+                        p_obs, self.p_epochs, e & 0xFFFFFFFF, (e + 1) & 0xFFFFFFFF, 0 if self.fenced else _lib.OVERLAP_PREDECESSOR,
+                        self._stream().cuda_stream)
+        if code:
+            _lib.check(code)
+        self.epoch = e + 1
+        self.fenced = False
+
+
 def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
     """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
     lib = _lib.load()

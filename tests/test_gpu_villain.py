@@ -321,3 +321,43 @@ def test_tiled_path_equals_oracle_and_global_path(N, chains, sweeps, arith):
     ops.villain_sweep(g_phi, g_n, kappa, n_sweeps=sweeps, seed=seed, sweep0=3, chain0=7, arithmetic=arith, path='global',
                       accept_mask=g_mask)
     assert torch.equal(g_phi, phi) and torch.equal(g_n, n) and torch.equal(g_mask, mask)
+
+
+@pytest.mark.parametrize('N,chains', [(32, 2000), (16, 3000), (64, 300)])
+def test_overlapped_launches_equal_ordinary_launches(N, chains):
+    """svb_villain_sweep_overlapped: K steps whose launches overlap (per-chain epochs order the data) leave exactly the
+    fields and per-step records of K ordinary launches; two chain sets interleaved on one stream stay independent."""
+    kappa, K = 0.5, 7
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    sets = [svb.BatchedEnsemble(S, chains)._start('hot', 5 + r) for r in range(2)]
+    ref = [(phi.clone(), n.clone()) for phi, n in sets]
+    rec_ref = torch.zeros((2, K, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for r, (phi, n) in enumerate(ref):
+        for k in range(K):
+            ops.villain_sweep(phi, n, kappa, seed=11 + r, sweep0=3 * k, n_sweeps=1 + (k % 2), obs=rec_ref[r, k])
+    rec = torch.zeros_like(rec_ref)
+    steppers = [ops.VillainOverlappedSweeps(phi, n, kappa, seed=11 + r) for r, (phi, n) in enumerate(sets)]
+    for k in range(K):
+        for r in range(2):
+            steppers[r].step(3 * k, 1 + (k % 2), obs=rec[r, k])
+    torch.cuda.synchronize()
+    for r in range(2):
+        assert torch.equal(sets[r][0], ref[r][0]) and torch.equal(sets[r][1], ref[r][1])
+    assert torch.equal(rec, rec_ref)
+    # a foreign write between steps needs fence(): the next launch then waits for the whole stream
+    phi, n = sets[0]
+    phi.add_(0.125); ref[0][0].add_(0.125)
+    steppers[0].fence()
+    steppers[0].step(100, 1)
+    steppers[0].step(101, 1)
+    ops.villain_sweep(ref[0][0], ref[0][1], kappa, seed=11, sweep0=100, n_sweeps=2)
+    torch.cuda.synchronize()
+    assert torch.equal(phi, ref[0][0]) and torch.equal(n, ref[0][1])
+    assert int(steppers[0].epochs.min()) == steppers[0].epoch == K + 2
+
+
+def test_overlapped_launches_reject_what_they_do_not_serve():
+    S = svb.Villain(svb.Lattice2D(48), 0.5)
+    phi, n = svb.BatchedEnsemble(S, 4)._start('cold', 0)
+    with pytest.raises(NotImplementedError):
+        ops.VillainOverlappedSweeps(phi, n, 0.5)
