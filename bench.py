@@ -11,7 +11,10 @@ scaling; chains are independent, there is no collective on the hot path; a final
 the observable records runs outside the timed region).
 
 A step is ONE kernel launch.  The chain state (64 MiB) would fit the 126 MB L2, so the timed loop
-rotates over 4 independent chain sets (256 MiB): every step streams its set from HBM.
+rotates over 4 independent chain sets (256 MiB): every step streams its set from HBM.  Steps are
+issued as overlapped launches (svb_villain_sweep_overlapped: programmatic dependent launch with
+per-chain epochs ordering the data), the way BatchedEnsemble.generate issues them, so the ramp-up
+of one launch hides under the tail of the one before; `--no-overlap` times ordinary launches.
 
 One JSON line on stdout; see the task contract for the keys.  `--impl reference` times the CPU
 restatement of the reference's numpy algorithm (oracle/villain_np.py) on all host cores.
@@ -38,6 +41,17 @@ BYTES_PER_SITE_UPDATE = 32          # fp64 phi + 2 x int32 n, one read + one wri
 ROTATE = 4                           # chain sets rotated through so every step comes from HBM, not L2
 THERMALISE = 200                     # untimed sweeps applied to each synthetic hot start before the warm-up
 WORKLOAD = 'config2: Villain (phi,n) L=32 kappa=0.5 W=1, 4096 chains/GPU, NeighborhoodUpdate checkerboard sweep + action/winding/wrapping'
+
+
+def traffic_from_profile(override):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel, from the committed ncu capture."""
+    if override is not None:
+        return override
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    return None
 
 
 def measured_peaks():
@@ -185,14 +199,25 @@ def run_gpu(args):
     for r in range(ROTATE):
         E = svb.BatchedEnsemble(S, CHAINS, chain0=chain0)
         sets.append(E._start('hot', 20260101 + 7919 * (rank * ROTATE + r)))
-    obs = torch.zeros((CHAINS, VOBS_COUNT), dtype=torch.float64, device=dev)
+    obs_sets = [torch.zeros((CHAINS, VOBS_COUNT), dtype=torch.float64, device=dev) for _ in sets]   # one record per set
     for phi, n in sets:                                       # untimed thermalisation of the synthetic hot starts
         G.sweep_device(phi, n, THERMALISE, chain0=chain0)
 
-    plans = [G.plan_device(phi, n, obs=obs, chain0=chain0) for phi, n in sets]    # arguments validated once
+    if args.no_overlap:
+        plans = [G.plan_device(phi, n, obs=o, chain0=chain0) for (phi, n), o in zip(sets, obs_sets)]
 
-    def step(k):
-        plans[k % ROTATE](args.sweeps_per_step)
+        def step(k):
+            plans[k % ROTATE](args.sweeps_per_step)
+    else:
+        # the way BatchedEnsemble.generate steps: launch k writes its counters to record k and completes the state columns
+        # of record k - 1 (the observables of the chains as they arrive ride along with the pass that builds the residuals)
+        steppers = [G.overlapped_device(phi, n, chain0=chain0) for phi, n in sets]
+        prev_sets = [torch.zeros_like(o) for o in obs_sets]
+
+        def step(k):
+            r = k % ROTATE
+            steppers[r](args.sweeps_per_step, obs_sets[r], prev_sets[r])
+            obs_sets[r], prev_sets[r] = prev_sets[r], obs_sets[r]
 
     def barrier():
         if world > 1:
@@ -231,7 +256,8 @@ def run_gpu(args):
     launch_s = (ms * 1e-3) / args.steps
     achieved = BYTES_PER_SITE_UPDATE * CHAINS * L * L * args.sweeps_per_step / launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': args.traffic, 'kernel': 'villain_smem_pipelined_kernel<double, STRICT=false, N=32, T=128>',
+                'traffic': traffic_from_profile(args.traffic), 'kernel': 'villain_smem_filtered_kernel<N=32, 128 threads>',
+                'launches': 'ordinary' if args.no_overlap else 'overlapped (programmatic dependent launch + per-chain epochs)',
                 'algorithmic_bytes_per_launch': BYTES_PER_SITE_UPDATE * CHAINS * L * L,
                 'peak_source': peak_src, 'sweeps_per_launch': args.sweeps_per_step}
 
@@ -255,6 +281,8 @@ def run_gpu(args):
            'steps': e2e_steps, 'api': 'HostStepper.step(phi_host, n_host): pinned host fields in and out + observables'}
 
     # ---- final gather of observables (outside the timed region; the only inter-GPU traffic) ----
+    torch.cuda.synchronize()
+    obs = svb.ops.villain_observables(sets[0][0], sets[0][1], KAPPA)      # final state of set 0
     all_obs = sharding.gather_columns(obs)                    # (world * CHAINS, VOBS_COUNT) on every rank
     mean_action_density = float(all_obs[:, 0].mean().item()) / (L * L)
 
@@ -294,6 +322,7 @@ def main():
     ap.add_argument('--impl', default='svb200', choices=['svb200', 'reference'])
     ap.add_argument('--sweeps-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='ordinary launches instead of overlapped ones')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)')
     args = ap.parse_args()

@@ -158,6 +158,13 @@ int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
  *                 Launches on different chain sets may be interleaved freely; each set has its own epochs.
  *  obs            optional (chains, SVB_VOBS_COUNT); give consecutive launches DIFFERENT records (e.g. rows of a
  *                 (steps, chains, SVB_VOBS_COUNT) column) if they may overlap.
+ *  obs_in         optional (chains, SVB_VOBS_COUNT).  NULL: `obs` is the full record of the state AFTER the sweeps (one
+ *                 more fp64 pass over the chain).  Non-NULL: the state columns ACTION .. WRAP1 of the chain AS IT ARRIVES
+ *                 are written to obs_in (they ride along with the pass that builds the residuals, for a quarter of the
+ *                 cost), its two counter columns are left alone, and `obs` receives only this launch's ACCEPTED and
+ *                 ACCEPTANCE.  In a sequence of steps pass obs_in = the previous step's record: every record is then
+ *                 complete one launch later, with exactly the bits the separate pass would have produced; the last
+ *                 state's columns come from svb_villain_observables.
  * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64}; anything else returns SVB_E_UNSUPPORTED (use
  * svb_villain_sweep).  A kernel launched normally after these waits for all of them, as usual.
  */
@@ -166,7 +173,7 @@ int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N,
                                  double kappa, const double* kappa_chain, int W,
                                  double interval_phi, int interval_n,
                                  int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
-                                 double* obs, uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch,
+                                 double* obs, double* obs_in, uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch,
                                  int flags, void* stream);
 
 /*

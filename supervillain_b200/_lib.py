@@ -30,7 +30,7 @@ SIGNATURES = {
     'svb_last_error': (ctypes.c_char_p, []),
     'svb_villain_sweep': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'svb_villain_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp,
+    'svb_villain_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp,
                                           ctypes.c_uint32, ctypes.c_uint32, _i, _vp]),
     'svb_villain_observables': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),

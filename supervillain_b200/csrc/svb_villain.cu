@@ -60,6 +60,7 @@ struct VillainArgs {
     uint8_t* accept_mask;
     double* dS_out;
     // overlapped launches (svb_villain_sweep_overlapped); epochs == nullptr otherwise
+    double* obs_in;
     uint32_t* epochs;
     uint32_t wait_epoch, signal_epoch;
     int grid_wait;
@@ -1417,11 +1418,9 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 #include "svb_villain_filtered.cuh"
 
 #ifndef SVB_FILT_MINB32
-#define SVB_FILT_MINB32 6
+#define SVB_FILT_MINB32 8        /* 64 registers per thread: 8 CTAs = 32 warps per SM (28.5 vs 30.0 us at config 2) */
 #endif
-#ifndef SVB_FILT_STAGES
 #define SVB_FILT_STAGES 1
-#endif
 #ifndef SVB_RESID_STAGES
 #define SVB_RESID_STAGES 1
 #endif
@@ -1436,7 +1435,7 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
     if (!INJECTED && !STRICT && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out) {
         // production path: fp32-filtered decisions on resident fp32 residuals (svb_villain_filtered.cuh)
         switch (a.N) {
-            case 16: return launch_villain_filtered<16, 16, 2>(a, stream, info);
+            case 16: return launch_villain_filtered<16, 16, 1>(a, stream, info);
             case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, stream, info);
             case 64: return launch_villain_filtered<64, 2, 1>(a, stream, info);
             default: break;
@@ -1570,7 +1569,7 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
     }
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
-    a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (phi_dtype == SVB_F64) return dispatch_villain<double>(a, rng_mode, arith_mode, path, st);
     return dispatch_villain<float>(a, rng_mode, arith_mode, path, st);
@@ -1578,7 +1577,7 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
 
 extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain,
                                             int W, double interval_phi, int interval_n, int n_sweeps, uint64_t seed,
-                                            uint64_t sweep0, uint64_t chain0, double* obs, uint32_t* epochs,
+                                            uint64_t sweep0, uint64_t chain0, double* obs, double* obs_in, uint32_t* epochs,
                                             uint32_t wait_epoch, uint32_t signal_epoch, int flags, void* stream) {
     if (!phi || !n || !epochs) return fail(SVB_E_NULL, "svb_villain_sweep_overlapped: phi, n and epochs are required");
     if (chains < 0) return fail(SVB_E_SHAPE, "svb_villain_sweep_overlapped: chains=%lld", (long long)chains);
@@ -1601,14 +1600,14 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
     }
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
-    a.epochs = epochs; a.wait_epoch = wait_epoch; a.signal_epoch = signal_epoch;
+    a.obs_in = obs_in; a.epochs = epochs; a.wait_epoch = wait_epoch; a.signal_epoch = signal_epoch;
     a.grid_wait = (flags & SVB_OVERLAP_PREDECESSOR) ? 0 : 1;
     DeviceInfo info;
     int rc = get_device_info(info);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (N) {
-        case 16: return launch_villain_filtered<16, 16, 2>(a, st, info);
+        case 16: return launch_villain_filtered<16, 16, 1>(a, st, info);
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
         default: return launch_villain_filtered<64, 2, 1>(a, st, info);
     }
@@ -1706,7 +1705,7 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     }
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
-    a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // An even number of ping-pong sweeps ends in (phi, n).  An odd count would end in the workspace, so the last sweep of
     // an odd count is done in place by the per-colour global path instead (cheaper than copying the state back).

@@ -118,16 +118,71 @@ __device__ __forceinline__ PairResiduals villain_pair_residuals(const double* p_
     return o;
 }
 
+// Per-chain record in two halves.  chain_partials: every warp reduces its sums and lane 0 parks them in the warp's shared
+// slot.  chain_finish (ONE thread, behind the next block barrier): adds the slots in warp order -- deterministic -- and writes
+// the record.  No atomics and no fences: a fence in the thread that has just issued the chain's bulk store would wait for it.
+// STATE slots (4 doubles per warp) and COUNTER slots (2 per warp) are separate, so the two kinds never collide.
+template <bool STATE, bool COUNTERS>
+__device__ __forceinline__ void chain_partials(double* red_state, double* red_count, int lane, int warp, double action,
+                                               long long dn2, int w0, int w1, double sum_A, int n_acc) {
+    unsigned lo = 0, hi = 0;
+    if (STATE) {
+        action = warp_sum(action);
+        lo = __reduce_add_sync(0xffffffffu, (unsigned)(dn2 & 0xFFFFFF));
+        hi = __reduce_add_sync(0xffffffffu, (unsigned)((unsigned long long)dn2 >> 24));
+        w0 = __reduce_add_sync(0xffffffffu, w0);
+        w1 = __reduce_add_sync(0xffffffffu, w1);
+    }
+    if (COUNTERS) {
+        sum_A = warp_sum(sum_A);
+        n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+    }
+    if (lane == 0) {
+        if (STATE) {
+            double* slot = red_state + 4 * warp;
+            slot[0] = action;
+            slot[1] = (double)((long long)lo + ((long long)hi << 24));
+            slot[2] = (double)w0; slot[3] = (double)w1;
+        }
+        if (COUNTERS) {
+            double* slot = red_count + 2 * warp;
+            slot[0] = sum_A; slot[1] = (double)n_acc;
+        }
+    }
+}
+template <int NW, bool STATE, bool COUNTERS>
+__device__ __forceinline__ void chain_finish(const double* red_state, const double* red_count, double half_kappa,
+                                             double* state_row, double* counter_row) {
+    if (STATE) {
+        double t[4] = {0, 0, 0, 0};
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] += red_state[4 * w + i];
+        state_row[SVB_VOBS_ACTION] = half_kappa * t[0];
+        state_row[SVB_VOBS_SUM_DN2] = t[1];
+        state_row[SVB_VOBS_WRAP0] = t[2];
+        state_row[SVB_VOBS_WRAP1] = t[3];
+    }
+    if (COUNTERS) {
+        double t[2] = {0, 0};
+        for (int w = 0; w < NW; ++w) { t[0] += red_count[2 * w]; t[1] += red_count[2 * w + 1]; }
+        counter_row[SVB_VOBS_ACCEPTED] = t[1];
+        counter_row[SVB_VOBS_ACCEPTANCE] = t[0];
+    }
+}
+
 // OVERLAP: the launch takes part in the overlapped-launch protocol of svb_villain_sweep_overlapped -- it may begin
 // while its predecessor in the stream is still running (programmatic dependent launch), and every chain is ordered
 // individually through `a.epochs`: a chain is loaded only once its epoch reads a.wait_epoch (written by the launch that
 // last stored it), and a CTA sets the epochs of its chains to a.signal_epoch once all its stores and records are complete.
-template <int NT, int MINB, int STAGES, bool OVERLAP>
+// UNIT: W == 1 and interval_n == 1 (the reference's defaults) as compile-time constants.
+template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT>
 __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                              const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
     constexpr int PER = VH / T;                                  // sites per thread per colour (rows x0 + 8 q)
+    static_assert(STAGES == 1, "one shared-memory stage per CTA: occupancy, not double buffering, hides the copies");
     static_assert(PER >= 2 && PER % 2 == 0, "villain_smem_filtered_kernel: unsupported geometry");
     constexpr uint32_t bytes_phi = V * sizeof(double);
     constexpr uint32_t bytes_n = 2 * V * sizeof(int32_t);
@@ -135,13 +190,13 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* rc0 = reinterpret_cast<float*>(smem_raw + STAGES * stage_bytes);      // [colour][VH]: residual of link (0, x)
     float* rc1 = rc0 + V;                                                         // [colour][VH]: residual of link (1, x)
-    double* red = reinterpret_cast<double*>(rc1 + V);                             // [NW][6] per-warp partial sums
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 6 * 32);
-    unsigned* arrivals = reinterpret_cast<unsigned*>(bar + 2);
+    double* red_state = reinterpret_cast<double*>(rc1 + V);                       // [NW][4] per-warp partial sums
+    double* red_count = red_state + 4 * 32;                                       // [NW][2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red_count + 2 * 32);
+    constexpr int kWriter = 32;            // finishes the records: lane 0 of warp 1 (thread 0 is busy with the bulk copies)
 
     if (tid == 0) {
         for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
-        *arrivals = 0;
         fence_mbar_init();
     }
     if (OVERLAP) {
@@ -151,10 +206,14 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         if (a.grid_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     __syncthreads();
-    const bool want_obs = a.obs != nullptr;
-    const uint32_t K = (uint32_t)(2 * a.interval_n + 1);
-    const int W = a.W, mWI = -a.W * a.interval_n;
-    const float cIn = fc.c * (float)a.interval_n;
+    const bool obs_of_input = a.obs_in != nullptr;                // state columns describe the chain as it ARRIVES
+    const bool want_obs = a.obs != nullptr && !obs_of_input;     // ... or as it leaves (one more fp64 pass)
+    const int interval_n = UNIT ? 1 : a.interval_n;
+    const uint32_t K = (uint32_t)(2 * interval_n + 1);
+    const int W = UNIT ? 1 : a.W, mWI = -W * interval_n;
+    const float cIn = fc.c * (float)interval_n;
+    const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
+    const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
 
     // per-thread geometry: rows row8 + 8 q of the compact column k
     const int row8 = tid / HN, k = tid - row8 * HN;
@@ -216,7 +275,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 
     int it = 0;
     for (; chain < a.chains; chain += gridDim.x, ++it) {
-        const int b = (STAGES == 2) ? (it & 1) : 0;
+        constexpr int b = 0;
         unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
         double* sphi = reinterpret_cast<double*>(stage);
         int32_t* sn0 = reinterpret_cast<int32_t*>(stage + bytes_phi);
@@ -226,16 +285,17 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         const double half_kappa = kappa / 2;
         const float hk2 = (float)(half_kappa * 1.4426950408889634);                 // decisions are taken in units of ln 2
         const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+        const float2 hk22 = make_float2(hk2, hk2), hkA2 = make_float2(hkA, hkA), hkB2 = make_float2(hkB, hkB);
         // pair pointers: phi / n at (row8, 2k); rows advance by 8 N per q
         const double* pp = sphi + row8 * N + 2 * k;
         const double* pp_r = sphi + row8 * N + ((2 * k + 2) & (N - 1));
         const int32_t* pn0 = sn0 + row8 * N + 2 * k;
         const int32_t* pn1 = sn1 + row8 * N + 2 * k;
 
-        mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
+        mbar_wait(&bar[b], (uint32_t)(it & 1));
 
         int n_acc = 0;
-        double sum_A_all = 0.0;
+        double sum_A_all = 0.0;        // per sweep in fp32 (<= 2 PER terms per thread), across sweeps in fp64
         for (int s = 0; s < a.n_sweeps; ++s) {
             float sum_A = 0.0f;
             // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) in fp64, stored rounded to fp32 ----
@@ -244,18 +304,37 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                 float* w1e = rc1 + cc * VH + tid;
                 float* w0o = rc0 + (cc ^ 1) * VH + tid;
                 float* w1o = rc1 + (cc ^ 1) * VH + tid;
+                const bool sums = obs_of_input && s == 0;            // the observables of the arriving state ride along
+                double action = 0.0;
+                int w0 = 0, w1 = 0;
+                long long dn2 = 0;
 #pragma unroll
                 for (int q = 0; q < PER; ++q) {
                     const int o = 8 * N * q;
-                    const PairResiduals pr = villain_pair_residuals(pp + o, pp + o + ((q == PER - 1) ? up_off : N), pp_r + o,
-                                                                    pn0 + o, pn1 + o);
+                    const int uo = (q == PER - 1) ? up_off : N;
+                    const PairResiduals pr = villain_pair_residuals(pp + o, pp + o + uo, pp_r + o, pn0 + o, pn1 + o);
                     w0e[T * q] = (float)pr.r0e;
                     w1e[T * q] = (float)pr.r1e;
                     w0o[T * q] = (float)pr.r0o;
                     w1o[T * q] = (float)pr.r1o;
+                    if (sums) {
+                        action = fma(pr.r0e, pr.r0e, action);
+                        action = fma(pr.r0o, pr.r0o, action);
+                        action = fma(pr.r1e, pr.r1e, action);
+                        action = fma(pr.r1o, pr.r1o, action);
+                        const int hr = sn0[(row8 + 8 * q) * N + ((2 * k + 2) & (N - 1))];            // n0[x + 2 e1]
+                        const int2 up = *reinterpret_cast<const int2*>(pn1 + o + uo);                 // n1[x + e0]
+                        const int d0 = (up.x - pr.a1.x) - (pr.a0.y - pr.a0.x), d1 = (up.y - pr.a1.y) - (hr - pr.a0.y);
+                        dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+                        w0 += pr.a0.x + pr.a0.y;
+                        w1 += pr.a1.x + pr.a1.y;
+                    }
                 }
+                if (sums) chain_partials<true, false>(red_state, red_count, lane, warp, action, dn2, w0, w1, 0.0, 0);
             }
             __syncthreads();
+            if (obs_of_input && s == 0 && tid == kWriter)
+                chain_finish<NW, true, false>(red_state, red_count, kappa / 2, a.obs_in + chain * SVB_VOBS_COUNT, nullptr);
 
             const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)s;
 #pragma unroll 1
@@ -280,40 +359,57 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                 for (int p = 0; p < PER / 2; ++p) {
                     const uint32_t c0 = (uint32_t)((row8 + 16 * p) * N + x1);                 // villain_pair_counter
                     const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+                    const int qA = 2 * p, qB = 2 * p + 1;
+                    float* r0bA = (p == 0) ? R0b_q0 : R0b;             // q == 0 is the only row whose e0-neighbour wraps
+                    int32_t* n0bA = (p == 0) ? N0b_q0 : N0b;
+                    // proposals: four base-K digits each, then the leading 32 bits of the uniform
+                    uint32_t fA = bits.y, fB = bits.w;
+                    int digA[4], digB[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
+                        fA = (uint32_t)pa; digA[i] = (int)(pa >> 32);
+                        fB = (uint32_t)pb; digB[i] = (int)(pb >> 32);
+                    }
+                    // dphi from 23 centred bits
+                    float2 U = make_float2(__uint_as_float(0x3F800000u | (bits.x >> 9)), __uint_as_float(0x3F800000u | (bits.z >> 9)));
+                    U = __fadd2_rn(U, make_float2(-0.99999994f, -0.99999994f));
+                    const float2 dphi = __ffma2_rn(make_float2(fc.two_I, fc.two_I), U, make_float2(-fc.I, -fc.I));
+                    const float2 base_f = __ffma2_rn(dphi, make_float2(-1.0f, -1.0f), cIn2), base_b = __fadd2_rn(cIn2, dphi);
+                    const float2 r_f0 = make_float2(R0own[T * qA], R0own[T * qB]), r_f1 = make_float2(R1own[T * qA], R1own[T * qB]);
+                    const float2 r_b0 = make_float2(r0bA[T * qA], R0b[T * qB]), r_b1 = make_float2(R1b[T * qA], R1b[T * qB]);
+                    // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
+                    const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
+                    const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
+                    const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
+                    const float2 dr_b1 = __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
+                    acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
+                    acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
+                    acc2 = __ffma2_rn(dr_b1, __ffma2_rn(two2, r_b1, dr_b1), acc2);
+                    const float2 dS2 = __fmul2_rn(hk22, acc2);                          // dS / ln 2
+                    // -log2(f 2^-32); u lies in [f, f + 1] 2^-32
+                    const float2 L2 = __ffma2_rn(make_float2(fast_lg2((float)fA), fast_lg2((float)fB)), make_float2(-1.0f, -1.0f),
+                                                 make_float2(32.0f, 32.0f));
+                    const float2 Rmax = make_float2(fmaxf(fmaxf(fabsf(r_f0.x), fabsf(r_b0.x)), fmaxf(fabsf(r_f1.x), fabsf(r_b1.x))),
+                                                    fmaxf(fmaxf(fabsf(r_f0.y), fabsf(r_b0.y)), fmaxf(fabsf(r_f1.y), fabsf(r_b1.y))));
+                    const float2 band = __ffma2_rn(hkA2, Rmax, __ffma2_rn(make_float2(4e-6f, 4e-6f), L2, hkB2));
+                    const float2 diff = __ffma2_rn(L2, make_float2(-1.0f, -1.0f), dS2);
+                    sum_A += fminf(fast_ex2(-dS2.x), 1.0f) + fminf(fast_ex2(-dS2.y), 1.0f);
+                    // the residuals an accepted proposal leaves behind
+                    const float2 n_f0 = __fadd2_rn(r_f0, dr_f0), n_b0 = __fadd2_rn(r_b0, dr_b0);
+                    const float2 n_f1 = __fadd2_rn(r_f1, dr_f1), n_b1 = __fadd2_rn(r_b1, dr_b1);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int q = 2 * p + h;
-                        float* r0b = (q == 0) ? R0b_q0 : R0b;
-                        int32_t* n0b = (q == 0) ? N0b_q0 : N0b;
-                        const uint32_t wA = h ? bits.z : bits.x, wB = h ? bits.w : bits.y;
-                        // proposal: four base-K digits, then the leading 32 bits of the uniform
-                        uint32_t f = wB;
-                        int dig[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint64_t prod = (uint64_t)f * K;
-                            f = (uint32_t)prod;
-                            dig[i] = (int)(prod >> 32);
-                        }
-                        const float U = __uint_as_float(0x3F800000u | (wA >> 9)) - 0.99999994f;       // in (0, 1), 23 bits, centred
-                        const float dphi = fmaf(fc.two_I, U, -fc.I);
-                        const float base_f = cIn - dphi, base_b = cIn + dphi;
-                        const float r_f0 = R0own[T * q], r_f1 = R1own[T * q], r_b0 = r0b[T * q], r_b1 = R1b[T * q];
-                        // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
-                        const float dr_f0 = fmaf(-fc.c, (float)dig[0], base_f), dr_b0 = fmaf(-fc.c, (float)dig[1], base_b);
-                        const float dr_f1 = fmaf(-fc.c, (float)dig[2], base_f), dr_b1 = fmaf(-fc.c, (float)dig[3], base_b);
-                        float acc2 = dr_f0 * fmaf(2.0f, r_f0, dr_f0);
-                        acc2 = fmaf(dr_b0, fmaf(2.0f, r_b0, dr_b0), acc2);
-                        acc2 = fmaf(dr_f1, fmaf(2.0f, r_f1, dr_f1), acc2);
-                        acc2 = fmaf(dr_b1, fmaf(2.0f, r_b1, dr_b1), acc2);
-                        const float dS2 = hk2 * acc2;                                   // dS / ln 2
-                        const float L2 = 32.0f - fast_lg2((float)f);                    // -log2(f 2^-32); u lies in [f, f + 1] 2^-32
-                        const float Rmax = fmaxf(fmaxf(fabsf(r_f0), fabsf(r_b0)), fmaxf(fabsf(r_f1), fabsf(r_b1)));
-                        const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L2, hkB));
-                        const float diff = dS2 - L2;
-                        bool ok = diff < 0.0f;
-                        sum_A += fminf(fast_ex2(-dS2), 1.0f);
-                        if (!(fabsf(diff) > band) || f < 65536u) {
+                        float* r0b = h ? R0b : r0bA;
+                        int32_t* n0b = h ? N0b : n0bA;
+                        const uint32_t wA = h ? bits.z : bits.x;
+                        const uint32_t f = h ? fB : fA;
+                        const int* dig = h ? digB : digA;
+                        const float dif = h ? diff.y : diff.x, bnd = h ? band.y : band.x;
+                        bool ok = dif < 0.0f;
+                        if (!(fabsf(dif) > bnd) || f < 65536u) {
                             ExactProposal ep;
                             ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1;
                             const int x0 = row8 + 8 * q;
@@ -326,36 +422,30 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             ep.c = SVB_TWO_PI * (double)W;
                             ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - a.interval_n;
+                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
                             ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
                             ok = villain_exact_decision(ep);
                         }
+                        n_acc += ok ? 1 : 0;
                         if (ok) {                                               // (:121-129)
-                            Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], villain_dphi_from_word(wA, a.interval_phi));
+                            // phi += dphi with dphi = -I + fl((2 I 2^-32) (A + 1/2)): the scaling by 2^-32 is exact, so this
+                            // is villain_dphi_from_word bit for bit with one multiply less
+                            const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
+                            Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
                             atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);      // only this thread touches these links in this pass
                             atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
                             atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
                             atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
-                            R0own[T * q] = r_f0 + dr_f0;
-                            r0b[T * q] = r_b0 + dr_b0;
-                            R1own[T * q] = r_f1 + dr_f1;
-                            R1b[T * q] = r_b1 + dr_b1;
-                            ++n_acc;
+                            R0own[T * q] = h ? n_f0.y : n_f0.x;
+                            r0b[T * q] = h ? n_b0.y : n_b0.x;
+                            R1own[T * q] = h ? n_f1.y : n_f1.x;
+                            R1b[T * q] = h ? n_b1.y : n_b1.x;
                         }
                     }
                 }
                 if (s == a.n_sweeps - 1 && c == 1) fence_proxy_async();      // this thread's phi / n writes -> visible to the bulk store
-                uint32_t seen = 0;
-                if (STAGES == 2 && s == 0 && c == 0 && tid == 0) {
-                    if (next < a.chains) seen = peek_epoch(next);
-                    bulk_wait_read0();                                      // the previous chain's store (issued a pass ago)
-                }
                 __syncthreads();
-                if (STAGES == 2 && s == 0 && c == 0) {
-                    // every warp is past the previous chain's observable pass; its store has completed
-                    if (tid == 0 && next < a.chains) issue_load(next, b ^ 1, seen);
-                }
             }
             sum_A_all += (double)sum_A;
         }
@@ -366,7 +456,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
             bulk_s2g(reinterpret_cast<double*>(a.phi) + chain * V, sphi, bytes_phi);
             bulk_s2g(a.n + chain * 2 * V, sn0, bytes_n);
             bulk_commit();
-            if (STAGES == 1 && next < a.chains) seen_next = peek_epoch(next);     // lands during the observable pass
+            if (next < a.chains) seen_next = peek_epoch(next);     // lands during the observable pass
         }
 
         if (want_obs) {
@@ -391,44 +481,20 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                 w0 += pr.a0.x + pr.a0.y;
                 w1 += pr.a1.x + pr.a1.y;
             }
-            // warp partials -> shared slots; the last warp to arrive adds them in warp order (deterministic) and writes
-            // the record.  No block barrier: the next use of the slots is behind the next chain's first barrier.
-            action = warp_sum(action);
-            sum_A_all = warp_sum(sum_A_all);
-            const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(dn2 & 0xFFFFFF));
-            const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)((unsigned long long)dn2 >> 24));
-            w0 = __reduce_add_sync(0xffffffffu, w0);
-            w1 = __reduce_add_sync(0xffffffffu, w1);
-            n_acc = __reduce_add_sync(0xffffffffu, n_acc);
-            if (lane == 0) {
-                double* slot = red + 6 * warp;
-                slot[0] = action; slot[1] = sum_A_all;
-                slot[2] = (double)((long long)lo + ((long long)hi << 24));
-                slot[3] = (double)w0; slot[4] = (double)w1; slot[5] = (double)n_acc;
-                __threadfence_block();
-                if (atomicAdd(arrivals, 1u) == NW - 1) {
-                    __threadfence_block();
-                    double t[6] = {0, 0, 0, 0, 0, 0};
-                    for (int w = 0; w < NW; ++w)
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) t[i] += red[6 * w + i];
-                    double* o = a.obs + chain * SVB_VOBS_COUNT;
-                    o[SVB_VOBS_ACTION] = (kappa / 2) * t[0];
-                    o[SVB_VOBS_SUM_DN2] = t[2];
-                    o[SVB_VOBS_WRAP0] = t[3];
-                    o[SVB_VOBS_WRAP1] = t[4];
-                    o[SVB_VOBS_ACCEPTED] = t[5];
-                    o[SVB_VOBS_ACCEPTANCE] = t[1];
-                    *arrivals = 0;
-                }
-            }
+            chain_partials<true, true>(red_state, red_count, lane, warp, action, dn2, w0, w1, sum_A_all, n_acc);
+        } else if (a.obs != nullptr) {
+            // the state columns went to obs_in at the start; only this launch's counters remain
+            chain_partials<false, true>(red_state, red_count, lane, warp, 0.0, 0, 0, 0, sum_A_all, n_acc);
         }
-        if (STAGES == 1) {
-            __syncthreads();           // every warp has read the final state before the buffer is refilled
-            if (tid == 0) {
-                bulk_wait_read0();
-                if (next < a.chains) issue_load(next, 0, seen_next);
-            }
+        __syncthreads();               // every warp has read the final state before the buffer is refilled
+        if (tid == 0) {
+            bulk_wait_read0();
+            if (next < a.chains) issue_load(next, 0, seen_next);
+        }
+        if (tid == kWriter && a.obs != nullptr) {
+            double* row = a.obs + chain * SVB_VOBS_COUNT;
+            if (want_obs) chain_finish<NW, true, true>(red_state, red_count, kappa / 2, row, row);
+            else chain_finish<NW, false, true>(red_state, red_count, kappa / 2, nullptr, row);
         }
     }
     if (tid == 0) bulk_wait0();
@@ -441,18 +507,21 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 template <int NT, int MINB, int STAGES>
 static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool overlap = a.epochs != nullptr;
-    auto kern = overlap ? villain_smem_filtered_kernel<NT, MINB, STAGES, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, false>;
+    const bool unit = a.W == 1 && a.interval_n == 1;
+    auto kern = overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false>)
+                        : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false>);
     const size_t V = (size_t)NT * NT;
     const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * 32 * sizeof(double) + 32;
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
-    static int per_sm_cache[2][64];
-    int per_sm = (info.device < 64) ? per_sm_cache[overlap ? 1 : 0][info.device] : 0;
+    static int per_sm_cache[4][64];
+    const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0);
+    int per_sm = (info.device < 64) ? per_sm_cache[variant][info.device] : 0;
     if (per_sm == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "filtered villain kernel does not fit an SM at N=%d", NT);
-        if (info.device < 64) per_sm_cache[overlap ? 1 : 0][info.device] = per_sm;
+        if (info.device < 64) per_sm_cache[variant][info.device] = per_sm;
     }
     long long grid = (long long)per_sm * info.sm_count;
     if (grid > a.chains) grid = a.chains;

@@ -179,13 +179,19 @@ class BatchedEnsemble:
                 overlapped = generator.overlapped_device(a, b, chain0=self.chain0, kappa_chain=kappa_chain)
             except NotImplementedError:
                 overlapped = None
+        scratch = torch.empty((self.chains, nobs), dtype=torch.float64, device=self.device) if overlapped is not None else None
         for k in progress(range(steps), desc='Generation'):
             if overlapped is not None:
-                overlapped(sweeps_per_step, obs=record[k])
+                # the state columns of draw k - 1 ride along with launch k (they describe the chains as they arrive);
+                # launch k's own counters go to row k
+                overlapped(sweeps_per_step, obs=record[k], obs_in=record[k - 1] if k else scratch)
             else:
                 generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
             if keep_every and (k + 1) % keep_every == 0:
                 kept.append((a.cpu().numpy(), b.cpu().numpy()))          # reads only: stream order suffices
+        if overlapped is not None and steps:
+            last = ops.villain_observables(a, b, self.Action.kappa, kappa_chain=kappa_chain)     # the final state's columns
+            record[steps - 1, :, :4] = last[:, :4]
         self.record = record.cpu().numpy().transpose(1, 0, 2)          # (chains, steps, nobs): ONE D2H
         self.steps = steps
         self.sweeps_per_step = sweeps_per_step

@@ -99,15 +99,16 @@ class NeighborhoodUpdate(Generator):
 
     def overlapped_device(self, phi, n, *, chain0=0, kappa_chain=None):
         """Overlapped-launch stepping of one resident chain set (ops.VillainOverlappedSweeps): returns `step(n_sweeps=1,
-        obs=None)` advancing the Philox counter, with `step.fence()` for foreign writes to the fields.  Raises
-        NotImplementedError where the overlapped kernel does not apply (then use `plan_device`)."""
+        obs=None, obs_in=None)` advancing the Philox counter, with `step.fence()` for foreign writes to the fields.
+        obs_in: the state columns of the chains as they ARRIVE are written there (the previous step's record) and `obs`
+        gets this launch's counters only.  Raises NotImplementedError where the overlapped kernel does not apply."""
         if self.rng is not None or self.arithmetic != 'fast' or self.path != 'auto':
             raise NotImplementedError('overlapped launches serve Philox draws, FAST arithmetic, path="auto"')
         ov = ops.VillainOverlappedSweeps(phi, n, self.kappa, W=self.Action.W, interval_phi=self.interval_phi,
                                          interval_n=self.interval_n, seed=self.seed, chain0=chain0, kappa_chain=kappa_chain)
 
-        def step(n_sweeps=1, obs=None):
-            ov.step(self.counter, n_sweeps, obs)
+        def step(n_sweeps=1, obs=None, obs_in=None):
+            ov.step(self.counter, n_sweeps, obs, obs_in)
             self.counter += n_sweeps
         step.fence = ov.fence
         return step

@@ -168,23 +168,33 @@ class VillainOverlappedSweeps:
         self._keep = (phi, n, kappa_chain)
         self._fn = self.lib.svb_villain_sweep_overlapped
         self._stream = torch.cuda.current_stream
-        self._last_obs = self._last_p_obs = None
+        self._records, self._record_keep = {}, {}
 
     def fence(self):
         """The next step waits for everything enqueued before it (use after foreign writes to the fields)."""
         self.fenced = True
 
-    def step(self, sweep0, n_sweeps=1, obs=None):
-        if obs is None:
-            p_obs = None
-        elif obs is self._last_obs:
-            p_obs = self._last_p_obs               # validated before: tight loops pay nothing per launch
-        else:
-            p_obs = _dev(obs, 'obs', (torch.float64,), (self.chains, VOBS_COUNT))
-            self._last_obs, self._last_p_obs = obs, p_obs
+    def _record(self, t, name):
+        if t is None:
+            return None
+        key = id(t)
+        ptr = self._records.get(key)
+        if ptr is None:                            # validated once: tight loops pay nothing per launch
+            ptr = _dev(t, name, (torch.float64,), (self.chains, VOBS_COUNT))
+            if len(self._records) > 64:
+                self._records.clear()
+                self._record_keep.clear()
+            self._records[key] = ptr
+            self._record_keep[key] = t
+        return ptr
+
+    def step(self, sweep0, n_sweeps=1, obs=None, obs_in=None):
+        """One launch of `n_sweeps` sweeps.  obs: this step's record.  obs_in: if given, the state columns of the chains
+        AS THEY ARRIVE go there (pass the previous step's record) and `obs` receives only this launch's counters."""
+        p_obs, p_obs_in = self._record(obs, 'obs'), self._record(obs_in, 'obs_in')
         e = self.epoch
         code = self._fn(self.p_phi, self.p_n, self.chains, self.N, *self.args, int(n_sweeps), self.seed, int(sweep0), self.chain0,
-                        p_obs, self.p_epochs, e & 0xFFFFFFFF, (e + 1) & 0xFFFFFFFF, 0 if self.fenced else _lib.OVERLAP_PREDECESSOR,
+                        p_obs, p_obs_in, self.p_epochs, e & 0xFFFFFFFF, (e + 1) & 0xFFFFFFFF, 0 if self.fenced else _lib.OVERLAP_PREDECESSOR,
                         self._stream().cuda_stream)
         if code:
             _lib.check(code)

@@ -361,3 +361,35 @@ def test_overlapped_launches_reject_what_they_do_not_serve():
     phi, n = svb.BatchedEnsemble(S, 4)._start('cold', 0)
     with pytest.raises(NotImplementedError):
         ops.VillainOverlappedSweeps(phi, n, 0.5)
+
+
+def test_observables_of_the_arriving_state_complete_the_previous_record():
+    """obs_in: the state columns computed while the residuals are built equal, bit for bit, what the separate pass of
+    the previous launch would have written; BatchedEnsemble.generate uses it and reproduces the ordinary records."""
+    N, chains, K, kappa = 32, 1500, 6, 0.5
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 3)
+    rphi, rn = phi.clone(), n.clone()
+    rec_ref = torch.zeros((K, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for k in range(K):
+        ops.villain_sweep(rphi, rn, kappa, seed=21, sweep0=k, obs=rec_ref[k])
+    rec = torch.full((K, chains, VOBS_COUNT), -7.0, dtype=torch.float64, device='cuda')
+    scratch = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ov = ops.VillainOverlappedSweeps(phi, n, kappa, seed=21)
+    for k in range(K):
+        ov.step(k, 1, obs=rec[k], obs_in=rec[k - 1] if k else scratch)
+    rec[K - 1, :, :4] = ops.villain_observables(phi, n, kappa)[:, :4]
+    torch.cuda.synchronize()
+    assert torch.equal(phi, rphi) and torch.equal(n, rn)
+    assert torch.equal(rec[:K - 1], rec_ref[:K - 1])
+    assert torch.equal(rec[K - 1, :, 1:], rec_ref[K - 1, :, 1:])              # integers and this launch's counters
+    # the last state's action comes from svb_villain_observables (another summation order): 1e-13, not bitwise
+    torch.testing.assert_close(rec[K - 1, :, 0], rec_ref[K - 1, :, 0], rtol=1e-13, atol=0)
+    # the ensemble driver: same records as ordinary launches record by record
+    G1 = NeighborhoodUpdate(S, seed=5)
+    E1 = svb.BatchedEnsemble(S, 64).generate(5, G1, start='hot', start_seed=9, sweeps_per_step=2)
+    G2 = NeighborhoodUpdate(S, seed=5, path='smem')        # path != 'auto': ordinary launches
+    E2 = svb.BatchedEnsemble(S, 64).generate(5, G2, start='hot', start_seed=9, sweeps_per_step=2)
+    assert np.array_equal(E1.record[:, :-1], E2.record[:, :-1]) and np.array_equal(E1.record[:, -1, 1:], E2.record[:, -1, 1:])
+    np.testing.assert_allclose(E1.record[:, -1, 0], E2.record[:, -1, 0], rtol=1e-13)
+    assert G1.accepted == G2.accepted and G1.acceptance == G2.acceptance

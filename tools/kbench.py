@@ -15,11 +15,14 @@ use_obs = os.environ.get('KB_OBS', '1') == '1'
 sweeps = int(os.environ.get('KB_SWEEPS', 1))
 overlap = os.environ.get('KB_OVERLAP', '0') == '1'
 obs_sets = [torch.zeros_like(obs) for _ in range(R)]
+obs_prev = [torch.zeros_like(obs) for _ in range(R)]
+obs_in = os.environ.get('KB_OBSIN', '0') == '1'
 steppers = [ops.VillainOverlappedSweeps(phi, n, 0.5, seed=1) for phi, n in sets] if overlap else None
 def step(k):
     phi, n = sets[k % R]
     if overlap:
-        steppers[k % R].step(k * sweeps, sweeps, obs=obs_sets[k % R] if use_obs else None)
+        steppers[k % R].step(k * sweeps, sweeps, obs=obs_sets[k % R] if use_obs else None,
+                             obs_in=obs_prev[k % R] if (use_obs and obs_in) else None)
     else:
         ops.villain_sweep(phi, n, 0.5, n_sweeps=sweeps, seed=1, sweep0=k * sweeps, obs=obs if use_obs else None)
 for k in range(10): step(k)
@@ -32,4 +35,4 @@ for rep in range(5):
     b.record(); torch.cuda.synchronize()
     best = min(best, a.elapsed_time(b) / 100)
 upd = CH * L * L * sweeps / (best * 1e-3)
-print(f"{os.environ.get('SVB200_LIB','default'):40s} L={L} obs={use_obs} sweeps={sweeps} overlap={overlap}: {best*1e3:8.2f} us/step  {upd:.3e} upd/s  {upd*32/6538.6e9*100:5.1f}% of HBM roofline")
+print(f"{os.environ.get('SVB200_LIB','default'):40s} L={L} obs={use_obs} sweeps={sweeps} overlap={overlap} obs_in={obs_in}: {best*1e3:8.2f} us/step  {upd:.3e} upd/s  {upd*32/6538.6e9*100:5.1f}% of HBM roofline")
