@@ -68,6 +68,6 @@ def srcline(key):
     return ''
 tots = sum(per_line_samp.values())
 print(f'total warp instructions {tot}' + (f' = {32 * tot / sites:.1f} thread-instr per site-update' if sites else ''))
-for key, c in per_line_instr.most_common(60):
+for key, c in per_line_instr.most_common(int(os.environ.get('NCU_LINES_TOP', 60))):
     per = f'{32 * c / sites:6.1f}/site' if sites else ''
     print(f'{key[0][:24]:24s}:{key[1]:4d} {100 * c / tot:5.1f}% {per} samp {100 * per_line_samp[key] / max(tots, 1):4.1f}%  {srcline(key)}')
