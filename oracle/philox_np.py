@@ -17,6 +17,7 @@ MASK32 = np.uint64(0xFFFFFFFF)
 STREAM_VILLAIN_NEIGHBORHOOD = 1
 STREAM_WORLDLINE_PLAQUETTE = 2
 STREAM_VILLAIN_REFINE = 4
+STREAM_WORLDLINE_REFINE = 5
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -91,16 +92,29 @@ def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
 def worldline_draws(seed, chain, sweep, N, mode, interval=1):
     """Dense per-plaquette proposals: u, a (dm | dv | t) and, for mode 'joint', b (dv).
 
-    u = (k44 + 1/2) 2^-44 with k44 = x << 12 | y >> 20; dm sign = bit 19 of y; choices = (w * K) >> 32."""
-    site = np.arange(N * N, dtype=np.uint64)
-    x, y, z, w = philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE)
-    ku = (x << np.uint64(12)) | (y >> np.uint64(20))
-    u = (ku.astype(np.float64) + 0.5) * TWO_M44
+    Draw mapping, version 2 (documented in supervillain_b200/csrc/svb_worldline.cu): the plaquettes (x0 with bits 3 and
+    4 varied, x1) share the Philox block with counter word 0 = (x0 & ~24) N + x1; plaquette x0 owns word (x0 >> 3) & 3 = w:
+      joint             dm = +1 if bit 31 of w else -1;  p = 3 (w << 1 mod 2^32);  dv = (p >> 32) - 1;  f = p mod 2^32
+      vortex / coexact  p = (2 I) w;  idx = p >> 32 picks from [-I..-1, 1..I];  f = p mod 2^32
+      u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53), e = the same word of the block with the same counter in stream
+      STREAM_WORLDLINE_REFINE (the kernels generate e only when f alone does not decide u < A; same decision)."""
+    x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
+    c0 = ((x0 & ~24) * N + x1).astype(np.uint64)
+    word = (x0 >> 3) & 3
+    blk = philox_site(seed, chain, sweep, c0, STREAM_WORLDLINE_PLAQUETTE)
+    ref = philox_site(seed, chain, sweep, c0, STREAM_WORLDLINE_REFINE)
+    w = np.choose(word, blk)
+    e = np.choose(word, ref)
     if mode == 'joint':
-        a = np.where(((y >> np.uint64(19)) & np.uint64(1)) == 1, 1, -1).astype(np.int64)
-        b = ((w * np.uint64(3)) >> np.uint64(32)).astype(np.int64) - 1
+        a = np.where((w >> np.uint64(31)) == 1, 1, -1).astype(np.int64)
+        p = ((w << np.uint64(1)) & MASK32) * np.uint64(3)
+        b = (p >> np.uint64(32)).astype(np.int64) - 1
     else:
-        idx = ((w * np.uint64(2 * interval)) >> np.uint64(32)).astype(np.int64)
+        p = w * np.uint64(2 * interval)
+        idx = (p >> np.uint64(32)).astype(np.int64)
         a = np.where(idx < interval, idx - interval, idx - interval + 1)
         b = np.zeros_like(a)
+    f = p & MASK32
+    frac = (e.astype(np.float64) + 0.5) * TWO_M32
+    u = np.minimum((f.astype(np.float64) + frac) * TWO_M32, 1.0 - 2.0 ** -53)
     return {'u': u.reshape(N, N), 'a': a.reshape(N, N), 'b': b.reshape(N, N)}

@@ -84,21 +84,32 @@ void svo_villain_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t si
     *u = uu < 0x1.fffffffffffffp-1 ? uu : 0x1.fffffffffffffp-1;
 }
 
-/* mode 0 joint: a = dm in {-1,+1}, b = dv in {-1,0,+1}; modes 1, 2: a in [-I..-1, 1..I] */
-void svo_worldline_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site, int mode, int interval, double* u,
+/* mode 0 joint: a = dm in {-1,+1}, b = dv in {-1,0,+1}; modes 1, 2: a in [-I..-1, 1..I].
+ * Draw mapping version 2 (see svb_worldline.cu): one word of the Philox block four plaquettes share. */
+void svo_worldline_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site, int N, int mode, int interval, double* u,
                         int* a, int* b) {
-    uint32_t w[4];
-    philox_site(seed, chain, sweep, site, 2u, w);
-    uint64_t ku = ((uint64_t)w[0] << 12) | (uint64_t)(w[1] >> 20);
-    *u = ((double)ku + 0.5) * 0x1p-44;
+    uint32_t blk[4], ref[4];
+    int x0 = (int)(site / (uint32_t)N), x1 = (int)(site % (uint32_t)N);
+    uint32_t c0 = (uint32_t)((x0 & ~24) * N + x1);
+    int word = (x0 >> 3) & 3;
+    philox_site(seed, chain, sweep, c0, 2u, blk);
+    philox_site(seed, chain, sweep, c0, 5u, ref);
+    uint32_t w = blk[word], e = ref[word];
+    uint64_t p;
     if (mode == 0) {
-        *a = ((w[1] >> 19) & 1u) ? +1 : -1;
-        *b = (int)(((uint64_t)w[3] * 3ull) >> 32) - 1;
+        *a = (w >> 31) ? +1 : -1;
+        p = (uint64_t)(uint32_t)(w << 1) * 3ull;
+        *b = (int)(p >> 32) - 1;
     } else {
-        int idx = (int)(((uint64_t)w[3] * (uint64_t)(2 * interval)) >> 32);
+        p = (uint64_t)w * (uint64_t)(2 * interval);
+        int idx = (int)(p >> 32);
         *a = (idx < interval) ? idx - interval : idx - interval + 1;
         *b = 0;
     }
+    uint32_t f = (uint32_t)p;
+    double frac = ((double)e + 0.5) * 0x1p-32;
+    double uu = ((double)f + frac) * 0x1p-32;
+    *u = uu < 0x1.fffffffffffffp-1 ? uu : 0x1.fffffffffffffp-1;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -329,7 +340,7 @@ int svo_worldline_sweep_philox(int64_t* m, int64_t* v, int64_t chains, int N, do
         for (int s = 0; s < n_sweeps; ++s) {
             for (int i = 0; i < V; ++i) {
                 int ai, bi;
-                svo_worldline_draw(seed, chain0 + (uint64_t)c, sweep0 + (uint64_t)s, (uint32_t)i, mode, interval, &u[i], &ai, &bi);
+                svo_worldline_draw(seed, chain0 + (uint64_t)c, sweep0 + (uint64_t)s, (uint32_t)i, N, mode, interval, &u[i], &ai, &bi);
                 a[i] = ai; b[i] = bi;
             }
             double accp = 0.0;

@@ -66,7 +66,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1,
 
 // Stream ids folded into the top byte of counter word 3, so the generators never share draws.
 enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u, STREAM_WORLDLINE_WRAPPING = 3u,
-                  STREAM_VILLAIN_REFINE = 4u };
+                  STREAM_VILLAIN_REFINE = 4u, STREAM_WORLDLINE_REFINE = 5u };
 
 __host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t chain, uint64_t sweep,
                                                          uint32_t site, uint32_t stream_id) {
@@ -140,6 +140,40 @@ __device__ __forceinline__ bool metropolis_filtered(double dS, double u, double&
     return u < prob;
 }
 #endif
+
+// ------------------------------------------------------------------------------------------
+// Lazily refined Metropolis uniforms.  A proposal carries only the LEADING 32 bits f of its uniform, so u is known to lie
+// in [f, f + 1] 2^-32; that decides u < A unless A falls inside the bracket (probability 2^-32 per proposal).  Only then
+// are the trailing bits generated: e = word `word` of the Philox block with the same counter in the refinement stream,
+//   u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53).
+// Every kernel and the oracle implement exactly this rule, so decisions are those of the full 64-bit uniform.
+// ------------------------------------------------------------------------------------------
+struct LazyUniform {
+    uint32_t f;        // leading 32 bits
+    uint32_t c0;       // counter word 0 of the block the proposal came from
+    uint32_t word;     // which word of the refinement block belongs to this proposal
+};
+struct RefineCtx {
+    unsigned long long seed, chain, sweep;
+};
+
+static __device__ __noinline__ double refined_uniform(uint32_t f, uint32_t c0, uint32_t word, uint32_t stream_id, unsigned long long seed,
+                                               unsigned long long chain, unsigned long long sweep) {
+    const Philox4 p = philox_site(seed, chain, sweep, c0, stream_id);
+    const uint32_t e = (word == 0) ? p.x : (word == 1) ? p.y : (word == 2) ? p.z : p.w;
+    const double frac = __dmul_rn(__dadd_rn((double)e, 0.5), 2.3283064365386963e-10);          // (e + 1/2) 2^-32
+    const double u = __dmul_rn(__dadd_rn((double)f, frac), 2.3283064365386963e-10);
+    return fmin(u, 0.99999999999999988898);                                                     // 1 - 2^-53
+}
+
+// u < A decided from the bracket of u, refining only when A falls inside it.
+__device__ __forceinline__ bool decide_lazy(double A, const LazyUniform& lu, uint32_t stream_id, const RefineCtx& rc) {
+    const double u_lo = __dmul_rn((double)lu.f, 2.3283064365386963e-10);
+    const double u_hi = __dadd_rn(u_lo, 2.3283064365386963e-10);
+    if (A > u_hi) return true;
+    if (A <= u_lo) return false;
+    return refined_uniform(lu.f, lu.c0, lu.word, stream_id, rc.seed, rc.chain, rc.sweep) < A;
+}
 
 // ------------------------------------------------------------------------------------------
 // checkerboard colouring (supervillain/lattice/compact.py:192-239, D = 2)
@@ -240,5 +274,51 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // all but the most recent bulk group of this thread have completed (their global writes are performed)
 __device__ __forceinline__ void bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// Overlapped launches (svb_*_sweep_overlapped): a launch may begin while its predecessor in the stream is still running
+// (programmatic dependent launch) and the data is ordered per chain through a caller-owned epoch word per chain.
+//   prologue      every thread, first thing: let the next launch start once all CTAs of this one are resident, and --
+//                 unless the caller vouches for the predecessor -- wait for everything before this launch
+//   peek / wait   one thread: a chain may be loaded once its epoch reads wait_epoch; `peek` early so the common case
+//                 costs no round trip at the point of the load
+//   publish_all   one warp, when the CTA is done and behind a block barrier before which the thread that issued the bulk
+//                 stores has seen them complete: ONE gpu-scope release fence, then a relaxed store per chain
+// ------------------------------------------------------------------------------------------
+struct OverlapArgs {
+    uint32_t* epochs;          // nullptr: an ordinary launch
+    uint32_t wait_epoch, signal_epoch;
+    int grid_wait;
+};
+
+__device__ __forceinline__ void overlap_prologue(const OverlapArgs& o) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (o.grid_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t overlap_peek(const OverlapArgs& o, long long chain) {
+    uint32_t e = o.wait_epoch;
+    if (!o.grid_wait) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(o.epochs + chain) : "memory");
+    return e;
+}
+__device__ __forceinline__ void overlap_wait(const OverlapArgs& o, long long chain, uint32_t seen) {
+    if (o.grid_wait) return;
+    uint32_t e = seen;
+    unsigned ns = 32, naps = 0;
+    while (e != o.wait_epoch) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(o.epochs + chain) : "memory");
+        if (e == o.wait_epoch) break;
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
+        if (++naps > (1u << 21)) __trap();      // a producer that never comes is a caller error: fail, do not hang the GPU
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void overlap_publish_all(const OverlapArgs& o, int lane, int count, long long first, long long stride) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    for (int i = lane; i < count; i += 32)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(o.epochs + first + (long long)i * stride), "r"(o.signal_epoch)
+                     : "memory");
+}
 
 }  // namespace svb

@@ -193,27 +193,17 @@ __device__ __forceinline__ VillainDraw villain_draw_from_words(uint32_t A, uint3
     return d;
 }
 
-// The trailing bits of the uniform, generated only when a decision needs them (cold path).
-__device__ __noinline__ double villain_refined_uniform(uint32_t f, uint32_t c0, uint32_t half, unsigned long long seed,
-                                                       unsigned long long chain, unsigned long long sweep) {
-    const Philox4 p = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE);
-    const uint32_t e = half ? p.z : p.x;
-    const double frac = __dmul_rn(__dadd_rn((double)e, 0.5), 2.3283064365386963e-10);          // (e + 1/2) 2^-32
-    const double u = __dmul_rn(__dadd_rn((double)f, frac), 2.3283064365386963e-10);
-    return fmin(u, 0.99999999999999988898);                                                     // 1 - 2^-53
+// The trailing bits of the uniform, generated only when a decision needs them (cold path; svb_common.cuh).
+__device__ __forceinline__ double villain_refined_uniform(uint32_t f, uint32_t c0, uint32_t half, unsigned long long seed,
+                                                          unsigned long long chain, unsigned long long sweep) {
+    return refined_uniform(f, c0, 2 * half, STREAM_VILLAIN_REFINE, seed, chain, sweep);
 }
-
-struct RefineCtx {
-    unsigned long long seed, chain, sweep;
-};
 
 // u < A decided from the bracket [f, f + 1] 2^-32 of u, refining only when A falls inside it.
 __device__ __forceinline__ bool villain_decide_lazy(double A, const VillainDraw& d, const RefineCtx& rc) {
-    const double u_lo = __dmul_rn((double)d.f, 2.3283064365386963e-10);
-    const double u_hi = __dadd_rn(u_lo, 2.3283064365386963e-10);
-    if (A > u_hi) return true;
-    if (A <= u_lo) return false;
-    return villain_refined_uniform(d.f, d.c0, d.half, rc.seed, rc.chain, rc.sweep) < A;
+    LazyUniform lu;
+    lu.f = d.f; lu.c0 = d.c0; lu.word = 2 * d.half;
+    return decide_lazy(A, lu, STREAM_VILLAIN_REFINE, rc);
 }
 
 // Philox4x32-10 with the key schedule read from kernel parameters (constant bank operands).

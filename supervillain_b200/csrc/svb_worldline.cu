@@ -34,46 +34,54 @@ struct WorldlineArgs {
     double* obs;
     uint8_t* accept_mask;
     double* dS_out;
+    OverlapArgs ov;           // overlapped launches (svb_worldline_sweep_overlapped); ov.epochs == nullptr otherwise
 };
 
 struct WlDraw {
-    double u;
-    int a;   // dm (JOINT), dv (VORTEX), t (COEXACT)
-    int b;   // dv (JOINT)
+    double u;        // INJECTED: the Metropolis uniform.  Philox: the midpoint (f + 1/2) 2^-32 of the known bracket
+    int a;           // dm (JOINT), dv (VORTEX), t (COEXACT)
+    int b;           // dv (JOINT)
+    LazyUniform lu;  // Philox: leading 32 bits of the uniform and where its trailing bits come from (svb_common.cuh)
 };
 
-// Philox draw mapping for one plaquette: 44 bits (x, top of y) -> u in (0,1); bit 19 of y -> dm sign
-// (JOINT); the 32-bit fraction w / 2^32 -> one choice among K values (choice = (w * K) >> 32).
+// The Philox draw mapping (version 2): ONE 32-bit word per plaquette per sweep, and more only when a decision needs it.
+//   The four plaquettes (x0 with bits 3 and 4 varied, x1) -- same colour -- share one Philox4x32-10 block with counter
+//   word 0  c0 = (x0 & ~24) N + x1; plaquette x0 owns word (x0 >> 3) & 3 = w:
+//   JOINT    dm = bit 31 of w ? +1 : -1   (rng.choice([-1,+1]), plaquette.py:58);  g = w << 1;  p = 3 g;
+//            dv = (p >> 32) - 1           (rng.choice([-1,0,+1]), plaquette.py:59);  f = p mod 2^32
+//   VORTEX / COEXACT   p = (2 I) w;  idx = p >> 32 picks from [-I..-1, 1..I] (vortex.py:39, coexact.py:40);  f = p mod 2^32
+//   and the remainder f -- uniform, independent of the choices -- is the leading 32 bits of the Metropolis uniform,
+//   refined lazily from stream STREAM_WORLDLINE_REFINE (same counter, same word).
+__host__ __device__ __forceinline__ uint32_t worldline_quad_counter(int x0, int x1, int N) { return (uint32_t)((x0 & ~24) * N + x1); }
+__host__ __device__ __forceinline__ uint32_t worldline_quad_word(int x0) { return (uint32_t)((x0 >> 3) & 3); }
+
 template <int MODE>
-__host__ __device__ __forceinline__ WlDraw worldline_draw_from_bits(const Philox4& p, int interval) {
+__device__ __forceinline__ WlDraw worldline_draw_from_word(uint32_t w, int interval) {
     WlDraw d;
-    const double two_m44 = 5.6843418860808015e-14;  // 2^-44
-    const uint64_t ku = ((uint64_t)p.x << 12) | (uint64_t)(p.y >> 20);
-#ifdef __CUDA_ARCH__
-    d.u = (__hiloint2double(0x43300000 | (int)(ku >> 32), (int)(uint32_t)ku) - 4503599627370495.5) * two_m44;   // exact
-#else
-    d.u = ((double)(long long)ku + 0.5) * two_m44;
-#endif
+    uint32_t f;
     if (MODE == SVB_WL_JOINT) {
-        d.a = ((p.y >> 19) & 1u) ? +1 : -1;                               // rng.choice([-1,+1])   (plaquette.py:58)
-        d.b = (int)(((uint64_t)p.w * 3ull) >> 32) - 1;                    // rng.choice([-1,0,+1]) (plaquette.py:59)
+        d.a = (w >> 31) ? +1 : -1;
+        const uint64_t p = (uint64_t)(w << 1) * 3ull;
+        d.b = (int)(p >> 32) - 1;
+        f = (uint32_t)p;
     } else {
-        // choice over [-I..-1, 1..I]  (vortex.py:39, coexact.py:40)
-        const int idx = (int)(((uint64_t)p.w * (uint64_t)(2 * interval)) >> 32);
+        const uint64_t p = (uint64_t)w * (uint64_t)(2 * interval);
+        const int idx = (int)(p >> 32);
         d.a = (idx < interval) ? idx - interval : idx - interval + 1;
         d.b = 0;
+        f = (uint32_t)p;
     }
+    d.lu.f = f;
+    d.u = (__hiloint2double(0x43300000, (int)f) - 4503599627370495.5) * 2.3283064365386963e-10;    // (f + 1/2) 2^-32
     return d;
 }
 
-template <int MODE>
-__host__ __device__ __forceinline__ WlDraw worldline_draw_philox(uint64_t seed, uint64_t chain, uint64_t sweep,
-                                                                 uint32_t site, int interval) {
-    return worldline_draw_from_bits<MODE>(philox_site(seed, chain, sweep, site, STREAM_WORLDLINE_PLAQUETTE), interval);
+__device__ __forceinline__ uint32_t philox_word(const Philox4& p, uint32_t word) {
+    return (word == 0) ? p.x : (word == 1) ? p.y : (word == 2) ? p.z : p.w;
 }
 
 template <int MODE, bool INJECTED>
-__device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, long long chain, int sweep, int site) {
+__device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, long long chain, int sweep, int x0, int x1, int site) {
     if (INJECTED) {
         const long long V = (long long)a.N * a.N;
         const long long base = ((long long)sweep * a.chains + chain) * V + site;
@@ -81,11 +89,29 @@ __device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, lon
         d.u = a.inj_u[base];
         d.a = a.inj_a[base];
         d.b = (MODE == SVB_WL_JOINT) ? a.inj_b[base] : 0;
+        d.lu.f = 0; d.lu.c0 = 0; d.lu.word = 0;
         return d;
     } else {
-        return worldline_draw_philox<MODE>(a.seed, a.chain0 + (unsigned long long)chain,
-                                           a.sweep0 + (unsigned long long)sweep, (uint32_t)site, a.interval);
+        const uint32_t c0 = worldline_quad_counter(x0, x1, a.N), word = worldline_quad_word(x0);
+        const Philox4 p = philox_site(a.seed, a.chain0 + (unsigned long long)chain, a.sweep0 + (unsigned long long)sweep, c0,
+                                      STREAM_WORLDLINE_PLAQUETTE);
+        WlDraw d = worldline_draw_from_word<MODE>(philox_word(p, word), a.interval);
+        d.lu.c0 = c0; d.lu.word = word;
+        return d;
     }
+}
+
+__device__ __forceinline__ RefineCtx worldline_refine_ctx(const WorldlineArgs& a, long long chain, int sweep) {
+    RefineCtx rc;
+    rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain; rc.sweep = a.sweep0 + (unsigned long long)sweep;
+    return rc;
+}
+
+// u < min(1, e^-dS) for either kind of draw: INJECTED compares the given uniform, Philox decides lazily.
+template <bool LAZY>
+__device__ __forceinline__ bool worldline_decide(double acc, const WlDraw& d, const RefineCtx& rc) {
+    if (LAZY) return decide_lazy(acc, d.lu, STREAM_WORLDLINE_REFINE, rc);
+    return d.u < acc;
 }
 
 struct PlaqOut {
@@ -94,10 +120,10 @@ struct PlaqOut {
     double dS;
 };
 
-template <int MODE>
+template <int MODE, bool LAZY>
 __device__ __forceinline__ PlaqOut worldline_plaquette_update(int32_t* __restrict__ m0, int32_t* __restrict__ m1,
                                                               int32_t* __restrict__ v, int N, int x0, int x1, double kappa,
-                                                              double Wd, const WlDraw& d) {
+                                                              double Wd, const WlDraw& d, const RefineCtx& rc) {
     const int xp0 = (x0 + 1 == N) ? 0 : x0 + 1;
     const int xm0 = (x0 == 0) ? N - 1 : x0 - 1;
     const int xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
@@ -151,7 +177,7 @@ __device__ __forceinline__ PlaqOut worldline_plaquette_update(int32_t* __restric
         dS = __dadd_rn(dS, t_0p);
     }
     const double acc = fmin(exp(-dS), 1.0);
-    const bool ok = d.u < acc;
+    const bool ok = worldline_decide<LAZY>(acc, d, rc);
     if (ok) {
         if (MODE == SVB_WL_JOINT) {
             m0[i_c] = m_0x + d.a;      // plaquette.py:91-95
@@ -256,8 +282,9 @@ __global__ void __launch_bounds__(256) worldline_smem_kernel(WorldlineArgs a, in
                         const int x0 = j / halfN;
                         const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                         const int site = x0 * N + x1;
-                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, site);
-                        const PlaqOut o = worldline_plaquette_update<MODE>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d);
+                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, x0, x1, site);
+                        const PlaqOut o = worldline_plaquette_update<MODE, !INJECTED>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d,
+                                                                                      worldline_refine_ctx(a, chain, s));
                         n_acc += o.ok ? 1.0 : 0.0;
                         sum_A += o.A;
                         if (last) {
@@ -269,8 +296,9 @@ __global__ void __launch_bounds__(256) worldline_smem_kernel(WorldlineArgs a, in
                     for (int site = tid; site < V; site += T) {
                         const int x0 = site / N, x1 = site - x0 * N;
                         if (site_colour(x0, x1, N) != c) continue;
-                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, site);
-                        const PlaqOut o = worldline_plaquette_update<MODE>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d);
+                        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, s, x0, x1, site);
+                        const PlaqOut o = worldline_plaquette_update<MODE, !INJECTED>(sm0, sm1, sv, N, x0, x1, kappa, Wd, d,
+                                                                                      worldline_refine_ctx(a, chain, s));
                         n_acc += o.ok ? 1.0 : 0.0;
                         sum_A += o.A;
                         if (last) {
@@ -351,7 +379,7 @@ template <int MODE, int NT>
 __device__ __forceinline__ PlaqOut worldline_plaquette_update_w1(int32_t* __restrict__ m0, int32_t* __restrict__ m1,
                                                                  int32_t* __restrict__ v, int x0, int x1, double inv_kappa,
                                                                  double half_inv_kappa, const WlDraw& d, bool collect,
-                                                                 WlSums& sums) {
+                                                                 WlSums& sums, const RefineCtx& rc) {
     const int xp0 = (x0 + 1) & (NT - 1), xm0 = (x0 - 1) & (NT - 1);
     const int xp1 = (x1 + 1) & (NT - 1), xm1 = (x1 - 1) & (NT - 1);
     const int i_c = x0 * NT + x1;
@@ -393,7 +421,16 @@ __device__ __forceinline__ PlaqOut worldline_plaquette_update_w1(int32_t* __rest
         dS = __dadd_rn(dS, t_0p);
     }
     double acc;                                          // fp32-accurate statistic; the decision is the exact fp64 one
-    const bool ok = metropolis_filtered(dS, d.u, acc);
+    bool ok;
+    {
+        int r = -1;
+        if (d.lu.f >= 65536u) r = metropolis_log_filter(dS, d.u, 7.62939453125e-06f, acc);    // bracket half-width <= 2^-17 u
+        if (r >= 0) ok = r != 0;
+        else {
+            acc = exp_clipped(-dS);
+            ok = decide_lazy(acc, d.lu, STREAM_WORLDLINE_REFINE, rc);
+        }
+    }
     if (ok) {
         if (MODE != SVB_WL_VORTEX) {
             m0[i_c] = m_0x + d.a;
@@ -491,11 +528,13 @@ __global__ void __launch_bounds__(TT, MINB) worldline_smem_fast_kernel(const __g
                     const int x0 = j / halfN;
                     const int x1 = 2 * (j - x0 * halfN) + ((x0 + c) & 1);
                     const int site = x0 * N + x1;
+                    const uint32_t qc0 = worldline_quad_counter(x0, x1, N), qword = worldline_quad_word(x0);
                     const Philox4 bits = philox_plaquette_keys(a, a.chain0 + (unsigned long long)chain,
-                                                               a.sweep0 + (unsigned long long)s, (uint32_t)site);
-                    const WlDraw d = worldline_draw_from_bits<MODE>(bits, a.interval);
+                                                               a.sweep0 + (unsigned long long)s, qc0);
+                    WlDraw d = worldline_draw_from_word<MODE>(philox_word(bits, qword), a.interval);
+                    d.lu.c0 = qc0; d.lu.word = qword;
                     const PlaqOut o = worldline_plaquette_update_w1<MODE, NT>(sm0, sm1, sv, x0, x1, inv_kappa, half_inv_kappa, d,
-                                                                              collect, ws);
+                                                                              collect, ws, worldline_refine_ctx(a, chain, s));
                     n_acc += o.ok ? 1 : 0;
                     sum_A += o.A;
                     if (debug) {
@@ -583,8 +622,9 @@ __global__ void __launch_bounds__(256) worldline_colour_pass_kernel(WorldlineArg
         }
     }
     if (site >= 0) {
-        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, sweep, site);
-        const PlaqOut o = worldline_plaquette_update<MODE>(gm0, gm1, gv, N, x0, x1, kappa, (double)a.W, d);
+        const WlDraw d = worldline_get_draw<MODE, INJECTED>(a, chain, sweep, x0, x1, site);
+        const PlaqOut o = worldline_plaquette_update<MODE, !INJECTED>(gm0, gm1, gv, N, x0, x1, kappa, (double)a.W, d,
+                                                                      worldline_refine_ctx(a, chain, sweep));
         n_acc = o.ok ? 1.0 : 0.0;
         sum_A = o.A;
         if (write_debug) {
@@ -714,6 +754,8 @@ static int launch_worldline_fast(const WorldlineArgs& a, cudaStream_t stream, in
     return 0;
 }
 
+#include "svb_worldline_table.cuh"
+
 template <int MODE>
 static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cudaStream_t stream) {
     int dev = 0, sm_count = 0, max_smem = 0;
@@ -725,6 +767,17 @@ static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cu
         if (worldline_smem_bytes(a.N) > (size_t)max_smem)
             return fail(SVB_E_UNSUPPORTED, "N=%d does not fit shared memory; use SVB_PATH_GLOBAL", a.N);
         const bool aligned = ((uintptr_t)a.m % 16 == 0) && ((uintptr_t)a.v % 16 == 0);
+#ifndef SVB_NO_TABLE_KERNEL
+        if (MODE == SVB_WL_JOINT && rng_mode == SVB_RNG_PHILOX && a.W == 1 && aligned && !a.accept_mask && !a.dS_out) {
+            // production path: tabulated integer acceptance thresholds on resident f (svb_worldline_table.cuh)
+            switch (a.N) {
+                case 16: return launch_worldline_table<16, 16>(a, stream, sm_count);
+                case 32: return launch_worldline_table<32, 8>(a, stream, sm_count);
+                case 64: return launch_worldline_table<64, 4>(a, stream, sm_count);
+                default: break;
+            }
+        }
+#endif
         if (rng_mode == SVB_RNG_PHILOX && a.W == 1 && aligned) {
             switch (a.N) {
                 case 16: return launch_worldline_fast<MODE, 16, 32, 16, 2>(a, stream, sm_count);
@@ -769,11 +822,45 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
         a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
     a.inj_u = inj_u; a.inj_a = inj_a; a.inj_b = inj_b; a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
+    a.ov.epochs = nullptr; a.ov.wait_epoch = 0; a.ov.signal_epoch = 0; a.ov.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (mode) {
         case SVB_WL_JOINT: return dispatch_worldline<SVB_WL_JOINT>(a, rng_mode, path, st);
         case SVB_WL_VORTEX: return dispatch_worldline<SVB_WL_VORTEX>(a, rng_mode, path, st);
         default: return dispatch_worldline<SVB_WL_COEXACT>(a, rng_mode, path, st);
+    }
+}
+
+extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                              int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0, double* obs,
+                                              uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch, int flags,
+                                              void* stream) {
+    if (!m || !v || !epochs) return fail(SVB_E_NULL, "svb_worldline_sweep_overlapped: m, v and epochs are required");
+    if (chains < 0) return fail(SVB_E_SHAPE, "svb_worldline_sweep_overlapped: chains=%lld", (long long)chains);
+    if (N != 16 && N != 32 && N != 64) return fail(SVB_E_UNSUPPORTED, "svb_worldline_sweep_overlapped: N must be 16, 32 or 64 (got %d)", N);
+    if (((uintptr_t)m % 16) || ((uintptr_t)v % 16)) return fail(SVB_E_ALIGN, "svb_worldline_sweep_overlapped: fields must be 16-byte aligned");
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: kappa must be positive");
+    if (n_sweeps < 1) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: n_sweeps must be >= 1 (every launch signals its epoch)");
+    if (flags & ~SVB_OVERLAP_PREDECESSOR) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: flags");
+    if (chains == 0) return SVB_OK;
+    WorldlineArgs a;
+    a.m = m; a.v = v; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = 1;
+    a.interval = 1; a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    a.inj_u = nullptr; a.inj_a = nullptr; a.inj_b = nullptr; a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.ov.epochs = epochs; a.ov.wait_epoch = wait_epoch; a.ov.signal_epoch = signal_epoch;
+    a.ov.grid_wait = (flags & SVB_OVERLAP_PREDECESSOR) ? 0 : 1;
+    int dev = 0, sm_count = 0;
+    SVB_CUDA_TRY(cudaGetDevice(&dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (N) {
+        case 16: return launch_worldline_table<16, 16>(a, st, sm_count);
+        case 32: return launch_worldline_table<32, 8>(a, st, sm_count);
+        default: return launch_worldline_table<64, 4>(a, st, sm_count);
     }
 }
 

@@ -1,0 +1,290 @@
+// svb_worldline_table.cuh -- the production worldline sweep kernel (included by svb_worldline.cu, inside namespace svb).
+//
+// PlaquetteUpdate's move (supervillain/generator/worldline/plaquette.py:79-101) in the red/black order of
+// VortexUpdate / CoexactUpdate (worldline/vortex.py:86-128), for W = 1, Philox draws and N in {16, 32, 64}:
+//
+//  * With W = 1 every f = m - delta v (plaquette.py:53) is an integer, and so is everything dS is made of:
+//      delta_f = dm - dv in {-2..2},   s = f1 + f2 - f3 - f4 + 2 delta_f,   dS = (delta_f / kappa) s   (plaquette.py:84-85).
+//    The acceptance probability takes a few hundred distinct values per chain; they are TABULATED per (delta_f, s) -- each
+//    entry computed in fp64 exactly as the general path computes it, fl(fl(delta_f (1/kappa)) s) then the fp64 exponential --
+//    as 32-bit integer thresholds.  A proposal is decided by ONE integer comparison of the leading 32 bits of its uniform
+//    with the threshold; if they are within one unit (probability 2^-31) or s is outside the table, the exact lazy test of
+//    the general path decides.  No floating-point instruction is left on the hot path except the acceptance statistic.
+//  * The m fields are transformed IN PLACE to f when a chain arrives and back to m = f + delta v when it leaves, so a
+//    proposal reads four integers (v is touched only on acceptance) and the action, winding and wrapping sums are plain
+//    integer sums over f (sum_x m_mu = sum_x f_mu on a torus).
+//  * One Philox4x32-10 block serves the four plaquettes (x0 + {0, 8, 16, 24}, x1) a thread owns (draw mapping version 2).
+//
+// Geometry: T = 4 N threads per CTA, one chain at a time, grid-stride over chains, 1-D TMA bulk copies, three block
+// barriers per chain (five with observables).
+#pragma once
+
+struct WlTableEntry {
+    uint32_t thr;      // floor(A 2^32) for A < 1
+    float A;           // the acceptance probability, for the generator's statistic
+};
+constexpr int kWlTableS = 32;                      // s in [-32, 31]
+constexpr int kWlTableSize = 5 * 2 * kWlTableS;    // delta_f in [-2, 2]
+
+// OVERLAP: the launch takes part in the overlapped-launch protocol (svb_common.cuh, svb_worldline_sweep_overlapped).
+template <int NT, int MINB, bool OVERLAP>
+__global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(const __grid_constant__ WorldlineArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
+    constexpr int PER = VH / T;                                  // plaquettes per thread per colour (rows row8 + 8 q)
+    constexpr int QUADS = (PER + 3) / 4, QW = PER < 4 ? PER : 4; // Philox blocks per thread per colour, words used of each
+    constexpr uint32_t bytes_m = 2 * V * sizeof(int32_t);
+    constexpr uint32_t bytes_v = V * sizeof(int32_t);
+    constexpr uint32_t stage_bytes = bytes_m + bytes_v;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t* F0 = reinterpret_cast<int32_t*>(smem_raw);           // m_0 on arrival, f_0 during the sweeps
+    int32_t* F1 = F0 + V;
+    int32_t* sv = F1 + V;
+    WlTableEntry* table = reinterpret_cast<WlTableEntry*>(smem_raw + stage_bytes);
+    long long* red = reinterpret_cast<long long*>(table + kWlTableSize);          // [NW][4] integer partial sums
+    float* redA = reinterpret_cast<float*>(red + 4 * 32);                         // [NW]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(redA + 32);
+    constexpr int kWriter = 32;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (OVERLAP) overlap_prologue(a.ov);
+    __syncthreads();
+    const bool want_obs = a.obs != nullptr;
+
+    auto issue_load = [&](long long chain, uint32_t seen) {
+        if (OVERLAP) overlap_wait(a.ov, chain, seen);
+        mbar_expect_tx(bar, stage_bytes);
+        bulk_g2s(F0, a.m + chain * 2 * V, bytes_m, bar);
+        bulk_g2s(sv, a.v + chain * V, bytes_v, bar);
+    };
+    // acceptance table of one coupling: entry (delta_f, s) from the same fp64 expressions as the general path
+    auto build_table = [&](double kappa) {
+        const double inv_kappa = __ddiv_rn(1.0, kappa);
+        for (int i = tid; i < kWlTableSize; i += T) {
+            const int df = i / (2 * kWlTableS) - 2, s = i % (2 * kWlTableS) - kWlTableS;
+            const double dS = __dmul_rn(__dmul_rn((double)df, inv_kappa), (double)s);
+            const double A = exp_clipped(-dS);
+            WlTableEntry e;
+            const double scaled = A * 4294967296.0;
+            e.thr = (A >= 1.0) ? 0xFFFFFFFFu : (uint32_t)__double2ull_rd(scaled);
+            e.A = (float)A;
+            table[i] = e;
+        }
+    };
+
+    const int row8 = tid / HN, k = tid - row8 * HN;
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, OVERLAP ? overlap_peek(a.ov, chain) : 0u);
+    if (!a.kappa_chain) build_table(a.kappa);
+
+    int it = 0;
+    for (; chain < a.chains; chain += gridDim.x, ++it) {
+        const long long next = chain + gridDim.x;
+        uint32_t seen_next = 0;
+        if (OVERLAP && tid == 0 && next < a.chains) seen_next = overlap_peek(a.ov, next);      // lands during the sweep
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        if (a.kappa_chain) build_table(kappa);          // the previous chain's last reader is behind two barriers
+        mbar_wait(bar, (uint32_t)(it & 1));
+
+        // ---- m -> f = m - delta v, in place, four consecutive sites per step   (plaquette.py:53; compact.py delta,2 rows:
+        //      (delta v)_0[x] = v[x] - v[x - e1],  (delta v)_1[x] = -(v[x] - v[x - e0]))
+#pragma unroll
+        for (int i4 = tid; i4 < V / 4; i4 += T) {
+            const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+            const int4 vc = *reinterpret_cast<const int4*>(sv + i);
+            const int4 vu = *reinterpret_cast<const int4*>(sv + ((x0 - 1) & (N - 1)) * N + x1);        // v[x - e0]
+            const int vl = sv[x0 * N + ((x1 - 1) & (N - 1))];                                           // v[x - e1] of the first
+            int4 m0 = *reinterpret_cast<int4*>(F0 + i), m1 = *reinterpret_cast<int4*>(F1 + i);
+            m0.x -= vc.x - vl;   m0.y -= vc.y - vc.x; m0.z -= vc.z - vc.y; m0.w -= vc.w - vc.z;
+            m1.x -= vu.x - vc.x; m1.y -= vu.y - vc.y; m1.z -= vu.z - vc.z; m1.w -= vu.w - vc.w;
+            *reinterpret_cast<int4*>(F0 + i) = m0;
+            *reinterpret_cast<int4*>(F1 + i) = m1;
+        }
+        __syncthreads();
+
+        int n_acc = 0;
+        float sum_A = 0.0f;
+        const double inv_kappa = __ddiv_rn(1.0, kappa);
+        for (int s = 0; s < a.n_sweeps; ++s) {
+            const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)s;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const int par = (row8 + c) & 1;
+                const int x1 = 2 * k + par;
+                const int xp1 = (x1 + 1) & (N - 1);
+                // the four links of plaquette x: (0,x) F0[x], (1,x+e0) F1[x+e0], (0,x+e1) F0[x+e1], (1,x) F1[x]
+                int32_t* pF0c = F0 + row8 * N + x1;
+                int32_t* pF1c = F1 + row8 * N + x1;
+                int32_t* pF0r = F0 + row8 * N + xp1;
+                int32_t* pv = sv + row8 * N + x1;
+#pragma unroll
+                for (int g = 0; g < QUADS; ++g) {
+                    const uint32_t c0 = (uint32_t)((row8 + 32 * g) * N + x1);                 // worldline_quad_counter
+                    const Philox4 bits = philox_plaquette_keys(a, gc, gs, c0);
+#pragma unroll
+                    for (int wd = 0; wd < QW; ++wd) {
+                        const int q = 4 * g + wd;
+                        const int o = 8 * N * q;                                               // row row8 + 8 q
+                        const int od = (q == PER - 1 && row8 == 7) ? (o + N - V) : (o + N);    // row below (wraps after the last)
+                        const uint32_t w = (wd == 0) ? bits.x : (wd == 1) ? bits.y : (wd == 2) ? bits.z : bits.w;
+                        // dm = +-1 from bit 31, dv in {-1, 0, 1} from the next bits, the remainder leads the uniform
+                        const uint64_t p = (uint64_t)(w << 1) * 3ull;
+                        const int hi = (int)(p >> 32);
+                        const uint32_t f = (uint32_t)p;
+                        const int dmh = (int)(w >> 31);                       // dm = 2 dmh - 1, dv = hi - 1
+                        const int df = 2 * dmh - hi;                          // delta_f = dm - dv
+                        const int f0c = pF0c[o], f1d = pF1c[od], f0r = pF0r[o], f1c = pF1c[o];
+                        const int sI = (f0c + f1d) - f0r - f1c + 2 * df;      // f1 + f2 - f3 - f4 + 2 delta_f
+                        const int kk = df * sI;
+                        bool ok = true;
+                        float A = 1.0f;
+                        if (kk > 0) {                                         // dS > 0: a real Metropolis test
+                            bool exact = (unsigned)(sI + kWlTableS) >= (unsigned)(2 * kWlTableS);
+                            if (!exact) {
+                                const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sI + kWlTableS];
+                                A = e.A;
+                                ok = f < e.thr;
+                                exact = (f - (e.thr - 1u)) <= 1u;            // f in {thr - 1, thr}: the bracket of u touches A
+                            }
+                            if (exact) {
+                                const double dS = __dmul_rn(__dmul_rn((double)df, inv_kappa), (double)sI);
+                                const double Ad = exp_clipped(-dS);
+                                LazyUniform lu;
+                                lu.f = f; lu.c0 = c0; lu.word = (uint32_t)wd;
+                                RefineCtx rc;
+                                rc.seed = a.seed; rc.chain = gc; rc.sweep = gs;
+                                A = (float)Ad;
+                                ok = decide_lazy(Ad, lu, STREAM_WORLDLINE_REFINE, rc);
+                            }
+                        }
+                        sum_A += A;
+                        n_acc += ok ? 1 : 0;
+                        if (ok) {                                             // plaquette.py:91-101
+                            pF0c[o] = f0c + df;
+                            pF1c[od] = f1d + df;
+                            pF0r[o] = f0r - df;
+                            pF1c[o] = f1c - df;
+                            if (hi != 1) atomicAdd(pv + o, hi - 1);           // v[x] += dv; only this thread touches x in this pass
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        if (want_obs) {
+            // integer sums over f: sum f^2 (action), sum (d f)^2 (winding), sum f_mu = sum m_mu (wrapping)
+            long long f2 = 0, df2 = 0;
+            int w0 = 0, w1 = 0;
+#pragma unroll
+            for (int i4 = tid; i4 < V / 4; i4 += T) {
+                const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+                const int4 a0 = *reinterpret_cast<const int4*>(F0 + i), a1 = *reinterpret_cast<const int4*>(F1 + i);
+                const int4 d1 = *reinterpret_cast<const int4*>(F1 + ((x0 + 1) & (N - 1)) * N + x1);     // f_1[x + e0]
+                const int r0 = F0[x0 * N + ((x1 + 4) & (N - 1))];                                        // f_0[x + e1] of the last
+                f2 += (long long)a0.x * a0.x + (long long)a0.y * a0.y + (long long)a0.z * a0.z + (long long)a0.w * a0.w;
+                f2 += (long long)a1.x * a1.x + (long long)a1.y * a1.y + (long long)a1.z * a1.z + (long long)a1.w * a1.w;
+                // (d f)[x] = (f_1[x+e0] - f_1[x]) - (f_0[x+e1] - f_0[x])      (compact.py d,1 rows)
+                const int c0 = (d1.x - a1.x) - (a0.y - a0.x), c1 = (d1.y - a1.y) - (a0.z - a0.y);
+                const int c2 = (d1.z - a1.z) - (a0.w - a0.z), c3 = (d1.w - a1.w) - (r0 - a0.w);
+                df2 += (long long)c0 * c0 + (long long)c1 * c1 + (long long)c2 * c2 + (long long)c3 * c3;
+                w0 += a0.x + a0.y + a0.z + a0.w;
+                w1 += a1.x + a1.y + a1.z + a1.w;
+            }
+            f2 = warp_sum(f2);
+            df2 = warp_sum(df2);
+            w0 = __reduce_add_sync(0xffffffffu, w0);
+            w1 = __reduce_add_sync(0xffffffffu, w1);
+            n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum_A += __shfl_xor_sync(0xffffffffu, sum_A, off);
+            if (lane == 0) {
+                long long* slot = red + 4 * warp;
+                slot[0] = f2; slot[1] = df2; slot[2] = ((long long)w0 << 32) | (unsigned)w1; slot[3] = n_acc;
+                redA[warp] = sum_A;
+            }
+            __syncthreads();           // every warp has read f; the slots are written
+            if (tid == kWriter) {
+                long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                double tA = 0.0;
+                for (int w = 0; w < NW; ++w) {
+                    t0 += red[4 * w]; t1 += red[4 * w + 1];
+                    t2 += red[4 * w + 2] >> 32; t3 += (int)(red[4 * w + 2] & 0xFFFFFFFFLL);
+                    t4 += red[4 * w + 3];
+                    tA += (double)redA[w];
+                }
+                double* o = a.obs + chain * SVB_WOBS_COUNT;
+                o[SVB_WOBS_SUM_F2] = (double)t0;
+                o[SVB_WOBS_SUM_DF2] = (double)t1;
+                o[SVB_WOBS_WRAP0] = (double)t2;
+                o[SVB_WOBS_WRAP1] = (double)t3;
+                o[SVB_WOBS_ACCEPTED] = (double)t4;
+                o[SVB_WOBS_ACCEPTANCE] = tA;
+                o[SVB_WOBS_DELTA_M_ABS] = -1.0;       // not evaluated by the sweep (the move preserves delta m identically)
+            }
+        }
+
+        // ---- f -> m = f + delta v with the final v, in place ----
+#pragma unroll
+        for (int i4 = tid; i4 < V / 4; i4 += T) {
+            const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+            const int4 vc = *reinterpret_cast<const int4*>(sv + i);
+            const int4 vu = *reinterpret_cast<const int4*>(sv + ((x0 - 1) & (N - 1)) * N + x1);
+            const int vl = sv[x0 * N + ((x1 - 1) & (N - 1))];
+            int4 m0 = *reinterpret_cast<int4*>(F0 + i), m1 = *reinterpret_cast<int4*>(F1 + i);
+            m0.x += vc.x - vl;   m0.y += vc.y - vc.x; m0.z += vc.z - vc.y; m0.w += vc.w - vc.z;
+            m1.x += vu.x - vc.x; m1.y += vu.y - vc.y; m1.z += vu.z - vc.z; m1.w += vu.w - vc.w;
+            *reinterpret_cast<int4*>(F0 + i) = m0;
+            *reinterpret_cast<int4*>(F1 + i) = m1;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(a.m + chain * 2 * V, F0, bytes_m);
+            bulk_s2g(a.v + chain * V, sv, bytes_v);
+            bulk_commit();
+            bulk_wait_read0();
+            if (next < a.chains) issue_load(next, seen_next);
+        }
+    }
+    if (tid == 0) bulk_wait0();
+    if (OVERLAP) {
+        __syncthreads();                                   // every store has completed, every record is written
+        if (warp == 0) overlap_publish_all(a.ov, lane, it, blockIdx.x, gridDim.x);
+    }
+}
+
+template <int NT, int MINB>
+static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, int sm_count) {
+    const bool overlap = a.ov.epochs != nullptr;
+    auto kern = overlap ? worldline_smem_table_kernel<NT, MINB, true> : worldline_smem_table_kernel<NT, MINB, false>;
+    const size_t smem = (size_t)NT * NT * 3 * sizeof(int32_t) + kWlTableSize * sizeof(WlTableEntry) + 4 * 32 * sizeof(long long) +
+                        32 * sizeof(float) + 16;
+    static int per_sm_cache[2] = {0, 0};
+    int per_sm = per_sm_cache[overlap ? 1 : 0];
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "worldline table kernel does not fit an SM at N=%d", NT);
+        per_sm_cache[overlap ? 1 : 0] = per_sm;
+    }
+    long long grid = (long long)per_sm * sm_count;
+    if (grid > a.chains) grid = a.chains;
+    if (overlap) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+        return 0;
+    }
+    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -181,7 +181,9 @@ class BatchedEnsemble:
                 overlapped = None
         scratch = torch.empty((self.chains, nobs), dtype=torch.float64, device=self.device) if overlapped is not None else None
         for k in progress(range(steps), desc='Generation'):
-            if overlapped is not None:
+            if overlapped is not None and getattr(overlapped, 'complete_records', False):
+                overlapped(sweeps_per_step, obs=record[k])
+            elif overlapped is not None:
                 # the state columns of draw k - 1 ride along with launch k (they describe the chains as they arrive);
                 # launch k's own counters go to row k
                 overlapped(sweeps_per_step, obs=record[k], obs_in=record[k - 1] if k else scratch)
@@ -189,7 +191,7 @@ class BatchedEnsemble:
                 generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
             if keep_every and (k + 1) % keep_every == 0:
                 kept.append((a.cpu().numpy(), b.cpu().numpy()))          # reads only: stream order suffices
-        if overlapped is not None and steps:
+        if overlapped is not None and steps and not getattr(overlapped, 'complete_records', False):
             last = ops.villain_observables(a, b, self.Action.kappa, kappa_chain=kappa_chain)     # the final state's columns
             record[steps - 1, :, :4] = last[:, :4]
         self.record = record.cpu().numpy().transpose(1, 0, 2)          # (chains, steps, nobs): ONE D2H

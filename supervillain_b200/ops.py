@@ -202,6 +202,43 @@ class VillainOverlappedSweeps:
         self.fenced = False
 
 
+class WorldlineOverlappedSweeps:
+    """Back-to-back Philox PlaquetteUpdate sweeps (mode 'joint', W = 1) of ONE chain set as overlapped launches
+    (svb_worldline_sweep_overlapped); the protocol and the `fence()` rule are those of `VillainOverlappedSweeps`."""
+
+    def __init__(self, m, v, kappa, *, seed=0, chain0=0, kappa_chain=None):
+        self.lib = _lib.load()
+        self.chains, self.N = _fields_shape(m, 'm', 2)
+        if self.N not in OVERLAP_SIZES:
+            raise NotImplementedError('overlapped sweeps need N in (16, 32, 64)')
+        self.p_m = _dev(m, 'm', (torch.int32,))
+        self.p_v = _dev(v, 'v', (torch.int32,), (self.chains, 1, self.N, self.N))
+        self.p_kc = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (self.chains,))
+        self.kappa = float(kappa)
+        self.seed, self.chain0 = int(seed) & (2**64 - 1), int(chain0)
+        self.epochs = torch.zeros((self.chains,), dtype=torch.int32, device=m.device)
+        self.p_epochs = self.epochs.data_ptr()
+        self.epoch = 0
+        self.fenced = True
+        self._keep = (m, v, kappa_chain)
+        self._fn = self.lib.svb_worldline_sweep_overlapped
+        self._stream = torch.cuda.current_stream
+
+    def fence(self):
+        self.fenced = True
+
+    def step(self, sweep0, n_sweeps=1, obs=None):
+        p_obs = None if obs is None else _dev(obs, 'obs', (torch.float64,), (self.chains, WOBS_COUNT))
+        e = self.epoch
+        code = self._fn(self.p_m, self.p_v, self.chains, self.N, self.kappa, self.p_kc, int(n_sweeps), self.seed, int(sweep0),
+                        self.chain0, p_obs, self.p_epochs, e & 0xFFFFFFFF, (e + 1) & 0xFFFFFFFF,
+                        0 if self.fenced else _lib.OVERLAP_PREDECESSOR, self._stream().cuda_stream)
+        if code:
+            _lib.check(code)
+        self.epoch = e + 1
+        self.fenced = False
+
+
 def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
     """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
     lib = _lib.load()

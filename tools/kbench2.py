@@ -41,6 +41,13 @@ if 'c3' in which:
             m, v = sets[k[0] % 6]; k[0] += 1
             ops.worldline_sweep(m, v, 0.5, mode=mode, seed=1, sweep0=k[0], obs=obs)
         report(f'worldline {mode} L=64 x 1024 chains (C3 shard), smem path', CH * N * N, 24, timeit(f))
+    obs6 = [torch.zeros_like(obs) for _ in range(6)]
+    steppers = [ops.WorldlineOverlappedSweeps(m, v, 0.5, seed=1) for m, v in sets]
+    k = [0]
+    def g():
+        i = k[0] % 6; k[0] += 1
+        steppers[i].step(k[0], 1, obs6[i])
+    report('worldline joint L=64 x 1024 chains (C3 shard), overlapped launches', CH * N * N, 24, timeit(g, n=60))
 if 'c4' in which:
     N, CH = 128, 1024                                   # 1/8 of a GPU's C4 shard; 256 MiB of state
     S = svb.Villain(svb.Lattice2D(N), 0.5)
