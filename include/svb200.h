@@ -177,6 +177,29 @@ int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N,
                                  int flags, void* stream);
 
 /*
+ * The decoupled Villain updates: SiteUpdate.step (generator/villain/site.py:43-120: phi alone, checkerboard),
+ * LinkUpdate.step (link.py:53-101: every n independently against the frozen phi) and ExactUpdate.step
+ * (exact.py:50-129: n += d z, z on one colour at a time), IN PLACE, fp64 phi, STRICT arithmetic.
+ *  interval_phi   SITE: dphi ~ uniform(-interval_phi, +interval_phi)
+ *  interval       LINK: dn in W * ([-interval, interval] \ {0});  EXACT: z in [-interval, interval] \ {0}
+ *  injected       inj_u (n_sweeps, chains, N, N) f64 (LINK: (n_sweeps, chains, 2, N, N));
+ *                 SITE: inj_dphi (n_sweeps, chains, N, N) f64;  LINK: inj_a (n_sweeps, chains, 2, N, N) i32 = the
+ *                 proposed change, already times W;  EXACT: inj_a (n_sweeps, chains, N, N) i32 = z
+ *  obs            optional (chains, SVB_VOBS_COUNT): state after the last sweep + ACCEPTED / ACCEPTANCE of the call
+ *  accept_mask / dS_out   optional, last sweep, shaped like inj_u (no accept_mask for LINK)
+ */
+#define SVB_VU_SITE  0
+#define SVB_VU_LINK  1
+#define SVB_VU_EXACT 2
+int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t chains, int N,
+                          double kappa, const double* kappa_chain, int W,
+                          double interval_phi, int interval,
+                          int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                          int rng_mode, int path,
+                          const double* inj_u, const double* inj_dphi, const int32_t* inj_a,
+                          double* obs, uint8_t* accept_mask, double* dS_out, void* stream);
+
+/*
  * The same sweep with HOST buffers: the reference's `step(cfg)` contract (host arrays in, host arrays out,
  * neighborhood.py:59-137) for a whole batch.  phi_host / n_host / obs_host are pinned HOST buffers updated in place;
  * phi_dev / n_dev / obs_dev are caller-owned DEVICE staging buffers of the same shapes.  The chains are processed in

@@ -18,6 +18,8 @@ STREAM_VILLAIN_NEIGHBORHOOD = 1
 STREAM_WORLDLINE_PLAQUETTE = 2
 STREAM_VILLAIN_REFINE = 4
 STREAM_WORLDLINE_REFINE = 5
+STREAM_VILLAIN_LINK = 6
+STREAM_VILLAIN_LINK_REFINE = 7
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -118,3 +120,41 @@ def worldline_draws(seed, chain, sweep, N, mode, interval=1):
     frac = (e.astype(np.float64) + 0.5) * TWO_M32
     u = np.minimum((f.astype(np.float64) + frac) * TWO_M32, 1.0 - 2.0 ** -53)
     return {'u': u.reshape(N, N), 'a': a.reshape(N, N), 'b': b.reshape(N, N)}
+
+
+def _lazy_uniform(f, e):
+    frac = (e.astype(np.float64) + 0.5) * TWO_M32
+    return np.minimum((f.astype(np.float64) + frac) * TWO_M32, 1.0 - 2.0 ** -53)
+
+
+def _nonzero_choice(idx, interval):
+    return np.where(idx < interval, idx - interval, idx - interval + 1)
+
+
+def villain_exact_draws(seed, chain, sweep, N, interval_z=1):
+    """ExactUpdate on the GPU: the site's pair block as in villain_draws; word B picks z among the 2 I nonzero values
+    (p = (2 I) B, index = p >> 32) and the remainder leads the uniform (refined from STREAM_VILLAIN_REFINE)."""
+    x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
+    c0 = ((x0 & ~8) * N + x1).astype(np.uint64)
+    half = ((x0 >> 3) & 1).astype(bool)
+    w = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD)
+    r = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE)
+    B = np.where(half, w[3], w[1])
+    e = np.where(half, r[2], r[0])
+    p = B * np.uint64(2 * interval_z)
+    z = _nonzero_choice((p >> np.uint64(32)).astype(np.int64), interval_z)
+    return {'u': _lazy_uniform(p & MASK32, e).reshape(N, N), 'a': z.reshape(N, N)}
+
+
+def villain_link_draws(seed, chain, sweep, N, W=1, interval_n=1):
+    """LinkUpdate on the GPU: block with counter word 0 = site index in STREAM_VILLAIN_LINK, word mu for link (mu, x):
+    p = (2 I) w, change = W * nonzero[p >> 32], remainder -> uniform (refined from STREAM_VILLAIN_LINK_REFINE, word mu)."""
+    site = np.arange(N * N, dtype=np.uint64)
+    w = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_LINK)
+    r = philox_site(seed, chain, sweep, site, STREAM_VILLAIN_LINK_REFINE)
+    us, cs = [], []
+    for mu in range(2):
+        p = w[mu] * np.uint64(2 * interval_n)
+        cs.append(W * _nonzero_choice((p >> np.uint64(32)).astype(np.int64), interval_n))
+        us.append(_lazy_uniform(p & MASK32, r[mu]))
+    return {'u': np.stack(us).reshape(2, N, N), 'a': np.stack(cs).reshape(2, N, N)}

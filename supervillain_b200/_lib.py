@@ -20,6 +20,7 @@ WL_JOINT, WL_VORTEX, WL_COEXACT = 0, 1, 2
 OP_D, OP_DELTA, OP_FACE_SUM, OP_COFACE_SUM = 0, 1, 2, 3
 CORR_SPIN, CORR_WINDING, CORR_VORTEX = 0, 1, 2
 OVERLAP_PREDECESSOR = 1
+VU_SITE, VU_LINK, VU_EXACT = 0, 1, 2
 
 E_NULL, E_SHAPE, E_DTYPE, E_PARAM, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4, -5, -6
 
@@ -32,6 +33,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp,
                                           ctypes.c_uint32, ctypes.c_uint32, _i, _vp]),
+    'svb_villain_decoupled': (_i, [_i, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'svb_villain_observables': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),

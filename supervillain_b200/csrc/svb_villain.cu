@@ -59,6 +59,9 @@ struct VillainArgs {
     double* obs;
     uint8_t* accept_mask;
     double* dS_out;
+    // ExactUpdate as a mode of the site kernels (svb_villain_decoupled): proposals are (dphi = 0, dn = d z restricted to x)
+    int exact_mode;
+    const int32_t* inj_z;
     // overlapped launches (svb_villain_sweep_overlapped); epochs == nullptr otherwise
     double* obs_in;
     uint32_t* epochs;
@@ -351,17 +354,37 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
         const long long lbase = ((long long)sweep * a.chains + chain) * 2 * V + site;
         VillainDraw d;
         d.u = a.inj_u[base];
-        d.dphi = a.inj_dphi[base];
-        d.dg[0] = a.inj_dn_fwd[lbase];
-        d.dg[1] = a.inj_dn_bwd[lbase];
-        d.dg[2] = a.inj_dn_fwd[lbase + V];
-        d.dg[3] = a.inj_dn_bwd[lbase + V];
         d.f = 0; d.c0 = 0; d.half = 0;
+        if (a.exact_mode) {
+            // ExactUpdate (exact.py:94-102): z on the proposing site alone, n += d z: forward links -z, backward links +z
+            const int z = a.inj_z[base];
+            d.dphi = 0.0;
+            d.dg[0] = -z; d.dg[1] = z; d.dg[2] = -z; d.dg[3] = z;
+            return d;
+        }
+        d.dphi = a.inj_dphi[base];
+        d.dg[0] = a.inj_dn_fwd ? a.inj_dn_fwd[lbase] : 0;          // SiteUpdate: no dn proposals at all
+        d.dg[1] = a.inj_dn_bwd ? a.inj_dn_bwd[lbase] : 0;
+        d.dg[2] = a.inj_dn_fwd ? a.inj_dn_fwd[lbase + V] : 0;
+        d.dg[3] = a.inj_dn_bwd ? a.inj_dn_bwd[lbase + V] : 0;
         return d;
     } else {
         const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
         const uint32_t c0 = villain_pair_counter(x0, x1, a.N), half = villain_pair_half(x0);
         const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, c0) : philox_site(a.seed, gc, gs, c0, STREAM_VILLAIN_NEIGHBORHOOD);
+        if (a.exact_mode) {
+            // word B: z = one of the 2 I nonzero values (exact.py:38, :94), the remainder leads the uniform; word A unused
+            const uint64_t pz = (uint64_t)(half ? p.w : p.y) * (uint64_t)(2 * a.interval_n);
+            const int idx = (int)(pz >> 32);
+            const int z = (idx < a.interval_n) ? idx - a.interval_n : idx - a.interval_n + 1;
+            VillainDraw d;
+            d.dphi = 0.0;
+            d.dg[0] = -z; d.dg[1] = z; d.dg[2] = -z; d.dg[3] = z;
+            d.f = (uint32_t)pz;
+            d.u = (__hiloint2double(0x43300000, (int)d.f) - 4503599627370495.5) * 2.3283064365386963e-10;
+            d.c0 = c0; d.half = half;
+            return d;
+        }
         VillainDraw d = villain_draw_from_words(half ? p.z : p.x, half ? p.w : p.y, a.interval_phi, a.interval_n);
         d.c0 = c0; d.half = half;
         if (dg_scale != 1) {
@@ -381,7 +404,11 @@ __device__ __forceinline__ RefineCtx villain_refine_ctx(const VillainArgs& a, lo
 // (unit, c, dg_scale) for a launch: FAST Philox keeps dg in units of W; everything else folds W into dg
 template <bool INJECTED, bool STRICT>
 __device__ __forceinline__ void villain_consts(const VillainArgs& a, VillainConsts& k, int& dg_scale) {
-    if (!INJECTED && !STRICT) {
+    if (a.exact_mode) {
+        k.unit = 1;
+        k.c = SVB_TWO_PI;
+        dg_scale = 1;
+    } else if (!INJECTED && !STRICT) {
         k.unit = a.W;
         k.c = SVB_TWO_PI * (double)a.W;
         dg_scale = 1;
@@ -1307,6 +1334,86 @@ __global__ void villain_draws_kernel(long long chains, int N, int W, double inte
 }
 
 // ------------------------------------------------------------------------------------------
+// LinkUpdate (supervillain/generator/villain/link.py:53-101): every link independently against the frozen phi,
+//   change = W * choice([-I..-1, 1..I]);  dS = ((-2 pi) kappa change) ((dphi - (2 pi) n) - pi change);  n += change if u < e^-dS.
+// One thread per link; STRICT arithmetic (one rounding per numpy operation).  Philox draws: the block with counter word 0 =
+// site index in stream STREAM_VILLAIN_LINK, word mu for link (mu, x): p = (2 I) w, choice index = p >> 32, the remainder
+// leads the lazily refined uniform (stream STREAM_VILLAIN_LINK_REFINE).
+// ------------------------------------------------------------------------------------------
+struct LinkArgs {
+    const double* phi;
+    int32_t* n;
+    long long chains;
+    int N;
+    double kappa;
+    const double* kappa_chain;
+    int W, interval;
+    unsigned long long seed, sweep, chain0;
+    const double* inj_u;        // (chains, 2, N, N)
+    const int32_t* inj_c;       // (chains, 2, N, N), already times W
+    double* obs;                // ACCEPTED / ACCEPTANCE accumulate here (atomics)
+    double* dS_out;             // (chains, 2, N, N)
+};
+
+template <bool INJECTED>
+__global__ void __launch_bounds__(256) villain_link_kernel(LinkArgs a) {
+    __shared__ double scratch[2 * 32];
+    const int N = a.N, V = N * N;
+    const int blocks_per_chain = (2 * V + 255) / 256;
+    const long long chain = blockIdx.x / blocks_per_chain;
+    const int l = (blockIdx.x - (int)(chain * blocks_per_chain)) * 256 + threadIdx.x;
+    double acc_n = 0.0, acc_A = 0.0;
+    if (l < 2 * V) {
+        const int mu = l / V, site = l - mu * V;
+        const int x0 = site / N, x1 = site - x0 * N;
+        const int head = (mu == 0) ? ((x0 + 1 == N ? 0 : x0 + 1) * N + x1) : (x0 * N + (x1 + 1 == N ? 0 : x1 + 1));
+        const double* gphi = a.phi + chain * V;
+        int32_t* gn = a.n + chain * 2 * V;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double dphi = __dsub_rn(gphi[head], gphi[site]);                          // d(phi)   (link.py:74)
+        int c;
+        double u = 0.0;
+        LazyUniform lu;
+        lu.f = 0; lu.c0 = (uint32_t)site; lu.word = (uint32_t)mu;
+        if (INJECTED) {
+            c = a.inj_c[chain * 2 * V + l];
+            u = a.inj_u[chain * 2 * V + l];
+        } else {
+            const Philox4 p = philox_site(a.seed, a.chain0 + (unsigned long long)chain, a.sweep, (uint32_t)site, STREAM_VILLAIN_LINK);
+            const uint64_t pz = (uint64_t)(mu ? p.y : p.x) * (uint64_t)(2 * a.interval);
+            const int idx = (int)(pz >> 32);
+            c = a.W * ((idx < a.interval) ? idx - a.interval : idx - a.interval + 1);
+            lu.f = (uint32_t)pz;
+        }
+        const int nl = gn[l];
+        // dS = -2 pi kappa change (dphi - 2 pi n - pi change), numpy's left-to-right order   (link.py:83-86)
+        const double t1 = __dmul_rn(__dmul_rn(-SVB_TWO_PI, kappa), (double)c);
+        const double t2 = __dsub_rn(__dsub_rn(dphi, __dmul_rn(SVB_TWO_PI, (double)nl)), __dmul_rn(3.141592653589793116, (double)c));
+        const double dS = __dmul_rn(t1, t2);
+        const double A = exp_clipped(-dS);
+        bool ok;
+        if (INJECTED) ok = u < A;
+        else {
+            RefineCtx rc;
+            rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain; rc.sweep = a.sweep;
+            ok = decide_lazy(A, lu, STREAM_VILLAIN_LINK_REFINE, rc);
+        }
+        if (ok) gn[l] = nl + c;
+        if (a.dS_out) a.dS_out[chain * 2 * V + l] = dS;
+        acc_n = ok ? 1.0 : 0.0;
+        acc_A = A;
+    }
+    if (a.obs) {
+        double s[2] = {acc_n, acc_A};
+        block_sum<2>(s, scratch);
+        if (threadIdx.x == 0) {
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, s[0]);
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, s[1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static size_t villain_smem_bytes(int N, size_t real_size) {
@@ -1422,7 +1529,7 @@ template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
 #ifndef SVB_NO_FILTERED_KERNEL
-    if (!INJECTED && !STRICT && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out) {
+    if (!INJECTED && !STRICT && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out && !a.exact_mode) {
         // production path: fp32-filtered decisions on resident fp32 residuals (svb_villain_filtered.cuh)
         switch (a.N) {
             case 16: return launch_villain_filtered<16, 16, 1>(a, stream, info);
@@ -1432,7 +1539,7 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
         }
     }
 #endif
-    if (!INJECTED && aligned && sizeof(real) == 8) {
+    if (!INJECTED && aligned && sizeof(real) == 8 && !a.exact_mode) {
         // One sweep per launch in FAST arithmetic: recomputing the residuals is as cheap as building the resident copy,
         // and the two-stage pipeline hides the loads (52.0 vs 53.5 us at config 2).  Fused sweeps, and STRICT
         // arithmetic always (bit-exact dS), keep the residuals resident (34.9 vs 38.3 us per sweep).
@@ -1559,7 +1666,7 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
     }
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
-    a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    a.exact_mode = 0; a.inj_z = nullptr; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (phi_dtype == SVB_F64) return dispatch_villain<double>(a, rng_mode, arith_mode, path, st);
     return dispatch_villain<float>(a, rng_mode, arith_mode, path, st);
@@ -1590,6 +1697,7 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
     }
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.exact_mode = 0; a.inj_z = nullptr;
     a.obs_in = obs_in; a.epochs = epochs; a.wait_epoch = wait_epoch; a.signal_epoch = signal_epoch;
     a.grid_wait = (flags & SVB_OVERLAP_PREDECESSOR) ? 0 : 1;
     DeviceInfo info;
@@ -1601,6 +1709,74 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
         default: return launch_villain_filtered<64, 2, 1>(a, st, info);
     }
+}
+
+// SiteUpdate, LinkUpdate, ExactUpdate (generator/villain/{site,link,exact}.py): see include/svb200.h
+extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                     int W, double interval_phi, int interval, int n_sweeps, uint64_t seed, uint64_t sweep0,
+                                     uint64_t chain0, int rng_mode, int path, const double* inj_u, const double* inj_dphi,
+                                     const int32_t* inj_a, double* obs, uint8_t* accept_mask, double* dS_out, void* stream) {
+    if (kind < SVB_VU_SITE || kind > SVB_VU_EXACT) return fail(SVB_E_PARAM, "svb_villain_decoupled: kind %d", kind);
+    if (!phi || !n) return fail(SVB_E_NULL, "svb_villain_decoupled: phi and n are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_villain_decoupled: chains=%lld N=%d", (long long)chains, N);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_decoupled: kappa must be positive");
+    if (W < 1) return fail(SVB_E_PARAM, "svb_villain_decoupled: W must be a finite integer >= 1 (got %d)", W);
+    if (kind != SVB_VU_SITE && (interval < 1 || interval > 1024)) return fail(SVB_E_PARAM, "svb_villain_decoupled: interval");
+    if (kind == SVB_VU_SITE && !(interval_phi >= 0)) return fail(SVB_E_PARAM, "svb_villain_decoupled: interval_phi must be >= 0");
+    if (n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_decoupled: n_sweeps < 0");
+    if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_villain_decoupled: rng_mode");
+    if (rng_mode == SVB_RNG_INJECTED && (!inj_u || (kind == SVB_VU_SITE ? !inj_dphi : !inj_a)))
+        return fail(SVB_E_NULL, "svb_villain_decoupled: injected mode needs inj_u and inj_dphi (SITE) or inj_a (LINK, EXACT)");
+    if (path < SVB_PATH_AUTO || path > SVB_PATH_GLOBAL) return fail(SVB_E_PARAM, "svb_villain_decoupled: path");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    if (kind == SVB_VU_LINK) {
+        if (accept_mask) return fail(SVB_E_UNSUPPORTED, "svb_villain_decoupled: no accept_mask for LINK");
+        const long long V = (long long)N * N;
+        const long long blocks = chains * ((2 * V + 255) / 256);
+        if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_decoupled: too many blocks");
+        if (obs) {
+            villain_zero_counters_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+        LinkArgs a;
+        a.phi = reinterpret_cast<const double*>(phi); a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain;
+        a.W = W; a.interval = interval; a.seed = seed; a.chain0 = chain0; a.obs = obs;
+        for (int s = 0; s < n_sweeps; ++s) {
+            a.sweep = sweep0 + (uint64_t)s;
+            a.dS_out = (s == n_sweeps - 1) ? dS_out : nullptr;
+            if (rng_mode == SVB_RNG_INJECTED) {
+                a.inj_u = inj_u + (long long)s * chains * 2 * V;
+                a.inj_c = inj_a + (long long)s * chains * 2 * V;
+                villain_link_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+            } else {
+                a.inj_u = nullptr; a.inj_c = nullptr;
+                villain_link_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+            }
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+        if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
+        return SVB_OK;
+    }
+
+    // SITE = the neighbourhood move with no dn proposals; EXACT = the site kernels with (dphi = 0, dn = d z) proposals.
+    // STRICT arithmetic: fp64, one rounding per numpy operation.
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = (kind == SVB_VU_SITE) ? interval_phi : 0.0;
+    a.interval_n = (kind == SVB_VU_SITE) ? 0 : interval;
+    a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
+    a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
+    a.exact_mode = (kind == SVB_VU_EXACT) ? 1 : 0;
+    a.inj_z = inj_a;
+    a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    return dispatch_villain<double>(a, rng_mode, SVB_ARITH_STRICT, path, st);
 }
 
 extern "C" int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n, int64_t chains, int N, double kappa,
@@ -1695,7 +1871,7 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     }
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
-    a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    a.exact_mode = 0; a.inj_z = nullptr; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // An even number of ping-pong sweeps ends in (phi, n).  An odd count would end in the workspace, so the last sweep of
     // an odd count is done in place by the per-colour global path instead (cheaper than copying the state back).

@@ -55,3 +55,31 @@ def worldline_wrapping(rng, lattice, interval=1):
     c = np.stack([rng.choice(ws, N), rng.choice(ws, N)]).astype(np.int32)
     u = np.stack([rng.uniform(0, 1, N), rng.uniform(0, 1, N)])
     return u, c
+
+
+def villain_site(rng, lattice, interval_phi):
+    """One SiteUpdate sweep's draws (site.py:66, :89): the uniforms, then per colour the dphi."""
+    N = lattice.N
+    u = rng.uniform(0, 1, (N,) * 2)
+    dphi = np.zeros((N, N))
+    for color in lattice.checkerboarding:
+        dphi[color] = rng.uniform(-interval_phi, +interval_phi, len(color[0]))
+    return u, dphi
+
+
+def villain_link(rng, lattice, W, interval_n):
+    """One LinkUpdate sweep's draws (link.py:77, :92): the changes of the whole 1-form, then the uniforms."""
+    N = lattice.N
+    c = (W * rng.choice(_nonzero_choices(interval_n), size=(2, N, N))).astype(np.int32)
+    u = rng.uniform(0, 1, size=(2, N, N))
+    return u, c
+
+
+def villain_exact(rng, lattice, interval_z):
+    """One ExactUpdate sweep's draws (exact.py:75, :94): the uniforms, then per colour z."""
+    N = lattice.N
+    u = rng.uniform(0, 1, (N,) * 2)
+    z = np.zeros((N, N), dtype=np.int32)
+    for color in lattice.checkerboarding:
+        z[color] = rng.choice(_nonzero_choices(interval_z), len(color[0]))
+    return u, z

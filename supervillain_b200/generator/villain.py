@@ -178,3 +178,146 @@ class NeighborhoodUpdate(Generator):
             + '\n' +
             f'    {self.acceptance / self.sweeps:.6f} average Metropolis acceptance probability.'
         )
+
+
+class _DecoupledVillain(Generator):
+    """Shared machinery of SiteUpdate / LinkUpdate / ExactUpdate on the GPU (svb_villain_decoupled)."""
+    kind = None
+    noun = None
+
+    def _init(self, action, seed, path):
+        if not _is_villain(action):
+            raise ValueError(self._wrong_action)
+        self.Action = action
+        self.Lattice = action.Lattice
+        self.kappa = action.kappa
+        self.rng = None
+        self.seed = fresh_seed() if seed is None else int(seed)
+        self.counter = 0
+        self.path = path
+        self.accepted = 0
+        self.proposed = 0
+        self.acceptance = 0.
+        self.sweeps = 0
+
+    def _per_sweep(self):
+        return self.Lattice.sites * (2 if self.kind == 'link' else 1)
+
+    def _interval(self):
+        return 1
+
+    def sweep_device(self, phi, n, n_sweeps=1, *, obs=None, chain0=0, kappa_chain=None, injected=None, accept_mask=None,
+                     dS_out=None):
+        ops.villain_decoupled(self.kind, phi, n, self.kappa, W=self.Action.W, interval_phi=getattr(self, 'interval_phi', np.pi),
+                              interval=self._interval(), n_sweeps=n_sweeps, seed=self.seed, sweep0=self.counter, chain0=chain0,
+                              injected=injected, path=self.path, kappa_chain=kappa_chain, obs=obs, accept_mask=accept_mask,
+                              dS_out=dS_out)
+        if injected is None:
+            self.counter += n_sweeps
+
+    def _count(self, rec, chains, n_sweeps):
+        self.sweeps += n_sweeps * chains
+        self.proposed += self._per_sweep() * n_sweeps * chains
+        self.accepted += int(round(float(rec[:, VOBS_ACCEPTED].sum())))
+        self.acceptance += float(rec[:, VOBS_ACCEPTANCE].sum()) / self._per_sweep()
+
+    def step(self, cfg, n_sweeps=1):
+        N = self.Lattice.N
+        phi, single = to_device(cfg['phi'], torch.float64, 1, N)
+        n, _ = to_device(cfg['n'], torch.int32, 2, N)
+        if isinstance(cfg['phi'], torch.Tensor):
+            phi, n = phi.clone(), n.clone()
+        chains = phi.shape[0]
+        injected = self._injected_draws(chains, n_sweeps) if self.rng is not None else None
+        obs = torch.empty((chains, VOBS_COUNT), dtype=torch.float64, device=phi.device)
+        self.sweep_device(phi, n, n_sweeps, obs=obs, injected=injected)
+        self._count(obs.cpu().numpy(), chains, n_sweeps)
+        L = self.Lattice
+        result = {}
+        if self.kind == 'site':
+            out = phi.cpu().numpy()
+            result['phi'] = Form(out[0], degree=0, lattice=L) if single else out
+        else:
+            out = n.cpu().numpy().astype(np.int64)
+            result['n'] = Form(out[0], degree=1, lattice=L) if single else out
+        return cfg | result
+
+    def inline_observables(self, steps):
+        return {}
+
+    def report(self):
+        return (
+            f'There were {self.accepted} {self.noun} proposals accepted of {self.proposed} proposed updates.'
+            + '\n' +
+            f'    {self.accepted/self.proposed:.6f} acceptance rate'
+            + '\n' +
+            f'    {self.acceptance / self.sweeps:.6f} average Metropolis acceptance probability.'
+        )
+
+
+class SiteUpdate(_DecoupledVillain):
+    """Checkerboard Metropolis on phi alone; drop-in for supervillain.generator.villain.SiteUpdate (site.py:12-132)."""
+    kind, noun, _wrong_action = 'site', 'single-phi', 'Need a Villain action'
+
+    def __init__(self, action, interval_phi=np.pi, *, seed=None, path='auto'):
+        self._init(action, seed, path)
+        self.interval_phi = interval_phi
+
+    def __str__(self):
+        return 'SiteUpdate'
+
+    def _injected_draws(self, chains, n_sweeps):
+        N = self.Lattice.N
+        u = np.empty((n_sweeps, chains, N, N)); dphi = np.empty_like(u)
+        for c in range(chains):
+            for s in range(n_sweeps):
+                u[s, c], dphi[s, c] = _replay.villain_site(self.rng, self.Lattice, self.interval_phi)
+        return {'u': torch.from_numpy(u).cuda(), 'dphi': torch.from_numpy(dphi).cuda()}
+
+
+class LinkUpdate(_DecoupledVillain):
+    """Every n independently against the frozen phi; drop-in for supervillain.generator.villain.LinkUpdate (link.py:12-114)."""
+    kind, noun, _wrong_action = 'link', 'single-link', 'The LinkUpdate requires the Villain action.'
+
+    def __init__(self, action, interval_n=1, *, seed=None, path='auto'):
+        self._init(action, seed, path)
+        self.interval_n = interval_n
+        self.n_changes = tuple(n for n in range(-interval_n, 0)) + tuple(n for n in range(1, interval_n + 1))
+
+    def __str__(self):
+        return 'LinkUpdate'
+
+    def _interval(self):
+        return self.interval_n
+
+    def _injected_draws(self, chains, n_sweeps):
+        N = self.Lattice.N
+        u = np.empty((n_sweeps, chains, 2, N, N)); a = np.empty((n_sweeps, chains, 2, N, N), dtype=np.int32)
+        for c in range(chains):
+            for s in range(n_sweeps):
+                u[s, c], a[s, c] = _replay.villain_link(self.rng, self.Lattice, self.Action.W, self.interval_n)
+        return {'u': torch.from_numpy(u).cuda(), 'a': torch.from_numpy(a).cuda()}
+
+
+class ExactUpdate(_DecoupledVillain):
+    """n += d z, z on one colour at a time; drop-in for supervillain.generator.villain.ExactUpdate (exact.py:12-141)."""
+    kind, noun, _wrong_action = 'exact', 'exact', 'Need a Villain action'
+
+    def __init__(self, action, interval_z=1, *, seed=None, path='auto'):
+        self._init(action, seed, path)
+        self.interval_z = interval_z
+        self.zs = tuple(z for z in range(-interval_z, 0)) + tuple(z for z in range(1, interval_z + 1))
+
+    def __str__(self):
+        return 'ExactUpdate'
+
+    def _interval(self):
+        return self.interval_z
+
+    def _injected_draws(self, chains, n_sweeps):
+        N = self.Lattice.N
+        u = np.empty((n_sweeps, chains, N, N)); a = np.empty((n_sweeps, chains, N, N), dtype=np.int32)
+        for c in range(chains):
+            for s in range(n_sweeps):
+                u[s, c], a[s, c] = _replay.villain_exact(self.rng, self.Lattice, self.interval_z)
+        return {'u': torch.from_numpy(u).cuda(), 'a': torch.from_numpy(a).cuda()}

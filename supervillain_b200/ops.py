@@ -239,6 +239,38 @@ class WorldlineOverlappedSweeps:
         self.fenced = False
 
 
+_VU_KINDS = {'site': _lib.VU_SITE, 'link': _lib.VU_LINK, 'exact': _lib.VU_EXACT}
+
+
+def villain_decoupled(kind, phi, n, kappa, *, W=1, interval_phi=math.pi, interval=1, n_sweeps=1, seed=0, sweep0=0, chain0=0,
+                      injected=None, path='auto', kappa_chain=None, obs=None, accept_mask=None, dS_out=None):
+    """`n_sweeps` sweeps of SiteUpdate ('site'), LinkUpdate ('link') or ExactUpdate ('exact') on every chain, in place
+    (svb_villain_decoupled).  phi (chains,1,N,N) float64, n (chains,2,N,N) int32.  `injected`: dict with u and, for
+    'site', dphi (n_sweeps,chains,N,N); for 'link', u and a shaped (n_sweeps,chains,2,N,N); for 'exact', a = z."""
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    p_phi = _dev(phi, 'phi', (torch.float64,))
+    p_n = _dev(n, 'n', (torch.int32,), (chains, 2, N, N))
+    if W != W or W == float('inf') or int(W) != W:
+        raise ValueError('the Villain updates need a finite integer W')
+    per = (chains, 2, N, N) if kind == 'link' else (chains, N, N)
+    pu = pd = pa = None
+    rng_mode = RNG_PHILOX
+    if injected is not None:
+        rng_mode = RNG_INJECTED
+        pu = _dev(injected['u'], 'injected[u]', (torch.float64,), (n_sweeps,) + per)
+        if kind == 'site':
+            pd = _dev(injected['dphi'], 'injected[dphi]', (torch.float64,), (n_sweeps,) + per)
+        else:
+            pa = _dev(injected['a'], 'injected[a]', (torch.int32,), (n_sweeps,) + per)
+    code = lib.svb_villain_decoupled(
+        _VU_KINDS[kind], p_phi, p_n, chains, N, float(kappa), _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)),
+        int(W), float(interval_phi), int(interval), int(n_sweeps), int(seed) & (2**64 - 1), int(sweep0), int(chain0),
+        rng_mode, _PATHS[path], pu, pd, pa, _opt(obs, 'obs', (torch.float64,), (chains, VOBS_COUNT)),
+        _opt(accept_mask, 'accept_mask', (torch.uint8,), per), _opt(dS_out, 'dS_out', (torch.float64,), per), _stream())
+    _lib.check(code)
+
+
 def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
     """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
     lib = _lib.load()

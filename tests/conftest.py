@@ -65,3 +65,8 @@ def golden_worldline_observables():
 @pytest.fixture(scope='session')
 def golden_worldline_wrapping():
     return load_golden('worldline_wrapping')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_villain_decoupled():
+    return load_golden('villain_decoupled')[0]

@@ -262,8 +262,50 @@ def worldline_wrapping():
     _pack(cases, 'worldline_wrapping')
 
 
+def villain_decoupled():
+    """SiteUpdate / LinkUpdate / ExactUpdate chains (generator/villain/{site,link,exact}.py) with rng = default_rng(99):
+    inputs, the dense draws of every sweep, and the reference's fields, accept counts and acceptance after every sweep."""
+    cases = []
+    gens = sv.generator.villain
+    for kind, (N, kappa, W, interval, sweeps, cfg_seed) in [
+        ('site', (4, 0.5, 1, np.pi, 8, 0)), ('site', (5, 0.3, 1, 1.0, 8, 1)), ('site', (8, 0.7, 2, np.pi, 6, 2)), ('site', (16, 0.5, 1, np.pi, 4, 3)),
+        ('link', (4, 0.5, 1, 1, 8, 4)), ('link', (5, 0.2, 2, 2, 8, 5)), ('link', (8, 0.1, 3, 1, 6, 6)), ('link', (16, 0.5, 1, 1, 4, 7)),
+        ('exact', (4, 0.5, 1, 1, 8, 8)), ('exact', (5, 0.1, 1, 2, 8, 9)), ('exact', (8, 0.05, 2, 1, 6, 10)), ('exact', (16, 0.2, 1, 1, 4, 11)),
+    ]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Villain(L, kappa, W=W)
+        G = {'site': lambda: gens.SiteUpdate(S, interval_phi=interval), 'link': lambda: gens.LinkUpdate(S, interval_n=interval),
+             'exact': lambda: gens.ExactUpdate(S, interval_z=interval)}[kind]()
+        G.rng = np.random.default_rng(99)
+        replay = np.random.default_rng(99)
+        phi0, n0 = villain_np.hot_start(np.random.default_rng(cfg_seed), N)
+        n0 = n0 * W
+        cfg = {'phi': Form(phi0, degree=0, lattice=L), 'n': Form(n0, degree=1, lattice=L)}
+        us, aa, phis, ns, acc, accp = [], [], [], [], [], []
+        for s in range(sweeps):
+            if kind == 'site':
+                d = villain_np.draw_site(replay, N, interval)
+                us.append(d['u']); aa.append(d['dphi'])
+            elif kind == 'link':
+                d = villain_np.draw_link(replay, N, W=W, interval_n=interval)
+                us.append(d['u']); aa.append(d['a'])
+            else:
+                d = villain_np.draw_exact(replay, N, interval)
+                us.append(d['u']); aa.append(d['a'])
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            phis.append(np.asarray(cfg['phi']).copy()); ns.append(np.asarray(cfg['n']).copy())
+            acc.append(int(G.accepted - before[0])); accp.append(float(G.acceptance - before[1]))
+        cases.append(dict(kind=np.array({'site': 0, 'link': 1, 'exact': 2}[kind]), N=N, kappa=kappa, W=W, interval=interval,
+                          sweeps=sweeps, phi0=phi0, n0=n0, u=np.array(us), a=np.array(aa), phi=np.array(phis), n=np.array(ns),
+                          accepted=np.array(acc), acceptance=np.array(accp)))
+    _pack(cases, 'villain_decoupled')
+    print('villain_decoupled.npz:', len(cases), 'cases; accepted per case:', [int(c['accepted'].sum()) for c in cases])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
-                             'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping']
+                             'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping',
+                             'villain_decoupled']
     for name in which:
         globals()[name]()

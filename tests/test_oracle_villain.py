@@ -105,3 +105,35 @@ def test_delta_S_formula_equals_action_difference():
             n2[0, x0, x1] += draws['dn_fwd'][0, x0, x1]; n2[0, (x0 - 1) % N, x1] += draws['dn_bwd'][0, x0, x1]
             n2[1, x0, x1] += draws['dn_fwd'][1, x0, x1]; n2[1, x0, (x1 - 1) % N] += draws['dn_bwd'][1, x0, x1]
             assert abs(dS[x0, x1] - (V.action(p2, n2, kappa) - V.action(phi, n, kappa))) < 1e-10
+
+
+def test_decoupled_updates_reproduce_reference_chains(golden_villain_decoupled):
+    """SiteUpdate / LinkUpdate / ExactUpdate restatements (oracle/villain_np.py) against chains produced by the
+    UNMODIFIED reference with rng = default_rng(99): vectorised form with the replayed numpy stream, and the dense
+    per-site / per-link form (the arithmetic the kernels perform) with the stored draws -- fields bit for bit."""
+    for c in golden_villain_decoupled:
+        kind = ['site', 'link', 'exact'][int(c['kind'])]
+        N, kappa, W, sweeps = int(c['N']), float(c['kappa']), int(c['W']), int(c['sweeps'])
+        interval = float(c['interval']) if kind == 'site' else int(c['interval'])
+        rng = np.random.default_rng(99)
+        phi, n = c['phi0'].copy(), c['n0'].copy()
+        pd, nd = c['phi0'].copy(), c['n0'].copy()
+        for s in range(sweeps):
+            st, sd = {}, {}
+            if kind == 'site':
+                phi, n = V.site_step(phi, n, kappa, rng, interval_phi=interval, stats=st)
+                draws = {'u': c['u'][s], 'dphi': c['a'][s], 'dn_fwd': np.zeros((2, N, N), dtype=np.int64),
+                         'dn_bwd': np.zeros((2, N, N), dtype=np.int64)}
+                pd, nd = V.neighborhood_step_dense(pd, nd, kappa, draws, stats=sd)
+            elif kind == 'link':
+                phi, n = V.link_step(phi, n, kappa, W, rng, interval_n=interval, stats=st)
+                pd, nd = V.link_step_dense(pd, nd, kappa, {'u': c['u'][s], 'a': c['a'][s]}, stats=sd)
+            else:
+                phi, n = V.exact_step(phi, n, kappa, rng, interval_z=interval, stats=st)
+                pd, nd = V.exact_step_dense(pd, nd, kappa, {'u': c['u'][s], 'a': c['a'][s]}, stats=sd)
+            for (p_, n_, stats) in ((phi, n, st), (pd, nd, sd)):
+                assert (n_ == c['n'][s]).all(), (kind, N, s)
+                assert (p_ == c['phi'][s]).all(), (kind, N, s)
+                assert stats['accepted'] == int(c['accepted'][s])
+                norm = 2 * N * N if kind == 'link' else N * N
+                assert stats['acceptance'] / norm == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
