@@ -200,6 +200,18 @@ int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t chains, int N
                           double* obs, uint8_t* accept_mask, double* dS_out, void* stream);
 
 /*
+ * CohomologyUpdate.step (generator/villain/cohomology.py:64-117): per chain and direction mu one proposal h in
+ * [-interval, interval] \ {0} added to n_mu on the whole slice x_mu = 0 (changes the winding sector), IN PLACE on n.
+ *  injected       inj_u (chains, 2) f64 and inj_h (chains, 2) i32, [mu] in the reference's draw order (h, u per direction)
+ *  counters       optional (chains, 2) f64, ACCUMULATED: accepted, sum of min(1, e^-dS);  dS_out optional (chains, 2)
+ */
+int svb_villain_cohomology(const void* phi, int32_t* n, int64_t chains, int N,
+                           double kappa, const double* kappa_chain, int interval,
+                           uint64_t seed, uint64_t sweep, uint64_t chain0, int rng_mode,
+                           const double* inj_u, const int32_t* inj_h,
+                           double* counters, double* dS_out, void* stream);
+
+/*
  * The same sweep with HOST buffers: the reference's `step(cfg)` contract (host arrays in, host arrays out,
  * neighborhood.py:59-137) for a whole batch.  phi_host / n_host / obs_host are pinned HOST buffers updated in place;
  * phi_dev / n_dev / obs_dev are caller-owned DEVICE staging buffers of the same shapes.  The chains are processed in

@@ -20,6 +20,7 @@ STREAM_VILLAIN_REFINE = 4
 STREAM_WORLDLINE_REFINE = 5
 STREAM_VILLAIN_LINK = 6
 STREAM_VILLAIN_LINK_REFINE = 7
+STREAM_VILLAIN_COHOMOLOGY = 8
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -158,3 +159,13 @@ def villain_link_draws(seed, chain, sweep, N, W=1, interval_n=1):
         cs.append(W * _nonzero_choice((p >> np.uint64(32)).astype(np.int64), interval_n))
         us.append(_lazy_uniform(p & MASK32, r[mu]))
     return {'u': np.stack(us).reshape(2, N, N), 'a': np.stack(cs).reshape(2, N, N)}
+
+
+def villain_cohomology_draws(seed, chain, sweep, interval_h=1):
+    """CohomologyUpdate on the GPU: block with counter word 0 = mu in STREAM_VILLAIN_COHOMOLOGY; word 0 -> h (index =
+    (2 I) w >> 32), words 1, 2 -> u = (k52 + 1/2) 2^-52 with k52 = (y & 0xFFFFF) << 32 | z.  Returns (u[2], h[2])."""
+    x, y, z, _ = philox_site(seed, chain, sweep, np.arange(2, dtype=np.uint64), STREAM_VILLAIN_COHOMOLOGY)
+    h = _nonzero_choice(((x * np.uint64(2 * interval_h)) >> np.uint64(32)).astype(np.int64), interval_h)
+    ku = ((y & np.uint64(0xFFFFF)) << np.uint64(32)) | z
+    u = (ku.astype(np.float64) + 0.5) * TWO_M52
+    return u, h

@@ -35,6 +35,7 @@ SIGNATURES = {
                                           ctypes.c_uint32, ctypes.c_uint32, _i, _vp]),
     'svb_villain_decoupled': (_i, [_i, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'svb_villain_cohomology': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp, _vp]),
     'svb_villain_observables': (_i, [_vp, _i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),

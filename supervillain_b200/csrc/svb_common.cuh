@@ -67,7 +67,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1,
 // Stream ids folded into the top byte of counter word 3, so the generators never share draws.
 enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u, STREAM_WORLDLINE_WRAPPING = 3u,
                   STREAM_VILLAIN_REFINE = 4u, STREAM_WORLDLINE_REFINE = 5u,
-                  STREAM_VILLAIN_LINK = 6u, STREAM_VILLAIN_LINK_REFINE = 7u };
+                  STREAM_VILLAIN_LINK = 6u, STREAM_VILLAIN_LINK_REFINE = 7u, STREAM_VILLAIN_COHOMOLOGY = 8u };
 
 __host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t chain, uint64_t sweep,
                                                          uint32_t site, uint32_t stream_id) {

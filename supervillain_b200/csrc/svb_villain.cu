@@ -1414,6 +1414,75 @@ __global__ void __launch_bounds__(256) villain_link_kernel(LinkArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// CohomologyUpdate (supervillain/generator/villain/cohomology.py:64-117): per direction mu one proposal h added to n_mu on
+// the whole slice x_mu = 0;  change_r = -2 pi h;  dS = sum over the slice of ((kappa/2) change_r) ((2 r) + change_r).
+// The two directions touch different components, so they are decided concurrently: one warp per (chain, mu), lanes striding
+// over the N links of the slice.  The N terms are summed by a warp tree where numpy sums pairwise: dS agrees to ~1e-15
+// relative, not bitwise.  Philox: block with counter word 0 = mu in stream STREAM_VILLAIN_COHOMOLOGY; word 0 -> h (index =
+// (2 I) w >> 32), words 1, 2 -> a 52-bit uniform (k + 1/2) 2^-52.
+// ------------------------------------------------------------------------------------------
+struct CohomologyArgs {
+    const double* phi;
+    int32_t* n;
+    long long chains;
+    int N;
+    double kappa;
+    const double* kappa_chain;
+    int interval;
+    unsigned long long seed, sweep, chain0;
+    const double* inj_u;       // (chains, 2)
+    const int32_t* inj_h;      // (chains, 2)
+    double* counters;          // (chains, 2): accepted, sum of acceptance (accumulated)
+    double* dS_out;            // (chains, 2)
+};
+
+template <bool INJECTED>
+__global__ void __launch_bounds__(128) villain_cohomology_kernel(CohomologyArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long job = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);          // (chain, mu)
+    if (job >= 2 * a.chains) return;
+    const long long chain = job >> 1;
+    const int mu = (int)(job & 1), N = a.N, V = N * N;
+    const double* gphi = a.phi + chain * V;
+    int32_t* gn = a.n + chain * 2 * V + (long long)mu * V;
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    int h;
+    double u;
+    if (INJECTED) {
+        h = a.inj_h[job];
+        u = a.inj_u[job];
+    } else {
+        const Philox4 p = philox_site(a.seed, a.chain0 + (unsigned long long)chain, a.sweep, (uint32_t)mu, STREAM_VILLAIN_COHOMOLOGY);
+        const int idx = (int)(((uint64_t)p.x * (uint64_t)(2 * a.interval)) >> 32);
+        h = (idx < a.interval) ? idx - a.interval : idx - a.interval + 1;
+        const uint64_t ku = ((uint64_t)(p.y & 0xFFFFFu) << 32) | (uint64_t)p.z;
+        u = __dmul_rn(__dadd_rn((double)ku, 0.5), 2.220446049250313e-16);
+    }
+    const double change_r = __dmul_rn(-SVB_TWO_PI, (double)h);                         // -2 * np.pi * h
+    const double hk_cr = __dmul_rn(kappa / 2, change_r);
+    double dS = 0.0;
+    for (int j = lane; j < N; j += 32) {
+        // slice x_mu = 0: link (mu, x) with x = (0, j) for mu = 0, (j, 0) for mu = 1
+        const int tail = (mu == 0) ? j : j * N;
+        const int head = (mu == 0) ? N + j : j * N + 1;
+        const double r = __dsub_rn(__dsub_rn(gphi[head], gphi[tail]), __dmul_rn(SVB_TWO_PI, (double)gn[tail]));
+        dS = __dadd_rn(dS, __dmul_rn(hk_cr, __dadd_rn(__dmul_rn(2.0, r), change_r)));
+    }
+    dS = warp_sum(dS);
+    const double A = exp_clipped(-dS);
+    const bool ok = u < A;
+    if (ok)
+        for (int j = lane; j < N; j += 32) gn[(mu == 0) ? j : j * N] += h;
+    if (lane == 0) {
+        if (a.counters) {
+            atomicAdd(a.counters + chain * 2, ok ? 1.0 : 0.0);
+            atomicAdd(a.counters + chain * 2 + 1, A);
+        }
+        if (a.dS_out) a.dS_out[job] = dS;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static size_t villain_smem_bytes(int N, size_t real_size) {
@@ -1777,6 +1846,29 @@ extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t ch
     a.inj_z = inj_a;
     a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     return dispatch_villain<double>(a, rng_mode, SVB_ARITH_STRICT, path, st);
+}
+
+extern "C" int svb_villain_cohomology(const void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                      int interval, uint64_t seed, uint64_t sweep, uint64_t chain0, int rng_mode,
+                                      const double* inj_u, const int32_t* inj_h, double* counters, double* dS_out, void* stream) {
+    if (!phi || !n) return fail(SVB_E_NULL, "svb_villain_cohomology: phi and n are required");
+    if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_villain_cohomology: chains=%lld N=%d", (long long)chains, N);
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_cohomology: kappa must be positive");
+    if (interval < 1 || interval > 1024) return fail(SVB_E_PARAM, "svb_villain_cohomology: interval");
+    if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_villain_cohomology: rng_mode");
+    if (rng_mode == SVB_RNG_INJECTED && (!inj_u || !inj_h)) return fail(SVB_E_NULL, "svb_villain_cohomology: injected mode needs inj_u, inj_h");
+    if (chains == 0) return SVB_OK;
+    CohomologyArgs a;
+    a.phi = reinterpret_cast<const double*>(phi); a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain;
+    a.interval = interval; a.seed = seed; a.sweep = sweep; a.chain0 = chain0; a.inj_u = inj_u; a.inj_h = inj_h;
+    a.counters = counters; a.dS_out = dS_out;
+    const long long blocks = (2 * chains + 3) / 4;
+    if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_cohomology: too many blocks");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (rng_mode == SVB_RNG_INJECTED) villain_cohomology_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a);
+    else villain_cohomology_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
 }
 
 extern "C" int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n, int64_t chains, int N, double kappa,

@@ -83,3 +83,13 @@ def villain_exact(rng, lattice, interval_z):
     for color in lattice.checkerboarding:
         z[color] = rng.choice(_nonzero_choices(interval_z), len(color[0]))
     return u, z
+
+
+def villain_cohomology(rng, interval_h):
+    """One CohomologyUpdate step's draws (cohomology.py:90, :101): per direction h, then the uniform."""
+    hs = _nonzero_choices(interval_h)
+    h = np.zeros(2, dtype=np.int32); u = np.zeros(2)
+    for mu in range(2):
+        h[mu] = rng.choice(hs)
+        u[mu] = rng.uniform(0, 1)
+    return u, h

@@ -321,3 +321,74 @@ class ExactUpdate(_DecoupledVillain):
             for s in range(n_sweeps):
                 u[s, c], a[s, c] = _replay.villain_exact(self.rng, self.Lattice, self.interval_z)
         return {'u': torch.from_numpy(u).cuda(), 'a': torch.from_numpy(a).cuda()}
+
+
+class CohomologyUpdate(Generator):
+    """Winding-sector moves of n (supervillain/generator/villain/cohomology.py:12-130): `CohomologyUpdate(action,
+    interval_h=1)`; one slice proposal per direction and chain."""
+
+    def __init__(self, action, interval_h=1, *, seed=None):
+        if not _is_villain(action):
+            raise ValueError('Need a Villain action')
+        self.Action = action
+        self.Lattice = action.Lattice
+        self.kappa = action.kappa
+        self.interval_h = interval_h
+        self.h = tuple(h for h in range(-interval_h, 0)) + tuple(h for h in range(1, interval_h + 1))
+        self.rng = None
+        self.seed = fresh_seed() if seed is None else int(seed)
+        self.counter = 0
+        self.accepted = 0
+        self.proposed = 0
+        self.acceptance = 0.
+        self.sweeps = 0
+
+    def __str__(self):
+        return 'CohomologyUpdate'
+
+    def sweep_device(self, phi, n, n_sweeps=1, *, obs=None, chain0=0, kappa_chain=None, injected=None, counters=None,
+                     dS_out=None):
+        """`n_sweeps` cohomology steps in place on n (chains,2,N,N) int32; `obs`, if given, is refreshed from the final
+        state with svb_villain_observables (its two counter columns are zeroed: use `counters`)."""
+        for s in range(n_sweeps):
+            ops.villain_cohomology(phi, n, self.kappa, interval=self.interval_h, seed=self.seed, sweep=self.counter + s,
+                                   chain0=chain0, injected=injected, kappa_chain=kappa_chain, counters=counters, dS_out=dS_out)
+        if injected is None:
+            self.counter += n_sweeps
+        if obs is not None:
+            ops.villain_observables(phi, n, self.kappa, kappa_chain=kappa_chain, obs=obs)
+
+    def step(self, cfg):
+        N = self.Lattice.N
+        phi, single = to_device(cfg['phi'], torch.float64, 1, N)
+        n, _ = to_device(cfg['n'], torch.int32, 2, N)
+        if isinstance(cfg['n'], torch.Tensor):
+            n = n.clone()
+        chains = phi.shape[0]
+        injected = None
+        if self.rng is not None:
+            u = np.empty((chains, 2)); h = np.empty((chains, 2), dtype=np.int32)
+            for k in range(chains):
+                u[k], h[k] = _replay.villain_cohomology(self.rng, self.interval_h)
+            injected = {'u': torch.from_numpy(u).cuda(), 'h': torch.from_numpy(h).cuda()}
+        counters = torch.zeros((chains, 2), dtype=torch.float64, device=phi.device)
+        self.sweep_device(phi, n, 1, injected=injected, counters=counters)
+        rec = counters.cpu().numpy()
+        self.proposed += 2 * chains
+        self.accepted += int(round(float(rec[:, 0].sum())))
+        self.acceptance += float(rec[:, 1].sum()) / 2
+        self.sweeps += chains
+        out_n = n.cpu().numpy().astype(np.int64)
+        return cfg | {'n': Form(out_n[0], degree=1, lattice=self.Lattice) if single else out_n}
+
+    def inline_observables(self, steps):
+        return {}
+
+    def report(self):
+        return (
+            f'There were {self.accepted} cohomology proposals accepted of {self.proposed} proposed updates.'
+            + '\n' +
+            f'    {self.accepted/self.proposed:.6f} acceptance rate'
+            + '\n' +
+            f'    {self.acceptance / self.sweeps:.6f} average Metropolis acceptance probability.'
+        )

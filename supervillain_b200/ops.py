@@ -271,6 +271,27 @@ def villain_decoupled(kind, phi, n, kappa, *, W=1, interval_phi=math.pi, interva
     _lib.check(code)
 
 
+def villain_cohomology(phi, n, kappa, *, interval=1, seed=0, sweep=0, chain0=0, injected=None, kappa_chain=None,
+                       counters=None, dS_out=None):
+    """One CohomologyUpdate step (one slice proposal per direction and chain), in place on n (svb_villain_cohomology).
+    `injected`: dict of u (chains,2) f64 and h (chains,2) int32.  counters (chains,2), accumulated: accepted, acceptance."""
+    lib = _lib.load()
+    chains, N = _fields_shape(phi, 'phi', 1)
+    p_phi = _dev(phi, 'phi', (torch.float64,))
+    p_n = _dev(n, 'n', (torch.int32,), (chains, 2, N, N))
+    if injected is None:
+        rng_mode, pu, ph = RNG_PHILOX, None, None
+    else:
+        rng_mode = RNG_INJECTED
+        pu = _dev(injected['u'], 'injected[u]', (torch.float64,), (chains, 2))
+        ph = _dev(injected['h'], 'injected[h]', (torch.int32,), (chains, 2))
+    _lib.check(lib.svb_villain_cohomology(
+        p_phi, p_n, chains, N, float(kappa), _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(interval),
+        int(seed) & (2**64 - 1), int(sweep), int(chain0), rng_mode, pu, ph,
+        _opt(counters, 'counters', (torch.float64,), (chains, 2)), _opt(dS_out, 'dS_out', (torch.float64,), (chains, 2)),
+        _stream()))
+
+
 def villain_observables(phi, n, kappa, *, kappa_chain=None, obs=None):
     """Per-chain action / sum dn^2 / wrapping sums of the current state -> (chains, VOBS_COUNT) f64."""
     lib = _lib.load()

@@ -70,3 +70,8 @@ def golden_worldline_wrapping():
 @pytest.fixture(scope='session')
 def golden_villain_decoupled():
     return load_golden('villain_decoupled')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_villain_cohomology():
+    return load_golden('villain_cohomology')[0]

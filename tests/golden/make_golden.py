@@ -303,9 +303,38 @@ def villain_decoupled():
     print('villain_decoupled.npz:', len(cases), 'cases; accepted per case:', [int(c['accepted'].sum()) for c in cases])
 
 
+def villain_cohomology():
+    """CohomologyUpdate chains (generator/villain/cohomology.py) with rng = default_rng(99)."""
+    cases = []
+    for (N, kappa, W, interval, sweeps, cfg_seed) in [(4, 0.05, 1, 1, 12, 0), (5, 0.02, 2, 2, 12, 1), (8, 0.03, 1, 1, 12, 2),
+                                                      (16, 0.01, 1, 1, 10, 3), (32, 0.004, 1, 2, 10, 4)]:
+        L = sv.lattice.Lattice2D(N)
+        S = sv.action.Villain(L, kappa, W=W)
+        G = sv.generator.villain.CohomologyUpdate(S, interval_h=interval)
+        G.rng = np.random.default_rng(99)
+        replay = np.random.default_rng(99)
+        phi0, n0 = villain_np.hot_start(np.random.default_rng(cfg_seed), N)
+        n0 = n0 * W
+        cfg = {'phi': Form(phi0, degree=0, lattice=L), 'n': Form(n0, degree=1, lattice=L)}
+        hs = tuple(range(-interval, 0)) + tuple(range(1, interval + 1))
+        us, hh, ns, acc, accp = [], [], [], [], []
+        for s in range(sweeps):
+            u, h = np.zeros(2), np.zeros(2, dtype=np.int64)
+            for mu in range(2):
+                h[mu] = replay.choice(hs); u[mu] = replay.uniform(0, 1)
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            us.append(u); hh.append(h); ns.append(np.asarray(cfg['n']).copy())
+            acc.append(int(G.accepted - before[0])); accp.append(float(G.acceptance - before[1]))
+        cases.append(dict(N=N, kappa=kappa, W=W, interval=interval, sweeps=sweeps, phi0=phi0, n0=n0, u=np.array(us), h=np.array(hh),
+                          n=np.array(ns), accepted=np.array(acc), acceptance=np.array(accp)))
+    _pack(cases, 'villain_cohomology')
+    print('accepted per case:', [int(c['accepted'].sum()) for c in cases])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
                              'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping',
-                             'villain_decoupled']
+                             'villain_decoupled', 'villain_cohomology']
     for name in which:
         globals()[name]()

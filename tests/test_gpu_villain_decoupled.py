@@ -83,3 +83,46 @@ def test_wrong_action_raises_like_the_reference():
     for cls in (SiteUpdate, LinkUpdate, ExactUpdate):
         with pytest.raises(ValueError):
             cls(S)
+
+
+def test_cohomology_update_reproduces_reference_chains(golden_villain_cohomology):
+    """CohomologyUpdate on the GPU with the reference's draws injected: n identical to the reference chain."""
+    from supervillain_b200.generator.villain import CohomologyUpdate
+    for c in golden_villain_cohomology:
+        N, kappa, W = int(c['N']), float(c['kappa']), int(c['W'])
+        S = svb.Villain(svb.Lattice2D(N), kappa, W=W)
+        G = CohomologyUpdate(S, interval_h=int(c['interval']))
+        G.rng = np.random.default_rng(99)
+        cfg = {'phi': c['phi0'], 'n': c['n0']}
+        for s in range(int(c['sweeps'])):
+            before = (G.accepted, G.acceptance)
+            cfg = G.step(cfg)
+            assert (np.asarray(cfg['n']) == c['n'][s]).all(), (N, s)
+            assert G.accepted - before[0] == int(c['accepted'][s])
+            assert G.acceptance - before[1] == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
+    assert sum(int(c['accepted'].sum()) for c in golden_villain_cohomology) > 10
+
+
+def test_cohomology_philox_matches_oracle_and_changes_the_sector():
+    N, kappa, chains, interval = 16, 0.01, 64, 2
+    rng = np.random.default_rng(3)
+    phi0 = np.stack([V.hot_start(rng, N)[0] for _ in range(chains)])
+    n0 = np.stack([V.hot_start(rng, N)[1] for _ in range(chains)])
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    counters = torch.zeros((chains, 2), dtype=torch.float64, device='cuda')
+    dS = torch.zeros((chains, 2), dtype=torch.float64, device='cuda')
+    for s in range(3):
+        ops.villain_cohomology(phi, n, kappa, interval=interval, seed=9, sweep=s, chain0=4, counters=counters, dS_out=dS)
+    changed = 0
+    for c in range(chains):
+        q, acc, dref = n0[c].copy(), 0, np.zeros(2)
+        for s in range(3):
+            st = {}
+            _, q = V.cohomology_step(phi0[c], q, kappa, None, interval_h=interval, stats=st, dS_out=dref,
+                                     draws=P.villain_cohomology_draws(9, 4 + c, s, interval))
+            acc += st['accepted']
+        assert (n[c].cpu().numpy() == q).all()
+        assert int(counters[c, 0]) == acc
+        np.testing.assert_allclose(dS[c].cpu().numpy(), dref, rtol=1e-12, atol=1e-12)
+        changed += int((q.sum(axis=(1, 2)) != n0[c].sum(axis=(1, 2))).any())
+    assert changed > 5          # the winding sector does move

@@ -137,3 +137,21 @@ def test_decoupled_updates_reproduce_reference_chains(golden_villain_decoupled):
                 assert stats['accepted'] == int(c['accepted'][s])
                 norm = 2 * N * N if kind == 'link' else N * N
                 assert stats['acceptance'] / norm == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
+
+
+def test_cohomology_update_reproduces_reference_chains(golden_villain_cohomology):
+    """CohomologyUpdate restatement against chains of the UNMODIFIED reference (rng = default_rng(99)), with the replayed
+    numpy stream and with the stored draws."""
+    for c in golden_villain_cohomology:
+        N, kappa, interval = int(c['N']), float(c['kappa']), int(c['interval'])
+        rng = np.random.default_rng(99)
+        phi = c['phi0']
+        n, nd = c['n0'].copy(), c['n0'].copy()
+        for s in range(int(c['sweeps'])):
+            st, sd = {}, {}
+            _, n = V.cohomology_step(phi, n, kappa, rng, interval_h=interval, stats=st)
+            _, nd = V.cohomology_step(phi, nd, kappa, None, interval_h=interval, stats=sd, draws=(c['u'][s], c['h'][s]))
+            for n_, stats in ((n, st), (nd, sd)):
+                assert (n_ == c['n'][s]).all(), (N, s)
+                assert stats['accepted'] == int(c['accepted'][s])
+                assert stats['acceptance'] / 2 == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
