@@ -78,3 +78,15 @@ def test_worldline_plaquette_only_matches_reference_in_the_trivial_sector(kappa)
         mean, err = chain_statistics(E, 'ActionDensity', 30)
         ref = anchor('Worldline', 'PlaquetteUpdate', 8, 0.5)                # the reference's sequential PlaquetteUpdate
         assert abs(mean - ref['ActionDensity'][0]) < NSIGMA * np.hypot(err, ref['ActionDensity'][1])
+
+
+def test_villain_decoupled_updates_match_reference_hammer():
+    """Sequentially((SiteUpdate, LinkUpdate, ExactUpdate, CohomologyUpdate)) -- the reference's villain Hammer without the
+    worm -- samples the same ensemble as NeighborhoodUpdate and as the reference's Hammers."""
+    from supervillain_b200.generator.villain import CohomologyUpdate, ExactUpdate, LinkUpdate, SiteUpdate
+    N, kappa = 8, 0.3
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    G = Sequentially((SiteUpdate(S, seed=1), LinkUpdate(S, seed=2), ExactUpdate(S, seed=3), CohomologyUpdate(S, seed=4)))
+    E = svb.BatchedEnsemble(S, 1024).generate(120, G, 'cold', sweeps_per_step=40)
+    check(E, anchor('Villain', 'Hammer', N, kappa), discard=40)
+    check(E, anchor('Worldline', 'Hammer', N, kappa), discard=40)
