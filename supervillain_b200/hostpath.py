@@ -35,7 +35,9 @@ class HostStepper:
         self.dev_a = torch.empty((self.chains, self.comps[0], N, N), dtype=self.dtypes[0], device=self.device)
         self.dev_b = torch.empty((self.chains, self.comps[1], N, N), dtype=self.dtypes[1], device=self.device)
         self.dev_obs = torch.empty((self.chains, self.nobs), dtype=torch.float64, device=self.device)
-        self.host_obs = torch.empty((self.chains, self.nobs), dtype=torch.float64, pin_memory=True)
+        self._host_obs = [torch.empty((self.chains, self.nobs), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        self._flip = 0
+        self.host_obs = self._host_obs[0]
         self.h2d_bytes = self.dev_a.numel() * self.dev_a.element_size() + self.dev_b.numel() * self.dev_b.element_size()
         self.d2h_bytes = self.h2d_bytes + self.host_obs.numel() * 8
 
@@ -48,12 +50,29 @@ class HostStepper:
             b.copy_(from_device[1])
         return a, b
 
+    class Pending:
+        """A step in flight (`step_async`): `wait()` returns the pinned observable record once the host fields are final."""
+
+        def __init__(self, events, record):
+            self.events, self.record = events, record
+
+        def wait(self):
+            for e in self.events:
+                e.synchronize()
+            return self.record
+
     def step(self, host_a, host_b, n_sweeps=1):
         """One step on host fields, IN PLACE in the pinned host buffers; returns the pinned observable record.
 
         host_a, host_b: (phi, n) for a Villain generator, (m, v) for a worldline generator, pinned,
         shaped (chains, C, N, N) with the device dtypes (float64/float32 phi, int32 integer fields).
         """
+        return self.step_async(host_a, host_b, n_sweeps).wait()
+
+    def step_async(self, host_a, host_b, n_sweeps=1):
+        """`step` without the final wait: returns a `Pending`.  Issue the next step on ANOTHER pair of host buffers before
+        waiting for this one and its copies overlap this one's (chunk i of consecutive steps shares a stream, so the
+        device staging buffers are reused in order); at most two steps should be in flight (two observable records)."""
         for t, d in ((host_a, self.dev_a), (host_b, self.dev_b)):
             if tuple(t.shape) != tuple(d.shape) or t.dtype != d.dtype or t.is_cuda:
                 raise ValueError(f'host field must be a CPU tensor of shape {tuple(d.shape)} and dtype {d.dtype}')
@@ -76,9 +95,7 @@ class HostStepper:
                 _lib.ARITH_FAST if G.arithmetic == 'fast' else _lib.ARITH_STRICT,
                 len(self.bounds), handles, len(self.streams)))
             G.counter = sweep0 + n_sweeps
-            for s in self.streams:
-                s.synchronize()
-            return self.host_obs
+            return self._pending()
         for i, (lo, hi) in enumerate(self.bounds):
             st = self.streams[i % len(self.streams)]
             with torch.cuda.stream(st):
@@ -91,6 +108,15 @@ class HostStepper:
                 host_b[lo:hi].copy_(self.dev_b[lo:hi], non_blocking=True)
                 self.host_obs[lo:hi].copy_(self.dev_obs[lo:hi], non_blocking=True)
         G.counter = sweep0 + n_sweeps
+        return self._pending()
+
+    def _pending(self):
+        events = []
         for s in self.streams:
-            s.synchronize()
-        return self.host_obs
+            e = torch.cuda.Event()
+            e.record(s)
+            events.append(e)
+        record = self.host_obs
+        self._flip ^= 1
+        self.host_obs = self._host_obs[self._flip]
+        return HostStepper.Pending(events, record)

@@ -393,3 +393,30 @@ def test_observables_of_the_arriving_state_complete_the_previous_record():
     assert np.array_equal(E1.record[:, :-1], E2.record[:, :-1]) and np.array_equal(E1.record[:, -1, 1:], E2.record[:, -1, 1:])
     np.testing.assert_allclose(E1.record[:, -1, 0], E2.record[:, -1, 0], rtol=1e-13)
     assert G1.accepted == G2.accepted and G1.acceptance == G2.acceptance
+
+
+def test_host_stepper_two_steps_in_flight():
+    """step_async: two steps in flight on alternating host buffer pairs give the records and fields of waited steps."""
+    from supervillain_b200.hostpath import HostStepper
+    N, chains, kappa = 32, 200, 0.5
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    starts = [V.hot_start(np.random.default_rng(20 + r), N, chains) for r in range(2)]
+    G1, G2 = NeighborhoodUpdate(S, seed=3), NeighborhoodUpdate(S, seed=3)
+    st1, st2 = HostStepper(G1, chains, chunks=7, streams=3), HostStepper(G2, chains, chunks=7, streams=3)
+    sets1 = [st1.pinned_fields() for _ in range(2)]
+    sets2 = [st2.pinned_fields() for _ in range(2)]
+    for r in range(2):
+        for sets in (sets1, sets2):
+            sets[r][0].copy_(torch.from_numpy(starts[r][0])); sets[r][1].copy_(torch.from_numpy(starts[r][1]).to(torch.int32))
+    waited = [st1.step(*sets1[k % 2]).clone() for k in range(6)]
+    records, pending = [], None
+    for k in range(6):
+        issued = st2.step_async(*sets2[k % 2])
+        if pending is not None:
+            records.append(pending.wait().clone())
+        pending = issued
+    records.append(pending.wait().clone())
+    for r in range(2):
+        assert torch.equal(sets1[r][0], sets2[r][0]) and torch.equal(sets1[r][1], sets2[r][1])
+    for a, b in zip(waited, records):
+        assert torch.equal(a, b)
