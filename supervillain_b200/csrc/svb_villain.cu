@@ -18,6 +18,8 @@
 // index arithmetic folds to shifts/immediates, loops unroll, integer->double conversions go
 // through the fp64 adder instead of the conversion unit, and integer reductions use REDUX.
 
+#include <type_traits>
+
 #include "svb_common.cuh"
 
 #ifndef SVB_SITE_UNROLL
@@ -1983,8 +1985,15 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
         const int fuse = (obs && last) ? 1 : 0;
         if (arith_mode == SVB_ARITH_STRICT)
             villain_tiled_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
-        else
+        else if (a.accept_mask || a.dS_out)       // debug outputs: the fp64 kernel
             villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
+        else
+#ifndef SVB_NO_FILTERED_KERNEL
+            villain_tiled_filtered_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, make_filter_consts(interval_phi, W, interval_n), bufp[src],
+                                                                            bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
+#else
+            villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
+#endif
         SVB_CUDA_TRY(cudaGetLastError());
     }
     if (tail_global) {

@@ -18,7 +18,7 @@
 // Geometry: T = 4 N threads per CTA (so a thread's sites of one colour are rows x0, x0 + 8, x0 + 16, ... of one
 // column), one CTA per chain at a time, grid-stride over chains, chains moved by 1-D TMA bulk copies.
 #pragma once
-// (included inside namespace svb)
+// (included inside namespace svb; <type_traits> comes with svb_villain.cu)
 
 // Band of the fp32 decision (everything in units of ln 2 inside the kernel; natural units here).  With
 // D = interval_phi + 2 pi W interval_n >= |dr|, R = max |r| over the four links and eps = 2^-24, worst cases:
@@ -541,4 +541,184 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a, fc);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// TILED path with fp32-filtered decisions (configs 4 and 5: lattices beyond shared memory; FAST arithmetic).
+//
+// The geometry, ghost zones and ping-pong of villain_tiled_kernel (svb_villain.cu) with the arithmetic of the kernel
+// above: the residuals of every link inside the 37 x 38 region are built once in fp64 and kept in fp32, proposals are
+// decided in fp32 with the exact fp64 + lazy-uniform test inside the error band, phi / n are touched on acceptance.
+// Philox is keyed by the GLOBAL site, so redundant ghost updates are bit-identical in every tile that computes them --
+// including the (rare) exact-path decisions, which depend only on the global state around the site.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) villain_tiled_filtered_kernel(const __grid_constant__ VillainArgs a,
+                                                                        const __grid_constant__ FilterConsts fc,
+                                                                        const double* __restrict__ phi_in,
+                                                                        const int32_t* __restrict__ n_in, double* __restrict__ phi_out,
+                                                                        int32_t* __restrict__ n_out, int sweep, int tiles_per_side,
+                                                                        int fuse_obs) {
+    __shared__ __align__(16) double sphi[kRegSize];
+    __shared__ __align__(16) int32_t sn0[kRegSize];
+    __shared__ __align__(16) int32_t sn1[kRegSize];
+    __shared__ __align__(16) float sr0[kRegSize];        // residual of link (0, x): x -> x + e0 (valid for local rows < 36)
+    __shared__ __align__(16) float sr1[kRegSize];        // residual of link (1, x): x -> x + e1 (valid for local cols < 36)
+    __shared__ double red[2 * 32];
+    const int N = a.N;
+    const long long V = (long long)N * N;
+    const int tiles = tiles_per_side * tiles_per_side;
+    const long long chain = blockIdx.x / tiles;
+    const int tile = blockIdx.x - (int)(chain * tiles);
+    const int a0 = (tile / tiles_per_side) * kTile, a1 = (tile % tiles_per_side) * kTile;
+    const int tid = threadIdx.x;
+    const double* gphi = phi_in + chain * V;
+    const int32_t* gn0 = n_in + chain * 2 * V;
+    const int32_t* gn1 = gn0 + V;
+
+    // ---- load the region, two sites at a time (N and the origins are even: a pair never straddles the wrap) ----
+    for (int p = tid; p < kRegRows * (kRegCols / 2); p += 128) {
+        const int i = p / (kRegCols / 2), jj = 2 * (p - i * (kRegCols / 2));
+        int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+        int x1 = a1 - 2 + jj; x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+        const long long g = (long long)x0 * N + x1;
+        const int l = i * kRegCols + jj;
+        *reinterpret_cast<double2*>(sphi + l) = *reinterpret_cast<const double2*>(gphi + g);
+        *reinterpret_cast<int2*>(sn0 + l) = *reinterpret_cast<const int2*>(gn0 + g);
+        *reinterpret_cast<int2*>(sn1 + l) = *reinterpret_cast<const int2*>(gn1 + g);
+    }
+    __syncthreads();
+    // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) for the links inside the region, fp64 rounded to fp32 ----
+    for (int l = tid; l < (kRegRows - 1) * kRegCols; l += 128) {
+        const int j = l % kRegCols;
+        const double pc = sphi[l];
+        sr0[l] = (float)fma(-SVB_TWO_PI, int_to_double(sn0[l]), sphi[l + kRegCols] - pc);
+        if (j < kRegCols - 2) sr1[l] = (float)fma(-SVB_TWO_PI, int_to_double(sn1[l]), sphi[l + 1] - pc);
+    }
+    __syncthreads();
+
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    const double half_kappa = kappa / 2;
+    const float hk2 = (float)(half_kappa * 1.4426950408889634);
+    const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+    const uint32_t K = (uint32_t)(2 * a.interval_n + 1);
+    const int W = a.W, mWI = -a.W * a.interval_n;
+    const float cIn = fc.c * (float)a.interval_n;
+    const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
+    double n_acc = 0.0, sum_A = 0.0;
+
+    // one colour pass with compile-time geometry: colour 0 on local [1, 36) (35 x 35), colour 1 on local [2, 35) (33 x 33)
+    auto colour_pass = [&](auto colour_tag) {
+        constexpr int c = decltype(colour_tag)::value;
+        constexpr int lo = (c == 0) ? 1 : 2;
+        constexpr int side = (c == 0) ? kTile + 3 : kTile + 1;
+        constexpr int per_row = (side + 1) / 2;
+        // global coordinates of local (lo, *): one conditional wrap per step instead of a modulo per site
+        for (int idx = tid; idx < side * per_row; idx += 128) {
+            const int di = idx / per_row;                                        // constant divisor
+            const int i = lo + di;
+            const int j = lo + 2 * (idx - di * per_row) + ((i + lo + c) & 1);   // (i + j) & 1 == c  (origins are even)
+            if (j >= lo + side) continue;
+            int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+            int x1 = a1 - 2 + j;  x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+            const int l = i * kRegCols + j;
+            const uint32_t c0 = villain_pair_counter(x0, x1, N), half = villain_pair_half(x0);            const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+            const uint32_t wA = half ? bits.z : bits.x, wB = half ? bits.w : bits.y;
+            uint32_t f = wB;
+            int dig[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t prod = (uint64_t)f * K;
+                f = (uint32_t)prod;
+                dig[q] = (int)(prod >> 32);
+            }
+            const float U = __uint_as_float(0x3F800000u | (wA >> 9)) - 0.99999994f;
+            const float dphi = fmaf(fc.two_I, U, -fc.I);
+            const float base_f = cIn - dphi, base_b = cIn + dphi;
+            const float r_f0 = sr0[l], r_b0 = sr0[l - kRegCols], r_f1 = sr1[l], r_b1 = sr1[l - 1];
+            const float dr_f0 = fmaf(-fc.c, (float)dig[0], base_f), dr_b0 = fmaf(-fc.c, (float)dig[1], base_b);
+            const float dr_f1 = fmaf(-fc.c, (float)dig[2], base_f), dr_b1 = fmaf(-fc.c, (float)dig[3], base_b);
+            float acc2 = dr_f0 * fmaf(2.0f, r_f0, dr_f0);
+            acc2 = fmaf(dr_b0, fmaf(2.0f, r_b0, dr_b0), acc2);
+            acc2 = fmaf(dr_f1, fmaf(2.0f, r_f1, dr_f1), acc2);
+            acc2 = fmaf(dr_b1, fmaf(2.0f, r_b1, dr_b1), acc2);
+            const float dS2 = hk2 * acc2;
+            const float L2 = 32.0f - fast_lg2((float)f);
+            const float Rmax = fmaxf(fmaxf(fabsf(r_f0), fabsf(r_b0)), fmaxf(fabsf(r_f1), fabsf(r_b1)));
+            const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L2, hkB));
+            const float diff = dS2 - L2;
+            bool ok = diff < 0.0f;
+            const float Aest = fminf(fast_ex2(-dS2), 1.0f);
+            if (!(fabsf(diff) > band) || f < 65536u) {
+                ExactProposal ep;
+                ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1;
+                ep.i_c = l; ep.i_b0 = l - kRegCols; ep.i_b1 = l - 1; ep.i_f0 = l + kRegCols; ep.i_f1 = l + 1;
+                ep.half_kappa = half_kappa;
+                ep.c = SVB_TWO_PI * (double)W;
+                ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ep.g[q] = dig[q] - a.interval_n;
+                ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
+                ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
+                ok = villain_exact_decision(ep);
+            }
+            if (ok) {
+                sphi[l] = __dadd_rn(sphi[l], villain_dphi_from_word(wA, a.interval_phi));
+                sn0[l] += W * dig[0] + mWI;
+                sn0[l - kRegCols] += W * dig[1] + mWI;
+                sn1[l] += W * dig[2] + mWI;
+                sn1[l - 1] += W * dig[3] + mWI;
+                sr0[l] = r_f0 + dr_f0;
+                sr0[l - kRegCols] = r_b0 + dr_b0;
+                sr1[l] = r_f1 + dr_f1;
+                sr1[l - 1] = r_b1 + dr_b1;
+            }
+            const bool owned = (i >= 2) && (i < 2 + kTile) && (j >= 2) && (j < 2 + kTile);
+            if (owned) {
+                n_acc += ok ? 1.0 : 0.0;
+                sum_A += (double)Aest;
+            }
+        }
+        __syncthreads();
+    };
+    colour_pass(std::integral_constant<int, 0>{});
+    colour_pass(std::integral_constant<int, 1>{});
+
+    // ---- write the owned tile ----
+    double* ophi = phi_out + chain * V;
+    int32_t* on0 = n_out + chain * 2 * V;
+    int32_t* on1 = on0 + V;
+    for (int p = tid; p < kTile * (kTile / 2); p += 128) {
+        const int i = p / (kTile / 2), jj = 2 * (p - i * (kTile / 2));
+        const long long g = (long long)(a0 + i) * N + (a1 + jj);
+        const int l = (i + 2) * kRegCols + (jj + 2);
+        *reinterpret_cast<double2*>(ophi + g) = *reinterpret_cast<const double2*>(sphi + l);
+        *reinterpret_cast<int2*>(on0 + g) = *reinterpret_cast<const int2*>(sn0 + l);
+        *reinterpret_cast<int2*>(on1 + g) = *reinterpret_cast<const int2*>(sn1 + l);
+    }
+    if (a.obs) {
+        double sred[2] = {n_acc, sum_A};
+        block_sum<2>(sred, red);
+        if (tid == 0) {
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, sred[0]);
+            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, sred[1]);
+        }
+        if (fuse_obs) {
+            __syncthreads();
+            ChainSums cs;
+            cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
+            for (int p = tid; p < kTile * kTile; p += 128) {
+                const int i = 2 + p / kTile, j = 2 + (p % kTile);
+                villain_obs_site<double, 0>(sphi, sn0, sn1, kRegCols, i, j, cs.action, cs.dn2, cs.w0, cs.w1);
+            }
+            double* scratch = reinterpret_cast<double*>(sr0);            // the residuals are no longer needed: 6 * 32 doubles
+            cs = block_reduce_chain(cs, scratch);
+            if (tid == 0) {
+                double* o = a.obs + chain * SVB_VOBS_COUNT;
+                atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * cs.action);
+                atomicAdd(o + SVB_VOBS_SUM_DN2, (double)cs.dn2);
+                atomicAdd(o + SVB_VOBS_WRAP0, (double)cs.w0);
+                atomicAdd(o + SVB_VOBS_WRAP1, (double)cs.w1);
+            }
+        }
+    }
 }
