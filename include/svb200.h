@@ -254,12 +254,12 @@ int svb_worldline_sweep(int32_t* m, int32_t* v,
                         void* stream);
 
 /*
- * The worldline sweep (SVB_WL_JOINT, W = 1, Philox draws, N in {16, 32, 64}) as OVERLAPPED launches: the same protocol
- * as svb_villain_sweep_overlapped (epochs, wait_epoch / signal_epoch, SVB_OVERLAP_PREDECESSOR); `obs` is the full record
- * of the state after the sweeps.
+ * The worldline sweeps (W = 1, Philox draws, N in {16, 32, 64}; interval 1 or 2 for VORTEX / COEXACT) as OVERLAPPED
+ * launches: the same protocol as svb_villain_sweep_overlapped (epochs, wait_epoch / signal_epoch,
+ * SVB_OVERLAP_PREDECESSOR); `obs` is the full record of the state after the sweeps.
  */
 int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t chains, int N,
-                                   double kappa, const double* kappa_chain,
+                                   double kappa, const double* kappa_chain, int mode, int interval,
                                    int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
                                    double* obs, uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch,
                                    int flags, void* stream);

@@ -41,7 +41,7 @@ SIGNATURES = {
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),
     'svb_worldline_sweep': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _i, _i, _u64, _u64, _u64, _i, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'svb_worldline_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _u64, _u64, _u64, _vp, _vp,
+    'svb_worldline_sweep_overlapped': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _i, _u64, _u64, _u64, _vp, _vp,
                                             ctypes.c_uint32, ctypes.c_uint32, _i, _vp]),
     'svb_worldline_observables': (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     'svb_worldline_wrapping': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp, _vp]),

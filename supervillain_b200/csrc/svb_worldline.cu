@@ -768,12 +768,13 @@ static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cu
             return fail(SVB_E_UNSUPPORTED, "N=%d does not fit shared memory; use SVB_PATH_GLOBAL", a.N);
         const bool aligned = ((uintptr_t)a.m % 16 == 0) && ((uintptr_t)a.v % 16 == 0);
 #ifndef SVB_NO_TABLE_KERNEL
-        if (MODE == SVB_WL_JOINT && rng_mode == SVB_RNG_PHILOX && a.W == 1 && aligned && !a.accept_mask && !a.dS_out) {
+        if ((MODE == SVB_WL_JOINT || a.interval <= 2) && rng_mode == SVB_RNG_PHILOX && a.W == 1 && aligned && !a.accept_mask &&
+            !a.dS_out) {
             // production path: tabulated integer acceptance thresholds on resident f (svb_worldline_table.cuh)
             switch (a.N) {
-                case 16: return launch_worldline_table<16, 16>(a, stream, sm_count);
-                case 32: return launch_worldline_table<32, 8>(a, stream, sm_count);
-                case 64: return launch_worldline_table<64, 4>(a, stream, sm_count);
+                case 16: return launch_worldline_table<MODE, 16, 16>(a, stream, sm_count);
+                case 32: return launch_worldline_table<MODE, 32, 8>(a, stream, sm_count);
+                case 64: return launch_worldline_table<MODE, 64, 4>(a, stream, sm_count);
                 default: break;
             }
         }
@@ -832,7 +833,8 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
 }
 
 extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t chains, int N, double kappa, const double* kappa_chain,
-                                              int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0, double* obs,
+                                              int mode, int interval, int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                                              double* obs,
                                               uint32_t* epochs, uint32_t wait_epoch, uint32_t signal_epoch, int flags,
                                               void* stream) {
     if (!m || !v || !epochs) return fail(SVB_E_NULL, "svb_worldline_sweep_overlapped: m, v and epochs are required");
@@ -840,12 +842,15 @@ extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t ch
     if (N != 16 && N != 32 && N != 64) return fail(SVB_E_UNSUPPORTED, "svb_worldline_sweep_overlapped: N must be 16, 32 or 64 (got %d)", N);
     if (((uintptr_t)m % 16) || ((uintptr_t)v % 16)) return fail(SVB_E_ALIGN, "svb_worldline_sweep_overlapped: fields must be 16-byte aligned");
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: kappa must be positive");
+    if (mode < SVB_WL_JOINT || mode > SVB_WL_COEXACT) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: mode %d", mode);
+    if (mode != SVB_WL_JOINT && (interval < 1 || interval > 2))
+        return fail(SVB_E_UNSUPPORTED, "svb_worldline_sweep_overlapped: interval must be 1 or 2 for VORTEX / COEXACT (got %d)", interval);
     if (n_sweeps < 1) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: n_sweeps must be >= 1 (every launch signals its epoch)");
     if (flags & ~SVB_OVERLAP_PREDECESSOR) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: flags");
     if (chains == 0) return SVB_OK;
     WorldlineArgs a;
     a.m = m; a.v = v; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = 1;
-    a.interval = 1; a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    a.interval = (mode == SVB_WL_JOINT) ? 1 : interval; a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
     for (int r = 0; r < 10; ++r) {
         a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -857,11 +862,16 @@ extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t ch
     SVB_CUDA_TRY(cudaGetDevice(&dev));
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (N) {
-        case 16: return launch_worldline_table<16, 16>(a, st, sm_count);
-        case 32: return launch_worldline_table<32, 8>(a, st, sm_count);
-        default: return launch_worldline_table<64, 4>(a, st, sm_count);
+#define SVB_WL_OV_DISPATCH(M)                                                                  \
+    switch (N) {                                                                               \
+        case 16: return launch_worldline_table<M, 16, 16>(a, st, sm_count);                    \
+        case 32: return launch_worldline_table<M, 32, 8>(a, st, sm_count);                     \
+        default: return launch_worldline_table<M, 64, 4>(a, st, sm_count);                     \
     }
+    if (mode == SVB_WL_JOINT) { SVB_WL_OV_DISPATCH(SVB_WL_JOINT) }
+    if (mode == SVB_WL_VORTEX) { SVB_WL_OV_DISPATCH(SVB_WL_VORTEX) }
+    SVB_WL_OV_DISPATCH(SVB_WL_COEXACT)
+#undef SVB_WL_OV_DISPATCH
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,8 +26,12 @@ struct WlTableEntry {
 constexpr int kWlTableS = 32;                      // s in [-32, 31]
 constexpr int kWlTableSize = 5 * 2 * kWlTableS;    // delta_f in [-2, 2]
 
+// MODE: SVB_WL_JOINT (PlaquetteUpdate's move), SVB_WL_VORTEX (dv = a alone: delta_f = -a, vortex.py:108-112) or SVB_WL_COEXACT
+// (dm = a alone: delta_f = +a, coexact.py:102-106), the latter two for interval <= 2.  Their reference formula sums four
+// separately rounded link terms; the table holds fl(fl(delta_f / kappa) s), equal to a few ulp, so the integer comparison is
+// trusted only at distance >= 2 from the threshold and the exact path evaluates the reference's own expression.
 // OVERLAP: the launch takes part in the overlapped-launch protocol (svb_common.cuh, svb_worldline_sweep_overlapped).
-template <int NT, int MINB, bool OVERLAP>
+template <int MODE, int NT, int MINB, bool OVERLAP>
 __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(const __grid_constant__ WorldlineArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
 
         int n_acc = 0;
         float sum_A = 0.0f;
-        const double inv_kappa = __ddiv_rn(1.0, kappa);
+        const double inv_kappa = __ddiv_rn(1.0, kappa), half_inv_kappa = __ddiv_rn(0.5, kappa);
         for (int s = 0; s < a.n_sweeps; ++s) {
             const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)s;
 #pragma unroll 1
@@ -130,12 +134,23 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                         const int o = 8 * N * q;                                               // row row8 + 8 q
                         const int od = (q == PER - 1 && row8 == 7) ? (o + N - V) : (o + N);    // row below (wraps after the last)
                         const uint32_t w = (wd == 0) ? bits.x : (wd == 1) ? bits.y : (wd == 2) ? bits.z : bits.w;
-                        // dm = +-1 from bit 31, dv in {-1, 0, 1} from the next bits, the remainder leads the uniform
-                        const uint64_t p = (uint64_t)(w << 1) * 3ull;
-                        const int hi = (int)(p >> 32);
-                        const uint32_t f = (uint32_t)p;
-                        const int dmh = (int)(w >> 31);                       // dm = 2 dmh - 1, dv = hi - 1
-                        const int df = 2 * dmh - hi;                          // delta_f = dm - dv
+                        int df, dv;                                           // delta_f on the (+) links; change of v[x]
+                        uint32_t f;
+                        if (MODE == SVB_WL_JOINT) {
+                            // dm = +-1 from bit 31, dv in {-1, 0, 1} from the next bits, the remainder leads the uniform
+                            const uint64_t p = (uint64_t)(w << 1) * 3ull;
+                            const int hi = (int)(p >> 32);
+                            f = (uint32_t)p;
+                            dv = hi - 1;
+                            df = 2 * (int)(w >> 31) - hi;                     // delta_f = dm - dv, dm = 2 (w >> 31) - 1
+                        } else {
+                            const uint64_t p = (uint64_t)w * (uint64_t)(2 * a.interval);
+                            const int idx = (int)(p >> 32);
+                            f = (uint32_t)p;
+                            const int ch = (idx < a.interval) ? idx - a.interval : idx - a.interval + 1;
+                            dv = (MODE == SVB_WL_VORTEX) ? ch : 0;
+                            df = (MODE == SVB_WL_VORTEX) ? -ch : ch;
+                        }
                         const int f0c = pF0c[o], f1d = pF1c[od], f0r = pF0r[o], f1c = pF1c[o];
                         const int sI = (f0c + f1d) - f0r - f1c + 2 * df;      // f1 + f2 - f3 - f4 + 2 delta_f
                         const int kk = df * sI;
@@ -147,10 +162,19 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                                 const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sI + kWlTableS];
                                 A = e.A;
                                 ok = f < e.thr;
-                                exact = (f - (e.thr - 1u)) <= 1u;            // f in {thr - 1, thr}: the bracket of u touches A
+                                exact = (f - (e.thr - 2u)) <= 3u;            // f within 2 of thr: the bracket of u may touch A
                             }
                             if (exact) {
-                                const double dS = __dmul_rn(__dmul_rn((double)df, inv_kappa), (double)sI);
+                                double dS;
+                                if (MODE == SVB_WL_JOINT) {
+                                    dS = __dmul_rn(__dmul_rn((double)df, inv_kappa), (double)sI);      // plaquette.py:84-85
+                                } else {
+                                    // coface_sum order: T(1,x) + T(1,x+e0) + T(0,x) + T(0,x+e1), T = ((0.5/kappa) c)((2 f) + c)
+                                    const double Pp = __dmul_rn(half_inv_kappa, (double)df), Pm = __dmul_rn(half_inv_kappa, (double)(-df));
+                                    dS = __dadd_rn(__dmul_rn(Pm, (double)(2 * f1c - df)), __dmul_rn(Pp, (double)(2 * f1d + df)));
+                                    dS = __dadd_rn(dS, __dmul_rn(Pp, (double)(2 * f0c + df)));
+                                    dS = __dadd_rn(dS, __dmul_rn(Pm, (double)(2 * f0r - df)));
+                                }
                                 const double Ad = exp_clipped(-dS);
                                 LazyUniform lu;
                                 lu.f = f; lu.c0 = c0; lu.word = (uint32_t)wd;
@@ -167,7 +191,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                             pF1c[od] = f1d + df;
                             pF0r[o] = f0r - df;
                             pF1c[o] = f1c - df;
-                            if (hi != 1) atomicAdd(pv + o, hi - 1);           // v[x] += dv; only this thread touches x in this pass
+                            if (MODE != SVB_WL_COEXACT && dv != 0) atomicAdd(pv + o, dv);    // only this thread touches x in this pass
                         }
                     }
                 }
@@ -227,7 +251,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
             }
         }
 
-        // ---- f -> m = f + delta v with the final v, in place ----
+        // ---- f -> m = f + delta v with the final v, in place (VORTEX leaves m as it was: nothing to write back) ----
+        if (MODE != SVB_WL_VORTEX)
 #pragma unroll
         for (int i4 = tid; i4 < V / 4; i4 += T) {
             const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
@@ -243,8 +268,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(a.m + chain * 2 * V, F0, bytes_m);
-            bulk_s2g(a.v + chain * V, sv, bytes_v);
+            if (MODE != SVB_WL_VORTEX) bulk_s2g(a.m + chain * 2 * V, F0, bytes_m);
+            if (MODE != SVB_WL_COEXACT) bulk_s2g(a.v + chain * V, sv, bytes_v);
             bulk_commit();
             bulk_wait_read0();
             if (next < a.chains) issue_load(next, seen_next);
@@ -257,10 +282,10 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
     }
 }
 
-template <int NT, int MINB>
+template <int MODE, int NT, int MINB>
 static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, int sm_count) {
     const bool overlap = a.ov.epochs != nullptr;
-    auto kern = overlap ? worldline_smem_table_kernel<NT, MINB, true> : worldline_smem_table_kernel<NT, MINB, false>;
+    auto kern = overlap ? worldline_smem_table_kernel<MODE, NT, MINB, true> : worldline_smem_table_kernel<MODE, NT, MINB, false>;
     const size_t smem = (size_t)NT * NT * 3 * sizeof(int32_t) + kWlTableSize * sizeof(WlTableEntry) + 4 * 32 * sizeof(long long) +
                         32 * sizeof(float) + 16;
     static int per_sm_cache[2] = {0, 0};

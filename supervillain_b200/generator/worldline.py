@@ -85,10 +85,11 @@ class _CheckerboardWorldline(Generator):
     def overlapped_device(self, m, v, *, chain0=0, kappa_chain=None):
         """Overlapped-launch stepping of one resident chain set (ops.WorldlineOverlappedSweeps): returns
         `step(n_sweeps=1, obs=None)` advancing the Philox counter, with `step.fence()` for foreign writes to the fields.
-        Serves PlaquetteUpdate's move with W = 1 and Philox draws; raises NotImplementedError otherwise."""
-        if self.mode != 'joint' or self.rng is not None or self.Action.W != 1 or self.path != 'auto':
-            raise NotImplementedError('overlapped launches serve the joint move with W = 1, Philox draws, path="auto"')
-        ov = ops.WorldlineOverlappedSweeps(m, v, self.kappa, seed=self.seed, chain0=chain0, kappa_chain=kappa_chain)
+        Serves W = 1 and Philox draws (interval <= 2 for vortex / coexact); raises NotImplementedError otherwise."""
+        if self.rng is not None or self.Action.W != 1 or self.path != 'auto':
+            raise NotImplementedError('overlapped launches serve W = 1, Philox draws, path="auto"')
+        ov = ops.WorldlineOverlappedSweeps(m, v, self.kappa, mode=self.mode, interval=self.interval, seed=self.seed, chain0=chain0,
+                                           kappa_chain=kappa_chain)
 
         def step(n_sweeps=1, obs=None, obs_in=None):
             if obs_in is not None:

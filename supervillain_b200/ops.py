@@ -203,14 +203,16 @@ class VillainOverlappedSweeps:
 
 
 class WorldlineOverlappedSweeps:
-    """Back-to-back Philox PlaquetteUpdate sweeps (mode 'joint', W = 1) of ONE chain set as overlapped launches
-    (svb_worldline_sweep_overlapped); the protocol and the `fence()` rule are those of `VillainOverlappedSweeps`."""
+    """Back-to-back Philox worldline sweeps (W = 1; mode 'joint', or 'vortex' / 'coexact' with interval <= 2) of ONE chain
+    set as overlapped launches (svb_worldline_sweep_overlapped); the protocol and the `fence()` rule are those of
+    `VillainOverlappedSweeps`."""
 
-    def __init__(self, m, v, kappa, *, seed=0, chain0=0, kappa_chain=None):
+    def __init__(self, m, v, kappa, *, mode='joint', interval=1, seed=0, chain0=0, kappa_chain=None):
         self.lib = _lib.load()
         self.chains, self.N = _fields_shape(m, 'm', 2)
-        if self.N not in OVERLAP_SIZES:
-            raise NotImplementedError('overlapped sweeps need N in (16, 32, 64)')
+        if self.N not in OVERLAP_SIZES or (mode != 'joint' and interval > 2):
+            raise NotImplementedError('overlapped sweeps need N in (16, 32, 64) and interval <= 2')
+        self.mode, self.interval = _WL_MODES[mode], int(interval)
         self.p_m = _dev(m, 'm', (torch.int32,))
         self.p_v = _dev(v, 'v', (torch.int32,), (self.chains, 1, self.N, self.N))
         self.p_kc = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (self.chains,))
@@ -230,7 +232,8 @@ class WorldlineOverlappedSweeps:
     def step(self, sweep0, n_sweeps=1, obs=None):
         p_obs = None if obs is None else _dev(obs, 'obs', (torch.float64,), (self.chains, WOBS_COUNT))
         e = self.epoch
-        code = self._fn(self.p_m, self.p_v, self.chains, self.N, self.kappa, self.p_kc, int(n_sweeps), self.seed, int(sweep0),
+        code = self._fn(self.p_m, self.p_v, self.chains, self.N, self.kappa, self.p_kc, self.mode, self.interval, int(n_sweeps),
+                        self.seed, int(sweep0),
                         self.chain0, p_obs, self.p_epochs, e & 0xFFFFFFFF, (e + 1) & 0xFFFFFFFF,
                         0 if self.fenced else _lib.OVERLAP_PREDECESSOR, self._stream().cuda_stream)
         if code:

@@ -209,8 +209,9 @@ def test_sequentially_plaquette_and_wrapping_in_a_batched_ensemble():
     np.testing.assert_allclose(E.ActionDensity[:, -1], ref, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize('mode', ['joint', 'vortex', 'coexact'])
 @pytest.mark.parametrize('N,chains', [(64, 700), (32, 1500), (16, 2500)])
-def test_overlapped_launches_equal_ordinary_launches(N, chains):
+def test_overlapped_launches_equal_ordinary_launches(N, chains, mode):
     """svb_worldline_sweep_overlapped: K overlapped steps leave exactly the fields and records of K ordinary launches."""
     kappa, K = 0.5, 6
     S = svb.Worldline(svb.Lattice2D(N), kappa)
@@ -218,9 +219,9 @@ def test_overlapped_launches_equal_ordinary_launches(N, chains):
     rm, rv = m.clone(), v.clone()
     rec_ref = torch.zeros((K, chains, WOBS_COUNT), dtype=torch.float64, device='cuda')
     for k in range(K):
-        ops.worldline_sweep(rm, rv, kappa, mode='joint', seed=13, sweep0=2 * k, n_sweeps=1 + (k % 2), obs=rec_ref[k])
+        ops.worldline_sweep(rm, rv, kappa, mode=mode, interval=2, seed=13, sweep0=2 * k, n_sweeps=1 + (k % 2), obs=rec_ref[k])
     rec = torch.zeros_like(rec_ref)
-    ov = ops.WorldlineOverlappedSweeps(m, v, kappa, seed=13)
+    ov = ops.WorldlineOverlappedSweeps(m, v, kappa, mode=mode, interval=2, seed=13)
     for k in range(K):
         ov.step(2 * k, 1 + (k % 2), obs=rec[k])
     torch.cuda.synchronize()
