@@ -224,11 +224,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()                                           # its first nvidia-smi fork lands in the warm-up, not in the timed region
     for k in range(args.warmup):
         step(k)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for k in range(args.steps):
@@ -323,8 +323,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='svb200', choices=['svb200', 'reference'])
     ap.add_argument('--sweeps-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     float* rc0 = reinterpret_cast<float*>(smem_raw + STAGES * stage_bytes);      // [colour][VH]: residual of link (0, x)
     float* rc1 = rc0 + V;                                                         // [colour][VH]: residual of link (1, x)
     double* red_state = reinterpret_cast<double*>(rc1 + V);                       // [NW][4] per-warp partial sums
-    double* red_count = red_state + 4 * 32;                                       // [NW][2]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red_count + 2 * 32);
+    double* red_count = red_state + 4 * NW;                                       // [NW][2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red_count + 2 * NW);
     constexpr int kWriter = 32;            // finishes the records: lane 0 of warp 1 (thread 0 is busy with the bulk copies)
 
     if (tid == 0) {
@@ -511,7 +511,7 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     auto kern = overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false>)
                         : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false>);
     const size_t V = (size_t)NT * NT;
-    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * 32 * sizeof(double) + 32;
+    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32;
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
     static int per_sm_cache[4][64];
     const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0);
