@@ -150,3 +150,37 @@ def test_gpu_generators_accept_the_reference_action_objects():
     with pytest.raises(ValueError):
         NeighborhoodUpdate(sv.action.Worldline(L, 0.5))
     assert len(G.Lattice.checkerboarding) == 2        # _replay uses the reference lattice's own colour lists
+
+
+def test_new_generators_keep_the_reference_constructor_contract():
+    """SiteUpdate / LinkUpdate / ExactUpdate / CohomologyUpdate: same constructor signatures, attributes and wrong-action
+    errors as the reference classes (site.py:23-38, link.py:32-48, exact.py:29-46, cohomology.py:44-60); no GPU needed."""
+    import supervillain_b200 as svb
+    from supervillain_b200.generator.villain import CohomologyUpdate, ExactUpdate, LinkUpdate, SiteUpdate
+    S = svb.Villain(svb.Lattice2D(6), 0.4, W=2)
+    Wl = svb.Worldline(svb.Lattice2D(6), 0.4)
+    for cls, kw, attr, value in ((SiteUpdate, {'interval_phi': 1.5}, 'interval_phi', 1.5), (LinkUpdate, {'interval_n': 2}, 'n_changes', (-2, -1, 1, 2)),
+                                 (ExactUpdate, {'interval_z': 2}, 'zs', (-2, -1, 1, 2)), (CohomologyUpdate, {'interval_h': 1}, 'h', (-1, 1))):
+        G = cls(S, **kw)
+        assert getattr(G, attr) == value and str(G) == cls.__name__
+        assert (G.accepted, G.proposed, G.sweeps, G.acceptance) == (0, 0, 0, 0.) and G.rng is None
+        assert G.inline_observables(5) == {}
+        with pytest.raises(ValueError):
+            cls(Wl)
+
+
+def test_no_cpu_fallback_for_the_overlapped_and_decoupled_paths():
+    import torch
+    from supervillain_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip('a device is present')
+    phi = torch.zeros((2, 1, 32, 32), dtype=torch.float64)
+    n = torch.zeros((2, 2, 32, 32), dtype=torch.int32)
+    with pytest.raises(ValueError):
+        ops.VillainOverlappedSweeps(phi, n, 0.5)
+    with pytest.raises(ValueError):
+        ops.villain_decoupled('link', phi, n, 0.5)
+    with pytest.raises(ValueError):
+        ops.villain_cohomology(phi, n, 0.5)
+    with pytest.raises(ValueError):
+        ops.WorldlineOverlappedSweeps(n, n[:, :1].contiguous(), 0.5)
