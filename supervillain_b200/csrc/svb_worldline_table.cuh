@@ -19,6 +19,12 @@
 // barriers per chain (five with observables).
 #pragma once
 
+__device__ __forceinline__ float fast_ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct WlTableEntry {
     uint32_t thr;      // floor(A 2^32) for A < 1
     float A;           // the acceptance probability, for the generator's statistic
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
         int n_acc = 0;
         float sum_A = 0.0f;
         const double inv_kappa = __ddiv_rn(1.0, kappa), half_inv_kappa = __ddiv_rn(0.5, kappa);
+        const float inv_kappa_f = (float)inv_kappa;
         for (int s = 0; s < a.n_sweeps; ++s) {
             const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)s;
 #pragma unroll 1
@@ -157,12 +164,19 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                         bool ok = true;
                         float A = 1.0f;
                         if (kk > 0) {                                         // dS > 0: a real Metropolis test
-                            bool exact = (unsigned)(sI + kWlTableS) >= (unsigned)(2 * kWlTableS);
-                            if (!exact) {
-                                const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sI + kWlTableS];
+                            // beyond the table A is below the edge entry of the same delta_f (dS grows with |s|): a uniform at
+                            // least 2 units above the edge threshold rejects for sure; otherwise (probability ~ A_edge) exact
+                            const int sC = min(max(sI, -kWlTableS), kWlTableS - 1);
+                            const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sC + kWlTableS];
+                            bool exact;
+                            if (sC == sI) {
                                 A = e.A;
                                 ok = f < e.thr;
                                 exact = (f - (e.thr - 2u)) <= 3u;            // f within 2 of thr: the bracket of u may touch A
+                            } else {
+                                A = fast_ex2f(-1.4426950408889634f * inv_kappa_f * (float)kk);
+                                ok = false;
+                                exact = f < e.thr + 2u || e.thr >= 0xFFFFFFFEu;
                             }
                             if (exact) {
                                 double dS;
