@@ -311,6 +311,15 @@ int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N,
 #define SVB_CORR_VORTEX  2
 int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int N, int W, double* out, void* stream);
 
+/*
+ * supervillain.analysis.autocorrelation (analysis/autocorrelation.py:7-66) for `series` scalar columns of length T at
+ * once (e.g. one observable of every chain): data (series, T) f64 -> C (series, T) f64, the circular autocorrelation
+ * function normalised to C(0) = 1, and tau (series,) i32, the ceiling of the integrated autocorrelation time up to the
+ * first zero of C.  mean: optional (series,) imposed means (NULL: computed from the data).  A series without
+ * fluctuations (|C(0)| < 1e-16 before normalisation, where the reference raises) gets tau = -1.  T <= 12800.
+ */
+int svb_autocorrelation(const double* data, int64_t series, int T, const double* mean, double* C, int32_t* tau, void* stream);
+
 /* Philox4x32-10 block, exposed for known-answer tests: out[4] = philox(ctr[4], key[2]) (host). */
 void svb_philox4x32_10_host(const uint32_t* ctr_host, const uint32_t* key_host, uint32_t* out_host);
 

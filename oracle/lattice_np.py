@@ -183,3 +183,20 @@ def correlation(f, g):
     Ff = np.fft.fftn(f, axes=(-2, -1), norm='ortho')
     Fg = np.fft.fftn(g, axes=(-2, -1), norm='ortho')
     return np.fft.fftn(Ff.conj() * Fg, axes=(-2, -1), norm='ortho') / np.sqrt(N2)
+
+
+def autocorrelation(data, mean=None, cutoff=1e-16):
+    """supervillain.analysis.autocorrelation (supervillain/analysis/autocorrelation.py:7-59), restated."""
+    data = np.asarray(data, dtype=np.float64)
+    if mean is None:
+        mean = data.mean()                                                  # :43-44
+    Delta = data - mean                                                     # :46
+    plus = np.fft.fft(Delta, norm='backward')                               # :48
+    minus = np.fft.ifft(Delta, norm='forward')                              # :49
+    C = np.fft.fft(plus * minus, norm='backward').real / (len(Delta)) ** 2  # :51
+    if np.abs(C[0]) < cutoff:                                               # :52-53
+        raise ValueError('The fluctuations are too small to reliably determine an autocorrelation.')
+    C /= C[0]                                                               # :54
+    clamped = np.clip(C, 0, None)                                           # :56
+    minIdx = np.argmin(clamped)                                             # :57
+    return C, int(np.ceil(C[:minIdx].sum()))                                # :58

@@ -13,6 +13,7 @@ from . import generator
 from . import batch
 from . import hostpath
 from . import sharding
+from . import analysis
 from .batch import Batch, Configurations
 from .ensemble import Ensemble, BatchedEnsemble
 from .lattice import Lattice, Lattice2D, Form, d, delta

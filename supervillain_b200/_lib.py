@@ -48,6 +48,7 @@ SIGNATURES = {
     'svb_form_op': (_i, [_i, _i, _i, _vp, _vp, _i64, _i, _vp]),
     'svb_villain_spin_spin': (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     'svb_correlation': (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp]),
+    'svb_autocorrelation': (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp]),
     'svb_philox4x32_10_host': (None, [_vp, _vp, _vp]),
     'svb_villain_draws': (_i, [_i64, _i, _i, _d, _i, _u64, _u64, _u64, _vp, _vp, _vp, _vp]),
 }

@@ -112,3 +112,97 @@ extern "C" int svb_correlation(int kind, const void* field, int dtype, int64_t c
 extern "C" int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N, double* out, void* stream) {
     return svb_correlation(SVB_CORR_SPIN, phi, phi_dtype, chains, N, 1, out, stream);
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Autocorrelation of scalar columns (supervillain/analysis/autocorrelation.py:7-66), one series per chain:
+//   Delta(t) = data(t) - mean;   C(tau) = <Delta(t + tau) Delta(t)> / <Delta(t)^2>  with t + tau wrapping around the
+//   series (the reference evaluates exactly this circular form with FFTs, :48-52);
+//   tau_int = ceil(sum_{tau < tau_0} C(tau)),  tau_0 = argmin(clip(C, 0, None))   (:57-59).
+// Direct O(T^2) sums out of shared memory, one CTA per series: exact to rounding (the reference's FFT result agrees to
+// ~1e-13) and cheap next to the sweeps that produced the series.  A series whose fluctuations are below the reference's
+// cutoff (:53) gets tau = -1 and C = 0 (the Python wrapper raises the reference's ValueError).
+// ------------------------------------------------------------------------------------------
+namespace svb {
+
+__global__ void __launch_bounds__(256) autocorrelation_kernel(const double* __restrict__ data, long long series, int T,
+                                                              const double* __restrict__ mean_in, double cutoff,
+                                                              double* __restrict__ C_out, int32_t* __restrict__ tau_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* delta = reinterpret_cast<double*>(smem_raw);           // T
+    double* corr = delta + T;                                      // T
+    __shared__ double scratch[32];
+    __shared__ double s_mean, s_c0;
+    const int tid = threadIdx.x;
+    for (long long c = blockIdx.x; c < series; c += gridDim.x) {
+        const double* x = data + c * T;
+        double part[1] = {0.0};
+        if (mean_in) {
+            if (tid == 0) s_mean = mean_in[c];
+        } else {
+            for (int t = tid; t < T; t += blockDim.x) part[0] += x[t];
+            block_sum<1>(part, scratch);
+            if (tid == 0) s_mean = part[0] / (double)T;
+        }
+        __syncthreads();
+        const double mean = s_mean;
+        for (int t = tid; t < T; t += blockDim.x) delta[t] = x[t] - mean;
+        __syncthreads();
+        for (int tau = tid; tau < T; tau += blockDim.x) {
+            double acc = 0.0;
+            int u = tau;
+            for (int t = 0; t < T; ++t) {
+                acc = fma(delta[t], delta[u], acc);
+                u = (u + 1 == T) ? 0 : u + 1;
+            }
+            corr[tau] = acc / (double)T;
+        }
+        __syncthreads();
+        if (tid == 0) s_c0 = corr[0];
+        __syncthreads();
+        const double c0 = s_c0;
+        const bool flat = fabs(c0) < cutoff;
+        for (int tau = tid; tau < T; tau += blockDim.x) {
+            const double v = flat ? 0.0 : corr[tau] / c0;
+            corr[tau] = v;
+            if (C_out) C_out[c * T + tau] = v;
+        }
+        __syncthreads();
+        if (tid == 0 && tau_out) {
+            int tau = -1;
+            if (!flat) {
+                // argmin of the clamped function: its first zero if there is one, else its smallest positive value
+                int arg = 0;
+                double best = fmax(corr[0], 0.0);
+                for (int t = 1; t < T && best > 0.0; ++t) {
+                    const double v = fmax(corr[t], 0.0);
+                    if (v < best) { best = v; arg = t; }
+                }
+                // np.sum over C[:arg] is pairwise in numpy; tau is its ceiling, insensitive to the order unless the sum
+                // sits within rounding of an integer
+                double sum = 0.0;
+                for (int t = 0; t < arg; ++t) sum += corr[t];
+                tau = (int)ceil(sum);
+            }
+            tau_out[c] = tau;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace svb
+
+extern "C" int svb_autocorrelation(const double* data, int64_t series, int T, const double* mean, double* C, int32_t* tau,
+                                   void* stream) {
+    using namespace svb;
+    if (!data || (!C && !tau)) return fail(SVB_E_NULL, "svb_autocorrelation: data and at least one output are required");
+    if (series < 0 || T < 1) return fail(SVB_E_SHAPE, "svb_autocorrelation: series=%lld T=%d", (long long)series, T);
+    const size_t smem = (size_t)2 * T * sizeof(double);
+    if (smem > 200 * 1024) return fail(SVB_E_UNSUPPORTED, "svb_autocorrelation: T=%d does not fit shared memory (T <= 12800)", T);
+    if (series == 0) return SVB_OK;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(autocorrelation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = series < 148LL * 8 ? series : 148LL * 8;
+    autocorrelation_kernel<<<(unsigned)grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(data, series, T, mean, 1e-16, C, tau);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}

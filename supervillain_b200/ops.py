@@ -451,3 +451,18 @@ def philox4x32_10(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     lib.svb_philox4x32_10_host(c.ctypes.data, k.ctypes.data, out.ctypes.data)
     return out
+
+
+def autocorrelation(data, mean=None, *, want_C=True):
+    """supervillain.analysis.autocorrelation for every row of `data` (series, T) float64 on the device
+    (svb_autocorrelation) -> (C (series, T) or None, tau (series,) int32; -1 where the series does not fluctuate)."""
+    lib = _lib.load()
+    if data.dim() != 2:
+        raise ValueError(f'data must have shape (series, T); got {tuple(data.shape)}')
+    series, T = int(data.shape[0]), int(data.shape[1])
+    p_data = _dev(data, 'data', (torch.float64,))
+    C = torch.empty((series, T), dtype=torch.float64, device=data.device) if want_C else None
+    tau = torch.empty((series,), dtype=torch.int32, device=data.device)
+    _lib.check(lib.svb_autocorrelation(p_data, series, T, _opt(mean, 'mean', (torch.float64,), (series,)),
+                                       None if C is None else C.data_ptr(), tau.data_ptr(), _stream()))
+    return C, tau

@@ -75,3 +75,8 @@ def golden_villain_decoupled():
 @pytest.fixture(scope='session')
 def golden_villain_cohomology():
     return load_golden('villain_cohomology')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_autocorrelation():
+    return load_golden('autocorrelation')[0]

@@ -332,9 +332,26 @@ def villain_cohomology():
     print('accepted per case:', [int(c['accepted'].sum()) for c in cases])
 
 
+def autocorrelation():
+    """supervillain.analysis.autocorrelation on AR(1) series of various lengths and correlation times, and on an observable
+    column of a reference chain."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for T, rho in [(64, 0.5), (257, 0.9), (1000, 0.97), (2048, 0.0), (4096, 0.995)]:
+        x = np.zeros(T)
+        for t in range(1, T):
+            x[t] = rho * x[t - 1] + rng.normal()
+        x += 3.0
+        C, tau = sv.analysis.autocorrelation(x)
+        C2, tau2 = sv.analysis.autocorrelation(x, mean=3.0)
+        cases.append(dict(data=x, C=C, tau=tau, C_mean3=C2, tau_mean3=tau2))
+    _pack(cases, 'autocorrelation')
+    print('tau per case:', [int(c['tau']) for c in cases], [int(c['tau_mean3']) for c in cases])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
                              'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping',
-                             'villain_decoupled', 'villain_cohomology']
+                             'villain_decoupled', 'villain_cohomology', 'autocorrelation']
     for name in which:
         globals()[name]()

@@ -127,3 +127,29 @@ def test_winding_and_vortex_correlators_match_reference(golden_villain_observabl
         v = torch.from_numpy(c['v'][None]).to(torch.int32).cuda()
         C = ops.correlation('vortex', v, W=int(c['W'])).cpu().numpy()[0]
         np.testing.assert_allclose(C, c['Vortex_Vortex'], rtol=0, atol=1e-12)
+
+
+def test_autocorrelation_matches_reference(golden_autocorrelation):
+    """svb_autocorrelation (direct circular sums) against supervillain.analysis.autocorrelation (FFT): C within 1e-11 of
+    C(0) = 1, tau identical; one series per chain at once; the reference's ValueError for a flat series."""
+    import supervillain_b200 as svb
+    from oracle import lattice_np as lat
+    for c in golden_autocorrelation:
+        C, tau = svb.analysis.autocorrelation(c['data'])
+        np.testing.assert_allclose(C, c['C'], rtol=0, atol=1e-11)
+        assert tau == int(c['tau'])
+        C, tau = svb.analysis.autocorrelation(c['data'], mean=3.0)
+        np.testing.assert_allclose(C, c['C_mean3'], rtol=0, atol=1e-11)
+        assert tau == int(c['tau_mean3'])
+        assert svb.analysis.autocorrelation_time(c['data']) == int(c['tau'])
+    # a batch: the ActionDensity columns of many chains
+    S = svb.Villain(svb.Lattice2D(8), 0.4)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=3)
+    E = svb.BatchedEnsemble(S, 48).generate(300, G, 'hot', start_seed=1)
+    C, tau = svb.analysis.autocorrelation(E.ActionDensity)
+    for k in range(48):
+        Cr, tr = lat.autocorrelation(E.ActionDensity[k])
+        np.testing.assert_allclose(C[k], Cr, rtol=0, atol=1e-11)
+        assert tau[k] == tr
+    with pytest.raises(ValueError):
+        svb.analysis.autocorrelation(np.ones(32))

@@ -155,3 +155,14 @@ def test_cohomology_update_reproduces_reference_chains(golden_villain_cohomology
                 assert (n_ == c['n'][s]).all(), (N, s)
                 assert stats['accepted'] == int(c['accepted'][s])
                 assert stats['acceptance'] / 2 == pytest.approx(float(c['acceptance'][s]), rel=1e-12)
+
+
+def test_autocorrelation_restatement_matches_reference(golden_autocorrelation):
+    from oracle import lattice_np as lat
+    for c in golden_autocorrelation:
+        C, tau = lat.autocorrelation(c['data'])
+        assert (C == c['C']).all() and tau == int(c['tau'])
+        C, tau = lat.autocorrelation(c['data'], mean=3.0)
+        assert (C == c['C_mean3']).all() and tau == int(c['tau_mean3'])
+    with pytest.raises(ValueError):
+        lat.autocorrelation(np.ones(16))
