@@ -1989,8 +1989,11 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
             villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
         else
 #ifndef SVB_NO_FILTERED_KERNEL
-            villain_tiled_filtered_kernel<<<(unsigned)blocks, 128, 0, st>>>(a, make_filter_consts(interval_phi, W, interval_n), bufp[src],
-                                                                            bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
+        {
+            const int rc = launch_villain_tiled_filtered(a, make_filter_consts(interval_phi, W, interval_n), bufp[src], bufn[src],
+                                                         bufp[dst], bufn[dst], s, tps, fuse, blocks, st);
+            if (rc) return rc;
+        }
 #else
             villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
 #endif

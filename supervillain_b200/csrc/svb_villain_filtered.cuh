@@ -551,204 +551,299 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
 // decided in fp32 with the exact fp64 + lazy-uniform test inside the error band, phi / n are touched on acceptance.
 // Philox is keyed by the GLOBAL site, so redundant ghost updates are bit-identical in every tile that computes them --
 // including the (rare) exact-path decisions, which depend only on the global state around the site.
+//
+// Table-driven: what does not depend on the tile -- the list of work items of each colour pass -- is tabulated once per
+// process.  An item is the PAIR of region rows (r, r + 8) of one column that share a Philox block (rows 0..7 and 16..23 of
+// the tile, bit 3 of the global row clear), or a single site for the ghost rows whose partner lies outside the region;
+// per tile only the wrapped global coordinates of the region's rows and columns are tabulated.  A proposal then costs a
+// table entry and two coordinate look-ups instead of divisions and wraps, and half a Philox block.
 // ------------------------------------------------------------------------------------------
+constexpr int kItemsPerPass = 384;                 // 3 rounds of 128 threads
+constexpr unsigned kNoSite = 0xFFFFu;
+
+// per colour: local index of site A | local index of site B << 16 (kNoSite: none).  The same for every tile of every
+// lattice: filled once per process by villain_tiled_items_kernel (like a kernel attribute, not state of any call).
+__device__ uint32_t g_tiled_items[2][kItemsPerPass];
+
+struct TiledShared {
+    double phi[kRegSize];
+    int32_t n0[kRegSize];
+    int32_t n1[kRegSize];
+    float r0[kRegSize];            // residual of link (0, x): x -> x + e0 (valid for local rows < 36)
+    float r1[kRegSize];            // residual of link (1, x): x -> x + e1 (valid for local cols < 36)
+    int x0row[kRegRows + 3];       // wrapped global row of local row i
+    int x1col[kRegCols + 2];       // wrapped global column of local column j
+    double red[2 * 32];
+};
+
+// One proposal at local index l of the region (global site (x0, x1)); returns the acceptance estimate, sets ok.
+__device__ __forceinline__ float villain_tiled_site(TiledShared& sh, const VillainArgs& a, const FilterConsts& fc, int l, uint32_t wA,
+                                                    uint32_t wB, uint32_t c0, uint32_t half, double half_kappa, float hk2, float hkA,
+                                                    float hkB, uint32_t K, int W, int mWI, float cIn, unsigned long long gc,
+                                                    unsigned long long gs, bool& ok) {
+    uint32_t f = wB;
+    int dig[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint64_t prod = (uint64_t)f * K;
+        f = (uint32_t)prod;
+        dig[q] = (int)(prod >> 32);
+    }
+    const float U = __uint_as_float(0x3F800000u | (wA >> 9)) - 0.99999994f;
+    const float dphi = fmaf(fc.two_I, U, -fc.I);
+    const float base_f = cIn - dphi, base_b = cIn + dphi;
+    const float r_f0 = sh.r0[l], r_b0 = sh.r0[l - kRegCols], r_f1 = sh.r1[l], r_b1 = sh.r1[l - 1];
+    const float dr_f0 = fmaf(-fc.c, (float)dig[0], base_f), dr_b0 = fmaf(-fc.c, (float)dig[1], base_b);
+    const float dr_f1 = fmaf(-fc.c, (float)dig[2], base_f), dr_b1 = fmaf(-fc.c, (float)dig[3], base_b);
+    float acc2 = dr_f0 * fmaf(2.0f, r_f0, dr_f0);
+    acc2 = fmaf(dr_b0, fmaf(2.0f, r_b0, dr_b0), acc2);
+    acc2 = fmaf(dr_f1, fmaf(2.0f, r_f1, dr_f1), acc2);
+    acc2 = fmaf(dr_b1, fmaf(2.0f, r_b1, dr_b1), acc2);
+    const float dS2 = hk2 * acc2;
+    const float L2 = 32.0f - fast_lg2((float)f);
+    const float Rmax = fmaxf(fmaxf(fabsf(r_f0), fabsf(r_b0)), fmaxf(fabsf(r_f1), fabsf(r_b1)));
+    const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L2, hkB));
+    const float diff = dS2 - L2;
+    ok = diff < 0.0f;
+    const float Aest = fminf(fast_ex2(-dS2), 1.0f);
+    if (!(fabsf(diff) > band) || f < 65536u) {
+        ExactProposal ep;
+        ep.phi = sh.phi; ep.n0 = sh.n0; ep.n1 = sh.n1;
+        ep.i_c = l; ep.i_b0 = l - kRegCols; ep.i_b1 = l - 1; ep.i_f0 = l + kRegCols; ep.i_f1 = l + 1;
+        ep.half_kappa = half_kappa;
+        ep.c = SVB_TWO_PI * (double)W;
+        ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ep.g[q] = dig[q] - a.interval_n;
+        ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
+        ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
+        ok = villain_exact_decision(ep);
+    }
+    if (ok) {
+        sh.phi[l] = __dadd_rn(sh.phi[l], villain_dphi_from_word(wA, a.interval_phi));
+        sh.n0[l] += W * dig[0] + mWI;
+        sh.n0[l - kRegCols] += W * dig[1] + mWI;
+        sh.n1[l] += W * dig[2] + mWI;
+        sh.n1[l - 1] += W * dig[3] + mWI;
+        sh.r0[l] = r_f0 + dr_f0;
+        sh.r0[l - kRegCols] = r_b0 + dr_b0;
+        sh.r1[l] = r_f1 + dr_f1;
+        sh.r1[l - 1] = r_b1 + dr_b1;
+    }
+    return Aest;
+}
+
+// The work items of the two colour passes.  Colour c works on local [lo, lo + side)^2, lo = 1 / 2, side = 35 / 33; tile row
+// r = i - 2.  Rows r in {0..7, 16..23} pair with r + 8 (same column, same colour); the remaining rows of the pass (c = 0:
+// r = -1, 32, 33; c = 1: r = 32) are single.
+__global__ void villain_tiled_items_kernel() {
+    for (int c = 0; c < 2; ++c) {
+        const int lo = (c == 0) ? 1 : 2, side = (c == 0) ? kTile + 3 : kTile + 1, per_row = (side + 1) / 2;
+        const int n_single = (c == 0) ? 3 : 1;
+        for (int e = threadIdx.x; e < kItemsPerPass; e += blockDim.x) {
+            uint32_t item = kNoSite | (kNoSite << 16);
+            const int row_slot = e / per_row, kcol = e - row_slot * per_row;
+            if (row_slot < 16 + n_single) {
+                int rA, rB = -100;
+                if (row_slot < 16) {
+                    rA = (row_slot < 8) ? row_slot : row_slot + 8;
+                    rB = rA + 8;
+                } else {
+                    rA = (c == 0) ? ((row_slot == 16) ? -1 : 32 + (row_slot - 17)) : 32;
+                }
+                const int iA = rA + 2;
+                const int j = lo + 2 * kcol + ((iA + lo + c) & 1);          // (i + j) & 1 == c (tile origins are even)
+                if (j < lo + side) {
+                    const uint32_t lA = (uint32_t)(iA * kRegCols + j);
+                    const uint32_t lB = (rB > -100) ? (uint32_t)((rB + 2) * kRegCols + j) : kNoSite;
+                    item = lA | (lB << 16);
+                }
+            }
+            g_tiled_items[c][e] = item;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, 6) villain_tiled_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                         const __grid_constant__ FilterConsts fc,
                                                                         const double* __restrict__ phi_in,
                                                                         const int32_t* __restrict__ n_in, double* __restrict__ phi_out,
                                                                         int32_t* __restrict__ n_out, int sweep, int tiles_per_side,
                                                                         int fuse_obs) {
-    __shared__ __align__(16) double sphi[kRegSize];
-    __shared__ __align__(16) int32_t sn0[kRegSize];
-    __shared__ __align__(16) int32_t sn1[kRegSize];
-    __shared__ __align__(16) float sr0[kRegSize];        // residual of link (0, x): x -> x + e0 (valid for local rows < 36)
-    __shared__ __align__(16) float sr1[kRegSize];        // residual of link (1, x): x -> x + e1 (valid for local cols < 36)
-    __shared__ double red[2 * 32];
+    extern __shared__ __align__(16) unsigned char tiled_smem_raw[];
+    TiledShared& sh = *reinterpret_cast<TiledShared*>(tiled_smem_raw);
     const int N = a.N;
-    const long long V = (long long)N * N;
+    const unsigned V = (unsigned)N * (unsigned)N;
     const int tiles = tiles_per_side * tiles_per_side;
-    const long long chain = blockIdx.x / tiles;
-    const int tile = blockIdx.x - (int)(chain * tiles);
-    const int a0 = (tile / tiles_per_side) * kTile, a1 = (tile % tiles_per_side) * kTile;
     const int tid = threadIdx.x;
-    const double* gphi = phi_in + chain * V;
-    const int32_t* gn0 = n_in + chain * 2 * V;
-    const int32_t* gn1 = gn0 + V;
 
-    // ---- load the region, two sites at a time (N and the origins are even: a pair never straddles the wrap);
-    //      offsets inside one chain fit 32 bits (N <= 32768).  All of a thread's loads are issued before the first
-    //      shared-memory store, so ~18 requests per thread are in flight instead of 3 ----
-    {
-        constexpr int kPairs = kRegRows * (kRegCols / 2), kIter = (kPairs + 127) / 128;
-        double2 vp[kIter];
-        int2 v0[kIter], v1[kIter];
-#pragma unroll
-        for (int t = 0; t < kIter; ++t) {
-            const int p = tid + 128 * t;
-            if (p < kPairs) {
-                const int i = p / (kRegCols / 2), jj = 2 * (p - i * (kRegCols / 2));
-                int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
-                int x1 = a1 - 2 + jj; x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
-                const unsigned g = (unsigned)x0 * (unsigned)N + (unsigned)x1;
-                vp[t] = *reinterpret_cast<const double2*>(gphi + g);
-                v0[t] = *reinterpret_cast<const int2*>(gn0 + g);
-                v1[t] = *reinterpret_cast<const int2*>(gn1 + g);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < kIter; ++t) {
-            const int p = tid + 128 * t;
-            if (p < kPairs) {
-                *reinterpret_cast<double2*>(sphi + 2 * p) = vp[t];           // 2 p = i * kRegCols + jj (kRegCols is even)
-                *reinterpret_cast<int2*>(sn0 + 2 * p) = v0[t];
-                *reinterpret_cast<int2*>(sn1 + 2 * p) = v1[t];
-            }
-        }
-    }
-    __syncthreads();
-    // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) for the links inside the region, fp64 rounded to fp32, two sites per
-    //      step (rows 0..35; the last pair of a row produces a link past the region that nothing reads) ----
-    for (int p = tid; p < (kRegRows - 1) * (kRegCols / 2); p += 128) {
-        const int i = p / (kRegCols / 2);
-        const int l = 2 * p;                                        // = i * kRegCols + jj, kRegCols is even
-        const double2 pc = *reinterpret_cast<const double2*>(sphi + l);
-        const double2 pu = *reinterpret_cast<const double2*>(sphi + l + kRegCols);
-        const double pr = sphi[l + 2];
-        const int2 b0 = *reinterpret_cast<const int2*>(sn0 + l), b1 = *reinterpret_cast<const int2*>(sn1 + l);
-        float2 o0, o1;
-        o0.x = (float)fma(-SVB_TWO_PI, int_to_double(b0.x), pu.x - pc.x);
-        o0.y = (float)fma(-SVB_TWO_PI, int_to_double(b0.y), pu.y - pc.y);
-        o1.x = (float)fma(-SVB_TWO_PI, int_to_double(b1.x), pc.y - pc.x);
-        o1.y = (float)fma(-SVB_TWO_PI, int_to_double(b1.y), pr - pc.y);
-        *reinterpret_cast<float2*>(sr0 + l) = o0;
-        *reinterpret_cast<float2*>(sr1 + l) = o1;
-        (void)i;
-    }
-    __syncthreads();
-
-    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
-    const double half_kappa = kappa / 2;
-    const float hk2 = (float)(half_kappa * 1.4426950408889634);
-    const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
     const uint32_t K = (uint32_t)(2 * a.interval_n + 1);
     const int W = a.W, mWI = -a.W * a.interval_n;
     const float cIn = fc.c * (float)a.interval_n;
-    const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
-    double n_acc = 0.0, sum_A = 0.0;
+    const unsigned long long gs = a.sweep0 + (unsigned long long)sweep;
+    // this thread's work items of both passes: fetched now, needed after the region has been loaded
+    uint32_t my_items[2][kItemsPerPass / 128];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int u = 0; u < kItemsPerPass / 128; ++u) my_items[c][u] = g_tiled_items[c][tid + 128 * u];
 
-    // one colour pass with compile-time geometry: colour 0 on local [1, 36) (35 x 35), colour 1 on local [2, 35) (33 x 33)
-    auto colour_pass = [&](auto colour_tag) {
-        constexpr int c = decltype(colour_tag)::value;
-        constexpr int lo = (c == 0) ? 1 : 2;
-        constexpr int side = (c == 0) ? kTile + 3 : kTile + 1;
-        constexpr int per_row = (side + 1) / 2;
-        // global coordinates of local (lo, *): one conditional wrap per step instead of a modulo per site
-        for (int idx = tid; idx < side * per_row; idx += 128) {
-            const int di = idx / per_row;                                        // constant divisor
-            const int i = lo + di;
-            const int j = lo + 2 * (idx - di * per_row) + ((i + lo + c) & 1);   // (i + j) & 1 == c  (origins are even)
-            if (j >= lo + side) continue;
-            int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
-            int x1 = a1 - 2 + j;  x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
-            const int l = i * kRegCols + j;
-            const uint32_t c0 = villain_pair_counter(x0, x1, N), half = villain_pair_half(x0);            const Philox4 bits = philox_site_keys(a, gc, gs, c0);
-            const uint32_t wA = half ? bits.z : bits.x, wB = half ? bits.w : bits.y;
-            uint32_t f = wB;
-            int dig[4];
+    {
+        const long long t = blockIdx.x;                             // one tile per CTA: CTA scheduling staggers the loads
+        const long long chain = t / tiles;
+        const int tile = (int)(t - chain * tiles);
+        const int a0 = (tile / tiles_per_side) * kTile, a1 = (tile % tiles_per_side) * kTile;
+        const double* gphi = phi_in + chain * V;
+        const int32_t* gn0 = n_in + chain * 2 * V;
+        const int32_t* gn1 = gn0 + V;
+        // wrapped global coordinates of the region's rows and columns, for the colour passes (first read behind two barriers)
+        if (tid < kRegRows) {
+            int x0 = a0 - 2 + tid;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+            sh.x0row[tid] = x0;
+        } else if (tid >= 64 && tid < 64 + kRegCols) {
+            int x1 = a1 - 2 + (tid - 64);  x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+            sh.x1col[tid - 64] = x1;
+        }
+
+        // ---- load the region, two sites at a time (N and the origins are even: a pair never straddles the wrap); all of a
+        //      thread's loads are issued before its first shared-memory store ----
+        {
+            constexpr int kPairs = kRegRows * (kRegCols / 2), kIter = (kPairs + 127) / 128;
+            double2 vp[kIter];
+            int2 v0[kIter], v1[kIter];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint64_t prod = (uint64_t)f * K;
-                f = (uint32_t)prod;
-                dig[q] = (int)(prod >> 32);
+            for (int u = 0; u < kIter; ++u) {
+                const int p = tid + 128 * u;
+                if (p < kPairs) {
+                    const int i = p / (kRegCols / 2), jj = 2 * (p - i * (kRegCols / 2));
+                    int x0 = a0 - 2 + i;  x0 += (x0 < 0) ? N : 0;  x0 -= (x0 >= N) ? N : 0;
+                    int x1 = a1 - 2 + jj; x1 += (x1 < 0) ? N : 0;  x1 -= (x1 >= N) ? N : 0;
+                    const unsigned g = (unsigned)x0 * (unsigned)N + (unsigned)x1;
+                    vp[u] = *reinterpret_cast<const double2*>(gphi + g);
+                    v0[u] = *reinterpret_cast<const int2*>(gn0 + g);
+                    v1[u] = *reinterpret_cast<const int2*>(gn1 + g);
+                }
             }
-            const float U = __uint_as_float(0x3F800000u | (wA >> 9)) - 0.99999994f;
-            const float dphi = fmaf(fc.two_I, U, -fc.I);
-            const float base_f = cIn - dphi, base_b = cIn + dphi;
-            const float r_f0 = sr0[l], r_b0 = sr0[l - kRegCols], r_f1 = sr1[l], r_b1 = sr1[l - 1];
-            const float dr_f0 = fmaf(-fc.c, (float)dig[0], base_f), dr_b0 = fmaf(-fc.c, (float)dig[1], base_b);
-            const float dr_f1 = fmaf(-fc.c, (float)dig[2], base_f), dr_b1 = fmaf(-fc.c, (float)dig[3], base_b);
-            float acc2 = dr_f0 * fmaf(2.0f, r_f0, dr_f0);
-            acc2 = fmaf(dr_b0, fmaf(2.0f, r_b0, dr_b0), acc2);
-            acc2 = fmaf(dr_f1, fmaf(2.0f, r_f1, dr_f1), acc2);
-            acc2 = fmaf(dr_b1, fmaf(2.0f, r_b1, dr_b1), acc2);
-            const float dS2 = hk2 * acc2;
-            const float L2 = 32.0f - fast_lg2((float)f);
-            const float Rmax = fmaxf(fmaxf(fabsf(r_f0), fabsf(r_b0)), fmaxf(fabsf(r_f1), fabsf(r_b1)));
-            const float band = fmaf(hkA, Rmax, fmaf(4e-6f, L2, hkB));
-            const float diff = dS2 - L2;
-            bool ok = diff < 0.0f;
-            const float Aest = fminf(fast_ex2(-dS2), 1.0f);
-            if (!(fabsf(diff) > band) || f < 65536u) {
-                ExactProposal ep;
-                ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1;
-                ep.i_c = l; ep.i_b0 = l - kRegCols; ep.i_b1 = l - 1; ep.i_f0 = l + kRegCols; ep.i_f1 = l + 1;
-                ep.half_kappa = half_kappa;
-                ep.c = SVB_TWO_PI * (double)W;
-                ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ep.g[q] = dig[q] - a.interval_n;
-                ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
-                ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
-                ok = villain_exact_decision(ep);
-            }
-            if (ok) {
-                sphi[l] = __dadd_rn(sphi[l], villain_dphi_from_word(wA, a.interval_phi));
-                sn0[l] += W * dig[0] + mWI;
-                sn0[l - kRegCols] += W * dig[1] + mWI;
-                sn1[l] += W * dig[2] + mWI;
-                sn1[l - 1] += W * dig[3] + mWI;
-                sr0[l] = r_f0 + dr_f0;
-                sr0[l - kRegCols] = r_b0 + dr_b0;
-                sr1[l] = r_f1 + dr_f1;
-                sr1[l - 1] = r_b1 + dr_b1;
-            }
-            const bool owned = (i >= 2) && (i < 2 + kTile) && (j >= 2) && (j < 2 + kTile);
-            if (owned) {
-                n_acc += ok ? 1.0 : 0.0;
-                sum_A += (double)Aest;
+            for (int u = 0; u < kIter; ++u) {
+                const int p = tid + 128 * u;
+                if (p < kPairs) {
+                    *reinterpret_cast<double2*>(sh.phi + 2 * p) = vp[u];        // 2 p = i * kRegCols + jj (kRegCols is even)
+                    *reinterpret_cast<int2*>(sh.n0 + 2 * p) = v0[u];
+                    *reinterpret_cast<int2*>(sh.n1 + 2 * p) = v1[u];
+                }
             }
         }
         __syncthreads();
-    };
-    colour_pass(std::integral_constant<int, 0>{});
-    colour_pass(std::integral_constant<int, 1>{});
+        // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) for the links inside the region, fp64 rounded to fp32, two sites
+        //      per step (rows 0..35; the last pair of a row produces a link past the region that nothing reads) ----
+        for (int p = tid; p < (kRegRows - 1) * (kRegCols / 2); p += 128) {
+            const int l = 2 * p;
+            const double2 pc = *reinterpret_cast<const double2*>(sh.phi + l);
+            const double2 pu = *reinterpret_cast<const double2*>(sh.phi + l + kRegCols);
+            const double pr = sh.phi[l + 2];
+            const int2 b0 = *reinterpret_cast<const int2*>(sh.n0 + l), b1 = *reinterpret_cast<const int2*>(sh.n1 + l);
+            float2 o0, o1;
+            o0.x = (float)fma(-SVB_TWO_PI, int_to_double(b0.x), pu.x - pc.x);
+            o0.y = (float)fma(-SVB_TWO_PI, int_to_double(b0.y), pu.y - pc.y);
+            o1.x = (float)fma(-SVB_TWO_PI, int_to_double(b1.x), pc.y - pc.x);
+            o1.y = (float)fma(-SVB_TWO_PI, int_to_double(b1.y), pr - pc.y);
+            *reinterpret_cast<float2*>(sh.r0 + l) = o0;
+            *reinterpret_cast<float2*>(sh.r1 + l) = o1;
+        }
+        __syncthreads();
 
-    // ---- write the owned tile ----
-    double* ophi = phi_out + chain * V;
-    int32_t* on0 = n_out + chain * 2 * V;
-    int32_t* on1 = on0 + V;
-    for (int p = tid; p < kTile * (kTile / 2); p += 128) {
-        const int i = p / (kTile / 2), jj = 2 * (p - i * (kTile / 2));
-        const long long g = (long long)(a0 + i) * N + (a1 + jj);
-        const int l = (i + 2) * kRegCols + (jj + 2);
-        *reinterpret_cast<double2*>(ophi + g) = *reinterpret_cast<const double2*>(sphi + l);
-        *reinterpret_cast<int2*>(on0 + g) = *reinterpret_cast<const int2*>(sn0 + l);
-        *reinterpret_cast<int2*>(on1 + g) = *reinterpret_cast<const int2*>(sn1 + l);
-    }
-    if (a.obs) {
-        double sred[2] = {n_acc, sum_A};
-        block_sum<2>(sred, red);
-        if (tid == 0) {
-            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, sred[0]);
-            atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, sred[1]);
-        }
-        if (fuse_obs) {
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double half_kappa = kappa / 2;
+        const float hk2 = (float)(half_kappa * 1.4426950408889634);
+        const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+        const unsigned long long gc = a.chain0 + (unsigned long long)chain;
+        float n_acc = 0.0f, sum_A = 0.0f;
+
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll 1
+            for (int u = 0; u < kItemsPerPass / 128; ++u) {
+                const uint32_t item = (u == 0) ? my_items[c][0] : (u == 1) ? my_items[c][1] : my_items[c][2];
+                const uint32_t lA = item & 0xFFFFu, lB = item >> 16;
+                if (lA == kNoSite) continue;
+                const int iA = (int)lA / kRegCols, j = (int)lA - iA * kRegCols;
+                const int x0 = sh.x0row[iA], x1 = sh.x1col[j];
+                const uint32_t c0 = villain_pair_counter(x0, x1, N);
+                const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+                const uint32_t halfA = villain_pair_half(x0);                 // 0 for the first of a pair
+                bool ok;
+                const float AA = villain_tiled_site(sh, a, fc, (int)lA, halfA ? bits.z : bits.x, halfA ? bits.w : bits.y, c0, halfA,
+                                                    half_kappa, hk2, hkA, hkB, K, W, mWI, cIn, gc, gs, ok);
+                // counters: owned sites only (local [2, 34)^2)
+                if (iA >= 2 && iA < 2 + kTile && j >= 2 && j < 2 + kTile) { n_acc += ok ? 1.0f : 0.0f; sum_A += AA; }
+                if (lB != kNoSite) {
+                    const float AB = villain_tiled_site(sh, a, fc, (int)lB, bits.z, bits.w, c0, 1u, half_kappa, hk2, hkA, hkB, K, W, mWI,
+                                                        cIn, gc, gs, ok);
+                    if (iA + 8 < 2 + kTile && j >= 2 && j < 2 + kTile) { n_acc += ok ? 1.0f : 0.0f; sum_A += AB; }
+                }
+            }
             __syncthreads();
-            ChainSums cs;
-            cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
-            for (int p = tid; p < kTile * kTile; p += 128) {
-                const int i = 2 + p / kTile, j = 2 + (p % kTile);
-                villain_obs_site<double, 0>(sphi, sn0, sn1, kRegCols, i, j, cs.action, cs.dn2, cs.w0, cs.w1);
-            }
-            double* scratch = reinterpret_cast<double*>(sr0);            // the residuals are no longer needed: 6 * 32 doubles
-            cs = block_reduce_chain(cs, scratch);
+        }
+
+        // ---- write the owned tile ----
+        double* ophi = phi_out + chain * V;
+        int32_t* on0 = n_out + chain * 2 * V;
+        int32_t* on1 = on0 + V;
+        for (int p = tid; p < kTile * (kTile / 2); p += 128) {
+            const int i = p / (kTile / 2), jj = 2 * (p - i * (kTile / 2));
+            const unsigned g = (unsigned)(a0 + i) * (unsigned)N + (unsigned)(a1 + jj);
+            const int l = (i + 2) * kRegCols + (jj + 2);
+            *reinterpret_cast<double2*>(ophi + g) = *reinterpret_cast<const double2*>(sh.phi + l);
+            *reinterpret_cast<int2*>(on0 + g) = *reinterpret_cast<const int2*>(sh.n0 + l);
+            *reinterpret_cast<int2*>(on1 + g) = *reinterpret_cast<const int2*>(sh.n1 + l);
+        }
+        if (a.obs) {
+            double sred[2] = {(double)n_acc, (double)sum_A};
+            block_sum<2>(sred, sh.red);
             if (tid == 0) {
-                double* o = a.obs + chain * SVB_VOBS_COUNT;
-                atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * cs.action);
-                atomicAdd(o + SVB_VOBS_SUM_DN2, (double)cs.dn2);
-                atomicAdd(o + SVB_VOBS_WRAP0, (double)cs.w0);
-                atomicAdd(o + SVB_VOBS_WRAP1, (double)cs.w1);
+                atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, sred[0]);
+                atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, sred[1]);
+            }
+            if (fuse_obs) {
+                __syncthreads();
+                ChainSums cs;
+                cs.action = 0.0; cs.sumA = 0.0; cs.dn2 = 0; cs.w0 = 0; cs.w1 = 0; cs.accepted = 0;
+                for (int p = tid; p < kTile * kTile; p += 128) {
+                    const int i = 2 + p / kTile, j = 2 + (p % kTile);
+                    villain_obs_site<double, 0>(sh.phi, sh.n0, sh.n1, kRegCols, i, j, cs.action, cs.dn2, cs.w0, cs.w1);
+                }
+                double* scratch = reinterpret_cast<double*>(sh.r0);        // the residuals are no longer needed: 6 * 32 doubles
+                cs = block_reduce_chain(cs, scratch);
+                if (tid == 0) {
+                    double* o = a.obs + chain * SVB_VOBS_COUNT;
+                    atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * cs.action);
+                    atomicAdd(o + SVB_VOBS_SUM_DN2, (double)cs.dn2);
+                    atomicAdd(o + SVB_VOBS_WRAP0, (double)cs.w0);
+                    atomicAdd(o + SVB_VOBS_WRAP1, (double)cs.w1);
+                }
             }
         }
     }
+}
+
+static int launch_villain_tiled_filtered(const VillainArgs& a, const FilterConsts& fc, const double* phi_in, const int32_t* n_in,
+                                         double* phi_out, int32_t* n_out, int sweep, int tps, int fuse, long long blocks,
+                                         cudaStream_t st) {
+    static bool ready[64];
+    const size_t smem = sizeof(TiledShared);
+    int dev = 0;
+    SVB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !ready[dev]) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tiled_filtered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tiled_filtered_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        villain_tiled_items_kernel<<<1, 128, 0, st>>>();           // idempotent; ordered before the sweep on this stream
+        SVB_CUDA_TRY(cudaGetLastError());
+        SVB_CUDA_TRY(cudaStreamSynchronize(st));                    // once per process and device: other streams may follow
+        if (dev >= 0 && dev < 64) ready[dev] = true;
+    }
+    villain_tiled_filtered_kernel<<<(unsigned)blocks, 128, smem, st>>>(a, fc, phi_in, n_in, phi_out, n_out, sweep, tps, fuse);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
 }
