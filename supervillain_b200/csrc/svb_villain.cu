@@ -1967,10 +1967,17 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     a.exact_mode = 0; a.inj_z = nullptr; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // An even number of ping-pong sweeps ends in (phi, n).  An odd count would end in the workspace, so the last sweep of
-    // an odd count is done in place by the per-colour global path instead (cheaper than copying the state back).
-    const int n_tiled = n_sweeps & ~1;
-    const bool tail_global = (n_sweeps & 1) != 0;
+    // An even number of ping-pong sweeps ends in (phi, n); an odd count ends in the workspace.  The filtered kernel is fast
+    // enough that copying the state back (two device-to-device copies) beats doing the last sweep in place with the
+    // per-colour global path (330 vs 385 us for a config-4 shard); the fp64 kernels (STRICT, debug outputs) keep the latter.
+    const bool odd = (n_sweeps & 1) != 0;
+#ifndef SVB_NO_FILTERED_KERNEL
+    const bool copy_back = odd && arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out;
+#else
+    const bool copy_back = false;
+#endif
+    const int n_tiled = copy_back ? n_sweeps : (n_sweeps & ~1);
+    const bool tail_global = odd && !copy_back;
     if (obs) {
         villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains, 0);
         SVB_CUDA_TRY(cudaGetLastError());
@@ -1998,6 +2005,11 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
             villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
 #endif
         SVB_CUDA_TRY(cudaGetLastError());
+    }
+    if (copy_back) {
+        const size_t V = (size_t)N * N;
+        SVB_CUDA_TRY(cudaMemcpyAsync(phi, phi_ws, (size_t)chains * V * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        SVB_CUDA_TRY(cudaMemcpyAsync(n, n_ws, (size_t)chains * 2 * V * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
     if (tail_global) {
         const int V = N * N;
