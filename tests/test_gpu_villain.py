@@ -420,3 +420,50 @@ def test_host_stepper_two_steps_in_flight():
         assert torch.equal(sets1[r][0], sets2[r][0]) and torch.equal(sets1[r][1], sets2[r][1])
     for a, b in zip(waited, records):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('N,chains,W,interval_n,interval_phi,kappa', [(32, 300, 2, 1, np.pi, 0.3), (32, 300, 1, 3, 1.0, 0.1), (16, 600, 3, 2, 2.0, 0.05),
+                                                                       (64, 80, 2, 2, np.pi, 0.2), (128, 4, 2, 2, 1.5, 0.1)])
+def test_general_proposals_bit_exact_against_c_oracle(N, chains, W, interval_n, interval_phi, kappa):
+    """The fp32-filtered kernels with W > 1, wider dn intervals and narrower dphi intervals (the run-time form of the
+    constants that config 2 has at compile time), smem and tiled: fields identical to the C oracle, also through the
+    overlapped-launch entry point."""
+    from oracle import c_oracle as C
+    seed, sweeps = 17, 2
+    phi0, n0 = V.hot_start(np.random.default_rng(N + W), N, chains)
+    n0 = n0 * W
+    kw = dict(W=W, interval_phi=interval_phi, interval_n=interval_n)
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=sweeps, seed=seed, sweep0=4, chain0=9, **kw)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps, seed=seed, sweep0=4, chain0=9, obs=obs, **kw)
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, VOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-5)
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, kappa), rtol=1e-12)
+    assert acc.sum() > 0
+    if N <= 64:
+        phi, n = dev(phi0), dev(n0, torch.int32)
+        ov = ops.VillainOverlappedSweeps(phi, n, kappa, seed=seed, chain0=9, **kw)
+        ov.step(4, 1)
+        ov.step(5, 1)
+        torch.cuda.synchronize()
+        assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+
+
+@pytest.mark.parametrize('phi_scale,n_scale,kappa', [(50.0, 1, 0.5), (1.0, 12, 0.02), (300.0, 40, 0.001), (1.0, 1, 8.0)])
+def test_filtered_decisions_stay_exact_far_from_equilibrium(phi_scale, n_scale, kappa):
+    """The fp32 filter must never decide differently from fp64: large |phi| (a field that has wandered), large residuals
+    (|r| ~ 250), tiny and large couplings.  The error band scales with max |r|; whatever falls inside it takes the exact
+    path.  Fields identical to the C oracle."""
+    from oracle import c_oracle as C
+    N, chains, seed = 32, 400, 23
+    phi0, n0 = V.hot_start(np.random.default_rng(int(phi_scale) + n_scale), N, chains)
+    phi0, n0 = phi0 * phi_scale, n0 * n_scale
+    p_ref, n_ref, acc, _ = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=3, seed=seed)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=3, seed=seed, obs=obs)
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    assert (obs.cpu().numpy()[:, VOBS_ACCEPTED] == acc).all()
