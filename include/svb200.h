@@ -320,6 +320,16 @@ int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int 
  */
 int svb_autocorrelation(const double* data, int64_t series, int T, const double* mean, double* C, int32_t* tau, void* stream);
 
+/*
+ * Test hook: the decision u < A of the lazily refined Metropolis uniform (leading 32 bits f known; trailing bits from word
+ * `word` of the Philox block (c0, chain, sweep) in refinement stream `stream_id`: 4 Villain, 5 worldline, 7 LinkUpdate) and
+ * the refined uniform itself, for n caller-chosen inputs.  The sweeps reach the refinement with probability 2^-32 per
+ * proposal; this makes it testable against the oracle.
+ */
+int svb_debug_decide_lazy(const double* A, const uint32_t* f, const uint32_t* c0, const uint32_t* word, int64_t n,
+                          uint32_t stream_id, uint64_t seed, uint64_t chain, uint64_t sweep,
+                          uint8_t* decision, double* u_out, void* stream);
+
 /* Philox4x32-10 block, exposed for known-answer tests: out[4] = philox(ctr[4], key[2]) (host). */
 void svb_philox4x32_10_host(const uint32_t* ctr_host, const uint32_t* key_host, uint32_t* out_host);
 

@@ -206,3 +206,36 @@ extern "C" int svb_autocorrelation(const double* data, int64_t series, int T, co
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Test hook for the lazily refined uniform (svb_common.cuh): the refinement branch of decide_lazy is taken with probability
+// 2^-32 per proposal, so no sweep test ever reaches it.  This evaluates decide_lazy(A, (f, c0, word)) and the refined
+// uniform itself for caller-chosen inputs, to be compared with the oracle's statement of the same rule.
+// ------------------------------------------------------------------------------------------
+namespace svb {
+__global__ void debug_decide_lazy_kernel(const double* A, const uint32_t* f, const uint32_t* c0, const uint32_t* word, long long n,
+                                         uint32_t stream_id, unsigned long long seed, unsigned long long chain,
+                                         unsigned long long sweep, uint8_t* decision, double* u_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    LazyUniform lu;
+    lu.f = f[i]; lu.c0 = c0[i]; lu.word = word[i];
+    RefineCtx rc;
+    rc.seed = seed; rc.chain = chain; rc.sweep = sweep;
+    decision[i] = decide_lazy(A[i], lu, stream_id, rc) ? 1 : 0;
+    u_out[i] = refined_uniform(lu.f, lu.c0, lu.word, stream_id, seed, chain, sweep);
+}
+}  // namespace svb
+
+extern "C" int svb_debug_decide_lazy(const double* A, const uint32_t* f, const uint32_t* c0, const uint32_t* word, int64_t n,
+                                     uint32_t stream_id, uint64_t seed, uint64_t chain, uint64_t sweep, uint8_t* decision,
+                                     double* u_out, void* stream) {
+    using namespace svb;
+    if (!A || !f || !c0 || !word || !decision || !u_out) return fail(SVB_E_NULL, "svb_debug_decide_lazy: all arrays are required");
+    if (n <= 0) return SVB_OK;
+    debug_decide_lazy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        A, f, c0, word, n, stream_id, seed, chain, sweep, decision, u_out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}

@@ -46,3 +46,37 @@ def test_worldline_draw_mapping_ranges():
         assert (d['u'] > 0).all() and (d['u'] < 1).all()
         if mode == 'joint':
             assert set(np.unique(d['b'])) == {-1, 0, 1}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('stream_id', [P.STREAM_VILLAIN_REFINE, P.STREAM_WORLDLINE_REFINE, P.STREAM_VILLAIN_LINK_REFINE])
+def test_lazy_uniform_refinement_matches_oracle(stream_id):
+    """The refinement branch of the lazily refined uniform is reached with probability 2^-32 per proposal, i.e. never in a
+    sweep test.  svb_debug_decide_lazy forces it: acceptance probabilities placed inside the bracket [f, f + 1] 2^-32 of
+    the uniform, on both sides of the refined value, must be decided exactly as the oracle's rule
+    u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53) decides them."""
+    import torch
+    from supervillain_b200 import _lib
+    rng = np.random.default_rng(stream_id)
+    n, seed, chain, sweep = 4000, 0x1234567890ABCDEF, 2**33 + 5, 2**34 + 9
+    f = rng.integers(0, 2**32, n, dtype=np.uint64)
+    f[:8] = [0, 1, 2**32 - 1, 2**32 - 2, 65535, 65536, 2**31, 12345]
+    c0 = rng.integers(0, 2**20, n, dtype=np.uint64)
+    word = rng.integers(0, 4, n, dtype=np.uint64)
+    blk = P.philox_site(seed, chain, sweep, c0, stream_id)
+    e = np.choose(word.astype(np.int64), blk)
+    u_ref = np.minimum((f.astype(np.float64) + (e.astype(np.float64) + 0.5) * 2.0**-32) * 2.0**-32, 1.0 - 2.0**-53)
+    # A: just above / just below / equal to the refined uniform (inside the bracket), and the bracket's ends and beyond
+    kinds = rng.integers(0, 7, n)
+    A = np.select([kinds == 0, kinds == 1, kinds == 2, kinds == 3, kinds == 4, kinds == 5],
+                  [np.nextafter(u_ref, 2.0), np.nextafter(u_ref, -1.0), u_ref, f * 2.0**-32, (f + 1.0) * 2.0**-32,
+                   (f + 1.5) * 2.0**-32], default=(f - 0.5) * 2.0**-32)
+    A = np.clip(A, 0.0, 1.0)
+    dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).cuda()
+    dA, df, dc, dw = dev(A, np.float64), dev(f, np.uint32).view(torch.int32), dev(c0, np.uint32).view(torch.int32), dev(word, np.uint32).view(torch.int32)
+    dec = torch.zeros(n, dtype=torch.uint8, device='cuda')
+    u = torch.zeros(n, dtype=torch.float64, device='cuda')
+    _lib.check(_lib.load().svb_debug_decide_lazy(dA.data_ptr(), df.data_ptr(), dc.data_ptr(), dw.data_ptr(), n, stream_id, seed, chain,
+                                                 sweep, dec.data_ptr(), u.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert (u.cpu().numpy() == u_ref).all()
+    assert (dec.cpu().numpy().astype(bool) == (u_ref < A)).all()
