@@ -138,35 +138,49 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons every 100 ms from ONE long-lived `nvidia-smi -lms` process (started before the
+    warm-up: forking inside the timed region costs the launching thread milliseconds)."""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []               # (timestamp, fields)
         self.stop_flag = threading.Event()
+        self.proc = None
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(',')]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.samples.append((time.time(), parts))
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+        self.join(timeout=3)
 
-    def summary(self):
-        if not self.samples:
+    def summary(self, t_from=None, t_to=None):
+        rows = [f for (t, f) in self.samples if (t_from is None or t >= t_from) and (t_to is None or t <= t_to)]
+        if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
-        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(self.samples[0][1]),
-                'reasons': reasons, 'samples': len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(rows[0][1]),
+                'reasons': reasons, 'samples': len(rows)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -225,10 +239,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()                                           # its first nvidia-smi fork lands in the warm-up, not in the timed region
+    sampler.start()                                           # one nvidia-smi process for the whole run, forked before the warm-up
     for k in range(args.warmup):
         step(k)
     barrier()
+    t_load0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for k in range(args.steps):
@@ -236,14 +251,13 @@ def run_gpu(args):
     stop.record()
     barrier()
     ms = start.elapsed_time(stop)
-    if args.steps * (ms / max(args.steps, 1)) < 300:          # keep the sampler alive long enough to see the load
-        t_end = time.time() + 0.5
+    if ms < 1000:             # a short timed region sees few 100 ms samples: keep the same load on until a second has passed
         k = 0
-        while time.time() < t_end:
+        while time.time() < t_load0 + 1.0:
             step(k); k += 1
         torch.cuda.synchronize()
-    sampler.stop_flag.set()
-    sampler.join()
+    t_load1 = time.time()
+    sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,7 +325,7 @@ def run_gpu(args):
                        'l2': f'inputs larger than L2: {ROTATE} chain sets ({ROTATE * CHAINS * L * L * 16 >> 20} MiB) rotated',
                        'parallelism': f'chains sharded over {world} GPU(s), no hot-path collective'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
-            'clocks': sampler.summary(), 'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
+            'clocks': sampler.summary(t_load0, t_load1), 'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
