@@ -221,6 +221,26 @@ class BatchedEnsemble:
             return obs[name]
         raise AttributeError(name)
 
+    def autocorrelation_time(self, observables=None, every=False):
+        """The batched form of `Ensemble.autocorrelation_time` (supervillain/ensemble.py:184-239): the integrated
+        autocorrelation time of every scalar observable column of every chain, computed on the device
+        (`svb_autocorrelation`), maximised over chains.  Columns that do not fluctuate enough are left out, as the
+        reference does; with nothing left, half the length.  every=True: a dict name -> (chains,) array of times
+        (-1 where a chain's column does not fluctuate)."""
+        from . import ops
+        names = [n for n, v in self.observables.items() if v.ndim == 2] if observables is None else list(observables)
+        auto = {}
+        for name in names:
+            col = np.ascontiguousarray(getattr(self, name), dtype=np.float64)
+            if col.ndim != 2:
+                continue
+            _, tau = ops.autocorrelation(torch.from_numpy(col).to(self.device), want_C=False)
+            auto[name] = tau.cpu().numpy().astype(np.int64)
+        if every:
+            return auto
+        times = [int(t[t >= 0].max()) for t in auto.values() if (t >= 0).any()]
+        return max(times) if times else int(np.ceil(self.steps / 2))
+
     def chain(self, c):
         """Chain `c` as a reference-layout `Ensemble` (needs keep_every > 0): fields `(draw, C, N, N)` Batches
         plus the inline observable columns, exactly what `Ensemble.generate` would have stored."""

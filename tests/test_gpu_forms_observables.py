@@ -153,3 +153,23 @@ def test_autocorrelation_matches_reference(golden_autocorrelation):
         assert tau[k] == tr
     with pytest.raises(ValueError):
         svb.analysis.autocorrelation(np.ones(32))
+
+
+def test_batched_ensemble_autocorrelation_time_matches_per_chain_reference_definition():
+    from oracle import lattice_np as lat
+    S = svb.Villain(svb.Lattice2D(8), 0.4)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=8)
+    E = svb.BatchedEnsemble(S, 24).generate(400, G, 'hot', start_seed=2)
+    every = E.autocorrelation_time(every=True)
+    expect = 0
+    for name in ('ActionDensity', 'WindingSquared', 'WrappingSquared'):
+        for k in range(24):
+            try:
+                tau = lat.autocorrelation(getattr(E, name)[k])[1]
+            except ValueError:
+                tau = -1
+            assert every[name][k] == tau, (name, k)
+            expect = max(expect, tau)
+    assert 'TorusWrapping' not in every                      # not a scalar column
+    total = E.autocorrelation_time()
+    assert total >= expect and total == max(int(v.max()) for v in every.values())
