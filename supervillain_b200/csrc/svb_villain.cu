@@ -1641,6 +1641,15 @@ static int launch_villain_obs(const real* phi, const int32_t* n, long long chain
                               double* obs, int keep_counters, cudaStream_t stream) {
     const long long V = (long long)N * N;
     const long long want_ctas = 148LL * 8;
+    if (sizeof(real) == 8 && chains >= 64 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)n % 16 == 0)) {
+        const double* p64 = reinterpret_cast<const double*>(phi);
+        switch (N) {          // the chain staged in shared memory by TMA, one vectorised pass (svb_villain_filtered.cuh)
+            case 16: return launch_villain_obs_smem<16>(p64, n, chains, kappa, kappa_chain, obs, keep_counters, stream);
+            case 32: return launch_villain_obs_smem<32>(p64, n, chains, kappa, kappa_chain, obs, keep_counters, stream);
+            case 64: return launch_villain_obs_smem<64>(p64, n, chains, kappa, kappa_chain, obs, keep_counters, stream);
+            default: break;
+        }
+    }
     if (V <= 16384 || chains >= want_ctas) {
         long long grid = chains < want_ctas ? chains : want_ctas;
         villain_obs_kernel<real><<<(unsigned)grid, 256, 0, stream>>>(phi, n, chains, N, kappa, kappa_chain, obs, keep_counters);

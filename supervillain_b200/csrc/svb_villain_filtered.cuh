@@ -847,3 +847,97 @@ static int launch_villain_tiled_filtered(const VillainArgs& a, const FilterConst
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// svb_villain_observables for N in {16, 32, 64}, fp64 phi: one CTA per chain at a time, the chain staged by a 1-D TMA bulk
+// copy, one conflict-free fp64 pass over site pairs (the pass of the sweep kernel above), records without atomics.
+// HBM-bound: one read of the state.
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(4 * NT) villain_obs_smem_kernel(const double* __restrict__ phi, const int32_t* __restrict__ n,
+                                                                  long long chains, double kappa_scalar,
+                                                                  const double* __restrict__ kappa_chain, double* __restrict__ obs,
+                                                                  int keep_counters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = N * N, HN = N / 2, T = 4 * NT, NW = T / 32, PER = V / 2 / T;
+    constexpr uint32_t bytes_phi = V * sizeof(double), bytes_n = 2 * V * sizeof(int32_t);
+    double* sphi = reinterpret_cast<double*>(smem_raw);
+    int32_t* sn0 = reinterpret_cast<int32_t*>(smem_raw + bytes_phi);
+    int32_t* sn1 = sn0 + V;
+    double* red_state = reinterpret_cast<double*>(smem_raw + bytes_phi + bytes_n);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red_state + 4 * NW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue_load = [&](long long chain) {
+        mbar_expect_tx(bar, bytes_phi + bytes_n);
+        bulk_g2s(sphi, phi + chain * V, bytes_phi, bar);
+        bulk_g2s(sn0, n + chain * 2 * V, bytes_n, bar);
+    };
+    const int row8 = tid / HN, k = tid - row8 * HN;
+    const int up_off = (row8 == 7) ? (N - V) : N;
+    const double* pp = sphi + row8 * N + 2 * k;
+    const double* pp_r = sphi + row8 * N + ((2 * k + 2) & (N - 1));
+    const int32_t* pn0 = sn0 + row8 * N + 2 * k;
+    const int32_t* pn1 = sn1 + row8 * N + 2 * k;
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < chains) issue_load(chain);
+    for (int it = 0; chain < chains; chain += gridDim.x, ++it) {
+        mbar_wait(bar, (uint32_t)(it & 1));
+        double action = 0.0;
+        int w0 = 0, w1 = 0;
+        long long dn2 = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int o = 8 * N * q;
+            const int uo = (q == PER - 1) ? up_off : N;
+            const PairResiduals pr = villain_pair_residuals(pp + o, pp + o + uo, pp_r + o, pn0 + o, pn1 + o);
+            action = fma(pr.r0e, pr.r0e, action);
+            action = fma(pr.r0o, pr.r0o, action);
+            action = fma(pr.r1e, pr.r1e, action);
+            action = fma(pr.r1o, pr.r1o, action);
+            const int hr = sn0[(row8 + 8 * q) * N + ((2 * k + 2) & (N - 1))];
+            const int2 up = *reinterpret_cast<const int2*>(pn1 + o + uo);
+            const int d0 = (up.x - pr.a1.x) - (pr.a0.y - pr.a0.x), d1 = (up.y - pr.a1.y) - (hr - pr.a0.y);
+            dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+            w0 += pr.a0.x + pr.a0.y;
+            w1 += pr.a1.x + pr.a1.y;
+        }
+        chain_partials<true, false>(red_state, nullptr, lane, warp, action, dn2, w0, w1, 0.0, 0);
+        __syncthreads();                       // every warp has read the chain; the slots are written
+        const long long next = chain + gridDim.x;
+        if (tid == 0 && next < chains) issue_load(next);
+        if (tid == 32) {
+            const double kappa = kappa_chain ? kappa_chain[chain] : kappa_scalar;
+            double* row = obs + chain * SVB_VOBS_COUNT;
+            chain_finish<NW, true, false>(red_state, nullptr, kappa / 2, row, nullptr);
+            if (!keep_counters) { row[SVB_VOBS_ACCEPTED] = 0.0; row[SVB_VOBS_ACCEPTANCE] = 0.0; }
+        }
+        __syncthreads();                       // the slots are free again (the next chain's partials follow its load)
+    }
+}
+
+template <int NT>
+static int launch_villain_obs_smem(const double* phi, const int32_t* n, long long chains, double kappa, const double* kappa_chain,
+                                   double* obs, int keep_counters, cudaStream_t stream) {
+    auto kern = villain_obs_smem_kernel<NT>;
+    const size_t smem = (size_t)NT * NT * 16 + 4 * (4 * NT / 32) * sizeof(double) + 16;
+    static int grid_cap = 0;
+    if (grid_cap == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        SVB_CUDA_TRY(cudaGetDevice(&dev));
+        SVB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "villain observable kernel does not fit an SM at N=%d", NT);
+        grid_cap = per_sm * sms;
+    }
+    const long long grid = chains < grid_cap ? chains : grid_cap;
+    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(phi, n, chains, kappa, kappa_chain, obs, keep_counters);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
