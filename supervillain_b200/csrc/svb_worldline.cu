@@ -1001,6 +1001,15 @@ extern "C" int svb_worldline_observables(const int32_t* m, const int32_t* v, int
     if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_worldline_observables: shape");
     if (W < 1) return fail(SVB_E_PARAM, "svb_worldline_observables: W");
     if (chains == 0) return SVB_OK;
+    if (W == 1 && chains >= 64 && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0)) {
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        switch (N) {          // TMA-staged integer pass (svb_worldline_table.cuh)
+            case 16: return launch_worldline_obs_smem<16>(m, v, chains, obs, 0, st);
+            case 32: return launch_worldline_obs_smem<32>(m, v, chains, obs, 0, st);
+            case 64: return launch_worldline_obs_smem<64>(m, v, chains, obs, 0, st);
+            default: break;
+        }
+    }
     long long grid = chains < 148 * 8 ? chains : 148 * 8;
     worldline_obs_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(m, v, chains, N, W, obs, 0);
     SVB_CUDA_TRY(cudaGetLastError());

@@ -327,3 +327,130 @@ static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, i
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// svb_worldline_observables for W = 1 and N in {16, 32, 64}: the chain staged by a 1-D TMA bulk copy, f = m - delta v built
+// in place as in the sweep kernel, then integer sums over f (action, winding, wrapping) and |delta m| from the staged m.
+// HBM-bound: one read of the state (12 B per site).
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(4 * NT) worldline_obs_smem_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ v,
+                                                                    long long chains, double* __restrict__ obs, int keep_counters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = N * N, T = 4 * NT, NW = T / 32;
+    constexpr uint32_t bytes_m = 2 * V * sizeof(int32_t), bytes_v = V * sizeof(int32_t);
+    int32_t* F0 = reinterpret_cast<int32_t*>(smem_raw);
+    int32_t* F1 = F0 + V;
+    int32_t* sv = F1 + V;
+    long long* red = reinterpret_cast<long long*>(smem_raw + bytes_m + bytes_v);          // [NW][4]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 4 * NW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue_load = [&](long long chain) {
+        mbar_expect_tx(bar, bytes_m + bytes_v);
+        bulk_g2s(F0, m + chain * 2 * V, bytes_m, bar);
+        bulk_g2s(sv, v + chain * V, bytes_v, bar);
+    };
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < chains) issue_load(chain);
+    for (int it = 0; chain < chains; chain += gridDim.x, ++it) {
+        mbar_wait(bar, (uint32_t)(it & 1));
+        // |delta m| from the staged m:  (delta m)[x] = -(m0[x] - m0[x-e0]) - (m1[x] - m1[x-e1])   (compact.py delta,1 rows)
+        long long dm_abs = 0;
+#pragma unroll
+        for (int i4 = tid; i4 < V / 4; i4 += T) {
+            const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+            const int4 a0 = *reinterpret_cast<const int4*>(F0 + i), a1 = *reinterpret_cast<const int4*>(F1 + i);
+            const int4 u0 = *reinterpret_cast<const int4*>(F0 + ((x0 - 1) & (N - 1)) * N + x1);
+            const int l1 = F1[x0 * N + ((x1 - 1) & (N - 1))];
+            const int d0 = -(a0.x - u0.x) - (a1.x - l1), d1 = -(a0.y - u0.y) - (a1.y - a1.x);
+            const int d2 = -(a0.z - u0.z) - (a1.z - a1.y), d3 = -(a0.w - u0.w) - (a1.w - a1.z);
+            dm_abs += abs(d0) + abs(d1) + abs(d2) + abs(d3);
+        }
+        __syncthreads();
+        // m -> f = m - delta v, in place (as in the sweep kernel)
+#pragma unroll
+        for (int i4 = tid; i4 < V / 4; i4 += T) {
+            const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+            const int4 vc = *reinterpret_cast<const int4*>(sv + i);
+            const int4 vu = *reinterpret_cast<const int4*>(sv + ((x0 - 1) & (N - 1)) * N + x1);
+            const int vl = sv[x0 * N + ((x1 - 1) & (N - 1))];
+            int4 m0 = *reinterpret_cast<int4*>(F0 + i), m1 = *reinterpret_cast<int4*>(F1 + i);
+            m0.x -= vc.x - vl;   m0.y -= vc.y - vc.x; m0.z -= vc.z - vc.y; m0.w -= vc.w - vc.z;
+            m1.x -= vu.x - vc.x; m1.y -= vu.y - vc.y; m1.z -= vu.z - vc.z; m1.w -= vu.w - vc.w;
+            *reinterpret_cast<int4*>(F0 + i) = m0;
+            *reinterpret_cast<int4*>(F1 + i) = m1;
+        }
+        __syncthreads();
+        long long f2 = 0, df2 = 0;
+        int w0 = 0, w1 = 0;
+#pragma unroll
+        for (int i4 = tid; i4 < V / 4; i4 += T) {
+            const int i = 4 * i4, x0 = i / N, x1 = i - x0 * N;
+            const int4 a0 = *reinterpret_cast<const int4*>(F0 + i), a1 = *reinterpret_cast<const int4*>(F1 + i);
+            const int4 d1 = *reinterpret_cast<const int4*>(F1 + ((x0 + 1) & (N - 1)) * N + x1);
+            const int r0 = F0[x0 * N + ((x1 + 4) & (N - 1))];
+            f2 += (long long)a0.x * a0.x + (long long)a0.y * a0.y + (long long)a0.z * a0.z + (long long)a0.w * a0.w;
+            f2 += (long long)a1.x * a1.x + (long long)a1.y * a1.y + (long long)a1.z * a1.z + (long long)a1.w * a1.w;
+            const int c0 = (d1.x - a1.x) - (a0.y - a0.x), c1 = (d1.y - a1.y) - (a0.z - a0.y);
+            const int c2 = (d1.z - a1.z) - (a0.w - a0.z), c3 = (d1.w - a1.w) - (r0 - a0.w);
+            df2 += (long long)c0 * c0 + (long long)c1 * c1 + (long long)c2 * c2 + (long long)c3 * c3;
+            w0 += a0.x + a0.y + a0.z + a0.w;
+            w1 += a1.x + a1.y + a1.z + a1.w;
+        }
+        f2 = warp_sum(f2);
+        df2 = warp_sum(df2);
+        dm_abs = warp_sum(dm_abs);
+        w0 = __reduce_add_sync(0xffffffffu, w0);
+        w1 = __reduce_add_sync(0xffffffffu, w1);
+        if (lane == 0) {
+            long long* slot = red + 4 * warp;
+            slot[0] = f2; slot[1] = df2; slot[2] = ((long long)w0 << 32) | (unsigned)w1; slot[3] = dm_abs;
+        }
+        __syncthreads();                       // every warp has read the chain; the slots are written
+        const long long next = chain + gridDim.x;
+        if (tid == 0 && next < chains) issue_load(next);
+        if (tid == 32) {
+            long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+            for (int w = 0; w < NW; ++w) {
+                t0 += red[4 * w]; t1 += red[4 * w + 1];
+                t2 += red[4 * w + 2] >> 32; t3 += (int)(red[4 * w + 2] & 0xFFFFFFFFLL);
+                t4 += red[4 * w + 3];
+            }
+            double* o = obs + chain * SVB_WOBS_COUNT;
+            o[SVB_WOBS_SUM_F2] = (double)t0;
+            o[SVB_WOBS_SUM_DF2] = (double)t1;
+            o[SVB_WOBS_WRAP0] = (double)t2;
+            o[SVB_WOBS_WRAP1] = (double)t3;
+            o[SVB_WOBS_DELTA_M_ABS] = (double)t4;
+            if (!keep_counters) { o[SVB_WOBS_ACCEPTED] = 0.0; o[SVB_WOBS_ACCEPTANCE] = 0.0; }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NT>
+static int launch_worldline_obs_smem(const int32_t* m, const int32_t* v, long long chains, double* obs, int keep_counters,
+                                     cudaStream_t stream) {
+    auto kern = worldline_obs_smem_kernel<NT>;
+    const size_t smem = (size_t)NT * NT * 12 + 4 * (4 * NT / 32) * sizeof(long long) + 16;
+    static int grid_cap = 0;
+    if (grid_cap == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        SVB_CUDA_TRY(cudaGetDevice(&dev));
+        SVB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "worldline observable kernel does not fit an SM at N=%d", NT);
+        grid_cap = per_sm * sms;
+    }
+    const long long grid = chains < grid_cap ? chains : grid_cap;
+    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(m, v, chains, obs, keep_counters);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}

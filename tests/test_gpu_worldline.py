@@ -227,3 +227,17 @@ def test_overlapped_launches_equal_ordinary_launches(N, chains, mode):
     torch.cuda.synchronize()
     assert torch.equal(m, rm) and torch.equal(v, rv)
     assert torch.equal(rec, rec_ref)
+
+
+@pytest.mark.parametrize('N', [16, 32, 64])
+def test_staged_observable_kernel_equals_the_generic_one(N):
+    """svb_worldline_observables: the TMA-staged integer kernel (W = 1, >= 64 chains) against the generic fp64 kernel (the
+    same call on slices of < 64 chains), on random fields that also violate delta m = 0."""
+    g = torch.Generator(device='cuda'); g.manual_seed(N)
+    chains = 150
+    m = torch.randint(-9, 10, (chains, 2, N, N), generator=g, device='cuda', dtype=torch.int32)
+    v = torch.randint(-9, 10, (chains, 1, N, N), generator=g, device='cuda', dtype=torch.int32)
+    fast = ops.worldline_observables(m, v)
+    slow = torch.cat([ops.worldline_observables(m[lo:lo + 50].contiguous(), v[lo:lo + 50].contiguous()) for lo in range(0, chains, 50)])
+    assert torch.equal(fast, slow)
+    assert (fast[:, WOBS_DELTA_M_ABS] > 0).all()

@@ -84,3 +84,12 @@ if 'forms' in which:
     n = b
     obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
     report('villain_observables L=32 x 65536', CH * N * N, 16, timeit(lambda: ops.villain_observables(phi, n, 0.5, obs=obs)))
+if 'forms' in which:
+    N, CH = 64, 16384
+    m = torch.randint(-3, 4, (CH, 2, N, N), dtype=torch.int32, device='cuda')
+    v = torch.randint(-3, 4, (CH, 1, N, N), dtype=torch.int32, device='cuda')
+    wobs = torch.zeros((CH, ops.WOBS_COUNT), dtype=torch.float64, device='cuda')
+    report('worldline_observables L=64 x 16384', CH * N * N, 12, timeit(lambda: ops.worldline_observables(m, v, obs=wobs)))
+    N, CH = 32, 8192
+    phi = torch.rand((CH, 1, N, N), dtype=torch.float64, device='cuda')
+    report('spin_spin correlator L=32 x 8192 (O(N^4) direct sum)', CH * N * N, 8, timeit(lambda: ops.villain_spin_spin(phi), n=3, reps=2))
