@@ -69,9 +69,105 @@ __global__ void __launch_bounds__(256) correlation_kernel(const real* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same correlators by FFT for power-of-two lattices that fit shared memory (N = 16, 32, 64), the reference's own route
+// (compact.py:465-536):  sum_x conj(s[x]) s[x - r] = N^-2 DFT[ |DFT s|^2 ](r), so C = N^-4 fft2(|fft2 s|^2).
+// Two radix-2 transforms per dimension out of shared memory: decimation in frequency (natural order in, bit-reversed out),
+// the pointwise |.|^2 in bit-reversed order, then decimation in time (bit-reversed in, natural out) -- no permutation pass.
+// O(N^2 log N) per chain instead of O(N^4): 8192 chains of 32^2 take 6.4 ms by direct summation.
+// ------------------------------------------------------------------------------------------
+template <int NT, bool ROWS, bool DIF>
+__device__ __forceinline__ void fft_pass(double* __restrict__ re, double* __restrict__ im, const double* __restrict__ twr,
+                                         const double* __restrict__ twi) {
+    constexpr int N = NT, HALF = N / 2;
+    for (int st = 0; (1 << st) < N; ++st) {
+        const int half = DIF ? (HALF >> st) : (1 << st);
+        const int tw_step = HALF / half;                          // twiddle e^{-2 pi i j / (2 half)} = tw[j * tw_step]
+        for (int b = threadIdx.x; b < N * HALF; b += blockDim.x) {
+            int line, bb;
+            if (ROWS) { line = b / HALF; bb = b - line * HALF; }   // lanes walk along a row
+            else { bb = b / N; line = b - bb * N; }               // lanes walk across columns: contiguous addresses
+            const int group = bb / half, j = bb - group * half;
+            const int i0 = group * 2 * half + j, i1 = i0 + half;
+            const int a = ROWS ? line * N + i0 : i0 * N + line;
+            const int c = ROWS ? line * N + i1 : i1 * N + line;
+            const double wr = twr[j * tw_step], wi = twi[j * tw_step];
+            const double ar = re[a], ai = im[a], cr = re[c], ci = im[c];
+            if (DIF) {
+                const double dr = ar - cr, di = ai - ci;
+                re[a] = ar + cr; im[a] = ai + ci;
+                re[c] = dr * wr - di * wi; im[c] = dr * wi + di * wr;
+            } else {
+                const double tr = cr * wr - ci * wi, ti = cr * wi + ci * wr;
+                re[a] = ar + tr; im[a] = ai + ti;
+                re[c] = ar - tr; im[c] = ai - ti;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename real, int KIND, int NT>
+__global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __restrict__ field, long long chains, int W,
+                                                              double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = NT, V = N * N;
+    double* sre = reinterpret_cast<double*>(smem_raw);
+    double* sim = sre + V;
+    double* twr = sim + V;
+    double* twi = twr + N / 2;
+    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) sincospi(-2.0 * (double)k / (double)N, &twi[k], &twr[k]);
+    const double scale = 1.0 / ((double)V * (double)V);
+    for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
+        const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+        __syncthreads();
+        for (int i = threadIdx.x; i < V; i += blockDim.x) {
+            if (KIND == SVB_CORR_WINDING) {
+                const int x0 = i / N, x1 = i - x0 * N;
+                const int i0 = ((x0 + 1) & (N - 1)) * N + x1, i1 = x0 * N + ((x1 + 1) & (N - 1));
+                sre[i] = (double)(((long long)g[V + i0] - (long long)g[V + i]) - ((long long)g[i1] - (long long)g[i]));
+                sim[i] = 0.0;
+            } else {
+                double s, c;
+                const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[i]) / (double)W : (double)g[i];
+                sincos(ang, &s, &c);
+                sre[i] = c;
+                sim[i] = s;
+            }
+        }
+        __syncthreads();
+        fft_pass<NT, true, true>(sre, sim, twr, twi);
+        fft_pass<NT, false, true>(sre, sim, twr, twi);
+        for (int i = threadIdx.x; i < V; i += blockDim.x) {
+            const double a = sre[i], b = sim[i];
+            sre[i] = a * a + b * b;
+            sim[i] = 0.0;
+        }
+        __syncthreads();
+        fft_pass<NT, false, false>(sre, sim, twr, twi);
+        fft_pass<NT, true, false>(sre, sim, twr, twi);
+        for (int i = threadIdx.x; i < V; i += blockDim.x)
+            *reinterpret_cast<double2*>(out + (chain * V + i) * 2) = make_double2(sre[i] * scale, sim[i] * scale);
+    }
+}
+
 }  // namespace svb
 
 using namespace svb;
+
+template <typename real, int KIND, int NT>
+static int launch_correlation_fft(const void* field, long long chains, int W, double* out, int sms, cudaStream_t st) {
+    auto kern = correlation_fft_kernel<real, KIND, NT>;
+    const size_t smem = (size_t)(2 * NT * NT + NT) * sizeof(double);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)per_sm * sms;
+    kern<<<(unsigned)(chains < cap ? chains : cap), 256, smem, st>>>(reinterpret_cast<const real*>(field), chains, W, out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
 
 template <typename real, int KIND>
 static int launch_correlation(const void* field, long long chains, int N, int W, double* out, size_t smem, long long grid,
@@ -98,6 +194,20 @@ extern "C" int svb_correlation(int kind, const void* field, int dtype, int64_t c
     if (smem > (size_t)max_smem)
         return fail(SVB_E_UNSUPPORTED, "svb_correlation: direct evaluation needs the lattice in shared memory (N=%d too large)", N);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define SVB_CORR_FFT(real, KIND)                                                                             \
+    switch (N) {                                                                                             \
+        case 16: return launch_correlation_fft<real, KIND, 16>(field, chains, W, out, sms, st);             \
+        case 32: return launch_correlation_fft<real, KIND, 32>(field, chains, W, out, sms, st);             \
+        case 64: return launch_correlation_fft<real, KIND, 64>(field, chains, W, out, sms, st);             \
+        default: break;                                                                                      \
+    }
+    if ((uintptr_t)out % 16 == 0) {
+        if (kind == SVB_CORR_SPIN && dtype == SVB_F64) { SVB_CORR_FFT(double, SVB_CORR_SPIN) }
+        if (kind == SVB_CORR_SPIN && dtype == SVB_F32) { SVB_CORR_FFT(float, SVB_CORR_SPIN) }
+        if (kind == SVB_CORR_WINDING) { SVB_CORR_FFT(int32_t, SVB_CORR_WINDING) }
+        if (kind == SVB_CORR_VORTEX) { SVB_CORR_FFT(int32_t, SVB_CORR_VORTEX) }
+    }
+#undef SVB_CORR_FFT
     const long long grid = chains < (long long)sms * 4 ? chains : (long long)sms * 4;
     switch (kind) {
         case SVB_CORR_SPIN:

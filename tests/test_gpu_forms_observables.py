@@ -173,3 +173,24 @@ def test_batched_ensemble_autocorrelation_time_matches_per_chain_reference_defin
     assert 'TorusWrapping' not in every                      # not a scalar column
     total = E.autocorrelation_time()
     assert total >= expect and total == max(int(v.max()) for v in every.values())
+
+
+@pytest.mark.parametrize('N', [16, 32, 64])
+def test_fft_correlators_match_the_reference_formula(N):
+    """The shared-memory FFT route (N = 16, 32, 64) for all three correlators against the restated Lattice.correlation
+    (compact.py:465-536), 1e-12, on a batch."""
+    rng = np.random.default_rng(N)
+    chains = 5
+    phi = rng.uniform(-7, 7, (chains, 1, N, N))
+    n = rng.integers(-3, 4, (chains, 2, N, N))
+    v = rng.integers(-5, 6, (chains, 1, N, N))
+    Cs = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    Cw = ops.correlation('winding', torch.from_numpy(n).to(torch.int32).cuda()).cpu().numpy()
+    Cv = ops.correlation('vortex', torch.from_numpy(v).to(torch.int32).cuda(), W=3).cpu().numpy()
+    for c in range(chains):
+        s = np.exp(1j * phi[c, 0])
+        np.testing.assert_allclose(Cs[c], lat.correlation(s, s), rtol=0, atol=1e-12)
+        dn = lat.d1(n[c])[0].astype(np.float64)
+        np.testing.assert_allclose(Cw[c], lat.correlation(dn, dn), rtol=0, atol=1e-12 * max(1.0, np.abs(dn).max() ** 2))
+        e = np.exp(2j * np.pi * v[c, 0] / 3)
+        np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)

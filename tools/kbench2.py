@@ -92,4 +92,4 @@ if 'forms' in which:
     report('worldline_observables L=64 x 16384', CH * N * N, 12, timeit(lambda: ops.worldline_observables(m, v, obs=wobs)))
     N, CH = 32, 8192
     phi = torch.rand((CH, 1, N, N), dtype=torch.float64, device='cuda')
-    report('spin_spin correlator L=32 x 8192 (O(N^4) direct sum)', CH * N * N, 8, timeit(lambda: ops.villain_spin_spin(phi), n=3, reps=2))
+    report('spin_spin correlator L=32 x 8192 (shared-memory FFT)', CH * N * N, 24, timeit(lambda: ops.villain_spin_spin(phi), n=3, reps=2))
