@@ -1584,6 +1584,7 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 }
 
 #include "svb_villain_filtered.cuh"
+#include "svb_villain_cluster.cuh"
 
 #ifndef SVB_FILT_MINB32
 #define SVB_FILT_MINB32 8        /* 64 registers per thread: 8 CTAs = 32 warps per SM (28.5 vs 30.0 us at config 2) */
@@ -1696,6 +1697,13 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
     DeviceInfo info;
     int rc = get_device_info(info);
     if (rc) return rc;
+#ifndef SVB_NO_CLUSTER_KERNEL
+    if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED && arith_mode != SVB_ARITH_STRICT &&
+        !a.accept_mask && !a.dS_out && !a.exact_mode && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
+        // one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
+        return launch_villain_cluster<128, 4>(a, stream, info);
+    }
+#endif
     if (path == SVB_PATH_AUTO) {
         path = (villain_smem_bytes(a.N, sizeof(real)) <= (size_t)info.max_smem_optin) ? SVB_PATH_SMEM : SVB_PATH_GLOBAL;
     }
@@ -1758,7 +1766,8 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
                                             uint32_t wait_epoch, uint32_t signal_epoch, int flags, void* stream) {
     if (!phi || !n || !epochs) return fail(SVB_E_NULL, "svb_villain_sweep_overlapped: phi, n and epochs are required");
     if (chains < 0) return fail(SVB_E_SHAPE, "svb_villain_sweep_overlapped: chains=%lld", (long long)chains);
-    if (N != 16 && N != 32 && N != 64) return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_overlapped: N must be 16, 32 or 64 (got %d)", N);
+    if (N != 16 && N != 32 && N != 64 && N != 128)
+        return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_overlapped: N must be 16, 32, 64 or 128 (got %d)", N);
     if (((uintptr_t)phi % 16) || ((uintptr_t)n % 16)) return fail(SVB_E_ALIGN, "svb_villain_sweep_overlapped: fields must be 16-byte aligned");
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: kappa must be positive");
     if (W < 1) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: W must be a finite integer >= 1 (got %d)", W);
@@ -1787,7 +1796,8 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
     switch (N) {
         case 16: return launch_villain_filtered<16, 16, 1>(a, st, info);
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
-        default: return launch_villain_filtered<64, 2, 1>(a, st, info);
+        case 64: return launch_villain_filtered<64, 2, 1>(a, st, info);
+        default: return launch_villain_cluster<128, 4>(a, st, info);
     }
 }
 

@@ -16,6 +16,7 @@ from ._lib import (ARITH_FAST, ARITH_STRICT, PATH_AUTO, PATH_GLOBAL, PATH_SMEM, 
 _PATHS = {'auto': PATH_AUTO, 'smem': PATH_SMEM, 'global': PATH_GLOBAL}
 _TILE = 32
 _SMEM_MAX_N = 96            # largest fp64 lattice whose chain fits one SM's shared memory
+_CLUSTER_N = (128,)         # lattices svb_villain_sweep spreads over a thread-block cluster (svb_villain_cluster.cuh)
 _workspaces = {}            # (device, chains, N) -> (phi_ws, n_ws) for the tiled ping-pong path
 _ARITH = {'strict': ARITH_STRICT, 'fast': ARITH_FAST}
 _WL_MODES = {'joint': WL_JOINT, 'vortex': WL_VORTEX, 'coexact': WL_COEXACT}
@@ -71,7 +72,8 @@ def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_s
     tiled_ok = injected is None and phi.dtype == torch.float64 and N % _TILE == 0
     if path == 'tiled' and not tiled_ok:
         raise NotImplementedError('the tiled path needs fp64 phi, Philox draws and N a multiple of 32')
-    if path == 'tiled' or (path == 'auto' and tiled_ok and N > _SMEM_MAX_N):
+    cluster_ok = (tiled_ok and N in _CLUSTER_N and arithmetic == 'fast' and accept_mask is None and dS_out is None)
+    if path == 'tiled' or (path == 'auto' and tiled_ok and N > _SMEM_MAX_N and not cluster_ok):
         key = (phi.device, chains, N)
         ws = _workspaces.get(key)
         if ws is None:
@@ -135,7 +137,8 @@ def villain_sweep_plan(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1
     return run
 
 
-OVERLAP_SIZES = (16, 32, 64)
+OVERLAP_SIZES = (16, 32, 64)             # worldline table kernels
+VILLAIN_OVERLAP_SIZES = (16, 32, 64, 128)  # filtered kernels; 128 is the cluster kernel
 
 
 class VillainOverlappedSweeps:
@@ -152,8 +155,8 @@ class VillainOverlappedSweeps:
     def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None):
         self.lib = _lib.load()
         self.chains, self.N = _fields_shape(phi, 'phi', 1)
-        if self.N not in OVERLAP_SIZES or phi.dtype != torch.float64:
-            raise NotImplementedError('overlapped sweeps need fp64 phi and N in (16, 32, 64)')
+        if self.N not in VILLAIN_OVERLAP_SIZES or phi.dtype != torch.float64:
+            raise NotImplementedError('overlapped sweeps need fp64 phi and N in (16, 32, 64, 128)')
         self.p_phi = _dev(phi, 'phi', (torch.float64,))
         self.p_n = _dev(n, 'n', (torch.int32,), (self.chains, 2, self.N, self.N))
         if W != W or W == float('inf') or int(W) != W:

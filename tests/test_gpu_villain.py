@@ -323,7 +323,38 @@ def test_tiled_path_equals_oracle_and_global_path(N, chains, sweeps, arith):
     assert torch.equal(g_phi, phi) and torch.equal(g_n, n) and torch.equal(g_mask, mask)
 
 
-@pytest.mark.parametrize('N,chains', [(32, 2000), (16, 3000), (64, 300)])
+@pytest.mark.parametrize('chains,sweeps,interval_n,W', [(3, 1, 1, 1), (5, 3, 1, 1), (700, 2, 1, 1), (4, 2, 3, 2)])
+def test_cluster_kernel_equals_oracle(chains, sweeps, interval_n, W):
+    """L = 128 (config 4) through svb_villain_sweep: one chain per cluster of four CTAs, a 32-row strip each, strip
+    boundaries through distributed shared memory (svb_villain_cluster.cuh).  Identical to the C oracle -- fields,
+    accepted counts, records -- for fewer chains than clusters, more chains than clusters (every cluster loops), fused
+    sweeps and general proposal widths; also with the records of the arriving state (obs_in)."""
+    from oracle import c_oracle as C
+    N, kappa, seed = 128, 0.55, 77
+    phi0, n0 = V.hot_start(np.random.default_rng(chains), N, chains)
+    kc = np.linspace(0.3, 1.1, chains)
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps, seed=seed, sweep0=5, chain0=2, obs=obs, kappa_chain=dev(kc), W=W,
+                      interval_n=interval_n, interval_phi=2.5)
+    per_chain = [C.villain_sweep_philox(phi0[i:i + 1], n0[i:i + 1], kc[i], n_sweeps=sweeps, seed=seed, sweep0=5, chain0=2 + i, W=W,
+                                        interval_n=interval_n, interval_phi=2.5) for i in range(chains)]
+    p_ref, n_ref, acc, accp = (np.concatenate([r[j] for r in per_chain]) for j in range(4))
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, VOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, VOBS_ACCEPTANCE], accp, rtol=1e-5)
+    np.testing.assert_allclose(rec[:, VOBS_ACTION], V.action(p_ref, n_ref, 1.0) * kc, rtol=1e-12)
+    assert (rec[:, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum(axis=(-3, -2, -1))).all()
+    assert (rec[:, VOBS_WRAP0] == n_ref[:, 0].sum(axis=(-2, -1))).all() and (rec[:, VOBS_WRAP1] == n_ref[:, 1].sum(axis=(-2, -1))).all()
+    # identical to the tiled path
+    t_phi, t_n = dev(phi0), dev(n0, torch.int32)
+    ops.villain_sweep(t_phi, t_n, kappa, n_sweeps=sweeps, seed=seed, sweep0=5, chain0=2, kappa_chain=dev(kc), W=W,
+                      interval_n=interval_n, interval_phi=2.5, path='tiled')
+    assert torch.equal(t_phi, phi) and torch.equal(t_n, n)
+
+
+@pytest.mark.parametrize('N,chains', [(32, 2000), (16, 3000), (64, 300), (128, 150)])
 def test_overlapped_launches_equal_ordinary_launches(N, chains):
     """svb_villain_sweep_overlapped: K steps whose launches overlap (per-chain epochs order the data) leave exactly the
     fields and per-step records of K ordinary launches; two chain sets interleaved on one stream stay independent."""
@@ -393,6 +424,28 @@ def test_observables_of_the_arriving_state_complete_the_previous_record():
     assert np.array_equal(E1.record[:, :-1], E2.record[:, :-1]) and np.array_equal(E1.record[:, -1, 1:], E2.record[:, -1, 1:])
     np.testing.assert_allclose(E1.record[:, -1, 0], E2.record[:, -1, 0], rtol=1e-13)
     assert G1.accepted == G2.accepted and G1.acceptance == G2.acceptance
+
+
+def test_cluster_kernel_records_of_the_arriving_state():
+    """obs_in at L = 128 (the cluster kernel): each strip's share of the sums rides along with the residual build and
+    rank 0 gathers them -- bit for bit the records of ordinary launches."""
+    N, chains, K, kappa = 128, 160, 5, 0.7
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 3)
+    rphi, rn = phi.clone(), n.clone()
+    rec_ref = torch.zeros((K, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for k in range(K):
+        ops.villain_sweep(rphi, rn, kappa, seed=21, sweep0=2 * k, n_sweeps=2, obs=rec_ref[k])
+    rec = torch.full((K, chains, VOBS_COUNT), -7.0, dtype=torch.float64, device='cuda')
+    scratch = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ov = ops.VillainOverlappedSweeps(phi, n, kappa, seed=21)
+    for k in range(K):
+        ov.step(2 * k, 2, obs=rec[k], obs_in=rec[k - 1] if k else scratch)
+    torch.cuda.synchronize()
+    assert torch.equal(phi, rphi) and torch.equal(n, rn)
+    assert torch.equal(rec[:K - 1], rec_ref[:K - 1])
+    assert torch.equal(rec[K - 1, :, 4:], rec_ref[K - 1, :, 4:])
+    assert int(ov.epochs.min()) == ov.epoch == K
 
 
 def test_host_stepper_two_steps_in_flight():

@@ -54,12 +54,19 @@ if 'c4' in which:
     phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
     obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
     kc = torch.linspace(0.3, 1.2, CH, dtype=torch.float64, device='cuda')
-    for path, sw in (('global', 1), ('tiled', 1), ('tiled', 2), ('tiled', 10)):
+    for path, sw in (('auto', 1), ('auto', 2), ('auto', 10), ('global', 1), ('tiled', 1), ('tiled', 2), ('tiled', 10)):
         k = [0]
         def f():
             k[0] += sw
             ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], kappa_chain=kc, obs=obs, path=path, n_sweeps=sw)
         report(f'villain L=128 x 1024 chains (C4), {path}, {sw} sweep(s)/call', CH * N * N * sw, 32, timeit(f, n=5))
+    ov = ops.VillainOverlappedSweeps(phi, n, 0.5, seed=1, kappa_chain=kc)
+    obs2 = [torch.zeros_like(obs) for _ in range(2)]
+    k = [0]
+    def g():
+        k[0] += 1
+        ov.step(k[0], 1, obs2[k[0] & 1], obs2[(k[0] & 1) ^ 1])
+    report('villain L=128 x 1024 chains (C4), overlapped launches + obs_in, 1 sweep/call', CH * N * N, 32, timeit(g, n=20))
 if 'c5' in which:
     N, CH = 4096, 1
     S = svb.Villain(svb.Lattice2D(N), 0.5)
