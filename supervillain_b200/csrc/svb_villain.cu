@@ -1585,6 +1585,15 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 
 #include "svb_villain_filtered.cuh"
 #include "svb_villain_cluster.cuh"
+#ifndef SVB_CLUSTER_TPB
+#define SVB_CLUSTER_TPB 512
+#endif
+#ifndef SVB_CLUSTER_CL
+#define SVB_CLUSTER_CL 4
+#endif
+#ifndef SVB_CLUSTER_STAGES
+#define SVB_CLUSTER_STAGES 1
+#endif
 
 #ifndef SVB_FILT_MINB32
 #define SVB_FILT_MINB32 8        /* 64 registers per thread: 8 CTAs = 32 warps per SM (28.5 vs 30.0 us at config 2) */
@@ -1701,7 +1710,7 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
     if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED && arith_mode != SVB_ARITH_STRICT &&
         !a.accept_mask && !a.dS_out && !a.exact_mode && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
         // one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
-        return launch_villain_cluster<128, 4>(a, stream, info);
+        return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, stream, info);
     }
 #endif
     if (path == SVB_PATH_AUTO) {
@@ -1797,7 +1806,7 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
         case 16: return launch_villain_filtered<16, 16, 1>(a, st, info);
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
         case 64: return launch_villain_filtered<64, 2, 1>(a, st, info);
-        default: return launch_villain_cluster<128, 4>(a, st, info);
+        default: return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, st, info);
     }
 }
 

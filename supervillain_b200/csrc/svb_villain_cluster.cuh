@@ -25,9 +25,23 @@ __device__ __forceinline__ int cluster_cta_rank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// the two halves separately: work that touches nothing another thread writes may sit between them
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// The two halves separately: work that touches nothing another thread writes may sit between them.
+// arrive: a release at cluster scope costs a gpu-scope MEMBAR (SASS: MEMBAR.ALL.GPU, ~0.3 us, and 16 warps of them queue
+// up) -- the top stall of the first version of this kernel.  One warp releases on behalf of the CTA instead: the block
+// barrier orders every thread's writes (also those into a neighbour's shared memory) before warp 0's release fence, and
+// fences are cumulative, so the other warps arrive relaxed.  203 -> 190 us per config-4 shard sweep.  (No release at all,
+// -DSVB_CLUSTER_RELAXED: 179 us, passes every test, and is a data race by the PTX memory model -- not used.)
+#ifdef SVB_CLUSTER_RELAXED   /* EXPERIMENT ONLY */
+__device__ __forceinline__ void cluster_arrive() { asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+#else
+__device__ __forceinline__ void cluster_arrive() {
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+#endif
 // the generic address of `p` (a shared-memory address of this CTA) in the CTA of rank `rank`
 template <typename T>
 __device__ __forceinline__ T* cluster_map(T* p, int rank) {
@@ -65,21 +79,43 @@ __device__ __noinline__ bool villain_exact_decision_ptr(const ExactProposalPtr& 
 // OVERLAP: the overlapped-launch protocol of svb_villain_sweep_overlapped (see villain_smem_filtered_kernel): thread 0 of
 // every CTA acquires the chain's epoch before loading its strip; rank 0 publishes the epochs of all the cluster's chains at
 // the end, behind a cluster barrier that follows every CTA's completed bulk stores.
-template <int NT, int CL, bool OVERLAP>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
+// TPB threads per CTA (8 or 16 row groups of N/2 column slots); STAGES = 2: phi and n double-buffered, so that the next
+// chain's strip arrives and the previous one's leaves while this one is swept (one CTA of 1024 threads per SM).
+// The cold half of the epoch wait (the producer launch has not stored the chain yet), out of line: it must not cost the
+// sweep loop registers.
+static __device__ __noinline__ void cluster_epoch_spin(const uint32_t* epoch, uint32_t want) {
+    unsigned ns = 32, naps = 0;
+    while (true) {
+        uint32_t e;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(epoch) : "memory");
+        if (e == want) return;
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
+        if (++naps > (1u << 21)) __trap();          // > 2 s: a producer that never comes is a caller error
+    }
+}
+
+constexpr int cluster_min_blocks(int NT, int CL, int TPB, int STAGES) {
+    return (TPB >= 1024 || (STAGES * 16 + 8) * (NT / CL) * NT > 112 * 1024) ? 1 : 2;          // two CTAs per SM where they fit
+}
+template <int NT, int CL, int TPB, int STAGES, bool OVERLAP>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_blocks(NT, CL, TPB, STAGES))
     villain_cluster_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int N = NT, V = N * N, HN = N / 2, ROWS = N / CL, VL = ROWS * N, VHL = ROWS * HN, T = 8 * HN, NW = T / 32;
-    constexpr int PER = VHL / T;                                  // sites per thread per colour (rows row8 + 8 q)
-    static_assert(T == 4 * NT && ROWS % 16 == 0 && PER >= 2 && PER % 2 == 0, "villain_cluster_kernel: unsupported geometry");
-    constexpr uint32_t bytes_phi = VL * sizeof(double), bytes_n = VL * sizeof(int32_t);
+    constexpr int N = NT, V = N * N, HN = N / 2, ROWS = N / CL, VL = ROWS * N, VHL = ROWS * HN, T = TPB, NW = T / 32;
+    constexpr int RG = T / HN;                                    // row groups
+    constexpr int PER = ROWS / RG;                                // sites per thread per colour (rows r0 + 8 q)
+    constexpr int Q = 8 * HN;                                     // compact-index distance between a thread's rows
+    static_assert(RG % 8 == 0 && RG * HN == T && PER * RG == ROWS && PER >= 2 && PER % 2 == 0 && (STAGES == 1 || STAGES == 2),
+                  "villain_cluster_kernel: unsupported geometry");
+    constexpr uint32_t bytes_phi = VL * sizeof(double), bytes_n = VL * sizeof(int32_t), stage_bytes = bytes_phi + 2 * bytes_n;
     const int rank = cluster_cta_rank();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    double* sphi = reinterpret_cast<double*>(smem_raw);
+    double* sphi = reinterpret_cast<double*>(smem_raw);           // the stage being swept (set per chain)
     int32_t* sn0 = reinterpret_cast<int32_t*>(smem_raw + bytes_phi);
     int32_t* sn1 = sn0 + VL;
-    float* rc0 = reinterpret_cast<float*>(sn1 + VL);              // [colour][VHL]: residual of link (0, x)
+    float* rc0 = reinterpret_cast<float*>(smem_raw + STAGES * stage_bytes);   // [colour][VHL]: residual of link (0, x)
     float* rc1 = rc0 + 2 * VHL;                                   // [colour][VHL]: residual of link (1, x)
     double* red_state = reinterpret_cast<double*>(rc1 + 2 * VHL); // [NW][4] per-warp partial sums
     double* red_count = red_state + 4 * NW;                       // [NW][2]
@@ -97,7 +133,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
 #define PREV_RC0 cluster_map(rc0, prev_rank)
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+        for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
         fence_mbar_init();
     }
     if (OVERLAP) {
@@ -114,9 +150,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
     const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
     const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;
 
-    const int row8 = tid / HN, k = tid - row8 * HN;
-    const int cc = row8 & 1;
-    const bool first_row_thread = (row8 == 0), last_row_thread = (row8 == 7);
+    // a thread's rows are r0 + 8 q, q < PER; rows r0 + 16 p and r0 + 16 p + 8 share a Philox block
+    const int rg = tid / HN, k = tid - rg * HN;
+    const int r0 = (rg & 7) + 8 * PER * (rg >> 3);
+    const int jb = r0 * HN + k;                                   // compact index of the thread's first site
+    const int cc = r0 & 1;
+    const bool first_row_thread = (r0 == 0), last_row_thread = (r0 + 8 * (PER - 1) == ROWS - 1);
 
     const long long n_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
     auto peek_epoch = [&](long long chain) -> uint32_t {
@@ -125,24 +164,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.epochs + chain) : "memory");
         return e;
     };
-    auto issue_load = [&](long long chain, uint32_t seen) {
+    auto issue_load = [&](long long chain, int b, uint32_t seen) {
         if (OVERLAP && !a.grid_wait) {
-            uint32_t e = seen;
-            unsigned ns = 32, naps = 0;
-            while (true) {
-                if (e == a.wait_epoch) break;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.epochs + chain) : "memory");
-                if (e == a.wait_epoch) break;
-                __nanosleep(ns);
-                if (ns < 1024) ns *= 2;
-                if (++naps > (1u << 21)) __trap();          // > 2 s: a producer that never comes is a caller error
-            }
+            if (seen != a.wait_epoch) cluster_epoch_spin(a.epochs + chain, a.wait_epoch);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        mbar_expect_tx(bar, bytes_phi + 2 * bytes_n);
-        bulk_g2s(sphi, reinterpret_cast<const double*>(a.phi) + chain * V + (long long)rank * VL, bytes_phi, bar);
-        bulk_g2s(sn0, a.n + chain * 2 * V + (long long)rank * VL, bytes_n, bar);
-        bulk_g2s(sn1, a.n + chain * 2 * V + V + (long long)rank * VL, bytes_n, bar);
+        unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
+        mbar_expect_tx(&bar[b], stage_bytes);
+        bulk_g2s(stage, reinterpret_cast<const double*>(a.phi) + chain * V + (long long)rank * VL, bytes_phi, &bar[b]);
+        bulk_g2s(stage + bytes_phi, a.n + chain * 2 * V + (long long)rank * VL, bytes_n, &bar[b]);
+        bulk_g2s(stage + bytes_phi + bytes_n, a.n + chain * 2 * V + V + (long long)rank * VL, bytes_n, &bar[b]);
     };
     // the next chain's strip on its way into L2 while this one is being swept: the load phase then runs at L2 speed
     auto prefetch_l2 = [&](long long chain) {
@@ -155,6 +186,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
 #endif
     };
     // rank 0 gathers the four CTAs' shares of a finished chain's record (call behind a cluster barrier that follows them)
+    // Records: ONE thread (lane 0 of warp 1; thread 0 is busy with the bulk copies) adds the slots in a fixed order.  A
+    // shuffle-tree version over warp 1 measured 10 % SLOWER per launch -- with or without records: it costs registers in
+    // the 64-register budget of the sweep loop (88 vs 44 bytes spilled).
     auto gather_record = [&](long long chain, double kappa) {
         if (rank == 0 && tid == kWriter && (a.obs || a.obs_in)) {
             double t[6] = {0, 0, 0, 0, 0, 0};
@@ -175,7 +209,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
             }
         }
     };
-    // this CTA's share: the warp slots summed in warp order (call behind a block barrier that follows chain_partials)
     auto cta_share = [&](bool state, bool counters) {
         if (tid == kWriter) {
             if (state) {
@@ -196,24 +229,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
     // sums of the strip's forward links and plaquettes from the current phi and n (fp64), as in the smem kernel
     // part 0: the rows that need nothing from another strip (q < PER - 1); part 1: q = PER - 1; part 2: all
     auto state_sums = [&](double& action, long long& dn2, int& w0, int& w1, bool store_r, bool sums, int part) {
-        float* w0e = rc0 + cc * VHL + tid;
-        float* w1e = rc1 + cc * VHL + tid;
-        float* w0o = rc0 + (cc ^ 1) * VHL + tid;
-        float* w1o = rc1 + (cc ^ 1) * VHL + tid;
+        float* w0e = rc0 + cc * VHL + jb;
+        float* w1e = rc1 + cc * VHL + jb;
+        float* w0o = rc0 + (cc ^ 1) * VHL + jb;
+        float* w1o = rc1 + (cc ^ 1) * VHL + jb;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             if ((part == 0 && q == PER - 1) || (part == 1 && q != PER - 1)) continue;
-            const int lx0 = row8 + 8 * q;
+            const int lx0 = r0 + 8 * q;
             const double* p_c = sphi + lx0 * N + 2 * k;
             const bool below_remote = (q == PER - 1) && last_row_thread;
             const double* p_u = below_remote ? NEXT_PHI + 2 * k : p_c + N;
             const PairResiduals pr = villain_pair_residuals(p_c, p_u, sphi + lx0 * N + ((2 * k + 2) & (N - 1)), sn0 + lx0 * N + 2 * k,
                                                             sn1 + lx0 * N + 2 * k);
             if (store_r) {
-                w0e[T * q] = (float)pr.r0e;
-                w1e[T * q] = (float)pr.r1e;
-                w0o[T * q] = (float)pr.r0o;
-                w1o[T * q] = (float)pr.r1o;
+                w0e[Q * q] = (float)pr.r0e;
+                w1e[Q * q] = (float)pr.r1e;
+                w0o[Q * q] = (float)pr.r0o;
+                w1o[Q * q] = (float)pr.r1o;
             }
             if (sums) {
                 action = fma(pr.r0e, pr.r0e, action);
@@ -232,7 +265,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
     };
 
     long long chain = cluster_id;
-    if (tid == 0 && chain < a.chains) issue_load(chain, peek_epoch(chain));
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0, peek_epoch(chain));
     long long pending_chain = -1;
     double pending_kappa = 0.0;
 
@@ -244,8 +277,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
         const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
         const float2 hk22 = make_float2(hk2, hk2), hkA2 = make_float2(hkA, hkA), hkB2 = make_float2(hkB, hkB);
 
-        mbar_wait(bar, (uint32_t)(it & 1));
-        if (tid == 0 && next < a.chains) prefetch_l2(next);
+        const int b = (STAGES == 2) ? (it & 1) : 0;
+        sphi = reinterpret_cast<double*>(smem_raw + (size_t)b * stage_bytes);
+        sn0 = reinterpret_cast<int32_t*>(smem_raw + (size_t)b * stage_bytes + bytes_phi);
+        sn1 = sn0 + VL;
+        mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
+        if (STAGES == 1 && tid == 0 && next < a.chains) prefetch_l2(next);
         cluster_arrive();                                          // S1: every strip of the chain has landed (waited for below)
 
         int n_acc = 0;
@@ -262,6 +299,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
                     // the strip's own rows while the other strips are still landing; its last row needs the next strip
                     state_sums(action, dn2, w0, w1, true, sums, 0);
                     cluster_wait();                                // S1
+                    // the other stage is free in every strip now (its last readers have arrived here): fetch the next chain
+                    if (STAGES == 2 && tid == 0 && next < a.chains) {
+                        bulk_wait_read0();                         // (the previous chain's store has long read it)
+                        issue_load(next, b ^ 1, peek_epoch(next));
+                    }
                     if (pending_chain >= 0) gather_record(pending_chain, pending_kappa);
                     state_sums(action, dn2, w0, w1, true, sums, 1);
                 } else {
@@ -274,18 +316,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
             const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)s;
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                const int par = (row8 + c) & 1;
+                const int par = (r0 + c) & 1;
                 const int x1 = 2 * k + par;
                 const int ob1 = par ? 0 : ((k == 0) ? (1 - HN) : 1);
                 const int wrap1 = (x1 == 0) ? N : 0;
-                float* R0own = rc0 + c * VHL + tid;
-                float* R1own = rc1 + c * VHL + tid;
-                float* R0b = rc0 + (c ^ 1) * VHL + tid - HN;        // backward link (0, x - e0): row above, same compact column
+                float* R0own = rc0 + c * VHL + jb;
+                float* R1own = rc1 + c * VHL + jb;
+                float* R0b = rc0 + (c ^ 1) * VHL + jb - HN;        // backward link (0, x - e0): row above, same compact column
                 float* R0b_q0 = first_row_thread ? PREV_RC0 + (c ^ 1) * VHL + (ROWS - 1) * HN + k : R0b;   // ... in the previous strip
-                float* R1b = rc1 + (c ^ 1) * VHL + tid - ob1;
-                double* Pc = sphi + 2 * tid + par;
-                int32_t* N0c = sn0 + 2 * tid + par;
-                int32_t* N1c = sn1 + 2 * tid + par;
+                float* R1b = rc1 + (c ^ 1) * VHL + jb - ob1;
+                double* Pc = sphi + 2 * jb + par;
+                int32_t* N0c = sn0 + 2 * jb + par;
+                int32_t* N1c = sn1 + 2 * jb + par;
                 int32_t* N0b = N0c - N;
                 int32_t* N0b_q0 = first_row_thread ? PREV_N0 + (ROWS - 1) * N + x1 : N0b;
                 int32_t* N1b = N1c - 1 + wrap1;
@@ -293,12 +335,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
                 Philox4 bits_p[PER / 2];
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p)
-                    bits_p[p] = philox_site_keys(a, gc, gs, (uint32_t)((rank * ROWS + row8 + 16 * p) * N + x1));
+                    bits_p[p] = philox_site_keys(a, gc, gs, (uint32_t)((rank * ROWS + r0 + 16 * p) * N + x1));
                 cluster_wait();                                    // S2 / S3: the previous pass is complete in every strip
                 if (c == 0 && obs_of_input && s == 0) cta_share(true, false);
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p) {
-                    const int gx0 = rank * ROWS + row8 + 16 * p;                              // global row of the pair's first site
+                    const int gx0 = rank * ROWS + r0 + 16 * p;                              // global row of the pair's first site
                     const uint32_t c0 = (uint32_t)(gx0 * N + x1);                             // villain_pair_counter (bit 3 clear)
                     const Philox4 bits = bits_p[p];
                     const int qA = 2 * p, qB = 2 * p + 1;
@@ -316,9 +358,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
                     U = __fadd2_rn(U, make_float2(-0.99999994f, -0.99999994f));
                     const float2 dphi = __ffma2_rn(make_float2(fc.two_I, fc.two_I), U, make_float2(-fc.I, -fc.I));
                     const float2 base_f = __ffma2_rn(dphi, make_float2(-1.0f, -1.0f), cIn2), base_b = __fadd2_rn(cIn2, dphi);
-                    const float2 r_f0 = make_float2(R0own[T * qA], R0own[T * qB]), r_f1 = make_float2(R1own[T * qA], R1own[T * qB]);
-                    const float2 r_b0 = make_float2(r0bA[T * qA], R0b[T * qB]);
-                    const float2 r_b1 = make_float2(R1b[T * qA], R1b[T * qB]);
+                    const float2 r_f0 = make_float2(R0own[Q * qA], R0own[Q * qB]), r_f1 = make_float2(R1own[Q * qA], R1own[Q * qB]);
+                    const float2 r_b0 = make_float2(r0bA[Q * qA], R0b[Q * qB]);
+                    const float2 r_b1 = make_float2(R1b[Q * qA], R1b[Q * qB]);
                     const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
                     const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
                     const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
@@ -340,15 +382,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int q = 2 * p + h;
-                        float* r0b_site = (h ? R0b : r0bA) + T * q;                   // q == 0 of row 0: in the previous strip
-                        int32_t* n0b_site = (h ? N0b : n0bA) + 2 * T * q;
+                        float* r0b_site = (h ? R0b : r0bA) + Q * q;                   // q == 0 of row 0: in the previous strip
+                        int32_t* n0b_site = (h ? N0b : n0bA) + 2 * Q * q;
                         const uint32_t wA = h ? bits.z : bits.x;
                         const uint32_t f = h ? fB : fA;
                         const int* dig = h ? digB : digA;
                         const float dif = h ? diff.y : diff.x, bnd = h ? band.y : band.x;
                         bool ok = dif < 0.0f;
                         if (!(fabsf(dif) > bnd) || f < 65536u) {
-                            const int lx0 = row8 + 8 * q;
+                            const int lx0 = r0 + 8 * q;
                             ExactProposalPtr ep;
                             ep.p_c = sphi + lx0 * N + x1;
                             ep.p_f0 = (lx0 + 1 < ROWS) ? ep.p_c + N : NEXT_PHI + x1;
@@ -371,15 +413,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
                         n_acc += ok ? 1 : 0;
                         if (ok) {
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
-                            Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
-                            atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
+                            Pc[2 * Q * q] = __dadd_rn(Pc[2 * Q * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
+                            atomicAdd(N0c + 2 * Q * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
                             atomicAdd(n0b_site, W * dig[1] + mWI);
-                            atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
-                            atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
-                            R0own[T * q] = h ? n_f0.y : n_f0.x;
+                            atomicAdd(N1c + 2 * Q * q, W * dig[2] + mWI);
+                            atomicAdd(N1b + 2 * Q * q, W * dig[3] + mWI);
+                            R0own[Q * q] = h ? n_f0.y : n_f0.x;
                             *r0b_site = h ? n_b0.y : n_b0.x;
-                            R1own[T * q] = h ? n_f1.y : n_f1.x;
-                            R1b[T * q] = h ? n_b1.y : n_b1.x;
+                            R1own[Q * q] = h ? n_f1.y : n_f1.x;
+                            R1b[Q * q] = h ? n_b1.y : n_b1.x;
                         }
                     }
                 }
@@ -401,7 +443,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
             long long dn2 = 0;
             state_sums(action, dn2, w0, w1, false, true, 2);
             chain_partials<true, false>(red_state, red_count, lane, warp, action, dn2, w0, w1, 0.0, 0);
-            cluster_sync_all();                                        // S5: nobody reads this strip any more
+            if (STAGES == 1) { cluster_arrive(); cluster_wait(); }     // S5: nobody reads this strip any more, it may be refilled
+            else __syncthreads();                                      // (two stages: the refill waits behind the next chain's S1)
             cta_share(true, false);
         }
 
@@ -411,9 +454,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
             bulk_s2g(a.n + chain * 2 * V + (long long)rank * VL, sn0, bytes_n);
             bulk_s2g(a.n + chain * 2 * V + V + (long long)rank * VL, sn1, bytes_n);
             bulk_commit();
-            const uint32_t seen_next = (next < a.chains) ? peek_epoch(next) : 0;
-            bulk_wait_read0();
-            if (next < a.chains) issue_load(next, seen_next);
+            const uint32_t seen_next = (STAGES == 1 && next < a.chains) ? peek_epoch(next) : 0;
+            if (STAGES == 1) {
+                bulk_wait_read0();
+                if (next < a.chains) issue_load(next, 0, seen_next);
+            }
         }
         pending_chain = chain;
         pending_kappa = kappa;
@@ -440,19 +485,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(4 * NT, 2)
 #undef PREV_RC0
 }
 
-template <int NT, int CL>
+template <int NT, int CL, int TPB, int STAGES>
 static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool overlap = a.epochs != nullptr;
-    auto kern = overlap ? villain_cluster_kernel<NT, CL, true> : villain_cluster_kernel<NT, CL, false>;
-    constexpr int ROWS = NT / CL, VL = ROWS * NT, VHL = ROWS * NT / 2, NW = 4 * NT / 32;
-    const size_t smem = (size_t)VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16;
+    auto kern = overlap ? villain_cluster_kernel<NT, CL, TPB, STAGES, true> : villain_cluster_kernel<NT, CL, TPB, STAGES, false>;
+    constexpr int ROWS = NT / CL, VL = ROWS * NT, VHL = ROWS * NT / 2, NW = TPB / 32;
+    const size_t smem = (size_t)STAGES * VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16 * STAGES;
     static int clusters_cache[2][64];
     int clusters = (info.device < 64) ? clusters_cache[overlap][info.device] : 0;
     if (clusters == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(CL * info.sm_count); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(CL * info.sm_count); cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -466,7 +511,7 @@ static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, con
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
     if (overlap) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n_clusters * CL)); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned)(n_clusters * CL)); cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -474,7 +519,7 @@ static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, con
         SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, fc));
         return 0;
     }
-    kern<<<(unsigned)(n_clusters * CL), 4 * NT, smem, stream>>>(a, fc);
+    kern<<<(unsigned)(n_clusters * CL), TPB, smem, stream>>>(a, fc);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
