@@ -4,8 +4,9 @@
 //   Spin_Spin.Villain        s = exp(i phi)             supervillain/observable/spin.py:28-42
 //   Winding_Winding.Villain  s = dn                     supervillain/observable/winding.py:77-86
 //   Vortex_Vortex.Worldline  s = exp(2 pi i v / W)      supervillain/observable/vortex.py:22-37
-// The reference evaluates it with three FFTs; here it is the direct O(N^4) sum out of shared
-// memory, which is exact to rounding and cheap for the lattices that fit an SM (N <= 64).
+// The reference evaluates it with three FFTs.  Here: the direct O(N^4) sum out of shared memory for small or
+// non-power-of-two lattices (exact to rounding), a shared-memory FFT for N = 16, 32, 64, and a three-launch FFT for
+// power-of-two lattices up to N = 4096.
 
 #include "svb_common.cuh"
 
@@ -151,9 +152,178 @@ __global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Power-of-two lattices beyond shared memory (128 <= N <= 4096: configs 4 and 5) -- the same transform in three launches
+// that use `out` (chains, N, N) complex128 itself as the workspace:
+//   1. rows:    s from the field, decimation-in-frequency FFT of R rows per CTA, written in bit-reversed column order;
+//   2. columns: C columns per CTA (padded in shared memory): DIF, |.|^2, decimation-in-time -- back in natural row order;
+//   3. rows:    DIT of the bit-reversed rows, scaling by N^-4.
+// No transposes and no bit-reversal passes; 16 + 32 + 32 B of traffic per site on top of reading the field.
+// ------------------------------------------------------------------------------------------
+template <bool DIF>
+__device__ __forceinline__ void fft_lines(double2* __restrict__ d, int n, int log2n, int lines, int line_stride,
+                                          const double2* __restrict__ tw) {
+    const int half_n = n >> 1;
+    for (int st = 0; st < log2n; ++st) {
+        const int lh = DIF ? (log2n - 1 - st) : st;               // log2 of the butterfly half-span
+        const int half = 1 << lh;
+        const int tw_shift = log2n - 1 - lh;                      // twiddle e^{-2 pi i j / (2 half)} = tw[j << tw_shift]
+        for (int b = threadIdx.x; b < lines * half_n; b += blockDim.x) {
+            const int line = b >> (log2n - 1), bb = b & (half_n - 1);
+            const int group = bb >> lh, j = bb & (half - 1);
+            double2* p0 = d + line * line_stride + (group << (lh + 1)) + j;
+            double2* p1 = p0 + half;
+            const double2 w = tw[j << tw_shift];
+            const double2 a = *p0, c = *p1;
+            if (DIF) {
+                const double dr = a.x - c.x, di = a.y - c.y;
+                *p0 = make_double2(a.x + c.x, a.y + c.y);
+                *p1 = make_double2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+            } else {
+                const double tr = c.x * w.x - c.y * w.y, ti = c.x * w.y + c.y * w.x;
+                *p0 = make_double2(a.x + tr, a.y + ti);
+                *p1 = make_double2(a.x - tr, a.y - ti);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void fft_twiddles(double2* tw, int n) {
+    for (int k = threadIdx.x; k < n / 2; k += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)k / (double)n, &sn, &cs);
+        tw[k] = make_double2(cs, sn);
+    }
+}
+
+// launch 1: R rows per work item
+template <typename real, int KIND>
+__global__ void __launch_bounds__(256) correlation_rows_forward_kernel(const real* __restrict__ field, long long chains, int N, int log2n,
+                                                                       int W, int R, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* d = reinterpret_cast<double2*>(smem_raw);
+    double2* tw = d + (size_t)R * N;
+    fft_twiddles(tw, N);
+    const long long V = (long long)N * N, groups = N / R, items = chains * groups;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / groups;
+        const int row0 = (int)(item - chain * groups) * R;
+        const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+        __syncthreads();
+        for (int i = threadIdx.x; i < R * N; i += blockDim.x) {
+            const int x0 = row0 + (i >> log2n), x1 = i & (N - 1);
+            const long long at = (long long)x0 * N + x1;
+            if (KIND == SVB_CORR_WINDING) {
+                const long long i0 = (long long)((x0 + 1) & (N - 1)) * N + x1, i1 = (long long)x0 * N + ((x1 + 1) & (N - 1));
+                d[i] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
+            } else {
+                double sn, cs;
+                const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[at]) / (double)W : (double)g[at];
+                sincos(ang, &sn, &cs);
+                d[i] = make_double2(cs, sn);
+            }
+        }
+        __syncthreads();
+        fft_lines<true>(d, N, log2n, R, N, tw);
+        double2* o = out + chain * V + (long long)row0 * N;
+        for (int i = threadIdx.x; i < R * N; i += blockDim.x) o[i] = d[i];
+    }
+}
+
+// launch 2: C columns per work item, both column transforms and the pointwise square in one visit
+__global__ void __launch_bounds__(256) correlation_columns_kernel(long long chains, int N, int log2n, int C, int log2c,
+                                                                  double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* d = reinterpret_cast<double2*>(smem_raw);
+    const int stride = N + 1;                                     // padded: a column's rows are contiguous, columns a bank apart
+    double2* tw = d + (size_t)C * stride;
+    fft_twiddles(tw, N);
+    const long long V = (long long)N * N, groups = N / C, items = chains * groups;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / groups;
+        const int col0 = (int)(item - chain * groups) * C;
+        double2* o = out + chain * V + col0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * N; i += blockDim.x) {
+            const int r = i >> log2c, c = i & (C - 1);
+            d[c * stride + r] = o[(long long)r * N + c];
+        }
+        __syncthreads();
+        fft_lines<true>(d, N, log2n, C, stride, tw);
+        for (int i = threadIdx.x; i < C * N; i += blockDim.x) {
+            double2* q = d + (i >> log2n) * stride + (i & (N - 1));
+            const double2 v = *q;
+            *q = make_double2(v.x * v.x + v.y * v.y, 0.0);
+        }
+        __syncthreads();
+        fft_lines<false>(d, N, log2n, C, stride, tw);
+        for (int i = threadIdx.x; i < C * N; i += blockDim.x) {
+            const int r = i >> log2c, c = i & (C - 1);
+            o[(long long)r * N + c] = d[c * stride + r];
+        }
+    }
+}
+
+// launch 3
+__global__ void __launch_bounds__(256) correlation_rows_inverse_kernel(long long chains, int N, int log2n, int R, double scale,
+                                                                       double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* d = reinterpret_cast<double2*>(smem_raw);
+    double2* tw = d + (size_t)R * N;
+    fft_twiddles(tw, N);
+    const long long V = (long long)N * N, groups = N / R, items = chains * groups;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / groups;
+        double2* o = out + chain * V + (long long)((int)(item - chain * groups) * R) * N;
+        __syncthreads();
+        for (int i = threadIdx.x; i < R * N; i += blockDim.x) d[i] = o[i];
+        __syncthreads();
+        fft_lines<false>(d, N, log2n, R, N, tw);
+        for (int i = threadIdx.x; i < R * N; i += blockDim.x) {
+            const double2 v = d[i];
+            o[i] = make_double2(v.x * scale, v.y * scale);
+        }
+    }
+}
+
 }  // namespace svb
 
 using namespace svb;
+
+template <typename real, int KIND>
+static int launch_correlation_fft_large(const void* field, long long chains, int N, int W, double* out, int sms, cudaStream_t st) {
+    int log2n = 0;
+    while ((1 << log2n) < N) ++log2n;
+    const int R = N >= 2048 ? 1 : 2048 / N;                       // 32 KiB of rows per work item
+    int C = 8192 / N;                                             // <= 128 KiB of columns per work item
+    if (C > 8) C = 8;
+    int log2c = 0;
+    while ((1 << log2c) < C) ++log2c;
+    const size_t smem_rows = ((size_t)R * N + N / 2) * sizeof(double2);
+    const size_t smem_cols = ((size_t)C * (N + 1) + N / 2) * sizeof(double2);
+    auto k1 = correlation_rows_forward_kernel<real, KIND>;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_rows_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    int per_sm_rows = 0, per_sm_cols = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rows, k1, 256, smem_rows));
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cols, correlation_columns_kernel, 256, smem_cols));
+    if (per_sm_rows < 1 || per_sm_cols < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the FFT kernels", N);
+    const long long row_items = chains * (N / R), col_items = chains * (N / C);
+    const long long cap_rows = (long long)per_sm_rows * sms, cap_cols = (long long)per_sm_cols * sms;
+    double2* o = reinterpret_cast<double2*>(out);
+    k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
+                                                                                         log2n, W, R, o);
+    SVB_CUDA_TRY(cudaGetLastError());
+    correlation_columns_kernel<<<(unsigned)(col_items < cap_cols ? col_items : cap_cols), 256, smem_cols, st>>>(chains, N, log2n, C, log2c, o);
+    SVB_CUDA_TRY(cudaGetLastError());
+    const double V = (double)N * (double)N;
+    correlation_rows_inverse_kernel<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(chains, N, log2n, R,
+                                                                                                                     1.0 / (V * V), o);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
 
 template <typename real, int KIND, int NT>
 static int launch_correlation_fft(const void* field, long long chains, int W, double* out, int sms, cudaStream_t st) {
@@ -191,9 +361,18 @@ extern "C" int svb_correlation(int kind, const void* field, int dtype, int64_t c
     SVB_CUDA_TRY(cudaGetDevice(&dev));
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     SVB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (smem > (size_t)max_smem)
-        return fail(SVB_E_UNSUPPORTED, "svb_correlation: direct evaluation needs the lattice in shared memory (N=%d too large)", N);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (N >= 128 && N <= 4096 && (N & (N - 1)) == 0 && (uintptr_t)out % 16 == 0) {
+        // power-of-two lattices beyond shared memory: three-launch FFT with `out` as the workspace
+        if (kind == SVB_CORR_SPIN && dtype == SVB_F64) return launch_correlation_fft_large<double, SVB_CORR_SPIN>(field, chains, N, W, out, sms, st);
+        if (kind == SVB_CORR_SPIN && dtype == SVB_F32) return launch_correlation_fft_large<float, SVB_CORR_SPIN>(field, chains, N, W, out, sms, st);
+        if (kind == SVB_CORR_WINDING) return launch_correlation_fft_large<int32_t, SVB_CORR_WINDING>(field, chains, N, W, out, sms, st);
+        if (kind == SVB_CORR_VORTEX) return launch_correlation_fft_large<int32_t, SVB_CORR_VORTEX>(field, chains, N, W, out, sms, st);
+        return fail(SVB_E_PARAM, "svb_correlation: kind %d", kind);
+    }
+    if (smem > (size_t)max_smem)
+        return fail(SVB_E_UNSUPPORTED,
+                    "svb_correlation: N=%d is neither a power of two in [16, 4096] (FFT) nor small enough for the direct sum out of shared memory", N);
 #define SVB_CORR_FFT(real, KIND)                                                                             \
     switch (N) {                                                                                             \
         case 16: return launch_correlation_fft<real, KIND, 16>(field, chains, W, out, sms, st);             \

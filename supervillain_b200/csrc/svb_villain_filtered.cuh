@@ -80,6 +80,25 @@ __device__ __noinline__ bool villain_exact_decision(const ExactProposal& p) {
     return villain_decide_lazy(exp_clipped(-dS), p.d, p.rc);
 }
 
+// The same decision in the reference's operation order (STRICT arithmetic of villain_site_update: one rounding per numpy
+// operation, neighborhood.py:91,110-112): p.c = 2 pi and p.g = dn in units of 1.  With this fallback the filtered kernel is
+// decision for decision the STRICT kernel -- the filter only ever answers when the answer does not depend on the last bits.
+__device__ __noinline__ bool villain_exact_decision_strict(const ExactProposal& p) {
+    const double pc = p.phi[p.i_c];
+    const double r_f0 = __dsub_rn(__dsub_rn(p.phi[p.i_f0], pc), __dmul_rn(SVB_TWO_PI, (double)p.n0[p.i_c]));
+    const double r_b0 = __dsub_rn(__dsub_rn(pc, p.phi[p.i_b0]), __dmul_rn(SVB_TWO_PI, (double)p.n0[p.i_b0]));
+    const double r_f1 = __dsub_rn(__dsub_rn(p.phi[p.i_f1], pc), __dmul_rn(SVB_TWO_PI, (double)p.n1[p.i_c]));
+    const double r_b1 = __dsub_rn(__dsub_rn(pc, p.phi[p.i_b1]), __dmul_rn(SVB_TWO_PI, (double)p.n1[p.i_b1]));
+    const double dr_f0 = __dsub_rn(-p.dphi, __dmul_rn(p.c, (double)p.g[0])), dr_b0 = __dsub_rn(p.dphi, __dmul_rn(p.c, (double)p.g[1]));
+    const double dr_f1 = __dsub_rn(-p.dphi, __dmul_rn(p.c, (double)p.g[2])), dr_b1 = __dsub_rn(p.dphi, __dmul_rn(p.c, (double)p.g[3]));
+    const double hk = p.half_kappa;
+    double dS = __dmul_rn(__dmul_rn(hk, dr_f0), __dadd_rn(__dmul_rn(2.0, r_f0), dr_f0));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_b0), __dadd_rn(__dmul_rn(2.0, r_b0), dr_b0)));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_f1), __dadd_rn(__dmul_rn(2.0, r_f1), dr_f1)));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_b1), __dadd_rn(__dmul_rn(2.0, r_b1), dr_b1)));
+    return villain_decide_lazy(exp_clipped(-dS), p.d, p.rc);
+}
+
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -176,7 +195,15 @@ __device__ __forceinline__ void chain_finish(const double* red_state, const doub
 // individually through `a.epochs`: a chain is loaded only once its epoch reads a.wait_epoch (written by the launch that
 // last stored it), and a CTA sets the epochs of its chains to a.signal_epoch once all its stores and records are complete.
 // UNIT: W == 1 and interval_n == 1 (the reference's defaults) as compile-time constants.
-template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT>
+// MODE: SVB_FILT_FAST       NeighborhoodUpdate, the cold path decides in FAST fp64 arithmetic (the production sweep);
+//       SVB_FILT_STRICT     the same proposals, the cold path decides in the reference's operation order: SiteUpdate
+//                           (interval_n = 0: no dn proposals, site.py:43-120) identical to the STRICT kernels;
+//       SVB_FILT_EXACT      ExactUpdate (exact.py:50-129): dphi = 0, dn = d z with z one of the 2 a.interval_n nonzero values
+//                           drawn from word B (villain_get_draw), STRICT cold path.
+#define SVB_FILT_FAST 0
+#define SVB_FILT_STRICT 1
+#define SVB_FILT_EXACT 2
+template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT, int MODE>
 __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                              const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -208,9 +235,10 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     __syncthreads();
     const bool obs_of_input = a.obs_in != nullptr;                // state columns describe the chain as it ARRIVES
     const bool want_obs = a.obs != nullptr && !obs_of_input;     // ... or as it leaves (one more fp64 pass)
+    static_assert(!(UNIT && MODE != SVB_FILT_FAST), "UNIT is the production sweep");
     const int interval_n = UNIT ? 1 : a.interval_n;
-    const uint32_t K = (uint32_t)(2 * interval_n + 1);
-    const int W = UNIT ? 1 : a.W, mWI = -W * interval_n;
+    const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
+    const int W = (UNIT || MODE == SVB_FILT_EXACT) ? 1 : a.W, mWI = -W * interval_n;
     const float cIn = fc.c * (float)interval_n;
     const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
     const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
@@ -365,11 +393,23 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     // proposals: four base-K digits each, then the leading 32 bits of the uniform
                     uint32_t fA = bits.y, fB = bits.w;
                     int digA[4], digB[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    if (MODE == SVB_FILT_EXACT) {
+                        // z = the idx-th of the 2 I nonzero values in [-I, I]; n += d z: forward links -z, backward links +z.
+                        // As "digits" (dn = digit - I): I - z forward, I + z backward.
                         const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
-                        fA = (uint32_t)pa; digA[i] = (int)(pa >> 32);
-                        fB = (uint32_t)pb; digB[i] = (int)(pb >> 32);
+                        fA = (uint32_t)pa; fB = (uint32_t)pb;
+                        const int ia = (int)(pa >> 32), ib = (int)(pb >> 32);
+                        const int za = (ia < interval_n) ? ia - interval_n : ia - interval_n + 1;
+                        const int zb = (ib < interval_n) ? ib - interval_n : ib - interval_n + 1;
+                        digA[0] = digA[2] = interval_n - za; digA[1] = digA[3] = interval_n + za;
+                        digB[0] = digB[2] = interval_n - zb; digB[1] = digB[3] = interval_n + zb;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
+                            fA = (uint32_t)pa; digA[i] = (int)(pa >> 32);
+                            fB = (uint32_t)pb; digB[i] = (int)(pb >> 32);
+                        }
                     }
                     // dphi from 23 centred bits
                     float2 U = make_float2(__uint_as_float(0x3F800000u | (bits.x >> 9)), __uint_as_float(0x3F800000u | (bits.z >> 9)));
@@ -419,13 +459,20 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             ep.i_f0 = ((x0 + 1) & (N - 1)) * N + x1;
                             ep.i_f1 = x0 * N + ((x1 + 1) & (N - 1));
                             ep.half_kappa = half_kappa;
-                            ep.c = SVB_TWO_PI * (double)W;
-                            ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                            ep.dphi = (MODE == SVB_FILT_EXACT) ? 0.0 : villain_dphi_from_word(wA, a.interval_phi);
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
                             ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
-                            ok = villain_exact_decision(ep);
+                            if (MODE == SVB_FILT_FAST) {
+                                ep.c = SVB_TWO_PI * (double)W;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                                ok = villain_exact_decision(ep);
+                            } else {
+                                ep.c = SVB_TWO_PI;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) ep.g[i] = W * (dig[i] - interval_n);
+                                ok = villain_exact_decision_strict(ep);
+                            }
                         }
                         n_acc += ok ? 1 : 0;
                         if (ok) {                                               // (:121-129)
@@ -507,14 +554,20 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 template <int NT, int MINB, int STAGES>
 static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool overlap = a.epochs != nullptr;
-    const bool unit = a.W == 1 && a.interval_n == 1;
-    auto kern = overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false>)
-                        : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true> : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false>);
+    const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? SVB_FILT_STRICT : SVB_FILT_FAST);
+    const bool unit = mode == SVB_FILT_FAST && a.W == 1 && a.interval_n == 1;
+    if (mode != SVB_FILT_FAST && overlap) return fail(SVB_E_UNSUPPORTED, "overlapped launches serve the NeighborhoodUpdate sweep only");
+    auto kern = mode == SVB_FILT_EXACT    ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_EXACT>
+                : mode == SVB_FILT_STRICT ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_STRICT>
+                : overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true, SVB_FILT_FAST>
+                                  : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false, SVB_FILT_FAST>)
+                          : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true, SVB_FILT_FAST>
+                                  : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_FAST>);
     const size_t V = (size_t)NT * NT;
     const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32;
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
-    static int per_sm_cache[4][64];
-    const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0);
+    static int per_sm_cache[6][64];
+    const int variant = mode != SVB_FILT_FAST ? 3 + mode : (overlap ? 1 : 0) + (unit ? 2 : 0);
     int per_sm = (info.device < 64) ? per_sm_cache[variant][info.device] : 0;
     if (per_sm == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -525,7 +578,7 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     }
     long long grid = (long long)per_sm * info.sm_count;
     if (grid > a.chains) grid = a.chains;
-    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    const FilterConsts fc = make_filter_consts(a.interval_phi, mode == SVB_FILT_EXACT ? 1 : a.W, a.interval_n);
     if (overlap) {
         // programmatic dependent launch: this grid may start once every CTA of the previous kernel in the stream has
         // executed griddepcontrol.launch_dependents (or exited); the per-chain epochs order the data

@@ -175,12 +175,12 @@ def test_batched_ensemble_autocorrelation_time_matches_per_chain_reference_defin
     assert total >= expect and total == max(int(v.max()) for v in every.values())
 
 
-@pytest.mark.parametrize('N', [16, 32, 64])
+@pytest.mark.parametrize('N', [16, 32, 64, 128, 256, 1024])
 def test_fft_correlators_match_the_reference_formula(N):
-    """The shared-memory FFT route (N = 16, 32, 64) for all three correlators against the restated Lattice.correlation
-    (compact.py:465-536), 1e-12, on a batch."""
+    """The shared-memory FFT route (N = 16, 32, 64) and the three-launch route (power-of-two N from 128 to 4096: configs 4
+    and 5) for all three correlators against the restated Lattice.correlation (compact.py:465-536), 1e-12, on a batch."""
     rng = np.random.default_rng(N)
-    chains = 5
+    chains = 5 if N <= 256 else 2
     phi = rng.uniform(-7, 7, (chains, 1, N, N))
     n = rng.integers(-3, 4, (chains, 2, N, N))
     v = rng.integers(-5, 6, (chains, 1, N, N))
@@ -194,3 +194,27 @@ def test_fft_correlators_match_the_reference_formula(N):
         np.testing.assert_allclose(Cw[c], lat.correlation(dn, dn), rtol=0, atol=1e-12 * max(1.0, np.abs(dn).max() ** 2))
         e = np.exp(2j * np.pi * v[c, 0] / 3)
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
+
+
+def test_fft_correlator_of_a_config5_lattice_properties():
+    """L = 4096 (config 5), too large to compare element by element in a test: size-independent properties of
+    Lattice.correlation instead -- C[0] = mean |s|^2 = 1 for a spin field, C[-r] = conj(C[r]), sum_r C[r] = N^2 |mean s|^2 ...
+    and a plane wave s = exp(i k.x), whose correlator is exp(-i k.r) exactly."""
+    N = 4096
+    rng = np.random.default_rng(5)
+    phi = rng.uniform(-np.pi, np.pi, (1, 1, N, N))
+    C = ops.villain_spin_spin(torch.from_numpy(phi).cuda())[0]
+    s = torch.from_numpy(np.exp(1j * phi[0, 0])).cuda()
+    assert abs(complex(C[0, 0]) - 1.0) < 1e-12
+    flipped = torch.roll(torch.flip(C, (0, 1)), (1, 1), (0, 1))
+    assert float((flipped - C.conj()).abs().max()) < 1e-12
+    assert abs(complex(C.sum()) - N * N * abs(complex(s.mean())) ** 2) < 1e-8
+    # one displacement checked against its definition  C[r] = mean_x conj(s[x]) s[x - r]
+    r0, r1 = 1234, 77
+    direct = (s.conj() * torch.roll(s, (r0, r1), (0, 1))).mean()
+    assert abs(complex(C[r0, r1]) - complex(direct)) < 1e-12
+    k0, k1 = 5, 1000
+    x = np.arange(N)
+    wave = 2 * np.pi * (k0 * x[:, None] + k1 * x[None, :]) / N
+    Cw = ops.villain_spin_spin(torch.from_numpy(wave[None, None]).cuda())[0].cpu().numpy()
+    np.testing.assert_allclose(Cw, np.exp(-1j * wave), rtol=0, atol=1e-9)

@@ -100,3 +100,25 @@ if 'forms' in which:
     N, CH = 32, 8192
     phi = torch.rand((CH, 1, N, N), dtype=torch.float64, device='cuda')
     report('spin_spin correlator L=32 x 8192 (shared-memory FFT)', CH * N * N, 24, timeit(lambda: ops.villain_spin_spin(phi), n=3, reps=2))
+    for N, CH in ((128, 512), (4096, 1)):
+        phi = torch.rand((CH, 1, N, N), dtype=torch.float64, device='cuda')
+        out = torch.empty((CH, N, N, 2), dtype=torch.float64, device='cuda')
+        # three launches: field in (8 B), rows out (16), columns in + out (32), rows in + out (32) per site
+        report(f'spin_spin correlator L={N} x {CH} (three-launch FFT)', CH * N * N, 88, timeit(lambda: ops.villain_spin_spin(phi, out=out), n=3, reps=2))
+if 'dec' in which:
+    N, CH = 32, 4096                                     # config-2 shape: the decoupled Villain updates and the Hammer sequence
+    S = svb.Villain(svb.Lattice2D(N), 0.5)
+    sets = [svb.BatchedEnsemble(S, CH)._start('hot', 1 + r) for r in range(4)]
+    obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for kind, sites in (('site', N * N), ('link', 2 * N * N), ('exact', N * N)):
+        k = [0]
+        def f():
+            phi, n = sets[k[0] % 4]; k[0] += 1
+            ops.villain_decoupled(kind, phi, n, 0.5, seed=1, sweep0=k[0], obs=obs)
+        report(f'villain {kind} update L=32 x 4096 chains', CH * sites, 32 * N * N / sites, timeit(f))
+    cnt = torch.zeros((CH, 2), dtype=torch.float64, device='cuda')
+    k = [0]
+    def f():
+        phi, n = sets[k[0] % 4]; k[0] += 1
+        ops.villain_cohomology(phi, n, 0.5, seed=1, sweep=k[0], counters=cnt)
+    report('villain cohomology update L=32 x 4096 chains (2 proposals per chain; state read + n written)', CH * N * N, 32, timeit(f))
