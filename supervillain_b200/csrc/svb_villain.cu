@@ -1587,6 +1587,7 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 
 #include "svb_villain_filtered.cuh"
 #include "svb_villain_cluster.cuh"
+#include "svb_villain_link.cuh"
 #ifndef SVB_CLUSTER_TPB
 #define SVB_CLUSTER_TPB 512
 #endif
@@ -1836,6 +1837,22 @@ extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t ch
     if (kind == SVB_VU_LINK) {
         if (accept_mask) return fail(SVB_E_UNSUPPORTED, "svb_villain_decoupled: no accept_mask for LINK");
         const long long V = (long long)N * N;
+        if (rng_mode == SVB_RNG_PHILOX && !dS_out && path != SVB_PATH_GLOBAL && (N == 16 || N == 32 || N == 64) &&
+            ((uintptr_t)phi % 16 == 0) && ((uintptr_t)n % 16 == 0)) {
+            // the chain staged in shared memory, all sweeps and the observables in one launch (svb_villain_link.cuh)
+            LinkArgs la;
+            la.phi = reinterpret_cast<const double*>(phi); la.n = n; la.chains = chains; la.N = N; la.kappa = kappa; la.kappa_chain = kappa_chain;
+            la.W = W; la.interval = interval; la.seed = seed; la.chain0 = chain0; la.obs = obs; la.sweep = sweep0;
+            la.inj_u = nullptr; la.inj_c = nullptr; la.dS_out = nullptr;
+            DeviceInfo info;
+            const int rc = get_device_info(info);
+            if (rc) return rc;
+            switch (N) {
+                case 16: return launch_villain_link_smem<16, 16>(la, n_sweeps, st, info);
+                case 32: return launch_villain_link_smem<32, 8>(la, n_sweeps, st, info);
+                default: return launch_villain_link_smem<64, 3>(la, n_sweeps, st, info);
+            }
+        }
         const long long blocks = chains * ((2 * V + 255) / 256);
         if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_decoupled: too many blocks");
         if (obs) {

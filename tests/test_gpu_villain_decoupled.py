@@ -79,12 +79,13 @@ def test_philox_mode_matches_oracle_replay(kind, N, W, kappa, interval):
         assert float(obs[c, VOBS_ACTION]) == pytest.approx(float(V.action(p, q, kappa)), rel=1e-12)
 
 
-@pytest.mark.parametrize('kind', ['site', 'exact'])
+@pytest.mark.parametrize('kind', KINDS)
 @pytest.mark.parametrize('N,chains,kappa,W,interval', [(32, 1500, 0.5, 1, 1), (16, 2000, 2.5, 2, 3), (64, 200, 0.05, 1, 2)])
 def test_filtered_kernels_decide_like_the_strict_kernels(kind, N, chains, kappa, W, interval):
-    """SiteUpdate and ExactUpdate with Philox draws run on the fp32-filtered kernel whose cold path decides in STRICT
-    arithmetic; a debug output (accept_mask) sends the same call to the STRICT fp64 kernels.  Millions of proposals,
-    hot and cold regimes: identical fields and accepted counts, i.e. the filter never answers differently."""
+    """SiteUpdate, ExactUpdate and LinkUpdate with Philox draws run on fp32-filtered shared-memory kernels whose cold path
+    decides in STRICT arithmetic; a debug output (accept_mask / dS_out) sends the same call to the STRICT fp64 kernels.
+    Millions of proposals, hot and cold regimes: identical fields and accepted counts, i.e. the filter never answers
+    differently."""
     S = svb.Villain(svb.Lattice2D(N), kappa, W=W)
     phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 11)
     n *= W
@@ -92,13 +93,14 @@ def test_filtered_kernels_decide_like_the_strict_kernels(kind, N, chains, kappa,
     obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
     robs = torch.zeros_like(obs)
     mask = torch.zeros((chains, N, N), dtype=torch.uint8, device='cuda')
+    debug = dict(dS_out=torch.zeros((chains, 2, N, N), dtype=torch.float64, device='cuda')) if kind == 'link' else dict(accept_mask=mask)
     for s in range(4):
         ops.villain_decoupled(kind, phi, n, kappa, W=W, interval_phi=2.0, interval=interval, seed=5, sweep0=s, obs=obs)
-        ops.villain_decoupled(kind, rphi, rn, kappa, W=W, interval_phi=2.0, interval=interval, seed=5, sweep0=s, obs=robs,
-                              accept_mask=mask)
+        ops.villain_decoupled(kind, rphi, rn, kappa, W=W, interval_phi=2.0, interval=interval, seed=5, sweep0=s, obs=robs, **debug)
         assert torch.equal(phi, rphi) and torch.equal(n, rn)
         assert torch.equal(obs[:, VOBS_ACCEPTED], robs[:, VOBS_ACCEPTED])
-        assert float(obs[:, VOBS_ACCEPTED].sum()) == float(mask.sum())
+        if kind != 'link':
+            assert float(obs[:, VOBS_ACCEPTED].sum()) == float(mask.sum())
         torch.testing.assert_close(obs[:, VOBS_ACCEPTANCE], robs[:, VOBS_ACCEPTANCE], rtol=1e-5, atol=0)
         torch.testing.assert_close(obs[:, :4], robs[:, :4], rtol=1e-12, atol=0)
     assert float(obs[:, VOBS_ACCEPTED].sum()) > 0

@@ -115,10 +115,10 @@ if 'dec' in which:
         def f():
             phi, n = sets[k[0] % 4]; k[0] += 1
             ops.villain_decoupled(kind, phi, n, 0.5, seed=1, sweep0=k[0], obs=obs)
-        report(f'villain {kind} update L=32 x 4096 chains', CH * sites, 32 * N * N / sites, timeit(f))
+        report(f'villain {kind} update L=32 x 4096 chains', CH * sites, (24 if kind == 'link' else 32) * N * N / sites, timeit(f))
     cnt = torch.zeros((CH, 2), dtype=torch.float64, device='cuda')
     k = [0]
     def f():
         phi, n = sets[k[0] % 4]; k[0] += 1
         ops.villain_cohomology(phi, n, 0.5, seed=1, sweep=k[0], counters=cnt)
-    report('villain cohomology update L=32 x 4096 chains (2 proposals per chain; state read + n written)', CH * N * N, 32, timeit(f))
+    report('villain cohomology update L=32 x 4096 chains (2 slice proposals per chain; reads 2 N links + sites, writes N links on accept)', CH * 2 * N, 32, timeit(f))
