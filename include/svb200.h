@@ -321,6 +321,20 @@ int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int 
 int svb_autocorrelation(const double* data, int64_t series, int T, const double* mean, double* C, int32_t* tau, void* stream);
 
 /*
+ * Blocking and Bootstrap of scalar columns (analysis/blocking.py:54-66 `_block`, analysis/bootstrap.py:57-67 `_resample`),
+ * one column of T samples per series (e.g. one observable of every chain): data (series, T) f64, weight optional (T,) f64
+ * (NULL: unit weights, what every generator on this path produces).
+ *   svb_block_mean      out (series, (T - drop) / width):  mean over `width` consecutive samples of weight * data, the first
+ *                       `drop` samples left out; (T - drop) must be a multiple of width.
+ *   svb_bootstrap_mean  out (series, draws):  mean_c(weight[idx[c,d]] data[s, idx[c,d]]) / mean_c(weight[idx[c,d]]) with
+ *                       idx (T, draws) int64 -- the resampling indices, drawn by the caller (the reference draws them with
+ *                       numpy: np.random.randint(0, T, (T, draws)), bootstrap.py:52).
+ */
+int svb_block_mean(const double* data, const double* weight, int64_t series, int64_t T, int width, int64_t drop, double* out, void* stream);
+int svb_bootstrap_mean(const double* data, const double* weight, int64_t series, int64_t T, const int64_t* idx, int draws, double* out,
+                       void* stream);
+
+/*
  * Test hook: the decision u < A of the lazily refined Metropolis uniform (leading 32 bits f known; trailing bits from word
  * `word` of the Philox block (c0, chain, sweep) in refinement stream `stream_id`: 4 Villain, 5 worldline, 7 LinkUpdate) and
  * the refined uniform itself, for n caller-chosen inputs.  The sweeps reach the refinement with probability 2^-32 per

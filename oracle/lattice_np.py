@@ -200,3 +200,22 @@ def autocorrelation(data, mean=None, cutoff=1e-16):
     clamped = np.clip(C, 0, None)                                           # :56
     minIdx = np.argmin(clamped)                                             # :57
     return C, int(np.ceil(C[:minIdx].sum()))                                # :58
+
+
+def block_mean(data, width, weight=None):
+    """supervillain.analysis.Blocking._block (supervillain/analysis/blocking.py:54-66; drop = len % width, :35), restated
+    for a scalar column (T,) or a batch of columns (series, T) -> (..., blocks)."""
+    data = np.asarray(data, dtype=np.float64)
+    T = data.shape[-1]
+    drop = T % width
+    w = np.ones(T) if weight is None else np.asarray(weight, dtype=np.float64)
+    return (data[..., drop:] * w[drop:]).reshape(*data.shape[:-1], -1, width).mean(axis=-1)
+
+
+def bootstrap_mean(data, indices, weight=None):
+    """supervillain.analysis.Bootstrap._resample (supervillain/analysis/bootstrap.py:57-67), restated for a scalar column
+    (T,) or a batch of columns (series, T); indices (T, draws) -> (..., draws)."""
+    data = np.asarray(data, dtype=np.float64)
+    T = data.shape[-1]
+    w = (np.ones(T) if weight is None else np.asarray(weight, dtype=np.float64))[indices]          # (T, draws)
+    return (w * data[..., indices]).mean(axis=-2) / w.mean(axis=0)

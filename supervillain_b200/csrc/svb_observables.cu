@@ -498,6 +498,53 @@ extern "C" int svb_autocorrelation(const double* data, int64_t series, int T, co
 
 
 // ------------------------------------------------------------------------------------------
+// Blocking and Bootstrap of scalar columns (supervillain/analysis/blocking.py:54-66, bootstrap.py:57-67), one column per
+// series (e.g. one observable of every chain), T samples each, data (series, T):
+//   block_mean      out[s, b] = mean_{i < width} w[drop + b width + i] data[s, drop + b width + i]
+//   bootstrap_mean  out[s, d] = mean_c (w[idx[c, d]] data[s, idx[c, d]]) / mean_c w[idx[c, d]],  idx (T, draws) as numpy drew it
+// (w == nullptr: unit weights).  Sums run in sample order, which is numpy's order for the bootstrap (a reduction over the
+// leading axis); numpy blocks along the contiguous axis with its pairwise scheme, so block means agree to ~1e-15 relative.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_mean_kernel(const double* __restrict__ data, const double* __restrict__ w, long long series,
+                                                         long long T, int width, long long drop, long long blocks,
+                                                         double* __restrict__ out) {
+    const long long total = series * blocks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / blocks, b = i - s * blocks;
+        const double* p = data + s * T + drop + b * width;
+        const double* q = w ? w + drop + b * width : nullptr;
+        double acc = 0.0;
+        for (int k = 0; k < width; ++k) acc += q ? __dmul_rn(p[k], q[k]) : p[k];
+        out[i] = acc / (double)width;
+    }
+}
+
+__global__ void __launch_bounds__(256) bootstrap_mean_kernel(const double* __restrict__ data, const double* __restrict__ w,
+                                                             long long series, long long T, const long long* __restrict__ idx,
+                                                             int draws, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* col = reinterpret_cast<double*>(smem_raw);           // the series' column, staged when it fits
+    const bool staged = (size_t)T * sizeof(double) <= 160 * 1024;
+    for (long long s = blockIdx.x; s < series; s += gridDim.x) {
+        const double* g = data + s * T;
+        __syncthreads();
+        if (staged)
+            for (long long c = threadIdx.x; c < T; c += blockDim.x) col[c] = w ? __dmul_rn(w[c], g[c]) : g[c];
+        __syncthreads();
+        for (int d = threadIdx.x; d < draws; d += blockDim.x) {
+            double acc = 0.0, wsum = 0.0;
+            for (long long c = 0; c < T; ++c) {
+                const long long j = idx[c * draws + d];
+                acc += staged ? col[j] : (w ? __dmul_rn(w[j], g[j]) : g[j]);
+                if (w) wsum += w[j];
+            }
+            const double mean = acc / (double)T;
+            out[s * draws + d] = w ? mean / (wsum / (double)T) : mean;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Test hook for the lazily refined uniform (svb_common.cuh): the refinement branch of decide_lazy is taken with probability
 // 2^-32 per proposal, so no sweep test ever reaches it.  This evaluates decide_lazy(A, (f, c0, word)) and the refined
 // uniform itself for caller-chosen inputs, to be compared with the oracle's statement of the same rule.
@@ -525,6 +572,35 @@ extern "C" int svb_debug_decide_lazy(const double* A, const uint32_t* f, const u
     if (n <= 0) return SVB_OK;
     debug_decide_lazy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         A, f, c0, word, n, stream_id, seed, chain, sweep, decision, u_out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_block_mean(const double* data, const double* weight, int64_t series, int64_t T, int width, int64_t drop, double* out,
+                              void* stream) {
+    if (!data || !out) return fail(SVB_E_NULL, "svb_block_mean: data and out are required");
+    if (series < 0 || T < 0 || width < 1 || drop < 0 || drop > T || (T - drop) % width != 0)
+        return fail(SVB_E_SHAPE, "svb_block_mean: (T - drop) must be a multiple of width (T=%lld drop=%lld width=%d)", (long long)T,
+                    (long long)drop, width);
+    const long long blocks = (T - drop) / width;
+    if (series == 0 || blocks == 0) return SVB_OK;
+    const long long total = series * blocks;
+    const long long grid = (total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16;
+    block_mean_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(data, weight, series, T, width, drop, blocks, out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_bootstrap_mean(const double* data, const double* weight, int64_t series, int64_t T, const int64_t* idx, int draws,
+                                  double* out, void* stream) {
+    if (!data || !idx || !out) return fail(SVB_E_NULL, "svb_bootstrap_mean: data, idx and out are required");
+    if (series < 0 || T < 1 || draws < 1) return fail(SVB_E_SHAPE, "svb_bootstrap_mean: shape");
+    if (series == 0) return SVB_OK;
+    const size_t smem = ((size_t)T * sizeof(double) <= 160 * 1024) ? (size_t)T * sizeof(double) : 0;
+    SVB_CUDA_TRY(cudaFuncSetAttribute(bootstrap_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    const long long grid = series < 148 * 8 ? series : 148 * 8;
+    bootstrap_mean_kernel<<<(unsigned)grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        data, weight, series, T, reinterpret_cast<const long long*>(idx), draws, out);
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }

@@ -215,6 +215,10 @@ class BatchedEnsemble:
             account(flat, self.chains, steps * sweeps_per_step)
         return self
 
+    def __len__(self):
+        """The number of recorded samples per chain (what `len(Ensemble)` is for the reference's single chain)."""
+        return int(self.__dict__.get('steps', 0))
+
     def __getattr__(self, name):
         obs = self.__dict__.get('observables')
         if obs is not None and name in obs:

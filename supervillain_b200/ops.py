@@ -469,3 +469,35 @@ def autocorrelation(data, mean=None, *, want_C=True):
     _lib.check(lib.svb_autocorrelation(p_data, series, T, _opt(mean, 'mean', (torch.float64,), (series,)),
                                        None if C is None else C.data_ptr(), tau.data_ptr(), _stream()))
     return C, tau
+
+
+def block_mean(data, width, drop=0, weight=None):
+    """Blocking._block (analysis/blocking.py:54-66) for every row of `data` (series, T) float64 on the device
+    (svb_block_mean) -> (series, (T - drop) // width)."""
+    lib = _lib.load()
+    if data.dim() != 2:
+        raise ValueError(f'data must have shape (series, T); got {tuple(data.shape)}')
+    series, T = int(data.shape[0]), int(data.shape[1])
+    width, drop = int(width), int(drop)
+    if width < 1 or drop < 0 or drop > T or (T - drop) % width:
+        raise ValueError(f'(T - drop) must be a multiple of width; got T={T} drop={drop} width={width}')
+    out = torch.empty((series, (T - drop) // width), dtype=torch.float64, device=data.device)
+    _lib.check(lib.svb_block_mean(_dev(data, 'data', (torch.float64,)), _opt(weight, 'weight', (torch.float64,), (T,)), series, T,
+                                  width, drop, out.data_ptr(), _stream()))
+    return out
+
+
+def bootstrap_mean(data, indices, weight=None):
+    """Bootstrap._resample (analysis/bootstrap.py:57-67) for every row of `data` (series, T) float64 on the device
+    (svb_bootstrap_mean); `indices` (T, draws) int64 as numpy drew them -> (series, draws)."""
+    lib = _lib.load()
+    if data.dim() != 2:
+        raise ValueError(f'data must have shape (series, T); got {tuple(data.shape)}')
+    series, T = int(data.shape[0]), int(data.shape[1])
+    if indices.dim() != 2 or int(indices.shape[0]) != T:
+        raise ValueError(f'indices must have shape (T, draws) = ({T}, draws); got {tuple(indices.shape)}')
+    draws = int(indices.shape[1])
+    out = torch.empty((series, draws), dtype=torch.float64, device=data.device)
+    _lib.check(lib.svb_bootstrap_mean(_dev(data, 'data', (torch.float64,)), _opt(weight, 'weight', (torch.float64,), (T,)), series, T,
+                                      _dev(indices, 'indices', (torch.int64,)), draws, out.data_ptr(), _stream()))
+    return out

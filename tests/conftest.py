@@ -80,3 +80,8 @@ def golden_villain_cohomology():
 @pytest.fixture(scope='session')
 def golden_autocorrelation():
     return load_golden('autocorrelation')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_resampling():
+    return load_golden('resampling')[0]

@@ -349,9 +349,35 @@ def autocorrelation():
     print('tau per case:', [int(c['tau']) for c in cases], [int(c['tau_mean3']) for c in cases])
 
 
+def resampling():
+    """supervillain.analysis.Blocking._block and Bootstrap._resample (analysis/blocking.py:54-66, bootstrap.py:57-67) on
+    scalar columns, driven through the reference classes with a minimal ensemble stand-in (they only ask it for its
+    length, weight and the column); np.random.seed fixes the reference's own np.random.randint draw of the indices."""
+    rng = np.random.default_rng(8)
+    cases = []
+    for T, width, draws, weighted in [(100, 7, 16, False), (1000, 50, 100, False), (4096, 64, 33, False), (257, 16, 20, True)]:
+        class Stub:
+            Action = None
+            index_stride = 1
+            weight = rng.uniform(0.5, 1.5, T) if weighted else np.ones(T)
+            def __len__(self):
+                return T
+        E = Stub()
+        E.column = np.cumsum(rng.normal(size=T)) * 0.1 + rng.normal(size=T)
+        B = sv.analysis.Blocking(E, width=width)
+        blocked = B._block(E.column)
+        np.random.seed(1000 + T)
+        R = sv.analysis.Bootstrap(E, draws=draws)
+        resampled = R._resample(E.column)
+        cases.append(dict(data=E.column, weight=np.asarray(E.weight), width=width, drop=B.drop, blocked=blocked,
+                          indices=R.indices, resampled=resampled))
+    _pack(cases, 'resampling')
+    print('resampling cases:', [(len(c['data']), c['width'], c['drop'], c['blocked'].shape, c['resampled'].shape) for c in cases])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
                              'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping',
-                             'villain_decoupled', 'villain_cohomology', 'autocorrelation']
+                             'villain_decoupled', 'villain_cohomology', 'autocorrelation', 'resampling']
     for name in which:
         globals()[name]()

@@ -218,3 +218,41 @@ def test_fft_correlator_of_a_config5_lattice_properties():
     wave = 2 * np.pi * (k0 * x[:, None] + k1 * x[None, :]) / N
     Cw = ops.villain_spin_spin(torch.from_numpy(wave[None, None]).cuda())[0].cpu().numpy()
     np.testing.assert_allclose(Cw, np.exp(-1j * wave), rtol=0, atol=1e-9)
+
+
+def test_blocking_and_bootstrap_match_reference(golden_resampling):
+    """svb_block_mean / svb_bootstrap_mean against Blocking._block and Bootstrap._resample of the unmodified reference on
+    its own resampling indices (1e-13: the bootstrap sums in numpy's order, block means differ from numpy's pairwise sums
+    in the last bits), with and without weights; then the batched classes on an ensemble of chains against the oracle,
+    including Bootstrap(Blocking(E))."""
+    for c in golden_resampling:
+        data = torch.from_numpy(c['data'][None]).cuda()
+        unit = bool((c['weight'] == 1).all())
+        w = None if unit else torch.from_numpy(c['weight']).cuda()
+        blocked = ops.block_mean(data, int(c['width']), int(c['drop']), weight=w)[0].cpu().numpy()
+        np.testing.assert_allclose(blocked, c['blocked'], rtol=1e-13, atol=1e-15)
+        res = ops.bootstrap_mean(data, torch.from_numpy(c['indices']).cuda(), weight=w)[0].cpu().numpy()
+        np.testing.assert_allclose(res, c['resampled'], rtol=1e-13, atol=1e-15)
+    S = svb.Villain(svb.Lattice2D(8), 0.4)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=3)
+    E = svb.BatchedEnsemble(S, 40).generate(203, G, 'hot', start_seed=1)
+    assert len(E) == 203
+    B = svb.analysis.Blocking(E, width=10)
+    assert (B.drop, B.blocks, len(B)) == (3, 20, 20)
+    np.testing.assert_allclose(B.ActionDensity, lat.block_mean(E.ActionDensity, 10), rtol=1e-13)
+    np.testing.assert_allclose(B.index, np.asarray(E.index)[3:].reshape(-1, 10).mean(axis=1))
+    np.random.seed(4)
+    R = svb.analysis.Bootstrap(E, draws=25)
+    np.random.seed(4)
+    expect_idx = np.random.randint(0, 203, (203, 25))
+    assert (R.indices == expect_idx).all()                    # drawn exactly as the reference draws them
+    np.testing.assert_allclose(R.WindingSquared, lat.bootstrap_mean(E.WindingSquared, expect_idx), rtol=1e-13)
+    mean, err = R.estimate('ActionDensity')
+    assert mean.shape == err.shape == (40,) and (err > 0).all()
+    assert np.abs(mean - E.ActionDensity.mean(axis=1)).max() < 5 * err.max()
+    RB = svb.analysis.Bootstrap(B, draws=12, indices=np.random.randint(0, 20, (20, 12)))
+    np.testing.assert_allclose(RB.ActionDensity, lat.bootstrap_mean(lat.block_mean(E.ActionDensity, 10), RB.indices), rtol=1e-13)
+    with pytest.raises(AttributeError):
+        R.NoSuchObservable
+    auto = svb.analysis.Blocking(E)                          # width='auto': the ensemble's autocorrelation time
+    assert auto.width == E.autocorrelation_time()

@@ -166,3 +166,16 @@ def test_autocorrelation_restatement_matches_reference(golden_autocorrelation):
         assert (C == c['C_mean3']).all() and tau == int(c['tau_mean3'])
     with pytest.raises(ValueError):
         lat.autocorrelation(np.ones(16))
+
+
+def test_blocking_and_bootstrap_restatements_match_reference(golden_resampling):
+    """oracle.lattice_np.block_mean / bootstrap_mean against Blocking._block and Bootstrap._resample of the unmodified
+    reference (bit for bit: the same numpy expressions), with unit and non-unit weights."""
+    for c in golden_resampling:
+        w = c['weight']
+        assert c['drop'] == len(c['data']) % int(c['width'])
+        assert (lat.block_mean(c['data'], int(c['width']), w) == c['blocked']).all()
+        assert (lat.bootstrap_mean(c['data'], c['indices'], w) == c['resampled']).all()
+        batch = np.stack([c['data'], 2 * c['data'] + 1])
+        np.testing.assert_allclose(lat.block_mean(batch, int(c['width']), w)[1], 2 * c['blocked'] + w[int(c['drop']):].reshape(-1, int(c['width'])).mean(axis=1), rtol=1e-13)
+        np.testing.assert_allclose(lat.bootstrap_mean(batch, c['indices'], w)[1], 2 * c['resampled'] + 1, rtol=1e-13)
