@@ -321,6 +321,17 @@ int svb_correlation(int kind, const void* field, int dtype, int64_t chains, int 
 int svb_autocorrelation(const double* data, int64_t series, int T, const double* mean, double* C, int32_t* tau, void* stream);
 
 /*
+ * The taxicab reweighting observables (D = 2): Spin_Spin.Worldline (observable/spin.py:50-224) from links = m - delta(v)/W
+ * and Vortex_Vortex.Villain (observable/vortex.py:63-189) from links = d(phi) - 2 pi n.  links (chains, 2, N, N) f64 ->
+ * out (chains, N, N) f64 indexed by the displacement in FFT coordinates, out[., 0, 0] = 1, averaged over all starting sites.
+ * N (N + 1) 16 bytes of shared memory: N <= 118.
+ */
+#define SVB_TAXI_SPIN   0
+#define SVB_TAXI_VORTEX 1
+int svb_taxicab_correlator(int kind, const double* links, int64_t chains, int N, double kappa, const double* kappa_chain, double* out,
+                           void* stream);
+
+/*
  * Blocking and Bootstrap of scalar columns (analysis/blocking.py:54-66 `_block`, analysis/bootstrap.py:57-67 `_resample`),
  * one column of T samples per series (e.g. one observable of every chain): data (series, T) f64, weight optional (T,) f64
  * (NULL: unit weights, what every generator on this path produces).

@@ -219,3 +219,43 @@ def bootstrap_mean(data, indices, weight=None):
     T = data.shape[-1]
     w = (np.ones(T) if weight is None else np.asarray(weight, dtype=np.float64))[indices]          # (T, draws)
     return (w * data[..., indices]).mean(axis=-2) / w.mean(axis=0)
+
+
+def fft_coordinate(a, N):
+    """The displacement an index stands for (supervillain/lattice/__init__.py:4-9): 0 .. N//2, then -(N-1)//2 .. -1."""
+    return a if a <= N // 2 else a - N
+
+
+def _taxicab(links, alpha, beta, comp_t, comp_s, offset, sign_s):
+    """mean_x exp(alpha * S(x; D) + beta * |D|) for every displacement D = (Dt, Dx), where S sums `links` along the taxicab
+    path from x: first |Dt| steps in time on component comp_t at column x1 -- rows x0 + offset + i (i = 0 .. Dt-1, sign +)
+    for Dt > 0, rows x0 + offset - i (i = 1 .. |Dt|, sign -) for Dt < 0 -- then |Dx| steps in space on component comp_s at
+    row x0 + Dt -- columns x1 + offset + j (sign sign_s) for Dx > 0, x1 + offset - j (sign -sign_s) for Dx < 0."""
+    links = np.asarray(links, dtype=np.float64)
+    N = links.shape[-1]
+    out = np.zeros((N, N))
+    x0, x1 = np.meshgrid(np.arange(N), np.arange(N), indexing='ij')
+    for a in range(N):
+        for b in range(N):
+            Dt, Dx = fft_coordinate(a, N), fft_coordinate(b, N)
+            S = np.zeros((N, N))
+            for i in (range(Dt) if Dt > 0 else range(-1, Dt - 1, -1)):
+                S += (1 if Dt > 0 else -1) * links[comp_t, (x0 + offset + i) % N, x1]
+            for j in (range(Dx) if Dx > 0 else range(-1, Dx - 1, -1)):
+                S += (sign_s if Dx > 0 else -sign_s) * links[comp_s, (x0 + Dt) % N, (x1 + offset + j) % N]
+            out[a, b] = np.exp(alpha * S + beta * (abs(Dt) + abs(Dx))).mean()
+    return out
+
+
+def spin_spin_worldline(links, kappa):
+    """Spin_Spin.Worldline (supervillain/observable/spin.py:50-224): links = m - delta(v)/W; the taxicab path from x goes
+    Dt in time along (0, .) links then Dx in space along (1, .) links, P = +1 along / -1 against a link, and the
+    reweighting factor is exp(-(2 P.links + |P|) / (2 kappa)), averaged over x."""
+    return _taxicab(links, -1.0 / kappa, -0.5 / kappa, 0, 1, 0, +1)
+
+
+def vortex_vortex_villain(links, kappa):
+    """Vortex_Vortex.Villain (supervillain/observable/vortex.py:63-189): links = d(phi) - 2 pi n; the dual taxicab path
+    changes n by +-1 on the (1, .) links of rows x0 + 1 .. x0 + Dt (column x1) and by -+1 on the (0, .) links of columns
+    x1 + 1 .. x1 + Dx (row x0 + Dt); dS = -2 pi kappa (change.links - pi |P|) and V = mean_x exp(-dS)."""
+    return _taxicab(links, 2 * np.pi * kappa, -2 * np.pi ** 2 * kappa, 1, 0, 1, -1)

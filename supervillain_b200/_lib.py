@@ -49,6 +49,7 @@ SIGNATURES = {
     'svb_villain_spin_spin': (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     'svb_correlation': (_i, [_i, _vp, _i, _i64, _i, _i, _vp, _vp]),
     'svb_autocorrelation': (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    'svb_taxicab_correlator': (_i, [_i, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     'svb_block_mean': (_i, [_vp, _vp, _i64, _i64, _i, _i64, _vp, _vp]),
     'svb_bootstrap_mean': (_i, [_vp, _vp, _i64, _i64, _vp, _i, _vp, _vp]),
     'svb_debug_decide_lazy': (_i, [_vp, _vp, _vp, _vp, _i64, ctypes.c_uint32, _u64, _u64, _u64, _vp, _vp, _vp]),

@@ -498,6 +498,82 @@ extern "C" int svb_autocorrelation(const double* data, int64_t series, int T, co
 
 
 // ------------------------------------------------------------------------------------------
+// The taxicab reweighting observables: Spin_Spin.Worldline (supervillain/observable/spin.py:50-224) and Vortex_Vortex.Villain
+// (supervillain/observable/vortex.py:63-189).  For every displacement D = (Dt, Dx) (FFT coordinates) and every starting site x
+// a fixed path P -- |Dt| steps in time, then |Dx| steps in space -- picks +-1 on |D| links, and
+//     out[D] = mean_x exp(alpha P(x; D).links + beta |D|)
+//   SPIN   links = m - delta(v)/W:   time part on (0, .) links, rows x0 .. x0 + Dt - 1; space part on (1, .) links of row
+//          x0 + Dt, columns x1 .. x1 + Dx - 1; + along, - against;  alpha = -1/kappa, beta = -1/(2 kappa)
+//   VORTEX links = d(phi) - 2 pi n:  time part on (1, .) links, rows x0 + 1 .. x0 + Dt; space part on (0, .) links of row
+//          x0 + Dt, columns x1 + 1 .. x1 + Dx with the opposite sign;  alpha = 2 pi kappa, beta = -2 pi^2 kappa
+// The reference gathers the |D| links of all N^2 translates for each of the N^2 displacements: O(N^5).  Here circular prefix
+// sums of the two components along their path directions live in shared memory and a path sum is two differences:
+// O(N^4) exponentials per chain, one thread per displacement, 256 displacements per CTA.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double circular_range(const double* __restrict__ P, int stride, int N, int start, int count) {
+    const int end = start + count;                                // P[k * stride] = sum of the first k elements
+    if (end <= N) return P[end * stride] - P[start * stride];
+    return (P[N * stride] - P[start * stride]) + P[(end - N) * stride];
+}
+
+__global__ void __launch_bounds__(256) taxicab_kernel(const double* __restrict__ links, long long chains, int N, int kind, double kappa,
+                                                      const double* __restrict__ kappa_chain, int tiles, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* PT = reinterpret_cast<double*>(smem_raw);            // [N + 1][N]: prefix over rows of the time component
+    double* PS = PT + (size_t)(N + 1) * N;                        // [N][N + 1]: prefix over columns of the space component
+    const int V = N * N;
+    const int comp_t = kind == SVB_TAXI_SPIN ? 0 : 1, comp_s = 1 - comp_t, offset = kind == SVB_TAXI_SPIN ? 0 : 1;
+    const double sign_s = kind == SVB_TAXI_SPIN ? 1.0 : -1.0;
+    const long long items = chains * tiles;
+    long long staged = -1;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / tiles;
+        const int tile = (int)(item - chain * tiles);
+        const double k = kappa_chain ? kappa_chain[chain] : kappa;
+        const double alpha = kind == SVB_TAXI_SPIN ? -1.0 / k : SVB_TWO_PI * k;
+        const double beta = kind == SVB_TAXI_SPIN ? -0.5 / k : -0.5 * SVB_TWO_PI * SVB_TWO_PI * k;
+        if (chain != staged) {
+            __syncthreads();
+            const double* g = links + chain * 2 * V;
+            for (int x = threadIdx.x; x < N; x += blockDim.x) {
+                double acc = 0.0;
+                PT[x] = 0.0;
+                for (int t = 0; t < N; ++t) { acc += g[comp_t * V + t * N + x]; PT[(t + 1) * N + x] = acc; }
+            }
+            for (int r = threadIdx.x; r < N; r += blockDim.x) {
+                double acc = 0.0;
+                PS[r * (N + 1)] = 0.0;
+                for (int x = 0; x < N; ++x) { acc += g[comp_s * V + r * N + x]; PS[r * (N + 1) + x + 1] = acc; }
+            }
+            staged = chain;
+            __syncthreads();
+        }
+        const int d = tile * 256 + threadIdx.x;
+        if (d < V) {
+            const int a = d / N, b = d - a * N;
+            const int Dt = a <= N / 2 ? a : a - N, Dx = b <= N / 2 ? b : b - N;
+            const int T = Dt < 0 ? -Dt : Dt, X = Dx < 0 ? -Dx : Dx;
+            const double st = Dt < 0 ? -1.0 : 1.0, ss = Dx < 0 ? -sign_s : sign_s;
+            const double shift = beta * (double)(T + X);
+            double acc = 0.0;
+            for (int x0 = 0; x0 < N; ++x0) {
+                int t_start = x0 + offset - (Dt < 0 ? T : 0);
+                t_start %= N; if (t_start < 0) t_start += N;
+                int row = (x0 + Dt) % N; if (row < 0) row += N;
+                const double* prow = PS + row * (N + 1);
+                for (int x1 = 0; x1 < N; ++x1) {
+                    int s_start = x1 + offset - (Dx < 0 ? X : 0);
+                    s_start %= N; if (s_start < 0) s_start += N;
+                    const double S = st * circular_range(PT + x1, N, N, t_start, T) + ss * circular_range(prow, 1, N, s_start, X);
+                    acc += exp(fma(alpha, S, shift));
+                }
+            }
+            out[chain * V + d] = acc / (double)V;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Blocking and Bootstrap of scalar columns (supervillain/analysis/blocking.py:54-66, bootstrap.py:57-67), one column per
 // series (e.g. one observable of every chain), T samples each, data (series, T):
 //   block_mean      out[s, b] = mean_{i < width} w[drop + b width + i] data[s, drop + b width + i]
@@ -601,6 +677,28 @@ extern "C" int svb_bootstrap_mean(const double* data, const double* weight, int6
     const long long grid = series < 148 * 8 ? series : 148 * 8;
     bootstrap_mean_kernel<<<(unsigned)grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         data, weight, series, T, reinterpret_cast<const long long*>(idx), draws, out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_taxicab_correlator(int kind, const double* links, int64_t chains, int N, double kappa, const double* kappa_chain,
+                                      double* out, void* stream) {
+    if (kind != SVB_TAXI_SPIN && kind != SVB_TAXI_VORTEX) return fail(SVB_E_PARAM, "svb_taxicab_correlator: kind %d", kind);
+    if (!links || !out) return fail(SVB_E_NULL, "svb_taxicab_correlator: links and out are required");
+    if (chains < 0 || N < 2) return fail(SVB_E_SHAPE, "svb_taxicab_correlator: shape");
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_taxicab_correlator: kappa must be positive");
+    if (chains == 0) return SVB_OK;
+    const size_t smem = (size_t)2 * N * (N + 1) * sizeof(double);
+    int dev = 0, max_smem = 0, sms = 0;
+    SVB_CUDA_TRY(cudaGetDevice(&dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SVB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > (size_t)max_smem) return fail(SVB_E_UNSUPPORTED, "svb_taxicab_correlator: the prefix sums of N=%d do not fit shared memory", N);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(taxicab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (N * N + 255) / 256;
+    const long long items = chains * tiles, cap = (long long)sms * 8;
+    taxicab_kernel<<<(unsigned)(items < cap ? items : cap), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        links, chains, N, kind, kappa, kappa_chain, tiles, out);
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }

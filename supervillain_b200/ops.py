@@ -501,3 +501,35 @@ def bootstrap_mean(data, indices, weight=None):
     _lib.check(lib.svb_bootstrap_mean(_dev(data, 'data', (torch.float64,)), _opt(weight, 'weight', (torch.float64,), (T,)), series, T,
                                       _dev(indices, 'indices', (torch.int64,)), draws, out.data_ptr(), _stream()))
     return out
+
+
+TAXI_SPIN, TAXI_VORTEX = 0, 1
+
+
+def taxicab_correlator(kind, links, kappa, kappa_chain=None):
+    """The taxicab reweighting observables from the gauge-invariant links (chains, 2, N, N) float64 -> (chains, N, N)
+    (svb_taxicab_correlator): kind 'spin' = Spin_Spin.Worldline (links = m - delta(v)/W, observable/spin.py:50-224),
+    kind 'vortex' = Vortex_Vortex.Villain (links = d(phi) - 2 pi n, observable/vortex.py:63-189)."""
+    lib = _lib.load()
+    chains, N = _fields_shape(links, 'links', 2)
+    out = torch.empty((chains, N, N), dtype=torch.float64, device=links.device)
+    _lib.check(lib.svb_taxicab_correlator({'spin': TAXI_SPIN, 'vortex': TAXI_VORTEX}[kind], _dev(links, 'links', (torch.float64,)),
+                                          chains, N, float(kappa), _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)),
+                                          out.data_ptr(), _stream()))
+    return out
+
+
+def worldline_spin_spin(m, v, kappa, W=1, kappa_chain=None):
+    """Spin_Spin.Worldline for every chain: Links.Worldline = m - delta(v)/W (observable/links.py:35-45) by the form kernel,
+    then the taxicab reweighting."""
+    links = m.to(torch.float64)
+    if W != float('inf'):
+        links = links - form_op('delta', 2, v).to(torch.float64) / float(W)
+    return taxicab_correlator('spin', links.contiguous(), kappa, kappa_chain)
+
+
+def villain_vortex_vortex(phi, n, kappa, kappa_chain=None):
+    """Vortex_Vortex.Villain for every chain: Links.Villain = d(phi) - 2 pi n (observable/links.py:18-32), then the taxicab
+    reweighting."""
+    links = form_op('d', 0, phi.to(torch.float64)) - (2 * math.pi) * n.to(torch.float64)
+    return taxicab_correlator('vortex', links.contiguous(), kappa, kappa_chain)

@@ -85,3 +85,8 @@ def golden_autocorrelation():
 @pytest.fixture(scope='session')
 def golden_resampling():
     return load_golden('resampling')[0]
+
+
+@pytest.fixture(scope='session')
+def golden_taxicab():
+    return load_golden('taxicab')[0]

@@ -375,9 +375,33 @@ def resampling():
     print('resampling cases:', [(len(c['data']), c['width'], c['drop'], c['blocked'].shape, c['resampled'].shape) for c in cases])
 
 
+def taxicab():
+    """Spin_Spin.Worldline (observable/spin.py:50-224) and Vortex_Vortex.Villain (observable/vortex.py:63-189): the taxicab
+    reweighting observables on random link fields, even and odd N."""
+    rng = np.random.default_rng(12)
+    cases = []
+    for N, kappa, W in [(4, 0.5, 1), (5, 0.7, 1), (6, 0.3, 2), (8, 1.1, 1)]:
+        L = sv.lattice.Lattice2D(N)
+        Sw = sv.action.Worldline(L, kappa, W=W)
+        m_, v_ = _wl_random_cfg(L, int(rng.integers(1 << 30)))
+        cfg = {'m': L.form(1, dtype=int), 'v': L.form(2, dtype=int)}
+        cfg['m'][...] = m_; cfg['v'][...] = v_
+        links_w = np.asarray(sv.observable.Links.Worldline(Sw, cfg['m'], cfg['v']), dtype=np.float64)
+        spin = sv.observable.Spin_Spin.Worldline(Sw, links_w)
+        Sv = sv.action.Villain(L, kappa, W=W)
+        phi = L.form(0); phi[...] = rng.uniform(-np.pi, np.pi, phi.shape)
+        n = L.form(1, dtype=int); n[...] = rng.integers(-2, 3, n.shape)
+        links_v = np.asarray(sv.observable.Links.Villain(Sv, phi, n), dtype=np.float64)
+        vortex = sv.observable.Vortex_Vortex.Villain(Sv, links_v)
+        cases.append(dict(N=N, kappa=kappa, W=W, m=np.asarray(cfg['m']), v=np.asarray(cfg['v']), links_w=links_w, spin_spin=spin,
+                          phi=np.asarray(phi), n=np.asarray(n), links_v=links_v, vortex_vortex=vortex))
+    _pack(cases, 'taxicab')
+    print('taxicab:', [(c['N'], float(c['spin_spin'].min()), float(c['vortex_vortex'].max())) for c in cases])
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['villain_neighborhood', 'villain_observables', 'lattice_forms',
                              'worldline_checkerboard', 'worldline_plaquette', 'worldline_observables', 'worldline_wrapping',
-                             'villain_decoupled', 'villain_cohomology', 'autocorrelation', 'resampling']
+                             'villain_decoupled', 'villain_cohomology', 'autocorrelation', 'resampling', 'taxicab']
     for name in which:
         globals()[name]()

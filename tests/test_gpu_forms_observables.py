@@ -256,3 +256,28 @@ def test_blocking_and_bootstrap_match_reference(golden_resampling):
         R.NoSuchObservable
     auto = svb.analysis.Blocking(E)                          # width='auto': the ensemble's autocorrelation time
     assert auto.width == E.autocorrelation_time()
+
+
+def test_taxicab_observables_match_reference(golden_taxicab):
+    """Spin_Spin.Worldline and Vortex_Vortex.Villain (the taxicab reweighting observables) from the fields, against the
+    unmodified reference on its own configurations (even and odd N; 1e-11 relative over 100 orders of magnitude), then
+    against the oracle on a batch at a production size with per-chain kappa."""
+    for c in golden_taxicab:
+        kappa, W = float(c['kappa']), int(c['W'])
+        m = torch.from_numpy(c['m'][None]).to(torch.int32).cuda()
+        v = torch.from_numpy(c['v'][None]).to(torch.int32).cuda()
+        spin = ops.worldline_spin_spin(m, v, kappa, W=W)[0].cpu().numpy()
+        np.testing.assert_allclose(spin, c['spin_spin'], rtol=1e-11)
+        phi = torch.from_numpy(c['phi'][None]).cuda()
+        n = torch.from_numpy(c['n'][None]).to(torch.int32).cuda()
+        vortex = ops.villain_vortex_vortex(phi, n, kappa)[0].cpu().numpy()
+        np.testing.assert_allclose(vortex, c['vortex_vortex'], rtol=1e-11)
+        assert spin[0, 0] == 1 and vortex[0, 0] == 1
+    rng = np.random.default_rng(2)
+    chains, N = 6, 16
+    links = rng.normal(size=(chains, 2, N, N)) * 0.3
+    kc = np.linspace(0.4, 1.5, chains)
+    for kind, fn in (('spin', lat.spin_spin_worldline), ('vortex', lat.vortex_vortex_villain)):
+        out = ops.taxicab_correlator(kind, torch.from_numpy(links).cuda(), 1.0, kappa_chain=torch.from_numpy(kc).cuda()).cpu().numpy()
+        for k in range(chains):
+            np.testing.assert_allclose(out[k], fn(links[k], kc[k]), rtol=1e-11)
