@@ -225,6 +225,33 @@ class BatchedEnsemble:
             return obs[name]
         raise AttributeError(name)
 
+    def measure(self, name):
+        """A two-point observable of every kept configuration (needs keep_every > 0) -> (chains, draws, N, N), computed on
+        the device, named as the reference names them:
+          Villain    Spin_Spin (spin.py:28-42, complex), Winding_Winding (winding.py:77-86, complex),
+                     Vortex_Vortex (vortex.py:63-189, the taxicab reweighting)
+          Worldline  Vortex_Vortex (vortex.py:22-37, complex), Spin_Spin (spin.py:50-224, the taxicab reweighting)"""
+        from . import ops
+        if 'configuration' not in self.__dict__:
+            raise ValueError('no configurations were kept; call generate(..., keep_every=k)')
+        kappa, W = self.Action.kappa, self.Action.W
+        cfg = self.configuration
+        dev = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x)).to(device=self.device, dtype=dt)
+        if self.kind == 'Villain':
+            fn = {'Spin_Spin': lambda phi, n: ops.villain_spin_spin(phi),
+                  'Winding_Winding': lambda phi, n: ops.correlation('winding', n),
+                  'Vortex_Vortex': lambda phi, n: ops.villain_vortex_vortex(phi, n, kappa)}.get(name)
+            fields = ('phi', torch.float64), ('n', torch.int32)
+        else:
+            fn = {'Vortex_Vortex': lambda m, v: ops.correlation('vortex', v, W=W),
+                  'Spin_Spin': lambda m, v: ops.worldline_spin_spin(m, v, kappa, W=W)}.get(name)
+            fields = ('m', torch.int32), ('v', torch.int32)
+        if fn is None:
+            raise NotImplementedError(f'{name} is not a two-point observable of the {self.kind} formulation on this path')
+        draws = cfg[fields[0][0]].shape[1]
+        out = [fn(*(dev(cfg[k][:, t], dt) for k, dt in fields)).cpu().numpy() for t in range(draws)]
+        return np.stack(out, axis=1)
+
     def autocorrelation_time(self, observables=None, every=False):
         """The batched form of `Ensemble.autocorrelation_time` (supervillain/ensemble.py:184-239): the integrated
         autocorrelation time of every scalar observable column of every chain, computed on the device

@@ -281,3 +281,29 @@ def test_taxicab_observables_match_reference(golden_taxicab):
         out = ops.taxicab_correlator(kind, torch.from_numpy(links).cuda(), 1.0, kappa_chain=torch.from_numpy(kc).cuda()).cpu().numpy()
         for k in range(chains):
             np.testing.assert_allclose(out[k], fn(links[k], kc[k]), rtol=1e-11)
+
+
+def test_ensemble_measures_two_point_observables_of_kept_configurations():
+    """BatchedEnsemble.measure: the reference's two-point observables by name on the kept draws of every chain, against
+    the oracle's restatements applied to the same configurations."""
+    from oracle import villain_np as V
+    S = svb.Villain(svb.Lattice2D(8), 0.6)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=2)
+    E = svb.BatchedEnsemble(S, 5).generate(6, G, 'hot', start_seed=4, keep_every=2)
+    vv, ss, ww = E.measure('Vortex_Vortex'), E.measure('Spin_Spin'), E.measure('Winding_Winding')
+    assert vv.shape == ss.shape == ww.shape == (5, 3, 8, 8)
+    for c in range(5):
+        for t in range(3):
+            phi, n = E.configuration['phi'][c, t], E.configuration['n'][c, t]
+            np.testing.assert_allclose(vv[c, t], lat.vortex_vortex_villain(V.links(phi, n), 0.6), rtol=1e-11)
+            s = np.exp(1j * phi[0])
+            np.testing.assert_allclose(ss[c, t], lat.correlation(s, s), atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        E.measure('NoSuchCorrelator')
+    Sw = svb.Worldline(svb.Lattice2D(8), 0.6)
+    Ew = svb.BatchedEnsemble(Sw, 4).generate(4, svb.generator.worldline.PlaquetteUpdate(Sw, seed=1), 'cold', keep_every=2)
+    sp = Ew.measure('Spin_Spin')
+    for c in range(4):
+        m, v = Ew.configuration['m'][c, 1], Ew.configuration['v'][c, 1]
+        links = m - lat.delta2(v)
+        np.testing.assert_allclose(sp[c, 1], lat.spin_spin_worldline(links, 0.6), rtol=1e-11)
