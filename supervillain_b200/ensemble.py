@@ -9,6 +9,9 @@ axis.  All chains live in HBM for the whole run; one kernel launch advances ever
 `sweeps_per_step` sweeps and reduces the observables; only the per-chain observable record (a few
 doubles per chain) crosses PCIe per step, and configurations only at the stride asked for.
 """
+import os
+import pickle
+
 import numpy as np
 import torch
 
@@ -214,6 +217,59 @@ class BatchedEnsemble:
             flat = self.record.reshape(-1, self.record.shape[-1])
             account(flat, self.chains, steps * sweeps_per_step)
         return self
+
+    # -- continuation and checkpoints ------------------------------------------------------------
+    @classmethod
+    def continue_from(cls, ensemble, steps, *, keep_every=0, progress=_no_op):
+        """The batched form of `Ensemble.continue_from` (supervillain/ensemble.py:103-142): `steps` more samples of every
+        chain from the last state of `ensemble` (a BatchedEnsemble or the path of a checkpoint written by `save`) with its
+        generator.  The generator's Philox state is (seed, sweep counter), so the continuation is the run that was never
+        interrupted: fields and records are bit for bit those of one longer `generate`."""
+        e = cls.load(ensemble) if isinstance(ensemble, (str, os.PathLike)) else ensemble
+        if not isinstance(e, BatchedEnsemble) or e.fields is None or 'generator' not in e.__dict__:
+            raise ValueError('The ensemble must be a BatchedEnsemble (or a checkpoint of one) that has generated at least one sample.')
+        new = cls(e.Action, e.chains, device=e.device, dtype=e.dtype, chain0=e.chain0)
+        new.fields = tuple(f.clone() for f in e.fields)
+        new.generate(steps, e.generator, start='continue', sweeps_per_step=e.sweeps_per_step, keep_every=keep_every,
+                     kappa_chain=e.__dict__.get('kappa_chain'), progress=progress)
+        new.index = int(e.index[-1]) + new.index
+        return new
+
+    def save(self, path):
+        """Checkpoint: the resident fields, the records, the sample index and the (action, generator) pair -- whose state is
+        the Philox (seed, counter) -- in one .npz.  (The reference stores ensembles as HDF5, supervillain/h5/; h5py is not
+        part of this environment.)"""
+        if self.fields is None:
+            raise ValueError('nothing to save: generate first')
+        blob = np.frombuffer(pickle.dumps((self.Action, self.__dict__.get('generator'))), dtype=np.uint8)
+        arrays = dict(field0=self.fields[0].cpu().numpy(), field1=self.fields[1].cpu().numpy(), record=self.record, index=self.index,
+                      meta=np.array([self.chains, self.chain0, self.sweeps_per_step, self.steps], dtype=np.int64), state=blob)
+        if self.__dict__.get('kappa_chain') is not None:
+            arrays['kappa_chain'] = self.kappa_chain.cpu().numpy()
+        for k, v in self.__dict__.get('configuration', {}).items():
+            arrays['configuration_' + k] = v
+        with open(path, 'wb') as f:
+            np.savez(f, **arrays)
+
+    @classmethod
+    def load(cls, path, device=None):
+        """A BatchedEnsemble as `save` left it (fields back on the device), ready for `continue_from`."""
+        with np.load(path, allow_pickle=False) as z:
+            action, generator = pickle.loads(z['state'].tobytes())
+            chains, chain0, sweeps_per_step, steps = (int(x) for x in z['meta'])
+            e = cls(action, chains, device=device, chain0=chain0)
+            e.fields = tuple(torch.from_numpy(z[k]).to(e.device) for k in ('field0', 'field1'))
+            e.dtype = e.fields[0].dtype if e.kind == 'Villain' else e.dtype
+            e.record, e.index = z['record'], z['index']
+            e.steps, e.sweeps_per_step, e.generator = steps, sweeps_per_step, generator
+            e.kappa_chain = torch.from_numpy(z['kappa_chain']).to(e.device) if 'kappa_chain' in z.files else None
+            cfg = {k[len('configuration_'):]: z[k] for k in z.files if k.startswith('configuration_')}
+            if cfg:
+                e.configuration = cfg
+        N = action.Lattice.N
+        kappa = action.kappa if e.kappa_chain is None else e.kappa_chain.cpu().numpy()[:, None]
+        e.observables = (villain_inline_values if e.kind == 'Villain' else worldline_inline_values)(e.record, N, kappa)
+        return e
 
     def __len__(self):
         """The number of recorded samples per chain (what `len(Ensemble)` is for the reference's single chain)."""
