@@ -196,13 +196,15 @@ __device__ __forceinline__ void chain_finish(const double* red_state, const doub
 // last stored it), and a CTA sets the epochs of its chains to a.signal_epoch once all its stores and records are complete.
 // UNIT: W == 1 and interval_n == 1 (the reference's defaults) as compile-time constants.
 // MODE: SVB_FILT_FAST       NeighborhoodUpdate, the cold path decides in FAST fp64 arithmetic (the production sweep);
-//       SVB_FILT_STRICT     the same proposals, the cold path decides in the reference's operation order: SiteUpdate
-//                           (interval_n = 0: no dn proposals, site.py:43-120) identical to the STRICT kernels;
+//       SVB_FILT_STRICT     the same proposals, the cold path decides in the reference's operation order: identical to
+//                           the STRICT kernels;  SVB_FILT_SITE: the same with interval_n == 0 -- SiteUpdate (no dn
+//                           proposals, site.py:43-120);
 //       SVB_FILT_EXACT      ExactUpdate (exact.py:50-129): dphi = 0, dn = d z with z one of the 2 a.interval_n nonzero values
 //                           drawn from word B (villain_get_draw), STRICT cold path.
 #define SVB_FILT_FAST 0
 #define SVB_FILT_STRICT 1
 #define SVB_FILT_EXACT 2
+#define SVB_FILT_SITE 3          /* SVB_FILT_STRICT with interval_n == 0 at compile time: no digits, no n updates */
 template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT, int MODE>
 __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                              const __grid_constant__ FilterConsts fc) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     const bool obs_of_input = a.obs_in != nullptr;                // state columns describe the chain as it ARRIVES
     const bool want_obs = a.obs != nullptr && !obs_of_input;     // ... or as it leaves (one more fp64 pass)
     static_assert(!(UNIT && MODE != SVB_FILT_FAST), "UNIT is the production sweep");
-    const int interval_n = UNIT ? 1 : a.interval_n;
+    const int interval_n = UNIT ? 1 : (MODE == SVB_FILT_SITE ? 0 : a.interval_n);
     const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
     const int W = (UNIT || MODE == SVB_FILT_EXACT) ? 1 : a.W, mWI = -W * interval_n;
     const float cIn = fc.c * (float)interval_n;
@@ -403,6 +405,9 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                         const int zb = (ib < interval_n) ? ib - interval_n : ib - interval_n + 1;
                         digA[0] = digA[2] = interval_n - za; digA[1] = digA[3] = interval_n + za;
                         digB[0] = digB[2] = interval_n - zb; digB[1] = digB[3] = interval_n + zb;
+                    } else if (MODE == SVB_FILT_SITE) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) digA[i] = digB[i] = 0;            // word B is the uniform's leading bits as it stands
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -419,10 +424,10 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     const float2 r_f0 = make_float2(R0own[T * qA], R0own[T * qB]), r_f1 = make_float2(R1own[T * qA], R1own[T * qB]);
                     const float2 r_b0 = make_float2(r0bA[T * qA], R0b[T * qB]), r_b1 = make_float2(R1b[T * qA], R1b[T * qB]);
                     // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
-                    const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
-                    const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
-                    const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
-                    const float2 dr_b1 = __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    const float2 dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
+                    const float2 dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
+                    const float2 dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
+                    const float2 dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
                     float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
                     acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
                     acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
@@ -480,10 +485,12 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             // is villain_dphi_from_word bit for bit with one multiply less
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
                             Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
-                            atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);      // only this thread touches these links in this pass
-                            atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
-                            atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
-                            atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
+                            if (MODE != SVB_FILT_SITE) {
+                                atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
+                                atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
+                                atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
+                                atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
+                            }
                             R0own[T * q] = h ? n_f0.y : n_f0.x;
                             r0b[T * q] = h ? n_b0.y : n_b0.x;
                             R1own[T * q] = h ? n_f1.y : n_f1.x;
@@ -554,10 +561,11 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 template <int NT, int MINB, int STAGES>
 static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool overlap = a.epochs != nullptr;
-    const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? SVB_FILT_STRICT : SVB_FILT_FAST);
+    const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? (a.interval_n == 0 ? SVB_FILT_SITE : SVB_FILT_STRICT) : SVB_FILT_FAST);
     const bool unit = mode == SVB_FILT_FAST && a.W == 1 && a.interval_n == 1;
     if (mode != SVB_FILT_FAST && overlap) return fail(SVB_E_UNSUPPORTED, "overlapped launches serve the NeighborhoodUpdate sweep only");
     auto kern = mode == SVB_FILT_EXACT    ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_EXACT>
+                : mode == SVB_FILT_SITE   ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_SITE>
                 : mode == SVB_FILT_STRICT ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_STRICT>
                 : overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true, SVB_FILT_FAST>
                                   : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false, SVB_FILT_FAST>)
@@ -566,7 +574,7 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     const size_t V = (size_t)NT * NT;
     const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32;
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
-    static int per_sm_cache[6][64];
+    static int per_sm_cache[7][64];
     const int variant = mode != SVB_FILT_FAST ? 3 + mode : (overlap ? 1 : 0) + (unit ? 2 : 0);
     int per_sm = (info.device < 64) ? per_sm_cache[variant][info.device] : 0;
     if (per_sm == 0) {
