@@ -264,6 +264,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
         }
     };
 
+    // (plain strided chain assignment: the ChainMap of the other persistent kernels costs this one registers it does not
+    // have -- 213 instead of 191 us per launch)
     long long chain = cluster_id;
     if (tid == 0 && chain < a.chains) issue_load(chain, 0, peek_epoch(chain));
     long long pending_chain = -1;
@@ -332,17 +334,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                 int32_t* N0b_q0 = first_row_thread ? PREV_N0 + (ROWS - 1) * N + x1 : N0b;
                 int32_t* N1b = N1c - 1 + wrap1;
                 // the draws depend on nothing in memory: they fill the wait for the slowest strip
+#ifndef SVB_CLUSTER_PRE
+#define SVB_CLUSTER_PRE 1                  /* how many of the pass's PER / 2 Philox blocks are drawn before the wait: both
+                                              cost registers the sweep needs (200 us), none leaves the wait empty (203 us) */
+#endif
                 Philox4 bits_p[PER / 2];
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p)
-                    bits_p[p] = philox_site_keys(a, gc, gs, (uint32_t)((rank * ROWS + r0 + 16 * p) * N + x1));
+                    if (p < SVB_CLUSTER_PRE) bits_p[p] = philox_site_keys(a, gc, gs, (uint32_t)((rank * ROWS + r0 + 16 * p) * N + x1));
                 cluster_wait();                                    // S2 / S3: the previous pass is complete in every strip
                 if (c == 0 && obs_of_input && s == 0) cta_share(true, false);
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p) {
                     const int gx0 = rank * ROWS + r0 + 16 * p;                              // global row of the pair's first site
                     const uint32_t c0 = (uint32_t)(gx0 * N + x1);                             // villain_pair_counter (bit 3 clear)
-                    const Philox4 bits = bits_p[p];
+                    const Philox4 bits = (p < SVB_CLUSTER_PRE) ? bits_p[p] : philox_site_keys(a, gc, gs, c0);
                     const int qA = 2 * p, qB = 2 * p + 1;
                     float* r0bA = (p == 0) ? R0b_q0 : R0b;
                     int32_t* n0bA = (p == 0) ? N0b_q0 : N0b;
