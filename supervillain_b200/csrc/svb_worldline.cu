@@ -775,6 +775,7 @@ static int dispatch_worldline(const WorldlineArgs& a, int rng_mode, int path, cu
                 case 16: return launch_worldline_table<MODE, 16, 16>(a, stream, sm_count);
                 case 32: return launch_worldline_table<MODE, 32, 8>(a, stream, sm_count);
                 case 64: return launch_worldline_table<MODE, 64, 4>(a, stream, sm_count);
+                case 128: return launch_worldline_table<MODE, 128, 1>(a, stream, sm_count);        // 192 KiB: one chain per SM
                 default: break;
             }
         }
@@ -839,7 +840,8 @@ extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t ch
                                               void* stream) {
     if (!m || !v || !epochs) return fail(SVB_E_NULL, "svb_worldline_sweep_overlapped: m, v and epochs are required");
     if (chains < 0) return fail(SVB_E_SHAPE, "svb_worldline_sweep_overlapped: chains=%lld", (long long)chains);
-    if (N != 16 && N != 32 && N != 64) return fail(SVB_E_UNSUPPORTED, "svb_worldline_sweep_overlapped: N must be 16, 32 or 64 (got %d)", N);
+    if (N != 16 && N != 32 && N != 64 && N != 128)
+        return fail(SVB_E_UNSUPPORTED, "svb_worldline_sweep_overlapped: N must be 16, 32, 64 or 128 (got %d)", N);
     if (((uintptr_t)m % 16) || ((uintptr_t)v % 16)) return fail(SVB_E_ALIGN, "svb_worldline_sweep_overlapped: fields must be 16-byte aligned");
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: kappa must be positive");
     if (mode < SVB_WL_JOINT || mode > SVB_WL_COEXACT) return fail(SVB_E_PARAM, "svb_worldline_sweep_overlapped: mode %d", mode);
@@ -866,7 +868,8 @@ extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t ch
     switch (N) {                                                                               \
         case 16: return launch_worldline_table<M, 16, 16>(a, st, sm_count);                    \
         case 32: return launch_worldline_table<M, 32, 8>(a, st, sm_count);                     \
-        default: return launch_worldline_table<M, 64, 4>(a, st, sm_count);                     \
+        case 64: return launch_worldline_table<M, 64, 4>(a, st, sm_count);                     \
+        default: return launch_worldline_table<M, 128, 1>(a, st, sm_count);                    \
     }
     if (mode == SVB_WL_JOINT) { SVB_WL_OV_DISPATCH(SVB_WL_JOINT) }
     if (mode == SVB_WL_VORTEX) { SVB_WL_OV_DISPATCH(SVB_WL_VORTEX) }

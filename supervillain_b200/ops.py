@@ -137,7 +137,7 @@ def villain_sweep_plan(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1
     return run
 
 
-OVERLAP_SIZES = (16, 32, 64)             # worldline table kernels
+OVERLAP_SIZES = (16, 32, 64, 128)        # worldline table kernels (128: one chain per SM)
 VILLAIN_OVERLAP_SIZES = (16, 32, 64, 128)  # filtered kernels; 128 is the cluster kernel
 
 
@@ -214,7 +214,7 @@ class WorldlineOverlappedSweeps:
         self.lib = _lib.load()
         self.chains, self.N = _fields_shape(m, 'm', 2)
         if self.N not in OVERLAP_SIZES or (mode != 'joint' and interval > 2):
-            raise NotImplementedError('overlapped sweeps need N in (16, 32, 64) and interval <= 2')
+            raise NotImplementedError('overlapped sweeps need N in (16, 32, 64, 128) and interval <= 2')
         self.mode, self.interval = _WL_MODES[mode], int(interval)
         self.p_m = _dev(m, 'm', (torch.int32,))
         self.p_v = _dev(v, 'v', (torch.int32,), (self.chains, 1, self.N, self.N))

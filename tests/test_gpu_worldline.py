@@ -150,6 +150,30 @@ def test_full_size_config3_shard_bit_exact_against_c_oracle(mode):
     assert (ops.worldline_observables(m, v, W=W)[:, WOBS_DELTA_M_ABS] == 0).all().item()
 
 
+@pytest.mark.parametrize('mode', ['joint', 'vortex', 'coexact'])
+def test_L128_table_kernel_bit_exact_against_c_oracle(mode):
+    """L = 128: the chain (192 KiB of m and v) still fits one SM, so the table kernel serves it, one CTA per SM -- m and v
+    identical to the C oracle, also through the overlapped-launch entry point."""
+    from oracle import c_oracle as C
+    N, chains, kappa = 128, 170, 0.6
+    m0, v0 = WL.hot_start(np.random.default_rng(128), N, chains)
+    m, v = dev(m0, torch.int32), dev(v0, torch.int32)
+    obs = torch.zeros((chains, WOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.worldline_sweep(m, v, kappa, mode=mode, n_sweeps=2, seed=8, chain0=11, obs=obs)
+    m_ref, v_ref, acc, accp = C.worldline_sweep_philox(m0, v0, kappa, W=1, mode=mode, n_sweeps=2, seed=8, chain0=11)
+    assert (m.cpu().numpy() == m_ref).all() and (v.cpu().numpy() == v_ref).all()
+    rec = obs.cpu().numpy()
+    assert (rec[:, WOBS_ACCEPTED] == acc).all()
+    np.testing.assert_allclose(rec[:, WOBS_ACCEPTANCE], accp, rtol=1e-5)
+    m2, v2 = dev(m0, torch.int32), dev(v0, torch.int32)
+    ov = ops.WorldlineOverlappedSweeps(m2, v2, kappa, mode=mode, seed=8, chain0=11)
+    obs2 = torch.zeros_like(obs)
+    ov.step(0, 1, obs2)
+    ov.step(1, 1, obs2)
+    torch.cuda.synchronize()
+    assert torch.equal(m2, m) and torch.equal(v2, v)
+
+
 def test_wrapping_update_reproduces_reference_chain(golden_worldline_wrapping):
     """WrappingUpdate with rng=default_rng(99): identical m and accept counts to the reference (wrapping.py:43-90)."""
     from supervillain_b200.generator.worldline import WrappingUpdate

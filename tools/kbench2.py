@@ -122,3 +122,19 @@ if 'dec' in which:
         phi, n = sets[k[0] % 4]; k[0] += 1
         ops.villain_cohomology(phi, n, 0.5, seed=1, sweep=k[0], counters=cnt)
     report('villain cohomology update L=32 x 4096 chains (2 slice proposals per chain; reads 2 N links + sites, writes N links on accept)', CH * 2 * N, 32, timeit(f))
+if 'wl128' in which:
+    N, CH = 128, 512
+    S = svb.Worldline(svb.Lattice2D(N), 0.5)
+    m, v = svb.BatchedEnsemble(S, CH)._start('hot', 1)
+    obs = torch.zeros((CH, ops.WOBS_COUNT), dtype=torch.float64, device='cuda')
+    for mode in ('joint', 'vortex'):
+        k = [0]
+        def f():
+            k[0] += 1
+            ops.worldline_sweep(m, v, 0.5, mode=mode, seed=1, sweep0=k[0], obs=obs)
+        report(f'worldline {mode} L=128 x 512 chains, table kernel (one chain per SM)', CH * N * N, 24, timeit(f))
+    k = [0]
+    def g():
+        k[0] += 1
+        ops.worldline_sweep(m, v, 0.5, mode='joint', seed=1, sweep0=k[0], obs=obs, path='global')
+    report('worldline joint L=128 x 512 chains, global path', CH * N * N, 24, timeit(g, n=5))
