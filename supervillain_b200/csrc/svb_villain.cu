@@ -1711,8 +1711,9 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
     int rc = get_device_info(info);
     if (rc) return rc;
 #ifndef SVB_NO_CLUSTER_KERNEL
-    if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED && arith_mode != SVB_ARITH_STRICT &&
-        !a.accept_mask && !a.dS_out && !a.exact_mode && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
+    if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED &&
+        (arith_mode != SVB_ARITH_STRICT || a.filtered_strict) && !a.accept_mask && !a.dS_out && (!a.exact_mode || a.filtered_strict) &&
+        ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
         // one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
         return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, stream, info);
     }

@@ -81,6 +81,23 @@ __device__ __noinline__ bool villain_exact_decision_ptr(const ExactProposalPtr& 
 // the end, behind a cluster barrier that follows every CTA's completed bulk stores.
 // TPB threads per CTA (8 or 16 row groups of N/2 column slots); STAGES = 2: phi and n double-buffered, so that the next
 // chain's strip arrives and the previous one's leaves while this one is swept (one CTA of 1024 threads per SM).
+// ... and in the reference's operation order (villain_exact_decision_strict): p.c = 2 pi, p.g = dn in units of 1.
+__device__ __noinline__ bool villain_exact_decision_strict_ptr(const ExactProposalPtr& p) {
+    const double pc = *p.p_c;
+    const double r_f0 = __dsub_rn(__dsub_rn(*p.p_f0, pc), __dmul_rn(SVB_TWO_PI, (double)*p.n_f0));
+    const double r_b0 = __dsub_rn(__dsub_rn(pc, *p.p_b0), __dmul_rn(SVB_TWO_PI, (double)*p.n_b0));
+    const double r_f1 = __dsub_rn(__dsub_rn(*p.p_f1, pc), __dmul_rn(SVB_TWO_PI, (double)*p.n_f1));
+    const double r_b1 = __dsub_rn(__dsub_rn(pc, *p.p_b1), __dmul_rn(SVB_TWO_PI, (double)*p.n_b1));
+    const double dr_f0 = __dsub_rn(-p.dphi, __dmul_rn(p.c, (double)p.g[0])), dr_b0 = __dsub_rn(p.dphi, __dmul_rn(p.c, (double)p.g[1]));
+    const double dr_f1 = __dsub_rn(-p.dphi, __dmul_rn(p.c, (double)p.g[2])), dr_b1 = __dsub_rn(p.dphi, __dmul_rn(p.c, (double)p.g[3]));
+    const double hk = p.half_kappa;
+    double dS = __dmul_rn(__dmul_rn(hk, dr_f0), __dadd_rn(__dmul_rn(2.0, r_f0), dr_f0));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_b0), __dadd_rn(__dmul_rn(2.0, r_b0), dr_b0)));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_f1), __dadd_rn(__dmul_rn(2.0, r_f1), dr_f1)));
+    dS = __dadd_rn(dS, __dmul_rn(__dmul_rn(hk, dr_b1), __dadd_rn(__dmul_rn(2.0, r_b1), dr_b1)));
+    return villain_decide_lazy(exp_clipped(-dS), p.d, p.rc);
+}
+
 // The cold half of the epoch wait (the producer launch has not stored the chain yet), out of line: it must not cost the
 // sweep loop registers.
 static __device__ __noinline__ void cluster_epoch_spin(const uint32_t* epoch, uint32_t want) {
@@ -98,7 +115,9 @@ static __device__ __noinline__ void cluster_epoch_spin(const uint32_t* epoch, ui
 constexpr int cluster_min_blocks(int NT, int CL, int TPB, int STAGES) {
     return (TPB >= 1024 || (STAGES * 16 + 8) * (NT / CL) * NT > 112 * 1024) ? 1 : 2;          // two CTAs per SM where they fit
 }
-template <int NT, int CL, int TPB, int STAGES, bool OVERLAP>
+// MODE: SVB_FILT_FAST (the NeighborhoodUpdate sweep), SVB_FILT_STRICT / SVB_FILT_SITE / SVB_FILT_EXACT (the decoupled updates with
+// a STRICT cold path), exactly as in villain_smem_filtered_kernel.
+template <int NT, int CL, int TPB, int STAGES, bool OVERLAP, int MODE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_blocks(NT, CL, TPB, STAGES))
     villain_cluster_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -143,9 +162,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
     cluster_sync_all();
     const bool obs_of_input = a.obs_in != nullptr;
     const bool want_obs = a.obs != nullptr && !obs_of_input;
-    const int interval_n = a.interval_n;
-    const uint32_t K = (uint32_t)(2 * interval_n + 1);
-    const int W = a.W, mWI = -W * interval_n;
+    static_assert(!(OVERLAP && MODE != SVB_FILT_FAST), "overlapped launches serve the NeighborhoodUpdate sweep");
+    const int interval_n = MODE == SVB_FILT_SITE ? 0 : a.interval_n;
+    const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
+    const int W = MODE == SVB_FILT_EXACT ? 1 : a.W, mWI = -W * interval_n;
     const float cIn = fc.c * (float)interval_n;
     const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
     const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;
@@ -354,11 +374,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     int32_t* n0bA = (p == 0) ? N0b_q0 : N0b;
                     uint32_t fA = bits.y, fB = bits.w;
                     int digA[4], digB[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    if (MODE == SVB_FILT_EXACT) {                 // z from word B; as "digits": I - z forward, I + z backward
                         const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
-                        fA = (uint32_t)pa; digA[i] = (int)(pa >> 32);
-                        fB = (uint32_t)pb; digB[i] = (int)(pb >> 32);
+                        fA = (uint32_t)pa; fB = (uint32_t)pb;
+                        const int ia = (int)(pa >> 32), ib = (int)(pb >> 32);
+                        const int za = (ia < interval_n) ? ia - interval_n : ia - interval_n + 1;
+                        const int zb = (ib < interval_n) ? ib - interval_n : ib - interval_n + 1;
+                        digA[0] = digA[2] = interval_n - za; digA[1] = digA[3] = interval_n + za;
+                        digB[0] = digB[2] = interval_n - zb; digB[1] = digB[3] = interval_n + zb;
+                    } else if (MODE == SVB_FILT_SITE) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) digA[i] = digB[i] = 0;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
+                            fA = (uint32_t)pa; digA[i] = (int)(pa >> 32);
+                            fB = (uint32_t)pb; digB[i] = (int)(pb >> 32);
+                        }
                     }
                     float2 U = make_float2(__uint_as_float(0x3F800000u | (bits.x >> 9)), __uint_as_float(0x3F800000u | (bits.z >> 9)));
                     U = __fadd2_rn(U, make_float2(-0.99999994f, -0.99999994f));
@@ -367,10 +400,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     const float2 r_f0 = make_float2(R0own[Q * qA], R0own[Q * qB]), r_f1 = make_float2(R1own[Q * qA], R1own[Q * qB]);
                     const float2 r_b0 = make_float2(r0bA[Q * qA], R0b[Q * qB]);
                     const float2 r_b1 = make_float2(R1b[Q * qA], R1b[Q * qB]);
-                    const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
-                    const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
-                    const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
-                    const float2 dr_b1 = __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    const float2 dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
+                    const float2 dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
+                    const float2 dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
+                    const float2 dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
                     float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
                     acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
                     acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
@@ -408,22 +441,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                             ep.n_f1 = sn1 + lx0 * N + x1;
                             ep.n_b1 = sn1 + lx0 * N + ((x1 - 1) & (N - 1));
                             ep.half_kappa = half_kappa;
-                            ep.c = SVB_TWO_PI * (double)W;
-                            ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                            ep.dphi = (MODE == SVB_FILT_EXACT) ? 0.0 : villain_dphi_from_word(wA, a.interval_phi);
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
                             ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
-                            ok = villain_exact_decision_ptr(ep);
+                            if (MODE == SVB_FILT_FAST) {
+                                ep.c = SVB_TWO_PI * (double)W;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                                ok = villain_exact_decision_ptr(ep);
+                            } else {
+                                ep.c = SVB_TWO_PI;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) ep.g[i] = W * (dig[i] - interval_n);
+                                ok = villain_exact_decision_strict_ptr(ep);
+                            }
                         }
                         n_acc += ok ? 1 : 0;
                         if (ok) {
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
                             Pc[2 * Q * q] = __dadd_rn(Pc[2 * Q * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
-                            atomicAdd(N0c + 2 * Q * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
-                            atomicAdd(n0b_site, W * dig[1] + mWI);
-                            atomicAdd(N1c + 2 * Q * q, W * dig[2] + mWI);
-                            atomicAdd(N1b + 2 * Q * q, W * dig[3] + mWI);
+                            if (MODE != SVB_FILT_SITE) {
+                                atomicAdd(N0c + 2 * Q * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
+                                atomicAdd(n0b_site, W * dig[1] + mWI);
+                                atomicAdd(N1c + 2 * Q * q, W * dig[2] + mWI);
+                                atomicAdd(N1b + 2 * Q * q, W * dig[3] + mWI);
+                            }
                             R0own[Q * q] = h ? n_f0.y : n_f0.x;
                             *r0b_site = h ? n_b0.y : n_b0.x;
                             R1own[Q * q] = h ? n_f1.y : n_f1.x;
@@ -494,11 +536,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
 template <int NT, int CL, int TPB, int STAGES>
 static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool overlap = a.epochs != nullptr;
-    auto kern = overlap ? villain_cluster_kernel<NT, CL, TPB, STAGES, true> : villain_cluster_kernel<NT, CL, TPB, STAGES, false>;
+    const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? (a.interval_n == 0 ? SVB_FILT_SITE : SVB_FILT_STRICT) : SVB_FILT_FAST);
+    if (mode != SVB_FILT_FAST && overlap) return fail(SVB_E_UNSUPPORTED, "overlapped launches serve the NeighborhoodUpdate sweep only");
+    auto kern = mode == SVB_FILT_EXACT    ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_EXACT>
+                : mode == SVB_FILT_SITE   ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_SITE>
+                : mode == SVB_FILT_STRICT ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_STRICT>
+                : overlap ? villain_cluster_kernel<NT, CL, TPB, STAGES, true, SVB_FILT_FAST>
+                          : villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_FAST>;
     constexpr int ROWS = NT / CL, VL = ROWS * NT, VHL = ROWS * NT / 2, NW = TPB / 32;
     const size_t smem = (size_t)STAGES * VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16 * STAGES;
-    static int clusters_cache[2][64];
-    int clusters = (info.device < 64) ? clusters_cache[overlap][info.device] : 0;
+    static int clusters_cache[5][64];
+    const int variant = mode != SVB_FILT_FAST ? 1 + mode : (overlap ? 1 : 0);
+    int clusters = (info.device < 64) ? clusters_cache[variant][info.device] : 0;
     if (clusters == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -510,11 +559,11 @@ static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, con
         cfg.attrs = at; cfg.numAttrs = 1;
         SVB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg));
         if (clusters < 1) return fail(SVB_E_UNSUPPORTED, "cluster villain kernel does not fit the device at N=%d", NT);
-        if (info.device < 64) clusters_cache[overlap][info.device] = clusters;
+        if (info.device < 64) clusters_cache[variant][info.device] = clusters;
     }
     long long n_clusters = clusters;
     if (n_clusters > a.chains) n_clusters = a.chains;
-    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    const FilterConsts fc = make_filter_consts(a.interval_phi, mode == SVB_FILT_EXACT ? 1 : a.W, a.interval_n);
     if (overlap) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_clusters * CL)); cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = stream;

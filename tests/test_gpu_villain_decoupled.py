@@ -80,10 +80,10 @@ def test_philox_mode_matches_oracle_replay(kind, N, W, kappa, interval):
 
 
 @pytest.mark.parametrize('kind', KINDS)
-@pytest.mark.parametrize('N,chains,kappa,W,interval', [(32, 1500, 0.5, 1, 1), (16, 2000, 2.5, 2, 3), (64, 200, 0.05, 1, 2)])
+@pytest.mark.parametrize('N,chains,kappa,W,interval', [(32, 1500, 0.5, 1, 1), (16, 2000, 2.5, 2, 3), (64, 200, 0.05, 1, 2), (128, 90, 0.4, 2, 2)])
 def test_filtered_kernels_decide_like_the_strict_kernels(kind, N, chains, kappa, W, interval):
-    """SiteUpdate, ExactUpdate and LinkUpdate with Philox draws run on fp32-filtered shared-memory kernels whose cold path
-    decides in STRICT arithmetic; a debug output (accept_mask / dS_out) sends the same call to the STRICT fp64 kernels.
+    """SiteUpdate, ExactUpdate and LinkUpdate with Philox draws run on fp32-filtered shared-memory kernels (L = 128: Site
+    and Exact on the cluster kernel) whose cold path decides in STRICT arithmetic; a debug output (accept_mask / dS_out) sends the same call to the STRICT fp64 kernels.
     Millions of proposals, hot and cold regimes: identical fields and accepted counts, i.e. the filter never answers
     differently."""
     S = svb.Villain(svb.Lattice2D(N), kappa, W=W)
