@@ -28,16 +28,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 // The two halves separately: work that touches nothing another thread writes may sit between them.
 // arrive: a release at cluster scope costs a gpu-scope MEMBAR (SASS: MEMBAR.ALL.GPU, ~0.3 us, and 16 warps of them queue
 // up) -- the top stall of the first version of this kernel.  One warp releases on behalf of the CTA instead: the block
-// barrier orders every thread's writes (also those into a neighbour's shared memory) before warp 0's release fence, and
-// fences are cumulative, so the other warps arrive relaxed.  203 -> 190 us per config-4 shard sweep.  (No release at all,
+// barrier orders every thread's writes before warp 0's release fence, and fences are cumulative, so the other warps arrive
+// relaxed (the warps that store into a NEIGHBOUR's shared memory release as well, see cluster_arrive).  203 -> 190 us per config-4 shard sweep.  (No release at all,
 // -DSVB_CLUSTER_RELAXED: 179 us, passes every test, and is a data race by the PTX memory model -- not used.)
 #ifdef SVB_CLUSTER_RELAXED   /* EXPERIMENT ONLY */
-__device__ __forceinline__ void cluster_arrive() { asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive(int = 32) { asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 #else
-__device__ __forceinline__ void cluster_arrive() {
+// `releasers`: the first so many threads (whole warps) release.  Warp 0 always does, on behalf of every write into the CTA's
+// own shared memory; the warps whose threads store into a NEIGHBOUR's shared memory release their own stores themselves.
+__device__ __forceinline__ void cluster_arrive(int releasers = 32) {
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if ((int)threadIdx.x < releasers) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -477,7 +479,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     if (a.obs) chain_partials<false, true>(red_state, red_count, lane, warp, 0.0, 0, 0, 0, sum_A_all + (double)sum_A, n_acc);
                     asm volatile("fence.proxy.async;" ::: "memory");   // phi / n writes (also into the previous strip) -> bulk store
                 }
-                cluster_arrive();                                  // S3 / S4: this strip's share of the colour pass is complete
+                cluster_arrive(HN > 32 ? HN : 32);                 // S3 / S4: this strip's share of the colour pass is complete
+                                                                   // (threads < HN own row 0: they wrote into the previous strip)
             }
             cluster_wait();                                        // S4
             sum_A_all += (double)sum_A;
