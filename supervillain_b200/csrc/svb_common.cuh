@@ -314,30 +314,12 @@ __device__ __forceinline__ void overlap_wait(const OverlapArgs& o, long long cha
     }
     asm volatile("fence.proxy.async;" ::: "memory");
 }
-// Chains -> workers (CTAs or clusters) of a persistent kernel.  Worker b sweeps chains b, b + workers, ... (`full` of
-// them); the chains % workers left over go to the LAST workers, one each.  Workers are dispatched in index order, so in a
-// stream of overlapped launches the slots freed first -- by the workers without an extra chain -- are taken by the
-// successor's first workers, whose chains those very workers have just published.  With the remainder on the first
-// workers, the successor's first workers would sit in the freed slots waiting for the slowest (+3.6 % per step at config 2).
-struct ChainMap {
-    long long first, workers, full, extra_chain;
-    int count;
-    __device__ __forceinline__ ChainMap(long long chains, long long worker, long long n_workers) {
-        first = worker; workers = n_workers;
-        full = chains / n_workers;
-        const long long extra = chains - full * n_workers;
-        const bool has_extra = worker >= n_workers - extra;
-        extra_chain = full * n_workers + (worker - (n_workers - extra));
-        count = (int)full + (has_extra ? 1 : 0);
-    }
-    __device__ __forceinline__ long long at(int i) const { return i < full ? first + i * workers : extra_chain; }
-};
-
-__device__ __forceinline__ void overlap_publish_all(const OverlapArgs& o, int lane, const ChainMap& map) {
+__device__ __forceinline__ void overlap_publish_all(const OverlapArgs& o, int lane, int count, long long first, long long stride) {
     asm volatile("fence.proxy.async;" ::: "memory");
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    for (int i = lane; i < map.count; i += 32)
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(o.epochs + map.at(i)), "r"(o.signal_epoch) : "memory");
+    for (int i = lane; i < count; i += 32)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(o.epochs + first + (long long)i * stride), "r"(o.signal_epoch)
+                     : "memory");
 }
 
 }  // namespace svb

@@ -251,10 +251,6 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     const int wrap0 = (row8 == 0) ? VH : 0;                       // backward-0 neighbour of row 0 is row N - 1
     const int up_off = (row8 == 7) ? (N - V) : N;                 // row below the LAST of this thread's rows wraps to row 0
 
-    const ChainMap map(a.chains, blockIdx.x, gridDim.x);         // the remainder chains go to the last CTAs (svb_common.cuh)
-    const int my_count = map.count;
-    auto chain_at = [&](int i) -> long long { return map.at(i); };
-
     // The epochs of ALL of this CTA's chains are released together when the CTA is done: one gpu-scope release fence
     // (a memory barrier that costs ~0.7 us on a busy SM -- per chain it would eat most of what overlapping wins)
     // followed by one relaxed store per chain.  Call behind a block barrier before which thread 0 -- the thread whose
@@ -267,7 +263,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
             for (int i = lane; i < count; i += 32)
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.epochs + chain_at(i)),
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.epochs + blockIdx.x + (long long)i * gridDim.x),
                              "r"(a.signal_epoch)
                              : "memory");
         }
@@ -304,17 +300,17 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         bulk_g2s(stage + bytes_phi, a.n + chain * 2 * V, bytes_n, &bar[b]);
     };
 
-    if (tid == 0 && my_count > 0) issue_load(chain_at(0), 0, peek_epoch(chain_at(0)));
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, 0, peek_epoch(chain));
 
     int it = 0;
-    for (; it < my_count; ++it) {
-        const long long chain = chain_at(it);
+    for (; chain < a.chains; chain += gridDim.x, ++it) {
         constexpr int b = 0;
         unsigned char* stage = smem_raw + (size_t)b * stage_bytes;
         double* sphi = reinterpret_cast<double*>(stage);
         int32_t* sn0 = reinterpret_cast<int32_t*>(stage + bytes_phi);
         int32_t* sn1 = sn0 + V;
-        const long long next = (it + 1 < my_count) ? chain_at(it + 1) : a.chains;
+        const long long next = chain + gridDim.x;
         const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
         const double half_kappa = kappa / 2;
         const float hk2 = (float)(half_kappa * 1.4426950408889634);                 // decisions are taken in units of ln 2
@@ -589,9 +585,6 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
         if (info.device < 64) per_sm_cache[variant][info.device] = per_sm;
     }
     long long grid = (long long)per_sm * info.sm_count;
-#ifdef SVB_FILT_GRID
-    grid = SVB_FILT_GRID;
-#endif
     if (grid > a.chains) grid = a.chains;
     const FilterConsts fc = make_filter_consts(a.interval_phi, mode == SVB_FILT_EXACT ? 1 : a.W, a.interval_n);
     if (overlap) {

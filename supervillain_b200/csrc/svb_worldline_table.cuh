@@ -86,14 +86,13 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
     };
 
     const int row8 = tid / HN, k = tid - row8 * HN;
-    const ChainMap map(a.chains, blockIdx.x, gridDim.x);
-    if (tid == 0 && map.count > 0) issue_load(map.at(0), OVERLAP ? overlap_peek(a.ov, map.at(0)) : 0u);
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) issue_load(chain, OVERLAP ? overlap_peek(a.ov, chain) : 0u);
     if (!a.kappa_chain) build_table(a.kappa);
 
     int it = 0;
-    for (; it < map.count; ++it) {
-        const long long chain = map.at(it);
-        const long long next = (it + 1 < map.count) ? map.at(it + 1) : a.chains;
+    for (; chain < a.chains; chain += gridDim.x, ++it) {
+        const long long next = chain + gridDim.x;
         uint32_t seen_next = 0;
         if (OVERLAP && tid == 0 && next < a.chains) seen_next = overlap_peek(a.ov, next);      // lands during the sweep
         const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
@@ -293,7 +292,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
     if (tid == 0) bulk_wait0();
     if (OVERLAP) {
         __syncthreads();                                   // every store has completed, every record is written
-        if (warp == 0) overlap_publish_all(a.ov, lane, map);
+        if (warp == 0) overlap_publish_all(a.ov, lane, it, blockIdx.x, gridDim.x);
     }
 }
 
