@@ -165,7 +165,7 @@ int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
  *                 ACCEPTANCE.  In a sequence of steps pass obs_in = the previous step's record: every record is then
  *                 complete one launch later, with exactly the bits the separate pass would have produced; the last
  *                 state's columns come from svb_villain_observables.
- * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64}; anything else returns SVB_E_UNSUPPORTED (use
+ * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64, 128}; anything else returns SVB_E_UNSUPPORTED (use
  * svb_villain_sweep).  A kernel launched normally after these waits for all of them, as usual.
  */
 #define SVB_OVERLAP_PREDECESSOR 1
@@ -254,7 +254,7 @@ int svb_worldline_sweep(int32_t* m, int32_t* v,
                         void* stream);
 
 /*
- * The worldline sweeps (W = 1, Philox draws, N in {16, 32, 64}; interval 1 or 2 for VORTEX / COEXACT) as OVERLAPPED
+ * The worldline sweeps (W = 1, Philox draws, N in {16, 32, 64, 128}; interval 1 or 2 for VORTEX / COEXACT) as OVERLAPPED
  * launches: the same protocol as svb_villain_sweep_overlapped (epochs, wait_epoch / signal_epoch,
  * SVB_OVERLAP_PREDECESSOR); `obs` is the full record of the state after the sweeps.
  */
@@ -294,7 +294,8 @@ int svb_form_op(int op, int degree, int dtype, const void* in, void* out,
 
 /*
  * Spin_Spin.Villain (observable/spin.py:28-42): C[dx] = N^-2 sum_x e^{-i phi_x} e^{+i phi_{x-dx}},
- * out (chains, N, N, 2) f64 (re, im).  Direct O(N^4) evaluation, intended for N <= 64.
+ * out (chains, N, N, 2) f64 (re, im), 16-byte aligned.  FFT for power-of-two N from 16 to 4096 (`out` is the workspace for
+ * N >= 128), direct O(N^4) evaluation out of shared memory for the other N that fit it.
  */
 int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N,
                           double* out, void* stream);
@@ -304,7 +305,7 @@ int svb_villain_spin_spin(const void* phi, int phi_dtype, int64_t chains, int N,
  *   SVB_CORR_SPIN     field = phi (chains,1,N,N) f64|f32, s = exp(i phi)          Spin_Spin.Villain
  *   SVB_CORR_WINDING  field = n   (chains,2,N,N) i32,     s = dn                  Winding_Winding.Villain (winding.py:77-86)
  *   SVB_CORR_VORTEX   field = v   (chains,1,N,N) i32,     s = exp(2 pi i v / W)   Vortex_Vortex.Worldline (vortex.py:22-37)
- * out (chains, N, N, 2) f64 (re, im).  Direct evaluation, N <= 64.
+ * out (chains, N, N, 2) f64 (re, im).  As svb_villain_spin_spin: FFT for power-of-two N in [16, 4096], else the direct sum.
  */
 #define SVB_CORR_SPIN    0
 #define SVB_CORR_WINDING 1
