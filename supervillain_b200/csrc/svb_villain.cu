@@ -1854,6 +1854,25 @@ extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t ch
                 default: return launch_villain_link_smem<64, 3>(la, n_sweeps, st, info);
             }
         }
+        if (rng_mode == SVB_RNG_PHILOX && !dS_out && path != SVB_PATH_GLOBAL && N == 128 && ((uintptr_t)phi % 16 == 0) &&
+            ((uintptr_t)n % 16 == 0)) {
+            // strips of 32 rows (svb_villain_link.cuh): counters by atomics into a zeroed record, state columns afterwards
+            LinkArgs la;
+            la.phi = reinterpret_cast<const double*>(phi); la.n = n; la.chains = chains; la.N = N; la.kappa = kappa; la.kappa_chain = kappa_chain;
+            la.W = W; la.interval = interval; la.seed = seed; la.chain0 = chain0; la.obs = obs; la.sweep = sweep0;
+            la.inj_u = nullptr; la.inj_c = nullptr; la.dS_out = nullptr;
+            DeviceInfo info;
+            int rc = get_device_info(info);
+            if (rc) return rc;
+            if (obs) {
+                villain_zero_counters_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains);
+                SVB_CUDA_TRY(cudaGetLastError());
+            }
+            rc = launch_villain_link_strip<128, 32, 2>(la, n_sweeps, st, info);
+            if (rc) return rc;
+            if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
+            return SVB_OK;
+        }
         const long long blocks = chains * ((2 * V + 255) / 256);
         if (blocks > 0x7fffffffLL) return fail(SVB_E_SHAPE, "svb_villain_decoupled: too many blocks");
         if (obs) {

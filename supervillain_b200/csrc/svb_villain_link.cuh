@@ -176,3 +176,146 @@ static int launch_villain_link_smem(const LinkArgs& a, int n_sweeps, cudaStream_
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Chains beyond one SM's shared memory (L = 128): the same update on STRIPS of ROWS rows.  Link proposals are independent and
+// phi is read only, so a strip needs nothing from its neighbours but the phi row below it (loaded as row ROWS of the strip);
+// work item = (chain, strip).  The per-chain records cannot be finished inside one CTA any more: the acceptance counters
+// are added atomically to a zeroed record, the state columns come from svb_villain_observables afterwards.
+// ------------------------------------------------------------------------------------------
+template <int NT, int ROWS, int MINB>
+__global__ void __launch_bounds__(4 * NT, MINB) villain_link_strip_kernel(const __grid_constant__ LinkArgs a, int n_sweeps) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int N = NT, V = N * N, HN = N / 2, T = 4 * NT, VS = ROWS * N, PER = ROWS / 8, STRIPS = N / ROWS;
+    static_assert(ROWS % 8 == 0 && N % ROWS == 0 && ROWS < N, "villain_link_strip_kernel: strips of whole row groups");
+    constexpr uint32_t bytes_phi = VS * sizeof(double), bytes_row = N * sizeof(double), bytes_n = VS * sizeof(int32_t);
+    const int tid = threadIdx.x, lane = tid & 31;
+    double* sphi = reinterpret_cast<double*>(smem_raw);           // ROWS + 1 rows
+    int32_t* sn0 = reinterpret_cast<int32_t*>(smem_raw + bytes_phi + bytes_row);
+    int32_t* sn1 = sn0 + VS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sn1 + VS);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int row8 = tid / HN, k = tid - row8 * HN;
+    const uint32_t K = (uint32_t)(2 * a.interval);
+    const long long items = a.chains * STRIPS;
+    auto issue_load = [&](long long item) {
+        const long long chain = item / STRIPS;
+        const int r0 = (int)(item - chain * STRIPS) * ROWS;
+        mbar_expect_tx(bar, bytes_phi + bytes_row + 2 * bytes_n);
+        bulk_g2s(sphi, a.phi + chain * V + (long long)r0 * N, bytes_phi, bar);
+        bulk_g2s(sphi + VS, a.phi + chain * V + (long long)((r0 + ROWS) % N) * N, bytes_row, bar);      // the row below the strip
+        bulk_g2s(sn0, a.n + chain * 2 * V + (long long)r0 * N, bytes_n, bar);
+        bulk_g2s(sn1, a.n + chain * 2 * V + V + (long long)r0 * N, bytes_n, bar);
+    };
+    long long item = blockIdx.x;
+    if (tid == 0 && item < items) issue_load(item);
+
+    for (int it = 0; item < items; item += gridDim.x, ++it) {
+        const long long next = item + gridDim.x;
+        const long long chain = item / STRIPS;
+        const int r0 = (int)(item - chain * STRIPS) * ROWS;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double m2pik = __dmul_rn(-SVB_TWO_PI, kappa);
+        const double* pp = sphi + row8 * N + 2 * k;
+        const double* pp_r = sphi + row8 * N + ((2 * k + 2) & (N - 1));
+        int32_t* pn0 = sn0 + row8 * N + 2 * k;
+        int32_t* pn1 = sn1 + row8 * N + 2 * k;
+        mbar_wait(bar, (uint32_t)(it & 1));
+
+        int n_acc = 0;
+        double sum_A_all = 0.0;
+        RefineCtx rc;
+        rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain;
+#pragma unroll 1
+        for (int s = 0; s < n_sweeps; ++s) {
+            rc.sweep = a.sweep + (unsigned long long)s;
+            float sum_A = 0.0f;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int o = 8 * N * q;
+                const double2 pc = *reinterpret_cast<const double2*>(pp + o);
+                const double2 pu = *reinterpret_cast<const double2*>(pp + o + N);
+                const double pr = pp_r[o];
+                const double dphi[4] = {__dsub_rn(pu.x, pc.x), __dsub_rn(pc.y, pc.x), __dsub_rn(pu.y, pc.y), __dsub_rn(pr, pc.y)};
+                int2 m0 = *reinterpret_cast<const int2*>(pn0 + o), m1 = *reinterpret_cast<const int2*>(pn1 + o);
+                int nl[4] = {m0.x, m1.x, m0.y, m1.y};
+                const int site_e = (r0 + row8 + 8 * q) * N + 2 * k;                   // global site: the draws do not know about strips
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t site = (uint32_t)(site_e + h);
+                    const Philox4 p = philox_site(a.seed, rc.chain, rc.sweep, site, STREAM_VILLAIN_LINK);
+#pragma unroll
+                    for (int mu = 0; mu < 2; ++mu) {
+                        const int j = 2 * h + mu;
+                        const uint64_t pz = (uint64_t)(mu ? p.y : p.x) * (uint64_t)K;
+                        const int idx = (int)(pz >> 32);
+                        const uint32_t f = (uint32_t)pz;
+                        const int c = a.W * ((idx < a.interval) ? idx - a.interval : idx - a.interval + 1);
+                        const double t1 = __dmul_rn(m2pik, (double)c);                // (link.py:83-86), numpy's order
+                        const double t2 = __dsub_rn(__dsub_rn(dphi[j], __dmul_rn(SVB_TWO_PI, (double)nl[j])),
+                                                    __dmul_rn(3.141592653589793116, (double)c));
+                        const double dS = __dmul_rn(t1, t2);
+                        double prob;
+                        const double u_mid = (__hiloint2double(0x43300000, (int)f) - 4503599627370495.5) * 2.3283064365386963e-10;
+                        int r = (f >= 65536u) ? metropolis_log_filter(dS, u_mid, 7.62939453125e-06f, prob) : -1;
+                        if (r < 0) {
+                            LinkProposal lp;
+                            lp.dS = dS; lp.lu.f = f; lp.lu.c0 = site; lp.lu.word = (uint32_t)mu; lp.rc = rc;
+                            prob = exp_clipped(-dS);
+                            r = villain_link_exact_decision(lp) ? 1 : 0;
+                        }
+                        sum_A += (float)prob;
+                        n_acc += r;
+                        nl[j] += r ? c : 0;
+                    }
+                }
+                *reinterpret_cast<int2*>(pn0 + o) = make_int2(nl[0], nl[2]);
+                *reinterpret_cast<int2*>(pn1 + o) = make_int2(nl[1], nl[3]);
+            }
+            sum_A_all += (double)sum_A;
+        }
+        if (a.obs) {                                                   // one atomic pair per warp
+            const double wa = warp_sum(sum_A_all);
+            const int wn = __reduce_add_sync(0xffffffffu, n_acc);
+            if (lane == 0) {
+                atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, (double)wn);
+                atomicAdd(a.obs + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, wa);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(a.n + chain * 2 * V + (long long)r0 * N, sn0, bytes_n);
+            bulk_s2g(a.n + chain * 2 * V + V + (long long)r0 * N, sn1, bytes_n);
+            bulk_commit();
+            bulk_wait_read0();
+            if (next < items) issue_load(next);
+        }
+    }
+    if (tid == 0) bulk_wait0();
+}
+
+template <int NT, int ROWS, int MINB>
+static int launch_villain_link_strip(const LinkArgs& a, int n_sweeps, cudaStream_t stream, const DeviceInfo& info) {
+    auto kern = villain_link_strip_kernel<NT, ROWS, MINB>;
+    const size_t smem = (size_t)(ROWS + 1) * NT * sizeof(double) + (size_t)2 * ROWS * NT * sizeof(int32_t) + 16;
+    static int per_sm_cache[64];
+    int per_sm = (info.device < 64) ? per_sm_cache[info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "link strip kernel does not fit an SM at N=%d", NT);
+        if (info.device < 64) per_sm_cache[info.device] = per_sm;
+    }
+    const long long items = a.chains * (NT / ROWS);
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a, n_sweeps);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}

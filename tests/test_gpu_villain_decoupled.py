@@ -46,7 +46,7 @@ def test_injected_rng_reproduces_reference_chains(golden_villain_decoupled, path
 
 
 @pytest.mark.parametrize('kind', KINDS)
-@pytest.mark.parametrize('N,W,kappa,interval', [(4, 1, 0.5, 1), (5, 2, 0.3, 2), (8, 1, 0.1, 1), (16, 3, 0.2, 1), (32, 1, 0.5, 2), (64, 2, 0.4, 3)])
+@pytest.mark.parametrize('N,W,kappa,interval', [(4, 1, 0.5, 1), (5, 2, 0.3, 2), (8, 1, 0.1, 1), (16, 3, 0.2, 1), (32, 1, 0.5, 2), (64, 2, 0.4, 3), (128, 1, 0.6, 1)])
 def test_philox_mode_matches_oracle_replay(kind, N, W, kappa, interval):
     """Production RNG: the oracle regenerates the kernels' Philox draws and runs the restated reference algorithm."""
     chains, sweeps, seed = 3, 3, 77

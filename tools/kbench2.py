@@ -138,3 +138,18 @@ if 'wl128' in which:
         k[0] += 1
         ops.worldline_sweep(m, v, 0.5, mode='joint', seed=1, sweep0=k[0], obs=obs, path='global')
     report('worldline joint L=128 x 512 chains, global path', CH * N * N, 24, timeit(g, n=5))
+if 'dec128' in which:
+    N, CH = 128, 1024
+    S = svb.Villain(svb.Lattice2D(N), 0.5)
+    phi, n = svb.BatchedEnsemble(S, CH)._start('hot', 1)
+    obs = torch.zeros((CH, ops.VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for kind, sites in (('site', N * N), ('link', 2 * N * N), ('exact', N * N)):
+        k = [0]
+        def f():
+            k[0] += 1
+            ops.villain_decoupled(kind, phi, n, 0.5, seed=1, sweep0=k[0], obs=obs)
+        report(f'villain {kind} update L=128 x 1024 chains', CH * sites, (24 if kind == 'link' else 32) * N * N / sites, timeit(f, n=5))
+if 'taxi' in which:
+    N, CH = 32, 256
+    links = torch.randn((CH, 2, N, N), dtype=torch.float64, device='cuda') * 0.3
+    report('taxicab correlator (Vortex_Vortex.Villain) L=32 x 256 chains: N^4 exponentials per chain', CH * N ** 4, 0.016, timeit(lambda: ops.taxicab_correlator('vortex', links, 0.5), n=2, reps=2))
