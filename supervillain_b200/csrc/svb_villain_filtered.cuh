@@ -408,6 +408,18 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     } else if (MODE == SVB_FILT_SITE) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) digA[i] = digB[i] = 0;            // word B is the uniform's leading bits as it stands
+                    } else if (UNIT) {
+                        // four successive multiply-highs by 3 == one by 81: hi = 27 d0 + 9 d1 + 3 d2 + d3, lo = the remainder
+                        // (one quarter-rate IMAD.WIDE instead of a chain of four; 28.40 -> 28.24 us per step)
+                        const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
+                        fA = (uint32_t)pa; fB = (uint32_t)pb;
+                        uint32_t ia = (uint32_t)(pa >> 32), ib = (uint32_t)(pb >> 32);
+                        digA[0] = (int)((ia * 2428u) >> 16); ia -= 27u * (uint32_t)digA[0];
+                        digB[0] = (int)((ib * 2428u) >> 16); ib -= 27u * (uint32_t)digB[0];
+                        digA[1] = (int)((ia * 7282u) >> 16); ia -= 9u * (uint32_t)digA[1];
+                        digB[1] = (int)((ib * 7282u) >> 16); ib -= 9u * (uint32_t)digB[1];
+                        digA[2] = (int)((ia * 21846u) >> 16); digA[3] = (int)(ia - 3u * (uint32_t)digA[2]);
+                        digB[2] = (int)((ib * 21846u) >> 16); digB[3] = (int)(ib - 3u * (uint32_t)digB[2]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
