@@ -201,6 +201,7 @@ class BatchedEnsemble:
         self.steps = steps
         self.sweeps_per_step = sweeps_per_step
         self.generator = generator
+        self.keep_every = int(keep_every)
         self.index = sweeps_per_step * (1 + np.arange(steps))
         if kept:
             names = ('phi', 'n') if self.kind == 'Villain' else ('m', 'v')
@@ -243,7 +244,8 @@ class BatchedEnsemble:
             raise ValueError('nothing to save: generate first')
         blob = np.frombuffer(pickle.dumps((self.Action, self.__dict__.get('generator'))), dtype=np.uint8)
         arrays = dict(field0=self.fields[0].cpu().numpy(), field1=self.fields[1].cpu().numpy(), record=self.record, index=self.index,
-                      meta=np.array([self.chains, self.chain0, self.sweeps_per_step, self.steps], dtype=np.int64), state=blob)
+                      meta=np.array([self.chains, self.chain0, self.sweeps_per_step, self.steps, self.__dict__.get('keep_every', 0)],
+                                    dtype=np.int64), state=blob)
         if self.__dict__.get('kappa_chain') is not None:
             arrays['kappa_chain'] = self.kappa_chain.cpu().numpy()
         for k, v in self.__dict__.get('configuration', {}).items():
@@ -256,12 +258,14 @@ class BatchedEnsemble:
         """A BatchedEnsemble as `save` left it (fields back on the device), ready for `continue_from`."""
         with np.load(path, allow_pickle=False) as z:
             action, generator = pickle.loads(z['state'].tobytes())
-            chains, chain0, sweeps_per_step, steps = (int(x) for x in z['meta'])
+            chains, chain0, sweeps_per_step, steps = (int(x) for x in z['meta'][:4])
+            keep_every = int(z['meta'][4]) if len(z['meta']) > 4 else 0       # checkpoints of earlier builds have four entries
             e = cls(action, chains, device=device, chain0=chain0)
             e.fields = tuple(torch.from_numpy(z[k]).to(e.device) for k in ('field0', 'field1'))
             e.dtype = e.fields[0].dtype if e.kind == 'Villain' else e.dtype
             e.record, e.index = z['record'], z['index']
             e.steps, e.sweeps_per_step, e.generator = steps, sweeps_per_step, generator
+            e.keep_every = keep_every
             e.kappa_chain = torch.from_numpy(z['kappa_chain']).to(e.device) if 'kappa_chain' in z.files else None
             cfg = {k[len('configuration_'):]: z[k] for k in z.files if k.startswith('configuration_')}
             if cfg:
@@ -270,6 +274,54 @@ class BatchedEnsemble:
         kappa = action.kappa if e.kappa_chain is None else e.kappa_chain.cpu().numpy()[:, None]
         e.observables = (villain_inline_values if e.kind == 'Villain' else worldline_inline_values)(e.record, N, kappa)
         return e
+
+    def to_reference(self, chain, supervillain=None):
+        """One chain as an ensemble OF THE REFERENCE PACKAGE, so that everything downstream of generation -- `to_h5` in the
+        reference's HDF5 layout (supervillain/h5/), `Ensemble.from_h5`, the observables and `analysis/` --
+        consumes it unchanged.  Needs kept configurations (`generate(..., keep_every=k)`) and the reference importable
+        (pass the module as `supervillain` or have it on sys.path); nothing of the reference is used on the sampling path.
+
+        The result is what `supervillain.Ensemble(S).generate(draws, KeepEvery(k * sweeps_per_step, G))` stores
+        (ensemble.py:74-78, 94-95): `configuration.fields` = the field columns (phi float64 / integer fields int64, as Forms)
+        plus the inline scalar observables of the kept draws under the reference's observable names, so the reference reads
+        them instead of measuring again (observable/observable.py:49-54); `index` counts sweeps, `index_stride` is the
+        sweeps between kept draws, `weight` is one."""
+        if 'configuration' not in self.__dict__:
+            raise ValueError('no configurations were kept; call generate(..., keep_every=k)')
+        chain = int(chain)
+        if not 0 <= chain < self.chains:
+            raise IndexError(f'chain {chain} is not one of {self.chains}')
+        if supervillain is None:
+            import importlib
+            supervillain = importlib.import_module('supervillain')
+        sv = supervillain
+        A = self.Action
+        L = sv.lattice.Lattice2D(A.Lattice.N)
+        kappa = float(A.kappa if self.__dict__.get('kappa_chain') is None else self.kappa_chain[chain].item())
+        S = getattr(sv.action, self.kind)(L, kappa, int(A.W))
+        names = ('phi', 'n') if self.kind == 'Villain' else ('m', 'v')
+        draws = self.configuration[names[0]].shape[1]
+        k = self.__dict__.get('keep_every', 0) or self.steps // max(draws, 1)
+        kept = k * (1 + np.arange(draws)) - 1                     # the steps whose configurations were kept
+        cfgs = S.configurations(draws)
+        for name in names:
+            column = cfgs.fields[name]
+            for t in range(draws):
+                column[t] = self.configuration[name][chain, t]     # Batch.__setitem__ checks the cast is lossless (batch.py:206-227)
+        inline = {}
+        for name, values in self.observables.items():
+            v = np.asarray(values)[chain]
+            if v.shape[0] != self.steps:
+                continue
+            inline[name] = sv.batch.Batch(np.ascontiguousarray(v[kept]))
+        cfgs |= inline
+        E = sv.Ensemble(S).from_configurations(cfgs)
+        stride = k * self.sweeps_per_step
+        E.index_stride = stride
+        E.index = sv.batch.Batch(np.asarray(self.index)[kept].astype(np.int64))
+        E.weight = sv.batch.Batch(np.ones(draws))
+        E.start = 'cold'
+        return E
 
     def __len__(self):
         """The number of recorded samples per chain (what `len(Ensemble)` is for the reference's single chain)."""

@@ -53,3 +53,28 @@ def test_save_load_continue_equals_the_uninterrupted_run(kind, N, tmp_path):
     np.testing.assert_array_equal(b.record, resumed.record)
     with pytest.raises(ValueError):
         svb.BatchedEnsemble.continue_from(svb.BatchedEnsemble(S3, chains), 2)
+
+
+def test_kept_configurations_line_up_with_their_inline_columns(tmp_path):
+    """What `BatchedEnsemble.to_reference` relies on: draw t of the kept configurations is the state after step
+    keep_every * (t + 1), and row keep_every * (t + 1) - 1 of every inline column describes exactly that state;
+    `keep_every` survives a checkpoint."""
+    N, chains, keep = 16, 9, 3
+    S = svb.Villain(svb.Lattice2D(N), 0.6)
+    G = svb.generator.villain.NeighborhoodUpdate(S, seed=4)
+    E = svb.BatchedEnsemble(S, chains).generate(12, G, 'hot', start_seed=1, sweeps_per_step=2, keep_every=keep)
+    assert E.keep_every == keep and E.configuration['phi'].shape == (chains, 4, 1, N, N)
+    assert E.configuration['n'].dtype == np.int64
+    kept = keep * (1 + np.arange(4)) - 1
+    for t, row in enumerate(kept):
+        phi = torch.from_numpy(E.configuration['phi'][:, t]).cuda()
+        n = torch.from_numpy(E.configuration['n'][:, t]).to(device='cuda', dtype=torch.int32)
+        obs = svb.ops.villain_observables(phi, n, 0.6).cpu().numpy()
+        np.testing.assert_allclose(E.ActionDensity[:, row], obs[:, VOBS_ACTION] / (N * N), rtol=1e-12)
+        np.testing.assert_array_equal(E.record[:, row, 1:4], obs[:, 1:4])
+    assert torch.equal(torch.from_numpy(E.configuration['phi'][:, -1]).cuda(), E.fields[0])
+    path = tmp_path / 'kept.npz'
+    E.save(path)
+    L = svb.BatchedEnsemble.load(path)
+    assert L.keep_every == keep
+    np.testing.assert_array_equal(L.configuration['n'], E.configuration['n'])

@@ -184,3 +184,57 @@ def test_no_cpu_fallback_for_the_overlapped_and_decoupled_paths():
         ops.villain_cohomology(phi, n, 0.5)
     with pytest.raises(ValueError):
         ops.WorldlineOverlappedSweeps(n, n[:, :1].contiguous(), 0.5)
+
+
+def test_batched_ensemble_hands_a_chain_to_the_reference_package(tmp_path):
+    """`BatchedEnsemble.to_reference`: one chain becomes a reference `Ensemble` (the object `to_h5` writes, SURVEY App. C);
+    its field columns are the kept draws, and the inline columns are exactly what the reference measures from those fields
+    (so the short-circuit of observable/observable.py:49-54 returns the same numbers).  Build container only."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip('reference tree not mounted')
+    sv = refimport.import_reference()
+    import supervillain_b200 as svb
+    from supervillain_b200._lib import VOBS_ACTION, VOBS_COUNT, VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1
+    from supervillain_b200.generator.villain import NeighborhoodUpdate, villain_inline_values
+    from oracle import villain_np as V
+    N, chains, steps, keep, kappa = 6, 3, 6, 2, 0.45
+    rng = np.random.default_rng(5)
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    E = svb.BatchedEnsemble(S, chains, device='cpu')
+    phi = rng.uniform(-np.pi, np.pi, (chains, steps, 1, N, N))
+    n = rng.integers(-2, 3, (chains, steps, 2, N, N))
+    rec = np.zeros((chains, steps, VOBS_COUNT))
+    for c in range(chains):
+        for t in range(steps):
+            rec[c, t, VOBS_ACTION] = V.action(phi[c, t], n[c, t], kappa)
+            rec[c, t, VOBS_SUM_DN2] = V.winding_squared(n[c, t]) * N * N
+            rec[c, t, VOBS_WRAP0], rec[c, t, VOBS_WRAP1] = V.torus_wrapping(n[c, t])
+    kept = keep * (1 + np.arange(steps // keep)) - 1
+    E.record, E.steps, E.sweeps_per_step, E.keep_every = rec, steps, 5, keep
+    E.index = 5 * (1 + np.arange(steps))
+    E.generator = NeighborhoodUpdate(S)
+    E.configuration = {'phi': phi[:, kept], 'n': n[:, kept].astype(np.int64)}
+    E.observables = villain_inline_values(rec, N, kappa)
+    with pytest.raises(IndexError):
+        E.to_reference(chains, supervillain=sv)
+    R = E.to_reference(1, supervillain=sv)
+    assert type(R).__module__.startswith('supervillain') and len(R.configuration) == len(kept)
+    assert R.Action.kappa == kappa and R.Action.Lattice.nx == N and R.index_stride == 10
+    assert list(sv.batch.Batch.as_array(R.index)) == [10, 20, 30]
+    got_phi, got_n = (sv.batch.Batch.as_array(R.configuration.fields[k]) for k in ('phi', 'n'))
+    assert got_phi.dtype == np.float64 and (got_phi == phi[1, kept]).all()
+    assert got_n.dtype == np.int64 and (got_n == n[1, kept]).all()
+    cfg0 = R.configuration[0]
+    assert type(cfg0['phi']).__name__ == 'Form' and cfg0['n'].degree == 1
+    # the same fields without inline columns: the reference measures for itself
+    bare = sv.Ensemble(R.Action).from_configurations(sv.configurations.Configurations(
+        {k: R.configuration.fields[k] for k in ('phi', 'n')}))
+    for name in ('ActionDensity', 'InternalEnergyDensity', 'WindingSquared', 'TorusWrapping', 'WrappingSquared'):
+        inline, measured = np.asarray(getattr(R, name)), np.asarray(getattr(bare, name))
+        assert inline.shape == measured.shape, name
+        assert np.allclose(inline, measured, rtol=1e-12, atol=1e-12), name
+    # a kappa scan hands each chain its own coupling
+    import torch
+    E.kappa_chain = torch.tensor([0.3, 0.6, 0.9], dtype=torch.float64)
+    assert E.to_reference(2, supervillain=sv).Action.kappa == 0.9
