@@ -238,3 +238,49 @@ def test_batched_ensemble_hands_a_chain_to_the_reference_package(tmp_path):
     import torch
     E.kappa_chain = torch.tensor([0.3, 0.6, 0.9], dtype=torch.float64)
     assert E.to_reference(2, supervillain=sv).Action.kappa == 0.9
+
+
+def test_batched_worldline_ensemble_hands_a_chain_to_the_reference_package():
+    """The worldline side of `to_reference`: integer m, v columns (int64 Forms, delta m = 0 so the reference's action accepts
+    them, worldline.py:92-93) and the inline columns equal to the reference's own worldline measurements."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip('reference tree not mounted')
+    sv = refimport.import_reference()
+    import supervillain_b200 as svb
+    from supervillain_b200._lib import WOBS_COUNT, WOBS_SUM_DF2, WOBS_SUM_F2, WOBS_WRAP0, WOBS_WRAP1
+    from supervillain_b200.generator.worldline import PlaquetteUpdate, worldline_inline_values
+    from oracle import worldline_np as WL
+    from oracle import lattice_np as LT
+    N, chains, steps, kappa, W = 6, 2, 4, 0.7, 1
+    rng = np.random.default_rng(11)
+    S = svb.Worldline(svb.Lattice2D(N), kappa)
+    E = svb.BatchedEnsemble(S, chains, device='cpu')
+    m = np.zeros((chains, steps, 2, N, N), dtype=np.int64)
+    v = rng.integers(-2, 3, (chains, steps, 1, N, N))
+    rec = np.zeros((chains, steps, WOBS_COUNT))
+    for c in range(chains):
+        for t in range(steps):
+            m[c, t], _ = WL.hot_start(rng, N)
+            m[c, t, 0, :, 0] += 1                                   # one unit of wrapping in direction 0 keeps delta m = 0
+            assert WL.valid(m[c, t])
+            f = WL.links(m[c, t], v[c, t], W)
+            rec[c, t, WOBS_SUM_F2] = (f ** 2).sum()
+            rec[c, t, WOBS_SUM_DF2] = (LT.d1(f) ** 2).sum()
+            rec[c, t, WOBS_WRAP0], rec[c, t, WOBS_WRAP1] = m[c, t, 0].sum(), m[c, t, 1].sum()
+    E.record, E.steps, E.sweeps_per_step, E.keep_every = rec, steps, 1, 1
+    E.index = 1 + np.arange(steps)
+    E.generator = PlaquetteUpdate(S)
+    E.configuration = {'m': m, 'v': v.astype(np.int64)}
+    E.observables = worldline_inline_values(rec, N, kappa)
+    R = E.to_reference(1, supervillain=sv)
+    assert type(R.Action).__name__ == 'Worldline' and R.index_stride == 1
+    cfg = R.configuration[2]
+    assert cfg['m'].degree == 1 and cfg['m'].dtype == np.int64 and (np.asarray(cfg['v']) == v[1, 2]).all()
+    bare = sv.Ensemble(R.Action).from_configurations(sv.configurations.Configurations(
+        {k: R.configuration.fields[k] for k in ('m', 'v')}))
+    for name in ('ActionDensity', 'InternalEnergyDensity', 'InternalEnergyDensitySquared', 'WindingSquared', 'TorusWrapping',
+                 'WrappingSquared'):
+        inline, measured = np.asarray(getattr(R, name)), np.asarray(getattr(bare, name))
+        assert inline.shape == measured.shape, name
+        assert np.allclose(inline, measured, rtol=1e-12, atol=1e-12), name
