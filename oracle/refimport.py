@@ -29,5 +29,9 @@ def import_reference():
                 sys.path.append(_STUBS)  # appended: a real install always wins
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    os.environ.setdefault('NUMBA_CACHE_DIR', '/tmp/svb_numba_cache')
+    if 'NUMBA_CACHE_DIR' not in os.environ:
+        # the reference tree is read-only, so numba needs a cache directory elsewhere; a fresh one per process, because a
+        # cache written by another process has failed to load here ("NRT_adapt_ndarray_to_python: descr is NULL")
+        import tempfile
+        os.environ['NUMBA_CACHE_DIR'] = tempfile.mkdtemp(prefix='svb_numba_cache_')
     return importlib.import_module('supervillain')

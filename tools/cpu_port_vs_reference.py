@@ -4,12 +4,10 @@ kind "port") beside the UNMODIFIED reference generator on the same core and shap
 The reference cannot travel to the GPU box, so this is where the two are compared."""
 import os
 import sys
-import tempfile
 import time
 
 import numpy as np
 
-os.environ['NUMBA_CACHE_DIR'] = tempfile.mkdtemp(prefix='svb_numba_')     # a fresh JIT: a cache written by another process has failed to load here
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import refimport, villain_np as V                                                   # noqa: E402
