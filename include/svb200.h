@@ -142,6 +142,18 @@ int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
                             double* obs, uint8_t* accept_mask, double* dS_out, void* stream);
 
 /*
+ * svb_villain_sweep_tiled for a caller that owns both buffer pairs and exchanges their roles (a resident ensemble stepping
+ * one sweep at a time; the reference's NeighborhoodUpdate.step, neighborhood.py:59-137, returns fresh arrays anyway): after
+ * an odd number of FAST sweeps the state is left in (phi_ws, n_ws) and *state_in_workspace = 1 (host int, written before
+ * the call returns), sparing the copy back; otherwise the state is in (phi, n) and *state_in_workspace = 0.
+ */
+int svb_villain_sweep_tiled_swap(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws,
+                                 int64_t chains, int N, double kappa, const double* kappa_chain, int W,
+                                 double interval_phi, int interval_n, int n_sweeps,
+                                 uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode,
+                                 double* obs, int* state_in_workspace, void* stream);
+
+/*
  * The same sweeps as OVERLAPPED launches: a launch may begin while the previous launch in the stream is still running
  * (programmatic dependent launch), so the ramp-up of one sweep hides under the tail of the one before -- at config 2 a
  * quarter of a non-overlapped step.  Data dependencies are tracked per chain instead of per kernel:

@@ -2014,10 +2014,13 @@ extern "C" int svb_villain_sweep_host(void* phi_host, int phi_dtype, int32_t* n_
 
 // Tiled single-pass sweeps for lattices too large for shared memory (N a multiple of 32): ping-pong between the fields
 // and a caller-provided workspace of the same size; the result always ends in (phi, n).
-extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws, int64_t chains, int N, double kappa,
-                                       const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
-                                       uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode, double* obs,
-                                       uint8_t* accept_mask, double* dS_out, void* stream) {
+// allow_swap: an odd number of sweeps on the fast path may END in the workspace (*state_in_workspace = 1) instead of
+// being copied back -- for callers that own both buffer pairs and exchange their roles (svb_villain_sweep_tiled_swap).
+static int villain_sweep_tiled_impl(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws, int64_t chains, int N, double kappa,
+                                    const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
+                                    uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode, double* obs,
+                                    uint8_t* accept_mask, double* dS_out, void* stream, bool allow_swap, int* state_in_workspace) {
+    if (state_in_workspace) *state_in_workspace = 0;
     if (!phi || !n || !phi_ws || !n_ws) return fail(SVB_E_NULL, "svb_villain_sweep_tiled: fields and workspace are required");
     if (chains < 0 || N < kTile || (N % kTile) != 0) return fail(SVB_E_SHAPE, "svb_villain_sweep_tiled: N=%d must be a multiple of %d", N, kTile);
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_tiled: kappa must be positive");
@@ -2043,12 +2046,14 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
     // per-colour global path (330 vs 385 us for a config-4 shard); the fp64 kernels (STRICT, debug outputs) keep the latter.
     const bool odd = (n_sweeps & 1) != 0;
 #ifndef SVB_NO_FILTERED_KERNEL
-    const bool copy_back = odd && arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out;
+    const bool all_tiled = odd && arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out;
 #else
-    const bool copy_back = false;
+    const bool all_tiled = false;
 #endif
-    const int n_tiled = copy_back ? n_sweeps : (n_sweeps & ~1);
-    const bool tail_global = odd && !copy_back;
+    const bool copy_back = all_tiled && !allow_swap;
+    const int n_tiled = all_tiled ? n_sweeps : (n_sweeps & ~1);
+    const bool tail_global = odd && !all_tiled;
+    if (all_tiled && allow_swap && state_in_workspace) *state_in_workspace = 1;
     if (obs) {
         villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains, 0);
         SVB_CUDA_TRY(cudaGetLastError());
@@ -2099,4 +2104,24 @@ extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int3
         if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
     }
     return SVB_OK;
+}
+
+extern "C" int svb_villain_sweep_tiled(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws, int64_t chains, int N, double kappa,
+                                       const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
+                                       uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode, double* obs,
+                                       uint8_t* accept_mask, double* dS_out, void* stream) {
+    return villain_sweep_tiled_impl(phi, n, phi_ws, n_ws, chains, N, kappa, kappa_chain, W, interval_phi, interval_n, n_sweeps, seed,
+                                    sweep0, chain0, arith_mode, obs, accept_mask, dS_out, stream, false, nullptr);
+}
+
+// The same sweeps for a caller that owns both buffer pairs: after an odd number of sweeps on the fast path the state is
+// left in (phi_ws, n_ws) and *state_in_workspace = 1 -- no copy back (two device-to-device copies of the whole state, a
+// third of a single-sweep call at L=4096); otherwise the state is in (phi, n) and *state_in_workspace = 0.
+extern "C" int svb_villain_sweep_tiled_swap(void* phi, int32_t* n, void* phi_ws, int32_t* n_ws, int64_t chains, int N, double kappa,
+                                            const double* kappa_chain, int W, double interval_phi, int interval_n, int n_sweeps,
+                                            uint64_t seed, uint64_t sweep0, uint64_t chain0, int arith_mode, double* obs,
+                                            int* state_in_workspace, void* stream) {
+    if (!state_in_workspace) return fail(SVB_E_NULL, "svb_villain_sweep_tiled_swap: state_in_workspace is required");
+    return villain_sweep_tiled_impl(phi, n, phi_ws, n_ws, chains, N, kappa, kappa_chain, W, interval_phi, interval_n, n_sweeps, seed,
+                                    sweep0, chain0, arith_mode, obs, nullptr, nullptr, stream, true, state_in_workspace);
 }

@@ -183,6 +183,12 @@ class BatchedEnsemble:
             except NotImplementedError:
                 overlapped = None
         scratch = torch.empty((self.chains, nobs), dtype=torch.float64, device=self.device) if overlapped is not None else None
+        swapping = None
+        if overlapped is None and hasattr(generator, 'swapping_device'):
+            try:          # tiled path: the state alternates between two buffer pairs instead of being copied back
+                swapping = generator.swapping_device(a, b, chain0=self.chain0, kappa_chain=kappa_chain)
+            except NotImplementedError:
+                swapping = None
         for k in progress(range(steps), desc='Generation'):
             if overlapped is not None and getattr(overlapped, 'complete_records', False):
                 overlapped(sweeps_per_step, obs=record[k])
@@ -190,6 +196,8 @@ class BatchedEnsemble:
                 # the state columns of draw k - 1 ride along with launch k (they describe the chains as they arrive);
                 # launch k's own counters go to row k
                 overlapped(sweeps_per_step, obs=record[k], obs_in=record[k - 1] if k else scratch)
+            elif swapping is not None:
+                a, b = swapping(sweeps_per_step, obs=record[k])
             else:
                 generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
             if keep_every and (k + 1) % keep_every == 0:
@@ -197,6 +205,7 @@ class BatchedEnsemble:
         if overlapped is not None and steps and not getattr(overlapped, 'complete_records', False):
             last = ops.villain_observables(a, b, self.Action.kappa, kappa_chain=kappa_chain)     # the final state's columns
             record[steps - 1, :, :4] = last[:, :4]
+        self.fields = (a, b)
         self.record = record.cpu().numpy().transpose(1, 0, 2)          # (chains, steps, nobs): ONE D2H
         self.steps = steps
         self.sweeps_per_step = sweeps_per_step

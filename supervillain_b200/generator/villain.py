@@ -97,6 +97,22 @@ class NeighborhoodUpdate(Generator):
             self.counter += n_sweeps
         return step
 
+    def swapping_device(self, phi, n, *, chain0=0, kappa_chain=None):
+        """Stepping of one resident chain set on the tiled path without the copy back (ops.VillainSwappingSweeps): returns
+        `step(n_sweeps=1, obs=None) -> (phi, n)`, the tensors that hold the state after the step (they alternate between the
+        pair passed in and a second pair the stepper owns).  Raises NotImplementedError where the tiled path does not apply."""
+        if self.rng is not None or self.path not in ('auto', 'tiled'):
+            raise NotImplementedError('swapping sweeps serve Philox draws on path "auto" or "tiled"')
+        sw = ops.VillainSwappingSweeps(phi, n, self.kappa, W=self.Action.W, interval_phi=self.interval_phi,
+                                       interval_n=self.interval_n, seed=self.seed, chain0=chain0, arithmetic=self.arithmetic,
+                                       kappa_chain=kappa_chain, force_tiled=(self.path == 'tiled'))
+
+        def step(n_sweeps=1, obs=None):
+            fields = sw.step(self.counter, n_sweeps, obs)
+            self.counter += n_sweeps
+            return fields
+        return step
+
     def overlapped_device(self, phi, n, *, chain0=0, kappa_chain=None):
         """Overlapped-launch stepping of one resident chain set (ops.VillainOverlappedSweeps): returns `step(n_sweeps=1,
         obs=None, obs_in=None)` advancing the Philox counter, with `step.fence()` for foreign writes to the fields.

@@ -4,6 +4,7 @@ Arguments are `torch` CUDA tensors used purely as device storage (`data_ptr()` +
 stream); every function enqueues work on `torch.cuda.current_stream()` and returns immediately.
 Nothing here computes on the CPU -- a missing library or device raises.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -106,6 +107,45 @@ def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_s
         _opt(dS_out, 'dS_out', (torch.float64,), (chains, N, N)),
         _stream())
     _lib.check(code)
+
+
+class VillainSwappingSweeps:
+    """Tiled sweeps (lattices beyond one SM's shared memory and beyond the cluster kernel) for a caller that lets the
+    state move between two buffer pairs (svb_villain_sweep_tiled_swap): an odd number of sweeps ends in the other pair
+    and nothing is copied back.  `fields` is the pair that holds the state now; the pair passed in is used as is
+    (its tensors stay valid, but after `step` the state may live in the other pair)."""
+
+    def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, arithmetic='fast',
+                 kappa_chain=None, force_tiled=False):
+        self.lib = _lib.load()
+        self.chains, self.N = _fields_shape(phi, 'phi', 1)
+        if phi.dtype != torch.float64:
+            raise NotImplementedError('swapping sweeps need fp64 phi')
+        _dev(phi, 'phi', (torch.float64,))
+        _dev(n, 'n', (torch.int32,), (self.chains, 2, self.N, self.N))
+        if self.N % _TILE or (not force_tiled and (self.N <= _SMEM_MAX_N or self.N in _CLUSTER_N)):
+            raise NotImplementedError('swapping sweeps serve the tiled path: N a multiple of 32 above 96 that the cluster kernel does not take')
+        if W != W or W == float('inf') or int(W) != W:
+            raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W')
+        self.fields = (phi, n)
+        self.spare = (torch.empty_like(phi), torch.empty_like(n))
+        self.kappa_chain = kappa_chain
+        self.p_kappa_chain = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (self.chains,))
+        self.args = (float(kappa), int(W), float(interval_phi), int(interval_n))
+        self.tail = (int(seed) & (2**64 - 1), int(chain0), _ARITH[arithmetic])
+        self.flag = ctypes.c_int(0)
+
+    def step(self, sweep0, n_sweeps=1, obs=None):
+        kappa, W, interval_phi, interval_n = self.args
+        seed, chain0, arith = self.tail
+        (phi, n), (wphi, wn) = self.fields, self.spare
+        _lib.check(self.lib.svb_villain_sweep_tiled_swap(
+            phi.data_ptr(), n.data_ptr(), wphi.data_ptr(), wn.data_ptr(), self.chains, self.N, kappa, self.p_kappa_chain, W,
+            interval_phi, interval_n, int(n_sweeps), seed, int(sweep0), chain0, arith,
+            _opt(obs, 'obs', (torch.float64,), (self.chains, VOBS_COUNT)), ctypes.byref(self.flag), _stream()))
+        if self.flag.value:
+            self.fields, self.spare = self.spare, self.fields
+        return self.fields
 
 
 def villain_sweep_plan(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, arithmetic='fast',

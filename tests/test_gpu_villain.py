@@ -520,3 +520,36 @@ def test_filtered_decisions_stay_exact_far_from_equilibrium(phi_scale, n_scale, 
     ops.villain_sweep(phi, n, kappa, n_sweeps=3, seed=seed, obs=obs)
     assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
     assert (obs.cpu().numpy()[:, VOBS_ACCEPTED] == acc).all()
+
+
+@pytest.mark.parametrize('N,path,sweeps_per_step', [(256, 'auto', 1), (256, 'auto', 2), (128, 'tiled', 3), (64, 'tiled', 1)])
+def test_swapping_tiled_sweeps_equal_the_in_place_ones(N, path, sweeps_per_step):
+    """svb_villain_sweep_tiled_swap (the state alternates between two buffer pairs, no copy back) through
+    BatchedEnsemble.generate against svb_villain_sweep_tiled in place: fields and records bit for bit, for odd and even
+    sweep counts, and a continued run picks the state up from whichever pair holds it."""
+    import supervillain_b200 as svb
+    from supervillain_b200 import ops
+    from supervillain_b200._lib import VOBS_COUNT
+    from supervillain_b200.generator.villain import NeighborhoodUpdate
+    chains, steps, kappa = 3, 5, 0.6
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    G = NeighborhoodUpdate(S, seed=21)
+    G.path = path
+    assert callable(G.swapping_device(*svb.BatchedEnsemble(S, chains)._start('hot', 2)))
+    E = svb.BatchedEnsemble(S, chains, chain0=7).generate(steps, G, 'hot', start_seed=2, sweeps_per_step=sweeps_per_step)
+    phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 2)
+    rec = torch.empty((steps, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for k in range(steps):
+        ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps_per_step, seed=21, sweep0=k * sweeps_per_step, chain0=7, path='tiled',
+                          obs=rec[k])
+    assert torch.equal(E.fields[0], phi) and torch.equal(E.fields[1], n)
+    want = rec.cpu().numpy().transpose(1, 0, 2)
+    exact = [VOBS_SUM_DN2, VOBS_WRAP0, VOBS_WRAP1, VOBS_ACCEPTED]            # integer-valued columns
+    np.testing.assert_array_equal(E.record[..., exact], want[..., exact])
+    # the tiles of a chain add their fp64 partial sums atomically, in an order that varies from launch to launch
+    np.testing.assert_allclose(E.record, want, rtol=1e-13)
+    assert G.counter == steps * sweeps_per_step
+    E.generate(2, G, 'continue', sweeps_per_step=sweeps_per_step)
+    for k in range(steps, steps + 2):
+        ops.villain_sweep(phi, n, kappa, n_sweeps=sweeps_per_step, seed=21, sweep0=k * sweeps_per_step, chain0=7, path='tiled')
+    assert torch.equal(E.fields[0], phi) and torch.equal(E.fields[1], n)
