@@ -78,6 +78,12 @@ if 'c5' in which:
             k[0] += sw
             ops.villain_sweep(phi, n, 0.5, seed=1, sweep0=k[0], obs=obs, path=path, n_sweeps=sw)
         report(f'villain L=4096 x 1 chain (C5), {path}, {sw} sweep(s)/call', CH * N * N * sw, 32, timeit(f, n=5))
+    swp = ops.VillainSwappingSweeps(phi, n, 0.5, seed=1)       # the state alternates between two buffer pairs: no copy back
+    k = [0]
+    def g():
+        k[0] += 1
+        swp.step(k[0], 1, obs)
+    report('villain L=4096 x 1 chain (C5), tiled, swapping buffer pairs, 1 sweep/call', CH * N * N, 32, timeit(g, n=5))
 if 'forms' in which:
     N, CH = 32, 65536                                    # 512 MiB f64 0-forms
     a = torch.randn((CH, 1, N, N), dtype=torch.float64, device='cuda')
