@@ -281,7 +281,7 @@ def run_gpu(args):
     for k in range(2):
         stepper.step(*host_sets[k % 2], n_sweeps=args.sweeps_per_step)
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
     t0 = time.perf_counter()
     pending = None
     for k in range(e2e_steps):                               # two steps in flight, on alternating host buffer pairs
@@ -342,6 +342,7 @@ def main():
     ap.add_argument('--impl', default='svb200', choices=['svb200', 'reference'])
     ap.add_argument('--sweeps-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=20, help='timed steps of the host-buffer (e2e) leg')
     ap.add_argument('--no-overlap', action='store_true', help='ordinary launches instead of overlapped ones')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)')
