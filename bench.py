@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- site-updates/s of batched Villain Metropolis sweeps (BASELINE.json metric).
+"""bench.py -- site-updates/s of batched Villain Metropolis sweeps (BASELINE.json metric), every named shape.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs c2,c3,c4,c5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (N=1): BASELINE config 2 -- Villain (phi, n), L=32, kappa=0.5, 4096 independent chains on
-one B200, one checkerboard NeighborhoodUpdate sweep per step with the action / winding / wrapping
-reductions fused in.  With N GPUs every rank runs that workload on its own 4096 chains (weak
-scaling; chains are independent, there is no collective on the hot path; a final all_gather of
-the observable records runs outside the timed region).
+Headline workload (the top-level keys of the JSON line): BASELINE config 2 -- Villain (phi, n), L=32,
+kappa=0.5, 4096 independent chains per B200, one checkerboard NeighborhoodUpdate sweep per step with the
+action / winding / wrapping reductions fused in.  The `configs` array of the same line carries the other
+named shapes at their per-GPU shard sizes -- c3 (worldline L=64, 1024 chains/GPU = 8192 over 8 GPUs),
+c4 (L=128 kappa scan, 8 kappa x 1024 chains/GPU = 64 kappa over 8 GPUs), c5 (one L=4096 lattice; replicas
+with N GPUs) -- each with hot AND cold starts, its own roofline and, on rank 0 at N=1, the reference's own
+generators timed on the host cores.  With N GPUs every rank runs the same per-GPU shard on its own chains
+(weak scaling; chains are independent, there is no collective on the hot path; a final all_gather of the
+observable records runs outside the timed region).
 
-A step is ONE kernel launch.  The chain state (64 MiB) would fit the 126 MB L2, so the timed loop
-rotates over 4 independent chain sets (256 MiB): every step streams its set from HBM.  Steps are
-issued as overlapped launches (svb_villain_sweep_overlapped: programmatic dependent launch with
-per-chain epochs ordering the data), the way BatchedEnsemble.generate issues them, so the ramp-up
-of one launch hides under the tail of the one before; `--no-overlap` times ordinary launches.
+Timing protocol (every shape): the clock sampler is started and its FIRST sample awaited (NVML start-up
+is then over); ranks meet at a barrier; the step is issued back to back for >= 1 s (the warm-up: at least
+W steps, and the clocks settle under the power cap); WITHOUT draining the stream, 5 windows of exactly K
+steps follow, each bracketed by CUDA events on the launching stream; after a final barrier + synchronize
+the per-window times are reduced with MAX over ranks and the BEST window is reported (all five are in
+`windows_ms_per_step`).  A step is ONE kernel launch; inputs are larger than L2 (c2 / c3 rotate over 4 chain
+sets, c4 / c5 are larger than L2 by themselves), so every step streams from HBM.
 
-One JSON line on stdout; see the task contract for the keys.  `--impl reference` times the CPU
-restatement of the reference's numpy algorithm (oracle/villain_np.py) on all host cores.
+One JSON line on stdout; see the task contract for the keys.  `--impl reference` times the UNMODIFIED
+reference's NeighborhoodUpdate.step (staged under oracle/_ref by oracle/stage_reference.py) on all host
+cores; where the staged copy is missing it falls back to the oracle's numpy port and says so (`kind`).
 """
 import argparse
 import json
@@ -36,11 +43,39 @@ if ROOT not in sys.path:
 
 METRIC = 'site-updates/sec (batched Villain Metropolis sweeps)'
 UNIT = 'site-updates/s'
-L, KAPPA, W_CONSTRAINT, CHAINS = 32, 0.5, 1, 4096
-BYTES_PER_SITE_UPDATE = 32          # fp64 phi + 2 x int32 n, one read + one write
-ROTATE = 4                           # chain sets rotated through so every step comes from HBM, not L2
-THERMALISE = 200                     # untimed sweeps applied to each synthetic hot start before the warm-up
-WORKLOAD = 'config2: Villain (phi,n) L=32 kappa=0.5 W=1, 4096 chains/GPU, NeighborhoodUpdate checkerboard sweep + action/winding/wrapping'
+KAPPA, W_CONSTRAINT = 0.5, 1
+WINDOWS = 5                          # timed windows of --steps steps; the best one is the record
+SUSTAIN_S = 1.0                      # seconds of the same load issued before the first window
+SEED = 20260101
+
+# name -> the shape (per GPU).  bytes: algorithmic bytes per update; rotate: independent chain sets cycled
+# through so that every step streams from HBM; cap: most steps per window (long steps: keep the default run short)
+SHAPES = {
+    'c2': dict(kind='villain', L=32, chains=4096, bytes=32, rotate=4, thermalise=200, cap=None,
+               kernel='villain_smem_filtered_kernel<N=32, 128 threads>',
+               workload='config2: Villain (phi,n) L=32 kappa=0.5 W=1, 4096 chains/GPU, NeighborhoodUpdate checkerboard sweep + action/winding/wrapping'),
+    'c3': dict(kind='worldline', L=64, chains=1024, bytes=24, rotate=4, thermalise=200, cap=None,
+               kernel='worldline_smem_table_kernel<N=64>',
+               workload='config3: Worldline (m,v) L=64 kappa=0.5 W=1, 1024 chains/GPU (8192 over 8 GPUs), PlaquetteUpdate move in checkerboard order + observables'),
+    'c4': dict(kind='villain', L=128, chains=8192, bytes=32, rotate=1, thermalise=20, cap=100, kappas_per_gpu=8,
+               kernel='villain_cluster_kernel<N=128, cluster of 4 x 512 threads>',
+               workload='config4: Villain L=128 kappa scan, 8 kappa x 1024 chains/GPU (64 kappa in [0.3,1.2] over 8 GPUs), NeighborhoodUpdate sweep + observables'),
+    'c5': dict(kind='villain', L=4096, chains=1, bytes=32, rotate=1, thermalise=20, cap=200,
+               kernel='villain_tiled_filtered_kernel (one CTA per tile, swapping buffer pairs)',
+               workload='config5: Villain L=4096 kappa=0.5, one lattice per GPU (replicas only), NeighborhoodUpdate sweep + observables'),
+}
+WORKLOAD = SHAPES['c2']['workload']
+
+
+def config_dict(world, sweeps_per_step):
+    """The headline `config`: the same dict in both arms (`--impl reference` describes the workload it is the baseline of)."""
+    s = SHAPES['c2']
+    return {'workload': WORKLOAD, 'L': s['L'], 'kappa': KAPPA, 'W': W_CONSTRAINT, 'chains_per_gpu': s['chains'],
+            'sweeps_per_step': sweeps_per_step,
+            'start': f'hot (phi~U(-pi,pi), n~integers(-2,3)) + {s["thermalise"]} untimed sweeps',
+            'rng': 'philox4x32-10 in-kernel',
+            'l2': f'inputs larger than L2: {s["rotate"]} chain sets ({s["rotate"] * s["chains"] * s["L"] ** 2 * 16 >> 20} MiB) rotated',
+            'parallelism': f'chains sharded over {world} GPU(s), no hot-path collective'}
 
 
 def traffic_from_profile(override):
@@ -63,35 +98,78 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle's port of the reference's numpy NeighborhoodUpdate, one chain per process
+# CPU arm: the reference's own generators (oracle/_ref), one chain per process on every host core
 # ---------------------------------------------------------------------------------------------
+def reference_staged():
+    from oracle import refimport
+    return refimport.available()
+
+
 def _cpu_worker(args):
-    seed, sweeps = args
+    """Sweeps of ONE chain by the reference's generator `what` at lattice size L; returns the seconds `sweeps` sweeps took.
+
+    what: 'neighborhood' (generator/villain/neighborhood.py:59-137), 'plaquette' (generator/worldline/plaquette.py:35-104,
+    the sequential sweep the API names), 'vortex+coexact' (worldline/vortex.py:51-136 + coexact.py:53-128, the reference's
+    own checkerboard form of the same move), or 'port' (oracle/villain_np.py, only when the reference is not staged)."""
+    what, L, seed, sweeps, threads = args
+    os.environ['NUMBA_NUM_THREADS'] = str(threads)
     os.environ.setdefault('OMP_NUM_THREADS', '1')
-    from oracle import villain_np as V
-    rng = np.random.default_rng(seed)
-    phi, n = V.hot_start(np.random.default_rng(1000 + seed), L)
-    phi, n = V.neighborhood_step(phi, n, KAPPA, W_CONSTRAINT, rng)       # untimed first sweep (imports, caches)
+    rng = np.random.default_rng(1000 + seed)
+    if what == 'port':
+        from oracle import villain_np as V
+        draw = np.random.default_rng(seed)
+        phi, n = V.hot_start(rng, L)
+        step = lambda c: V.neighborhood_step(c[0], c[1], KAPPA, W_CONSTRAINT, draw)      # noqa: E731
+        cfg = (phi, n)
+    else:
+        import warnings
+        warnings.simplefilter('ignore')
+        from oracle import refimport
+        sv = refimport.import_reference()
+        lattice = sv.lattice.Lattice2D(L)
+        if what == 'neighborhood':
+            S = sv.action.Villain(lattice, KAPPA, W_CONSTRAINT)
+            G = sv.generator.villain.NeighborhoodUpdate(S)
+            cfg = {'phi': lattice.form(0), 'n': lattice.form(1, dtype=int)}
+            cfg['phi'][...] = rng.uniform(-np.pi, np.pi, cfg['phi'].shape)
+            cfg['n'][...] = rng.integers(-2, 3, cfg['n'].shape)
+        else:
+            S = sv.action.Worldline(lattice, KAPPA, W_CONSTRAINT)
+            if what == 'plaquette':
+                G = sv.generator.worldline.PlaquetteUpdate(S)
+            else:
+                G = sv.generator.combining.Sequentially((sv.generator.worldline.VortexUpdate(S), sv.generator.worldline.CoexactUpdate(S)))
+            cfg = S.configurations(1)[0]                  # cold: delta m = 0 holds trivially; the sweep cost does not depend on the state
+        step = G.step
+    cfg = step(cfg)                                       # untimed first sweep (imports, JIT, colour tables)
     t0 = time.perf_counter()
     for _ in range(sweeps):
-        phi, n = V.neighborhood_step(phi, n, KAPPA, W_CONSTRAINT, rng)
+        cfg = step(cfg)
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(procs, seconds):
-    """site-updates/s of `procs` processes each sweeping its own L=32 chain for about `seconds` of wall clock.
-
-    Returns (rate, wall, sweeps_per_process).  The sweep count is calibrated on a short untimed run so
-    the timed sample is bounded."""
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(i, 1) for i in range(procs)])            # warm the pool (imports)
-        probe = max(pool.map(_cpu_worker, [(i, 20) for i in range(procs)])) / 20
-        sweeps = max(10, int(seconds / max(probe, 1e-6)))
+def cpu_rate(what, L, procs, seconds, threads=1, pool=None):
+    """updates/s of `procs` processes each sweeping its own chain for about `seconds` of wall clock (calibrated on a short
+    untimed run, so the timed sample is bounded).  Returns (rate, wall, sweeps_per_process)."""
+    own = pool is None
+    if own:
+        pool = mp.get_context('spawn').Pool(procs)
+    try:
+        if L >= 1024:
+            sweeps = 1                                    # a sweep takes seconds: no probe, one timed sweep after the untimed first
+        else:
+            probe = max(pool.map(_cpu_worker, [(what, L, i, 3, threads) for i in range(procs)])) / 3
+            sweeps = max(1, int(seconds / max(probe, 1e-6)))
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(i, sweeps) for i in range(procs)])
+        inner = pool.map(_cpu_worker, [(what, L, i, sweeps, threads) for i in range(procs)])
         wall = time.perf_counter() - t0
-    return procs * sweeps * L * L / wall, wall, sweeps
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    # the rate of the sweeps themselves: each worker's own clock around its loop (the pool's wall clock also holds the import
+    # and JIT of the reference, which are not part of any sweep)
+    return sum(sweeps * L * L / t for t in inner), wall, sweeps
 
 
 def host_cores():
@@ -101,32 +179,73 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def headline_cpu_baseline(cores, seconds):
+    """config 2 on the host: the reference's NeighborhoodUpdate, one chain per core."""
+    if reference_staged():
+        rate, wall, sweeps = cpu_rate('neighborhood', 32, cores, seconds)
+        return {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                'sample': f'{cores} processes (NUMBA_NUM_THREADS=1) x {sweeps} sweeps of one L=32 kappa=0.5 chain each through the unmodified '
+                          f'supervillain.generator.villain.NeighborhoodUpdate.step (oracle/_ref), {wall:.1f} s wall incl. import + JIT'}
+    rate, wall, sweeps = cpu_rate('port', 32, cores, seconds)
+    return {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each, {wall:.1f} s wall (oracle/villain_np.py port of '
+                      f'neighborhood.py:59-137; the reference is not staged under oracle/_ref)'}
+
+
+def shape_cpu_baselines(name, cores):
+    """The reference's generators at the shape's lattice size (bounded samples); c2's is the headline `cpu_baseline`."""
+    if not reference_staged():
+        return None
+    L = SHAPES[name]['L']
+    out = {}
+    if name == 'c3':
+        for what, secs in (('plaquette', 1.0), ('vortex+coexact', 3.0)):
+            rate, wall, sweeps = cpu_rate(what, L, cores, secs)
+            out[what] = {'value': rate, 'unit': 'plaquette-updates/s', 'cores': cores, 'kind': 'reference',
+                         'sample': f'{cores} processes x {sweeps} sweeps of one L={L} chain each, {wall:.1f} s wall incl. import + JIT'}
+    elif name == 'c4':
+        rate, wall, sweeps = cpu_rate('neighborhood', L, cores, 3.0)
+        out['neighborhood'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                               'sample': f'{cores} processes x {sweeps} sweeps of one L={L} chain each, {wall:.1f} s wall incl. import + JIT'}
+    elif name == 'c5':
+        # one lattice: ONE process, the reference's numba kernels run parallel above 30 000 sites (lattice/_kernels.py:10,25)
+        rate, wall, sweeps = cpu_rate('neighborhood', L, 1, 1.0, threads=cores)
+        out['neighborhood'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                               'sample': f'1 process, NUMBA_NUM_THREADS={cores}, {sweeps} sweep(s) of the L={L} lattice, {wall:.1f} s wall incl. '
+                                         f'import, JIT and the colour tables'}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
     cores = host_cores()
-    per_step = []
     # bounded: the whole --steps/--warmup run stays within a few minutes whatever K and W are
     steps, warmup = min(args.steps, 20), min(args.warmup, 3)
     seconds = min(3.0, 60.0 / max(steps, 1))
-    for _ in range(warmup):
-        cpu_reference_rate(cores, 0.2)
-    t_all = time.perf_counter()
-    sweeps = 0
-    for _ in range(steps):
-        rate, wall, sweeps = cpu_reference_rate(cores, seconds)
-        per_step.append((rate, wall))
-    total_wall = time.perf_counter() - t_all
-    value = float(np.mean([r for r, _ in per_step]))
-    sample = (f'{steps} timed steps; each step = {cores} processes x ~{sweeps} sweeps of one L=32 kappa=0.5 chain each '
-              f'(~{seconds:.1f} s; numpy port of neighborhood.py:59-137)')
+    what = 'neighborhood' if reference_staged() else 'port'
+    kind = 'reference' if what == 'neighborhood' else 'port'
+    with mp.get_context('spawn').Pool(cores) as pool:             # one pool: the reference is imported and JIT-compiled once per core
+        for _ in range(warmup):
+            cpu_rate(what, 32, cores, 0.2, pool=pool)
+        t_all = time.perf_counter()
+        rates, sweeps = [], 0
+        for _ in range(steps):
+            rate, _, sweeps = cpu_rate(what, 32, cores, seconds, pool=pool)
+            rates.append(rate)
+        total_wall = time.perf_counter() - t_all
+    value = float(np.mean(rates))
+    source = ('the unmodified supervillain.generator.villain.NeighborhoodUpdate.step, staged under oracle/_ref' if kind == 'reference'
+              else 'oracle/villain_np.py, the numpy port of neighborhood.py:59-137 (oracle/_ref is not staged)')
+    sample = (f'{steps} timed steps; each step = {cores} processes (NUMBA_NUM_THREADS=1) x ~{sweeps} sweeps of one L=32 kappa=0.5 chain each '
+              f'(~{seconds:.1f} s) through {source}')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_wall / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'L': L, 'kappa': KAPPA, 'chains_per_gpu': CHAINS},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': config_dict(int(os.environ.get('WORLD_SIZE', '1')), args.sweeps_per_step),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -138,8 +257,9 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons every 100 ms from ONE long-lived `nvidia-smi -lms` process (started before the
-    warm-up: forking inside the timed region costs the launching thread milliseconds)."""
+    """SM clock and throttle reasons every 100 ms from ONE long-lived `nvidia-smi -lms` process.  `start_and_wait` returns
+    only once the first sample has arrived: NVML start-up (hundreds of ms of driver locks) is then behind us and cannot
+    land inside a timed window."""
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -147,6 +267,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []               # (timestamp, fields)
+        self.first = threading.Event()
         self.stop_flag = threading.Event()
         self.proc = None
 
@@ -158,10 +279,16 @@ class ClockSampler(threading.Thread):
                 parts = [p.strip() for p in line.strip().split(',')]
                 if len(parts) >= 6:
                     self.samples.append((time.time(), parts))
+                    self.first.set()
                 if self.stop_flag.is_set():
                     break
         except Exception:
             pass
+        self.first.set()
+
+    def start_and_wait(self, timeout=20.0):
+        self.start()
+        self.first.wait(timeout)
 
     def stop(self):
         self.stop_flag.set()
@@ -186,13 +313,126 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+class Shape:
+    """One named shape resident on this rank's GPU: `step(k)` issues step k (one kernel launch), `cold()` zeroes the fields."""
+
+    def __init__(self, name, world, rank, dev, sweeps_per_step, overlap=True):
+        import torch
+        import supervillain_b200 as svb
+        from supervillain_b200 import ops, sharding
+        from supervillain_b200.generator.villain import NeighborhoodUpdate
+        from supervillain_b200.generator.worldline import PlaquetteUpdate
+        self.torch, self.ops, self.name, self.spec = torch, ops, name, SHAPES[name]
+        s = self.spec
+        self.L, self.chains, self.sweeps_per_step = s['L'], s['chains'], sweeps_per_step
+        self.updates_per_step = self.chains * self.L * self.L * sweeps_per_step
+        self.kappa_chain = None
+        self.kappas = None
+        if name == 'c4':
+            per_kappa = self.chains // s['kappas_per_gpu']
+            self.kappas = 0.3 + 0.9 * np.arange(s['kappas_per_gpu'] * world) / max(s['kappas_per_gpu'] * world - 1, 1)
+            self.chain0, count, kc = sharding.kappa_scan(self.kappas, per_kappa, world, rank)
+            self.kappa_chain = torch.as_tensor(np.asarray(kc, dtype=np.float64)).to(dev)
+        else:
+            self.chain0, count = sharding.shard_chains(world * self.chains, world, rank)
+        assert count == self.chains
+        lattice = svb.Lattice2D(self.L)
+        if s['kind'] == 'villain':
+            self.action = svb.Villain(lattice, KAPPA, W=W_CONSTRAINT)
+            self.G = NeighborhoodUpdate(self.action, seed=SEED)
+            nobs = ops.VOBS_COUNT
+        else:
+            self.action = svb.Worldline(lattice, KAPPA, W=W_CONSTRAINT)
+            self.G = PlaquetteUpdate(self.action, seed=SEED)
+            nobs = ops.WOBS_COUNT
+        self.sets = []
+        for r in range(s['rotate']):
+            E = svb.BatchedEnsemble(self.action, self.chains, chain0=self.chain0)
+            self.sets.append(E._start('hot', SEED + 7919 * (rank * s['rotate'] + r)))
+        self.obs = [torch.zeros((self.chains, nobs), dtype=torch.float64, device=dev) for _ in self.sets]
+        self.prev = [torch.zeros_like(o) for o in self.obs]
+        self.mode = 'ordinary'
+        self.steppers = None
+        G, kc = self.G, self.kappa_chain
+        for a, b in self.sets:                                    # untimed thermalisation of the synthetic hot starts
+            G.sweep_device(a, b, s['thermalise'], chain0=self.chain0, kappa_chain=kc)
+        if name == 'c5':
+            self.mode = 'swapping buffer pairs (svb_villain_sweep_tiled_swap)'
+            self.steppers = [G.swapping_device(a, b, chain0=self.chain0) for a, b in self.sets]
+        elif overlap:
+            self.mode = 'overlapped (programmatic dependent launch + per-chain epochs)'
+            self.steppers = [G.overlapped_device(a, b, chain0=self.chain0, kappa_chain=kc) for a, b in self.sets]
+        else:
+            self.plans = [G.plan_device(a, b, obs=o, chain0=self.chain0, kappa_chain=kc) for (a, b), o in zip(self.sets, self.obs)]
+
+    def step(self, k):
+        r = k % len(self.sets)
+        sps = self.sweeps_per_step
+        if self.name == 'c5':
+            self.sets[r] = self.steppers[r](sps, obs=self.obs[r])
+        elif self.steppers is None:
+            self.plans[r](sps)
+        elif self.spec['kind'] == 'villain':
+            # the way BatchedEnsemble.generate steps: launch k writes its counters to record k and completes the state
+            # columns of record k - 1 (the observables of the chains as they arrive ride along with the residual build)
+            self.steppers[r](sps, self.obs[r], self.prev[r])
+            self.obs[r], self.prev[r] = self.prev[r], self.obs[r]
+        else:
+            self.steppers[r](sps, self.obs[r])
+
+    def cold(self):
+        """All-zero fields (the reference's 'cold' start, ensemble.py:80-81); the next launch waits for the memsets."""
+        for a, b in self.sets:
+            a.zero_()
+            b.zero_()
+        for st in self.steppers or ():
+            fence = getattr(st, 'fence', None)
+            if fence is not None:
+                fence()
+
+
+def time_windows(torch, dist, world, dev, step, steps, warmup, sustain_s, before_window=None):
+    """The timing protocol of the module docstring.  Returns (best ms per window, [ms per window], t_load0, t_load1)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t_load0 = time.time()
+    k = 0
+    if before_window is None:
+        while k < warmup or time.time() < t_load0 + sustain_s:    # the warm-up: the same load, back to back, not drained
+            step(k)
+            k += 1
+    events = []
+    for _ in range(WINDOWS):
+        if before_window is not None:                             # cold starts: reset, then W warm-up steps, per window
+            before_window()
+            for _ in range(warmup):
+                step(k)
+                k += 1
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step(k)
+            k += 1
+        b.record()
+        events.append((a, b))
+    barrier()
+    t_load1 = time.time()
+    t = torch.tensor([a.elapsed_time(b) for a, b in events], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = [float(x) for x in t.tolist()]
+    return min(ms), ms, t_load0, t_load1
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     import supervillain_b200 as svb
-    from supervillain_b200._lib import VOBS_COUNT
-    from supervillain_b200.generator.villain import NeighborhoodUpdate
     from supervillain_b200.hostpath import HostStepper
     from supervillain_b200 import sharding
 
@@ -203,81 +443,48 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
+    peak, peak_src = measured_peaks()
+    names = [c for c in args.configs.split(',') if c]
+    unknown = [c for c in names if c not in SHAPES]
+    if unknown or 'c2' not in names:
+        raise SystemExit(f'--configs must list c2 (the headline) and only {sorted(SHAPES)}; got {args.configs!r}')
 
-    S = svb.Villain(svb.Lattice2D(L), KAPPA, W=W_CONSTRAINT)
-    G = NeighborhoodUpdate(S, seed=20260101)
-    # weak scaling: 4096 chains per GPU; global chain ids make the draws independent of the GPU count
-    chain0, n_chains = sharding.shard_chains(world * CHAINS, world, rank)
-    assert n_chains == CHAINS
-    sets = []
-    for r in range(ROTATE):
-        E = svb.BatchedEnsemble(S, CHAINS, chain0=chain0)
-        sets.append(E._start('hot', 20260101 + 7919 * (rank * ROTATE + r)))
-    obs_sets = [torch.zeros((CHAINS, VOBS_COUNT), dtype=torch.float64, device=dev) for _ in sets]   # one record per set
-    for phi, n in sets:                                       # untimed thermalisation of the synthetic hot starts
-        G.sweep_device(phi, n, THERMALISE, chain0=chain0)
-
-    if args.no_overlap:
-        plans = [G.plan_device(phi, n, obs=o, chain0=chain0) for (phi, n), o in zip(sets, obs_sets)]
-
-        def step(k):
-            plans[k % ROTATE](args.sweeps_per_step)
-    else:
-        # the way BatchedEnsemble.generate steps: launch k writes its counters to record k and completes the state columns
-        # of record k - 1 (the observables of the chains as they arrive ride along with the pass that builds the residuals)
-        steppers = [G.overlapped_device(phi, n, chain0=chain0) for phi, n in sets]
-        prev_sets = [torch.zeros_like(o) for o in obs_sets]
-
-        def step(k):
-            r = k % ROTATE
-            steppers[r](args.sweeps_per_step, obs_sets[r], prev_sets[r])
-            obs_sets[r], prev_sets[r] = prev_sets[r], obs_sets[r]
+    sampler = ClockSampler(local)
+    sampler.start_and_wait()                                     # NVML start-up is over before anything is timed
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()                                           # one nvidia-smi process for the whole run, forked before the warm-up
-    for k in range(args.warmup):
-        step(k)
-    barrier()
-    t_load0 = time.time()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
-    stop.record()
-    barrier()
-    ms = start.elapsed_time(stop)
-    if ms < 1000:             # a short timed region sees few 100 ms samples: keep the same load on until a second has passed
-        k = 0
-        while time.time() < t_load0 + 1.0:
-            step(k); k += 1
-        torch.cuda.synchronize()
-    t_load1 = time.time()
-    sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    updates_per_step = CHAINS * L * L * args.sweeps_per_step
-    value = world * updates_per_step * args.steps / (ms * 1e-3)
+    def measure(shape, steps, start):
+        before = shape.cold if start == 'cold' else None
+        if before is not None:
+            shape.cold()
+        best, ms, t0, t1 = time_windows(torch, dist, world, dev, shape.step, steps, args.warmup, SUSTAIN_S, before)
+        launch_s = best * 1e-3 / steps
+        achieved = shape.spec['bytes'] * shape.updates_per_step / launch_s / 1e9
+        return {'start': start, 'value': world * shape.updates_per_step / launch_s,
+                'ms_per_step': best / steps, 'steps': steps, 'windows_ms_per_step': [m / steps for m in ms],
+                'roofline_frac': achieved / peak, 'achieved_gbs': achieved, 'clocks': sampler.summary(t0, t1)}
 
-    # ---- roofline of the dominant kernel (the step IS one launch of villain_smem_kernel) ----
-    peak, peak_src = measured_peaks()
-    launch_s = (ms * 1e-3) / args.steps
-    achieved = BYTES_PER_SITE_UPDATE * CHAINS * L * L * args.sweeps_per_step / launch_s / 1e9
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic_from_profile(args.traffic), 'kernel': 'villain_smem_filtered_kernel<N=32, 128 threads>',
-                'launches': 'ordinary' if args.no_overlap else 'overlapped (programmatic dependent launch + per-chain epochs)',
-                'algorithmic_bytes_per_launch': BYTES_PER_SITE_UPDATE * CHAINS * L * L,
-                'peak_source': peak_src, 'sweeps_per_launch': args.sweeps_per_step}
+    # ---- headline: config 2, hot start ----
+    c2 = Shape('c2', world, rank, dev, args.sweeps_per_step, overlap=not args.no_overlap)
+    head = measure(c2, args.steps, 'hot')
+    ms_per_step = head['ms_per_step']
+    value = head['value']
+    spec = SHAPES['c2']
+    roofline = {'bound': 'hbm', 'achieved': head['achieved_gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': head['roofline_frac'],
+                'traffic': traffic_from_profile(args.traffic), 'kernel': spec['kernel'], 'launches': c2.mode,
+                'algorithmic_bytes_per_launch': spec['bytes'] * c2.updates_per_step, 'peak_source': peak_src,
+                'sweeps_per_launch': args.sweeps_per_step}
+    clocks = head['clocks']
+    c2_cold = measure(c2, args.steps, 'cold')
 
     # ---- end to end through the host-buffer API: H2D of the fields, sweep, D2H of fields + observables ----
-    stepper = HostStepper(G, CHAINS, chain0=chain0)
-    host_sets = [stepper.pinned_fields(from_device=s) for s in sets[:2]]
+    G = c2.G
+    stepper = HostStepper(G, c2.chains, chain0=c2.chain0)
+    host_sets = [stepper.pinned_fields(from_device=s) for s in c2.sets[:2]]
     for k in range(2):
         stepper.step(*host_sets[k % 2], n_sweeps=args.sweeps_per_step)
     barrier()
@@ -295,37 +502,74 @@ def run_gpu(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * updates_per_step * e2e_steps / float(t.item())
+    e2e_value = world * c2.updates_per_step * e2e_steps / float(t.item())
     e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': stepper.h2d_bytes, 'd2h_bytes_per_step': stepper.d2h_bytes,
            'steps': e2e_steps, 'api': 'HostStepper.step_async(phi_host, n_host): pinned host fields in and out + observables, two steps in flight on '
                   'alternating host buffer pairs'}
 
     # ---- final gather of observables (outside the timed region; the only inter-GPU traffic) ----
     torch.cuda.synchronize()
-    obs = svb.ops.villain_observables(sets[0][0], sets[0][1], KAPPA)      # final state of set 0
+    obs = svb.ops.villain_observables(c2.sets[0][0], c2.sets[0][1], KAPPA)      # final state of set 0
     all_obs = sharding.gather_columns(obs)                    # (world * CHAINS, VOBS_COUNT) on every rank
-    mean_action_density = float(all_obs[:, 0].mean().item()) / (L * L)
+    mean_action_density = float(all_obs[:, 0].mean().item()) / (spec['L'] ** 2)
+    del stepper, host_sets
 
-    line = None
+    # ---- every named shape: hot and cold, its own roofline ----
+    def entry(name, shape, hot, cold):
+        s = SHAPES[name]
+        unit = UNIT if s['kind'] == 'villain' else 'plaquette-updates/s'
+        e = {'name': name, 'workload': s['workload'], 'unit': unit, 'value': hot['value'], 'ms_per_step': hot['ms_per_step'],
+             'steps': hot['steps'], 'windows_ms_per_step': hot['windows_ms_per_step'],
+             'L': s['L'], 'chains_per_gpu': s['chains'], 'chains_total': s['chains'] * world, 'launches': shape.mode,
+             'roofline': {'bound': 'hbm', 'achieved': hot['achieved_gbs'], 'peak': peak, 'unit': 'GB/s', 'frac': hot['roofline_frac'],
+                          'bytes_per_update': s['bytes'], 'algorithmic_bytes_per_launch': s['bytes'] * shape.updates_per_step,
+                          'kernel': s['kernel']},
+             'start': 'hot', 'clocks': hot['clocks'],
+             'cold': {k: cold[k] for k in ('value', 'ms_per_step', 'steps', 'windows_ms_per_step', 'roofline_frac')},
+             'l2': (f'{s["rotate"]} chain sets rotated' if s['rotate'] > 1 else 'one set') +
+                   f' ({s["rotate"] * s["chains"] * s["L"] ** 2 * (s["bytes"] // 2) >> 20} MiB of state per GPU: larger than L2)'}
+        if shape.kappas is not None:
+            e['kappas_total'] = len(shape.kappas)
+        return e
+
+    shapes_out = [entry('c2', c2, head, c2_cold)]
+    del c2, G
+    torch.cuda.empty_cache()
+    for name in names:
+        if name == 'c2':
+            continue
+        cap = SHAPES[name]['cap']
+        steps = args.steps if cap is None else min(args.steps, cap)
+        shape = Shape(name, world, rank, dev, args.sweeps_per_step)
+        hot = measure(shape, steps, 'hot')
+        cold = measure(shape, steps, 'cold')
+        shapes_out.append(entry(name, shape, hot, cold))
+        del shape
+        torch.cuda.empty_cache()
+    sampler.stop()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
-            rate, wall, sweeps = cpu_reference_rate(cores, 12.0)
-            cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': f'{cores} processes x {sweeps} sweeps of one L=32 kappa=0.5 chain each, {wall:.1f} s wall '
-                             f'(oracle/villain_np.py port of neighborhood.py:59-137)'}
+            cpu = headline_cpu_baseline(cores, 12.0)
+            for e in shapes_out:
+                if e['name'] != 'c2' and args.cpu_baselines == 'all':
+                    e['cpu_baseline'] = shape_cpu_baselines(e['name'], cores)
+            shapes_out[0]['cpu_baseline'] = cpu
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'L': L, 'kappa': KAPPA, 'W': W_CONSTRAINT, 'chains_per_gpu': CHAINS,
-                       'sweeps_per_step': args.sweeps_per_step, 'start': f'hot (phi~U(-pi,pi), n~integers(-2,3)) + {THERMALISE} untimed sweeps',
-                       'rng': 'philox4x32-10 in-kernel',
-                       'l2': f'inputs larger than L2: {ROTATE} chain sets ({ROTATE * CHAINS * L * L * 16 >> 20} MiB) rotated',
-                       'parallelism': f'chains sharded over {world} GPU(s), no hot-path collective'},
+            'config': config_dict(world, args.sweeps_per_step),
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
-            'clocks': sampler.summary(t_load0, t_load1), 'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
+            'clocks': clocks,
+            'timing': {'windows': WINDOWS, 'reported': 'best window (min over windows of the max over ranks)',
+                       'windows_ms_per_step': head['windows_ms_per_step'],
+                       'warmup': f'>= {args.warmup} steps and >= {SUSTAIN_S} s of the same load issued back to back; the stream is not drained '
+                                 f'before the first window; clock sampler started (first sample awaited) before the warm-up'},
+            'configs': shapes_out,
+            'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -340,10 +584,13 @@ def main():
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='svb200', choices=['svb200', 'reference'])
+    ap.add_argument('--configs', default='c2,c3,c4,c5', help='named shapes to run (c2, the headline, always)')
     ap.add_argument('--sweeps-per-step', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-baselines', default='all', choices=['all', 'headline'],
+                    help='reference generators timed on the host for every shape, or for config 2 only')
     ap.add_argument('--e2e-steps', type=int, default=20, help='timed steps of the host-buffer (e2e) leg')
-    ap.add_argument('--no-overlap', action='store_true', help='ordinary launches instead of overlapped ones')
+    ap.add_argument('--no-overlap', action='store_true', help='ordinary launches instead of overlapped ones (config 2)')
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)')
     args = ap.parse_args()
