@@ -70,7 +70,12 @@ extern "C" {
 #define SVB_VOBS_WRAP0         2   /* sum_x n_0[x]      TorusWrapping[0]        (observable/wrapping.py:17-25) */
 #define SVB_VOBS_WRAP1         3   /* sum_x n_1[x]      TorusWrapping[1] */
 #define SVB_VOBS_ACCEPTED      4   /* accepted proposals over the sweeps of this call (neighborhood.py:117,133) */
-#define SVB_VOBS_ACCEPTANCE    5   /* sum over proposals of min(1, e^-dS)         (neighborhood.py:118,132) */
+#define SVB_VOBS_ACCEPTANCE    5   /* sum over proposals of min(1, e^-dS)         (neighborhood.py:118,132).
+                                      A MONITOR, not an observable: the FAST kernels (Philox draws, fp32-filtered decisions)
+                                      accumulate it from the fp32 ex2.approx estimate of e^-dS, so it agrees with the fp64
+                                      sum to ~1e-5 relative (the tests state rtol = 1e-5) -- outside the 1e-12 that holds for
+                                      ACTION .. WRAP1 and for every accept/reject decision (those are exact).  STRICT
+                                      arithmetic and injected draws evaluate it in fp64. */
 #define SVB_VOBS_COUNT         6
 
 #define SVB_WOBS_SUM_F2        0   /* sum_l (m - delta v / W)_l^2  (action/worldline.py:94; observable/action.py:35-47) */
@@ -78,7 +83,7 @@ extern "C" {
 #define SVB_WOBS_WRAP0         2   /* sum_x m_0[x]   (TorusWrapping = /N, observable/wrapping.py:28-39) */
 #define SVB_WOBS_WRAP1         3
 #define SVB_WOBS_ACCEPTED      4
-#define SVB_WOBS_ACCEPTANCE    5
+#define SVB_WOBS_ACCEPTANCE    5   /* as SVB_VOBS_ACCEPTANCE: an fp32-accurate monitor on the W = 1 Philox kernels */
 #define SVB_WOBS_DELTA_M_ABS   6   /* sum_x |(delta m)[x]|: 0 iff the constraint holds (action/worldline.py:54-70);
                                       evaluated by svb_worldline_observables; a sweep may report -1 = not evaluated
                                       (the move preserves delta m identically) */
@@ -109,7 +114,10 @@ const char* svb_last_error(void);
  *  W              constraint integer (finite, >= 1): dn proposals are W * [-interval_n, interval_n]
  *  seed, sweep0, chain0   Philox key / counter offsets: chain c of this call, sweep s of this call
  *                 draws from counter (site, chain0 + c, sweep0 + s); results do not depend on
- *                 how chains are split over calls or GPUs
+ *                 how chains are split over calls or GPUs.  Every entry point (generator kind) draws from its own
+ *                 Philox stream pair, so the same seed may be given to all of them.
+ *  interval_n     in [0, 31].  0 and 1 run on the fp32-filtered kernels; >= 2 on the generic fp64 kernels (there the
+ *                 Metropolis uniform's leading bits come from a second Philox block, independent of the dn digits)
  *  rng_mode       SVB_RNG_PHILOX, or SVB_RNG_INJECTED with
  *                   inj_u, inj_dphi  (n_sweeps, chains, N, N) f64
  *                   inj_dn_fwd/bwd   (n_sweeps, chains, 2, N, N) i32, indexed by the PROPOSING site
@@ -177,8 +185,8 @@ int svb_villain_sweep_tiled_swap(void* phi, int32_t* n, void* phi_ws, int32_t* n
  *                 ACCEPTANCE.  In a sequence of steps pass obs_in = the previous step's record: every record is then
  *                 complete one launch later, with exactly the bits the separate pass would have produced; the last
  *                 state's columns come from svb_villain_observables.
- * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64, 128}; anything else returns SVB_E_UNSUPPORTED (use
- * svb_villain_sweep).  A kernel launched normally after these waits for all of them, as usual.
+ * Philox draws, fp64 phi, FAST arithmetic, N in {16, 32, 64, 128}, interval_n <= 1; anything else returns
+ * SVB_E_UNSUPPORTED (use svb_villain_sweep).  A kernel launched normally after these waits for all of them, as usual.
  */
 #define SVB_OVERLAP_PREDECESSOR 1
 int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N,
@@ -193,7 +201,7 @@ int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chains, int N,
  * LinkUpdate.step (link.py:53-101: every n independently against the frozen phi) and ExactUpdate.step
  * (exact.py:50-129: n += d z, z on one colour at a time), IN PLACE, fp64 phi, STRICT arithmetic.
  *  interval_phi   SITE: dphi ~ uniform(-interval_phi, +interval_phi)
- *  interval       LINK: dn in W * ([-interval, interval] \ {0});  EXACT: z in [-interval, interval] \ {0}
+ *  interval       LINK: dn in W * ([-interval, interval] \ {0});  EXACT: z in [-interval, interval] \ {0};  1 <= interval <= 128
  *  injected       inj_u (n_sweeps, chains, N, N) f64 (LINK: (n_sweeps, chains, 2, N, N));
  *                 SITE: inj_dphi (n_sweeps, chains, N, N) f64;  LINK: inj_a (n_sweeps, chains, 2, N, N) i32 = the
  *                 proposed change, already times W;  EXACT: inj_a (n_sweeps, chains, N, N) i32 = z
@@ -251,7 +259,7 @@ int svb_villain_observables(const void* phi, int phi_dtype, const int32_t* n,
  * worldline/coexact.py:91-120), IN PLACE on m (chains,2,N,N) i32 and v (chains,1,N,N) i32.
  *  mode           SVB_WL_JOINT / SVB_WL_VORTEX / SVB_WL_COEXACT
  *  interval       proposals are drawn from [-interval, interval] \ {0} for dv (VORTEX) and t
- *                 (COEXACT); JOINT is the reference's dm in {-1,+1}, dv in {-1,0,+1}
+ *                 (COEXACT), 1 <= interval <= 128; JOINT is the reference's dm in {-1,+1}, dv in {-1,0,+1}
  *  injected       inj_u (n_sweeps, chains, N, N) f64; inj_a (n_sweeps, chains, N, N) i32 = dm (JOINT),
  *                 dv (VORTEX) or t (COEXACT); inj_b same shape = dv (JOINT only)
  */
@@ -360,7 +368,8 @@ int svb_bootstrap_mean(const double* data, const double* weight, int64_t series,
 
 /*
  * Test hook: the decision u < A of the lazily refined Metropolis uniform (leading 32 bits f known; trailing bits from word
- * `word` of the Philox block (c0, chain, sweep) in refinement stream `stream_id`: 4 Villain, 5 worldline, 7 LinkUpdate) and
+ * `word` of the Philox block (c0, chain, sweep) in refinement stream `stream_id`: 4 NeighborhoodUpdate, 5 PlaquetteUpdate,
+ * 7 LinkUpdate, 10 SiteUpdate, 12 ExactUpdate, 14 VortexUpdate, 16 CoexactUpdate) and
  * the refined uniform itself, for n caller-chosen inputs.  The sweeps reach the refinement with probability 2^-32 per
  * proposal; this makes it testable against the oracle.
  */

@@ -21,6 +21,21 @@ STREAM_WORLDLINE_REFINE = 5
 STREAM_VILLAIN_LINK = 6
 STREAM_VILLAIN_LINK_REFINE = 7
 STREAM_VILLAIN_COHOMOLOGY = 8
+STREAM_VILLAIN_SITE = 9
+STREAM_VILLAIN_SITE_REFINE = 10
+STREAM_VILLAIN_EXACT = 11
+STREAM_VILLAIN_EXACT_REFINE = 12
+STREAM_WORLDLINE_VORTEX = 13
+STREAM_WORLDLINE_VORTEX_REFINE = 14
+STREAM_WORLDLINE_COEXACT = 15
+STREAM_WORLDLINE_COEXACT_REFINE = 16
+# every generator kind owns a (proposal, refinement) stream pair: generators sharing a seed never share a Philox block
+VILLAIN_STREAMS = {'neighborhood': (STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE),
+                   'site': (STREAM_VILLAIN_SITE, STREAM_VILLAIN_SITE_REFINE),
+                   'exact': (STREAM_VILLAIN_EXACT, STREAM_VILLAIN_EXACT_REFINE)}
+WORLDLINE_STREAMS = {'joint': (STREAM_WORLDLINE_PLAQUETTE, STREAM_WORLDLINE_REFINE),
+                     'vortex': (STREAM_WORLDLINE_VORTEX, STREAM_WORLDLINE_VORTEX_REFINE),
+                     'coexact': (STREAM_WORLDLINE_COEXACT, STREAM_WORLDLINE_COEXACT_REFINE)}
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -55,7 +70,7 @@ TWO_M52 = 2.0 ** -52
 TWO_M32 = 2.0 ** -32
 
 
-def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
+def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1, kind='neighborhood'):
     """Dense per-site proposals of one chain and sweep, in the layout of villain_np.draw_neighborhood.
 
     Draw mapping, version 2 (documented in supervillain_b200/csrc/svb_villain.cu): sites (x0, x1) and (x0 ^ 8, x1)
@@ -65,14 +80,18 @@ def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
       dn   = W * (digit_i - interval_n), digit_i = the four leading base-K digits (K = 2 interval_n + 1)
              of the fraction B / 2^32, ordered (fwd 0, bwd 0, fwd 1, bwd 1)
       u    = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53), f = the remainder of B after the four digits,
-             e = word 0 or 2 (by half) of the block with the same counter in stream STREAM_VILLAIN_REFINE
+             e = word 0 or 2 (by half) of the block with the same counter in the kind's refinement stream
     (the kernels generate e only when u < A is not already decided by f; the decision is the same).
+    Given the digits, f only takes every K^4-th value; for K^4 > 256 (interval_n >= 2, "wide") the acceptance probability
+    would be visibly quantised, so there f = refinement word 0 or 2 (by half) and e = refinement word 1 or 3.
+    kind: 'neighborhood' (streams 1, 4) or 'site' (SiteUpdate = the same mapping with interval_n = 0; streams 9, 10).
     """
     x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
     c0 = ((x0 & ~8) * N + x1).astype(np.uint64)
     half = ((x0 >> 3) & 1).astype(bool)
-    w = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD)
-    r = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE)
+    stream, refine = VILLAIN_STREAMS[kind]
+    w = philox_site(seed, chain, sweep, c0, stream)
+    r = philox_site(seed, chain, sweep, c0, refine)
     A = np.where(half, w[2], w[0])
     B = np.where(half, w[3], w[1])
     e = np.where(half, r[2], r[0])
@@ -85,6 +104,8 @@ def villain_draws(seed, chain, sweep, N, W=1, interval_phi=np.pi, interval_n=1):
         prod = f * K
         digits.append((prod >> np.uint64(32)).astype(np.int64) - interval_n)
         f = prod & MASK32
+    if int(K) ** 4 > 256:
+        f, e = e, np.where(half, r[3], r[1])
     frac = (e.astype(np.float64) + 0.5) * TWO_M32
     u = np.minimum((f.astype(np.float64) + frac) * TWO_M32, 1.0 - 2.0 ** -53)
     dn_fwd = np.stack([W * digits[0], W * digits[2]]).reshape(2, N, N)
@@ -99,13 +120,15 @@ def worldline_draws(seed, chain, sweep, N, mode, interval=1):
     4 varied, x1) share the Philox block with counter word 0 = (x0 & ~24) N + x1; plaquette x0 owns word (x0 >> 3) & 3 = w:
       joint             dm = +1 if bit 31 of w else -1;  p = 3 (w << 1 mod 2^32);  dv = (p >> 32) - 1;  f = p mod 2^32
       vortex / coexact  p = (2 I) w;  idx = p >> 32 picks from [-I..-1, 1..I];  f = p mod 2^32
-      u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53), e = the same word of the block with the same counter in stream
-      STREAM_WORLDLINE_REFINE (the kernels generate e only when f alone does not decide u < A; same decision)."""
+      u = min(fl(f + (e + 1/2) 2^-32) 2^-32, 1 - 2^-53), e = the same word of the block with the same counter in the kind's
+      refinement stream (the kernels generate e only when f alone does not decide u < A; same decision).
+      Streams (proposal, refinement): joint (2, 5), vortex (13, 14), coexact (15, 16)."""
     x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
     c0 = ((x0 & ~24) * N + x1).astype(np.uint64)
     word = (x0 >> 3) & 3
-    blk = philox_site(seed, chain, sweep, c0, STREAM_WORLDLINE_PLAQUETTE)
-    ref = philox_site(seed, chain, sweep, c0, STREAM_WORLDLINE_REFINE)
+    stream, refine = WORLDLINE_STREAMS[mode]
+    blk = philox_site(seed, chain, sweep, c0, stream)
+    ref = philox_site(seed, chain, sweep, c0, refine)
     w = np.choose(word, blk)
     e = np.choose(word, ref)
     if mode == 'joint':
@@ -134,12 +157,12 @@ def _nonzero_choice(idx, interval):
 
 def villain_exact_draws(seed, chain, sweep, N, interval_z=1):
     """ExactUpdate on the GPU: the site's pair block as in villain_draws; word B picks z among the 2 I nonzero values
-    (p = (2 I) B, index = p >> 32) and the remainder leads the uniform (refined from STREAM_VILLAIN_REFINE)."""
+    (p = (2 I) B, index = p >> 32) and the remainder leads the uniform (streams STREAM_VILLAIN_EXACT / _EXACT_REFINE)."""
     x0, x1 = np.divmod(np.arange(N * N, dtype=np.int64), N)
     c0 = ((x0 & ~8) * N + x1).astype(np.uint64)
     half = ((x0 >> 3) & 1).astype(bool)
-    w = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD)
-    r = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_REFINE)
+    w = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_EXACT)
+    r = philox_site(seed, chain, sweep, c0, STREAM_VILLAIN_EXACT_REFINE)
     B = np.where(half, w[3], w[1])
     e = np.where(half, r[2], r[0])
     p = B * np.uint64(2 * interval_z)

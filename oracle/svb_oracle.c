@@ -59,7 +59,9 @@ static void philox_site(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t 
 }
 
 /* draw mapping version 2 (see svb_villain.cu): 64 bits per site from the Philox block its pair shares, and the
- * trailing bits of the uniform from the refinement stream */
+ * trailing bits of the uniform from the refinement stream (NeighborhoodUpdate: streams 1 and 4).  Wide dn intervals
+ * (K^4 > 256): given the digits, the remainder of word B only takes every K^4-th value, so the uniform's leading bits are
+ * refinement word 2 half and its trailing bits refinement word 2 half + 1 instead. */
 void svo_villain_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t site, int N, int W, double interval_phi,
                       int interval_n, double* u, double* dphi, int dn[4]) {
     uint32_t w[4], r[4];
@@ -79,6 +81,10 @@ void svo_villain_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t si
         f = (uint32_t)p;
         dn[i] = W * ((int)(p >> 32) - interval_n);
     }
+    if ((uint64_t)K * K * K * K > 256u) {
+        f = r[2 * half];
+        e = r[2 * half + 1];
+    }
     double frac = ((double)e + 0.5) * 0x1p-32;
     double uu = ((double)f + frac) * 0x1p-32;
     *u = uu < 0x1.fffffffffffffp-1 ? uu : 0x1.fffffffffffffp-1;
@@ -92,8 +98,9 @@ void svo_worldline_draw(uint64_t seed, uint64_t chain, uint64_t sweep, uint32_t 
     int x0 = (int)(site / (uint32_t)N), x1 = (int)(site % (uint32_t)N);
     uint32_t c0 = (uint32_t)((x0 & ~24) * N + x1);
     int word = (x0 >> 3) & 3;
-    philox_site(seed, chain, sweep, c0, 2u, blk);
-    philox_site(seed, chain, sweep, c0, 5u, ref);
+    /* streams (proposal, refinement) by generator kind: joint 2 / 5, vortex 13 / 14, coexact 15 / 16 */
+    philox_site(seed, chain, sweep, c0, mode == 0 ? 2u : (mode == 1 ? 13u : 15u), blk);
+    philox_site(seed, chain, sweep, c0, mode == 0 ? 5u : (mode == 1 ? 14u : 16u), ref);
     uint32_t w = blk[word], e = ref[word];
     uint64_t p;
     if (mode == 0) {

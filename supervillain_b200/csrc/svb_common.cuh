@@ -64,10 +64,17 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1,
     return Philox4{c0, c1, c2, c3};
 }
 
-// Stream ids folded into the top byte of counter word 3, so the generators never share draws.
+// Stream ids folded into the top byte of counter word 3.  EVERY generator kind has its own pair (proposal stream,
+// refinement stream), so generators that are given the same seed and advance their sweep counters in lockstep (the natural
+// setup inside Sequentially) still consume disjoint Philox blocks: SiteUpdate never re-proposes NeighborhoodUpdate's dphi,
+// ExactUpdate's z is not a function of SiteUpdate's uniform, and so on.
 enum : uint32_t { STREAM_VILLAIN_NEIGHBORHOOD = 1u, STREAM_WORLDLINE_PLAQUETTE = 2u, STREAM_WORLDLINE_WRAPPING = 3u,
                   STREAM_VILLAIN_REFINE = 4u, STREAM_WORLDLINE_REFINE = 5u,
-                  STREAM_VILLAIN_LINK = 6u, STREAM_VILLAIN_LINK_REFINE = 7u, STREAM_VILLAIN_COHOMOLOGY = 8u };
+                  STREAM_VILLAIN_LINK = 6u, STREAM_VILLAIN_LINK_REFINE = 7u, STREAM_VILLAIN_COHOMOLOGY = 8u,
+                  STREAM_VILLAIN_SITE = 9u, STREAM_VILLAIN_SITE_REFINE = 10u,
+                  STREAM_VILLAIN_EXACT = 11u, STREAM_VILLAIN_EXACT_REFINE = 12u,
+                  STREAM_WORLDLINE_VORTEX = 13u, STREAM_WORLDLINE_VORTEX_REFINE = 14u,
+                  STREAM_WORLDLINE_COEXACT = 15u, STREAM_WORLDLINE_COEXACT_REFINE = 16u };
 
 __host__ __device__ __forceinline__ Philox4 philox_site(uint64_t seed, uint64_t chain, uint64_t sweep,
                                                          uint32_t site, uint32_t stream_id) {
@@ -156,6 +163,8 @@ struct LazyUniform {
 };
 struct RefineCtx {
     unsigned long long seed, chain, sweep;
+    uint32_t stream;   // the refinement stream of the generator kind that made the proposal
+    uint32_t wide;     // Villain proposals with wide dn intervals: the leading bits came from the refinement block too (svb_villain.cu)
 };
 
 static __device__ __noinline__ double refined_uniform(uint32_t f, uint32_t c0, uint32_t word, uint32_t stream_id, unsigned long long seed,

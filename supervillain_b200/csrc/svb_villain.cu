@@ -54,6 +54,9 @@ struct VillainArgs {
     int n_sweeps;
     unsigned long long seed, sweep0, chain0;
     uint32_t round_key[20];   // Philox key schedule (k0 + r W0, k1 + r W1), r = 0..9, precomputed on the host
+    uint32_t stream_hi;       // the proposal stream of the generator kind, << 24 (counter word 3)
+    uint32_t refine_stream;   // its refinement stream
+    int wide;                 // K^4 > 256: the uniform's leading bits come from the refinement block (draw mapping below)
     const double* inj_u;
     const double* inj_dphi;
     const int32_t* inj_dn_fwd;
@@ -175,6 +178,14 @@ struct VillainConsts {
 //   u is known to lie in [f, f + 1] 2^-32 without e, which decides u < A unless A falls in that bracket
 //   (probability 2^-32 per proposal); only then is e generated.  Every kernel and the oracle implement exactly this
 //   rule, so decisions are those of the full 64-bit uniform.
+//   The remainder f is uniform, but GIVEN the digits it only takes the values of a lattice of step K^4 (it is K^4 B mod 2^32
+//   with B confined to an interval of length 2^32 / K^4): P(u < A | proposal) is quantised in units of K^4 2^-32.  For
+//   K = 3 (interval_n = 1, the reference's default) that is 1.9e-8, below the 2^-24 resolution of an fp32 uniform, and
+//   the mapping stands.  For K^4 > 256 (interval_n >= 2; "wide") f is NOT taken from word B: the leading 32 bits are word
+//   `2 half` of the refinement block and the trailing bits e its word `2 half + 1` -- independent of the proposal.
+//   Wide launches are served by the generic kernels only (a second Philox block per site pair).
+//   The streams (proposal, refinement) belong to the generator kind: NeighborhoodUpdate (1, 4), SiteUpdate (9, 10),
+//   ExactUpdate (11, 12) -- generators that share a seed never share a Philox block.
 __host__ __device__ __forceinline__ uint32_t villain_pair_counter(int x0, int x1, int N) { return (uint32_t)((x0 & ~8) * N + x1); }
 __host__ __device__ __forceinline__ uint32_t villain_pair_half(int x0) { return (uint32_t)((x0 >> 3) & 1); }
 
@@ -200,24 +211,17 @@ __device__ __forceinline__ VillainDraw villain_draw_from_words(uint32_t A, uint3
     return d;
 }
 
-// The trailing bits of the uniform, generated only when a decision needs them (cold path; svb_common.cuh).
-__device__ __forceinline__ double villain_refined_uniform(uint32_t f, uint32_t c0, uint32_t half, unsigned long long seed,
-                                                          unsigned long long chain, unsigned long long sweep) {
-    return refined_uniform(f, c0, 2 * half, STREAM_VILLAIN_REFINE, seed, chain, sweep);
-}
-
-// u < A decided from the bracket [f, f + 1] 2^-32 of u, refining only when A falls inside it.
+// u < A decided from the bracket [f, f + 1] 2^-32 of u, refining only when A falls inside it (cold path; svb_common.cuh).
 __device__ __forceinline__ bool villain_decide_lazy(double A, const VillainDraw& d, const RefineCtx& rc) {
     LazyUniform lu;
-    lu.f = d.f; lu.c0 = d.c0; lu.word = 2 * d.half;
-    return decide_lazy(A, lu, STREAM_VILLAIN_REFINE, rc);
+    lu.f = d.f; lu.c0 = d.c0; lu.word = 2 * d.half + (rc.wide ? 1u : 0u);
+    return decide_lazy(A, lu, rc.stream, rc);
 }
 
 // Philox4x32-10 with the key schedule read from kernel parameters (constant bank operands).
 __device__ __forceinline__ Philox4 philox_site_keys(const VillainArgs& a, uint64_t chain, uint64_t sweep, uint32_t site) {
     uint32_t c0 = site, c1 = (uint32_t)chain, c2 = (uint32_t)sweep;
-    uint32_t c3 = (STREAM_VILLAIN_NEIGHBORHOOD << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
-                  (uint32_t)((sweep >> 32) & 0xFFFFu);
+    uint32_t c3 = a.stream_hi | ((uint32_t)((chain >> 32) & 0xFFu) << 16) | (uint32_t)((sweep >> 32) & 0xFFFFu);
 #pragma unroll
     for (int r = 0; r < SVB_PHILOX_ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
@@ -375,7 +379,7 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
     } else {
         const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
         const uint32_t c0 = villain_pair_counter(x0, x1, a.N), half = villain_pair_half(x0);
-        const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, c0) : philox_site(a.seed, gc, gs, c0, STREAM_VILLAIN_NEIGHBORHOOD);
+        const Philox4 p = KEYS ? philox_site_keys(a, gc, gs, c0) : philox_site(a.seed, gc, gs, c0, a.stream_hi >> 24);
         if (a.exact_mode) {
             // word B: z = one of the 2 I nonzero values (exact.py:38, :94), the remainder leads the uniform; word A unused
             const uint64_t pz = (uint64_t)(half ? p.w : p.y) * (uint64_t)(2 * a.interval_n);
@@ -391,6 +395,12 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
         }
         VillainDraw d = villain_draw_from_words(half ? p.z : p.x, half ? p.w : p.y, a.interval_phi, a.interval_n);
         d.c0 = c0; d.half = half;
+        if (a.wide) {
+            // wide dn intervals: the uniform's leading bits must not be the digits' remainder (mapping above)
+            const Philox4 r = philox_site(a.seed, gc, gs, c0, a.refine_stream);
+            d.f = half ? r.z : r.x;
+            d.u = (__hiloint2double(0x43300000, (int)d.f) - 4503599627370495.5) * 2.3283064365386963e-10;
+        }
         if (dg_scale != 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) d.dg[i] *= dg_scale;
@@ -402,6 +412,7 @@ __device__ __forceinline__ VillainDraw villain_get_draw(const VillainArgs& a, lo
 __device__ __forceinline__ RefineCtx villain_refine_ctx(const VillainArgs& a, long long chain, int sweep) {
     RefineCtx rc;
     rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain; rc.sweep = a.sweep0 + (unsigned long long)sweep;
+    rc.stream = a.refine_stream; rc.wide = (uint32_t)a.wide;
     return rc;
 }
 
@@ -1332,7 +1343,13 @@ __global__ void villain_draws_kernel(long long chains, int N, int W, double inte
     const uint32_t c0 = villain_pair_counter(x0, x1, N), half = villain_pair_half(x0);
     const Philox4 p = philox_site(seed, chain0 + chain, sweep, c0, STREAM_VILLAIN_NEIGHBORHOOD);
     const VillainDraw d = villain_draw_from_words(half ? p.z : p.x, half ? p.w : p.y, interval_phi, interval_n);
-    u[i] = villain_refined_uniform(d.f, c0, half, seed, chain0 + chain, sweep);
+    const long long K = 2LL * interval_n + 1;
+    if (K * K * K * K > 256) {                      // wide: leading bits = refinement word 2 half, trailing bits = word 2 half + 1
+        const Philox4 r = philox_site(seed, chain0 + chain, sweep, c0, STREAM_VILLAIN_REFINE);
+        u[i] = refined_uniform(half ? r.z : r.x, c0, 2 * half + 1, STREAM_VILLAIN_REFINE, seed, chain0 + chain, sweep);
+    } else {
+        u[i] = refined_uniform(d.f, c0, 2 * half, STREAM_VILLAIN_REFINE, seed, chain0 + chain, sweep);
+    }
     dphi[i] = d.dphi;
     for (int k = 0; k < 4; ++k) dn[(chain * 4 + k) * V + site] = W * d.dg[k];
 }
@@ -1614,7 +1631,7 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
     const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
 #ifndef SVB_NO_FILTERED_KERNEL
     if (!INJECTED && (!STRICT || a.filtered_strict) && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out &&
-        (!a.exact_mode || a.filtered_strict)) {
+        (!a.exact_mode || a.filtered_strict) && !a.wide) {
         // production path: fp32-filtered decisions on resident fp32 residuals (svb_villain_filtered.cuh)
         switch (a.N) {
             case 16: return launch_villain_filtered<16, 16, 1>(a, stream, info);
@@ -1624,7 +1641,7 @@ static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const 
         }
     }
 #endif
-    if (!INJECTED && aligned && sizeof(real) == 8 && !a.exact_mode) {
+    if (!INJECTED && aligned && sizeof(real) == 8 && !a.exact_mode && !a.wide) {
         // One sweep per launch in FAST arithmetic: recomputing the residuals is as cheap as building the resident copy,
         // and the two-stage pipeline hides the loads (52.0 vs 53.5 us at config 2).  Fused sweeps, and STRICT
         // arithmetic always (bit-exact dS), keep the residuals resident (34.9 vs 38.3 us per sweep).
@@ -1705,6 +1722,21 @@ static int launch_villain_global(const VillainArgs& a, cudaStream_t stream) {
     return 0;
 }
 
+// Philox key schedule and the stream pair of the generator kind; `wide`: see the draw mapping at villain_pair_counter.
+static int villain_wide(int interval_n) {
+    const long long K = 2LL * interval_n + 1;
+    return (K * K * K * K > 256) ? 1 : 0;
+}
+static void villain_rng_setup(VillainArgs& a, uint32_t stream, uint32_t refine_stream, int wide) {
+    for (int r = 0; r < 10; ++r) {
+        a.round_key[2 * r] = (uint32_t)a.seed + (uint32_t)r * 0x9E3779B9u;
+        a.round_key[2 * r + 1] = (uint32_t)(a.seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    a.stream_hi = stream << 24;
+    a.refine_stream = refine_stream;
+    a.wide = wide;
+}
+
 template <typename real>
 static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, int path, cudaStream_t stream) {
     DeviceInfo info;
@@ -1713,7 +1745,7 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
 #ifndef SVB_NO_CLUSTER_KERNEL
     if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED &&
         (arith_mode != SVB_ARITH_STRICT || a.filtered_strict) && !a.accept_mask && !a.dS_out && (!a.exact_mode || a.filtered_strict) &&
-        ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
+        !a.wide && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
         // one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
         return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, stream, info);
     }
@@ -1762,10 +1794,7 @@ extern "C" int svb_villain_sweep(void* phi, int phi_dtype, int32_t* n, int64_t c
     a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
     a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
     a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
-    for (int r = 0; r < 10; ++r) {
-        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
-        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
+    villain_rng_setup(a, STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE, villain_wide(interval_n));
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = inj_dn_fwd; a.inj_dn_bwd = inj_dn_bwd;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
     a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
@@ -1788,16 +1817,15 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
     if (interval_n < 0 || interval_n > 31) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: interval_n must be in [0, 31]");
     if (!(interval_phi >= 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: interval_phi must be >= 0");
     if (n_sweeps < 1) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: n_sweeps must be >= 1 (every launch signals its epoch)");
+    if (villain_wide(interval_n))
+        return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_overlapped: interval_n > 1 is served by svb_villain_sweep (generic kernels) only");
     if (flags & ~SVB_OVERLAP_PREDECESSOR) return fail(SVB_E_PARAM, "svb_villain_sweep_overlapped: flags");
     if (chains == 0) return SVB_OK;
     VillainArgs a;
     a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
     a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
     a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
-    for (int r = 0; r < 10; ++r) {
-        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
-        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
+    villain_rng_setup(a, STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE, 0);
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0;
@@ -1825,7 +1853,8 @@ extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t ch
     if (chains < 0 || N < 3 || N > 32768) return fail(SVB_E_SHAPE, "svb_villain_decoupled: chains=%lld N=%d", (long long)chains, N);
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_decoupled: kappa must be positive");
     if (W < 1) return fail(SVB_E_PARAM, "svb_villain_decoupled: W must be a finite integer >= 1 (got %d)", W);
-    if (kind != SVB_VU_SITE && (interval < 1 || interval > 1024)) return fail(SVB_E_PARAM, "svb_villain_decoupled: interval");
+    // 2 * interval <= 256: the choice's remainder leads the uniform, whose resolution given the choice is 2 interval 2^-32 <= 2^-24
+    if (kind != SVB_VU_SITE && (interval < 1 || interval > 128)) return fail(SVB_E_PARAM, "svb_villain_decoupled: interval must be in [1, 128]");
     if (kind == SVB_VU_SITE && !(interval_phi >= 0)) return fail(SVB_E_PARAM, "svb_villain_decoupled: interval_phi must be >= 0");
     if (n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_decoupled: n_sweeps < 0");
     if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_villain_decoupled: rng_mode");
@@ -1906,10 +1935,8 @@ extern "C" int svb_villain_decoupled(int kind, void* phi, int32_t* n, int64_t ch
     a.interval_phi = (kind == SVB_VU_SITE) ? interval_phi : 0.0;
     a.interval_n = (kind == SVB_VU_SITE) ? 0 : interval;
     a.n_sweeps = n_sweeps; a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
-    for (int r = 0; r < 10; ++r) {
-        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
-        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
+    if (kind == SVB_VU_SITE) villain_rng_setup(a, STREAM_VILLAIN_SITE, STREAM_VILLAIN_SITE_REFINE, 0);
+    else villain_rng_setup(a, STREAM_VILLAIN_EXACT, STREAM_VILLAIN_EXACT_REFINE, 0);
     a.inj_u = inj_u; a.inj_dphi = inj_dphi; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
     a.exact_mode = (kind == SVB_VU_EXACT) ? 1 : 0;
@@ -2033,10 +2060,7 @@ static int villain_sweep_tiled_impl(void* phi, int32_t* n, void* phi_ws, int32_t
     a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
     a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
     a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
-    for (int r = 0; r < 10; ++r) {
-        a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
-        a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
+    villain_rng_setup(a, STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE, villain_wide(interval_n));
     a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
@@ -2046,7 +2070,7 @@ static int villain_sweep_tiled_impl(void* phi, int32_t* n, void* phi_ws, int32_t
     // per-colour global path (330 vs 385 us for a config-4 shard); the fp64 kernels (STRICT, debug outputs) keep the latter.
     const bool odd = (n_sweeps & 1) != 0;
 #ifndef SVB_NO_FILTERED_KERNEL
-    const bool all_tiled = odd && arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out;
+    const bool all_tiled = odd && arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out && !a.wide;
 #else
     const bool all_tiled = false;
 #endif
@@ -2068,7 +2092,7 @@ static int villain_sweep_tiled_impl(void* phi, int32_t* n, void* phi_ws, int32_t
         const int fuse = (obs && last) ? 1 : 0;
         if (arith_mode == SVB_ARITH_STRICT)
             villain_tiled_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
-        else if (a.accept_mask || a.dS_out)       // debug outputs: the fp64 kernel
+        else if (a.accept_mask || a.dS_out || a.wide)       // debug outputs, wide dn intervals: the fp64 kernel
             villain_tiled_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a, bufp[src], bufn[src], bufp[dst], bufn[dst], s, tps, fuse);
         else
 #ifndef SVB_NO_FILTERED_KERNEL

@@ -445,7 +445,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                             ep.half_kappa = half_kappa;
                             ep.dphi = (MODE == SVB_FILT_EXACT) ? 0.0 : villain_dphi_from_word(wA, a.interval_phi);
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
-                            ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
+                            ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
                             if (MODE == SVB_FILT_FAST) {
                                 ep.c = SVB_TWO_PI * (double)W;
 #pragma unroll

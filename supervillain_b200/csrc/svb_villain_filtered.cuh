@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             ep.half_kappa = half_kappa;
                             ep.dphi = (MODE == SVB_FILT_EXACT) ? 0.0 : villain_dphi_from_word(wA, a.interval_phi);
                             ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
-                            ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
+                            ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
                             if (MODE == SVB_FILT_FAST) {
                                 ep.c = SVB_TWO_PI * (double)W;
 #pragma unroll
@@ -689,7 +689,7 @@ __device__ __forceinline__ float villain_tiled_site(TiledShared& sh, const Villa
 #pragma unroll
         for (int q = 0; q < 4; ++q) ep.g[q] = dig[q] - a.interval_n;
         ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
-        ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs;
+        ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
         ok = villain_exact_decision(ep);
     }
     if (ok) {

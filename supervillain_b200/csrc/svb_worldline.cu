@@ -32,6 +32,7 @@ struct WorldlineArgs {
     int n_sweeps;
     unsigned long long seed, sweep0, chain0;
     uint32_t round_key[20];   // Philox key schedule precomputed on the host
+    uint32_t stream, refine_stream;   // the Philox streams of the generator kind (JOINT 2 / 5, VORTEX 13 / 14, COEXACT 15 / 16)
     const double* inj_u;
     const int32_t* inj_a;
     const int32_t* inj_b;
@@ -54,8 +55,11 @@ struct WlDraw {
 //   JOINT    dm = bit 31 of w ? +1 : -1   (rng.choice([-1,+1]), plaquette.py:58);  g = w << 1;  p = 3 g;
 //            dv = (p >> 32) - 1           (rng.choice([-1,0,+1]), plaquette.py:59);  f = p mod 2^32
 //   VORTEX / COEXACT   p = (2 I) w;  idx = p >> 32 picks from [-I..-1, 1..I] (vortex.py:39, coexact.py:40);  f = p mod 2^32
-//   and the remainder f -- uniform, independent of the choices -- is the leading 32 bits of the Metropolis uniform,
-//   refined lazily from stream STREAM_WORLDLINE_REFINE (same counter, same word).
+//   and the remainder f is the leading 32 bits of the Metropolis uniform, refined lazily from the kind's refinement stream
+//   (same counter, same word).  Given the choice, f lies on a lattice of step 6 (JOINT) or 2 I (VORTEX / COEXACT): the
+//   acceptance probability is quantised in units of at most 256 x 2^-32 = 2^-24 (I <= 128 is enforced), the resolution
+//   of an fp32 uniform.  Streams (proposal, refinement) by kind: JOINT (2, 5), VORTEX (13, 14), COEXACT (15, 16), so
+//   generators sharing a seed inside Sequentially never share a Philox block.
 __host__ __device__ __forceinline__ uint32_t worldline_quad_counter(int x0, int x1, int N) { return (uint32_t)((x0 & ~24) * N + x1); }
 __host__ __device__ __forceinline__ uint32_t worldline_quad_word(int x0) { return (uint32_t)((x0 >> 3) & 3); }
 
@@ -98,7 +102,7 @@ __device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, lon
     } else {
         const uint32_t c0 = worldline_quad_counter(x0, x1, a.N), word = worldline_quad_word(x0);
         const Philox4 p = philox_site(a.seed, a.chain0 + (unsigned long long)chain, a.sweep0 + (unsigned long long)sweep, c0,
-                                      STREAM_WORLDLINE_PLAQUETTE);
+                                      a.stream);
         WlDraw d = worldline_draw_from_word<MODE>(philox_word(p, word), a.interval);
         d.lu.c0 = c0; d.lu.word = word;
         return d;
@@ -108,13 +112,14 @@ __device__ __forceinline__ WlDraw worldline_get_draw(const WorldlineArgs& a, lon
 __device__ __forceinline__ RefineCtx worldline_refine_ctx(const WorldlineArgs& a, long long chain, int sweep) {
     RefineCtx rc;
     rc.seed = a.seed; rc.chain = a.chain0 + (unsigned long long)chain; rc.sweep = a.sweep0 + (unsigned long long)sweep;
+    rc.stream = a.refine_stream; rc.wide = 0;
     return rc;
 }
 
 // u < min(1, e^-dS) for either kind of draw: INJECTED compares the given uniform, Philox decides lazily.
 template <bool LAZY>
 __device__ __forceinline__ bool worldline_decide(double acc, const WlDraw& d, const RefineCtx& rc) {
-    if (LAZY) return decide_lazy(acc, d.lu, STREAM_WORLDLINE_REFINE, rc);
+    if (LAZY) return decide_lazy(acc, d.lu, rc.stream, rc);
     return d.u < acc;
 }
 
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(256) worldline_smem_kernel(WorldlineArgs a, in
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ Philox4 philox_plaquette_keys(const WorldlineArgs& a, uint64_t chain, uint64_t sweep, uint32_t site) {
     uint32_t c0 = site, c1 = (uint32_t)chain, c2 = (uint32_t)sweep;
-    uint32_t c3 = (STREAM_WORLDLINE_PLAQUETTE << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
+    uint32_t c3 = (a.stream << 24) | ((uint32_t)((chain >> 32) & 0xFFu) << 16) |
                   (uint32_t)((sweep >> 32) & 0xFFFFu);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -432,7 +437,7 @@ __device__ __forceinline__ PlaqOut worldline_plaquette_update_w1(int32_t* __rest
         if (r >= 0) ok = r != 0;
         else {
             acc = exp_clipped(-dS);
-            ok = decide_lazy(acc, d.lu, STREAM_WORLDLINE_REFINE, rc);
+            ok = decide_lazy(acc, d.lu, rc.stream, rc);
         }
     }
     if (ok) {
@@ -812,7 +817,7 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
     if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_worldline_sweep: kappa must be positive");
     if (W < 1) return fail(SVB_E_PARAM, "svb_worldline_sweep: W must be a finite integer >= 1 (got %d)", W);
     if (mode < SVB_WL_JOINT || mode > SVB_WL_COEXACT) return fail(SVB_E_PARAM, "svb_worldline_sweep: mode %d", mode);
-    if (mode != SVB_WL_JOINT && (interval < 1 || interval > 1024)) return fail(SVB_E_PARAM, "svb_worldline_sweep: interval");
+    if (mode != SVB_WL_JOINT && (interval < 1 || interval > 128)) return fail(SVB_E_PARAM, "svb_worldline_sweep: interval must be in [1, 128]");
     if (n_sweeps < 0) return fail(SVB_E_PARAM, "svb_worldline_sweep: n_sweeps < 0");
     if (rng_mode != SVB_RNG_PHILOX && rng_mode != SVB_RNG_INJECTED) return fail(SVB_E_PARAM, "svb_worldline_sweep: rng_mode");
     if (rng_mode == SVB_RNG_INJECTED && (!inj_u || !inj_a || (mode == SVB_WL_JOINT && !inj_b)))
@@ -827,6 +832,9 @@ extern "C" int svb_worldline_sweep(int32_t* m, int32_t* v, int64_t chains, int N
         a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
+    a.stream = (mode == SVB_WL_JOINT) ? STREAM_WORLDLINE_PLAQUETTE : (mode == SVB_WL_VORTEX) ? STREAM_WORLDLINE_VORTEX : STREAM_WORLDLINE_COEXACT;
+    a.refine_stream = (mode == SVB_WL_JOINT) ? STREAM_WORLDLINE_REFINE
+                                             : (mode == SVB_WL_VORTEX) ? STREAM_WORLDLINE_VORTEX_REFINE : STREAM_WORLDLINE_COEXACT_REFINE;
     a.inj_u = inj_u; a.inj_a = inj_a; a.inj_b = inj_b; a.obs = obs; a.accept_mask = accept_mask; a.dS_out = dS_out;
     a.ov.epochs = nullptr; a.ov.wait_epoch = 0; a.ov.signal_epoch = 0; a.ov.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -861,6 +869,9 @@ extern "C" int svb_worldline_sweep_overlapped(int32_t* m, int32_t* v, int64_t ch
         a.round_key[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
         a.round_key[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
+    a.stream = (mode == SVB_WL_JOINT) ? STREAM_WORLDLINE_PLAQUETTE : (mode == SVB_WL_VORTEX) ? STREAM_WORLDLINE_VORTEX : STREAM_WORLDLINE_COEXACT;
+    a.refine_stream = (mode == SVB_WL_JOINT) ? STREAM_WORLDLINE_REFINE
+                                             : (mode == SVB_WL_VORTEX) ? STREAM_WORLDLINE_VORTEX_REFINE : STREAM_WORLDLINE_COEXACT_REFINE;
     a.inj_u = nullptr; a.inj_a = nullptr; a.inj_b = nullptr; a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     a.ov.epochs = epochs; a.ov.wait_epoch = wait_epoch; a.ov.signal_epoch = signal_epoch;
     a.ov.grid_wait = (flags & SVB_OVERLAP_PREDECESSOR) ? 0 : 1;

@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                                 LazyUniform lu;
                                 lu.f = f; lu.c0 = c0; lu.word = (uint32_t)wd;
                                 RefineCtx rc;
-                                rc.seed = a.seed; rc.chain = gc; rc.sweep = gs;
+                                rc.seed = a.seed; rc.chain = gc; rc.sweep = gs; rc.stream = a.refine_stream; rc.wide = 0;
                                 A = (float)Ad;
-                                ok = decide_lazy(Ad, lu, STREAM_WORLDLINE_REFINE, rc);
+                                ok = decide_lazy(Ad, lu, rc.stream, rc);
                             }
                         }
                         sum_A += A;

@@ -9,8 +9,8 @@ axis.  All chains live in HBM for the whole run; one kernel launch advances ever
 `sweeps_per_step` sweeps and reduces the observables; only the per-chain observable record (a few
 doubles per chain) crosses PCIe per step, and configurations only at the stride asked for.
 """
+import json
 import os
-import pickle
 
 import numpy as np
 import torch
@@ -247,14 +247,18 @@ class BatchedEnsemble:
 
     def save(self, path):
         """Checkpoint: the resident fields, the records, the sample index and the (action, generator) pair -- whose state is
-        the Philox (seed, counter) -- in one .npz.  (The reference stores ensembles as HDF5, supervillain/h5/; h5py is not
-        part of this environment.)"""
+        the Philox (seed, counter) -- in one .npz.  Everything is plain data: the action and the generator are stored as JSON
+        (class names from a whitelist, constructor arguments, counters; generator/_state.py), so reading a checkpoint never
+        executes code.  (The reference stores ensembles as HDF5, supervillain/h5/; h5py is not part of this environment.)"""
         if self.fields is None:
             raise ValueError('nothing to save: generate first')
-        blob = np.frombuffer(pickle.dumps((self.Action, self.__dict__.get('generator'))), dtype=np.uint8)
+        from .generator import _state
+        state = {'format': 1, 'action': _state.describe_action(self.Action),
+                 'generator': _state.describe_generator(self.__dict__.get('generator'))}
+        blob = np.frombuffer(json.dumps(state).encode('utf-8'), dtype=np.uint8)
         arrays = dict(field0=self.fields[0].cpu().numpy(), field1=self.fields[1].cpu().numpy(), record=self.record, index=self.index,
                       meta=np.array([self.chains, self.chain0, self.sweeps_per_step, self.steps, self.__dict__.get('keep_every', 0)],
-                                    dtype=np.int64), state=blob)
+                                    dtype=np.int64), state_json=blob)
         if self.__dict__.get('kappa_chain') is not None:
             arrays['kappa_chain'] = self.kappa_chain.cpu().numpy()
         for k, v in self.__dict__.get('configuration', {}).items():
@@ -264,9 +268,17 @@ class BatchedEnsemble:
 
     @classmethod
     def load(cls, path, device=None):
-        """A BatchedEnsemble as `save` left it (fields back on the device), ready for `continue_from`."""
+        """A BatchedEnsemble as `save` left it (fields back on the device), ready for `continue_from`.  The action and the
+        generator are rebuilt from plain JSON through a whitelist of classes; a checkpoint of an earlier build (which held
+        a pickle) is refused rather than unpickled."""
+        from .generator import _state
         with np.load(path, allow_pickle=False) as z:
-            action, generator = pickle.loads(z['state'].tobytes())
+            if 'state_json' not in z.files:
+                raise ValueError('this checkpoint holds a pickled (action, generator) pair from an earlier build; it is not read '
+                                 '(unpickling executes code) -- regenerate it with this version')
+            state = json.loads(z['state_json'].tobytes().decode('utf-8'))
+            action = _state.rebuild_action(state['action'])
+            generator = _state.rebuild_generator(state['generator'], action)
             chains, chain0, sweeps_per_step, steps = (int(x) for x in z['meta'][:4])
             keep_every = int(z['meta'][4]) if len(z['meta']) > 4 else 0       # checkpoints of earlier builds have four entries
             e = cls(action, chains, device=device, chain0=chain0)
@@ -397,11 +409,13 @@ class BatchedEnsemble:
         L = self.Action.Lattice
         degree = {'phi': 0, 'n': 1, 'm': 1, 'v': 2}
         cols = {k: Batch(v[c], cls=Form, degree=degree[k], lattice=L) for k, v in self.configuration.items()}
-        stride = self.steps // len(next(iter(cols.values())))
+        draws = len(next(iter(cols.values())))
+        stride = self.__dict__.get('keep_every', 0) or self.steps // max(draws, 1)
+        kept = stride * (1 + np.arange(draws)) - 1                  # the steps whose configurations were kept
         for name, v in self.observables.items():
-            cols[name] = Batch(v[c][stride - 1::stride])
+            cols[name] = Batch(np.ascontiguousarray(v[c][kept]))
         e = Ensemble(self.Action).from_configurations(Configurations(cols))
-        e.index = Batch(self.index[stride - 1::stride])
+        e.index = Batch(np.asarray(self.index)[kept])
         e.index_stride = stride * self.sweeps_per_step
         e.weight = Batch(np.ones(len(e.index)))
         e.generator = self.generator

@@ -18,7 +18,7 @@ _PATHS = {'auto': PATH_AUTO, 'smem': PATH_SMEM, 'global': PATH_GLOBAL}
 _TILE = 32
 _SMEM_MAX_N = 96            # largest fp64 lattice whose chain fits one SM's shared memory
 _CLUSTER_N = (128,)         # lattices svb_villain_sweep spreads over a thread-block cluster (svb_villain_cluster.cuh)
-_workspaces = {}            # (device, chains, N) -> (phi_ws, n_ws) for the tiled ping-pong path
+_workspaces = {}            # (device, stream) -> (chains, N, phi_ws, n_ws): the tiled path's ping-pong workspace, ONE PER STREAM
 _ARITH = {'strict': ARITH_STRICT, 'fast': ARITH_FAST}
 _WL_MODES = {'joint': WL_JOINT, 'vortex': WL_VORTEX, 'coexact': WL_COEXACT}
 _OPS = {'d': _lib.OP_D, 'delta': _lib.OP_DELTA, 'face_sum': _lib.OP_FACE_SUM, 'coface_sum': _lib.OP_COFACE_SUM}
@@ -75,11 +75,14 @@ def villain_sweep(phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, n_s
         raise NotImplementedError('the tiled path needs fp64 phi, Philox draws and N a multiple of 32')
     cluster_ok = (tiled_ok and N in _CLUSTER_N and arithmetic == 'fast' and accept_mask is None and dS_out is None)
     if path == 'tiled' or (path == 'auto' and tiled_ok and N > _SMEM_MAX_N and not cluster_ok):
-        key = (phi.device, chains, N)
-        ws = _workspaces.get(key)
-        if ws is None:
-            _workspaces.clear()                      # one workspace at a time: these are the large lattices
-            ws = _workspaces[key] = (torch.empty_like(phi), torch.empty_like(n))
+        # The workspace belongs to the stream the sweep is enqueued on: two streams sweeping at once (HostStepper's chunks)
+        # never share one, and a workspace is only ever replaced by the stream that used it -- it was allocated with that
+        # stream current, so the caching allocator hands its memory on in that stream's order.
+        key = (phi.device, _stream())
+        held = _workspaces.get(key)
+        if held is None or held[0] != chains or held[1] != N:
+            held = _workspaces[key] = (chains, N, torch.empty_like(phi), torch.empty_like(n))
+        ws = held[2:]
         _lib.check(lib.svb_villain_sweep_tiled(
             p_phi, p_n, ws[0].data_ptr(), ws[1].data_ptr(), chains, N, float(kappa),
             _opt(kappa_chain, 'kappa_chain', (torch.float64,), (chains,)), int(W), float(interval_phi), int(interval_n),
@@ -195,8 +198,8 @@ class VillainOverlappedSweeps:
     def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None):
         self.lib = _lib.load()
         self.chains, self.N = _fields_shape(phi, 'phi', 1)
-        if self.N not in VILLAIN_OVERLAP_SIZES or phi.dtype != torch.float64:
-            raise NotImplementedError('overlapped sweeps need fp64 phi and N in (16, 32, 64, 128)')
+        if self.N not in VILLAIN_OVERLAP_SIZES or phi.dtype != torch.float64 or int(interval_n) > 1:
+            raise NotImplementedError('overlapped sweeps need fp64 phi, N in (16, 32, 64, 128) and interval_n <= 1')
         self.p_phi = _dev(phi, 'phi', (torch.float64,))
         self.p_n = _dev(n, 'n', (torch.int32,), (self.chains, 2, self.N, self.N))
         if W != W or W == float('inf') or int(W) != W:

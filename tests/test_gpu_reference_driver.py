@@ -95,7 +95,7 @@ def test_reference_sequentially_of_gpu_plaquette_and_wrapping_updates():
     assert np.abs(m).max() > 0 and np.abs(v).max() > 0
     for t in (0, steps // 2, steps - 1):
         cfg = E.configuration[t]
-        assert S.valid(cfg['m'])
+        assert S.valid(cfg)
         assert np.isfinite(S(cfg['m'], cfg['v']))
     assert P.sweeps == steps and H.sweeps == steps
     assert 'PlaquetteUpdate' in str(G) and 'WrappingUpdate' in str(G)

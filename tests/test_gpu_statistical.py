@@ -90,3 +90,34 @@ def test_villain_decoupled_updates_match_reference_hammer():
     E = svb.BatchedEnsemble(S, 1024).generate(120, G, 'cold', sweeps_per_step=40)
     check(E, anchor('Villain', 'Hammer', N, kappa), discard=40)
     check(E, anchor('Worldline', 'Hammer', N, kappa), discard=40)
+
+
+def test_villain_neighborhood_with_wide_dn_proposals_matches_reference_hammer():
+    """interval_n = 2 (K = 5, K^4 = 625 > 256: the "wide" draw mapping, where the uniform's leading bits come from the
+    refinement block instead of the digits' remainder, svb_villain.cu) samples the same ensemble: the target distribution
+    does not depend on the proposal width.  Acceptance is ~5 x lower than at interval_n = 1, hence the longer run."""
+    N, kappa = 8, 0.3
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    G = NeighborhoodUpdate(S, interval_n=2, seed=777)
+    E = svb.BatchedEnsemble(S, 2048).generate(100, G, 'cold', sweeps_per_step=2000)
+    check(E, anchor('Villain', 'Hammer', N, kappa), discard=40)
+    check(E, anchor('Worldline', 'Hammer', N, kappa), discard=40)
+
+
+def test_generators_sharing_one_seed_still_sample_the_target():
+    """Every generator kind draws from its own Philox stream pair (svb_common.cuh), so handing ONE seed to all members of a
+    Sequentially -- whose sweep counters then advance in lockstep -- is safe: the composite chain samples the same ensemble
+    as with hand-picked distinct seeds."""
+    from supervillain_b200.generator.villain import CohomologyUpdate, ExactUpdate, LinkUpdate, SiteUpdate
+    from supervillain_b200.generator.worldline import CoexactUpdate, VortexUpdate
+    N, kappa, seed = 8, 0.3, 2026
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    G = Sequentially((NeighborhoodUpdate(S, seed=seed), SiteUpdate(S, seed=seed), LinkUpdate(S, seed=seed), ExactUpdate(S, seed=seed),
+                      CohomologyUpdate(S, seed=seed)))
+    E = svb.BatchedEnsemble(S, 1024).generate(120, G, 'cold', sweeps_per_step=40)
+    check(E, anchor('Villain', 'Hammer', N, kappa), discard=40)
+    check(E, anchor('Worldline', 'Hammer', N, kappa), discard=40)
+    Wl = svb.Worldline(svb.Lattice2D(N), kappa)
+    H = Sequentially((PlaquetteUpdate(Wl, seed=seed), VortexUpdate(Wl, seed=seed), CoexactUpdate(Wl, seed=seed), WrappingUpdate(Wl, seed=seed)))
+    F = svb.BatchedEnsemble(Wl, 1024).generate(150, H, 'cold', sweeps_per_step=10)
+    check(F, anchor('Worldline', 'Hammer', N, kappa), discard=50)

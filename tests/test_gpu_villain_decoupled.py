@@ -64,7 +64,7 @@ def test_philox_mode_matches_oracle_replay(kind, N, W, kappa, interval):
         for s in range(sweeps):
             st = {}
             if kind == 'site':
-                d = P.villain_draws(seed, 2 + c, 5 + s, N, W=W, interval_phi=ipi, interval_n=0)
+                d = P.villain_draws(seed, 2 + c, 5 + s, N, W=W, interval_phi=ipi, interval_n=0, kind='site')
                 p, q = V.neighborhood_step_dense(p, q, kappa, d, stats=st)
             elif kind == 'link':
                 p, q = V.link_step_dense(p, q, kappa, P.villain_link_draws(seed, 2 + c, 5 + s, N, W=W, interval_n=interval), stats=st)

@@ -284,3 +284,71 @@ def test_batched_worldline_ensemble_hands_a_chain_to_the_reference_package():
         inline, measured = np.asarray(getattr(R, name)), np.asarray(getattr(bare, name))
         assert inline.shape == measured.shape, name
         assert np.allclose(inline, measured, rtol=1e-12, atol=1e-12), name
+
+
+def test_checkpoint_state_is_plain_data_and_round_trips():
+    """generator/_state.py: an (action, generator) pair becomes JSON (no pickle, no class paths) and comes back through the
+    whitelisted constructors with its Philox (seed, counter), report counters and -- if assigned -- the numpy rng state."""
+    import json
+    import supervillain_b200 as svb
+    from supervillain_b200.generator import _state
+    from supervillain_b200.generator.combining import KeepEvery, Sequentially
+    from supervillain_b200.generator.villain import CohomologyUpdate, ExactUpdate, LinkUpdate, NeighborhoodUpdate, SiteUpdate
+    from supervillain_b200.generator.worldline import PlaquetteUpdate, WrappingUpdate
+    S = svb.Villain(svb.Lattice2D(12), 0.37, W=2)
+    G = NeighborhoodUpdate(S, 1.5, 2, seed=2**63 + 5, inline=('ActionDensity',), arithmetic='strict')
+    G.counter, G.accepted, G.proposed, G.acceptance, G.sweeps = 17, 3, 99, 0.25, 4
+    G.rng = np.random.default_rng(99)
+    G.rng.uniform(size=7)
+    combo = KeepEvery(5, Sequentially((G, SiteUpdate(S, 0.7, seed=1), LinkUpdate(S, 2, seed=2), ExactUpdate(S, 3, seed=3),
+                                       CohomologyUpdate(S, 1, seed=4))), blocked_inline=False)
+    text = json.dumps({'action': _state.describe_action(S), 'generator': _state.describe_generator(combo)})
+    d = json.loads(text)
+    S2 = _state.rebuild_action(d['action'])
+    assert type(S2).__name__ == 'Villain' and (S2.Lattice.N, S2.kappa, S2.W) == (12, 0.37, 2)
+    back = _state.rebuild_generator(d['generator'], S2)
+    assert str(back) == str(combo) and back.stride == 5 and back.blocked_inline is False
+    G2 = back.generator.generators[0]
+    assert (G2.seed, G2.counter, G2.accepted, G2.proposed, G2.acceptance, G2.sweeps) == (2**63 + 5, 17, 3, 99, 0.25, 4)
+    assert (G2.interval_phi, G2.interval_n, G2.inline, G2.arithmetic) == (1.5, 2, ('ActionDensity',), 'strict')
+    assert (G2.rng.uniform(size=3) == G.rng.uniform(size=3)).all()                  # the numpy stream continues where it was
+    assert [g.seed for g in back.generator.generators[1:]] == [1, 2, 3, 4]
+    assert back.generator.generators[3].zs == (-3, -2, -1, 1, 2, 3)
+    Wl = svb.Worldline(svb.Lattice2D(8), 0.5)
+    pair = Sequentially((PlaquetteUpdate(Wl, seed=7, inline=('WindingSquared',)), WrappingUpdate(Wl, 2, seed=8)))
+    back = _state.rebuild_generator(json.loads(json.dumps(_state.describe_generator(pair))), Wl)
+    assert str(back) == str(pair) and back.generators[1].interval_w == 2 and back.generators[0].inline == ('WindingSquared',)
+    with pytest.raises(TypeError):
+        _state.describe_generator(object())
+    with pytest.raises(ValueError):
+        _state.rebuild_generator({'class': 'os.system'}, S)
+
+
+def test_checkpoints_of_earlier_builds_are_refused_not_unpickled(tmp_path):
+    import pickle
+    import supervillain_b200 as svb
+    path = tmp_path / 'old.npz'
+    np.savez(path, state=np.frombuffer(pickle.dumps(('anything',)), dtype=np.uint8), meta=np.zeros(5, dtype=np.int64))
+    with pytest.raises(ValueError, match='pickled'):
+        svb.BatchedEnsemble.load(path, device='cpu')
+
+
+def test_chain_pairs_kept_configurations_with_their_own_steps():
+    """BatchedEnsemble.chain(): with steps not a multiple of keep_every (11 steps, every 4th kept -> steps 3 and 7) the
+    observable columns and the index come from exactly those steps."""
+    import supervillain_b200 as svb
+    from supervillain_b200._lib import VOBS_ACTION, VOBS_COUNT
+    from supervillain_b200.generator.villain import NeighborhoodUpdate, villain_inline_values
+    N, chains, steps, keep, sps = 4, 2, 11, 4, 3
+    S = svb.Villain(svb.Lattice2D(N), 0.5)
+    E = svb.BatchedEnsemble(S, chains, device='cpu')
+    rec = np.zeros((chains, steps, VOBS_COUNT))
+    rec[..., VOBS_ACTION] = 100 * np.arange(chains)[:, None] + np.arange(steps)[None, :]
+    E.record, E.steps, E.sweeps_per_step, E.keep_every = rec, steps, sps, keep
+    E.index = sps * (1 + np.arange(steps))
+    E.generator = NeighborhoodUpdate(S)
+    E.configuration = {'phi': np.zeros((chains, 2, 1, N, N)), 'n': np.zeros((chains, 2, 2, N, N), dtype=np.int64)}
+    E.observables = villain_inline_values(rec, N, 0.5)
+    c = E.chain(1)
+    assert list(np.asarray(c.index)) == [sps * 4, sps * 8] and c.index_stride == keep * sps
+    assert list(np.asarray(c.ActionDensity) * N * N) == [103.0, 107.0]

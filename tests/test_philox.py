@@ -49,7 +49,8 @@ def test_worldline_draw_mapping_ranges():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('stream_id', [P.STREAM_VILLAIN_REFINE, P.STREAM_WORLDLINE_REFINE, P.STREAM_VILLAIN_LINK_REFINE])
+@pytest.mark.parametrize('stream_id', [P.STREAM_VILLAIN_REFINE, P.STREAM_WORLDLINE_REFINE, P.STREAM_VILLAIN_LINK_REFINE, P.STREAM_VILLAIN_SITE_REFINE,
+                                       P.STREAM_VILLAIN_EXACT_REFINE, P.STREAM_WORLDLINE_VORTEX_REFINE, P.STREAM_WORLDLINE_COEXACT_REFINE])
 def test_lazy_uniform_refinement_matches_oracle(stream_id):
     """The refinement branch of the lazily refined uniform is reached with probability 2^-32 per proposal, i.e. never in a
     sweep test.  svb_debug_decide_lazy forces it: acceptance probabilities placed inside the bracket [f, f + 1] 2^-32 of
@@ -80,3 +81,23 @@ def test_lazy_uniform_refinement_matches_oracle(stream_id):
                                                  sweep, dec.data_ptr(), u.data_ptr(), torch.cuda.current_stream().cuda_stream))
     assert (u.cpu().numpy() == u_ref).all()
     assert (dec.cpu().numpy().astype(bool) == (u_ref < A)).all()
+
+
+def test_uniform_does_not_depend_on_wide_proposals():
+    """Given the four base-K digits, the remainder of word B only takes every K^4-th value, so P(accept | proposal) would
+    be quantised in units of K^4 2^-32.  At K = 3 (interval_n = 1) that is 1.9e-8 and the mapping keeps the remainder; for
+    K^4 > 256 the leading bits of u must come from elsewhere (the refinement block).  Check both regimes in the oracle's
+    statement of the mapping (the kernels are compared with it bit for bit in the GPU tests)."""
+    N = 64
+    for interval_n, lattice_expected in ((1, True), (2, False), (5, False)):
+        K4 = (2 * interval_n + 1) ** 4
+        d = P.villain_draws(seed=99, chain=3, sweep=1, N=N, interval_n=interval_n)
+        lead = np.floor(d['u'] * 2.0**32).astype(np.int64)                 # the leading 32 bits of the uniform
+        digits = np.stack([d['dn_fwd'][0], d['dn_bwd'][0], d['dn_fwd'][1], d['dn_bwd'][1]]).reshape(4, -1) + interval_n
+        code = ((digits[0] * (2 * interval_n + 1) + digits[1]) * (2 * interval_n + 1) + digits[2]) * (2 * interval_n + 1) + digits[3]
+        # remainder of word B after digits `code`: f = K^4 B - code 2^32, so (f + code 2^32) is a multiple of K^4
+        on_lattice = ((lead.reshape(-1) + code * 2**32) % K4 == 0)
+        if lattice_expected:
+            assert on_lattice.all()
+        else:
+            assert on_lattice.mean() < 5.0 / K4 + 0.01
