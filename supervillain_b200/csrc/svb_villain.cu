@@ -20,6 +20,8 @@
 
 #include <type_traits>
 
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
 #include "svb_common.cuh"
 
 #ifndef SVB_SITE_UNROLL
@@ -1603,6 +1605,7 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 }
 
 #include "svb_villain_filtered.cuh"
+#include "svb_villain_stream.cuh"
 #include "svb_villain_cluster.cuh"
 #include "svb_villain_link.cuh"
 #ifndef SVB_CLUSTER_TPB
@@ -1616,6 +1619,15 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 #endif
 
 #ifndef SVB_FILT_MINB32
+#ifndef SVB_STREAM_MINB32
+#define SVB_STREAM_MINB32 8     /* CTAs per SM the streaming chain kernel is compiled for: 4 N threads each */
+#endif
+#ifndef SVB_STREAM_MINB64
+#define SVB_STREAM_MINB64 4
+#endif
+#ifndef SVB_STREAM_MINB128
+#define SVB_STREAM_MINB128 2
+#endif
 #define SVB_FILT_MINB32 8        /* 64 registers per thread: 8 CTAs = 32 warps per SM (28.5 vs 30.0 us at config 2) */
 #endif
 #define SVB_FILT_STAGES 1
@@ -1626,9 +1638,39 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 #define SVB_RESID_T32 128
 #endif
 
+// Which kernel family serves the production sweeps (Philox, fp64, FAST): the streaming kernels (svb_villain_stream.cuh,
+// default) or the shared-memory-resident ones (svb_villain_filtered.cuh / svb_villain_cluster.cuh; SVB_VILLAIN_KERNEL=smem in
+// the environment, read per call so that one process can time both).
+static bool villain_stream_enabled() {
+    const char* e = getenv("SVB_VILLAIN_KERNEL");
+    return !(e && e[0] == 's' && e[1] == 'm');
+}
+// The chain-per-CTA streaming kernel is an experiment kept for A/B runs (SVB_VILLAIN_KERNEL=stream): it is bound by L1
+// wavefronts (nine global loads per site), 48.7 us per step at config 2 against 28.2 us for the shared-memory kernel and
+// 171 us at L = 128 against 157 us for the SPARSE cluster kernel.
+static bool villain_stream_chain_enabled(int N) {
+    const char* e = getenv("SVB_VILLAIN_KERNEL");
+    (void)N;
+    return e && e[0] == 's' && e[1] == 't';
+}
+static int launch_villain_stream_by_size(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    switch (a.N) {
+        case 16: return launch_villain_stream_chain<16, 16>(a, stream, info);
+        case 32: return launch_villain_stream_chain<32, SVB_STREAM_MINB32>(a, stream, info);
+        case 64: return launch_villain_stream_chain<64, SVB_STREAM_MINB64>(a, stream, info);
+        default: return launch_villain_stream_chain<128, SVB_STREAM_MINB128>(a, stream, info);
+    }
+}
+static bool villain_stream_serves(const VillainArgs& a, bool injected, bool strict, size_t real_size) {
+    return !injected && !strict && !a.filtered_strict && !a.exact_mode && !a.wide && real_size == 8 && !a.accept_mask && !a.dS_out &&
+           (a.N == 16 || a.N == 32 || a.N == 64 || a.N == 128) && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0) &&
+           villain_stream_chain_enabled(a.N);
+}
+
 template <typename real, bool INJECTED, bool STRICT>
 static int launch_villain_smem(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     const bool aligned = ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0);
+    if (villain_stream_serves(a, INJECTED, STRICT, sizeof(real))) return launch_villain_stream_by_size(a, stream, info);
 #ifndef SVB_NO_FILTERED_KERNEL
     if (!INJECTED && (!STRICT || a.filtered_strict) && aligned && sizeof(real) == 8 && !a.accept_mask && !a.dS_out &&
         (!a.exact_mode || a.filtered_strict) && !a.wide) {
@@ -1742,6 +1784,8 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
     DeviceInfo info;
     int rc = get_device_info(info);
     if (rc) return rc;
+    if (path != SVB_PATH_GLOBAL && villain_stream_serves(a, rng_mode == SVB_RNG_INJECTED, arith_mode == SVB_ARITH_STRICT, sizeof(real)))
+        return launch_villain_stream_by_size(a, stream, info);
 #ifndef SVB_NO_CLUSTER_KERNEL
     if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED &&
         (arith_mode != SVB_ARITH_STRICT || a.filtered_strict) && !a.accept_mask && !a.dS_out && (!a.exact_mode || a.filtered_strict) &&
@@ -1835,6 +1879,7 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
     int rc = get_device_info(info);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (villain_stream_serves(a, false, false, 8)) return launch_villain_stream_by_size(a, st, info);
     switch (N) {
         case 16: return launch_villain_filtered<16, 16, 1>(a, st, info);
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
@@ -2065,6 +2110,24 @@ static int villain_sweep_tiled_impl(void* phi, int32_t* n, void* phi_ws, int32_t
     a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
     a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0; a.obs_in = nullptr; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (arith_mode != SVB_ARITH_STRICT && !accept_mask && !dS_out && !a.wide && N % 16 == 0 && ((uintptr_t)phi % 16 == 0) &&
+        ((uintptr_t)n % 16 == 0) && villain_stream_enabled()) {
+        // the streaming colour passes (svb_villain_stream.cuh): in place, no workspace, the state stays in (phi, n)
+        DeviceInfo info;
+        int rc = get_device_info(info);
+        if (rc) return rc;
+        if (obs) {
+            villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs, chains, 0);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+        // TMA-staged tiles where the tile shape divides the lattice (SVB_VILLAIN_PASS=stream: straight from global memory)
+        const char* ep = getenv("SVB_VILLAIN_PASS");
+        const bool tma = N % kTileCols == 0 && chains * 2 < 0x7fffffffLL && !(ep && ep[0] == 's');
+        rc = tma ? launch_villain_tile_passes(a, nullptr, obs, st, info) : launch_villain_stream_passes(a, nullptr, obs, st, info);
+        if (rc) return rc;
+        if (obs) return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
+        return SVB_OK;
+    }
     // An even number of ping-pong sweeps ends in (phi, n); an odd count ends in the workspace.  The filtered kernel is fast
     // enough that copying the state back (two device-to-device copies) beats doing the last sweep in place with the
     // per-colour global path (330 vs 385 us for a config-4 shard); the fp64 kernels (STRICT, debug outputs) keep the latter.

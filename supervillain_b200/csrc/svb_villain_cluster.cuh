@@ -119,7 +119,11 @@ constexpr int cluster_min_blocks(int NT, int CL, int TPB, int STAGES) {
 }
 // MODE: SVB_FILT_FAST (the NeighborhoodUpdate sweep), SVB_FILT_STRICT / SVB_FILT_SITE / SVB_FILT_EXACT (the decoupled updates with
 // a STRICT cold path), exactly as in villain_smem_filtered_kernel.
-template <int NT, int CL, int TPB, int STAGES, bool OVERLAP, int MODE>
+// SPARSE (one sweep per launch, no record of the state after it), as in villain_smem_filtered_kernel: the staged phi and n are
+// dead once the residuals of EVERY strip are built (cluster barrier S2), accepted proposals go to global memory as
+// fire-and-forget reductions, the exact path reads global memory, nothing is stored back, and the next chain's strip is
+// loaded while this one is swept -- the store -> load -> barrier phase that bounded this kernel is gone.
+template <int NT, int CL, int TPB, int STAGES, bool OVERLAP, int MODE, bool SPARSE = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_blocks(NT, CL, TPB, STAGES))
     villain_cluster_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -165,6 +169,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
     const bool obs_of_input = a.obs_in != nullptr;
     const bool want_obs = a.obs != nullptr && !obs_of_input;
     static_assert(!(OVERLAP && MODE != SVB_FILT_FAST), "overlapped launches serve the NeighborhoodUpdate sweep");
+    static_assert(!SPARSE || (MODE == SVB_FILT_FAST && STAGES == 1), "SPARSE serves the NeighborhoodUpdate sweep, one stage");
     const int interval_n = MODE == SVB_FILT_SITE ? 0 : a.interval_n;
     const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
     const int W = MODE == SVB_FILT_EXACT ? 1 : a.W, mWI = -W * interval_n;
@@ -305,6 +310,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
         sphi = reinterpret_cast<double*>(smem_raw + (size_t)b * stage_bytes);
         sn0 = reinterpret_cast<int32_t*>(smem_raw + (size_t)b * stage_bytes + bytes_phi);
         sn1 = sn0 + VL;
+        // SPARSE: the chain in global memory (accepted proposals and the exact path go there)
+        double* gphi = reinterpret_cast<double*>(a.phi) + chain * V;
+        int32_t* gn0 = a.n + chain * 2 * V;
+        uint32_t seen_sparse = 0;
+        if (SPARSE && tid == 0 && next < a.chains) seen_sparse = peek_epoch(next);
         mbar_wait(&bar[b], (uint32_t)((STAGES == 2 ? (it >> 1) : it) & 1));
         if (STAGES == 1 && tid == 0 && next < a.chains) prefetch_l2(next);
         cluster_arrive();                                          // S1: every strip of the chain has landed (waited for below)
@@ -365,6 +375,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                 for (int p = 0; p < PER / 2; ++p)
                     if (p < SVB_CLUSTER_PRE) bits_p[p] = philox_site_keys(a, gc, gs, (uint32_t)((rank * ROWS + r0 + 16 * p) * N + x1));
                 cluster_wait();                                    // S2 / S3: the previous pass is complete in every strip
+                // SPARSE: every strip's residuals are built -- nobody reads any strip's staged phi and n again
+                if (SPARSE && c == 0 && tid == 0 && next < a.chains) issue_load(next, 0, seen_sparse);
                 if (c == 0 && obs_of_input && s == 0) cta_share(true, false);
 #pragma unroll
                 for (int p = 0; p < PER / 2; ++p) {
@@ -430,7 +442,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                         const int* dig = h ? digB : digA;
                         const float dif = h ? diff.y : diff.x, bnd = h ? band.y : band.x;
                         bool ok = dif < 0.0f;
-                        if (!(fabsf(dif) > bnd) || f < 65536u) {
+                        if (SPARSE && (!(fabsf(dif) > bnd) || f < 65536u)) {
+                            const int gx = rank * ROWS + r0 + 8 * q;
+                            ExactProposal ep;
+                            ep.phi = gphi; ep.n0 = gn0; ep.n1 = gn0 + V;
+                            ep.i_c = gx * N + x1;
+                            ep.i_b0 = ((gx - 1) & (N - 1)) * N + x1;
+                            ep.i_b1 = gx * N + ((x1 - 1) & (N - 1));
+                            ep.i_f0 = ((gx + 1) & (N - 1)) * N + x1;
+                            ep.i_f1 = gx * N + ((x1 + 1) & (N - 1));
+                            ep.half_kappa = half_kappa;
+                            ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
+                            ep.d.f = f; ep.d.c0 = c0; ep.d.half = (uint32_t)h;
+                            ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
+                            ep.c = SVB_TWO_PI * (double)W;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) ep.g[i] = dig[i] - interval_n;
+                            ok = villain_exact_decision(ep);
+                        }
+                        if (!SPARSE && (!(fabsf(dif) > bnd) || f < 65536u)) {
                             const int lx0 = r0 + 8 * q;
                             ExactProposalPtr ep;
                             ep.p_c = sphi + lx0 * N + x1;
@@ -461,12 +491,23 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                         n_acc += ok ? 1 : 0;
                         if (ok) {
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
+                            if (SPARSE) {
+                                // straight to global memory: one fp64 reduction (rounds once, to nearest, like phi + dphi) and four
+                                // integer ones; nothing waits for them
+                                const int gx = rank * ROWS + r0 + 8 * q, ic = gx * N + x1;
+                                atomicAdd(gphi + ic, __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
+                                atomicAdd(gn0 + ic, W * dig[0] + mWI);
+                                atomicAdd(gn0 + ((gx - 1) & (N - 1)) * N + x1, W * dig[1] + mWI);
+                                atomicAdd(gn0 + V + ic, W * dig[2] + mWI);
+                                atomicAdd(gn0 + V + gx * N + ((x1 - 1) & (N - 1)), W * dig[3] + mWI);
+                            } else {
                             Pc[2 * Q * q] = __dadd_rn(Pc[2 * Q * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
                             if (MODE != SVB_FILT_SITE) {
                                 atomicAdd(N0c + 2 * Q * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
                                 atomicAdd(n0b_site, W * dig[1] + mWI);
                                 atomicAdd(N1c + 2 * Q * q, W * dig[2] + mWI);
                                 atomicAdd(N1b + 2 * Q * q, W * dig[3] + mWI);
+                            }
                             }
                             R0own[Q * q] = h ? n_f0.y : n_f0.x;
                             *r0b_site = h ? n_b0.y : n_b0.x;
@@ -477,7 +518,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                 }
                 if (s == a.n_sweeps - 1 && c == 1) {
                     if (a.obs) chain_partials<false, true>(red_state, red_count, lane, warp, 0.0, 0, 0, 0, sum_A_all + (double)sum_A, n_acc);
-                    asm volatile("fence.proxy.async;" ::: "memory");   // phi / n writes (also into the previous strip) -> bulk store
+                    if (!SPARSE) asm volatile("fence.proxy.async;" ::: "memory");   // phi / n writes (also into the previous strip) -> bulk store
                 }
                 cluster_arrive(HN > 32 ? HN : 32);                 // S3 / S4: this strip's share of the colour pass is complete
                                                                    // (threads < HN own row 0: they wrote into the previous strip)
@@ -499,8 +540,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
             cta_share(true, false);
         }
 
-        // ---- store the strip; fetch the next chain's ----
-        if (tid == 0) {
+        // ---- store the strip; fetch the next chain's (SPARSE: nothing to store, the next strip is already on its way) ----
+        if (!SPARSE && tid == 0) {
             bulk_s2g(reinterpret_cast<double*>(a.phi) + chain * V + (long long)rank * VL, sphi, bytes_phi);
             bulk_s2g(a.n + chain * 2 * V + (long long)rank * VL, sn0, bytes_n);
             bulk_s2g(a.n + chain * 2 * V + V + (long long)rank * VL, sn1, bytes_n);
@@ -514,7 +555,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
         pending_chain = chain;
         pending_kappa = kappa;
     }
-    if (tid == 0) {
+    if (!SPARSE && tid == 0) {
         bulk_wait0();                                              // this CTA's bulk stores are complete ...
         if (OVERLAP) asm volatile("fence.proxy.async;" ::: "memory");
     }
@@ -541,15 +582,20 @@ static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, con
     const bool overlap = a.epochs != nullptr;
     const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? (a.interval_n == 0 ? SVB_FILT_SITE : SVB_FILT_STRICT) : SVB_FILT_FAST);
     if (mode != SVB_FILT_FAST && overlap) return fail(SVB_E_UNSUPPORTED, "overlapped launches serve the NeighborhoodUpdate sweep only");
+    const char* env_sparse = getenv("SVB_VILLAIN_SPARSE");
+    const bool sparse = STAGES == 1 && mode == SVB_FILT_FAST && a.n_sweeps == 1 && (a.obs == nullptr || a.obs_in != nullptr) &&
+                        !(env_sparse && env_sparse[0] == '0');
     auto kern = mode == SVB_FILT_EXACT    ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_EXACT>
                 : mode == SVB_FILT_SITE   ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_SITE>
                 : mode == SVB_FILT_STRICT ? villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_STRICT>
+                : sparse ? (overlap ? villain_cluster_kernel<NT, CL, TPB, 1, true, SVB_FILT_FAST, true>
+                                    : villain_cluster_kernel<NT, CL, TPB, 1, false, SVB_FILT_FAST, true>)
                 : overlap ? villain_cluster_kernel<NT, CL, TPB, STAGES, true, SVB_FILT_FAST>
                           : villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_FAST>;
     constexpr int ROWS = NT / CL, VL = ROWS * NT, VHL = ROWS * NT / 2, NW = TPB / 32;
     const size_t smem = (size_t)STAGES * VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16 * STAGES;
-    static int clusters_cache[5][64];
-    const int variant = mode != SVB_FILT_FAST ? 1 + mode : (overlap ? 1 : 0);
+    static int clusters_cache[7][64];
+    const int variant = mode != SVB_FILT_FAST ? 1 + mode : sparse ? 5 + (overlap ? 1 : 0) : (overlap ? 1 : 0);
     int clusters = (info.device < 64) ? clusters_cache[variant][info.device] : 0;
     if (clusters == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -205,7 +205,14 @@ __device__ __forceinline__ void chain_finish(const double* red_state, const doub
 #define SVB_FILT_STRICT 1
 #define SVB_FILT_EXACT 2
 #define SVB_FILT_SITE 3          /* SVB_FILT_STRICT with interval_n == 0 at compile time: no digits, no n updates */
-template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT, int MODE>
+// SPARSE (one sweep per launch, no record of the state AFTER the sweep): phi and n leave shared memory for good once the
+//       residuals are built.  An accepted proposal is applied to GLOBAL memory (five fire-and-forget reductions: phi += dphi
+//       as one fp64 RED -- the reference's one rounding -- and the four n), the exact path reads the current phi and n from
+//       global memory (L2), and NOTHING is stored back: an unchanged value is not rewritten.  The staging buffer is free as
+//       soon as the residuals exist, so the next chain's bulk load is issued right behind the build barrier and lands during
+//       the two colour passes -- the load latency that a one-stage CTA otherwise waits out per chain is gone, and so is the
+//       store phase.  DRAM traffic: one read of the state + the dirty sectors (acceptance is 0.5 - 5 %).
+template <int NT, int MINB, int STAGES, bool OVERLAP, bool UNIT, int MODE, bool SPARSE = false>
 __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(const __grid_constant__ VillainArgs a,
                                                                              const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     const bool obs_of_input = a.obs_in != nullptr;                // state columns describe the chain as it ARRIVES
     const bool want_obs = a.obs != nullptr && !obs_of_input;     // ... or as it leaves (one more fp64 pass)
     static_assert(!(UNIT && MODE != SVB_FILT_FAST), "UNIT is the production sweep");
+    static_assert(!SPARSE || MODE == SVB_FILT_FAST, "SPARSE serves the NeighborhoodUpdate sweep");
     const int interval_n = UNIT ? 1 : (MODE == SVB_FILT_SITE ? 0 : a.interval_n);
     const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
     const int W = (UNIT || MODE == SVB_FILT_EXACT) ? 1 : a.W, mWI = -W * interval_n;
@@ -322,6 +330,13 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         const int32_t* pn0 = sn0 + row8 * N + 2 * k;
         const int32_t* pn1 = sn1 + row8 * N + 2 * k;
 
+        // SPARSE: the fields of this chain in global memory (accepted proposals and the exact path go there)
+        double* gphi = reinterpret_cast<double*>(a.phi) + chain * V;
+        int32_t* gn0 = a.n + chain * 2 * V;
+        int32_t* gn1 = gn0 + V;
+        uint32_t seen_sparse = 0;
+        if (SPARSE && tid == 0 && next < a.chains) seen_sparse = peek_epoch(next);      // lands during the residual build
+
         mbar_wait(&bar[b], (uint32_t)(it & 1));
 
         int n_acc = 0;
@@ -363,6 +378,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                 if (sums) chain_partials<true, false>(red_state, red_count, lane, warp, action, dn2, w0, w1, 0.0, 0);
             }
             __syncthreads();
+            // SPARSE: nobody reads the staged phi and n again -- the next chain may land on them while this one is swept
+            if (SPARSE && tid == 0 && next < a.chains) issue_load(next, 0, seen_sparse);
             if (obs_of_input && s == 0 && tid == kWriter)
                 chain_finish<NW, true, false>(red_state, red_count, kappa / 2, a.obs_in + chain * SVB_VOBS_COUNT, nullptr);
 
@@ -468,7 +485,8 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                         bool ok = dif < 0.0f;
                         if (!(fabsf(dif) > bnd) || f < 65536u) {
                             ExactProposal ep;
-                            ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1;
+                            if (SPARSE) { ep.phi = gphi; ep.n0 = gn0; ep.n1 = gn1; }
+                            else { ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1; }
                             const int x0 = row8 + 8 * q;
                             ep.i_c = x0 * N + x1;
                             ep.i_b0 = ((x0 - 1) & (N - 1)) * N + x1;
@@ -496,12 +514,22 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             // phi += dphi with dphi = -I + fl((2 I 2^-32) (A + 1/2)): the scaling by 2^-32 is exact, so this
                             // is villain_dphi_from_word bit for bit with one multiply less
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
+                            if (SPARSE) {
+                                // straight to global memory, nothing waits for it: the fp64 reduction rounds once, to nearest,
+                                // like the reference's phi + dphi; the offsets are those of the shared-memory copy
+                                atomicAdd(gphi + (Pc - sphi) + 2 * T * q, __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
+                                atomicAdd(gn0 + (N0c - sn0) + 2 * T * q, W * dig[0] + mWI);
+                                atomicAdd(gn0 + (n0b - sn0) + 2 * T * q, W * dig[1] + mWI);
+                                atomicAdd(gn0 + (N1c - sn0) + 2 * T * q, W * dig[2] + mWI);      // sn1 = sn0 + V, gn1 = gn0 + V
+                                atomicAdd(gn0 + (N1b - sn0) + 2 * T * q, W * dig[3] + mWI);
+                            } else {
                             Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
                             if (MODE != SVB_FILT_SITE) {
                                 atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
                                 atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
                                 atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
                                 atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
+                            }
                             }
                             R0own[T * q] = h ? n_f0.y : n_f0.x;
                             r0b[T * q] = h ? n_b0.y : n_b0.x;
@@ -510,12 +538,21 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                         }
                     }
                 }
-                if (s == a.n_sweeps - 1 && c == 1) fence_proxy_async();      // this thread's phi / n writes -> visible to the bulk store
+                if (!SPARSE && s == a.n_sweeps - 1 && c == 1) fence_proxy_async();      // this thread's phi / n writes -> visible to the bulk store
+                // SPARSE (one sweep): this launch's counters ride on the barrier that ends the last pass
+                if (SPARSE && c == 1 && a.obs != nullptr)
+                    chain_partials<false, true>(red_state, red_count, lane, warp, 0.0, 0, 0, 0, sum_A_all + (double)sum_A, n_acc);
                 __syncthreads();
             }
             sum_A_all += (double)sum_A;
         }
 
+        if (SPARSE) {
+            // nothing to store; the state columns went to obs_in with the build, the counters' slots are complete
+            if (tid == kWriter && a.obs != nullptr)
+                chain_finish<NW, false, true>(red_state, red_count, kappa / 2, nullptr, a.obs + chain * SVB_VOBS_COUNT);
+            continue;
+        }
         // ---- store the chain (nothing below writes phi or n) ----
         uint32_t seen_next = 0;
         if (tid == 0) {
@@ -563,7 +600,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
             else chain_finish<NW, false, true>(red_state, red_count, kappa / 2, nullptr, row);
         }
     }
-    if (tid == 0) bulk_wait0();
+    if (!SPARSE && tid == 0) bulk_wait0();
     if (OVERLAP) {
         __syncthreads();                                   // every store has completed, every record is written
         if (warp == 0) publish_all(it);
@@ -576,9 +613,17 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     const int mode = a.exact_mode ? SVB_FILT_EXACT : (a.filtered_strict ? (a.interval_n == 0 ? SVB_FILT_SITE : SVB_FILT_STRICT) : SVB_FILT_FAST);
     const bool unit = mode == SVB_FILT_FAST && a.W == 1 && a.interval_n == 1;
     if (mode != SVB_FILT_FAST && overlap) return fail(SVB_E_UNSUPPORTED, "overlapped launches serve the NeighborhoodUpdate sweep only");
+    // one sweep per launch and no record of the state after it: nothing is stored back (SPARSE, see the kernel)
+    const char* env_sparse = getenv("SVB_VILLAIN_SPARSE");
+    const bool sparse = mode == SVB_FILT_FAST && a.n_sweeps == 1 && (a.obs == nullptr || a.obs_in != nullptr) &&
+                        !(env_sparse && env_sparse[0] == '0');
     auto kern = mode == SVB_FILT_EXACT    ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_EXACT>
                 : mode == SVB_FILT_SITE   ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_SITE>
                 : mode == SVB_FILT_STRICT ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_STRICT>
+                : sparse ? (overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true, SVB_FILT_FAST, true>
+                                            : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false, SVB_FILT_FAST, true>)
+                                    : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true, SVB_FILT_FAST, true>
+                                            : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_FAST, true>))
                 : overlap ? (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, true, true, SVB_FILT_FAST>
                                   : villain_smem_filtered_kernel<NT, MINB, STAGES, true, false, SVB_FILT_FAST>)
                           : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true, SVB_FILT_FAST>
@@ -586,8 +631,8 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
     const size_t V = (size_t)NT * NT;
     const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32;
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
-    static int per_sm_cache[7][64];
-    const int variant = mode != SVB_FILT_FAST ? 3 + mode : (overlap ? 1 : 0) + (unit ? 2 : 0);
+    static int per_sm_cache[11][64];
+    const int variant = mode != SVB_FILT_FAST ? 3 + mode : sparse ? 7 + (overlap ? 1 : 0) + (unit ? 2 : 0) : (overlap ? 1 : 0) + (unit ? 2 : 0);
     int per_sm = (info.device < 64) ? per_sm_cache[variant][info.device] : 0;
     if (per_sm == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,789 @@
+// svb_villain_stream.cuh -- the STREAMING Villain sweep kernels (included by svb_villain.cu).
+//
+// NeighborhoodUpdate.step (supervillain/generator/villain/neighborhood.py:59-137) for Philox draws, fp64 phi, FAST
+// arithmetic and even N that is a multiple of 16, with NO shared-memory copy of the fields at all:
+//
+//  * A colour pass reads what it needs straight from global memory (L1 / L2): a thread owns the site pair (r, x1),
+//    (r + 8, x1) that shares a Philox block (draw mapping version 2), loads the five phi and four n around each site
+//    (one 16-byte and three 8-byte loads of phi, one 8-byte and three 4-byte loads of n; a warp's loads are contiguous
+//    along the row), builds the four residuals r = d(phi) - 2 pi n (neighborhood.py:91) in fp64 and rounds them to fp32.
+//    Same-colour sites touch disjoint links and read only phi of the OTHER colour, so within a pass no
+//    thread reads anything another thread writes; the two passes of a sweep are separated by a block barrier (a chain per
+//    CTA) or by a launch boundary (one big lattice).
+//  * The decision is the fp32-filtered one of svb_villain_filtered.cuh -- dS32 against -log2 u with the error band, the
+//    exact fp64 test (from the fp64 residuals the thread already holds) and the lazily refined uniform inside it -- so every
+//    decision equals the exact fp64 decision.  The residuals are rebuilt from the current fields in every pass, never
+//    patched: their fp32 error is one rounding, inside the band derived for the patched copies.
+//  * phi and n are WRITTEN ONLY WHERE A PROPOSAL IS ACCEPTED (five stores).  An unchanged value is not rewritten: the DRAM
+//    traffic of a sweep is one read of the state plus the dirty sectors (acceptance is 0.5 - 5 %), against the algorithmic
+//    read + write of 32 B per site-update, and there is no store phase, no staging buffer to wait for and no ghost zone.
+//  * The next chain is prefetched into L2 (cp.async.bulk.prefetch.L2) while the current one is swept, so a pass starts from
+//    L2, not from DRAM.
+//  * A thread keeps its column and walks down the rows (r, r + 16, r + 32, ...): everything about the column -- parity, the
+//    wrapped neighbour columns -- is computed once, a step costs a handful of offset additions.
+//
+// Two kernels share the pair routine:
+//   villain_stream_chain_kernel   N in {16, 32, 64, 128}: one chain per CTA at a time (4 N threads), both colours (and all fused
+//                                 sweeps) in one launch, persistent CTAs striding over the chains, overlapped launches with
+//                                 per-chain epochs as svb_villain_filtered.cuh, records without atomics.
+//   villain_stream_pass_kernel    any N that is a multiple of 16 (config 5: L = 4096): one launch per colour pass; a CTA (8 warps)
+//                                 owns a band of 64 columns and a run of row groups; in place -- no workspace, no ping-pong,
+//                                 no ghost zones.
+#pragma once
+// (included inside namespace svb, after svb_villain_filtered.cuh)
+
+// A thread's column slot: constant while it walks down the rows.
+struct StreamCol {
+    int k2;          // 2 k: the aligned column pair [2k, 2k + 1] of every row holds the site and one in-row neighbour
+    int par;         // the site is column 2k + par
+    int x1, xm1, xp1;
+    int xo;          // the in-row neighbour outside the aligned pair: xp1 if par else xm1
+};
+__device__ __forceinline__ StreamCol stream_col(int k, int par, int N) {
+    StreamCol c;
+    c.k2 = 2 * k; c.par = par; c.x1 = 2 * k + par;
+    c.xm1 = (c.x1 == 0) ? N - 1 : c.x1 - 1;
+    c.xp1 = (c.x1 + 1 == N) ? 0 : c.x1 + 1;
+    c.xo = par ? c.xp1 : c.xm1;
+    return c;
+}
+
+// The four residuals of the site at row offset o (rows above / below at om / op), rounded to fp32.  SUMS: the observables of
+// the state as it is now -- every link has exactly one endpoint of this colour, and a site's own four links are written by
+// nobody else during the pass.  (sum (dn)^2 is NOT collected here: a plaquette's other links belong to same-colour sites that
+// may be writing them right now -- it has a pass of its own, stream_dn2_rows.)
+template <bool SUMS>
+__device__ __forceinline__ float4 stream_site_residuals(const double* gphi, const int32_t* gn0, const int32_t* gn1, int o, int om,
+                                                        int op, const StreamCol& col, double& action, int& w0, int& w1) {
+    const double2 pc2 = *reinterpret_cast<const double2*>(gphi + o + col.k2);
+    const double po = gphi[o + col.xo];
+    const double pu = gphi[op + col.x1], pd = gphi[om + col.x1];
+    const int2 n1p = *reinterpret_cast<const int2*>(gn1 + o + col.k2);
+    const int n1e = gn1[o + col.xo];                              // column 2k - 1 when par == 0 (unused otherwise)
+    const int n0c = gn0[o + col.x1], n0b = gn0[om + col.x1];
+    const double pc = col.par ? pc2.y : pc2.x;
+    const double pl = col.par ? pc2.x : po, pr = col.par ? po : pc2.y;
+    const int n1c = col.par ? n1p.y : n1p.x, n1b = col.par ? n1p.x : n1e;
+    const double rf0 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n0c), pu - pc);
+    const double rb0 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n0b), pc - pd);
+    const double rf1 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n1c), pr - pc);
+    const double rb1 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n1b), pc - pl);
+    if (SUMS) {
+        action = fma(rf0, rf0, action);
+        action = fma(rb0, rb0, action);
+        action = fma(rf1, rf1, action);
+        action = fma(rb1, rb1, action);
+        w0 += n0c + n0b;
+        w1 += n1c + n1b;
+    }
+    return make_float4((float)rf0, (float)rb0, (float)rf1, (float)rb1);
+}
+
+// The exact test of a proposal whose fp32 comparison is inside its error band (a few 1e-5 of the proposals): dS in fp64 from
+// the current phi and n (L1 / L2), the fp64 exponential, the lazily refined uniform.  Out of line on purpose: the hot loop
+// should not pay registers for it.
+__device__ __noinline__ bool stream_exact(const VillainArgs& a, const double* gphi, const int32_t* gn0, int V, int o, int om, int op, int x1,
+                                          int xm1, int xp1, uint32_t wA, uint32_t f, uint32_t c0, uint32_t half, int g0, int g1, int g2,
+                                          int g3, int W, double half_kappa, unsigned long long gc, unsigned long long gs) {
+    ExactProposal ep;
+    ep.phi = gphi; ep.n0 = gn0; ep.n1 = gn0 + V;
+    ep.i_c = o + x1; ep.i_b0 = om + x1; ep.i_b1 = o + xm1; ep.i_f0 = op + x1; ep.i_f1 = o + xp1;
+    ep.half_kappa = half_kappa; ep.c = SVB_TWO_PI * (double)W;
+    ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
+    ep.g[0] = g0; ep.g[1] = g1; ep.g[2] = g2; ep.g[3] = g3;
+    ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
+    ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
+    return villain_exact_decision(ep);
+}
+
+// An accepted proposal (:121-129), applied to global memory as fire-and-forget reductions: the fp64 one rounds once, to nearest,
+// like the reference's phi + dphi.  (Acceptance is 0.5 - 5 %, so some lane of most warps comes through here: it is inline.)
+__device__ __forceinline__ void stream_accept(double* gphi, int32_t* gn0, int V, int o, int om, int x1, int xm1, uint32_t wA,
+                                              double interval_phi, double two_I_scaled, int d0, int d1, int d2, int d3) {
+    const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;          // villain_dphi_from_word, one multiply less
+    atomicAdd(gphi + o + x1, __dadd_rn(-interval_phi, __dmul_rn(two_I_scaled, Ah)));
+    atomicAdd(gn0 + o + x1, d0);
+    atomicAdd(gn0 + om + x1, d1);
+    atomicAdd(gn0 + V + o + x1, d2);
+    atomicAdd(gn0 + V + o + xm1, d3);
+}
+
+// The decision half of a colour pass over a pair of sites (row offsets oA and oB = oA + 8 N, column x1) that share the Philox
+// block `bits` (counter word 0 = oA + x1, draw mapping version 2), from their fp32 residuals rA, rB = (f0, b0, f1, b1).
+template <bool UNIT>
+__device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const FilterConsts& fc, double* gphi, int32_t* gn0, int V, int oA,
+                                                   int oAm, int oAp, int oB, int oBm, int oBp, int x1, int xm1, int xp1, const Philox4& bits,
+                                                   uint32_t c0, const float4& rA, const float4& rB, unsigned long long gc,
+                                                   unsigned long long gs, double half_kappa, float hk2, float hkA, float hkB, int& n_acc,
+                                                   float& sum_A) {
+    const int interval_n = UNIT ? 1 : a.interval_n;
+    const uint32_t K = (uint32_t)(2 * interval_n + 1);
+    const int W = UNIT ? 1 : a.W;
+    // proposals: four base-K digits each, then the leading 32 bits of the uniform (svb_villain_filtered.cuh)
+    uint32_t fA = bits.y, fB = bits.w;
+    int a0, a1, a2, a3, b0, b1, b2, b3;
+    if (UNIT) {
+        const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
+        fA = (uint32_t)pa; fB = (uint32_t)pb;
+        uint32_t ia = (uint32_t)(pa >> 32), ib = (uint32_t)(pb >> 32);
+        a0 = (int)((ia * 2428u) >> 16); ia -= 27u * (uint32_t)a0;
+        b0 = (int)((ib * 2428u) >> 16); ib -= 27u * (uint32_t)b0;
+        a1 = (int)((ia * 7282u) >> 16); ia -= 9u * (uint32_t)a1;
+        b1 = (int)((ib * 7282u) >> 16); ib -= 9u * (uint32_t)b1;
+        a2 = (int)((ia * 21846u) >> 16); a3 = (int)(ia - 3u * (uint32_t)a2);
+        b2 = (int)((ib * 21846u) >> 16); b3 = (int)(ib - 3u * (uint32_t)b2);
+    } else {
+        uint64_t pa, pb;
+        pa = (uint64_t)fA * K; fA = (uint32_t)pa; a0 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b0 = (int)(pb >> 32);
+        pa = (uint64_t)fA * K; fA = (uint32_t)pa; a1 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b1 = (int)(pb >> 32);
+        pa = (uint64_t)fA * K; fA = (uint32_t)pa; a2 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b2 = (int)(pb >> 32);
+        pa = (uint64_t)fA * K; fA = (uint32_t)pa; a3 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b3 = (int)(pb >> 32);
+    }
+    const float cIn = fc.c * (float)interval_n;
+    const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
+    // dphi from 23 centred bits
+    float2 U = make_float2(__uint_as_float(0x3F800000u | (bits.x >> 9)), __uint_as_float(0x3F800000u | (bits.z >> 9)));
+    U = __fadd2_rn(U, make_float2(-0.99999994f, -0.99999994f));
+    const float2 dphi = __ffma2_rn(make_float2(fc.two_I, fc.two_I), U, make_float2(-fc.I, -fc.I));
+    const float2 base_f = __ffma2_rn(dphi, make_float2(-1.0f, -1.0f), cIn2), base_b = __fadd2_rn(cIn2, dphi);
+    const float2 r_f0 = make_float2(rA.x, rB.x), r_b0 = make_float2(rA.y, rB.y);
+    const float2 r_f1 = make_float2(rA.z, rB.z), r_b1 = make_float2(rA.w, rB.w);
+    // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
+    const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)a0, (float)b0), base_f);
+    const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)a1, (float)b1), base_b);
+    const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)a2, (float)b2), base_f);
+    const float2 dr_b1 = __ffma2_rn(negc2, make_float2((float)a3, (float)b3), base_b);
+    float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
+    acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
+    acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
+    acc2 = __ffma2_rn(dr_b1, __ffma2_rn(two2, r_b1, dr_b1), acc2);
+    const float2 dS2 = __fmul2_rn(make_float2(hk2, hk2), acc2);                          // dS / ln 2
+    // -log2(f 2^-32); u lies in [f, f + 1] 2^-32
+    const float2 L2 = __ffma2_rn(make_float2(fast_lg2((float)fA), fast_lg2((float)fB)), make_float2(-1.0f, -1.0f),
+                                 make_float2(32.0f, 32.0f));
+    const float2 Rmax = make_float2(fmaxf(fmaxf(fabsf(r_f0.x), fabsf(r_b0.x)), fmaxf(fabsf(r_f1.x), fabsf(r_b1.x))),
+                                    fmaxf(fmaxf(fabsf(r_f0.y), fabsf(r_b0.y)), fmaxf(fabsf(r_f1.y), fabsf(r_b1.y))));
+    const float2 band = __ffma2_rn(make_float2(hkA, hkA), Rmax, __ffma2_rn(make_float2(4e-6f, 4e-6f), L2, make_float2(hkB, hkB)));
+    const float2 diff = __ffma2_rn(L2, make_float2(-1.0f, -1.0f), dS2);
+    sum_A += fminf(fast_ex2(-dS2.x), 1.0f) + fminf(fast_ex2(-dS2.y), 1.0f);
+    // certainly rejected (the overwhelming majority): nothing more to do
+    const int mWI = -W * interval_n;
+    const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
+    bool okA = diff.x < 0.0f, okB = diff.y < 0.0f;
+    if (!(fabsf(diff.x) > band.x) || fA < 65536u)
+        okA = stream_exact(a, gphi, gn0, V, oA, oAm, oAp, x1, xm1, xp1, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n, a2 - interval_n,
+                           a3 - interval_n, W, half_kappa, gc, gs);
+    if (!(fabsf(diff.y) > band.y) || fB < 65536u)
+        okB = stream_exact(a, gphi, gn0, V, oB, oBm, oBp, x1, xm1, xp1, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n, b2 - interval_n,
+                           b3 - interval_n, W, half_kappa, gc, gs);
+    n_acc += (okA ? 1 : 0) + (okB ? 1 : 0);
+    if (okA) stream_accept(gphi, gn0, V, oA, oAm, x1, xm1, bits.x, a.interval_phi, two_I_scaled, W * a0 + mWI, W * a1 + mWI, W * a2 + mWI, W * a3 + mWI);
+    if (okB) stream_accept(gphi, gn0, V, oB, oBm, x1, xm1, bits.z, a.interval_phi, two_I_scaled, W * b0 + mWI, W * b1 + mWI, W * b2 + mWI, W * b3 + mWI);
+}
+
+// One colour pass over the pair of sites at row offsets oA and oB = oA + 8 N of the column slot `col`, straight from global memory.
+template <bool UNIT, bool SUMS>
+__device__ __forceinline__ void stream_pair(const VillainArgs& a, const FilterConsts& fc, double* gphi, int32_t* gn0, int V, int oA,
+                                            int oAm, int oAp, int oB, int oBm, int oBp, const StreamCol& col, unsigned long long gc,
+                                            unsigned long long gs, double half_kappa, float hk2, float hkA, float hkB, int& n_acc,
+                                            float& sum_A, double& action, int& w0, int& w1) {
+    // the Philox block does not depend on memory: issue it first so that it overlaps the loads
+    const uint32_t c0 = (uint32_t)(oA + col.x1);                          // villain_pair_counter: (x0 & ~8) N + x1
+    const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+    const float4 rA = stream_site_residuals<SUMS>(gphi, gn0, gn0 + V, oA, oAm, oAp, col, action, w0, w1);
+    const float4 rB = stream_site_residuals<SUMS>(gphi, gn0, gn0 + V, oB, oBm, oBp, col, action, w0, w1);
+    stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oAp, oB, oBm, oBp, col.x1, col.xm1, col.xp1, bits, c0, rA, rB, gc, gs, half_kappa,
+                             hk2, hkA, hkB, n_acc, sum_A);
+}
+
+// sum (dn)^2 of the plaquettes at the four sites (r, 2k), (r, 2k + 1), (r + 8, 2k), (r + 8, 2k + 1); reads n only.  Must not run
+// concurrently with a colour pass on the same lattice.
+__device__ __forceinline__ long long stream_dn2_rows(const int32_t* gn0, const int32_t* gn1, int N, int r, int k) {
+    const int x2 = (2 * k + 2 == N) ? 0 : 2 * k + 2;
+    long long t = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int rr = r + 8 * h, o = rr * N, op = ((rr + 1 == N) ? 0 : rr + 1) * N;
+        const int2 m0 = *reinterpret_cast<const int2*>(gn0 + o + 2 * k), m1 = *reinterpret_cast<const int2*>(gn1 + o + 2 * k);
+        const int2 up = *reinterpret_cast<const int2*>(gn1 + op + 2 * k);
+        const int hr = gn0[o + x2];
+        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x])      (compact.py d,1 rows)
+        const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (hr - m0.y);
+        t += (long long)d0 * d0 + (long long)d1 * d1;
+    }
+    return t;
+}
+
+// Observables of the CURRENT state from the four sites (r, 2k), (r, 2k + 1), (r + 8, 2k), (r + 8, 2k + 1): forward links and the
+// plaquette of each (the full record of a launch that does not use obs_in).
+__device__ __forceinline__ void stream_obs_rows(const double* gphi, const int32_t* gn0, const int32_t* gn1, int N, int r, int k,
+                                                double& action, long long& dn2, int& w0, int& w1) {
+    const int x2 = (2 * k + 2 == N) ? 0 : 2 * k + 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int rr = r + 8 * h, o = rr * N, op = ((rr + 1 == N) ? 0 : rr + 1) * N;
+        const double2 pc = *reinterpret_cast<const double2*>(gphi + o + 2 * k);
+        const double2 pu = *reinterpret_cast<const double2*>(gphi + op + 2 * k);
+        const double pr = gphi[o + x2];
+        const int2 m0 = *reinterpret_cast<const int2*>(gn0 + o + 2 * k), m1 = *reinterpret_cast<const int2*>(gn1 + o + 2 * k);
+        const int2 up = *reinterpret_cast<const int2*>(gn1 + op + 2 * k);
+        const int hr = gn0[o + x2];
+        const double r0e = fma(-SVB_TWO_PI, SVB_FILT_CVT(m0.x), pu.x - pc.x), r0o = fma(-SVB_TWO_PI, SVB_FILT_CVT(m0.y), pu.y - pc.y);
+        const double r1e = fma(-SVB_TWO_PI, SVB_FILT_CVT(m1.x), pc.y - pc.x), r1o = fma(-SVB_TWO_PI, SVB_FILT_CVT(m1.y), pr - pc.y);
+        action = fma(r0e, r0e, action);
+        action = fma(r0o, r0o, action);
+        action = fma(r1e, r1e, action);
+        action = fma(r1o, r1o, action);
+        const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (hr - m0.y);
+        dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+        w0 += m0.x + m0.y;
+        w1 += m1.x + m1.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// One chain per CTA at a time (N in {16, 32, 64, 128}), persistent CTAs striding over the chains.  4 N threads: thread
+// (w8, k) = (tid / (N/2), tid % (N/2)) owns column slot k and walks the rows 16 g + w8 (and + 8), g < N / 16.
+// OVERLAP: the overlapped-launch protocol of svb_villain_sweep_overlapped (svb_villain_filtered.cuh): programmatic dependent
+// launch, a chain is swept only once its epoch reads a.wait_epoch, all of a CTA's chains are released together at its end.
+// ------------------------------------------------------------------------------------------
+template <int NT, int MINB, bool OVERLAP, bool UNIT>
+__global__ void __launch_bounds__(4 * NT, MINB) villain_stream_chain_kernel(const __grid_constant__ VillainArgs a,
+                                                                            const __grid_constant__ FilterConsts fc) {
+    constexpr int N = NT, V = N * N, HN = N / 2, THREADS = 4 * NT, NW = THREADS / 32, GROUPS = N / 16;
+    static_assert(N % 16 == 0, "villain_stream_chain_kernel: unsupported geometry");
+    __shared__ double red_state[4 * NW];
+    __shared__ double red_count[2 * NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWriter = (NW > 1) ? 32 : 0;
+    const int w8 = tid / HN, k = tid - w8 * HN;
+
+    if (OVERLAP) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (a.grid_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    const bool obs_of_input = a.obs_in != nullptr;
+    const bool want_obs = a.obs != nullptr && !obs_of_input;
+
+    auto wait_epoch = [&](long long chain) {
+        if (OVERLAP && !a.grid_wait) {
+            uint32_t e;
+            unsigned ns = 32, naps = 0;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(a.epochs + chain) : "memory");
+                if (e == a.wait_epoch) break;
+                __nanosleep(ns);
+                if (ns < 1024) ns *= 2;
+                if (++naps > (1u << 21)) __trap();          // a producer that never comes is a caller error: fail, do not hang
+            }
+        }
+    };
+    auto prefetch = [&](long long chain) {
+        // the whole chain into L2 (it is the coherence point: whatever is prefetched there is current)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const double*>(a.phi) + chain * V),
+                     "r"((uint32_t)(V * sizeof(double)))
+                     : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.n + chain * 2 * V), "r"((uint32_t)(2 * V * sizeof(int32_t))) : "memory");
+    };
+
+    long long chain = blockIdx.x;
+    if (tid == 0 && chain < a.chains) wait_epoch(chain);
+    __syncthreads();
+
+    int it = 0;
+    for (; chain < a.chains; chain += gridDim.x, ++it) {
+        const long long next = chain + gridDim.x;
+        if (tid == 0 && next < a.chains) prefetch(next);
+        double* gphi = reinterpret_cast<double*>(a.phi) + chain * V;
+        int32_t* gn0 = a.n + chain * 2 * V;
+        const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+        const double half_kappa = kappa / 2;
+        const float hk2 = (float)(half_kappa * 1.4426950408889634);                 // decisions are taken in units of ln 2
+        const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+        const unsigned long long gc = a.chain0 + (unsigned long long)chain;
+
+        double action = 0.0, sum_A_all = 0.0;
+        long long dn2 = 0;
+        int w0 = 0, w1 = 0, n_acc = 0;
+        float sum_A = 0.0f;
+        if (obs_of_input) {
+            // sum (dn)^2 of the arriving state: every thread reads n here, nobody writes it before the barrier
+#pragma unroll 1
+            for (int g = 0; g < GROUPS; ++g) dn2 += stream_dn2_rows(gn0, gn0 + V, N, 16 * g + w8, k);
+            __syncthreads();
+        }
+        for (int sw = 0; sw < a.n_sweeps; ++sw) {
+            const unsigned long long gs = a.sweep0 + (unsigned long long)sw;
+            const bool sums = obs_of_input && sw == 0;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const StreamCol col = stream_col(k, (w8 + c) & 1, N);
+#pragma unroll 1
+                for (int g = 0; g < GROUPS; ++g) {
+                    const int r = 16 * g + w8;
+                    const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
+                    if (c == 0 && sums)
+                        stream_pair<UNIT, true>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB,
+                                                n_acc, sum_A, action, w0, w1);
+                    else
+                        stream_pair<UNIT, false>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB,
+                                                 n_acc, sum_A, action, w0, w1);
+                }
+                if (c == 0 && sums) chain_partials<true, false>(red_state, red_count, lane, warp, action, dn2, w0, w1, 0.0, 0);
+                const bool last = (sw == a.n_sweeps - 1) && c == 1;
+                if (last && !want_obs) {
+                    if (a.obs != nullptr)
+                        chain_partials<false, true>(red_state, red_count, lane, warp, 0.0, 0, 0, 0, sum_A_all + (double)sum_A, n_acc);
+                    // the next chain may be swept once its epoch has been seen: one thread looks before the barrier
+                    if (tid == 0 && next < a.chains) wait_epoch(next);
+                }
+                __syncthreads();               // this colour's writes are visible to the whole CTA
+                if (c == 0 && sums && tid == kWriter)
+                    chain_finish<NW, true, false>(red_state, red_count, half_kappa, a.obs_in + chain * SVB_VOBS_COUNT, nullptr);
+            }
+            sum_A_all += (double)sum_A;
+            sum_A = 0.0f;
+        }
+        if (want_obs) {
+            // the full record of the state after the sweeps: one more pass over the chain (L1 / L2)
+            action = 0.0; dn2 = 0; w0 = 0; w1 = 0;
+#pragma unroll 1
+            for (int g = 0; g < GROUPS; ++g) stream_obs_rows(gphi, gn0, gn0 + V, N, 16 * g + w8, k, action, dn2, w0, w1);
+            chain_partials<true, true>(red_state, red_count, lane, warp, action, dn2, w0, w1, sum_A_all, n_acc);
+            if (tid == 0 && next < a.chains) wait_epoch(next);
+            __syncthreads();
+        }
+        if (tid == kWriter && a.obs != nullptr) {
+            double* row = a.obs + chain * SVB_VOBS_COUNT;
+            if (want_obs) chain_finish<NW, true, true>(red_state, red_count, half_kappa, row, row);
+            else chain_finish<NW, false, true>(red_state, red_count, half_kappa, nullptr, row);
+        }
+    }
+    if (OVERLAP) {
+        __syncthreads();                                   // every write of every thread, every record
+        if (warp == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (int i = lane; i < it; i += 32)
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.epochs + blockIdx.x + (long long)i * gridDim.x), "r"(a.signal_epoch)
+                             : "memory");
+        }
+    }
+}
+
+template <int NT, int MINB>
+static int launch_villain_stream_chain(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
+    const bool overlap = a.epochs != nullptr;
+    const bool unit = a.W == 1 && a.interval_n == 1;
+    constexpr int THREADS = 4 * NT;
+    auto kern = overlap ? (unit ? villain_stream_chain_kernel<NT, MINB, true, true> : villain_stream_chain_kernel<NT, MINB, true, false>)
+                        : (unit ? villain_stream_chain_kernel<NT, MINB, false, true> : villain_stream_chain_kernel<NT, MINB, false, false>);
+    static int per_sm_cache[4][64];
+    const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0);
+    int per_sm = (info.device < 64) ? per_sm_cache[variant][info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "streaming villain kernel does not fit an SM at N=%d", NT);
+        if (info.device < 64) per_sm_cache[variant][info.device] = per_sm;
+    }
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > a.chains) grid = a.chains;
+    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    if (overlap) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, fc));
+        return 0;
+    }
+    kern<<<(unsigned)grid, THREADS, 0, stream>>>(a, fc);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// One colour pass per launch for lattices beyond a CTA (config 5, L = 4096), IN PLACE: a pass writes only accepted proposals
+// and nothing it writes is read by another thread of the same pass.  A CTA of 8 warps owns a band of 64 columns (warp w8 = row
+// 16 g + w8 and its partner + 8, lane = column slot) and `run` consecutive row groups g; one CTA per (chain, band, run), so the
+// hardware scheduler balances the load.  Records: per-CTA partial sums added atomically (a handful of atomics per CTA).
+//   pass 0 with state_out: the state columns ACTION, WRAP0, WRAP1 of the lattice AS IT ARRIVES; both passes: counters.
+//   sum (dn)^2 of the arriving state: villain_stream_dn2_kernel (reads n only), launched before pass 0.
+// ------------------------------------------------------------------------------------------
+template <bool UNIT>
+__global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc,
+                                                                     int colour, int sweep, int bands, int runs, int run,
+                                                                     double* __restrict__ state_out, double* __restrict__ counter_out) {
+    __shared__ double scratch[5 * 32];
+    const int N = a.N, V = N * N, groups = N / 16;
+    const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+    // blockIdx.x = (chain * runs + run index) * bands + band: neighbouring CTAs work on neighbouring bands of the same rows
+    const unsigned per_chain = (unsigned)(bands * runs);
+    const long long chain = blockIdx.x / per_chain;
+    const int rem = (int)(blockIdx.x - chain * per_chain);
+    const int ri = rem / bands, band = rem - ri * bands;
+    const int k = 32 * band + lane;
+    const bool sums = state_out != nullptr;
+    const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+    const double half_kappa = kappa / 2;
+    const float hk2 = (float)(half_kappa * 1.4426950408889634);
+    const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+    const unsigned long long gc = a.chain0 + (unsigned long long)chain, gs = a.sweep0 + (unsigned long long)sweep;
+    double* gphi = reinterpret_cast<double*>(a.phi) + chain * (long long)V;
+    int32_t* gn0 = a.n + chain * 2 * (long long)V;
+    double action = 0.0;
+    int w0 = 0, w1 = 0, n_acc = 0;
+    float sum_A = 0.0f;
+    if (k < N / 2) {                                              // N not a multiple of 64: the last band is ragged
+        const StreamCol col = stream_col(k, (w8 + colour) & 1, N);
+        const int g_end = min(groups, (ri + 1) * run);
+#pragma unroll 1
+        for (int g = ri * run; g < g_end; ++g) {
+            const int r = 16 * g + w8;
+            const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
+            if (sums)
+                stream_pair<UNIT, true>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB, n_acc,
+                                        sum_A, action, w0, w1);
+            else
+                stream_pair<UNIT, false>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB, n_acc,
+                                         sum_A, action, w0, w1);
+        }
+    }
+    if (sums || counter_out) {
+        double v[5] = {action, (double)w0, (double)w1, (double)n_acc, (double)sum_A};
+        block_sum<5>(v, scratch);
+        if (tid == 0) {
+            if (sums) {
+                double* o = state_out + chain * SVB_VOBS_COUNT;
+                atomicAdd(o + SVB_VOBS_ACTION, half_kappa * v[0]);
+                atomicAdd(o + SVB_VOBS_WRAP0, v[1]);
+                atomicAdd(o + SVB_VOBS_WRAP1, v[2]);
+            }
+            if (counter_out) {
+                atomicAdd(counter_out + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, v[3]);
+                atomicAdd(counter_out + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, v[4]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* __restrict__ n, long long chains, int N,
+                                                                 double* __restrict__ state_out) {
+    __shared__ double scratch[32];
+    const long long V = (long long)N * N;
+    const int HN = N / 2;
+    const long long quads_per_chain = (long long)(N / 2) * HN;          // thread = (row pair, column pair): four sites
+    const int tid = threadIdx.x;
+    const int chunks = (int)((quads_per_chain + 255) / 256);
+    long long chain_of_sum = -1;
+    long long dn2 = 0;
+    auto flush = [&](long long chain) {
+        double v[1] = {(double)dn2};
+        block_sum<1>(v, scratch);
+        if (tid == 0) atomicAdd(state_out + chain * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, v[0]);
+        __syncthreads();
+        dn2 = 0;
+    };
+    for (long long t = blockIdx.x; t < chains * chunks; t += gridDim.x) {
+        const long long chain = t / chunks;
+        if (chain != chain_of_sum) {
+            if (chain_of_sum >= 0) flush(chain_of_sum);
+            chain_of_sum = chain;
+        }
+        const long long q = (t - chain * chunks) * 256 + tid;
+        if (q < quads_per_chain) {
+            const int rp = (int)(q / HN), k = (int)(q - (long long)rp * HN);
+            dn2 += stream_dn2_rows(n + chain * 2 * V, n + chain * 2 * V + V, N, (rp & 7) | ((rp >> 3) << 4), k);
+        }
+    }
+    if (chain_of_sum >= 0) flush(chain_of_sum);
+}
+
+// n_sweeps sweeps in place; obs_in (optional): the state columns of the arriving lattice (zeroed by the caller), filled by a pass
+// over n and the first colour pass; counters (optional): ACCEPTED / ACCEPTANCE of this call are ADDED to it.
+static int launch_villain_stream_passes(const VillainArgs& a, double* obs_in, double* counters, cudaStream_t stream, const DeviceInfo& info) {
+    const bool unit = a.W == 1 && a.interval_n == 1;
+    auto kern = unit ? villain_stream_pass_kernel<true> : villain_stream_pass_kernel<false>;
+    static bool ready[2][64];
+    if (info.device >= 64 || !ready[unit ? 1 : 0][info.device]) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        if (info.device < 64) ready[unit ? 1 : 0][info.device] = true;
+    }
+    const int bands = (a.N / 2 + 31) / 32, groups = a.N / 16;
+    // rows per CTA: long runs amortise a thread's column set-up, short runs balance the load -- aim at >= 8 CTAs per SM slot
+    int run = groups;
+    while (run > 2 && (long long)a.chains * bands * ((groups + run - 1) / run) < 24LL * info.sm_count) run = (run + 1) / 2;
+    const int runs = (groups + run - 1) / run;
+    const long long grid = (long long)a.chains * bands * runs;
+    if (grid > 0x7fffffffLL) return fail(SVB_E_SHAPE, "streaming villain passes: too many CTAs (%lld)", grid);
+    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    if (obs_in) {
+        villain_stream_dn2_kernel<<<(unsigned)(8 * info.sm_count), 256, 0, stream>>>(a.n, a.chains, a.N, obs_in);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    for (int sw = 0; sw < a.n_sweeps; ++sw)
+        for (int c = 0; c < 2; ++c) {
+            kern<<<(unsigned)grid, 256, 0, stream>>>(a, fc, c, sw, bands, runs, run, (sw == 0 && c == 0) ? obs_in : nullptr, counters);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// The same colour pass with the tile STAGED IN SHARED MEMORY BY TMA TENSOR LOADS (config 5: L = 4096; N a multiple of 128).
+//
+// A pass over a big lattice out of global memory is latency bound: a thread's nine loads per site come from DRAM, and the
+// registers that would hold a second iteration's loads are what limits occupancy.  Here the copy engine does the waiting:
+//   * a tile is 16 rows x 128 columns (1024 sites of the colour); three 3-D tensor boxes (cp.async.bulk.tensor, SASS UTMALDG)
+//     bring phi (18 rows x 132 columns: one halo row above and below, the neighbour columns left and right), n0 and n1
+//     (17 x 132: the row above for the backward links, the column to the left) into one shared-memory stage and signal an
+//     mbarrier; the tensor maps describe the fields as (column, row, chain [x component]), so a halo row or column beyond the
+//     edge of the lattice is out of bounds and zero-filled, never a neighbouring chain's data;
+//   * two stages per CTA: the boxes of the tile after next are issued as soon as the CTA has finished reading a stage, and land
+//     while the next tile is being swept -- the load latency is hidden whatever the occupancy;
+//   * the periodic wrap touches only the tiles on the edge of the lattice (2 of 32 columns of tiles, 2 of 256 rows at L = 4096):
+//     their halo row / column is patched with ordinary loads behind the mbarrier;
+//   * persistent CTAs (3 per SM) stride over the tiles; a thread owns two column slots of a tile and the row pair (w8, w8 + 8);
+//   * everything after the residuals is stream_pair_decide: accepted proposals go to GLOBAL memory as reductions, in place --
+//     no workspace, no ping-pong, no ghost-zone recomputation, nothing stored that did not change.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileRows = 16, kTileCols = 128;
+constexpr int kTilePhiRows = kTileRows + 2, kTilePhiCols = kTileCols + 4;     // rows R-1 .. R+16, columns C-2 .. C+129
+constexpr int kTileNRows = kTileRows + 1, kTileNCols = kTileCols + 4;        // rows R-1 .. R+15, columns C-4 .. C+127
+constexpr int kTilePhiBytes = kTilePhiRows * kTilePhiCols * 8;                 // 19008
+constexpr int kTileNBytes = kTileNRows * kTileNCols * 4;                       // 8976
+constexpr int kTilePhiSlot = (kTilePhiBytes + 127) / 128 * 128, kTileNSlot = (kTileNBytes + 127) / 128 * 128;
+constexpr int kTileStageBytes = kTilePhiSlot + 2 * kTileNSlot;
+constexpr int kTileSmemBytes = 2 * kTileStageBytes + 64;
+
+__device__ __forceinline__ void tensor_box_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// residuals of the site at local row i (phi / n row index: 0 = the halo row R - 1), column slot base jc (even), parity par
+template <bool SUMS>
+__device__ __forceinline__ float4 tile_site_residuals(const double* P, const int32_t* N0, const int32_t* N1, int i, int jc, int par,
+                                                      double& action, int& w0, int& w1) {
+    const double* prow = P + i * kTilePhiCols + jc + 2;             // local column 0 is global C - 2
+    const int32_t* n0row = N0 + i * kTileNCols + jc + 4;            // local column 0 is global C - 4
+    const int32_t* n1row = N1 + i * kTileNCols + jc + 4;
+    const double2 pc2 = *reinterpret_cast<const double2*>(prow);
+    const double po = prow[par ? 2 : -1];
+    const double pu = prow[kTilePhiCols + par], pd = prow[par - kTilePhiCols];
+    const int2 n1p = *reinterpret_cast<const int2*>(n1row);
+    const int n1e = n1row[-1];
+    const int n0c = n0row[par], n0b = n0row[par - kTileNCols];
+    const double pc = par ? pc2.y : pc2.x;
+    const double pl = par ? pc2.x : po, pr = par ? po : pc2.y;
+    const int n1c = par ? n1p.y : n1p.x, n1b = par ? n1p.x : n1e;
+    const double rf0 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n0c), pu - pc);
+    const double rb0 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n0b), pc - pd);
+    const double rf1 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n1c), pr - pc);
+    const double rb1 = fma(-SVB_TWO_PI, SVB_FILT_CVT(n1b), pc - pl);
+    if (SUMS) {
+        action = fma(rf0, rf0, action);
+        action = fma(rb0, rb0, action);
+        action = fma(rf1, rf1, action);
+        action = fma(rb1, rb1, action);
+        w0 += n0c + n0b;
+        w1 += n1c + n1b;
+    }
+    return make_float4((float)rf0, (float)rb0, (float)rf1, (float)rb1);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc,
+                                                                   const __grid_constant__ CUtensorMap map_phi,
+                                                                   const __grid_constant__ CUtensorMap map_n, int colour, int sweep,
+                                                                   double* __restrict__ state_out, double* __restrict__ counter_out) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ double scratch[5 * 32];
+    const int N = a.N, V = N * N;
+    const int tiles_x = N / kTileCols, tiles_y = N / kTileRows, tiles_per_chain = tiles_x * tiles_y;
+    const long long tiles = (long long)tiles_per_chain * a.chains;
+    const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tile_smem + 2 * kTileStageBytes);
+    const bool sums = state_out != nullptr;
+    const unsigned long long gs = a.sweep0 + (unsigned long long)sweep;
+    const int par = (w8 + colour) & 1;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](long long t, int stage) {
+        const long long chain = t / tiles_per_chain;
+        const int tile = (int)(t - chain * tiles_per_chain);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int R = ty * kTileRows, C = tx * kTileCols;
+        unsigned char* st = tile_smem + stage * kTileStageBytes;
+        mbar_expect_tx(&bar[stage], (uint32_t)(kTilePhiBytes + 2 * kTileNBytes));
+        tensor_box_3d(st, &map_phi, C - 2, R - 1, (int)chain, &bar[stage]);
+        tensor_box_3d(st + kTilePhiSlot, &map_n, C - 4, R - 1, (int)(2 * chain), &bar[stage]);
+        tensor_box_3d(st + kTilePhiSlot + kTileNSlot, &map_n, C - 4, R - 1, (int)(2 * chain + 1), &bar[stage]);
+    };
+    long long t = blockIdx.x;
+    if (tid == 0) {
+        if (t < tiles) issue(t, 0);
+        if (t + gridDim.x < tiles) issue(t + gridDim.x, 1);
+    }
+
+    double action = 0.0, half_kappa = 0.0;
+    int w0 = 0, w1 = 0, n_acc = 0;
+    float sum_A = 0.0f, hk2 = 0.0f, hkA = 0.0f, hkB = 0.0f;
+    long long chain_of_sums = -1;
+    auto flush = [&](long long chain) {
+        double v[5] = {action, (double)w0, (double)w1, (double)n_acc, (double)sum_A};
+        block_sum<5>(v, scratch);
+        if (tid == 0) {
+            if (sums) {
+                double* o = state_out + chain * SVB_VOBS_COUNT;
+                atomicAdd(o + SVB_VOBS_ACTION, half_kappa * v[0]);
+                atomicAdd(o + SVB_VOBS_WRAP0, v[1]);
+                atomicAdd(o + SVB_VOBS_WRAP1, v[2]);
+            }
+            if (counter_out) {
+                atomicAdd(counter_out + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, v[3]);
+                atomicAdd(counter_out + chain * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, v[4]);
+            }
+        }
+        __syncthreads();
+        action = 0.0; w0 = 0; w1 = 0; n_acc = 0; sum_A = 0.0f;
+    };
+
+    for (int it = 0; t < tiles; t += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const long long chain = t / tiles_per_chain;
+        const int tile = (int)(t - chain * tiles_per_chain);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int R = ty * kTileRows, C = tx * kTileCols;
+        if (chain != chain_of_sums) {
+            if (chain_of_sums >= 0 && (sums || counter_out)) flush(chain_of_sums);
+            chain_of_sums = chain;
+            const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
+            half_kappa = kappa / 2;
+            hk2 = (float)(half_kappa * 1.4426950408889634);
+            hkA = 1.0001f * hk2 * fc.bA; hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+        }
+        double* gphi = reinterpret_cast<double*>(a.phi) + chain * (long long)V;
+        int32_t* gn0 = a.n + chain * 2 * (long long)V;
+        unsigned char* st = tile_smem + stage * kTileStageBytes;
+        double* P = reinterpret_cast<double*>(st);
+        int32_t* N0 = reinterpret_cast<int32_t*>(st + kTilePhiSlot);
+        int32_t* N1 = reinterpret_cast<int32_t*>(st + kTilePhiSlot + kTileNSlot);
+
+        mbar_wait(&bar[stage], (uint32_t)((it >> 1) & 1));
+        const bool top = R == 0, bottom = R + kTileRows == N, left = C == 0, right = C + kTileCols == N;
+        if (top || bottom || left || right) {
+            // the periodic wrap: what lies beyond the edge of the lattice arrived as zeros; patch it from the other side
+            if (top && tid < kTileCols) {
+                P[2 + tid] = gphi[(N - 1) * N + C + tid];                                  // halo row R - 1 = row N - 1
+                N0[4 + tid] = gn0[(N - 1) * N + C + tid];
+            }
+            if (bottom && tid >= 128 && tid < 128 + kTileCols) P[(kTilePhiRows - 1) * kTilePhiCols + 2 + (tid - 128)] = gphi[C + (tid - 128)];
+            if (left && tid < kTileRows) {
+                P[(tid + 1) * kTilePhiCols + 1] = gphi[(R + tid) * N + N - 1];            // column C - 1 = column N - 1
+                N1[(tid + 1) * kTileNCols + 3] = gn0[V + (R + tid) * N + N - 1];
+            }
+            if (right && tid >= 32 && tid < 32 + kTileRows) P[(tid - 31) * kTilePhiCols + 2 + kTileCols] = gphi[(R + tid - 32) * N];   // column N = 0
+            __syncthreads();
+        }
+
+        const unsigned long long gc = a.chain0 + (unsigned long long)chain;
+        const int r = R + w8;
+        const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int jc = 2 * (lane + 32 * h);
+            const int x1 = C + jc + par;
+            const int xm1 = (x1 == 0) ? N - 1 : x1 - 1, xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+            const uint32_t c0 = (uint32_t)(oA + x1);
+            const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+            float4 rA, rB;
+            if (sums) {
+                rA = tile_site_residuals<true>(P, N0, N1, w8 + 1, jc, par, action, w0, w1);
+                rB = tile_site_residuals<true>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
+            } else {
+                rA = tile_site_residuals<false>(P, N0, N1, w8 + 1, jc, par, action, w0, w1);
+                rB = tile_site_residuals<false>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
+            }
+            stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc, gs, half_kappa,
+                                     hk2, hkA, hkB, n_acc, sum_A);
+        }
+        __syncthreads();                                           // every thread has read the stage: it may be refilled
+        const long long t2 = t + 2LL * gridDim.x;
+        if (tid == 0 && t2 < tiles) issue(t2, stage);
+    }
+    if (chain_of_sums >= 0 && (sums || counter_out)) flush(chain_of_sums);
+}
+
+// Tensor maps of the fields for the tile kernel: phi as (column, row, chain), n as (column, row, 2 chain + component).
+typedef CUresult (*svb_tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int villain_tile_maps(const VillainArgs& a, CUtensorMap& map_phi, CUtensorMap& map_n) {
+    static svb_tensor_map_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        SVB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status));
+        if (status != cudaDriverEntryPointSuccess || !fn) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<svb_tensor_map_encode_fn>(fn);
+    }
+    const cuuint64_t N = (cuuint64_t)a.N;
+    const cuuint32_t ones[3] = {1, 1, 1};
+    {
+        const cuuint64_t dims[3] = {N, N, (cuuint64_t)a.chains}, strides[2] = {N * 8, N * N * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)kTilePhiCols, (cuuint32_t)kTilePhiRows, 1};
+        const CUresult r = encode(&map_phi, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, a.phi, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled(phi) failed: %d", (int)r);
+    }
+    {
+        const cuuint64_t dims[3] = {N, N, 2 * (cuuint64_t)a.chains}, strides[2] = {N * 4, N * N * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileNCols, (cuuint32_t)kTileNRows, 1};
+        const CUresult r = encode(&map_n, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, a.n, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled(n) failed: %d", (int)r);
+    }
+    return 0;
+}
+
+// n_sweeps sweeps in place by TMA-staged colour passes (N a multiple of 128); obs_in / counters as launch_villain_stream_passes.
+static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, double* counters, cudaStream_t stream, const DeviceInfo& info) {
+    const bool unit = a.W == 1 && a.interval_n == 1;
+    auto kern = unit ? villain_tile_pass_kernel<true> : villain_tile_pass_kernel<false>;
+    static int per_sm_cache[2][64];
+    int per_sm = (info.device < 64) ? per_sm_cache[unit ? 1 : 0][info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, kTileSmemBytes));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "the tile pass kernel does not fit an SM");
+        if (info.device < 64) per_sm_cache[unit ? 1 : 0][info.device] = per_sm;
+    }
+    CUtensorMap map_phi, map_n;
+    const int rc = villain_tile_maps(a, map_phi, map_n);
+    if (rc) return rc;
+    const long long tiles = (long long)(a.N / kTileCols) * (a.N / kTileRows) * a.chains;
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > tiles) grid = tiles;
+    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    if (obs_in) {
+        villain_stream_dn2_kernel<<<(unsigned)(8 * info.sm_count), 256, 0, stream>>>(a.n, a.chains, a.N, obs_in);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    for (int sw = 0; sw < a.n_sweeps; ++sw)
+        for (int c = 0; c < 2; ++c) {
+            kern<<<(unsigned)grid, 256, kTileSmemBytes, stream>>>(a, fc, map_phi, map_n, c, sw, (sw == 0 && c == 0) ? obs_in : nullptr, counters);
+            SVB_CUDA_TRY(cudaGetLastError());
+        }
+    return 0;
+}

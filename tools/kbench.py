@@ -25,6 +25,9 @@ def step(k):
                              obs_in=obs_prev[k % R] if (use_obs and obs_in) else None)
     else:
         ops.villain_sweep(phi, n, 0.5, n_sweeps=sweeps, seed=1, sweep0=k * sweeps, obs=obs if use_obs else None)
+therm = int(os.environ.get('KB_THERM', 200))     # untimed sweeps: the acceptance rate of a fresh hot start is far from equilibrium
+for phi, n in sets:
+    if therm: ops.villain_sweep(phi, n, 0.5, n_sweeps=therm, seed=7, sweep0=10**6)
 for k in range(10): step(k)
 torch.cuda.synchronize()
 best = 1e9

@@ -13,6 +13,7 @@ chains = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 S = svb.Villain(svb.Lattice2D(N), 0.5)
 phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 1)
 obs = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+ops.villain_sweep(phi, n, 0.5, n_sweeps=int(os.environ.get('KB_THERM', 300)), seed=9, sweep0=10**6, path='tiled')   # thermalise
 
 
 def timeit(fn, reps=50):
@@ -30,6 +31,8 @@ def timeit(fn, reps=50):
     return best * 1e3
 
 
+use_obs = os.environ.get('KB_OBS', '1') == '1'
+if not use_obs: obs = None
 k = [0]
 def in_place():
     ops.villain_sweep(phi, n, 0.5, n_sweeps=1, seed=3, sweep0=k[0], path='tiled', obs=obs); k[0] += 1
