@@ -61,7 +61,7 @@ SHAPES = {
                kernel='villain_cluster_kernel<N=128, cluster of 4 x 512 threads>',
                workload='config4: Villain L=128 kappa scan, 8 kappa x 1024 chains/GPU (64 kappa in [0.3,1.2] over 8 GPUs), NeighborhoodUpdate sweep + observables'),
     'c5': dict(kind='villain', L=4096, chains=1, bytes=32, rotate=1, thermalise=20, cap=200,
-               kernel='villain_tiled_filtered_kernel (one CTA per tile, swapping buffer pairs)',
+               kernel='villain_tile_pass_kernel (TMA tensor-staged 16 x 128 tiles, one launch per colour, in place)',
                workload='config5: Villain L=4096 kappa=0.5, one lattice per GPU (replicas only), NeighborhoodUpdate sweep + observables'),
 }
 WORKLOAD = SHAPES['c2']['workload']
@@ -356,11 +356,9 @@ class Shape:
         G, kc = self.G, self.kappa_chain
         for a, b in self.sets:                                    # untimed thermalisation of the synthetic hot starts
             G.sweep_device(a, b, s['thermalise'], chain0=self.chain0, kappa_chain=kc)
-        if name == 'c5':
-            self.mode = 'swapping buffer pairs (svb_villain_sweep_tiled_swap)'
-            self.steppers = [G.swapping_device(a, b, chain0=self.chain0) for a, b in self.sets]
-        elif overlap:
-            self.mode = 'overlapped (programmatic dependent launch + per-chain epochs)'
+        if overlap:
+            self.mode = ('in place, one launch per colour pass + one over n for sum (dn)^2 (svb_villain_sweep_inplace)' if name == 'c5'
+                         else 'overlapped (programmatic dependent launch + per-chain epochs)')
             self.steppers = [G.overlapped_device(a, b, chain0=self.chain0, kappa_chain=kc) for a, b in self.sets]
         else:
             self.plans = [G.plan_device(a, b, obs=o, chain0=self.chain0, kappa_chain=kc) for (a, b), o in zip(self.sets, self.obs)]
@@ -368,9 +366,7 @@ class Shape:
     def step(self, k):
         r = k % len(self.sets)
         sps = self.sweeps_per_step
-        if self.name == 'c5':
-            self.sets[r] = self.steppers[r](sps, obs=self.obs[r])
-        elif self.steppers is None:
+        if self.steppers is None:
             self.plans[r](sps)
         elif self.spec['kind'] == 'villain':
             # the way BatchedEnsemble.generate steps: launch k writes its counters to record k and completes the state

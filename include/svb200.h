@@ -162,6 +162,23 @@ int svb_villain_sweep_tiled_swap(void* phi, int32_t* n, void* phi_ws, int32_t* n
                                  double* obs, int* state_in_workspace, void* stream);
 
 /*
+ * The same sweeps IN PLACE for lattices beyond a CTA (config 5: one L = 4096 lattice; any N that is a multiple of 16): one
+ * launch per colour pass, the fields stay where they are, only accepted proposals are written (svb_villain_stream.cuh; the tile
+ * of a CTA is staged in shared memory by TMA tensor loads when N is a multiple of 128).  No workspace.  Philox draws, fp64 phi,
+ * FAST arithmetic, interval_n <= 1.
+ *  obs            optional (chains, SVB_VOBS_COUNT).  With obs_in == NULL: the full record of the state AFTER the sweeps
+ *                 (one more read of the state) and this call's ACCEPTED / ACCEPTANCE.
+ *  obs_in         optional (needs obs): as in svb_villain_sweep_overlapped -- the state columns ACTION .. WRAP1 of the lattice AS IT
+ *                 ARRIVES are written to obs_in (action and wrapping ride along with the first colour pass, sum (dn)^2 is one pass
+ *                 over n), its counter columns are left alone, and `obs` receives only this call's ACCEPTED and ACCEPTANCE.
+ */
+int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, int N,
+                              double kappa, const double* kappa_chain, int W,
+                              double interval_phi, int interval_n,
+                              int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                              double* obs, double* obs_in, void* stream);
+
+/*
  * The same sweeps as OVERLAPPED launches: a launch may begin while the previous launch in the stream is still running
  * (programmatic dependent launch), so the ramp-up of one sweep hides under the tail of the one before -- at config 2 a
  * quarter of a non-overlapped step.  Data dependencies are tracked per chain instead of per kernel:

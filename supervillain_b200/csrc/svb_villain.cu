@@ -1325,6 +1325,21 @@ __global__ void villain_zero_record_kernel(double* obs, long long chains, int ke
     }
 }
 
+// one launch for both records of svb_villain_sweep_inplace: the state columns of `state` (if any), the counters of `counters`
+__global__ void villain_zero_inplace_records_kernel(double* state, double* counters, long long chains) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < chains) {
+        if (state) {
+            double* o = state + c * SVB_VOBS_COUNT;
+            o[SVB_VOBS_ACTION] = 0.0; o[SVB_VOBS_SUM_DN2] = 0.0; o[SVB_VOBS_WRAP0] = 0.0; o[SVB_VOBS_WRAP1] = 0.0;
+        }
+        if (counters) {
+            counters[c * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED] = 0.0;
+            counters[c * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE] = 0.0;
+        }
+    }
+}
+
 __global__ void villain_zero_counters_kernel(double* obs, long long chains) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < chains) {
@@ -1726,6 +1741,14 @@ static int launch_villain_obs(const real* phi, const int32_t* n, long long chain
     if (V <= 16384 || chains >= want_ctas) {
         long long grid = chains < want_ctas ? chains : want_ctas;
         villain_obs_kernel<real><<<(unsigned)grid, 256, 0, stream>>>(phi, n, chains, N, kappa, kappa_chain, obs, keep_counters);
+        SVB_CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (sizeof(real) == 8 && N % 16 == 0 && ((uintptr_t)phi % 16 == 0) && ((uintptr_t)n % 16 == 0)) {
+        // vectorised streaming pass (svb_villain_stream.cuh): four sites per thread from 16-byte loads
+        villain_zero_record_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, stream>>>(obs, chains, keep_counters);
+        SVB_CUDA_TRY(cudaGetLastError());
+        villain_stream_obs_kernel<<<(unsigned)want_ctas, 256, 0, stream>>>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs);
         SVB_CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -2211,4 +2234,43 @@ extern "C" int svb_villain_sweep_tiled_swap(void* phi, int32_t* n, void* phi_ws,
     if (!state_in_workspace) return fail(SVB_E_NULL, "svb_villain_sweep_tiled_swap: state_in_workspace is required");
     return villain_sweep_tiled_impl(phi, n, phi_ws, n_ws, chains, N, kappa, kappa_chain, W, interval_phi, interval_n, n_sweeps, seed,
                                     sweep0, chain0, arith_mode, obs, nullptr, nullptr, stream, true, state_in_workspace);
+}
+
+// In-place sweeps by colour passes for lattices beyond a CTA (svb_villain_stream.cuh): see include/svb200.h.
+extern "C" int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain, int W,
+                                         double interval_phi, int interval_n, int n_sweeps, uint64_t seed, uint64_t sweep0,
+                                         uint64_t chain0, double* obs, double* obs_in, void* stream) {
+    if (!phi || !n) return fail(SVB_E_NULL, "svb_villain_sweep_inplace: phi and n are required");
+    if (chains < 0 || N < 16 || N > 32768 || (N % 16) != 0)
+        return fail(SVB_E_SHAPE, "svb_villain_sweep_inplace: N=%d must be a multiple of 16 (chains=%lld)", N, (long long)chains);
+    if (((uintptr_t)phi % 16) || ((uintptr_t)n % 16)) return fail(SVB_E_ALIGN, "svb_villain_sweep_inplace: fields must be 16-byte aligned");
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_inplace: kappa must be positive");
+    if (W < 1 || !(interval_phi >= 0) || n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_sweep_inplace: W / interval_phi / n_sweeps");
+    if (interval_n < 0 || villain_wide(interval_n))
+        return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_inplace: interval_n must be 0 or 1 (wider proposals: svb_villain_sweep)");
+    if (obs_in && !obs) return fail(SVB_E_NULL, "svb_villain_sweep_inplace: obs_in needs obs (this launch's counters go there)");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
+    a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    villain_rng_setup(a, STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE, 0);
+    a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
+    a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0; a.obs_in = obs_in; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceInfo info;
+    int rc = get_device_info(info);
+    if (rc) return rc;
+    if (obs || obs_in) {    // the state columns of the arriving state are accumulated into obs_in, this launch's counters into obs
+        villain_zero_inplace_records_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs_in, obs, chains);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    const char* ep = getenv("SVB_VILLAIN_PASS");
+    const bool tma = N % kTileCols == 0 && chains * 2 < 0x7fffffffLL && !(ep && ep[0] == 's');
+    rc = tma ? launch_villain_tile_passes(a, obs_in, obs, st, info) : launch_villain_stream_passes(a, obs_in, obs, st, info);
+    if (rc) return rc;
+    if (obs && !obs_in)     // the full record of the state after the sweeps: one more read of the state
+        return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
+    return SVB_OK;
 }

@@ -229,12 +229,19 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     double* red_state = reinterpret_cast<double*>(rc1 + V);                       // [NW][4] per-warp partial sums
     double* red_count = red_state + 4 * NW;                                       // [NW][2]
     uint64_t* bar = reinterpret_cast<uint64_t*>(red_count + 2 * NW);
+    // UNIT: the 81 proposals of (dn_f0, dn_b0, dn_f1, dn_b1) as the residual changes they make, -2 pi (digit): the code that the
+    // multiply by 81 leaves in the high word looks up all four at once (one LDS.128 instead of nine integer operations and four
+    // conversions per site).  0, 2 pi and 4 pi are exact in fp32, so base + lut is the fused multiply-add it replaces, bit for bit.
+    float4* dn_lut = reinterpret_cast<float4*>(bar + 2);
     constexpr int kWriter = 32;            // finishes the records: lane 0 of warp 1 (thread 0 is busy with the bulk copies)
 
     if (tid == 0) {
         for (int b = 0; b < STAGES; ++b) mbar_init(&bar[b], 1);
         fence_mbar_init();
     }
+    if (UNIT)
+        for (int i = tid; i < 81; i += T)
+            dn_lut[i] = make_float4(-fc.c * (float)(i / 27), -fc.c * (float)((i / 9) % 3), -fc.c * (float)((i / 3) % 3), -fc.c * (float)(i % 3));
     if (OVERLAP) {
         // let the next launch in the stream start as soon as every CTA of this one is resident ...
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -411,6 +418,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     int32_t* n0bA = (p == 0) ? N0b_q0 : N0b;
                     // proposals: four base-K digits each, then the leading 32 bits of the uniform
                     uint32_t fA = bits.y, fB = bits.w;
+                    uint32_t codeA = 0, codeB = 0;
                     int digA[4], digB[4];
                     if (MODE == SVB_FILT_EXACT) {
                         // z = the idx-th of the 2 I nonzero values in [-I, I]; n += d z: forward links -z, backward links +z.
@@ -426,17 +434,12 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
 #pragma unroll
                         for (int i = 0; i < 4; ++i) digA[i] = digB[i] = 0;            // word B is the uniform's leading bits as it stands
                     } else if (UNIT) {
-                        // four successive multiply-highs by 3 == one by 81: hi = 27 d0 + 9 d1 + 3 d2 + d3, lo = the remainder
-                        // (one quarter-rate IMAD.WIDE instead of a chain of four; 28.40 -> 28.24 us per step)
+                        // four successive multiply-highs by 3 == one by 81: hi = 27 d0 + 9 d1 + 3 d2 + d3 (the code), lo = the remainder
+                        // (one quarter-rate IMAD.WIDE instead of a chain of four); the digits themselves are needed only by the
+                        // rare paths (unit_digits below) -- the residual changes come from the look-up table
                         const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
                         fA = (uint32_t)pa; fB = (uint32_t)pb;
-                        uint32_t ia = (uint32_t)(pa >> 32), ib = (uint32_t)(pb >> 32);
-                        digA[0] = (int)((ia * 2428u) >> 16); ia -= 27u * (uint32_t)digA[0];
-                        digB[0] = (int)((ib * 2428u) >> 16); ib -= 27u * (uint32_t)digB[0];
-                        digA[1] = (int)((ia * 7282u) >> 16); ia -= 9u * (uint32_t)digA[1];
-                        digB[1] = (int)((ib * 7282u) >> 16); ib -= 9u * (uint32_t)digB[1];
-                        digA[2] = (int)((ia * 21846u) >> 16); digA[3] = (int)(ia - 3u * (uint32_t)digA[2]);
-                        digB[2] = (int)((ib * 21846u) >> 16); digB[3] = (int)(ib - 3u * (uint32_t)digB[2]);
+                        codeA = (uint32_t)(pa >> 32); codeB = (uint32_t)(pb >> 32);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -453,10 +456,19 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     const float2 r_f0 = make_float2(R0own[T * qA], R0own[T * qB]), r_f1 = make_float2(R1own[T * qA], R1own[T * qB]);
                     const float2 r_b0 = make_float2(r0bA[T * qA], R0b[T * qB]), r_b1 = make_float2(R1b[T * qA], R1b[T * qB]);
                     // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
-                    const float2 dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
-                    const float2 dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
-                    const float2 dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
-                    const float2 dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    float2 dr_f0, dr_b0, dr_f1, dr_b1;
+                    if (UNIT) {
+                        const float4 tA = dn_lut[codeA], tB = dn_lut[codeB];
+                        dr_f0 = __fadd2_rn(base_f, make_float2(tA.x, tB.x));
+                        dr_b0 = __fadd2_rn(base_b, make_float2(tA.y, tB.y));
+                        dr_f1 = __fadd2_rn(base_f, make_float2(tA.z, tB.z));
+                        dr_b1 = __fadd2_rn(base_b, make_float2(tA.w, tB.w));
+                    } else {
+                        dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
+                        dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
+                        dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
+                        dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    }
                     float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
                     acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
                     acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
@@ -473,21 +485,35 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                     // the residuals an accepted proposal leaves behind
                     const float2 n_f0 = __fadd2_rn(r_f0, dr_f0), n_b0 = __fadd2_rn(r_b0, dr_b0);
                     const float2 n_f1 = __fadd2_rn(r_f1, dr_f1), n_b1 = __fadd2_rn(r_b1, dr_b1);
+                    // certainly rejected (the overwhelming majority of proposals): nothing more to do.  Everything else -- accepted, or
+                    // inside the error band of the fp32 comparison -- is handled behind ONE branch per pair of sites.
+                    const bool candA = !(diff.x > band.x) || fA < 65536u, candB = !(diff.y > band.y) || fB < 65536u;
+                    if (candA || candB) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (!(h ? candB : candA)) continue;
                         const int q = 2 * p + h;
                         float* r0b = h ? R0b : r0bA;
                         int32_t* n0b = h ? N0b : n0bA;
                         const uint32_t wA = h ? bits.z : bits.x;
                         const uint32_t f = h ? fB : fA;
-                        const int* dig = h ? digB : digA;
+                        int dig[4];
+                        if (UNIT) {
+                            uint32_t code = h ? codeB : codeA;
+                            dig[0] = (int)((code * 2428u) >> 16); code -= 27u * (uint32_t)dig[0];
+                            dig[1] = (int)((code * 7282u) >> 16); code -= 9u * (uint32_t)dig[1];
+                            dig[2] = (int)((code * 21846u) >> 16); dig[3] = (int)(code - 3u * (uint32_t)dig[2]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dig[i] = h ? digB[i] : digA[i];
+                        }
                         const float dif = h ? diff.y : diff.x, bnd = h ? band.y : band.x;
+                        const int x0 = row8 + 8 * q;
                         bool ok = dif < 0.0f;
                         if (!(fabsf(dif) > bnd) || f < 65536u) {
                             ExactProposal ep;
                             if (SPARSE) { ep.phi = gphi; ep.n0 = gn0; ep.n1 = gn1; }
                             else { ep.phi = sphi; ep.n0 = sn0; ep.n1 = sn1; }
-                            const int x0 = row8 + 8 * q;
                             ep.i_c = x0 * N + x1;
                             ep.i_b0 = ((x0 - 1) & (N - 1)) * N + x1;
                             ep.i_b1 = x0 * N + ((x1 - 1) & (N - 1));
@@ -516,26 +542,28 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
                             const double Ah = __hiloint2double(0x43300000, (int)wA) - 4503599627370495.5;
                             if (SPARSE) {
                                 // straight to global memory, nothing waits for it: the fp64 reduction rounds once, to nearest,
-                                // like the reference's phi + dphi; the offsets are those of the shared-memory copy
-                                atomicAdd(gphi + (Pc - sphi) + 2 * T * q, __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
-                                atomicAdd(gn0 + (N0c - sn0) + 2 * T * q, W * dig[0] + mWI);
-                                atomicAdd(gn0 + (n0b - sn0) + 2 * T * q, W * dig[1] + mWI);
-                                atomicAdd(gn0 + (N1c - sn0) + 2 * T * q, W * dig[2] + mWI);      // sn1 = sn0 + V, gn1 = gn0 + V
-                                atomicAdd(gn0 + (N1b - sn0) + 2 * T * q, W * dig[3] + mWI);
+                                // like the reference's phi + dphi
+                                const int ic = x0 * N + x1;
+                                atomicAdd(gphi + ic, __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
+                                atomicAdd(gn0 + ic, W * dig[0] + mWI);
+                                atomicAdd(gn0 + ((x0 - 1) & (N - 1)) * N + x1, W * dig[1] + mWI);
+                                atomicAdd(gn1 + ic, W * dig[2] + mWI);
+                                atomicAdd(gn1 + x0 * N + ((x1 - 1) & (N - 1)), W * dig[3] + mWI);
                             } else {
-                            Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
-                            if (MODE != SVB_FILT_SITE) {
-                                atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
-                                atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
-                                atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
-                                atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
-                            }
+                                Pc[2 * T * q] = __dadd_rn(Pc[2 * T * q], __dadd_rn(-a.interval_phi, __dmul_rn(two_I_scaled, Ah)));
+                                if (MODE != SVB_FILT_SITE) {
+                                    atomicAdd(N0c + 2 * T * q, W * dig[0] + mWI);  // only this thread touches these links in this pass
+                                    atomicAdd(n0b + 2 * T * q, W * dig[1] + mWI);
+                                    atomicAdd(N1c + 2 * T * q, W * dig[2] + mWI);
+                                    atomicAdd(N1b + 2 * T * q, W * dig[3] + mWI);
+                                }
                             }
                             R0own[T * q] = h ? n_f0.y : n_f0.x;
                             r0b[T * q] = h ? n_b0.y : n_b0.x;
                             R1own[T * q] = h ? n_f1.y : n_f1.x;
                             R1b[T * q] = h ? n_b1.y : n_b1.x;
                         }
+                    }
                     }
                 }
                 if (!SPARSE && s == a.n_sweeps - 1 && c == 1) fence_proxy_async();      // this thread's phi / n writes -> visible to the bulk store
@@ -629,7 +657,7 @@ static int launch_villain_filtered(const VillainArgs& a, cudaStream_t stream, co
                           : (unit ? villain_smem_filtered_kernel<NT, MINB, STAGES, false, true, SVB_FILT_FAST>
                                   : villain_smem_filtered_kernel<NT, MINB, STAGES, false, false, SVB_FILT_FAST>);
     const size_t V = (size_t)NT * NT;
-    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32;
+    const size_t smem = STAGES * V * 16 + 2 * V * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 32 + 81 * sizeof(float4);
     // kernel attributes and occupancy are set / queried once per (instantiation, device)
     static int per_sm_cache[11][64];
     const int variant = mode != SVB_FILT_FAST ? 3 + mode : sparse ? 7 + (overlap ? 1 : 0) + (unit ? 2 : 0) : (overlap ? 1 : 0) + (unit ? 2 : 0);

@@ -469,36 +469,75 @@ __global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __gri
     }
 }
 
-__global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* __restrict__ n, long long chains, int N,
-                                                                 double* __restrict__ state_out) {
-    __shared__ double scratch[32];
+// sum (dn)^2 of every chain, reading n once: a warp owns 64 columns and walks down `rows` consecutive rows, a lane keeps the
+// pair (n0, n1)[2k, 2k + 1] of the current row and needs only the next row's n1 pair (which it keeps for the next step) and its
+// right-hand neighbour's n0 (a shuffle; the last lane of a warp loads it).  (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]).
+// Grid: chains x bands x row runs; per-warp partial sums added atomically (the caller zeroes SVB_VOBS_SUM_DN2).
+__global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* __restrict__ n, long long chains, int N, int bands,
+                                                                 int runs, int rows, double* __restrict__ state_out) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long w = (long long)blockIdx.x * 8 + (tid >> 5);                  // global warp index = (chain, run, band)
+    const long long per_chain = (long long)bands * runs;
+    if (w >= chains * per_chain) return;
+    const long long chain = w / per_chain;
+    const int rem = (int)(w - chain * per_chain);
+    const int run = rem / bands, band = rem - run * bands;
+    const int k = 32 * band + lane;
     const long long V = (long long)N * N;
-    const int HN = N / 2;
-    const long long quads_per_chain = (long long)(N / 2) * HN;          // thread = (row pair, column pair): four sites
-    const int tid = threadIdx.x;
-    const int chunks = (int)((quads_per_chain + 255) / 256);
-    long long chain_of_sum = -1;
+    const int32_t* gn0 = n + chain * 2 * V;
+    const int32_t* gn1 = gn0 + V;
     long long dn2 = 0;
-    auto flush = [&](long long chain) {
-        double v[1] = {(double)dn2};
-        block_sum<1>(v, scratch);
-        if (tid == 0) atomicAdd(state_out + chain * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, v[0]);
-        __syncthreads();
-        dn2 = 0;
-    };
-    for (long long t = blockIdx.x; t < chains * chunks; t += gridDim.x) {
-        const long long chain = t / chunks;
-        if (chain != chain_of_sum) {
-            if (chain_of_sum >= 0) flush(chain_of_sum);
-            chain_of_sum = chain;
+    const bool active = k < N / 2;
+    const int c = active ? 2 * k : 0;
+    const int cr = (c + 2 == N) ? 0 : c + 2;                                       // the column right of the pair, wrapped
+    const int r_lo = run * rows, r_hi = min(N, r_lo + rows);
+    int2 m1 = *reinterpret_cast<const int2*>(gn1 + (long long)r_lo * N + c);
+    const bool edge = lane == 31 || k + 1 >= N / 2;
+    int r = r_lo;
+    // four rows at a time: their eight (nine) loads are in flight together -- a warp has little else to hide DRAM latency with
+    for (; r + 4 <= r_hi; r += 4) {
+        int2 m0[4], up[4];
+        int hrq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rn = (r + i + 1 == N) ? 0 : r + i + 1;
+            m0[i] = *reinterpret_cast<const int2*>(gn0 + (long long)(r + i) * N + c);
+            up[i] = *reinterpret_cast<const int2*>(gn1 + (long long)rn * N + c);
+            hrq[i] = edge ? gn0[(long long)(r + i) * N + cr] : 0;
         }
-        const long long q = (t - chain * chunks) * 256 + tid;
-        if (q < quads_per_chain) {
-            const int rp = (int)(q / HN), k = (int)(q - (long long)rp * HN);
-            dn2 += stream_dn2_rows(n + chain * 2 * V, n + chain * 2 * V + V, N, (rp & 7) | ((rp >> 3) << 4), k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int sh = __shfl_down_sync(0xffffffffu, m0[i].x, 1);
+            const int hr = edge ? hrq[i] : sh;
+            const int d0 = (up[i].x - m1.x) - (m0[i].y - m0[i].x), d1 = (up[i].y - m1.y) - (hr - m0[i].y);
+            if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+            m1 = up[i];
         }
     }
-    if (chain_of_sum >= 0) flush(chain_of_sum);
+    for (; r < r_hi; ++r) {
+        const int rn = (r + 1 == N) ? 0 : r + 1;
+        const int2 m0 = *reinterpret_cast<const int2*>(gn0 + (long long)r * N + c);
+        const int2 up = *reinterpret_cast<const int2*>(gn1 + (long long)rn * N + c);
+        int hr = __shfl_down_sync(0xffffffffu, m0.x, 1);
+        if (edge) hr = gn0[(long long)r * N + cr];
+        const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (hr - m0.y);
+        if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+        m1 = up;
+    }
+    dn2 = warp_sum(dn2);
+    if (lane == 0) atomicAdd(state_out + chain * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, (double)dn2);
+}
+
+static int launch_villain_stream_dn2(const int32_t* n, long long chains, int N, double* state_out, cudaStream_t stream, const DeviceInfo& info) {
+    const int bands = (N / 2 + 31) / 32;
+    // rows per warp: long runs amortise the set-up and the one redundant row, short runs fill the machine (>= 16 warps per SM slot)
+    int rows = N;
+    while (rows > 16 && chains * bands * ((N + rows - 1) / rows) < 4LL * 64 * info.sm_count) rows = (rows + 1) / 2;
+    const int runs = (N + rows - 1) / rows;
+    const long long warps = chains * bands * runs;
+    villain_stream_dn2_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(n, chains, N, bands, runs, rows, state_out);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 // n_sweeps sweeps in place; obs_in (optional): the state columns of the arriving lattice (zeroed by the caller), filled by a pass
@@ -520,8 +559,8 @@ static int launch_villain_stream_passes(const VillainArgs& a, double* obs_in, do
     if (grid > 0x7fffffffLL) return fail(SVB_E_SHAPE, "streaming villain passes: too many CTAs (%lld)", grid);
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
     if (obs_in) {
-        villain_stream_dn2_kernel<<<(unsigned)(8 * info.sm_count), 256, 0, stream>>>(a.n, a.chains, a.N, obs_in);
-        SVB_CUDA_TRY(cudaGetLastError());
+        const int rc_dn2 = launch_villain_stream_dn2(a.n, a.chains, a.N, obs_in, stream, info);
+        if (rc_dn2) return rc_dn2;
     }
     for (int sw = 0; sw < a.n_sweeps; ++sw)
         for (int c = 0; c < 2; ++c) {
@@ -529,6 +568,51 @@ static int launch_villain_stream_passes(const VillainArgs& a, double* obs_in, do
             SVB_CUDA_TRY(cudaGetLastError());
         }
     return 0;
+}
+
+// Observables of the current state for lattices that do not fit a CTA (N a multiple of 16, fp64): a thread takes the four
+// sites (r, 2k), (r, 2k + 1), (r + 8, 2k), (r + 8, 2k + 1) with 16-byte loads (stream_obs_rows), CTAs stride over chunks of 256
+// such quads, block partials are added atomically (the caller zeroes the state columns).  One read of the state.
+__global__ void __launch_bounds__(256) villain_stream_obs_kernel(const double* __restrict__ phi, const int32_t* __restrict__ n,
+                                                                 long long chains, int N, double kappa_scalar,
+                                                                 const double* __restrict__ kappa_chain, double* __restrict__ obs) {
+    __shared__ double scratch[4 * 32];
+    const long long V = (long long)N * N;
+    const int HN = N / 2;
+    const long long quads_per_chain = (long long)(N / 2) * HN;
+    const int tid = threadIdx.x;
+    const int chunks = (int)((quads_per_chain + 255) / 256);
+    long long chain_of_sum = -1;
+    double action = 0.0;
+    long long dn2 = 0;
+    int w0 = 0, w1 = 0;
+    auto flush = [&](long long chain) {
+        double v[4] = {action, (double)dn2, (double)w0, (double)w1};
+        block_sum<4>(v, scratch);
+        if (tid == 0) {
+            const double kappa = kappa_chain ? kappa_chain[chain] : kappa_scalar;
+            double* o = obs + chain * SVB_VOBS_COUNT;
+            atomicAdd(o + SVB_VOBS_ACTION, (kappa / 2) * v[0]);
+            atomicAdd(o + SVB_VOBS_SUM_DN2, v[1]);
+            atomicAdd(o + SVB_VOBS_WRAP0, v[2]);
+            atomicAdd(o + SVB_VOBS_WRAP1, v[3]);
+        }
+        __syncthreads();
+        action = 0.0; dn2 = 0; w0 = 0; w1 = 0;
+    };
+    for (long long t = blockIdx.x; t < chains * chunks; t += gridDim.x) {
+        const long long chain = t / chunks;
+        if (chain != chain_of_sum) {
+            if (chain_of_sum >= 0) flush(chain_of_sum);
+            chain_of_sum = chain;
+        }
+        const long long q = (t - chain * chunks) * 256 + tid;
+        if (q < quads_per_chain) {
+            const int rp = (int)(q / HN), k = (int)(q - (long long)rp * HN);
+            stream_obs_rows(phi + chain * V, n + chain * 2 * V, n + chain * 2 * V + V, N, (rp & 7) | ((rp >> 3) << 4), k, action, dn2, w0, w1);
+        }
+    }
+    if (chain_of_sum >= 0) flush(chain_of_sum);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -603,6 +687,7 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
                                                                    double* __restrict__ state_out, double* __restrict__ counter_out) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ double scratch[5 * 32];
+    __shared__ int tile_coord[2][4];          // per stage: chain, R, C of the tile that was loaded into it (written by thread 0)
     const int N = a.N, V = N * N;
     const int tiles_x = N / kTileCols, tiles_y = N / kTileRows, tiles_per_chain = tiles_x * tiles_y;
     const long long tiles = (long long)tiles_per_chain * a.chains;
@@ -623,6 +708,7 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
         const int tile = (int)(t - chain * tiles_per_chain);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int R = ty * kTileRows, C = tx * kTileCols;
+        tile_coord[stage][0] = (int)chain; tile_coord[stage][1] = R; tile_coord[stage][2] = C;
         unsigned char* st = tile_smem + stage * kTileStageBytes;
         mbar_expect_tx(&bar[stage], (uint32_t)(kTilePhiBytes + 2 * kTileNBytes));
         tensor_box_3d(st, &map_phi, C - 2, R - 1, (int)chain, &bar[stage]);
@@ -634,6 +720,7 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
         if (t < tiles) issue(t, 0);
         if (t + gridDim.x < tiles) issue(t + gridDim.x, 1);
     }
+    __syncthreads();                                               // the coordinates of the first two tiles are published
 
     double action = 0.0, half_kappa = 0.0;
     int w0 = 0, w1 = 0, n_acc = 0;
@@ -660,10 +747,9 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
 
     for (int it = 0; t < tiles; t += gridDim.x, ++it) {
         const int stage = it & 1;
-        const long long chain = t / tiles_per_chain;
-        const int tile = (int)(t - chain * tiles_per_chain);
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int R = ty * kTileRows, C = tx * kTileCols;
+        // (one thread did the divisions when it issued the loads; everybody else reads the result)
+        const long long chain = tile_coord[stage][0];
+        const int R = tile_coord[stage][1], C = tile_coord[stage][2];
         if (chain != chain_of_sums) {
             if (chain_of_sums >= 0 && (sums || counter_out)) flush(chain_of_sums);
             chain_of_sums = chain;
@@ -717,9 +803,11 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
             stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc, gs, half_kappa,
                                      hk2, hkA, hkB, n_acc, sum_A);
         }
-        __syncthreads();                                           // every thread has read the stage: it may be refilled
+        __syncthreads();                                           // every thread has read the stage (and its coordinates): refill it
         const long long t2 = t + 2LL * gridDim.x;
         if (tid == 0 && t2 < tiles) issue(t2, stage);
+        // (the coordinates thread 0 has just written belong to the iteration after next: a barrier -- the next iteration's --
+        // lies between this write and their first read)
     }
     if (chain_of_sums >= 0 && (sums || counter_out)) flush(chain_of_sums);
 }
@@ -777,8 +865,8 @@ static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, doub
     if (grid > tiles) grid = tiles;
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
     if (obs_in) {
-        villain_stream_dn2_kernel<<<(unsigned)(8 * info.sm_count), 256, 0, stream>>>(a.n, a.chains, a.N, obs_in);
-        SVB_CUDA_TRY(cudaGetLastError());
+        const int rc_dn2 = launch_villain_stream_dn2(a.n, a.chains, a.N, obs_in, stream, info);
+        if (rc_dn2) return rc_dn2;
     }
     for (int sw = 0; sw < a.n_sweeps; ++sw)
         for (int c = 0; c < 2; ++c) {

@@ -120,8 +120,14 @@ class NeighborhoodUpdate(Generator):
         gets this launch's counters only.  Raises NotImplementedError where the overlapped kernel does not apply."""
         if self.rng is not None or self.arithmetic != 'fast' or self.path != 'auto':
             raise NotImplementedError('overlapped launches serve Philox draws, FAST arithmetic, path="auto"')
-        ov = ops.VillainOverlappedSweeps(phi, n, self.kappa, W=self.Action.W, interval_phi=self.interval_phi,
-                                         interval_n=self.interval_n, seed=self.seed, chain0=chain0, kappa_chain=kappa_chain)
+        kw = dict(W=self.Action.W, interval_phi=self.interval_phi, interval_n=self.interval_n, seed=self.seed, chain0=chain0,
+                  kappa_chain=kappa_chain)
+        N = int(phi.shape[-1])
+        if N not in ops.VILLAIN_OVERLAP_SIZES and N > 128 and N % 16 == 0:
+            # lattices beyond a CTA (config 5): in-place colour passes with the same step / obs_in protocol
+            ov = ops.VillainInplaceSweeps(phi, n, self.kappa, **kw)
+        else:
+            ov = ops.VillainOverlappedSweeps(phi, n, self.kappa, **kw)
 
         def step(n_sweeps=1, obs=None, obs_in=None):
             ov.step(self.counter, n_sweeps, obs, obs_in)

@@ -248,6 +248,38 @@ class VillainOverlappedSweeps:
         self.fenced = False
 
 
+class VillainInplaceSweeps:
+    """Back-to-back Philox sweeps of lattices beyond a CTA (config 5: L = 4096; any N that is a multiple of 16), IN PLACE by
+    colour passes (svb_villain_sweep_inplace): no workspace, only accepted proposals are written.  The `step` / `fence`
+    interface of `VillainOverlappedSweeps`, including the records of the arriving state (`obs_in`); the launches are ordinary
+    ones (two per sweep), so `fence` has nothing to do."""
+
+    def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None):
+        self.lib = _lib.load()
+        self.chains, self.N = _fields_shape(phi, 'phi', 1)
+        if self.N % 16 or phi.dtype != torch.float64 or int(interval_n) > 1:
+            raise NotImplementedError('in-place sweeps need fp64 phi, N a multiple of 16 and interval_n <= 1')
+        self.p_phi = _dev(phi, 'phi', (torch.float64,))
+        self.p_n = _dev(n, 'n', (torch.int32,), (self.chains, 2, self.N, self.N))
+        if W != W or W == float('inf') or int(W) != W:
+            raise ValueError('the Villain NeighborhoodUpdate needs a finite integer W')
+        self.p_kc = _opt(kappa_chain, 'kappa_chain', (torch.float64,), (self.chains,))
+        self.args = (float(kappa), self.p_kc, int(W), float(interval_phi), int(interval_n))
+        self.seed, self.chain0 = int(seed) & (2**64 - 1), int(chain0)
+        self._keep = (phi, n, kappa_chain)
+        self._fn = self.lib.svb_villain_sweep_inplace
+        self._stream = torch.cuda.current_stream
+
+    def fence(self):
+        pass
+
+    def step(self, sweep0, n_sweeps=1, obs=None, obs_in=None):
+        p_obs = None if obs is None else _dev(obs, 'obs', (torch.float64,), (self.chains, VOBS_COUNT))
+        p_obs_in = None if obs_in is None else _dev(obs_in, 'obs_in', (torch.float64,), (self.chains, VOBS_COUNT))
+        _lib.check(self._fn(self.p_phi, self.p_n, self.chains, self.N, *self.args, int(n_sweeps), self.seed, int(sweep0), self.chain0,
+                            p_obs, p_obs_in, self._stream().cuda_stream))
+
+
 class WorldlineOverlappedSweeps:
     """Back-to-back Philox worldline sweeps (W = 1; mode 'joint', or 'vortex' / 'coexact' with interval <= 2) of ONE chain
     set as overlapped launches (svb_worldline_sweep_overlapped); the protocol and the `fence()` rule are those of

@@ -610,3 +610,87 @@ def test_overlapped_launch_protocol_soak(kind):
         assert torch.equal(a, sets[i][0]) and torch.equal(b, sets[i][1]), (kind, i)
         assert torch.equal(total, recs[i][:, :, 4].sum(dim=0)) and float(total.sum()) > 0
         assert int(steppers[i].epochs.min()) == steppers[i].epoch == K
+
+
+@pytest.mark.parametrize('N,chains,W,kappa', [(256, 3, 1, 0.5), (128, 5, 2, 0.3), (144, 2, 1, 0.4), (48, 7, 1, 0.6), (384, 1, 1, 0.8)])
+def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa):
+    """svb_villain_sweep_inplace (svb_villain_stream.cuh): one launch per colour pass, in place, only accepted proposals written.
+    N a multiple of 128 runs on TMA tensor-staged tiles (tiles on the edge of the lattice patch the periodic wrap), any other
+    multiple of 16 straight from global memory.  Fields identical to the C oracle; the records of the ARRIVING state (obs_in:
+    action and wrapping from the first colour pass, sum (dn)^2 from a pass over n) complete the previous step's record, the
+    record of the state AFTER the sweeps (no obs_in) comes from one more read -- both equal to the restated reference."""
+    from oracle import c_oracle as C
+    seed, K = 29, 3
+    phi0, n0 = V.hot_start(np.random.default_rng(N + chains), N, chains)
+    n0 = n0 * W
+    kc = np.linspace(kappa, kappa + 0.2, chains)
+    refs = []
+    p, q = phi0, n0
+    for k in range(K):
+        out = [C.villain_sweep_philox(p[i:i + 1], q[i:i + 1], kc[i], W=W, n_sweeps=1, seed=seed, sweep0=k, chain0=4 + i) for i in range(chains)]
+        p, q = np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
+        refs.append((p, q, np.concatenate([o[2] for o in out]), np.concatenate([o[3] for o in out])))
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    st = ops.VillainInplaceSweeps(phi, n, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc))
+    rec = torch.full((K, chains, VOBS_COUNT), -7.0, dtype=torch.float64, device='cuda')
+    scratch = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    for k in range(K):
+        st.step(k, 1, obs=rec[k], obs_in=rec[k - 1] if k else scratch)
+    torch.cuda.synchronize()
+    p_ref, n_ref = refs[-1][0], refs[-1][1]
+    assert (n.cpu().numpy() == n_ref).all() and (phi.cpu().numpy() == p_ref).all()
+    got = rec.cpu().numpy()
+    for k in range(K):
+        assert (got[k, :, VOBS_ACCEPTED] == refs[k][2]).all()
+        np.testing.assert_allclose(got[k, :, VOBS_ACCEPTANCE], refs[k][3], rtol=1e-5)
+        if k < K - 1:                                   # completed by the launch after
+            pk, qk = refs[k][0], refs[k][1]
+            np.testing.assert_allclose(got[k, :, VOBS_ACTION], V.action(pk, qk, 1.0) * kc, rtol=1e-12)
+            assert (got[k, :, VOBS_SUM_DN2] == (lat.d1(qk) ** 2).sum(axis=(-3, -2, -1))).all()
+            assert (got[k, :, VOBS_WRAP0] == qk[:, 0].sum(axis=(-2, -1))).all() and (got[k, :, VOBS_WRAP1] == qk[:, 1].sum(axis=(-2, -1))).all()
+    # the full record of the state after the sweeps, two sweeps fused into one call
+    phi2, n2 = dev(phi0), dev(n0, torch.int32)
+    full = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.VillainInplaceSweeps(phi2, n2, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc)).step(0, 2, obs=full)
+    p2, q2 = refs[1][0], refs[1][1]
+    assert (n2.cpu().numpy() == q2).all() and (phi2.cpu().numpy() == p2).all()
+    f = full.cpu().numpy()
+    np.testing.assert_allclose(f[:, VOBS_ACTION], V.action(p2, q2, 1.0) * kc, rtol=1e-12)
+    assert (f[:, VOBS_SUM_DN2] == (lat.d1(q2) ** 2).sum(axis=(-3, -2, -1))).all()
+    assert (f[:, VOBS_ACCEPTED] == refs[0][2] + refs[1][2]).all()
+    # the ensemble driver steps big lattices this way
+    if N == 256:
+        S = svb.Villain(svb.Lattice2D(N), kappa)
+        E = svb.BatchedEnsemble(S, chains, chain0=4).generate(K, NeighborhoodUpdate(S, seed=seed), start={'phi': phi0, 'n': n0}, kappa_chain=kc)
+        assert (E.fields[1].cpu().numpy() == n_ref).all() and (E.fields[0].cpu().numpy() == p_ref).all()
+        np.testing.assert_allclose(E.record[:, :K - 1, VOBS_ACTION].T, got[:K - 1, :, VOBS_ACTION], rtol=1e-13)
+        np.testing.assert_allclose(E.record[:, K - 1, VOBS_ACTION], V.action(p_ref, n_ref, 1.0) * kc, rtol=1e-12)
+
+
+def test_config5_full_size_bit_exact_against_c_oracle():
+    """Config 5 at its named size: ONE L = 4096 lattice (16.7 M sites: 8192 tiles of 16 x 128 per colour pass, 32-bit offsets up
+    to 2^24, every kind of edge tile), two sweeps through both entry points that serve it -- svb_villain_sweep_inplace and
+    svb_villain_sweep_tiled_swap -- against the scalar C restatement of neighborhood.py:93-129 with the same Philox draws:
+    phi and n identical, accepted counts identical, action to 1e-12."""
+    from oracle import c_oracle as C
+    N, kappa, seed = 4096, 0.5, 77
+    rng = np.random.default_rng(5)
+    phi0 = rng.uniform(-np.pi, np.pi, (1, 1, N, N))
+    n0 = rng.integers(-2, 3, (1, 2, N, N))
+    p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=2, seed=seed, sweep0=3, chain0=1)
+    assert acc[0] > 100000
+    phi, n = dev(phi0), dev(n0, torch.int32)
+    obs = torch.zeros((1, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    ops.VillainInplaceSweeps(phi, n, kappa, seed=seed, chain0=1).step(3, 2, obs=obs)
+    assert torch.equal(n.cpu(), torch.from_numpy(n_ref).to(torch.int32)) and torch.equal(phi.cpu(), torch.from_numpy(p_ref))
+    rec = obs.cpu().numpy()
+    assert rec[0, VOBS_ACCEPTED] == acc[0]
+    np.testing.assert_allclose(rec[0, VOBS_ACCEPTANCE], accp[0], rtol=1e-5)
+    np.testing.assert_allclose(rec[0, VOBS_ACTION], float(V.action(p_ref, n_ref, kappa)[0]), rtol=1e-12)
+    assert rec[0, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum()
+    assert rec[0, VOBS_WRAP0] == n_ref[0, 0].sum() and rec[0, VOBS_WRAP1] == n_ref[0, 1].sum()
+    # the swapping entry point (one sweep per call, the state may change buffer pairs)
+    sw = ops.VillainSwappingSweeps(dev(phi0), dev(n0, torch.int32), kappa, seed=seed, chain0=1)
+    sw.step(3, 1)
+    f_phi, f_n = sw.step(4, 1)
+    assert torch.equal(f_n, n) and torch.equal(f_phi, phi)
