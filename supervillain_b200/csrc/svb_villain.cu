@@ -1327,6 +1327,9 @@ __global__ void villain_zero_record_kernel(double* obs, long long chains, int ke
 
 // one launch for both records of svb_villain_sweep_inplace: the state columns of `state` (if any), the counters of `counters`
 __global__ void villain_zero_inplace_records_kernel(double* state, double* counters, long long chains) {
+    // (programmatic dependent launch: see launch_pdl in svb_villain_stream.cuh)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < chains) {
         if (state) {
@@ -2263,8 +2266,7 @@ extern "C" int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, 
     int rc = get_device_info(info);
     if (rc) return rc;
     if (obs || obs_in) {    // the state columns of the arriving state are accumulated into obs_in, this launch's counters into obs
-        villain_zero_inplace_records_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(obs_in, obs, chains);
-        SVB_CUDA_TRY(cudaGetLastError());
+        SVB_CUDA_TRY(launch_pdl(villain_zero_inplace_records_kernel, (unsigned)((chains + 255) / 256), 256, 0, st, obs_in, obs, (long long)chains));
     }
     const char* ep = getenv("SVB_VILLAIN_PASS");
     const bool tma = N % kTileCols == 0 && chains * 2 < 0x7fffffffLL && !(ep && ep[0] == 's');

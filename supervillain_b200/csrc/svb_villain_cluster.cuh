@@ -146,6 +146,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
     double* red_count = red_state + 4 * NW;                       // [NW][2]
     double* cta_sums = red_count + 2 * NW;                        // [6]: this CTA's share of the chain's record
     uint64_t* bar = reinterpret_cast<uint64_t*>(cta_sums + 6);
+    // interval_n == 1 (K = 3): the 81 proposals of the four dn as residual changes -(2 pi W) digit, looked up by the code the
+    // multiply by 81 leaves (svb_villain_filtered.cuh); 0, c and 2 c are exact in fp32, so base + lut is the fma it replaces
+    float4* dn_lut = reinterpret_cast<float4*>(bar + 2 * STAGES);
     constexpr int kWriter = 32;
 
     // the neighbouring strips (DSMEM)
@@ -165,6 +168,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (a.grid_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    for (int i = tid; i < 81; i += T)
+        dn_lut[i] = make_float4(-fc.c * (float)(i / 27), -fc.c * (float)((i / 9) % 3), -fc.c * (float)((i / 3) % 3), -fc.c * (float)(i % 3));
     cluster_sync_all();
     const bool obs_of_input = a.obs_in != nullptr;
     const bool want_obs = a.obs != nullptr && !obs_of_input;
@@ -173,6 +178,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
     const int interval_n = MODE == SVB_FILT_SITE ? 0 : a.interval_n;
     const uint32_t K = (MODE == SVB_FILT_EXACT) ? (uint32_t)(2 * interval_n) : (uint32_t)(2 * interval_n + 1);
     const int W = MODE == SVB_FILT_EXACT ? 1 : a.W, mWI = -W * interval_n;
+    const bool lut3 = (MODE == SVB_FILT_FAST || MODE == SVB_FILT_STRICT) && K == 3u;     // block-uniform
     const float cIn = fc.c * (float)interval_n;
     const float2 cIn2 = make_float2(cIn, cIn), negc2 = make_float2(-fc.c, -fc.c), two2 = make_float2(2.0f, 2.0f);
     const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;
@@ -387,7 +393,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     float* r0bA = (p == 0) ? R0b_q0 : R0b;
                     int32_t* n0bA = (p == 0) ? N0b_q0 : N0b;
                     uint32_t fA = bits.y, fB = bits.w;
-                    int digA[4], digB[4];
+                    uint32_t codeA = 0, codeB = 0;
+                    int digA[4] = {0, 0, 0, 0}, digB[4] = {0, 0, 0, 0};
                     if (MODE == SVB_FILT_EXACT) {                 // z from word B; as "digits": I - z forward, I + z backward
                         const uint64_t pa = (uint64_t)fA * K, pb = (uint64_t)fB * K;
                         fA = (uint32_t)pa; fB = (uint32_t)pb;
@@ -399,6 +406,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     } else if (MODE == SVB_FILT_SITE) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) digA[i] = digB[i] = 0;
+                    } else if (lut3) {
+                        // one multiply by 81 = four successive multiply-highs by 3: hi = the code 27 d0 + 9 d1 + 3 d2 + d3, lo = the
+                        // remainder; the digits are decoded only on the rare paths
+                        const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
+                        fA = (uint32_t)pa; fB = (uint32_t)pb;
+                        codeA = (uint32_t)(pa >> 32); codeB = (uint32_t)(pb >> 32);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -414,10 +427,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     const float2 r_f0 = make_float2(R0own[Q * qA], R0own[Q * qB]), r_f1 = make_float2(R1own[Q * qA], R1own[Q * qB]);
                     const float2 r_b0 = make_float2(r0bA[Q * qA], R0b[Q * qB]);
                     const float2 r_b1 = make_float2(R1b[Q * qA], R1b[Q * qB]);
-                    const float2 dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
-                    const float2 dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
-                    const float2 dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
-                    const float2 dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    float2 dr_f0, dr_b0, dr_f1, dr_b1;
+                    if (lut3) {
+                        const float4 tA = dn_lut[codeA], tB = dn_lut[codeB];
+                        dr_f0 = __fadd2_rn(base_f, make_float2(tA.x, tB.x));
+                        dr_b0 = __fadd2_rn(base_b, make_float2(tA.y, tB.y));
+                        dr_f1 = __fadd2_rn(base_f, make_float2(tA.z, tB.z));
+                        dr_b1 = __fadd2_rn(base_b, make_float2(tA.w, tB.w));
+                    } else {
+                        dr_f0 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[0], (float)digB[0]), base_f);
+                        dr_b0 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[1], (float)digB[1]), base_b);
+                        dr_f1 = MODE == SVB_FILT_SITE ? base_f : __ffma2_rn(negc2, make_float2((float)digA[2], (float)digB[2]), base_f);
+                        dr_b1 = MODE == SVB_FILT_SITE ? base_b : __ffma2_rn(negc2, make_float2((float)digA[3], (float)digB[3]), base_b);
+                    }
                     float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
                     acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
                     acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
@@ -432,14 +454,27 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                     sum_A += fminf(fast_ex2(-dS2.x), 1.0f) + fminf(fast_ex2(-dS2.y), 1.0f);
                     const float2 n_f0 = __fadd2_rn(r_f0, dr_f0), n_b0 = __fadd2_rn(r_b0, dr_b0);
                     const float2 n_f1 = __fadd2_rn(r_f1, dr_f1), n_b1 = __fadd2_rn(r_b1, dr_b1);
+                    // certainly rejected (the overwhelming majority): nothing more to do; everything else behind ONE branch per pair
+                    const bool candA = !(diff.x > band.x) || fA < 65536u, candB = !(diff.y > band.y) || fB < 65536u;
+                    if (candA || candB) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (!(h ? candB : candA)) continue;
                         const int q = 2 * p + h;
                         float* r0b_site = (h ? R0b : r0bA) + Q * q;                   // q == 0 of row 0: in the previous strip
                         int32_t* n0b_site = (h ? N0b : n0bA) + 2 * Q * q;
                         const uint32_t wA = h ? bits.z : bits.x;
                         const uint32_t f = h ? fB : fA;
-                        const int* dig = h ? digB : digA;
+                        int dig[4];
+                        if (lut3) {
+                            uint32_t code = h ? codeB : codeA;
+                            dig[0] = (int)((code * 2428u) >> 16); code -= 27u * (uint32_t)dig[0];
+                            dig[1] = (int)((code * 7282u) >> 16); code -= 9u * (uint32_t)dig[1];
+                            dig[2] = (int)((code * 21846u) >> 16); dig[3] = (int)(code - 3u * (uint32_t)dig[2]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dig[i] = h ? digB[i] : digA[i];
+                        }
                         const float dif = h ? diff.y : diff.x, bnd = h ? band.y : band.x;
                         bool ok = dif < 0.0f;
                         if (SPARSE && (!(fabsf(dif) > bnd) || f < 65536u)) {
@@ -514,6 +549,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TPB, cluster_min_bl
                             R1own[Q * q] = h ? n_f1.y : n_f1.x;
                             R1b[Q * q] = h ? n_b1.y : n_b1.x;
                         }
+                    }
                     }
                 }
                 if (s == a.n_sweeps - 1 && c == 1) {
@@ -593,7 +629,8 @@ static int launch_villain_cluster(const VillainArgs& a, cudaStream_t stream, con
                 : overlap ? villain_cluster_kernel<NT, CL, TPB, STAGES, true, SVB_FILT_FAST>
                           : villain_cluster_kernel<NT, CL, TPB, STAGES, false, SVB_FILT_FAST>;
     constexpr int ROWS = NT / CL, VL = ROWS * NT, VHL = ROWS * NT / 2, NW = TPB / 32;
-    const size_t smem = (size_t)STAGES * VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16 * STAGES;
+    const size_t smem = (size_t)STAGES * VL * 16 + (size_t)4 * VHL * sizeof(float) + (size_t)(6 * NW + 6) * sizeof(double) + 16 * STAGES +
+                        81 * sizeof(float4);
     static int clusters_cache[7][64];
     const int variant = mode != SVB_FILT_FAST ? 1 + mode : sparse ? 5 + (overlap ? 1 : 0) : (overlap ? 1 : 0);
     int clusters = (info.device < 64) ? clusters_cache[variant][info.device] : 0;

@@ -32,6 +32,24 @@
 #pragma once
 // (included inside namespace svb, after svb_villain_filtered.cuh)
 
+// Programmatic dependent launch for the kernels of an in-place step (records -> sum dn^2 -> colour 0 -> colour 1): every kernel
+// lets its successor's CTAs be scheduled as soon as its own are resident (pdl_prologue) and waits for its predecessors to have
+// completed before it touches memory, so the launch latency and ramp-up of one kernel hide under the tail of the one before.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // A thread's column slot: constant while it walks down the rows.
 struct StreamCol {
     int k2;          // 2 k: the aligned column pair [2k, 2k + 1] of every row holds the site and one in-row neighbour
@@ -115,23 +133,20 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
                                                    int oAm, int oAp, int oB, int oBm, int oBp, int x1, int xm1, int xp1, const Philox4& bits,
                                                    uint32_t c0, const float4& rA, const float4& rB, unsigned long long gc,
                                                    unsigned long long gs, double half_kappa, float hk2, float hkA, float hkB, int& n_acc,
-                                                   float& sum_A) {
+                                                   float& sum_A, const float4* dn_lut) {
     const int interval_n = UNIT ? 1 : a.interval_n;
     const uint32_t K = (uint32_t)(2 * interval_n + 1);
     const int W = UNIT ? 1 : a.W;
     // proposals: four base-K digits each, then the leading 32 bits of the uniform (svb_villain_filtered.cuh)
     uint32_t fA = bits.y, fB = bits.w;
-    int a0, a1, a2, a3, b0, b1, b2, b3;
+    uint32_t codeA = 0, codeB = 0;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
     if (UNIT) {
+        // one multiply by 81: hi = 27 d0 + 9 d1 + 3 d2 + d3 (the code, which looks the four residual changes up in dn_lut), lo = the
+        // remainder that leads the uniform; the digits themselves are decoded only on the rare paths
         const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
         fA = (uint32_t)pa; fB = (uint32_t)pb;
-        uint32_t ia = (uint32_t)(pa >> 32), ib = (uint32_t)(pb >> 32);
-        a0 = (int)((ia * 2428u) >> 16); ia -= 27u * (uint32_t)a0;
-        b0 = (int)((ib * 2428u) >> 16); ib -= 27u * (uint32_t)b0;
-        a1 = (int)((ia * 7282u) >> 16); ia -= 9u * (uint32_t)a1;
-        b1 = (int)((ib * 7282u) >> 16); ib -= 9u * (uint32_t)b1;
-        a2 = (int)((ia * 21846u) >> 16); a3 = (int)(ia - 3u * (uint32_t)a2);
-        b2 = (int)((ib * 21846u) >> 16); b3 = (int)(ib - 3u * (uint32_t)b2);
+        codeA = (uint32_t)(pa >> 32); codeB = (uint32_t)(pb >> 32);
     } else {
         uint64_t pa, pb;
         pa = (uint64_t)fA * K; fA = (uint32_t)pa; a0 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b0 = (int)(pb >> 32);
@@ -149,10 +164,19 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
     const float2 r_f0 = make_float2(rA.x, rB.x), r_b0 = make_float2(rA.y, rB.y);
     const float2 r_f1 = make_float2(rA.z, rB.z), r_b1 = make_float2(rA.w, rB.w);
     // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
-    const float2 dr_f0 = __ffma2_rn(negc2, make_float2((float)a0, (float)b0), base_f);
-    const float2 dr_b0 = __ffma2_rn(negc2, make_float2((float)a1, (float)b1), base_b);
-    const float2 dr_f1 = __ffma2_rn(negc2, make_float2((float)a2, (float)b2), base_f);
-    const float2 dr_b1 = __ffma2_rn(negc2, make_float2((float)a3, (float)b3), base_b);
+    float2 dr_f0, dr_b0, dr_f1, dr_b1;
+    if (UNIT) {
+        const float4 tA = dn_lut[codeA], tB = dn_lut[codeB];          // -2 pi digit: exact in fp32, so the add is the fma below
+        dr_f0 = __fadd2_rn(base_f, make_float2(tA.x, tB.x));
+        dr_b0 = __fadd2_rn(base_b, make_float2(tA.y, tB.y));
+        dr_f1 = __fadd2_rn(base_f, make_float2(tA.z, tB.z));
+        dr_b1 = __fadd2_rn(base_b, make_float2(tA.w, tB.w));
+    } else {
+        dr_f0 = __ffma2_rn(negc2, make_float2((float)a0, (float)b0), base_f);
+        dr_b0 = __ffma2_rn(negc2, make_float2((float)a1, (float)b1), base_b);
+        dr_f1 = __ffma2_rn(negc2, make_float2((float)a2, (float)b2), base_f);
+        dr_b1 = __ffma2_rn(negc2, make_float2((float)a3, (float)b3), base_b);
+    }
     float2 acc2 = __fmul2_rn(dr_f0, __ffma2_rn(two2, r_f0, dr_f0));
     acc2 = __ffma2_rn(dr_b0, __ffma2_rn(two2, r_b0, dr_b0), acc2);
     acc2 = __ffma2_rn(dr_f1, __ffma2_rn(two2, r_f1, dr_f1), acc2);
@@ -166,19 +190,45 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
     const float2 band = __ffma2_rn(make_float2(hkA, hkA), Rmax, __ffma2_rn(make_float2(4e-6f, 4e-6f), L2, make_float2(hkB, hkB)));
     const float2 diff = __ffma2_rn(L2, make_float2(-1.0f, -1.0f), dS2);
     sum_A += fminf(fast_ex2(-dS2.x), 1.0f) + fminf(fast_ex2(-dS2.y), 1.0f);
-    // certainly rejected (the overwhelming majority): nothing more to do
-    const int mWI = -W * interval_n;
-    const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
-    bool okA = diff.x < 0.0f, okB = diff.y < 0.0f;
-    if (!(fabsf(diff.x) > band.x) || fA < 65536u)
-        okA = stream_exact(a, gphi, gn0, V, oA, oAm, oAp, x1, xm1, xp1, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n, a2 - interval_n,
-                           a3 - interval_n, W, half_kappa, gc, gs);
-    if (!(fabsf(diff.y) > band.y) || fB < 65536u)
-        okB = stream_exact(a, gphi, gn0, V, oB, oBm, oBp, x1, xm1, xp1, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n, b2 - interval_n,
-                           b3 - interval_n, W, half_kappa, gc, gs);
-    n_acc += (okA ? 1 : 0) + (okB ? 1 : 0);
-    if (okA) stream_accept(gphi, gn0, V, oA, oAm, x1, xm1, bits.x, a.interval_phi, two_I_scaled, W * a0 + mWI, W * a1 + mWI, W * a2 + mWI, W * a3 + mWI);
-    if (okB) stream_accept(gphi, gn0, V, oB, oBm, x1, xm1, bits.z, a.interval_phi, two_I_scaled, W * b0 + mWI, W * b1 + mWI, W * b2 + mWI, W * b3 + mWI);
+    // certainly rejected (the overwhelming majority): nothing more to do.  Everything else -- accepted, or inside the error band of
+    // the fp32 comparison -- is handled behind ONE branch per pair of sites.
+    const bool candA = !(diff.x > band.x) || fA < 65536u, candB = !(diff.y > band.y) || fB < 65536u;
+    if (candA || candB) {
+        const int mWI = -W * interval_n;
+        const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
+        if (UNIT) {
+            uint32_t c = codeA;
+            a0 = (int)((c * 2428u) >> 16); c -= 27u * (uint32_t)a0;
+            a1 = (int)((c * 7282u) >> 16); c -= 9u * (uint32_t)a1;
+            a2 = (int)((c * 21846u) >> 16); a3 = (int)(c - 3u * (uint32_t)a2);
+            c = codeB;
+            b0 = (int)((c * 2428u) >> 16); c -= 27u * (uint32_t)b0;
+            b1 = (int)((c * 7282u) >> 16); c -= 9u * (uint32_t)b1;
+            b2 = (int)((c * 21846u) >> 16); b3 = (int)(c - 3u * (uint32_t)b2);
+        }
+        if (candA) {
+            bool ok = diff.x < 0.0f;
+            if (!(fabsf(diff.x) > band.x) || fA < 65536u)
+                ok = stream_exact(a, gphi, gn0, V, oA, oAm, oAp, x1, xm1, xp1, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n,
+                                  a2 - interval_n, a3 - interval_n, W, half_kappa, gc, gs);
+            if (ok) {
+                n_acc += 1;
+                stream_accept(gphi, gn0, V, oA, oAm, x1, xm1, bits.x, a.interval_phi, two_I_scaled, W * a0 + mWI, W * a1 + mWI, W * a2 + mWI,
+                              W * a3 + mWI);
+            }
+        }
+        if (candB) {
+            bool ok = diff.y < 0.0f;
+            if (!(fabsf(diff.y) > band.y) || fB < 65536u)
+                ok = stream_exact(a, gphi, gn0, V, oB, oBm, oBp, x1, xm1, xp1, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n,
+                                  b2 - interval_n, b3 - interval_n, W, half_kappa, gc, gs);
+            if (ok) {
+                n_acc += 1;
+                stream_accept(gphi, gn0, V, oB, oBm, x1, xm1, bits.z, a.interval_phi, two_I_scaled, W * b0 + mWI, W * b1 + mWI, W * b2 + mWI,
+                              W * b3 + mWI);
+            }
+        }
+    }
 }
 
 // One colour pass over the pair of sites at row offsets oA and oB = oA + 8 N of the column slot `col`, straight from global memory.
@@ -186,14 +236,21 @@ template <bool UNIT, bool SUMS>
 __device__ __forceinline__ void stream_pair(const VillainArgs& a, const FilterConsts& fc, double* gphi, int32_t* gn0, int V, int oA,
                                             int oAm, int oAp, int oB, int oBm, int oBp, const StreamCol& col, unsigned long long gc,
                                             unsigned long long gs, double half_kappa, float hk2, float hkA, float hkB, int& n_acc,
-                                            float& sum_A, double& action, int& w0, int& w1) {
+                                            float& sum_A, double& action, int& w0, int& w1, const float4* dn_lut) {
     // the Philox block does not depend on memory: issue it first so that it overlaps the loads
     const uint32_t c0 = (uint32_t)(oA + col.x1);                          // villain_pair_counter: (x0 & ~8) N + x1
     const Philox4 bits = philox_site_keys(a, gc, gs, c0);
     const float4 rA = stream_site_residuals<SUMS>(gphi, gn0, gn0 + V, oA, oAm, oAp, col, action, w0, w1);
     const float4 rB = stream_site_residuals<SUMS>(gphi, gn0, gn0 + V, oB, oBm, oBp, col, action, w0, w1);
     stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oAp, oB, oBm, oBp, col.x1, col.xm1, col.xp1, bits, c0, rA, rB, gc, gs, half_kappa,
-                             hk2, hkA, hkB, n_acc, sum_A);
+                             hk2, hkA, hkB, n_acc, sum_A, dn_lut);
+}
+
+// The 81 proposals of (dn_f0, dn_b0, dn_f1, dn_b1) at interval_n = 1 as the residual changes they make, -2 pi W digit (exact in
+// fp32 for digits 0, 1, 2), indexed by the code 27 d0 + 9 d1 + 3 d2 + d3 (svb_villain_filtered.cuh).  Call before a block barrier.
+__device__ __forceinline__ void stream_fill_lut(float4* dn_lut, float c, int tid, int threads) {
+    for (int i = tid; i < 81; i += threads)
+        dn_lut[i] = make_float4(-c * (float)(i / 27), -c * (float)((i / 9) % 3), -c * (float)((i / 3) % 3), -c * (float)(i % 3));
 }
 
 // sum (dn)^2 of the plaquettes at the four sites (r, 2k), (r, 2k + 1), (r + 8, 2k), (r + 8, 2k + 1); reads n only.  Must not run
@@ -254,9 +311,11 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_stream_chain_kernel(cons
     static_assert(N % 16 == 0, "villain_stream_chain_kernel: unsupported geometry");
     __shared__ double red_state[4 * NW];
     __shared__ double red_count[2 * NW];
+    __shared__ float4 dn_lut[81];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWriter = (NW > 1) ? 32 : 0;
     const int w8 = tid / HN, k = tid - w8 * HN;
+    if (UNIT) stream_fill_lut(dn_lut, fc.c, tid, THREADS);          // (the barrier below orders it)
 
     if (OVERLAP) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -324,10 +383,10 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_stream_chain_kernel(cons
                     const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
                     if (c == 0 && sums)
                         stream_pair<UNIT, true>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB,
-                                                n_acc, sum_A, action, w0, w1);
+                                                n_acc, sum_A, action, w0, w1, dn_lut);
                     else
                         stream_pair<UNIT, false>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB,
-                                                 n_acc, sum_A, action, w0, w1);
+                                                 n_acc, sum_A, action, w0, w1, dn_lut);
                 }
                 if (c == 0 && sums) chain_partials<true, false>(red_state, red_count, lane, warp, action, dn2, w0, w1, 0.0, 0);
                 const bool last = (sw == a.n_sweeps - 1) && c == 1;
@@ -417,8 +476,14 @@ __global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __gri
                                                                      int colour, int sweep, int bands, int runs, int run,
                                                                      double* __restrict__ state_out, double* __restrict__ counter_out) {
     __shared__ double scratch[5 * 32];
+    __shared__ float4 dn_lut[81];
     const int N = a.N, V = N * N, groups = N / 16;
     const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+    if (UNIT) {
+        stream_fill_lut(dn_lut, fc.c, tid, 256);
+        __syncthreads();
+    }
+    pdl_prologue();
     // blockIdx.x = (chain * runs + run index) * bands + band: neighbouring CTAs work on neighbouring bands of the same rows
     const unsigned per_chain = (unsigned)(bands * runs);
     const long long chain = blockIdx.x / per_chain;
@@ -445,10 +510,10 @@ __global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __gri
             const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
             if (sums)
                 stream_pair<UNIT, true>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB, n_acc,
-                                        sum_A, action, w0, w1);
+                                        sum_A, action, w0, w1, dn_lut);
             else
                 stream_pair<UNIT, false>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, col, gc, gs, half_kappa, hk2, hkA, hkB, n_acc,
-                                         sum_A, action, w0, w1);
+                                         sum_A, action, w0, w1, dn_lut);
         }
     }
     if (sums || counter_out) {
@@ -476,6 +541,7 @@ __global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __gri
 __global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* __restrict__ n, long long chains, int N, int bands,
                                                                  int runs, int rows, double* __restrict__ state_out) {
     const int tid = threadIdx.x, lane = tid & 31;
+    pdl_prologue();
     const long long w = (long long)blockIdx.x * 8 + (tid >> 5);                  // global warp index = (chain, run, band)
     const long long per_chain = (long long)bands * runs;
     if (w >= chains * per_chain) return;
@@ -535,8 +601,7 @@ static int launch_villain_stream_dn2(const int32_t* n, long long chains, int N, 
     while (rows > 16 && chains * bands * ((N + rows - 1) / rows) < 4LL * 64 * info.sm_count) rows = (rows + 1) / 2;
     const int runs = (N + rows - 1) / rows;
     const long long warps = chains * bands * runs;
-    villain_stream_dn2_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(n, chains, N, bands, runs, rows, state_out);
-    SVB_CUDA_TRY(cudaGetLastError());
+    SVB_CUDA_TRY(launch_pdl(villain_stream_dn2_kernel, (unsigned)((warps + 7) / 8), 256, 0, stream, n, chains, N, bands, runs, rows, state_out));
     return 0;
 }
 
@@ -564,8 +629,8 @@ static int launch_villain_stream_passes(const VillainArgs& a, double* obs_in, do
     }
     for (int sw = 0; sw < a.n_sweeps; ++sw)
         for (int c = 0; c < 2; ++c) {
-            kern<<<(unsigned)grid, 256, 0, stream>>>(a, fc, c, sw, bands, runs, run, (sw == 0 && c == 0) ? obs_in : nullptr, counters);
-            SVB_CUDA_TRY(cudaGetLastError());
+            SVB_CUDA_TRY(launch_pdl(kern, (unsigned)grid, 256, 0, stream, a, fc, c, sw, bands, runs, run, (sw == 0 && c == 0) ? obs_in : nullptr,
+                                    counters));
         }
     return 0;
 }
@@ -686,8 +751,9 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap map_n, int colour, int sweep,
                                                                    double* __restrict__ state_out, double* __restrict__ counter_out) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ double scratch[5 * 32];
+    __shared__ double scratch[8 * 5];         // per-warp partial sums of the records (shared memory is what limits this kernel to 3 CTAs per SM)
     __shared__ int tile_coord[2][4];          // per stage: chain, R, C of the tile that was loaded into it (written by thread 0)
+    __shared__ float4 dn_lut[81];
     const int N = a.N, V = N * N;
     const int tiles_x = N / kTileCols, tiles_y = N / kTileRows, tiles_per_chain = tiles_x * tiles_y;
     const long long tiles = (long long)tiles_per_chain * a.chains;
@@ -702,7 +768,9 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
         mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
+    if (UNIT) stream_fill_lut(dn_lut, fc.c, tid, 256);
     __syncthreads();
+    pdl_prologue();
     auto issue = [&](long long t, int stage) {
         const long long chain = t / tiles_per_chain;
         const int tile = (int)(t - chain * tiles_per_chain);
@@ -728,8 +796,19 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
     long long chain_of_sums = -1;
     auto flush = [&](long long chain) {
         double v[5] = {action, (double)w0, (double)w1, (double)n_acc, (double)sum_A};
-        block_sum<5>(v, scratch);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = warp_sum(v[i]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) scratch[5 * w8 + i] = v[i];
+        }
+        __syncthreads();
         if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                v[i] = 0.0;
+                for (int w = 0; w < 8; ++w) v[i] += scratch[5 * w + i];
+            }
             if (sums) {
                 double* o = state_out + chain * SVB_VOBS_COUNT;
                 atomicAdd(o + SVB_VOBS_ACTION, half_kappa * v[0]);
@@ -801,7 +880,7 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
                 rB = tile_site_residuals<false>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
             }
             stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc, gs, half_kappa,
-                                     hk2, hkA, hkB, n_acc, sum_A);
+                                     hk2, hkA, hkB, n_acc, sum_A, dn_lut);
         }
         __syncthreads();                                           // every thread has read the stage (and its coordinates): refill it
         const long long t2 = t + 2LL * gridDim.x;
@@ -870,8 +949,8 @@ static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, doub
     }
     for (int sw = 0; sw < a.n_sweeps; ++sw)
         for (int c = 0; c < 2; ++c) {
-            kern<<<(unsigned)grid, 256, kTileSmemBytes, stream>>>(a, fc, map_phi, map_n, c, sw, (sw == 0 && c == 0) ? obs_in : nullptr, counters);
-            SVB_CUDA_TRY(cudaGetLastError());
+            SVB_CUDA_TRY(launch_pdl(kern, (unsigned)grid, 256, (size_t)kTileSmemBytes, stream, a, fc, map_phi, map_n, c, sw,
+                                    (sw == 0 && c == 0) ? obs_in : nullptr, counters));
         }
     return 0;
 }
