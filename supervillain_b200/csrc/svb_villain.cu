@@ -2276,3 +2276,12 @@ extern "C" int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, 
         return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
     return SVB_OK;
 }
+
+#ifdef SVB_TRACE
+// Evidence build only: copy the CTA time stamps of the overlapped launches to the host (launches x ctas x {start, end} u64).
+extern "C" int svb_debug_trace_read(unsigned long long* out_host, int* launches, int* ctas) {
+    *launches = svb::kTraceLaunches; *ctas = svb::kTraceCtas;
+    if (out_host) SVB_CUDA_TRY(cudaMemcpyFromSymbol(out_host, svb::g_svb_trace, sizeof(unsigned long long) * svb::kTraceLaunches * svb::kTraceCtas * 2));
+    return 0;
+}
+#endif

@@ -201,6 +201,17 @@ __device__ __forceinline__ void chain_finish(const double* red_state, const doub
 //                           proposals, site.py:43-120);
 //       SVB_FILT_EXACT      ExactUpdate (exact.py:50-129): dphi = 0, dn = d z with z one of the 2 a.interval_n nonzero values
 //                           drawn from word B (villain_get_draw), STRICT cold path.
+#ifdef SVB_TRACE
+// Evidence build only (tools/overlap_trace.py, -DSVB_TRACE): every CTA of an overlapped launch records %globaltimer when it starts
+// and when it has published its chains, indexed by the launch's signal epoch.  Not part of the product library.
+constexpr int kTraceLaunches = 128, kTraceCtas = 1536;
+__device__ unsigned long long g_svb_trace[kTraceLaunches][kTraceCtas][2];
+__device__ __forceinline__ unsigned long long svb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 #define SVB_FILT_FAST 0
 #define SVB_FILT_STRICT 1
 #define SVB_FILT_EXACT 2
@@ -224,6 +235,9 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
     constexpr uint32_t bytes_n = 2 * V * sizeof(int32_t);
     constexpr uint32_t stage_bytes = bytes_phi + bytes_n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SVB_TRACE
+    if (OVERLAP && tid == 0 && blockIdx.x < kTraceCtas) g_svb_trace[a.signal_epoch % kTraceLaunches][blockIdx.x][0] = svb_globaltimer();
+#endif
     float* rc0 = reinterpret_cast<float*>(smem_raw + STAGES * stage_bytes);      // [colour][VH]: residual of link (0, x)
     float* rc1 = rc0 + V;                                                         // [colour][VH]: residual of link (1, x)
     double* red_state = reinterpret_cast<double*>(rc1 + V);                       // [NW][4] per-warp partial sums
@@ -633,6 +647,9 @@ __global__ void __launch_bounds__(4 * NT, MINB) villain_smem_filtered_kernel(con
         __syncthreads();                                   // every store has completed, every record is written
         if (warp == 0) publish_all(it);
     }
+#ifdef SVB_TRACE
+    if (OVERLAP && tid == 0 && blockIdx.x < kTraceCtas) g_svb_trace[a.signal_epoch % kTraceLaunches][blockIdx.x][1] = svb_globaltimer();
+#endif
 }
 
 template <int NT, int MINB, int STAGES>

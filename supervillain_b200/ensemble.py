@@ -158,12 +158,16 @@ class BatchedEnsemble:
 
     # -- generation ----------------------------------------------------------------------------
     def generate(self, steps, generator, start='cold', *, sweeps_per_step=1, keep_every=0, start_seed=0,
-                 kappa_chain=None, progress=_no_op):
+                 kappa_chain=None, progress=_no_op, correlate_every=0, correlators=None):
         """Advance every chain `steps` times by `sweeps_per_step` sweeps.
 
         keep_every: 0 keeps no configurations (observables only); k > 0 copies the fields to the host
         every k-th step into reference-layout columns `(chain, draw, C, N, N)`.
         kappa_chain: optional per-chain couplings (kappa scans), device or host array of length `chains`.
+        correlate_every: k > 0 measures the two-point observables `correlators` (default: every one the formulation has on
+        the FFT path -- Villain: Spin_Spin, Winding_Winding; Worldline: Vortex_Vortex) INLINE on every k-th step: the kernels
+        run on the resident fields and write into device columns `self.two_point[name]` of shape (draws, chains, N, N)
+        complex128; nothing crosses to the host until the column is asked for (`E.Spin_Spin` -> (chains, draws, N, N) numpy).
         """
         if self.fields is None or start != 'continue':
             self.fields = self._start(start, start_seed)
@@ -176,6 +180,23 @@ class BatchedEnsemble:
         record = torch.empty((steps, self.chains, nobs), dtype=torch.float64, device=self.device)
         kept = []
         a, b = self.fields
+        two_point_fns = {}
+        if correlate_every:
+            N_ = self.Action.Lattice.N
+            if self.kind == 'Villain':
+                available = {'Spin_Spin': lambda phi, n, out: ops.villain_spin_spin(phi, out=out),
+                             'Winding_Winding': lambda phi, n, out: ops.correlation('winding', n, out=out)}
+            else:
+                W_ = self.Action.W
+                available = {'Vortex_Vortex': lambda m, v, out: ops.correlation('vortex', v, W=W_, out=out)}
+            for name in (tuple(available) if correlators is None else tuple(correlators)):
+                if name not in available:
+                    raise NotImplementedError(f'{name} is not an inline two-point observable of the {self.kind} formulation')
+                two_point_fns[name] = available[name]
+            draws_2pt = steps // int(correlate_every)
+            self.two_point = {name: torch.empty((draws_2pt, self.chains, N_, N_, 2), dtype=torch.float64, device=self.device)
+                              for name in two_point_fns}
+            self.correlate_every = int(correlate_every)
         overlapped = None
         if hasattr(generator, 'overlapped_device'):
             try:          # launches that overlap their predecessor; each step writes its own row of the record
@@ -202,6 +223,11 @@ class BatchedEnsemble:
                 generator.sweep_device(a, b, sweeps_per_step, obs=record[k], chain0=self.chain0, kappa_chain=kappa_chain)
             if keep_every and (k + 1) % keep_every == 0:
                 kept.append((a.cpu().numpy(), b.cpu().numpy()))          # reads only: stream order suffices
+            if two_point_fns and (k + 1) % correlate_every == 0:
+                # ordinary launches that only READ the fields: they wait for the sweep by stream order, and the next sweep launch
+                # (also an overlapped one: its predecessor in the stream is now this kernel) waits for them
+                for name, fn in two_point_fns.items():
+                    fn(a, b, self.two_point[name][(k + 1) // correlate_every - 1])
         if overlapped is not None and steps and not getattr(overlapped, 'complete_records', False):
             last = ops.villain_observables(a, b, self.Action.kappa, kappa_chain=kappa_chain)     # the final state's columns
             record[steps - 1, :, :4] = last[:, :4]
@@ -352,6 +378,9 @@ class BatchedEnsemble:
         obs = self.__dict__.get('observables')
         if obs is not None and name in obs:
             return obs[name]
+        two = self.__dict__.get('two_point')
+        if two is not None and name in two:             # (draws, chains, N, N, 2) on the device -> (chains, draws, N, N) complex
+            return torch.view_as_complex(two[name]).cpu().numpy().transpose(1, 0, 2, 3)
         raise AttributeError(name)
 
     def measure(self, name):

@@ -12,7 +12,11 @@ from . import _replay
 from .generator import Generator, fresh_seed
 
 INLINE_NAMES = ('ActionDensity', 'InternalEnergyDensity', 'InternalEnergyDensitySquared', 'WindingSquared',
-                'TorusWrapping', 'WrappingSquared')
+                'TorusWrapping', 'WrappingSquared', 'Spin_Spin', 'Winding_Winding')
+# the two-point observables among them: (N, N) complex per draw, evaluated on the device from the fields the sweep has just left
+# there (observable/spin.py:28-42, observable/winding.py:77-86 via Lattice.correlation, compact.py:465-536)
+TWO_POINT = {'Spin_Spin': lambda phi, n: ops.villain_spin_spin(phi),
+             'Winding_Winding': lambda phi, n: ops.correlation('winding', n)}
 
 
 def _is_villain(action):
@@ -184,12 +188,18 @@ class NeighborhoodUpdate(Generator):
         if self.inline:
             vals = villain_inline_values(rec, N, self.kappa)
             for name in self.inline:
-                result[name] = vals[name][0] if single else vals[name]
+                if name in TWO_POINT:
+                    # measured where the configuration is: only the (N, N) correlator crosses to the host
+                    v = TWO_POINT[name](phi if phi.dtype == torch.float64 else phi.to(torch.float64), n).cpu().numpy()
+                else:
+                    v = vals[name]
+                result[name] = v[0] if single else v
         return cfg | result
 
     def inline_observables(self, steps):
-        shapes = {'TorusWrapping': (2,)}
-        dtypes = {'TorusWrapping': int}
+        N = self.Lattice.N
+        shapes = {'TorusWrapping': (2,), 'Spin_Spin': (N, N), 'Winding_Winding': (N, N)}
+        dtypes = {'TorusWrapping': int, 'Spin_Spin': complex, 'Winding_Winding': complex}
         return {name: Batch(steps, shape=shapes.get(name, ()), dtype=dtypes.get(name, float)) for name in self.inline}
 
     def report(self):

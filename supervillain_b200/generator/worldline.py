@@ -22,7 +22,10 @@ from . import _replay
 from .generator import Generator, fresh_seed
 
 INLINE_NAMES = ('ActionDensity', 'InternalEnergyDensity', 'InternalEnergyDensitySquared', 'WindingSquared',
-                'TorusWrapping', 'WrappingSquared')
+                'TorusWrapping', 'WrappingSquared', 'Vortex_Vortex')
+# the two-point observable among them: (N, N) complex per draw, evaluated on the device from the v the sweep has just left there
+# (observable/vortex.py:22-37 via Lattice.correlation, compact.py:465-536)
+TWO_POINT = ('Vortex_Vortex',)
 
 
 def _is_worldline(action):
@@ -145,12 +148,18 @@ class _CheckerboardWorldline(Generator):
         if self.inline:
             vals = worldline_inline_values(rec, N, self.kappa)
             for name in self.inline:
-                result[name] = vals[name][0] if single else vals[name]
+                if name in TWO_POINT:
+                    val = ops.correlation('vortex', v, W=self.Action.W).cpu().numpy()
+                else:
+                    val = vals[name]
+                result[name] = val[0] if single else val
         return cfg | result
 
     def inline_observables(self, steps):
-        shapes = {'TorusWrapping': (2,)}
-        return {name: Batch(steps, shape=shapes.get(name, ()), dtype=float) for name in self.inline}
+        N = self.Lattice.N
+        shapes = {'TorusWrapping': (2,), 'Vortex_Vortex': (N, N)}
+        dtypes = {'Vortex_Vortex': complex}
+        return {name: Batch(steps, shape=shapes.get(name, ()), dtype=dtypes.get(name, float)) for name in self.inline}
 
     def report(self):
         return (

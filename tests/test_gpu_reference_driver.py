@@ -130,3 +130,60 @@ def test_to_reference_round_trips_through_hdf5_in_the_reference_layout(tmp_path)
         assert (arr(back.configuration.fields[k]) == arr(R.configuration.fields[k])).all()
     assert (arr(back.index) == arr(R.index)).all() and back.index_stride == R.index_stride
     assert np.allclose(arr(back.ActionDensity), arr(R.ActionDensity), rtol=0, atol=0)
+
+
+def test_inline_two_point_observables_short_circuit_the_reference_measurement():
+    """inline=('Spin_Spin', 'Winding_Winding') / ('Vortex_Vortex',): the generators return the correlators of the configuration
+    they have just produced, computed on the device (FFT kernels), under the reference's observable names -- so the reference
+    reads the stored column instead of measuring (observable/observable.py:49-54).  Measured afresh by the reference from the
+    stored fields (observable/spin.py:28-42, winding.py:77-86, vortex.py:22-37 via Lattice.correlation) they agree to 1e-12."""
+    N, kappa, steps = 16, 0.5, 12
+    S = sv.action.Villain(sv.lattice.Lattice2D(N), kappa, 1)
+    G = NeighborhoodUpdate(S, seed=11, inline=('Spin_Spin', 'Winding_Winding', 'ActionDensity'))
+    rng = np.random.default_rng(3)
+    hot = {'phi': S.Lattice.form(0), 'n': S.Lattice.form(1, dtype=int)}
+    hot['phi'][...] = rng.uniform(-np.pi, np.pi, hot['phi'].shape)
+    hot['n'][...] = rng.integers(-2, 3, hot['n'].shape)
+    E = sv.Ensemble(S).generate(steps, G, start=hot)
+    bare = sv.Ensemble(S).from_configurations(sv.configurations.Configurations({k: E.configuration.fields[k] for k in ('phi', 'n')}))
+    for name in ('Spin_Spin', 'Winding_Winding'):
+        inline, measured = arr(getattr(E, name)), arr(getattr(bare, name))
+        assert inline.shape == measured.shape == (steps, N, N) and np.iscomplexobj(inline), name
+        assert np.abs(inline - measured).max() <= 1e-12 * max(1.0, np.abs(measured).max()), name
+    Wl = sv.action.Worldline(sv.lattice.Lattice2D(N), kappa, 1)
+    P = PlaquetteUpdate(Wl, seed=12, inline=('Vortex_Vortex',))
+    F = sv.Ensemble(Wl).generate(steps, P, start='cold')
+    bare = sv.Ensemble(Wl).from_configurations(sv.configurations.Configurations({k: F.configuration.fields[k] for k in ('m', 'v')}))
+    inline, measured = arr(F.Vortex_Vortex), arr(bare.Vortex_Vortex)
+    assert inline.shape == measured.shape == (steps, N, N)
+    assert np.abs(inline - measured).max() <= 1e-12 * max(1.0, np.abs(measured).max())
+
+
+def test_batched_ensemble_measures_two_point_observables_on_the_resident_fields():
+    """BatchedEnsemble.generate(..., correlate_every=k): the FFT kernels run on the resident fields every k-th step into device
+    columns (no configuration crosses to the host); the columns equal the correlators of the kept configurations."""
+    import torch
+    from supervillain_b200 import ops
+    N, kappa, chains, steps, k = 32, 0.5, 6, 9, 3
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    E = svb.BatchedEnsemble(S, chains).generate(steps, NeighborhoodUpdate(S, seed=21), start='hot', start_seed=4, keep_every=k,
+                                                correlate_every=k)
+    assert set(E.two_point) == {'Spin_Spin', 'Winding_Winding'} and E.two_point['Spin_Spin'].is_cuda
+    assert E.Spin_Spin.shape == (chains, steps // k, N, N) and np.iscomplexobj(E.Spin_Spin)
+    for t in range(steps // k):
+        phi = torch.from_numpy(E.configuration['phi'][:, t]).cuda()
+        n = torch.from_numpy(E.configuration['n'][:, t]).to(device='cuda', dtype=torch.int32)
+        assert np.array_equal(E.Spin_Spin[:, t], ops.villain_spin_spin(phi).cpu().numpy())
+        assert np.array_equal(E.Winding_Winding[:, t], ops.correlation('winding', n).cpu().numpy())
+    assert abs(E.Spin_Spin[:, :, 0, 0] - 1.0).max() < 1e-12                       # C[0] = 1
+    # one big lattice (the in-place colour passes), one correlator
+    S2 = svb.Villain(svb.Lattice2D(256), kappa)
+    E2 = svb.BatchedEnsemble(S2, 1).generate(4, NeighborhoodUpdate(S2, seed=22), start='hot', start_seed=5, correlate_every=2,
+                                             correlators=('Spin_Spin',))
+    assert E2.Spin_Spin.shape == (1, 2, 256, 256)
+    assert np.array_equal(E2.Spin_Spin[:, -1], ops.villain_spin_spin(E2.fields[0]).cpu().numpy())
+    Wl = svb.Worldline(svb.Lattice2D(N), kappa)
+    E3 = svb.BatchedEnsemble(Wl, chains).generate(4, PlaquetteUpdate(Wl, seed=23), start='hot', start_seed=6, correlate_every=4)
+    assert np.array_equal(E3.Vortex_Vortex[:, 0], ops.correlation('vortex', E3.fields[1], W=1).cpu().numpy())
+    with pytest.raises(NotImplementedError):
+        svb.BatchedEnsemble(Wl, chains).generate(2, PlaquetteUpdate(Wl, seed=23), start='cold', correlate_every=1, correlators=('Spin_Spin',))
