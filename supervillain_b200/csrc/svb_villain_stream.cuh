@@ -128,7 +128,7 @@ __device__ __forceinline__ void stream_accept(double* gphi, int32_t* gn0, int V,
 
 // The decision half of a colour pass over a pair of sites (row offsets oA and oB = oA + 8 N, column x1) that share the Philox
 // block `bits` (counter word 0 = oA + x1, draw mapping version 2), from their fp32 residuals rA, rB = (f0, b0, f1, b1).
-template <bool UNIT>
+template <bool UNIT, bool LUT = true>
 __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const FilterConsts& fc, double* gphi, int32_t* gn0, int V, int oA,
                                                    int oAm, int oAp, int oB, int oBm, int oBp, int x1, int xm1, int xp1, const Philox4& bits,
                                                    uint32_t c0, const float4& rA, const float4& rB, unsigned long long gc,
@@ -147,6 +147,17 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
         const uint64_t pa = (uint64_t)fA * 81u, pb = (uint64_t)fB * 81u;
         fA = (uint32_t)pa; fB = (uint32_t)pb;
         codeA = (uint32_t)(pa >> 32); codeB = (uint32_t)(pb >> 32);
+        if (!LUT) {
+            // (the tile kernel keeps its shared-memory bandwidth for the staged fields: there the digits are decoded arithmetically)
+            uint32_t c = codeA;
+            a0 = (int)((c * 2428u) >> 16); c -= 27u * (uint32_t)a0;
+            a1 = (int)((c * 7282u) >> 16); c -= 9u * (uint32_t)a1;
+            a2 = (int)((c * 21846u) >> 16); a3 = (int)(c - 3u * (uint32_t)a2);
+            c = codeB;
+            b0 = (int)((c * 2428u) >> 16); c -= 27u * (uint32_t)b0;
+            b1 = (int)((c * 7282u) >> 16); c -= 9u * (uint32_t)b1;
+            b2 = (int)((c * 21846u) >> 16); b3 = (int)(c - 3u * (uint32_t)b2);
+        }
     } else {
         uint64_t pa, pb;
         pa = (uint64_t)fA * K; fA = (uint32_t)pa; a0 = (int)(pa >> 32);  pb = (uint64_t)fB * K; fB = (uint32_t)pb; b0 = (int)(pb >> 32);
@@ -165,7 +176,7 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
     const float2 r_f1 = make_float2(rA.z, rB.z), r_b1 = make_float2(rA.w, rB.w);
     // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
     float2 dr_f0, dr_b0, dr_f1, dr_b1;
-    if (UNIT) {
+    if (UNIT && LUT) {
         const float4 tA = dn_lut[codeA], tB = dn_lut[codeB];          // -2 pi digit: exact in fp32, so the add is the fma below
         dr_f0 = __fadd2_rn(base_f, make_float2(tA.x, tB.x));
         dr_b0 = __fadd2_rn(base_b, make_float2(tA.y, tB.y));
@@ -196,7 +207,7 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
     if (candA || candB) {
         const int mWI = -W * interval_n;
         const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
-        if (UNIT) {
+        if (UNIT && LUT) {
             uint32_t c = codeA;
             a0 = (int)((c * 2428u) >> 16); c -= 27u * (uint32_t)a0;
             a1 = (int)((c * 7282u) >> 16); c -= 9u * (uint32_t)a1;
@@ -534,10 +545,11 @@ __global__ void __launch_bounds__(256, 3) villain_stream_pass_kernel(const __gri
     }
 }
 
-// sum (dn)^2 of every chain, reading n once: a warp owns 64 columns and walks down `rows` consecutive rows, a lane keeps the
-// pair (n0, n1)[2k, 2k + 1] of the current row and needs only the next row's n1 pair (which it keeps for the next step) and its
-// right-hand neighbour's n0 (a shuffle; the last lane of a warp loads it).  (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]).
-// Grid: chains x bands x row runs; per-warp partial sums added atomically (the caller zeroes SVB_VOBS_SUM_DN2).
+// sum (dn)^2 of every chain, reading n once: a warp owns 128 columns (a lane four: 16-byte loads, 512 contiguous bytes per warp and
+// row) and walks down `rows` consecutive rows; a lane keeps n1[x] of the current row and needs only the next row's n1 (which it
+// keeps for the next step) and its right-hand neighbour's first n0 (a shuffle; the last lane of a band loads it).
+// (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]).  Grid: chains x bands x row runs; per-warp partial sums added atomically (the
+// caller zeroes SVB_VOBS_SUM_DN2).
 __global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* __restrict__ n, long long chains, int N, int bands,
                                                                  int runs, int rows, double* __restrict__ state_out) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -548,46 +560,48 @@ __global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* 
     const long long chain = w / per_chain;
     const int rem = (int)(w - chain * per_chain);
     const int run = rem / bands, band = rem - run * bands;
-    const int k = 32 * band + lane;
+    const int q = 32 * band + lane;                                               // column quad [4 q, 4 q + 3]
     const long long V = (long long)N * N;
     const int32_t* gn0 = n + chain * 2 * V;
     const int32_t* gn1 = gn0 + V;
     long long dn2 = 0;
-    const bool active = k < N / 2;
-    const int c = active ? 2 * k : 0;
-    const int cr = (c + 2 == N) ? 0 : c + 2;                                       // the column right of the pair, wrapped
+    const bool active = q < N / 4;
+    const int c = active ? 4 * q : 0;
+    const int cr = (c + 4 == N) ? 0 : c + 4;                                       // the column right of the quad, wrapped
+    const bool edge = lane == 31 || q + 1 >= N / 4;
     const int r_lo = run * rows, r_hi = min(N, r_lo + rows);
-    int2 m1 = *reinterpret_cast<const int2*>(gn1 + (long long)r_lo * N + c);
-    const bool edge = lane == 31 || k + 1 >= N / 2;
+    int4 m1 = *reinterpret_cast<const int4*>(gn1 + (long long)r_lo * N + c);
     int r = r_lo;
     // four rows at a time: their eight (nine) loads are in flight together -- a warp has little else to hide DRAM latency with
     for (; r + 4 <= r_hi; r += 4) {
-        int2 m0[4], up[4];
+        int4 m0[4], up[4];
         int hrq[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rn = (r + i + 1 == N) ? 0 : r + i + 1;
-            m0[i] = *reinterpret_cast<const int2*>(gn0 + (long long)(r + i) * N + c);
-            up[i] = *reinterpret_cast<const int2*>(gn1 + (long long)rn * N + c);
+            m0[i] = *reinterpret_cast<const int4*>(gn0 + (long long)(r + i) * N + c);
+            up[i] = *reinterpret_cast<const int4*>(gn1 + (long long)rn * N + c);
             hrq[i] = edge ? gn0[(long long)(r + i) * N + cr] : 0;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int sh = __shfl_down_sync(0xffffffffu, m0[i].x, 1);
             const int hr = edge ? hrq[i] : sh;
-            const int d0 = (up[i].x - m1.x) - (m0[i].y - m0[i].x), d1 = (up[i].y - m1.y) - (hr - m0[i].y);
-            if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+            const int d0 = (up[i].x - m1.x) - (m0[i].y - m0[i].x), d1 = (up[i].y - m1.y) - (m0[i].z - m0[i].y);
+            const int d2 = (up[i].z - m1.z) - (m0[i].w - m0[i].z), d3 = (up[i].w - m1.w) - (hr - m0[i].w);
+            if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1 + (long long)d2 * d2 + (long long)d3 * d3;
             m1 = up[i];
         }
     }
     for (; r < r_hi; ++r) {
         const int rn = (r + 1 == N) ? 0 : r + 1;
-        const int2 m0 = *reinterpret_cast<const int2*>(gn0 + (long long)r * N + c);
-        const int2 up = *reinterpret_cast<const int2*>(gn1 + (long long)rn * N + c);
+        const int4 m0 = *reinterpret_cast<const int4*>(gn0 + (long long)r * N + c);
+        const int4 up = *reinterpret_cast<const int4*>(gn1 + (long long)rn * N + c);
         int hr = __shfl_down_sync(0xffffffffu, m0.x, 1);
         if (edge) hr = gn0[(long long)r * N + cr];
-        const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (hr - m0.y);
-        if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1;
+        const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (m0.z - m0.y);
+        const int d2 = (up.z - m1.z) - (m0.w - m0.z), d3 = (up.w - m1.w) - (hr - m0.w);
+        if (active) dn2 += (long long)d0 * d0 + (long long)d1 * d1 + (long long)d2 * d2 + (long long)d3 * d3;
         m1 = up;
     }
     dn2 = warp_sum(dn2);
@@ -595,8 +609,8 @@ __global__ void __launch_bounds__(256) villain_stream_dn2_kernel(const int32_t* 
 }
 
 static int launch_villain_stream_dn2(const int32_t* n, long long chains, int N, double* state_out, cudaStream_t stream, const DeviceInfo& info) {
-    const int bands = (N / 2 + 31) / 32;
-    // rows per warp: long runs amortise the set-up and the one redundant row, short runs fill the machine (>= 16 warps per SM slot)
+    const int bands = (N / 4 + 31) / 32;
+    // rows per warp: long runs amortise the set-up and the one redundant row, short runs fill the machine
     int rows = N;
     while (rows > 16 && chains * bands * ((N + rows - 1) / rows) < 4LL * 64 * info.sm_count) rows = (rows + 1) / 2;
     const int runs = (N + rows - 1) / rows;
@@ -753,7 +767,6 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ double scratch[8 * 5];         // per-warp partial sums of the records (shared memory is what limits this kernel to 3 CTAs per SM)
     __shared__ int tile_coord[2][4];          // per stage: chain, R, C of the tile that was loaded into it (written by thread 0)
-    __shared__ float4 dn_lut[81];
     const int N = a.N, V = N * N;
     const int tiles_x = N / kTileCols, tiles_y = N / kTileRows, tiles_per_chain = tiles_x * tiles_y;
     const long long tiles = (long long)tiles_per_chain * a.chains;
@@ -768,7 +781,6 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
         mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
-    if (UNIT) stream_fill_lut(dn_lut, fc.c, tid, 256);
     __syncthreads();
     pdl_prologue();
     auto issue = [&](long long t, int stage) {
@@ -879,8 +891,8 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
                 rA = tile_site_residuals<false>(P, N0, N1, w8 + 1, jc, par, action, w0, w1);
                 rB = tile_site_residuals<false>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
             }
-            stream_pair_decide<UNIT>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc, gs, half_kappa,
-                                     hk2, hkA, hkB, n_acc, sum_A, dn_lut);
+            stream_pair_decide<UNIT, false>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc, gs,
+                                            half_kappa, hk2, hkA, hkB, n_acc, sum_A, nullptr);
         }
         __syncthreads();                                           // every thread has read the stage (and its coordinates): refill it
         const long long t2 = t + 2LL * gridDim.x;

@@ -85,7 +85,19 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
         }
     };
 
-    const int row8 = tid / HN, k = tid - row8 * HN;
+    // thread -> (row8, k): it owns the plaquettes (row8 + 8 q, 2 k + parity).  A warp takes 16 column slots of TWO adjacent rows
+    // (their column parities are opposite): its 32 accesses to a row-major int32 array then fall on 32 different banks, where
+    // 32 slots of ONE row (stride 2) collide pairwise -- a third of this kernel's shared-memory wavefronts were such replays.
+    // (Any bijection gives the same chain: the draws are keyed by the site.)
+    int row8, k;
+    if (HN >= 16) {
+        const int rest = tid >> 5;
+        row8 = 2 * (rest / (HN / 16)) + ((tid >> 4) & 1);
+        k = 16 * (rest % (HN / 16)) + (tid & 15);
+    } else {
+        row8 = tid / HN;
+        k = tid - row8 * HN;
+    }
     long long chain = blockIdx.x;
     if (tid == 0 && chain < a.chains) issue_load(chain, OVERLAP ? overlap_peek(a.ov, chain) : 0u);
     if (!a.kappa_chain) build_table(a.kappa);
