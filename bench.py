@@ -475,6 +475,10 @@ def run_gpu(args):
                 'algorithmic_bytes_per_launch': spec['bytes'] * c2.updates_per_step, 'peak_source': peak_src,
                 'sweeps_per_launch': args.sweeps_per_step}
     clocks = head['clocks']
+    # ---- gather of observables of the thermalised chains (outside the timed region; the only inter-GPU traffic) ----
+    obs = svb.ops.villain_observables(c2.sets[0][0], c2.sets[0][1], KAPPA)      # state of set 0 after the hot windows
+    all_obs = sharding.gather_columns(obs)                    # (world * CHAINS, VOBS_COUNT) on every rank
+    mean_action_density = float(all_obs[:, 0].mean().item()) / (spec['L'] ** 2)
     c2_cold = measure(c2, args.steps, 'cold')
 
     # ---- end to end through the host-buffer API: H2D of the fields, sweep, D2H of fields + observables ----
@@ -503,11 +507,7 @@ def run_gpu(args):
            'steps': e2e_steps, 'api': 'HostStepper.step_async(phi_host, n_host): pinned host fields in and out + observables, two steps in flight on '
                   'alternating host buffer pairs'}
 
-    # ---- final gather of observables (outside the timed region; the only inter-GPU traffic) ----
     torch.cuda.synchronize()
-    obs = svb.ops.villain_observables(c2.sets[0][0], c2.sets[0][1], KAPPA)      # final state of set 0
-    all_obs = sharding.gather_columns(obs)                    # (world * CHAINS, VOBS_COUNT) on every rank
-    mean_action_density = float(all_obs[:, 0].mean().item()) / (spec['L'] ** 2)
     del stepper, host_sets
 
     # ---- every named shape: hot and cold, its own roofline ----
@@ -565,7 +565,8 @@ def run_gpu(args):
                        'warmup': f'>= {args.warmup} steps and >= {SUSTAIN_S} s of the same load issued back to back; the stream is not drained '
                                  f'before the first window; clock sampler started (first sample awaited) before the warm-up'},
             'configs': shapes_out,
-            'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0])},
+            'check': {'mean_action_density': mean_action_density, 'gathered_chains': int(all_obs.shape[0]),
+                      'state': 'set 0 after the hot-start windows'},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -387,6 +387,35 @@ def test_overlapped_launches_equal_ordinary_launches(N, chains):
     assert int(steppers[0].epochs.min()) == steppers[0].epoch == K + 2
 
 
+@pytest.mark.parametrize('N,chains', [(16, 1500), (32, 2500), (64, 400), (128, 90)])
+def test_sparse_launches_equal_dense_launches(N, chains):
+    """A single-sweep launch that owes no record of the state it leaves applies its accepted proposals to global memory
+    as reductions and stores nothing back (SPARSE); a launch that must record the state it leaves, and a
+    launch of several fused sweeps, store the chain densely.  Same fields, same acceptance counters, sweep after sweep."""
+    kappa, K = 0.5, 5
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 21)
+    ophi, on = phi.clone(), n.clone()
+    dphi, dn = phi.clone(), n.clone()
+    fphi, fn = phi.clone(), n.clone()
+    rec_in = torch.zeros((K + 1, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    rec = torch.zeros((K, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    stepper = ops.VillainOverlappedSweeps(ophi, on, kappa, seed=4)
+    for k in range(K):
+        ops.villain_sweep(phi, n, kappa, seed=4, sweep0=k, n_sweeps=1)                       # sparse: no record at all
+        stepper.step(k, 1, obs=rec_in[k + 1], obs_in=rec_in[k])                              # sparse: record of the arriving state
+        ops.villain_sweep(dphi, dn, kappa, seed=4, sweep0=k, n_sweeps=1, obs=rec[k])         # dense: record of the state it leaves
+        assert torch.equal(phi, dphi) and torch.equal(n, dn)
+        assert torch.equal(ophi, dphi) and torch.equal(on, dn)
+    ops.villain_sweep(fphi, fn, kappa, seed=4, sweep0=0, n_sweeps=K)                         # dense: fused sweeps
+    torch.cuda.synchronize()
+    assert torch.equal(fphi, dphi) and torch.equal(fn, dn)
+    assert torch.equal(rec_in[1:, :, 4], rec[:, :, 4])                                        # SVB_VOBS_ACCEPTED
+    assert torch.allclose(rec_in[1:, :, 5], rec[:, :, 5], rtol=1e-6, atol=0)                 # SVB_VOBS_ACCEPTANCE: an fp32 monitor
+    assert torch.equal(rec_in[1:K, :, 1:4], rec[:K - 1, :, 1:4])                              # integer state columns arrive one launch late
+    assert torch.allclose(rec_in[1:K, :, 0], rec[:K - 1, :, 0], rtol=1e-13, atol=0)         # the action (summation order)
+
+
 def test_overlapped_launches_reject_what_they_do_not_serve():
     S = svb.Villain(svb.Lattice2D(48), 0.5)
     phi, n = svb.BatchedEnsemble(S, 4)._start('cold', 0)
