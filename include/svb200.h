@@ -179,6 +179,26 @@ int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, int N,
                               double* obs, double* obs_in, void* stream);
 
 /*
+ * svb_villain_sweep_inplace as ONE launch per step (N a multiple of 128; configs 4 and 5): the phases of a step -- sum (dn)^2 of
+ * the arriving state, colour 0, colour 1 [, the colours of further sweeps] -- follow one another down the lattice a few tile
+ * rows apart, so each phase reads from L2 what the one before left there, and DRAM sees one read of the state per launch plus
+ * the sectors that changed (the three launches of svb_villain_sweep_inplace read it 2.5 times).  Same proposals, same
+ * decisions, same fields bit for bit (NeighborhoodUpdate.step, generator/villain/neighborhood.py:59-137); obs / obs_in as above.
+ * On a B200 it takes the same time as svb_villain_sweep_inplace without a record and is slower with one (the colour passes are
+ * bound by instruction issue, not by DRAM: DESIGN 3.3), so the host layer uses it only on request.
+ *
+ *  workspace      int32 device scratch owned by the caller, at least svb_villain_wavefront_workspace(chains, N, 1, obs_in != NULL)
+ *                 ints (with room for k sweeps, k sweeps share a launch); it must be ALL ZERO before its first use and every
+ *                 call leaves it all zero.  Calls that share a workspace must be ordered (one stream).
+ */
+long long svb_villain_wavefront_workspace(int64_t chains, int N, int n_sweeps, int with_obs_in);
+int svb_villain_sweep_wavefront(void* phi, int32_t* n, int64_t chains, int N,
+                                double kappa, const double* kappa_chain, int W,
+                                double interval_phi, int interval_n,
+                                int n_sweeps, uint64_t seed, uint64_t sweep0, uint64_t chain0,
+                                double* obs, double* obs_in, int32_t* workspace, int64_t workspace_ints, void* stream);
+
+/*
  * The same sweeps as OVERLAPPED launches: a launch may begin while the previous launch in the stream is still running
  * (programmatic dependent launch), so the ramp-up of one sweep hides under the tail of the one before -- at config 2 a
  * quarter of a non-overlapped step.  Data dependencies are tracked per chain instead of per kernel:

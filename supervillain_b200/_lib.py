@@ -40,6 +40,8 @@ SIGNATURES = {
     'svb_villain_sweep_tiled': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
     'svb_villain_sweep_tiled_swap': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _i, _vp, _vp, _vp]),
     'svb_villain_sweep_inplace': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp]),
+    'svb_villain_sweep_wavefront': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _d, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i64, _vp]),
+    'svb_villain_wavefront_workspace': (ctypes.c_longlong, [_i64, _i, _i, _i]),
     'svb_villain_sweep_host': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _i, _d, _i, _i, _u64, _u64, _u64, _i, _i, _vp, _i]),
     'svb_worldline_sweep': (_i, [_vp, _vp, _i64, _i, _d, _vp, _i, _i, _i, _i, _u64, _u64, _u64, _i, _i,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

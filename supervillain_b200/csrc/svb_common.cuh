@@ -216,6 +216,13 @@ __device__ __forceinline__ long long warp_sum(long long v) {
     return v;
 }
 
+__device__ __forceinline__ int warp_sum_i32(int v) { return __reduce_add_sync(0xffffffffu, v); }      // REDUX
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // Sum K doubles per thread across the block; result valid in thread 0.  scratch: K * 32 doubles.
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* scratch) {

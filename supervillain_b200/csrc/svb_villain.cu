@@ -2277,6 +2277,50 @@ extern "C" int svb_villain_sweep_inplace(void* phi, int32_t* n, int64_t chains, 
     return SVB_OK;
 }
 
+// The same in-place sweeps as ONE launch per step: the phases follow one another down the lattice as a wavefront through L2
+// (villain_tile_wave_kernel, svb_villain_stream.cuh): see include/svb200.h.
+extern "C" long long svb_villain_wavefront_workspace(int64_t chains, int N, int n_sweeps, int with_obs_in) {
+    if (chains < 0 || N < 128 || (N % svb::kTileCols) != 0 || n_sweeps < 1) return 0;
+    return svb::villain_wave_workspace_ints(chains, N, n_sweeps, with_obs_in != 0);
+}
+
+extern "C" int svb_villain_sweep_wavefront(void* phi, int32_t* n, int64_t chains, int N, double kappa, const double* kappa_chain, int W,
+                                           double interval_phi, int interval_n, int n_sweeps, uint64_t seed, uint64_t sweep0,
+                                           uint64_t chain0, double* obs, double* obs_in, int32_t* workspace, int64_t workspace_ints,
+                                           void* stream) {
+    if (!phi || !n || !workspace) return fail(SVB_E_NULL, "svb_villain_sweep_wavefront: phi, n and the workspace are required");
+    if (chains < 0 || N < 128 || N > 32768 || (N % kTileCols) != 0 || chains * 2 >= 0x7fffffffLL)
+        return fail(SVB_E_SHAPE, "svb_villain_sweep_wavefront: N=%d must be a multiple of %d (chains=%lld)", N, kTileCols, (long long)chains);
+    if (((uintptr_t)phi % 16) || ((uintptr_t)n % 16) || ((uintptr_t)workspace % 4))
+        return fail(SVB_E_ALIGN, "svb_villain_sweep_wavefront: fields must be 16-byte aligned");
+    if (!kappa_chain && !(kappa > 0)) return fail(SVB_E_PARAM, "svb_villain_sweep_wavefront: kappa must be positive");
+    if (W < 1 || !(interval_phi >= 0) || n_sweeps < 0) return fail(SVB_E_PARAM, "svb_villain_sweep_wavefront: W / interval_phi / n_sweeps");
+    if (interval_n < 0 || villain_wide(interval_n))
+        return fail(SVB_E_UNSUPPORTED, "svb_villain_sweep_wavefront: interval_n must be 0 or 1 (wider proposals: svb_villain_sweep)");
+    if (obs_in && !obs) return fail(SVB_E_NULL, "svb_villain_sweep_wavefront: obs_in needs obs (this launch's counters go there)");
+    if (chains == 0 || n_sweeps == 0) return SVB_OK;
+    VillainArgs a;
+    a.phi = phi; a.n = n; a.chains = chains; a.N = N; a.kappa = kappa; a.kappa_chain = kappa_chain; a.W = W;
+    a.interval_phi = interval_phi; a.interval_n = interval_n; a.n_sweeps = n_sweeps;
+    a.seed = seed; a.sweep0 = sweep0; a.chain0 = chain0;
+    villain_rng_setup(a, STREAM_VILLAIN_NEIGHBORHOOD, STREAM_VILLAIN_REFINE, 0);
+    a.inj_u = nullptr; a.inj_dphi = nullptr; a.inj_dn_fwd = nullptr; a.inj_dn_bwd = nullptr;
+    a.obs = obs; a.accept_mask = nullptr; a.dS_out = nullptr;
+    a.exact_mode = 0; a.inj_z = nullptr; a.filtered_strict = 0; a.obs_in = obs_in; a.epochs = nullptr; a.wait_epoch = 0; a.signal_epoch = 0; a.grid_wait = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DeviceInfo info;
+    int rc = get_device_info(info);
+    if (rc) return rc;
+    if (obs || obs_in) {
+        SVB_CUDA_TRY(launch_pdl(villain_zero_inplace_records_kernel, (unsigned)((chains + 255) / 256), 256, 0, st, obs_in, obs, (long long)chains));
+    }
+    rc = launch_villain_tile_wave(a, obs_in, obs, workspace, (long long)workspace_ints, st, info);
+    if (rc) return rc;
+    if (obs && !obs_in)     // the full record of the state after the sweeps: one more read of the state
+        return launch_villain_obs<double>(reinterpret_cast<const double*>(phi), n, chains, N, kappa, kappa_chain, obs, 1, st);
+    return SVB_OK;
+}
+
 #ifdef SVB_TRACE
 // Evidence build only: copy the CTA time stamps of the overlapped launches to the host (launches x ctas x {start, end} u64).
 extern "C" int svb_debug_trace_read(unsigned long long* out_host, int* launches, int* ctas) {

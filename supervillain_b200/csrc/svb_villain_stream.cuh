@@ -97,6 +97,17 @@ __device__ __forceinline__ float4 stream_site_residuals(const double* gphi, cons
     return make_float4((float)rf0, (float)rb0, (float)rf1, (float)rb1);
 }
 
+// Geometry of a TMA-staged tile (villain_tile_pass_kernel, villain_tile_wave_kernel below).
+constexpr int kTileRows = 16, kTileCols = 128;
+constexpr int kTilePhiRows = kTileRows + 2, kTilePhiCols = kTileCols + 4;     // rows R-1 .. R+16, columns C-2 .. C+129
+constexpr int kTileNRows = kTileRows + 1, kTileNCols = kTileCols + 4;        // rows R-1 .. R+15, columns C-4 .. C+127
+constexpr int kTilePhiBytes = kTilePhiRows * kTilePhiCols * 8;                 // 19008
+constexpr int kTileNBytes = kTileNRows * kTileNCols * 4;                       // 8976
+constexpr int kTilePhiSlot = (kTilePhiBytes + 127) / 128 * 128, kTileNSlot = (kTileNBytes + 127) / 128 * 128;
+constexpr int kTileStageBytes = kTilePhiSlot + 2 * kTileNSlot;
+constexpr int kTileSmemBytes = 2 * kTileStageBytes + 64;
+static_assert(kTilePhiCols == kTileNCols, "the exact test of a staged tile indexes phi and n with one stride");
+
 // The exact test of a proposal whose fp32 comparison is inside its error band (a few 1e-5 of the proposals): dS in fp64 from
 // the current phi and n (L1 / L2), the fp64 exponential, the lazily refined uniform.  Out of line on purpose: the hot loop
 // should not pay registers for it.
@@ -106,6 +117,23 @@ __device__ __noinline__ bool stream_exact(const VillainArgs& a, const double* gp
     ExactProposal ep;
     ep.phi = gphi; ep.n0 = gn0; ep.n1 = gn0 + V;
     ep.i_c = o + x1; ep.i_b0 = om + x1; ep.i_b1 = o + xm1; ep.i_f0 = op + x1; ep.i_f1 = o + xp1;
+    ep.half_kappa = half_kappa; ep.c = SVB_TWO_PI * (double)W;
+    ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
+    ep.g[0] = g0; ep.g[1] = g1; ep.g[2] = g2; ep.g[3] = g3;
+    ep.d.f = f; ep.d.c0 = c0; ep.d.half = half;
+    ep.rc.seed = a.seed; ep.rc.chain = gc; ep.rc.sweep = gs; ep.rc.stream = a.refine_stream; ep.rc.wide = 0;
+    return villain_exact_decision(ep);
+}
+
+// The same test from a tile staged in shared memory (villain_tile_wave_kernel): idx = row * kTilePhiCols + column slot + 4 in the n
+// boxes, the phi box is shifted by two columns.  Nothing a site's test reads is written by anybody else during its colour phase,
+// so the staged copy is as current as global memory -- and, unlike a plain global load, it cannot come from a stale L1 line.
+__device__ __noinline__ bool tile_exact(const VillainArgs& a, const double* P, const int32_t* N0, const int32_t* N1, int idx, uint32_t wA,
+                                        uint32_t f, uint32_t c0, uint32_t half, int g0, int g1, int g2, int g3, int W, double half_kappa,
+                                        unsigned long long gc, unsigned long long gs) {
+    ExactProposal ep;
+    ep.phi = P - 2; ep.n0 = N0; ep.n1 = N1;
+    ep.i_c = idx; ep.i_b0 = idx - kTilePhiCols; ep.i_b1 = idx - 1; ep.i_f0 = idx + kTilePhiCols; ep.i_f1 = idx + 1;
     ep.half_kappa = half_kappa; ep.c = SVB_TWO_PI * (double)W;
     ep.dphi = villain_dphi_from_word(wA, a.interval_phi);
     ep.g[0] = g0; ep.g[1] = g1; ep.g[2] = g2; ep.g[3] = g3;
@@ -128,12 +156,13 @@ __device__ __forceinline__ void stream_accept(double* gphi, int32_t* gn0, int V,
 
 // The decision half of a colour pass over a pair of sites (row offsets oA and oB = oA + 8 N, column x1) that share the Philox
 // block `bits` (counter word 0 = oA + x1, draw mapping version 2), from their fp32 residuals rA, rB = (f0, b0, f1, b1).
-template <bool UNIT, bool LUT = true>
+template <bool UNIT, bool LUT = true, bool TILE = false>
 __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const FilterConsts& fc, double* gphi, int32_t* gn0, int V, int oA,
                                                    int oAm, int oAp, int oB, int oBm, int oBp, int x1, int xm1, int xp1, const Philox4& bits,
                                                    uint32_t c0, const float4& rA, const float4& rB, unsigned long long gc,
                                                    unsigned long long gs, double half_kappa, float hk2, float hkA, float hkB, int& n_acc,
-                                                   float& sum_A, const float4* dn_lut) {
+                                                   float& sum_A, const float4* dn_lut, const double* tP = nullptr,
+                                                   const int32_t* tN0 = nullptr, const int32_t* tN1 = nullptr, int tIdx = 0) {
     const int interval_n = UNIT ? 1 : a.interval_n;
     const uint32_t K = (uint32_t)(2 * interval_n + 1);
     const int W = UNIT ? 1 : a.W;
@@ -220,8 +249,10 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
         if (candA) {
             bool ok = diff.x < 0.0f;
             if (!(fabsf(diff.x) > band.x) || fA < 65536u)
-                ok = stream_exact(a, gphi, gn0, V, oA, oAm, oAp, x1, xm1, xp1, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n,
-                                  a2 - interval_n, a3 - interval_n, W, half_kappa, gc, gs);
+                ok = TILE ? tile_exact(a, tP, tN0, tN1, tIdx, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n, a2 - interval_n,
+                                       a3 - interval_n, W, half_kappa, gc, gs)
+                          : stream_exact(a, gphi, gn0, V, oA, oAm, oAp, x1, xm1, xp1, bits.x, fA, c0, 0u, a0 - interval_n, a1 - interval_n,
+                                         a2 - interval_n, a3 - interval_n, W, half_kappa, gc, gs);
             if (ok) {
                 n_acc += 1;
                 stream_accept(gphi, gn0, V, oA, oAm, x1, xm1, bits.x, a.interval_phi, two_I_scaled, W * a0 + mWI, W * a1 + mWI, W * a2 + mWI,
@@ -231,8 +262,10 @@ __device__ __forceinline__ void stream_pair_decide(const VillainArgs& a, const F
         if (candB) {
             bool ok = diff.y < 0.0f;
             if (!(fabsf(diff.y) > band.y) || fB < 65536u)
-                ok = stream_exact(a, gphi, gn0, V, oB, oBm, oBp, x1, xm1, xp1, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n,
-                                  b2 - interval_n, b3 - interval_n, W, half_kappa, gc, gs);
+                ok = TILE ? tile_exact(a, tP, tN0, tN1, tIdx + 8 * kTilePhiCols, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n,
+                                       b2 - interval_n, b3 - interval_n, W, half_kappa, gc, gs)
+                          : stream_exact(a, gphi, gn0, V, oB, oBm, oBp, x1, xm1, xp1, bits.z, fB, c0, 1u, b0 - interval_n, b1 - interval_n,
+                                         b2 - interval_n, b3 - interval_n, W, half_kappa, gc, gs);
             if (ok) {
                 n_acc += 1;
                 stream_accept(gphi, gn0, V, oB, oBm, x1, xm1, bits.z, a.interval_phi, two_I_scaled, W * b0 + mWI, W * b1 + mWI, W * b2 + mWI,
@@ -712,14 +745,6 @@ __global__ void __launch_bounds__(256) villain_stream_obs_kernel(const double* _
 //   * everything after the residuals is stream_pair_decide: accepted proposals go to GLOBAL memory as reductions, in place --
 //     no workspace, no ping-pong, no ghost-zone recomputation, nothing stored that did not change.
 // ------------------------------------------------------------------------------------------
-constexpr int kTileRows = 16, kTileCols = 128;
-constexpr int kTilePhiRows = kTileRows + 2, kTilePhiCols = kTileCols + 4;     // rows R-1 .. R+16, columns C-2 .. C+129
-constexpr int kTileNRows = kTileRows + 1, kTileNCols = kTileCols + 4;        // rows R-1 .. R+15, columns C-4 .. C+127
-constexpr int kTilePhiBytes = kTilePhiRows * kTilePhiCols * 8;                 // 19008
-constexpr int kTileNBytes = kTileNRows * kTileNCols * 4;                       // 8976
-constexpr int kTilePhiSlot = (kTilePhiBytes + 127) / 128 * 128, kTileNSlot = (kTileNBytes + 127) / 128 * 128;
-constexpr int kTileStageBytes = kTilePhiSlot + 2 * kTileNSlot;
-constexpr int kTileSmemBytes = 2 * kTileStageBytes + 64;
 
 __device__ __forceinline__ void tensor_box_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -935,6 +960,131 @@ static int villain_tile_maps(const VillainArgs& a, CUtensorMap& map_phi, CUtenso
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// sum (dn)^2 of big lattices (N a multiple of 128) as a TMA-fed stream: the pass over n that precedes the colour passes of a
+// step with a record.  villain_stream_dn2_kernel's per-thread loads reach 3.5 TB/s (38 us of a 173 us step at L = 4096); here
+// the copy engine does the streaming: a tile is 32 rows x 128 columns of plaquettes, its n0 and n1 arrive as two 3-D tensor
+// boxes of 33 rows x 132 columns (the row below for n1, the column to the right for n0; beyond the edge of the lattice they
+// are zero-filled and patched from the other side), three stages per CTA, persistent CTAs, a thread sums 16 plaquettes
+// from conflict-free 16-byte shared-memory loads.
+// ------------------------------------------------------------------------------------------
+constexpr int kDn2Rows = 32, kDn2BoxRows = kDn2Rows + 1, kDn2BoxCols = kTileCols + 4;
+constexpr int kDn2BoxBytes = kDn2BoxRows * kDn2BoxCols * 4;                            // 17424
+constexpr int kDn2BoxSlot = (kDn2BoxBytes + 127) / 128 * 128;
+constexpr int kDn2Stages = 3, kDn2StageBytes = 2 * kDn2BoxSlot;
+constexpr int kDn2SmemBytes = kDn2Stages * kDn2StageBytes + 64;
+
+__global__ void __launch_bounds__(256, 2) villain_tile_dn2_kernel(const __grid_constant__ CUtensorMap map_n, const int32_t* __restrict__ n,
+                                                                  long long chains, int N, double* __restrict__ state_out) {
+    extern __shared__ __align__(128) unsigned char dn2_smem[];
+    const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dn2_smem + kDn2Stages * kDn2StageBytes);
+    const int tiles_x = N / kTileCols, tiles_y = N / kDn2Rows, tiles_per_chain = tiles_x * tiles_y;
+    const long long tiles = (long long)tiles_per_chain * chains;
+    const long long V = (long long)N * N;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kDn2Stages; ++s) mbar_init(&bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_prologue();
+    auto issue = [&](long long t, int stage) {
+        const long long chain = t / tiles_per_chain;
+        const int tile = (int)(t - chain * tiles_per_chain);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        unsigned char* st = dn2_smem + stage * kDn2StageBytes;
+        mbar_expect_tx(&bar[stage], (uint32_t)(2 * kDn2BoxBytes));
+        tensor_box_3d(st, &map_n, tx * kTileCols, ty * kDn2Rows, (int)(2 * chain), &bar[stage]);
+        tensor_box_3d(st + kDn2BoxSlot, &map_n, tx * kTileCols, ty * kDn2Rows, (int)(2 * chain + 1), &bar[stage]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kDn2Stages; ++s)
+            if (blockIdx.x + (long long)s * gridDim.x < tiles) issue(blockIdx.x + (long long)s * gridDim.x, s);
+    }
+    long long dn2 = 0, chain_of_sum = -1;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long chain = t / tiles_per_chain;
+        const int tile = (int)(t - chain * tiles_per_chain);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int R = ty * kDn2Rows, C = tx * kTileCols;
+        if (chain != chain_of_sum) {
+            if (chain_of_sum >= 0) {
+                const long long v = warp_sum(dn2);
+                if (lane == 0) atomicAdd(state_out + chain_of_sum * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, (double)v);
+                dn2 = 0;
+            }
+            chain_of_sum = chain;
+        }
+        int32_t* N0 = reinterpret_cast<int32_t*>(dn2_smem + stage * kDn2StageBytes);
+        int32_t* N1 = reinterpret_cast<int32_t*>(dn2_smem + stage * kDn2StageBytes + kDn2BoxSlot);
+        mbar_wait(&bar[stage], parity);
+        const bool bottom = R + kDn2Rows == N, right = C + kTileCols == N;
+        if (bottom || right) {
+            const int32_t* gn0 = n + chain * 2 * V;
+            if (bottom && tid < kTileCols) N1[kDn2Rows * kDn2BoxCols + tid] = gn0[V + C + tid];                              // row N = row 0
+            if (right && tid >= 128 && tid < 128 + kDn2Rows) N0[(tid - 128) * kDn2BoxCols + kTileCols] = gn0[(long long)(R + tid - 128) * N];   // column N = 0
+            __syncthreads();
+        }
+        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]); a thread: rows w8 + 8 h, four columns
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int i = w8 + 8 * h;
+            const int4 m0 = *reinterpret_cast<const int4*>(N0 + i * kDn2BoxCols + 4 * lane);
+            const int hr = N0[i * kDn2BoxCols + 4 * lane + 4];
+            const int4 m1 = *reinterpret_cast<const int4*>(N1 + i * kDn2BoxCols + 4 * lane);
+            const int4 up = *reinterpret_cast<const int4*>(N1 + (i + 1) * kDn2BoxCols + 4 * lane);
+            const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (m0.z - m0.y);
+            const int d2 = (up.z - m1.z) - (m0.w - m0.z), d3 = (up.w - m1.w) - (hr - m0.w);
+            dn2 += (long long)d0 * d0 + (long long)d1 * d1 + (long long)d2 * d2 + (long long)d3 * d3;
+        }
+        __syncthreads();                                           // every thread has read the stage: refill it
+        const long long t2 = t + (long long)kDn2Stages * gridDim.x;
+        if (tid == 0 && t2 < tiles) issue(t2, stage);
+        if (++stage == kDn2Stages) { stage = 0; parity ^= 1u; }
+    }
+    if (chain_of_sum >= 0) {
+        const long long v = warp_sum(dn2);
+        if (lane == 0) atomicAdd(state_out + chain_of_sum * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, (double)v);
+    }
+}
+
+static int launch_villain_tile_dn2(const int32_t* n, long long chains, int N, double* state_out, cudaStream_t stream, const DeviceInfo& info) {
+    static svb_tensor_map_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        SVB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status));
+        if (status != cudaDriverEntryPointSuccess || !fn) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<svb_tensor_map_encode_fn>(fn);
+    }
+    static int per_sm_cache[64];
+    int per_sm = (info.device < 64) ? per_sm_cache[info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tile_dn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDn2SmemBytes));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tile_dn2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, villain_tile_dn2_kernel, 256, kDn2SmemBytes));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "the (dn)^2 tile kernel does not fit an SM");
+        if (info.device < 64) per_sm_cache[info.device] = per_sm;
+    }
+    CUtensorMap map_n;
+    const cuuint64_t NN = (cuuint64_t)N;
+    const cuuint32_t ones[3] = {1, 1, 1};
+    const cuuint64_t dims[3] = {NN, NN, 2 * (cuuint64_t)chains}, strides[2] = {NN * 4, NN * NN * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kDn2BoxCols, (cuuint32_t)kDn2BoxRows, 1};
+    const CUresult r = encode(&map_n, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int32_t*>(n), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled(n, (dn)^2 boxes) failed: %d", (int)r);
+    const long long tiles = (long long)(N / kTileCols) * (N / kDn2Rows) * chains;
+    long long grid = (long long)per_sm * info.sm_count;
+    if (grid > tiles) grid = tiles;
+    SVB_CUDA_TRY(launch_pdl(villain_tile_dn2_kernel, (unsigned)grid, 256, (size_t)kDn2SmemBytes, stream, map_n, n, chains, N, state_out));
+    return 0;
+}
+
 // n_sweeps sweeps in place by TMA-staged colour passes (N a multiple of 128); obs_in / counters as launch_villain_stream_passes.
 static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, double* counters, cudaStream_t stream, const DeviceInfo& info) {
     const bool unit = a.W == 1 && a.interval_n == 1;
@@ -956,7 +1106,9 @@ static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, doub
     if (grid > tiles) grid = tiles;
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
     if (obs_in) {
-        const int rc_dn2 = launch_villain_stream_dn2(a.n, a.chains, a.N, obs_in, stream, info);
+        const char* e = getenv("SVB_VILLAIN_DN2");                  // "stream": the per-thread-load kernel, for an A/B
+        const int rc_dn2 = (e && e[0] == 's') ? launch_villain_stream_dn2(a.n, a.chains, a.N, obs_in, stream, info)
+                                              : launch_villain_tile_dn2(a.n, a.chains, a.N, obs_in, stream, info);
         if (rc_dn2) return rc_dn2;
     }
     for (int sw = 0; sw < a.n_sweeps; ++sw)
@@ -964,5 +1116,452 @@ static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, doub
             SVB_CUDA_TRY(launch_pdl(kern, (unsigned)grid, 256, (size_t)kTileSmemBytes, stream, a, fc, map_phi, map_n, c, sw,
                                     (sw == 0 && c == 0) ? obs_in : nullptr, counters));
         }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// ONE launch per step for big lattices: the phases of a step as a WAVEFRONT through L2 (svb_villain_sweep_wavefront).
+//
+// The in-place step above is three launches -- sum (dn)^2 over n, colour 0, colour 1 -- and each of them streams the lattice
+// from DRAM: 2.5 reads of the state per sweep where the algorithm needs one (ncu of a pass: 6.0 TB/s of DRAM traffic, 92 % of
+// what the part delivers: the passes are DRAM bound at twice the algorithmic bytes).  Nothing in the algorithm asks for that
+// order.  Colour 1 of a tile row needs colour 0 of that row and of the rows above and below it, nothing more; so the phases
+// can follow one another down the lattice a few tile rows apart, and what phase p + 1 reads is what phase p left in L2 a few
+// megabytes ago.  DRAM then sees one read of the state and the eviction of the dirty sectors, the algorithmic 32 B per
+// site-update.
+//
+//   * Work items: (phase p, tile row, tile column).  Phase 0 is the sum (dn)^2 of the arriving state (if a record is asked
+//     for), then the colour passes of the sweeps in order.  A chain has R = N / 16 tile rows; the tile rows of all chains are
+//     numbered J = chain R + k, and phase p visits them in the order k -> tile row (k + p) mod R: the shift by p makes the
+//     dependency the same everywhere, the periodic wrap included -- item (p, J) needs (p - 1, chain R + (k + d) mod R), d = 0, 1, 2.
+//   * Order: slot s = (wave, p, tile column), J = wave - p lag (slots whose J falls outside the lattice are skipped).  One CTA
+//     per SM; its 24 sweeping warps form three GROUPS of eight, each with its own two shared-memory stages.  Slots are handed
+//     out in order through a ticket counter, four at a time, to whichever group asks next: the cheap (dn)^2 tiles and the
+//     colour tiles, fast SMs and slow ones, balance themselves.
+//   * Each group has a CONTROL WARP (warps 24 - 26, one lane active).  It decodes the group's next slot, checks its dependency,
+//     issues its TMA loads (full barrier, complete_tx), and -- when the group's eight warps have arrived on the stage's empty
+//     barrier -- publishes the finished tile and reuses the stage.  None of this is on the sweeping warps' path: a gpu-scope
+//     release fence and an acquire load cost 0.5 - 0.8 us each, a fifth of a tile's sweep; done by the sweeping threads
+//     themselves they made this kernel slower than the three launches it replaces (287 against 173 us at L = 4096), and so
+//     did one control warp for the three groups (a warp that sits in a fence serves nobody else: 238 us).
+//   * Completion: a counter per (p, J), p >= 1, that counts the finished tiles among the three rows (p, J) depends on.  A
+//     finished tile of phase p < P - 1 adds one to the counters of its three dependents (gpu-scope release: the group's
+//     arrivals on the empty barrier ordered every thread's reductions before the control lane's fence); the control lane
+//     loads a dependent tile once its counter reads 3 tiles_x (one acquire load).  The control lane never blocks: it polls
+//     the dependency of the next slot and the empty barrier of the oldest stage in turn, so a tile is always published no
+//     matter what its group is waiting for, and slots are loaded in order.  Hence no deadlock, whatever the scheduling: the
+//     smallest unfinished slot of the grid has all its dependencies (smaller slots, lag >= 3) finished and published.
+//     lag puts every dependency about six grids earlier in slot order, so it is normally complete when it is asked for.
+//     The counters live in a caller-owned workspace that is all zero between launches: the last CTA to finish clears them.
+//   * Everything a tile reads comes through TMA (L2) or ld.global.cg; the exact test reads the staged tile (tile_exact): no
+//     plain global load may see an L1 line from an earlier phase.
+//   * The tile itself is villain_tile_pass_kernel's: three tensor boxes per colour tile, two per (dn)^2 tile (n0, n1 at the
+//     plaquette origin), a warp = one row pair x 32 column pairs.
+//
+// MEASURED (B200, L = 4096, one sweep per step; tools/kbench_wave.py, profiles/r2_wavefront_c5.txt).  The protocol does what it
+// was built for: with the phases up to 18 waves apart DRAM reads 273 - 287 MB per step (one read of the 268 MB state; the
+// three launches read 676 MB), beyond 22 waves the lines are gone from L2 before the next phase arrives (575 MB at 28, 850 MB
+// at 36: the reuse distance L2 holds is about half its 126 MB).  It is NOT faster: without a record 129 us per step at its
+// best lag against 129 us for the two colour-pass launches, with a record 182 against 164 us.  The colour tiles are bound by
+// instruction issue (224 thread-instructions per site-update, issue slots 66 - 77 % busy), not by DRAM, so halving the DRAM
+// traffic buys nothing until the tile itself is cheaper; the lag that keeps every group supplied (28 - 36 waves) is larger
+// than the lag L2 can hold (about 20); and the (dn)^2 tiles, two per group in flight with nothing to compute, wait on DRAM
+// latency.  The three launches therefore remain the default for big lattices; this entry point stays for what it is good
+// at (half the DRAM traffic and energy at equal time) and as the base for a cheaper tile.
+// ------------------------------------------------------------------------------------------
+struct WaveArgs {
+    int phases;               // P
+    int dn2;                  // 1: phase 0 is the sum (dn)^2 pass
+    int lag;                  // waves between consecutive phases of one tile row
+    int rows;                 // R = N / kTileRows
+    int tiles_x;              // N / kTileCols
+    int sweep_first;          // sweep (relative to a.sweep0) of the first colour phase
+    int chunk;                // slots drawn per ticket
+    unsigned rows_total;      // chains R
+    unsigned slots;           // (rows_total + (P - 1) lag) P tiles_x
+    int* progress;            // (P - 1) rows_total dependency counters (phases 1 .. P - 1), the count of finished CTAs, the slot ticket
+    double* state_out;        // state columns of the arriving state (first colour phase, dn2 phase) or nullptr
+    double* counter_out;      // ACCEPTED / ACCEPTANCE are added here, or nullptr
+};
+
+constexpr int kWaveGroups = 3, kWaveStages = 2, kWaveChunk = 2;
+constexpr int kWaveThreads = 256 * kWaveGroups + 32 * kWaveGroups;       // 24 sweeping warps + one control warp per group
+constexpr int kWaveSmemBytes = kWaveGroups * kWaveStages * kTileStageBytes + 2 * kWaveGroups * kWaveStages * 8;
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(kWaveThreads, 1) villain_tile_wave_kernel(const __grid_constant__ VillainArgs a,
+                                                                            const __grid_constant__ FilterConsts fc,
+                                                                            const __grid_constant__ CUtensorMap map_phi,
+                                                                            const __grid_constant__ CUtensorMap map_n,
+                                                                            const __grid_constant__ WaveArgs wv) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    // per group and stage: chain (-1: no more work), R, C, phase of the tile loaded into it; k (its row index within the phase)
+    __shared__ int tile_coord[kWaveGroups][kWaveStages][4];
+    __shared__ int tile_k[kWaveGroups][kWaveStages];
+    __shared__ int last_cta;
+    const int N = a.N, V = N * N;
+    const int tid = threadIdx.x;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tile_smem + kWaveGroups * kWaveStages * kTileStageBytes);
+    // full[g][s] = bars[2 (2 g + s)], empty[g][s] = bars[2 (2 g + s) + 1]
+
+    if (tid == 0) {
+        for (int i = 0; i < kWaveGroups * kWaveStages; ++i) {
+            mbar_init(&bars[2 * i], 1);          // full: the control lane's arrive (+ the bytes of the boxes)
+            mbar_init(&bars[2 * i + 1], 8);      // empty: one arrival per sweeping warp
+        }
+        fence_mbar_init();
+        last_cta = 0;
+    }
+    __syncthreads();
+    pdl_prologue();
+
+    if (tid >= 256 * kWaveGroups) {
+        // ---------------- the control warps: lane 0 of warp 24 + g serves group g ----------------
+        const int g = (tid - 256 * kWaveGroups) >> 5;
+        if ((tid & 31) == 0) {
+            const unsigned per_wave = (unsigned)(wv.phases * wv.tiles_x);
+            const int ready = 3 * wv.tiles_x;
+            int* ticket = wv.progress + (size_t)(wv.phases - 1) * wv.rows_total + 1;
+            unsigned next = 0, chunk_left = 0;                    // the slots this group has drawn and not yet decoded
+            unsigned sat_p = 0xffffffffu, sat_J = 0;              // the last (p, J) whose dependency counter was seen complete
+            unsigned loaded = 0, retired = 0;                     // tiles of this group whose loads were issued / whose stage was handed back
+            unsigned idle = 0;
+            unsigned char* stages = tile_smem + g * kWaveStages * kTileStageBytes;
+            uint64_t* gbar = bars + 2 * kWaveStages * g;
+            // the slot after the ones in the stages: decoded, and its dependency checked, while the group is busy sweeping -- when
+            // a stage comes back its loads go out at once
+            bool have = false, dep_ok = false, ended = false;
+            int n_chain = 0, n_R = 0, n_C = 0, n_p = 0, n_k = 0;
+            // a tile that was handed back and is not published yet (its stage is refilled first)
+            bool owe = false;
+            int o_chain = 0, o_p = 0, o_k = 0;
+            while (true) {
+                bool progress = false;
+                // (A) a free stage and a slot that may be loaded: issue its boxes
+                if (have && dep_ok && loaded - retired < (unsigned)kWaveStages) {
+                    const int stage = (int)(loaded & 1u);
+                    tile_coord[g][stage][0] = n_chain; tile_coord[g][stage][1] = n_R; tile_coord[g][stage][2] = n_C; tile_coord[g][stage][3] = n_p;
+                    tile_k[g][stage] = n_k;
+                    unsigned char* st = stages + stage * kTileStageBytes;
+                    if (wv.dn2 && n_p == 0) {
+                        // plaquettes (R .. R+15, C .. C+127): n0 of columns C .. C+128, n1 of rows R .. R+16
+                        mbar_expect_tx(&gbar[2 * stage], (uint32_t)(2 * kTileNBytes));
+                        tensor_box_3d(st + kTilePhiSlot, &map_n, n_C, n_R, 2 * n_chain, &gbar[2 * stage]);
+                        tensor_box_3d(st + kTilePhiSlot + kTileNSlot, &map_n, n_C, n_R, 2 * n_chain + 1, &gbar[2 * stage]);
+                    } else {
+                        mbar_expect_tx(&gbar[2 * stage], (uint32_t)(kTilePhiBytes + 2 * kTileNBytes));
+                        tensor_box_3d(st, &map_phi, n_C - 2, n_R - 1, n_chain, &gbar[2 * stage]);
+                        tensor_box_3d(st + kTilePhiSlot, &map_n, n_C - 4, n_R - 1, 2 * n_chain, &gbar[2 * stage]);
+                        tensor_box_3d(st + kTilePhiSlot + kTileNSlot, &map_n, n_C - 4, n_R - 1, 2 * n_chain + 1, &gbar[2 * stage]);
+                    }
+                    ++loaded; have = false; progress = true;
+                }
+                // (B) publish the tile that was handed back: the three tile rows of phase p + 1 that read it are k, k - 1, k - 2
+                // (mod R) in that phase's order
+                if (owe) {
+                    int* cnt = wv.progress + (size_t)o_p * wv.rows_total + (size_t)o_chain * wv.rows;
+                    // release: the group's arrivals ordered every thread's reductions before this fence.  (A (dn)^2 tile wrote
+                    // nothing; what its dependents must not overtake are its READS, and those were complete when its boxes landed.)
+                    if (!(wv.dn2 && o_p == 0)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        int kk = o_k - d;
+                        if (kk < 0) kk += wv.rows;
+                        asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(cnt + kk) : "memory");
+                    }
+                    owe = false; progress = true;
+                }
+                // (C) the oldest tile in the stages: handed back once the group's eight warps have arrived
+                if (retired < loaded) {
+                    const int stage = (int)(retired & 1u);
+                    if (mbar_try(&gbar[2 * stage + 1], (retired >> 1) & 1u)) {
+                        o_p = tile_coord[g][stage][3]; o_chain = tile_coord[g][stage][0]; o_k = tile_k[g][stage];
+                        owe = o_p + 1 < wv.phases;
+                        ++retired; progress = true;
+                        continue;                                              // refill the stage before anything else
+                    }
+                }
+                // (D) draw the next slot -- slots are handed out in order, kWaveChunk at a time, to whichever group asks: a group
+                // that gets cheap tiles, or a fast SM, simply comes back sooner -- and decode it
+                if (!have && !ended) {
+                    if (chunk_left == 0) {
+                        next = (unsigned)atomicAdd(ticket, wv.chunk);
+                        chunk_left = (unsigned)wv.chunk;
+                    }
+                    const unsigned sl = next++;
+                    --chunk_left;
+                    if (sl >= wv.slots) {
+                        ended = true;
+                    } else {
+                        const unsigned wave = sl / per_wave, rem = sl - wave * per_wave;
+                        const int pp = (int)(rem / (unsigned)wv.tiles_x), tx = (int)(rem - (unsigned)pp * (unsigned)wv.tiles_x);
+                        const long long J = (long long)wave - (long long)pp * wv.lag;
+                        if (J >= 0 && J < (long long)wv.rows_total) {            // (else: a slot of the ramp that falls outside the lattice)
+                            n_chain = (int)((unsigned)J / (unsigned)wv.rows); n_k = (int)((unsigned)J - (unsigned)n_chain * (unsigned)wv.rows);
+                            n_R = ((n_k + pp) % wv.rows) * kTileRows; n_C = tx * kTileCols; n_p = pp;
+                            have = true;
+                            dep_ok = pp == 0 || ((unsigned)pp == sat_p && (unsigned)J == sat_J);
+                        }
+                    }
+                    progress = true;
+                }
+                // (E) its dependency: the counter of (p, J) reads 3 tiles_x once the three rows it reads are complete
+                if (have && !dep_ok) {
+                    int seen;
+                    const int* cnt = wv.progress + (size_t)(n_p - 1) * wv.rows_total + (size_t)n_chain * wv.rows + n_k;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                    if (seen >= ready) {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        dep_ok = true; progress = true;
+                        sat_p = (unsigned)n_p; sat_J = (unsigned)n_chain * (unsigned)wv.rows + (unsigned)n_k;
+                    }
+                }
+                // (F) no slot left: once both stages are back, wake the group with the end marker
+                if (ended && !have && !owe && retired == loaded) {
+                    const int stage = (int)(loaded & 1u);
+                    tile_coord[g][stage][0] = -1;
+                    mbar_arrive(&gbar[2 * stage]);
+                    break;
+                }
+                if (progress) {
+                    idle = 0;
+                } else {
+                    __nanosleep(64);
+                    if (++idle > (1u << 25)) __trap();            // > 2 s without progress: fail, do not hang the GPU
+                }
+            }
+        }
+    } else {
+        // ---------------- the sweeping warps: group g, warp w8 of the group ----------------
+        const int g = tid >> 8, t = tid & 255, w8 = t >> 5, lane = t & 31;
+        unsigned char* stages = tile_smem + g * kWaveStages * kTileStageBytes;
+        uint64_t* gbar = bars + 2 * kWaveStages * g;
+        double action = 0.0, hk_of_sums = 0.0;
+        long long dn2 = 0;
+        int w0 = 0, w1 = 0, n_acc = 0, dirty = 0;               // dirty: 1 = dn2, 2 = action / wrapping, 4 = the counters hold something
+        float sum_A = 0.0f;
+        int chain_of_sums = -1;
+        // the warps add their partial sums to a chain's record when the group moves on to another chain
+        auto flush = [&]() {
+            if (dirty & 1) {
+                const long long v = warp_sum(dn2);
+                if (lane == 0) atomicAdd(wv.state_out + (long long)chain_of_sums * SVB_VOBS_COUNT + SVB_VOBS_SUM_DN2, (double)v);
+                dn2 = 0;
+            }
+            if (dirty & 2) {
+                const double va = warp_sum(action);
+                const int v0 = warp_sum_i32(w0), v1 = warp_sum_i32(w1);
+                if (lane == 0) {
+                    double* o = wv.state_out + (long long)chain_of_sums * SVB_VOBS_COUNT;
+                    atomicAdd(o + SVB_VOBS_ACTION, hk_of_sums * va);
+                    atomicAdd(o + SVB_VOBS_WRAP0, (double)v0);
+                    atomicAdd(o + SVB_VOBS_WRAP1, (double)v1);
+                }
+                action = 0.0; w0 = 0; w1 = 0;
+            }
+            if (dirty & 4) {
+                if (wv.counter_out) {
+                    const int vn = warp_sum_i32(n_acc);
+                    const float vs = warp_sum_f32(sum_A);
+                    if (lane == 0) {
+                        atomicAdd(wv.counter_out + (long long)chain_of_sums * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTED, (double)vn);
+                        atomicAdd(wv.counter_out + (long long)chain_of_sums * SVB_VOBS_COUNT + SVB_VOBS_ACCEPTANCE, (double)vs);
+                    }
+                }
+                n_acc = 0; sum_A = 0.0f;
+            }
+            dirty = 0;
+        };
+
+        for (int it = 0;; ++it) {
+            const int stage = it & 1;
+            mbar_wait(&gbar[2 * stage], (uint32_t)((it >> 1) & 1));
+            const int chain = tile_coord[g][stage][0];
+            if (chain < 0) break;
+            const int R = tile_coord[g][stage][1], C = tile_coord[g][stage][2], p = tile_coord[g][stage][3];
+            const bool is_dn2 = wv.dn2 && p == 0;
+            const int q = p - wv.dn2;                                  // colour phase: sweep q / 2, colour q % 2
+            const bool sums = wv.state_out != nullptr && q == 0;
+            if (chain != chain_of_sums) {
+                if (dirty) flush();
+                chain_of_sums = chain;
+                hk_of_sums = (a.kappa_chain ? a.kappa_chain[chain] : a.kappa) / 2;
+            }
+            const double half_kappa = hk_of_sums;
+            double* gphi = reinterpret_cast<double*>(a.phi) + chain * (long long)V;
+            int32_t* gn0 = a.n + chain * 2 * (long long)V;
+            unsigned char* st = stages + stage * kTileStageBytes;
+            double* P = reinterpret_cast<double*>(st);
+            int32_t* N0 = reinterpret_cast<int32_t*>(st + kTilePhiSlot);
+            int32_t* N1 = reinterpret_cast<int32_t*>(st + kTilePhiSlot + kTileNSlot);
+            const bool bottom = R + kTileRows == N, right = C + kTileCols == N;
+
+            if (is_dn2) {
+                if (bottom || right) {
+                    if (bottom && t < kTileCols) N1[kTileRows * kTileNCols + t] = __ldcg(gn0 + V + C + t);        // row N = row 0
+                    if (right && t >= 128 && t < 128 + kTileRows) N0[(t - 128) * kTileNCols + kTileCols] = __ldcg(gn0 + (R + t - 128) * N);
+                    asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
+                }
+                // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]); a thread: rows w8 and w8 + 8, four columns
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = w8 + 8 * h;
+                    const int4 m0 = *reinterpret_cast<const int4*>(N0 + i * kTileNCols + 4 * lane);
+                    const int hr = N0[i * kTileNCols + 4 * lane + 4];
+                    const int4 m1 = *reinterpret_cast<const int4*>(N1 + i * kTileNCols + 4 * lane);
+                    const int4 up = *reinterpret_cast<const int4*>(N1 + (i + 1) * kTileNCols + 4 * lane);
+                    const int d0 = (up.x - m1.x) - (m0.y - m0.x), d1 = (up.y - m1.y) - (m0.z - m0.y);
+                    const int d2 = (up.z - m1.z) - (m0.w - m0.z), d3 = (up.w - m1.w) - (hr - m0.w);
+                    dn2 += (long long)d0 * d0 + (long long)d1 * d1 + (long long)d2 * d2 + (long long)d3 * d3;
+                }
+                dirty |= 1;
+            } else {
+                const bool top = R == 0, left = C == 0;
+                if (top || bottom || left || right) {
+                    // the periodic wrap: what lies beyond the edge of the lattice arrived as zeros; patch it from the other side (L2)
+                    if (top && t < kTileCols) {
+                        P[2 + t] = __ldcg(gphi + (N - 1) * N + C + t);                                  // halo row R - 1 = row N - 1
+                        N0[4 + t] = __ldcg(gn0 + (N - 1) * N + C + t);
+                    }
+                    if (bottom && t >= 128 && t < 128 + kTileCols) P[(kTilePhiRows - 1) * kTilePhiCols + 2 + (t - 128)] = __ldcg(gphi + C + (t - 128));
+                    if (left && t < kTileRows) {
+                        P[(t + 1) * kTilePhiCols + 1] = __ldcg(gphi + (R + t) * N + N - 1);            // column C - 1 = column N - 1
+                        N1[(t + 1) * kTileNCols + 3] = __ldcg(gn0 + V + (R + t) * N + N - 1);
+                    }
+                    if (right && t >= 32 && t < 32 + kTileRows) P[(t - 31) * kTilePhiCols + 2 + kTileCols] = __ldcg(gphi + (R + t - 32) * N);   // column N = 0
+                    asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
+                }
+                const float hk2 = (float)(half_kappa * 1.4426950408889634);
+                const float hkA = 1.0001f * hk2 * fc.bA, hkB = 1.0001f * hk2 * fc.bB + 3.7e-5f;
+                const unsigned long long gc = a.chain0 + (unsigned long long)chain;
+                const unsigned long long gs = a.sweep0 + (unsigned long long)(wv.sweep_first + (q >> 1));
+                const int par = (w8 + q) & 1;
+                const int r = R + w8;
+                const int oA = r * N, oAm = ((r == 0) ? N - 1 : r - 1) * N, oB = oA + 8 * N, oBp = ((r + 9 == N) ? 0 : r + 9) * N;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jc = 2 * (lane + 32 * h);
+                    const int x1 = C + jc + par;
+                    const int xm1 = (x1 == 0) ? N - 1 : x1 - 1, xp1 = (x1 + 1 == N) ? 0 : x1 + 1;
+                    const uint32_t c0 = (uint32_t)(oA + x1);
+                    const Philox4 bits = philox_site_keys(a, gc, gs, c0);
+                    float4 rA, rB;
+                    if (sums) {
+                        rA = tile_site_residuals<true>(P, N0, N1, w8 + 1, jc, par, action, w0, w1);
+                        rB = tile_site_residuals<true>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
+                    } else {
+                        rA = tile_site_residuals<false>(P, N0, N1, w8 + 1, jc, par, action, w0, w1);
+                        rB = tile_site_residuals<false>(P, N0, N1, w8 + 9, jc, par, action, w0, w1);
+                    }
+                    stream_pair_decide<UNIT, false, true>(a, fc, gphi, gn0, V, oA, oAm, oA + N, oB, oB - N, oBp, x1, xm1, xp1, bits, c0, rA, rB, gc,
+                                                          gs, half_kappa, hk2, hkA, hkB, n_acc, sum_A, nullptr, P, N0, N1,
+                                                          (w8 + 1) * kTilePhiCols + jc + 4 + par);
+                }
+                dirty |= sums ? 6 : 4;
+            }
+            // this warp has read the stage and issued its reductions (the arrival releases them at CTA scope to the control lane)
+            if (bottom || right || R == 0 || C == 0) fence_proxy_async();      // the patches it wrote precede the stage's next TMA fill
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&gbar[2 * stage + 1]);
+        }
+        if (dirty) flush();
+    }
+    // the workspace is all zero between launches: the last CTA to get here clears it (every other CTA has read its last counter)
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        const size_t done_at = (size_t)(wv.phases - 1) * wv.rows_total;
+        const int before = atomicAdd(wv.progress + done_at, 1);
+        if (before == (int)gridDim.x - 1) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            last_cta = 1;
+        }
+    }
+    __syncthreads();
+    if (last_cta) {
+        const size_t total = (size_t)(wv.phases - 1) * wv.rows_total + 2;
+        for (size_t i = tid; i < total; i += kWaveThreads) wv.progress[i] = 0;
+    }
+}
+
+// ints of zeroed workspace svb_villain_sweep_wavefront needs for `sweeps` sweeps in one launch
+static long long villain_wave_workspace_ints(long long chains, int N, int sweeps, bool with_dn2) {
+    return (long long)((with_dn2 ? 1 : 0) + 2 * sweeps) * chains * (N / kTileRows) + 2;
+}
+
+// n_sweeps sweeps in place, one wavefront launch per group of sweeps that the workspace has counters for.
+static int launch_villain_tile_wave(const VillainArgs& a, double* obs_in, double* counters, int* progress, long long progress_ints,
+                                    cudaStream_t stream, const DeviceInfo& info) {
+    const bool unit = a.W == 1 && a.interval_n == 1;
+    auto kern = unit ? villain_tile_wave_kernel<true> : villain_tile_wave_kernel<false>;
+    static int per_sm_cache[2][64];
+    int per_sm = (info.device < 64) ? per_sm_cache[unit ? 1 : 0][info.device] : 0;
+    if (per_sm == 0) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWaveSmemBytes));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWaveThreads, kWaveSmemBytes));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "the tile wavefront kernel does not fit an SM");
+        if (info.device < 64) per_sm_cache[unit ? 1 : 0][info.device] = per_sm;
+    }
+    CUtensorMap map_phi, map_n;
+    const int rc = villain_tile_maps(a, map_phi, map_n);
+    if (rc) return rc;
+    const int rows = a.N / kTileRows, tiles_x = a.N / kTileCols;
+    const long long rows_total = a.chains * rows;
+    const long long tiles = rows_total * tiles_x;
+    // every CTA must be resident (a tile may wait for a tile of another CTA): one CTA per SM, three groups of sweeping warps each
+    long long grid = info.sm_count;
+    if (grid * kWaveGroups > tiles) grid = (tiles + kWaveGroups - 1) / kWaveGroups;
+    const long long vgrid = grid * kWaveGroups;
+    const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
+    int done = 0;
+    while (done < a.n_sweeps) {
+        const int dn2 = (done == 0 && obs_in) ? 1 : 0;
+        // as many sweeps per launch as the workspace has counters for (at least one)
+        long long fit = ((progress_ints - 2) / rows_total - dn2) / 2;
+        if (fit < 1) return fail(SVB_E_SHAPE, "svb_villain_sweep_wavefront: the workspace has %lld ints, one sweep needs %lld", progress_ints,
+                                 villain_wave_workspace_ints(a.chains, a.N, 1, dn2 != 0));
+        int sweeps = (int)((fit < (long long)(a.n_sweeps - done)) ? fit : (long long)(a.n_sweeps - done));
+        if (sweeps > 16) sweeps = 16;
+        WaveArgs wv;
+        wv.phases = dn2 + 2 * sweeps; wv.dn2 = dn2; wv.rows = rows; wv.tiles_x = tiles_x; wv.sweep_first = done;
+        const long long per_wave = (long long)wv.phases * tiles_x;
+        // every dependency about six grids (of groups) earlier in slot order: a group holds up to four slots (two stages, the one it
+        // has decoded ahead, the rest of its ticket) and a tile is published a microsecond after it is finished -- measured at
+        // L = 4096: 210 us per step at lag 14, 188 at 28, 183 at 36 (SVB_WAVE_LAG overrides).  Any lag >= 3 is correct.
+        const long long lag_min = 3;
+        long long lag = 3 + (6 * vgrid + per_wave - 1) / per_wave;
+        if (const char* e = getenv("SVB_WAVE_LAG")) lag = atoll(e);
+        if (lag < lag_min) lag = lag_min;
+        if (lag > 0x3fffffff) lag = 0x3fffffff;
+        wv.lag = (int)lag;
+        wv.chunk = kWaveChunk;
+        if (const char* e = getenv("SVB_WAVE_CHUNK")) wv.chunk = atoi(e) > 0 ? atoi(e) : 1;
+        const long long slots = (rows_total + (long long)(wv.phases - 1) * lag) * per_wave;
+        if (rows_total > 0x7fffffffLL || slots > 0xf0000000LL)
+            return fail(SVB_E_SHAPE, "svb_villain_sweep_wavefront: too many tiles for one launch (%lld slots)", slots);
+        wv.rows_total = (unsigned)rows_total; wv.slots = (unsigned)slots;
+        wv.progress = progress; wv.state_out = (done == 0) ? obs_in : nullptr; wv.counter_out = counters;
+        SVB_CUDA_TRY(launch_pdl(kern, (unsigned)grid, (unsigned)kWaveThreads, (size_t)kWaveSmemBytes, stream, a, fc, map_phi, map_n, wv));
+        done += sweeps;
+    }
     return 0;
 }

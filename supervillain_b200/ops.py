@@ -6,6 +6,7 @@ Nothing here computes on the CPU -- a missing library or device raises.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -249,12 +250,19 @@ class VillainOverlappedSweeps:
 
 
 class VillainInplaceSweeps:
-    """Back-to-back Philox sweeps of lattices beyond a CTA (config 5: L = 4096; any N that is a multiple of 16), IN PLACE by
-    colour passes (svb_villain_sweep_inplace): no workspace, only accepted proposals are written.  The `step` / `fence`
-    interface of `VillainOverlappedSweeps`, including the records of the arriving state (`obs_in`); the launches are ordinary
-    ones (two per sweep), so `fence` has nothing to do."""
+    """Back-to-back Philox sweeps of lattices beyond a CTA (config 5: L = 4096; any N that is a multiple of 16), IN PLACE:
+    no second copy of the state, only accepted proposals are written.  The `step` / `fence` interface of
+    `VillainOverlappedSweeps`, including the records of the arriving state (`obs_in`).
 
-    def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None):
+    launches='passes' (the default): one launch per colour pass and one over n for sum (dn)^2 (svb_villain_sweep_inplace).
+    launches='wavefront' (N a multiple of 128): ONE launch per step, the phases of the step following one another down the
+    lattice through L2 (svb_villain_sweep_wavefront) -- one DRAM read of the state per step instead of 2.5, but no faster on
+    a B200, where the colour passes are bound by instruction issue, not by DRAM; SVB_VILLAIN_STEP=wavefront
+    makes it the default for an A/B.  Identical fields either way.  `fused_sweeps`: how many sweeps of a multi-sweep step the
+    wavefront workspace has room to put in one launch."""
+
+    def __init__(self, phi, n, kappa, *, W=1, interval_phi=math.pi, interval_n=1, seed=0, chain0=0, kappa_chain=None,
+                 launches='auto', fused_sweeps=2):
         self.lib = _lib.load()
         self.chains, self.N = _fields_shape(phi, 'phi', 1)
         if self.N % 16 or phi.dtype != torch.float64 or int(interval_n) > 1:
@@ -267,8 +275,23 @@ class VillainInplaceSweeps:
         self.args = (float(kappa), self.p_kc, int(W), float(interval_phi), int(interval_n))
         self.seed, self.chain0 = int(seed) & (2**64 - 1), int(chain0)
         self._keep = (phi, n, kappa_chain)
-        self._fn = self.lib.svb_villain_sweep_inplace
         self._stream = torch.cuda.current_stream
+        if launches not in ('auto', 'wavefront', 'passes'):
+            raise ValueError("launches must be 'auto', 'wavefront' or 'passes'")
+        serves = self.N % 128 == 0 and 2 * self.chains < 2**31 - 1
+        if launches == 'wavefront' and not serves:
+            raise NotImplementedError('wavefront launches need N a multiple of 128')
+        if launches == 'auto':
+            launches = 'wavefront' if serves and os.environ.get('SVB_VILLAIN_STEP', 'passes') == 'wavefront' else 'passes'
+        self.launches = launches
+        if launches == 'wavefront':
+            ints = int(self.lib.svb_villain_wavefront_workspace(self.chains, self.N, max(1, int(fused_sweeps)), 1))
+            self.workspace = torch.zeros((ints,), dtype=torch.int32, device=phi.device)      # zero before first use; calls leave it zero
+            self._tail = (self.workspace.data_ptr(), ints)
+            self._fn = self.lib.svb_villain_sweep_wavefront
+        else:
+            self._tail = ()
+            self._fn = self.lib.svb_villain_sweep_inplace
 
     def fence(self):
         pass
@@ -277,7 +300,7 @@ class VillainInplaceSweeps:
         p_obs = None if obs is None else _dev(obs, 'obs', (torch.float64,), (self.chains, VOBS_COUNT))
         p_obs_in = None if obs_in is None else _dev(obs_in, 'obs_in', (torch.float64,), (self.chains, VOBS_COUNT))
         _lib.check(self._fn(self.p_phi, self.p_n, self.chains, self.N, *self.args, int(n_sweeps), self.seed, int(sweep0), self.chain0,
-                            p_obs, p_obs_in, self._stream().cuda_stream))
+                            p_obs, p_obs_in, *self._tail, self._stream().cuda_stream))
 
 
 class WorldlineOverlappedSweeps:

@@ -641,9 +641,13 @@ def test_overlapped_launch_protocol_soak(kind):
         assert int(steppers[i].epochs.min()) == steppers[i].epoch == K
 
 
-@pytest.mark.parametrize('N,chains,W,kappa', [(256, 3, 1, 0.5), (128, 5, 2, 0.3), (144, 2, 1, 0.4), (48, 7, 1, 0.6), (384, 1, 1, 0.8)])
-def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa):
-    """svb_villain_sweep_inplace (svb_villain_stream.cuh): one launch per colour pass, in place, only accepted proposals written.
+@pytest.mark.parametrize('N,chains,W,kappa,launches', [(256, 3, 1, 0.5, 'passes'), (128, 5, 2, 0.3, 'passes'), (144, 2, 1, 0.4, 'passes'),
+                                                        (48, 7, 1, 0.6, 'passes'), (384, 1, 1, 0.8, 'passes'),
+                                                        (256, 3, 1, 0.5, 'wavefront'), (128, 5, 2, 0.3, 'wavefront'),
+                                                        (384, 1, 1, 0.8, 'wavefront'), (128, 37, 1, 0.7, 'wavefront')])
+def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa, launches):
+    """svb_villain_sweep_inplace (svb_villain_stream.cuh): one launch per colour pass, in place, only accepted proposals written;
+    svb_villain_sweep_wavefront (launches = 'wavefront'): the same phases in ONE launch, following one another through L2.
     N a multiple of 128 runs on TMA tensor-staged tiles (tiles on the edge of the lattice patch the periodic wrap), any other
     multiple of 16 straight from global memory.  Fields identical to the C oracle; the records of the ARRIVING state (obs_in:
     action and wrapping from the first colour pass, sum (dn)^2 from a pass over n) complete the previous step's record, the
@@ -660,7 +664,8 @@ def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa):
         p, q = np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
         refs.append((p, q, np.concatenate([o[2] for o in out]), np.concatenate([o[3] for o in out])))
     phi, n = dev(phi0), dev(n0, torch.int32)
-    st = ops.VillainInplaceSweeps(phi, n, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc))
+    st = ops.VillainInplaceSweeps(phi, n, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc), launches=launches)
+    assert st.launches == launches
     rec = torch.full((K, chains, VOBS_COUNT), -7.0, dtype=torch.float64, device='cuda')
     scratch = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
     for k in range(K):
@@ -680,7 +685,10 @@ def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa):
     # the full record of the state after the sweeps, two sweeps fused into one call
     phi2, n2 = dev(phi0), dev(n0, torch.int32)
     full = torch.zeros((chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
-    ops.VillainInplaceSweeps(phi2, n2, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc)).step(0, 2, obs=full)
+    st2 = ops.VillainInplaceSweeps(phi2, n2, kappa, W=W, seed=seed, chain0=4, kappa_chain=dev(kc), launches=launches)
+    st2.step(0, 2, obs=full)
+    if launches == 'wavefront':
+        assert int(st.workspace.abs().sum()) == 0 and int(st2.workspace.abs().sum()) == 0      # every call leaves its counters zero
     p2, q2 = refs[1][0], refs[1][1]
     assert (n2.cpu().numpy() == q2).all() and (phi2.cpu().numpy() == p2).all()
     f = full.cpu().numpy()
@@ -688,12 +696,38 @@ def test_inplace_colour_passes_equal_the_c_oracle(N, chains, W, kappa):
     assert (f[:, VOBS_SUM_DN2] == (lat.d1(q2) ** 2).sum(axis=(-3, -2, -1))).all()
     assert (f[:, VOBS_ACCEPTED] == refs[0][2] + refs[1][2]).all()
     # the ensemble driver steps big lattices this way
-    if N == 256:
+    if N == 256 and launches == 'passes':
         S = svb.Villain(svb.Lattice2D(N), kappa)
         E = svb.BatchedEnsemble(S, chains, chain0=4).generate(K, NeighborhoodUpdate(S, seed=seed), start={'phi': phi0, 'n': n0}, kappa_chain=kc)
         assert (E.fields[1].cpu().numpy() == n_ref).all() and (E.fields[0].cpu().numpy() == p_ref).all()
         np.testing.assert_allclose(E.record[:, :K - 1, VOBS_ACTION].T, got[:K - 1, :, VOBS_ACTION], rtol=1e-13)
         np.testing.assert_allclose(E.record[:, K - 1, VOBS_ACTION], V.action(p_ref, n_ref, 1.0) * kc, rtol=1e-12)
+
+
+@pytest.mark.parametrize('N,chains,fused', [(128, 300, 1), (128, 64, 3), (512, 2, 2), (1024, 1, 1), (256, 9, 4)])
+def test_wavefront_launches_equal_colour_pass_launches(N, chains, fused):
+    """svb_villain_sweep_wavefront against svb_villain_sweep_inplace over a run of steps: fields identical after every step,
+    integer records identical, the action to summation order; `fused` sweeps of a multi-sweep step share one launch (its
+    colour phases chase one another through L2 as the two colours of one sweep do); hot and cold starts; kappa per chain."""
+    kappa, K = 0.6, 4
+    S = svb.Villain(svb.Lattice2D(N), kappa)
+    kc = torch.linspace(0.3, 1.1, chains, dtype=torch.float64, device='cuda')
+    for start in ('hot', 'cold'):
+        phi, n = svb.BatchedEnsemble(S, chains)._start(start, 5)
+        wphi, wn = phi.clone(), n.clone()
+        a = ops.VillainInplaceSweeps(phi, n, kappa, seed=8, chain0=2, kappa_chain=kc, launches='passes')
+        b = ops.VillainInplaceSweeps(wphi, wn, kappa, seed=8, chain0=2, kappa_chain=kc, launches='wavefront', fused_sweeps=fused)
+        ra = torch.zeros((K + 1, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+        rb = torch.zeros_like(ra)
+        for k in range(K):
+            a.step(fused * k, fused, obs=ra[k + 1], obs_in=ra[k])
+            b.step(fused * k, fused, obs=rb[k + 1], obs_in=rb[k])
+            assert torch.equal(phi, wphi) and torch.equal(n, wn), (start, k)
+        assert torch.equal(ra[:, :, 1:5], rb[:, :, 1:5])                                  # sum dn^2, wrapping, accepted
+        assert torch.allclose(ra[:, :, 0], rb[:, :, 0], rtol=1e-12, atol=0)
+        assert torch.allclose(ra[:, :, 5], rb[:, :, 5], rtol=1e-5, atol=0)
+        assert int(b.workspace.abs().sum()) == 0
+        assert float(ra[1:, :, 4].sum()) > 0
 
 
 def test_config5_full_size_bit_exact_against_c_oracle():
@@ -708,16 +742,30 @@ def test_config5_full_size_bit_exact_against_c_oracle():
     n0 = rng.integers(-2, 3, (1, 2, N, N))
     p_ref, n_ref, acc, accp = C.villain_sweep_philox(phi0, n0, kappa, n_sweeps=2, seed=seed, sweep0=3, chain0=1)
     assert acc[0] > 100000
-    phi, n = dev(phi0), dev(n0, torch.int32)
-    obs = torch.zeros((1, VOBS_COUNT), dtype=torch.float64, device='cuda')
-    ops.VillainInplaceSweeps(phi, n, kappa, seed=seed, chain0=1).step(3, 2, obs=obs)
-    assert torch.equal(n.cpu(), torch.from_numpy(n_ref).to(torch.int32)) and torch.equal(phi.cpu(), torch.from_numpy(p_ref))
-    rec = obs.cpu().numpy()
-    assert rec[0, VOBS_ACCEPTED] == acc[0]
-    np.testing.assert_allclose(rec[0, VOBS_ACCEPTANCE], accp[0], rtol=1e-5)
-    np.testing.assert_allclose(rec[0, VOBS_ACTION], float(V.action(p_ref, n_ref, kappa)[0]), rtol=1e-12)
-    assert rec[0, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum()
-    assert rec[0, VOBS_WRAP0] == n_ref[0, 0].sum() and rec[0, VOBS_WRAP1] == n_ref[0, 1].sum()
+    for launches in ('wavefront', 'passes'):
+        phi, n = dev(phi0), dev(n0, torch.int32)
+        obs = torch.zeros((1, VOBS_COUNT), dtype=torch.float64, device='cuda')
+        st = ops.VillainInplaceSweeps(phi, n, kappa, seed=seed, chain0=1, launches=launches)
+        assert st.launches == launches
+        st.step(3, 2, obs=obs)
+        assert torch.equal(n.cpu(), torch.from_numpy(n_ref).to(torch.int32)) and torch.equal(phi.cpu(), torch.from_numpy(p_ref)), launches
+        rec = obs.cpu().numpy()
+        assert rec[0, VOBS_ACCEPTED] == acc[0]
+        np.testing.assert_allclose(rec[0, VOBS_ACCEPTANCE], accp[0], rtol=1e-5)
+        np.testing.assert_allclose(rec[0, VOBS_ACTION], float(V.action(p_ref, n_ref, kappa)[0]), rtol=1e-12)
+        assert rec[0, VOBS_SUM_DN2] == (lat.d1(n_ref) ** 2).sum()
+        assert rec[0, VOBS_WRAP0] == n_ref[0, 0].sum() and rec[0, VOBS_WRAP1] == n_ref[0, 1].sum()
+    # the record protocol of a running ensemble at this size: the arriving state's columns from the wavefront's own phases
+    phi_w, n_w = dev(phi0), dev(n0, torch.int32)
+    stw = ops.VillainInplaceSweeps(phi_w, n_w, kappa, seed=seed, chain0=1, launches='wavefront')
+    recs = torch.zeros((3, 1, VOBS_COUNT), dtype=torch.float64, device='cuda')
+    stw.step(3, 1, obs=recs[0], obs_in=recs[2])
+    stw.step(4, 1, obs=recs[1], obs_in=recs[0])
+    assert torch.equal(n_w, n) and torch.equal(phi_w, phi)
+    r = recs.cpu().numpy()
+    assert r[0, 0, VOBS_ACCEPTED] + r[1, 0, VOBS_ACCEPTED] == acc[0]
+    assert r[2, 0, VOBS_SUM_DN2] == (lat.d1(n0) ** 2).sum() and r[2, 0, VOBS_WRAP0] == n0[0, 0].sum()
+    np.testing.assert_allclose(r[2, 0, VOBS_ACTION], float(V.action(phi0, n0, kappa)[0]), rtol=1e-12)
     # the swapping entry point (one sweep per call, the state may change buffer pairs)
     sw = ops.VillainSwappingSweeps(dev(phi0), dev(n0, torch.int32), kappa, seed=seed, chain0=1)
     sw.step(3, 1)
