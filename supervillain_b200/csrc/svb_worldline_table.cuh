@@ -37,38 +37,43 @@ constexpr int kWlTableSize = 5 * 2 * kWlTableS;    // delta_f in [-2, 2]
 // separately rounded link terms; the table holds fl(fl(delta_f / kappa) s), equal to a few ulp, so the integer comparison is
 // trusted only at distance >= 2 from the threshold and the exact path evaluates the reference's own expression.
 // OVERLAP: the launch takes part in the overlapped-launch protocol (svb_common.cuh, svb_worldline_sweep_overlapped).
-template <int MODE, int NT, int MINB, bool OVERLAP>
-__global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(const __grid_constant__ WorldlineArgs a) {
+// TM, STAGES: TM N threads per CTA and STAGES chains of shared memory.  (4, 1): a chain per CTA, the next one loaded when this
+// one has been stored.  (8, 2) (N = 64: config 3): twice the threads on a chain -- a thread owns ONE Philox block of four
+// plaquettes per colour -- and the next chain already in the other stage when this one is finished, so a CTA never waits for
+// a load: two CTAs of 16 warps per SM instead of four of 8, the same warps and the same shared memory.
+template <int MODE, int NT, int MINB, bool OVERLAP, int TM = 4, int STAGES = 1>
+__global__ void __launch_bounds__(TM * NT, MINB) worldline_smem_table_kernel(const __grid_constant__ WorldlineArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
-    constexpr int PER = VH / T;                                  // plaquettes per thread per colour (rows row8 + 8 q)
-    constexpr int QUADS = (PER + 3) / 4, QW = PER < 4 ? PER : 4; // Philox blocks per thread per colour, words used of each
+    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = TM * NT, NW = T / 32;
+    constexpr int GSTEP = TM / 4;                                // threads that share a column slot and a row8 split the Philox blocks
+    constexpr int PER = VH / (4 * NT);                           // plaquettes per (row8, column slot) per colour (rows row8 + 8 q)
+    constexpr int QUADS = (PER + 3) / 4, QW = PER < 4 ? PER : 4; // Philox blocks per (row8, column slot) per colour, words used of each
+    static_assert(QUADS % GSTEP == 0, "every thread owns the same number of Philox blocks");
     constexpr uint32_t bytes_m = 2 * V * sizeof(int32_t);
     constexpr uint32_t bytes_v = V * sizeof(int32_t);
     constexpr uint32_t stage_bytes = bytes_m + bytes_v;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int32_t* F0 = reinterpret_cast<int32_t*>(smem_raw);           // m_0 on arrival, f_0 during the sweeps
-    int32_t* F1 = F0 + V;
-    int32_t* sv = F1 + V;
-    WlTableEntry* table = reinterpret_cast<WlTableEntry*>(smem_raw + stage_bytes);
+    WlTableEntry* table = reinterpret_cast<WlTableEntry*>(smem_raw + STAGES * stage_bytes);
     long long* red = reinterpret_cast<long long*>(table + kWlTableSize);          // [NW][4] integer partial sums
     float* redA = reinterpret_cast<float*>(red + 4 * 32);                         // [NW]
     uint64_t* bar = reinterpret_cast<uint64_t*>(redA + 32);
     constexpr int kWriter = 32;
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) mbar_init(&bar[st], 1);
         fence_mbar_init();
     }
     if (OVERLAP) overlap_prologue(a.ov);
     __syncthreads();
     const bool want_obs = a.obs != nullptr;
 
-    auto issue_load = [&](long long chain, uint32_t seen) {
+    auto issue_load = [&](long long chain, uint32_t seen, int st) {
         if (OVERLAP) overlap_wait(a.ov, chain, seen);
-        mbar_expect_tx(bar, stage_bytes);
-        bulk_g2s(F0, a.m + chain * 2 * V, bytes_m, bar);
-        bulk_g2s(sv, a.v + chain * V, bytes_v, bar);
+        int32_t* dst = reinterpret_cast<int32_t*>(smem_raw + st * stage_bytes);
+        mbar_expect_tx(&bar[st], stage_bytes);
+        bulk_g2s(dst, a.m + chain * 2 * V, bytes_m, &bar[st]);
+        bulk_g2s(dst + 2 * V, a.v + chain * V, bytes_v, &bar[st]);
     };
     // acceptance table of one coupling: entry (delta_f, s) from the same fp64 expressions as the general path
     auto build_table = [&](double kappa) {
@@ -90,26 +95,37 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
     // 32 slots of ONE row (stride 2) collide pairwise -- a third of this kernel's shared-memory wavefronts were such replays.
     // (Any bijection gives the same chain: the draws are keyed by the site.)
     int row8, k;
+    const int tq = tid % (4 * NT), g_first = tid / (4 * NT);     // (row8, column slot) and the first Philox block of this thread
     if (HN >= 16) {
-        const int rest = tid >> 5;
-        row8 = 2 * (rest / (HN / 16)) + ((tid >> 4) & 1);
-        k = 16 * (rest % (HN / 16)) + (tid & 15);
+        const int rest = tq >> 5;
+        row8 = 2 * (rest / (HN / 16)) + ((tq >> 4) & 1);
+        k = 16 * (rest % (HN / 16)) + (tq & 15);
     } else {
-        row8 = tid / HN;
-        k = tid - row8 * HN;
+        row8 = tq / HN;
+        k = tq - row8 * HN;
     }
     long long chain = blockIdx.x;
-    if (tid == 0 && chain < a.chains) issue_load(chain, OVERLAP ? overlap_peek(a.ov, chain) : 0u);
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) {
+            const long long c = chain + (long long)st * gridDim.x;
+            if (c < a.chains) issue_load(c, OVERLAP ? overlap_peek(a.ov, c) : 0u, st);
+        }
+    }
     if (!a.kappa_chain) build_table(a.kappa);
 
     int it = 0;
     for (; chain < a.chains; chain += gridDim.x, ++it) {
-        const long long next = chain + gridDim.x;
+        const int stage = it % STAGES;
+        int32_t* F0 = reinterpret_cast<int32_t*>(smem_raw + stage * stage_bytes);     // m_0 on arrival, f_0 during the sweeps
+        int32_t* F1 = F0 + V;
+        int32_t* sv = F1 + V;
+        const long long next = chain + (long long)STAGES * gridDim.x;                 // the chain that takes this stage next
         uint32_t seen_next = 0;
         if (OVERLAP && tid == 0 && next < a.chains) seen_next = overlap_peek(a.ov, next);      // lands during the sweep
         const double kappa = a.kappa_chain ? a.kappa_chain[chain] : a.kappa;
         if (a.kappa_chain) build_table(kappa);          // the previous chain's last reader is behind two barriers
-        mbar_wait(bar, (uint32_t)(it & 1));
+        mbar_wait(&bar[stage], (uint32_t)((it / STAGES) & 1));
 
         // ---- m -> f = m - delta v, in place, four consecutive sites per step   (plaquette.py:53; compact.py delta,2 rows:
         //      (delta v)_0[x] = v[x] - v[x - e1],  (delta v)_1[x] = -(v[x] - v[x - e0]))
@@ -144,14 +160,26 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                 int32_t* pF0r = F0 + row8 * N + xp1;
                 int32_t* pv = sv + row8 * N + x1;
 #pragma unroll
-                for (int g = 0; g < QUADS; ++g) {
+                for (int gi = 0; gi < QUADS / GSTEP; ++gi) {
+                    const int g = GSTEP == 1 ? gi : g_first + GSTEP * gi;
                     const uint32_t c0 = (uint32_t)((row8 + 32 * g) * N + x1);                 // worldline_quad_counter
                     const Philox4 bits = philox_plaquette_keys(a, gc, gs, c0);
+                    // The plaquettes of a block lie eight rows apart: they share no link and no site, so their loads, decisions
+                    // and stores are independent.  Written as three phases over the block -- all loads, all decisions, all
+                    // stores -- the shared-memory latency of the four overlaps instead of adding up (the compiler cannot prove
+                    // by itself that a store of one does not alias a load of the next).
+                    int f0c[QW], f1d[QW], f0r[QW], f1c[QW];
 #pragma unroll
                     for (int wd = 0; wd < QW; ++wd) {
                         const int q = 4 * g + wd;
                         const int o = 8 * N * q;                                               // row row8 + 8 q
                         const int od = (q == PER - 1 && row8 == 7) ? (o + N - V) : (o + N);    // row below (wraps after the last)
+                        f0c[wd] = pF0c[o]; f1d[wd] = pF1c[od]; f0r[wd] = pF0r[o]; f1c[wd] = pF1c[o];
+                    }
+                    int dfs[QW], dvs[QW];
+                    unsigned okm = 0;
+#pragma unroll
+                    for (int wd = 0; wd < QW; ++wd) {
                         const uint32_t w = (wd == 0) ? bits.x : (wd == 1) ? bits.y : (wd == 2) ? bits.z : bits.w;
                         int df, dv;                                           // delta_f on the (+) links; change of v[x]
                         uint32_t f;
@@ -170,22 +198,20 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                             dv = (MODE == SVB_WL_VORTEX) ? ch : 0;
                             df = (MODE == SVB_WL_VORTEX) ? -ch : ch;
                         }
-                        const int f0c = pF0c[o], f1d = pF1c[od], f0r = pF0r[o], f1c = pF1c[o];
-                        const int sI = (f0c + f1d) - f0r - f1c + 2 * df;      // f1 + f2 - f3 - f4 + 2 delta_f
+                        const int sI = (f0c[wd] + f1d[wd]) - f0r[wd] - f1c[wd] + 2 * df;      // f1 + f2 - f3 - f4 + 2 delta_f
                         const int kk = df * sI;
-                        bool ok = true;
-                        float A = 1.0f;
-                        if (kk > 0) {                                         // dS > 0: a real Metropolis test
-                            // beyond the table A is below the edge entry of the same delta_f (dS grows with |s|): a uniform at
-                            // least 2 units above the edge threshold rejects for sure; otherwise (probability ~ A_edge) exact
-                            const int sC = min(max(sI, -kWlTableS), kWlTableS - 1);
-                            const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sC + kWlTableS];
-                            bool exact;
-                            if (sC == sI) {
-                                A = e.A;
-                                ok = f < e.thr;
-                                exact = (f - (e.thr - 2u)) <= 3u;            // f within 2 of thr: the bracket of u may touch A
-                            } else {
+                        // dS > 0 (kk > 0) is a real Metropolis test: ONE integer comparison with the tabulated threshold.  Everything
+                        // else about it -- s beyond the table, a uniform within two units of the threshold -- is the cold branch.
+                        const int sC = min(max(sI, -kWlTableS), kWlTableS - 1);
+                        const WlTableEntry e = table[(df + 2) * (2 * kWlTableS) + sC + kWlTableS];
+                        const bool test = kk > 0, in = sC == sI;
+                        bool ok = !test || (in && f < e.thr);
+                        float A = test ? e.A : 1.0f;
+                        if (test && (!in || (f - (e.thr - 2u)) <= 3u)) {
+                            bool exact = true;                                // f within 2 of thr: the bracket of u may touch A
+                            if (!in) {
+                                // beyond the table A is below the edge entry of the same delta_f (dS grows with |s|): a uniform at
+                                // least 2 units above the edge threshold rejects for sure; otherwise (probability ~ A_edge) exact
                                 A = fast_ex2f(-1.4426950408889634f * inv_kappa_f * (float)kk);
                                 ok = false;
                                 exact = f < e.thr + 2u || e.thr >= 0xFFFFFFFEu;
@@ -197,9 +223,9 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                                 } else {
                                     // coface_sum order: T(1,x) + T(1,x+e0) + T(0,x) + T(0,x+e1), T = ((0.5/kappa) c)((2 f) + c)
                                     const double Pp = __dmul_rn(half_inv_kappa, (double)df), Pm = __dmul_rn(half_inv_kappa, (double)(-df));
-                                    dS = __dadd_rn(__dmul_rn(Pm, (double)(2 * f1c - df)), __dmul_rn(Pp, (double)(2 * f1d + df)));
-                                    dS = __dadd_rn(dS, __dmul_rn(Pp, (double)(2 * f0c + df)));
-                                    dS = __dadd_rn(dS, __dmul_rn(Pm, (double)(2 * f0r - df)));
+                                    dS = __dadd_rn(__dmul_rn(Pm, (double)(2 * f1c[wd] - df)), __dmul_rn(Pp, (double)(2 * f1d[wd] + df)));
+                                    dS = __dadd_rn(dS, __dmul_rn(Pp, (double)(2 * f0c[wd] + df)));
+                                    dS = __dadd_rn(dS, __dmul_rn(Pm, (double)(2 * f0r[wd] - df)));
                                 }
                                 const double Ad = exp_clipped(-dS);
                                 LazyUniform lu;
@@ -212,12 +238,21 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
                         }
                         sum_A += A;
                         n_acc += ok ? 1 : 0;
-                        if (ok) {                                             // plaquette.py:91-101
-                            pF0c[o] = f0c + df;
-                            pF1c[od] = f1d + df;
-                            pF0r[o] = f0r - df;
-                            pF1c[o] = f1c - df;
-                            if (MODE != SVB_WL_COEXACT && dv != 0) atomicAdd(pv + o, dv);    // only this thread touches x in this pass
+                        okm |= ok ? (1u << wd) : 0u;
+                        dfs[wd] = df; dvs[wd] = dv;
+                    }
+#pragma unroll
+                    for (int wd = 0; wd < QW; ++wd) {
+                        const int q = 4 * g + wd;
+                        const int o = 8 * N * q;
+                        const int od = (q == PER - 1 && row8 == 7) ? (o + N - V) : (o + N);
+                        if (okm & (1u << wd)) {                               // plaquette.py:91-101
+                            const int df = dfs[wd];
+                            pF0c[o] = f0c[wd] + df;
+                            pF1c[od] = f1d[wd] + df;
+                            pF0r[o] = f0r[wd] - df;
+                            pF1c[o] = f1c[wd] - df;
+                            if (MODE != SVB_WL_COEXACT && dvs[wd] != 0) atomicAdd(pv + o, dvs[wd]);    // only this thread touches x in this pass
                         }
                     }
                 }
@@ -298,7 +333,7 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
             if (MODE != SVB_WL_COEXACT) bulk_s2g(a.v + chain * V, sv, bytes_v);
             bulk_commit();
             bulk_wait_read0();
-            if (next < a.chains) issue_load(next, seen_next);
+            if (next < a.chains) issue_load(next, seen_next, stage);
         }
     }
     if (tid == 0) bulk_wait0();
@@ -308,18 +343,18 @@ __global__ void __launch_bounds__(4 * NT, MINB) worldline_smem_table_kernel(cons
     }
 }
 
-template <int MODE, int NT, int MINB>
+template <int MODE, int NT, int MINB, int TM = 4, int STAGES = 1>
 static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, int sm_count) {
     const bool overlap = a.ov.epochs != nullptr;
-    auto kern = overlap ? worldline_smem_table_kernel<MODE, NT, MINB, true> : worldline_smem_table_kernel<MODE, NT, MINB, false>;
-    const size_t smem = (size_t)NT * NT * 3 * sizeof(int32_t) + kWlTableSize * sizeof(WlTableEntry) + 4 * 32 * sizeof(long long) +
-                        32 * sizeof(float) + 16;
+    auto kern = overlap ? worldline_smem_table_kernel<MODE, NT, MINB, true, TM, STAGES> : worldline_smem_table_kernel<MODE, NT, MINB, false, TM, STAGES>;
+    const size_t smem = (size_t)STAGES * NT * NT * 3 * sizeof(int32_t) + kWlTableSize * sizeof(WlTableEntry) + 4 * 32 * sizeof(long long) +
+                        32 * sizeof(float) + 8 * STAGES + 8;
     static int per_sm_cache[2] = {0, 0};
     int per_sm = per_sm_cache[overlap ? 1 : 0];
     if (per_sm == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TM * NT, smem));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "worldline table kernel does not fit an SM at N=%d", NT);
         per_sm_cache[overlap ? 1 : 0] = per_sm;
     }
@@ -327,7 +362,7 @@ static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, i
     if (grid > a.chains) grid = a.chains;
     if (overlap) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TM * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -335,7 +370,7 @@ static int launch_worldline_table(const WorldlineArgs& a, cudaStream_t stream, i
         SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
         return 0;
     }
-    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a);
+    kern<<<(unsigned)grid, TM * NT, smem, stream>>>(a);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
