@@ -168,12 +168,17 @@ __device__ __forceinline__ void fft_lines(double2* __restrict__ d, int n, int lo
         const int lh = DIF ? (log2n - 1 - st) : st;               // log2 of the butterfly half-span
         const int half = 1 << lh;
         const int tw_shift = log2n - 1 - lh;                      // twiddle e^{-2 pi i j / (2 half)} = tw[j << tw_shift]
+        // a thread's butterflies of a stage share j, hence the twiddle, while half <= blockDim.x: loaded once -- tw[j << tw_shift] is
+        // a strided read (up to 32 lanes on four banks), and per butterfly it made these kernels wait on shared memory
+        const bool fixed_w = half <= (int)blockDim.x && (blockDim.x & (blockDim.x - 1)) == 0;
+        const double2 w_fixed = tw[(threadIdx.x & (half - 1)) << tw_shift];
+#pragma unroll 4
         for (int b = threadIdx.x; b < lines * half_n; b += blockDim.x) {
             const int line = b >> (log2n - 1), bb = b & (half_n - 1);
             const int group = bb >> lh, j = bb & (half - 1);
             double2* p0 = d + line * line_stride + (group << (lh + 1)) + j;
             double2* p1 = p0 + half;
-            const double2 w = tw[j << tw_shift];
+            const double2 w = fixed_w ? w_fixed : tw[j << tw_shift];
             const double2 a = *p0, c = *p1;
             if (DIF) {
                 const double dr = a.x - c.x, di = a.y - c.y;
@@ -287,6 +292,206 @@ __global__ void __launch_bounds__(256) correlation_rows_inverse_kernel(long long
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The column transforms of the BIGGEST lattices (N >= 2048: config 5) in two steps.  A whole column of N complex128 in shared
+// memory leaves room for 8192 / N columns per CTA -- at N = 4096 two, so correlation_columns_kernel moves 32-byte pieces of a
+// row and runs at a tenth of the memory bandwidth.  Here the column index is split, r = 64 r1 + r2, k = k1 + n1 k2 (n1 = N / 64):
+//   A.  (r2 fixed; rows 64 r1 + r2, strided)  n1-point DFT over r1, then the twiddle W_N^{r2 k1}
+//   B.  (k1 fixed; 64 consecutive rows)       64-point DFT over r2 -- |.|^2 -- 64-point DFT over k2, then the twiddle W_N^{k1 r2'}
+//   A'. (r2' fixed; rows 64 p + r2')          n1-point DFT over k1: row 64 r1' + r2' holds displacement r' in natural order
+// three visits of the array instead of one, but every one of them in tiles of 32 columns: 512 contiguous bytes per row.
+// Forward transforms are decimation in frequency (natural in, bit-reversed out), the second ones decimation in time (bit-
+// reversed in, natural out), so position p of a block holds k1 = bitrev(p) and nothing is ever permuted.
+// ------------------------------------------------------------------------------------------
+constexpr int kSplitCols = 32, kSplitLog2Cols = 5, kSplitN2 = 64, kSplitLog2N2 = 6;
+
+// FFT of length n along the ROWS of a tile d[row][kSplitCols] (a thread per column and butterfly: conflict-free); tw = the
+// n / 2 twiddles of the length-n transform
+template <bool DIF, int LOG2W = kSplitLog2Cols>
+__device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, int log2n, const double2* __restrict__ tw) {
+    const int half_n = n >> 1;
+    constexpr int WIDTH = 1 << LOG2W;
+    for (int st = 0; st < log2n; ++st) {
+        const int lh = DIF ? (log2n - 1 - st) : st;
+        const int half = 1 << lh;
+        const int tw_shift = log2n - 1 - lh;
+#pragma unroll 4
+        for (int b = threadIdx.x; b < WIDTH * half_n; b += blockDim.x) {
+            const int c = b & (WIDTH - 1), bb = b >> LOG2W;
+            const int group = bb >> lh, j = bb & (half - 1);
+            double2* p0 = d + (((group << (lh + 1)) + j) << LOG2W) + c;
+            double2* p1 = p0 + (half << LOG2W);
+            const double2 w = tw[j << tw_shift];
+            const double2 a = *p0, q = *p1;
+            if (DIF) {
+                const double dr = a.x - q.x, di = a.y - q.y;
+                *p0 = make_double2(a.x + q.x, a.y + q.y);
+                *p1 = make_double2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+            } else {
+                const double tr = q.x * w.x - q.y * w.y, ti = q.x * w.y + q.y * w.x;
+                *p0 = make_double2(a.x + tr, a.y + ti);
+                *p1 = make_double2(a.x - tr, a.y - ti);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The ROW transforms of the same lattices, split the same way inside a row held in shared memory: position r = 64 r1 + r2 of
+// the row is element (r1, r2) of an n1 x 64 tile, so step A is a transform down the tile's rows (a thread per column:
+// conflict-free, twiddles broadcast) and step B one of 64 contiguous elements per line (a warp per line).  The 4096-point
+// transform with strided twiddles it replaces ran at a seventh of this.  W_N^{t}, t = r2 k1 < 4096, comes from two tables of 64:
+// W_N^t = W_N^{64 (t >> 6)} W_N^{t & 63}.  FIRST: s from the field, A, twiddle, B, written in the mixed order (p, q) <-> k =
+// bitrev(p) + n1 bitrev(q) that every later pass works in; !FIRST: B', twiddle, A', scaling -- natural order out.
+template <typename real, int KIND, bool FIRST>
+__global__ void __launch_bounds__(256) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
+                                                                     double scale, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n1 = 1 << log2n1;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][64]: the row
+    double2* tw1 = d + N;                                               // n1 / 2 twiddles of the n1-point transform
+    double2* tw2 = tw1 + (n1 > 1 ? n1 / 2 : 1);                         // 32 twiddles of the 64-point transform
+    double2* th = tw2 + kSplitN2 / 2;                                   // W_N^{64 a}, a < 64
+    double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
+    fft_twiddles(tw1, n1);
+    fft_twiddles(tw2, kSplitN2);
+    for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)((i * kSplitN2) & (N - 1)) / (double)N, &sn, &cs);
+        th[i] = make_double2(cs, sn);
+        sincospi(-2.0 * (double)i / (double)N, &sn, &cs);
+        tl[i] = make_double2(cs, sn);
+    }
+    const long long V = (long long)N * N, items = chains * N;
+    auto twiddle = [&](int i) {                                         // d[p][r2] *= W_N^{r2 bitrev(p)}
+        const int p = i >> kSplitLog2N2, r2 = i & (kSplitN2 - 1);
+        const int t = r2 * (int)(__brev((unsigned)p) >> (32 - log2n1));
+        const double2 a = th[t >> kSplitLog2N2], b = tl[t & (kSplitN2 - 1)], v = d[i];
+        const double wr = a.x * b.x - a.y * b.y, wi = a.x * b.y + a.y * b.x;
+        d[i] = make_double2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+    };
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / N;
+        const int x0 = (int)(item - chain * N);
+        double2* o = out + chain * V + (long long)x0 * N;
+        __syncthreads();
+        if (FIRST) {
+            const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+            for (int x1 = threadIdx.x; x1 < N; x1 += blockDim.x) {
+                const long long at = (long long)x0 * N + x1;
+                if (KIND == SVB_CORR_WINDING) {
+                    const long long i0 = (long long)((x0 + 1) & (N - 1)) * N + x1, i1 = (long long)x0 * N + ((x1 + 1) & (N - 1));
+                    d[x1] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
+                } else {
+                    double sn, cs;
+                    const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[at]) / (double)W : (double)g[at];
+                    sincos(ang, &sn, &cs);
+                    d[x1] = make_double2(cs, sn);
+                }
+            }
+            __syncthreads();
+            fft_tile_rows<true, kSplitLog2N2>(d, n1, log2n1, tw1);
+            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
+            __syncthreads();
+            fft_lines<true>(d, kSplitN2, kSplitLog2N2, n1, kSplitN2, tw2);
+            for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = d[i];
+        } else {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) d[i] = o[i];
+            __syncthreads();
+            fft_lines<false>(d, kSplitN2, kSplitLog2N2, n1, kSplitN2, tw2);
+            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
+            __syncthreads();
+            fft_tile_rows<false, kSplitLog2N2>(d, n1, log2n1, tw1);
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const double2 v = d[i];
+                o[i] = make_double2(v.x * scale, v.y * scale);
+            }
+        }
+    }
+}
+
+// visits A (FIRST: DIF over r1, then W_N^{r2 bitrev(p)}) and A' (!FIRST: DIT over k1): a tile = (chain, r2, 32 columns)
+template <bool FIRST>
+__global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n1 = 1 << log2n1;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][32]
+    double2* tw = d + (size_t)n1 * kSplitCols;                          // n1 / 2 twiddles of the n1-point transform
+    double2* tq = tw + n1 / 2;                                          // n1 twiddles W_N^{r2 k1(p)}
+    fft_twiddles(tw, n1);
+    const long long V = (long long)N * N;
+    const int col_blocks = N / kSplitCols;
+    const long long items = chains * kSplitN2 * col_blocks;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / (kSplitN2 * col_blocks);
+        const int rem = (int)(item - chain * (kSplitN2 * col_blocks));
+        const int r2 = rem / col_blocks, c0 = (rem - r2 * col_blocks) * kSplitCols;
+        double2* o = out + chain * V + (long long)r2 * N + c0;
+        __syncthreads();
+        if (FIRST)
+            for (int p = threadIdx.x; p < n1; p += blockDim.x) {
+                const int k1 = (int)(__brev((unsigned)p) >> (32 - log2n1));
+                double sn, cs;
+                sincospi(-2.0 * (double)((r2 * k1) & (N - 1)) / (double)N, &sn, &cs);
+                tq[p] = make_double2(cs, sn);
+            }
+        for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) {
+            const int r1 = i >> kSplitLog2Cols, c = i & (kSplitCols - 1);
+            d[i] = o[(long long)r1 * kSplitN2 * N + c];
+        }
+        __syncthreads();
+        fft_tile_rows<FIRST>(d, n1, log2n1, tw);
+        for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) {
+            const int r1 = i >> kSplitLog2Cols, c = i & (kSplitCols - 1);
+            double2 v = d[i];
+            if (FIRST) {
+                const double2 w = tq[r1];
+                v = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+            }
+            o[(long long)r1 * kSplitN2 * N + c] = v;
+        }
+    }
+}
+
+// visit B: a tile = (chain, p, 32 columns) = 64 consecutive rows: DIF over r2, |.|^2, DIT over k2, W_N^{bitrev(p) r2'}
+__global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64][32]
+    double2* tw = d + (size_t)kSplitN2 * kSplitCols;                    // 32 twiddles of the 64-point transform
+    double2* tq = tw + kSplitN2 / 2;                                    // 64 twiddles W_N^{k1 r2'}
+    fft_twiddles(tw, kSplitN2);
+    const long long V = (long long)N * N;
+    const int n1 = 1 << log2n1, col_blocks = N / kSplitCols;
+    const long long items = chains * n1 * col_blocks;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / (n1 * col_blocks);
+        const int rem = (int)(item - chain * (n1 * col_blocks));
+        const int p = rem / col_blocks, c0 = (rem - p * col_blocks) * kSplitCols;
+        const int k1 = (int)(__brev((unsigned)p) >> (32 - log2n1));
+        double2* o = out + chain * V + (long long)p * kSplitN2 * N + c0;
+        __syncthreads();
+        for (int r = threadIdx.x; r < kSplitN2; r += blockDim.x) {
+            double sn, cs;
+            sincospi(-2.0 * (double)((k1 * r) & (N - 1)) / (double)N, &sn, &cs);
+            tq[r] = make_double2(cs, sn);
+        }
+        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) d[i] = o[(long long)(i >> kSplitLog2Cols) * N + (i & (kSplitCols - 1))];
+        __syncthreads();
+        fft_tile_rows<true>(d, kSplitN2, kSplitLog2N2, tw);
+        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
+            const double2 v = d[i];
+            d[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
+        }
+        __syncthreads();
+        fft_tile_rows<false>(d, kSplitN2, kSplitLog2N2, tw);
+        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
+            const int r = i >> kSplitLog2Cols;
+            const double2 v = d[i], w = tq[r];
+            o[(long long)r * N + (i & (kSplitCols - 1))] = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+        }
+    }
+}
+
 }  // namespace svb
 
 using namespace svb;
@@ -313,14 +518,64 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const long long row_items = chains * (N / R), col_items = chains * (N / C);
     const long long cap_rows = (long long)per_sm_rows * sms, cap_cols = (long long)per_sm_cols * sms;
     double2* o = reinterpret_cast<double2*>(out);
-    k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
-                                                                                         log2n, W, R, o);
-    SVB_CUDA_TRY(cudaGetLastError());
-    correlation_columns_kernel<<<(unsigned)(col_items < cap_cols ? col_items : cap_cols), 256, smem_cols, st>>>(chains, N, log2n, C, log2c, o);
-    SVB_CUDA_TRY(cudaGetLastError());
+    // whole lines in shared memory while at least eight columns fit a CTA; beyond (N >= 2048) every transform in two steps,
+    // r = 64 r1 + r2 (SVB_CORR_SPLIT_MIN_N lowers the threshold, for tests of the split at sizes that can be checked element by
+    // element)
+    int split_min = 2048;
+    if (const char* e = getenv("SVB_CORR_SPLIT_MIN_N")) split_min = atoi(e);
+    const bool split = N >= split_min && N >= 2 * kSplitN2;
     const double V = (double)N * (double)N;
-    correlation_rows_inverse_kernel<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(chains, N, log2n, R,
-                                                                                                                     1.0 / (V * V), o);
+    const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
+    const size_t smem_rsplit = ((size_t)N + (n1_rows > 1 ? n1_rows / 2 : 1) + kSplitN2 / 2 + 2 * kSplitN2) * sizeof(double2);
+    auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
+    auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
+    long long cap_rsplit = 0;
+    if (split) {
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kr1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
+        int per_sm = 0;
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr1, 256, smem_rsplit));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the split row kernels", N);
+        cap_rsplit = (long long)per_sm * sms;
+        const long long items = chains * N;
+        kr1<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), 256, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
+                                                                                           log2n1_rows, W, 1.0, o);
+    } else {
+        k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
+                                                                                             log2n, W, R, o);
+    }
+    SVB_CUDA_TRY(cudaGetLastError());
+    if (split) {
+        const int log2n1 = log2n - kSplitLog2N2, n1 = 1 << log2n1;
+        const size_t smem_outer = ((size_t)n1 * kSplitCols + n1 / 2 + n1) * sizeof(double2);
+        const size_t smem_inner = ((size_t)kSplitN2 * kSplitCols + kSplitN2 / 2 + kSplitN2) * sizeof(double2);
+        SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
+        SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inner));
+        int per_sm_outer = 0, per_sm_inner = 0;
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_outer, correlation_split_outer_kernel<true>, 256, smem_outer));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_inner, correlation_split_inner_kernel, 256, smem_inner));
+        if (per_sm_outer < 1 || per_sm_inner < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the split column kernels", N);
+        const long long outer_items = chains * kSplitN2 * (N / kSplitCols), inner_items = chains * n1 * (N / kSplitCols);
+        const long long cap_outer = (long long)per_sm_outer * sms, cap_inner = (long long)per_sm_inner * sms;
+        correlation_split_outer_kernel<true><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(chains, N, log2n1, o);
+        SVB_CUDA_TRY(cudaGetLastError());
+        correlation_split_inner_kernel<<<(unsigned)(inner_items < cap_inner ? inner_items : cap_inner), 256, smem_inner, st>>>(chains, N, log2n1, o);
+        SVB_CUDA_TRY(cudaGetLastError());
+        correlation_split_outer_kernel<false><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(chains, N, log2n1, o);
+        SVB_CUDA_TRY(cudaGetLastError());
+    } else {
+        correlation_columns_kernel<<<(unsigned)(col_items < cap_cols ? col_items : cap_cols), 256, smem_cols, st>>>(chains, N, log2n, C, log2c, o);
+        SVB_CUDA_TRY(cudaGetLastError());
+    }
+    if (split) {
+        const long long items = chains * N;
+        kr2<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), 256, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
+                                                                                           log2n1_rows, W, 1.0 / (V * V), o);
+    } else {
+        correlation_rows_inverse_kernel<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(chains, N, log2n, R,
+                                                                                                                         1.0 / (V * V), o);
+    }
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }

@@ -196,6 +196,28 @@ def test_fft_correlators_match_the_reference_formula(N):
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('N', [128, 256, 1024])
+def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
+    """The column transforms of the biggest lattices (N >= 2048) run in two steps, r = 64 r1 + r2 (correlation_split_*_kernel).
+    With the threshold lowered the same kernels serve sizes that can be compared element by element with the restated
+    Lattice.correlation (compact.py:465-536): n1 = N / 64 = 2, 4 and 16 rows per outer transform, 1e-12."""
+    monkeypatch.setenv('SVB_CORR_SPLIT_MIN_N', '128')
+    rng = np.random.default_rng(N + 1)
+    chains = 3 if N <= 256 else 1
+    phi = rng.uniform(-7, 7, (chains, 1, N, N))
+    n = rng.integers(-3, 4, (chains, 2, N, N))
+    Cs = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    Cw = ops.correlation('winding', torch.from_numpy(n).to(torch.int32).cuda()).cpu().numpy()
+    monkeypatch.setenv('SVB_CORR_SPLIT_MIN_N', '1000000')
+    whole = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    for c in range(chains):
+        s = np.exp(1j * phi[c, 0])
+        np.testing.assert_allclose(Cs[c], lat.correlation(s, s), rtol=0, atol=1e-12)
+        dn = lat.d1(n[c])[0].astype(np.float64)
+        np.testing.assert_allclose(Cw[c], lat.correlation(dn, dn), rtol=0, atol=1e-12 * max(1.0, np.abs(dn).max() ** 2))
+    np.testing.assert_allclose(Cs, whole, rtol=0, atol=1e-13)
+
+
 def test_fft_correlator_of_a_config5_lattice_properties():
     """L = 4096 (config 5), too large to compare element by element in a test: size-independent properties of
     Lattice.correlation instead -- C[0] = mean |s|^2 = 1 for a spin field, C[-r] = conj(C[r]), sum_r C[r] = N^2 |mean s|^2 ...
