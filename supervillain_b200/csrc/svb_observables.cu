@@ -8,6 +8,7 @@
 // non-power-of-two lattices (exact to rounding), a shared-memory FFT for N = 16, 32, 64, and a three-launch FFT for
 // power-of-two lattices up to N = 4096.
 
+#include <type_traits>
 #include "svb_common.cuh"
 
 namespace svb {
@@ -308,7 +309,8 @@ constexpr int kSplitCols = 32, kSplitLog2Cols = 5, kSplitN2 = 64, kSplitLog2N2 =
 // FFT of length n along the ROWS of a tile d[row][kSplitCols] (a thread per column and butterfly: conflict-free); tw = the
 // n / 2 twiddles of the length-n transform
 template <bool DIF, int LOG2W = kSplitLog2Cols>
-__device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, int log2n, const double2* __restrict__ tw) {
+__device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, int log2n, const double2* __restrict__ tw,
+                                              int row_stride = (1 << LOG2W)) {
     const int half_n = n >> 1;
     constexpr int WIDTH = 1 << LOG2W;
     for (int st = 0; st < log2n; ++st) {
@@ -319,8 +321,8 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
         for (int b = threadIdx.x; b < WIDTH * half_n; b += blockDim.x) {
             const int c = b & (WIDTH - 1), bb = b >> LOG2W;
             const int group = bb >> lh, j = bb & (half - 1);
-            double2* p0 = d + (((group << (lh + 1)) + j) << LOG2W) + c;
-            double2* p1 = p0 + (half << LOG2W);
+            double2* p0 = d + ((group << (lh + 1)) + j) * row_stride + c;
+            double2* p1 = p0 + half * row_stride;
             const double2 w = tw[j << tw_shift];
             const double2 a = *p0, q = *p1;
             if (DIF) {
@@ -337,6 +339,87 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
     }
 }
 
+// The 64-point transforms of the split (every one of them at N = 4096) as TWO radix-8 passes with the butterflies of a pass in
+// registers: a radix-2 stage costs about 18 instructions per element and a shared-memory round trip, three of them in registers
+// cost a third of that.  Position p = 8 a + b.  Decimation in frequency: DFT8 over a (stride 8) for every b, twiddle
+// W_64^{a b}, DFT8 over b -- position p then holds frequency (p >> 3) + 8 (p & 7) (digit reversal in base 8, fft64_freq).
+// Decimation in time takes that order back to the natural one: DFT8 over b, the same twiddle, DFT8 over a.
+__device__ __forceinline__ int fft64_freq(int p) { return ((p & 7) << 3) | (p >> 3); }
+__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(const double2 a, const double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(const double2 a, const double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(const double2 z) { return make_double2(z.y, -z.x); }                 // z (-i)
+// X[k] = sum_n x[n] e^{-2 pi i n k / 8}, natural order in and out
+__device__ __forceinline__ void dft8(double2 (&x)[8]) {
+    constexpr double S = 0.70710678118654752440;
+    const double2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
+    const double2 b0 = csub(x[0], x[4]), t1 = csub(x[1], x[5]), t2 = csub(x[2], x[6]), t3 = csub(x[3], x[7]);
+    const double2 b1 = make_double2((t1.x + t1.y) * S, (t1.y - t1.x) * S);                                      // w
+    const double2 b2 = mul_mi(t2);                                                                              // w^2 = -i
+    const double2 b3 = make_double2((t3.y - t3.x) * S, -(t3.x + t3.y) * S);                                     // w^3
+    const double2 c0 = cadd(a0, a2), c1 = cadd(a1, a3), d0 = csub(a0, a2), d1 = mul_mi(csub(a1, a3));
+    const double2 e0 = cadd(b0, b2), e1 = cadd(b1, b3), f0 = csub(b0, b2), f1 = mul_mi(csub(b1, b3));
+    x[0] = cadd(c0, c1); x[2] = cadd(d0, d1); x[4] = csub(c0, c1); x[6] = csub(d0, d1);
+    x[1] = cadd(e0, e1); x[3] = cadd(f0, f1); x[5] = csub(e0, e1); x[7] = csub(f0, f1);
+}
+// 64-point transforms of 2^lanes_log2 independent lines: element (line, position) at d[line * lane_stride + position * pos_stride];
+// w64[t] = e^{-2 pi i t / 64}.  Consecutive threads take consecutive lines.
+// `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
+// DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
+struct NoScale {};
+template <bool DIF, class Scale = NoScale>
+__device__ __forceinline__ void fft64(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
+                                      const double2* __restrict__ w64, Scale scale = Scale()) {
+    constexpr bool SCALED = !std::is_same<Scale, NoScale>::value;
+    const int items = 8 << lanes_log2, lmask = (1 << lanes_log2) - 1;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool strided = DIF ? pass == 0 : pass == 1;       // DFT8 over a (positions 8 j + g) or over b (positions 8 g + j)
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {
+            const int g = i >> lanes_log2, lane = i & lmask;
+            const int p0 = strided ? g : 8 * g, dp = strided ? 8 : 1;
+            double2* base = d + lane * lane_stride + p0 * pos_stride;
+            const int step = dp * pos_stride;
+            double2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = base[j * step];
+            if constexpr (SCALED && !DIF) {
+                if (pass == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = cmul(x[j], scale(lane, p0 + j * dp));
+                }
+            }
+            dft8(x);
+            if (pass == 0 && g != 0) {
+#pragma unroll
+                for (int k = 1; k < 8; ++k) x[k] = cmul(x[k], w64[g * k]);
+            }
+            if constexpr (SCALED && DIF) {
+                if (pass == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] = cmul(x[k], scale(lane, p0 + k * dp));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) base[k * step] = x[k];
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void fft64_twiddles(double2* w64) {
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)k / 64.0, &sn, &cs);
+        w64[k] = make_double2(cs, sn);
+    }
+}
+// the frequency that position p of an n1-point transform of the split holds: radix-8 passes at n1 = 64, radix-2 stages otherwise
+__device__ __forceinline__ int split_freq(int p, int log2n1) {
+    return log2n1 == 6 ? fft64_freq(p) : (int)(__brev((unsigned)p) >> (32 - log2n1));
+}
+
 // The ROW transforms of the same lattices, split the same way inside a row held in shared memory: position r = 64 r1 + r2 of
 // the row is element (r1, r2) of an n1 x 64 tile, so step A is a transform down the tile's rows (a thread per column:
 // conflict-free, twiddles broadcast) and step B one of 64 contiguous elements per line (a warp per line).  The 4096-point
@@ -344,17 +427,18 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
 // W_N^t = W_N^{64 (t >> 6)} W_N^{t & 63}.  FIRST: s from the field, A, twiddle, B, written in the mixed order (p, q) <-> k =
 // bitrev(p) + n1 bitrev(q) that every later pass works in; !FIRST: B', twiddle, A', scaling -- natural order out.
 template <typename real, int KIND, bool FIRST>
-__global__ void __launch_bounds__(256) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
+__global__ void __launch_bounds__(512) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
                                                                      double scale, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n1 = 1 << log2n1;
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][64]: the row
-    double2* tw1 = d + N;                                               // n1 / 2 twiddles of the n1-point transform
-    double2* tw2 = tw1 + (n1 > 1 ? n1 / 2 : 1);                         // 32 twiddles of the 64-point transform
-    double2* th = tw2 + kSplitN2 / 2;                                   // W_N^{64 a}, a < 64
+    constexpr int RS = kSplitN2 + 1;                                    // row stride of the tile: lines a bank group apart
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][64 (+1)]: the row
+    double2* tw1 = d + (size_t)n1 * RS;                                 // n1 / 2 twiddles of the n1-point transform
+    double2* w64 = tw1 + (n1 > 1 ? n1 / 2 : 1);                         // W_64^t, t < 64
+    double2* th = w64 + kSplitN2;                                       // W_N^{64 a}, a < 64
     double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
     fft_twiddles(tw1, n1);
-    fft_twiddles(tw2, kSplitN2);
+    fft64_twiddles(w64);
     for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
         double sn, cs;
         sincospi(-2.0 * (double)((i * kSplitN2) & (N - 1)) / (double)N, &sn, &cs);
@@ -363,12 +447,30 @@ __global__ void __launch_bounds__(256) correlation_rows_split_kernel(const real*
         tl[i] = make_double2(cs, sn);
     }
     const long long V = (long long)N * N, items = chains * N;
-    auto twiddle = [&](int i) {                                         // d[p][r2] *= W_N^{r2 bitrev(p)}
+    auto pad = [&](int i) { return i + (i >> kSplitLog2N2); };          // element i = 64 r1 + r2 of the row in the padded tile
+    auto twiddle = [&](int i) {                                         // d[p][r2] *= W_N^{r2 k1(p)}
         const int p = i >> kSplitLog2N2, r2 = i & (kSplitN2 - 1);
-        const int t = r2 * (int)(__brev((unsigned)p) >> (32 - log2n1));
-        const double2 a = th[t >> kSplitLog2N2], b = tl[t & (kSplitN2 - 1)], v = d[i];
-        const double wr = a.x * b.x - a.y * b.y, wi = a.x * b.y + a.y * b.x;
-        d[i] = make_double2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+        const int t = r2 * split_freq(p, log2n1);
+        const double2 w = cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
+        d[pad(i)] = cmul(d[pad(i)], w);
+    };
+    // the n1-point transforms down the tile (one per r2) together with the twiddle W_N^{r2 k1(p)} between the two steps
+    auto tw_of = [&](int r2, int p) {
+        const int t = r2 * fft64_freq(p);
+        return cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
+    };
+    auto outer = [&](bool dif) {
+        if (log2n1 == 6) {
+            if (dif) fft64<true>(d, RS, 1, kSplitLog2N2, w64, tw_of); else fft64<false>(d, RS, 1, kSplitLog2N2, w64, tw_of);
+        } else if (dif) {
+            fft_tile_rows<true, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
+            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
+            __syncthreads();
+        } else {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
+            __syncthreads();
+            fft_tile_rows<false, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
+        }
     };
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long chain = item / N;
@@ -381,29 +483,25 @@ __global__ void __launch_bounds__(256) correlation_rows_split_kernel(const real*
                 const long long at = (long long)x0 * N + x1;
                 if (KIND == SVB_CORR_WINDING) {
                     const long long i0 = (long long)((x0 + 1) & (N - 1)) * N + x1, i1 = (long long)x0 * N + ((x1 + 1) & (N - 1));
-                    d[x1] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
+                    d[pad(x1)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
                 } else {
                     double sn, cs;
                     const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[at]) / (double)W : (double)g[at];
                     sincos(ang, &sn, &cs);
-                    d[x1] = make_double2(cs, sn);
+                    d[pad(x1)] = make_double2(cs, sn);
                 }
             }
             __syncthreads();
-            fft_tile_rows<true, kSplitLog2N2>(d, n1, log2n1, tw1);
-            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
-            __syncthreads();
-            fft_lines<true>(d, kSplitN2, kSplitLog2N2, n1, kSplitN2, tw2);
-            for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = d[i];
+            outer(true);
+            fft64<true>(d, 1, RS, log2n1, w64);                         // 64 contiguous elements per line, a thread per line and group
+            for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = d[pad(i)];
         } else {
-            for (int i = threadIdx.x; i < N; i += blockDim.x) d[i] = o[i];
+            for (int i = threadIdx.x; i < N; i += blockDim.x) d[pad(i)] = o[i];
             __syncthreads();
-            fft_lines<false>(d, kSplitN2, kSplitLog2N2, n1, kSplitN2, tw2);
-            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
-            __syncthreads();
-            fft_tile_rows<false, kSplitLog2N2>(d, n1, log2n1, tw1);
+            fft64<false>(d, 1, RS, log2n1, w64);
+            outer(false);
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double2 v = d[i];
+                const double2 v = d[pad(i)];
                 o[i] = make_double2(v.x * scale, v.y * scale);
             }
         }
@@ -418,7 +516,9 @@ __global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long 
     double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][32]
     double2* tw = d + (size_t)n1 * kSplitCols;                          // n1 / 2 twiddles of the n1-point transform
     double2* tq = tw + n1 / 2;                                          // n1 twiddles W_N^{r2 k1(p)}
+    double2* w64 = tq + n1;                                             // W_64^t, t < 64
     fft_twiddles(tw, n1);
+    fft64_twiddles(w64);
     const long long V = (long long)N * N;
     const int col_blocks = N / kSplitCols;
     const long long items = chains * kSplitN2 * col_blocks;
@@ -430,7 +530,7 @@ __global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long 
         __syncthreads();
         if (FIRST)
             for (int p = threadIdx.x; p < n1; p += blockDim.x) {
-                const int k1 = (int)(__brev((unsigned)p) >> (32 - log2n1));
+                const int k1 = split_freq(p, log2n1);
                 double sn, cs;
                 sincospi(-2.0 * (double)((r2 * k1) & (N - 1)) / (double)N, &sn, &cs);
                 tq[p] = make_double2(cs, sn);
@@ -440,7 +540,8 @@ __global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long 
             d[i] = o[(long long)r1 * kSplitN2 * N + c];
         }
         __syncthreads();
-        fft_tile_rows<FIRST>(d, n1, log2n1, tw);
+        if (log2n1 == 6) fft64<FIRST>(d, kSplitCols, 1, kSplitLog2Cols, w64);
+        else fft_tile_rows<FIRST>(d, n1, log2n1, tw);
         for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) {
             const int r1 = i >> kSplitLog2Cols, c = i & (kSplitCols - 1);
             double2 v = d[i];
@@ -457,9 +558,9 @@ __global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long 
 __global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64][32]
-    double2* tw = d + (size_t)kSplitN2 * kSplitCols;                    // 32 twiddles of the 64-point transform
-    double2* tq = tw + kSplitN2 / 2;                                    // 64 twiddles W_N^{k1 r2'}
-    fft_twiddles(tw, kSplitN2);
+    double2* w64 = d + (size_t)kSplitN2 * kSplitCols;                   // W_64^t, t < 64
+    double2* tq = w64 + kSplitN2;                                       // 64 twiddles W_N^{k1 r2'}
+    fft64_twiddles(w64);
     const long long V = (long long)N * N;
     const int n1 = 1 << log2n1, col_blocks = N / kSplitCols;
     const long long items = chains * n1 * col_blocks;
@@ -467,7 +568,7 @@ __global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long 
         const long long chain = item / (n1 * col_blocks);
         const int rem = (int)(item - chain * (n1 * col_blocks));
         const int p = rem / col_blocks, c0 = (rem - p * col_blocks) * kSplitCols;
-        const int k1 = (int)(__brev((unsigned)p) >> (32 - log2n1));
+        const int k1 = split_freq(p, log2n1);
         double2* o = out + chain * V + (long long)p * kSplitN2 * N + c0;
         __syncthreads();
         for (int r = threadIdx.x; r < kSplitN2; r += blockDim.x) {
@@ -477,13 +578,13 @@ __global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long 
         }
         for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) d[i] = o[(long long)(i >> kSplitLog2Cols) * N + (i & (kSplitCols - 1))];
         __syncthreads();
-        fft_tile_rows<true>(d, kSplitN2, kSplitLog2N2, tw);
+        fft64<true>(d, kSplitCols, 1, kSplitLog2Cols, w64);
         for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
             const double2 v = d[i];
             d[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
         }
         __syncthreads();
-        fft_tile_rows<false>(d, kSplitN2, kSplitLog2N2, tw);
+        fft64<false>(d, kSplitCols, 1, kSplitLog2Cols, w64);
         for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
             const int r = i >> kSplitLog2Cols;
             const double2 v = d[i], w = tq[r];
@@ -526,19 +627,21 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const bool split = N >= split_min && N >= 2 * kSplitN2;
     const double V = (double)N * (double)N;
     const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
-    const size_t smem_rsplit = ((size_t)N + (n1_rows > 1 ? n1_rows / 2 : 1) + kSplitN2 / 2 + 2 * kSplitN2) * sizeof(double2);
+    const size_t smem_rsplit = ((size_t)n1_rows * (kSplitN2 + 1) + (n1_rows > 1 ? n1_rows / 2 : 1) + 3 * kSplitN2) * sizeof(double2);
     auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
     auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
     long long cap_rsplit = 0;
+    int rows_threads = 256;                                       // (512, an item of a radix-8 pass per thread at N = 4096: 1039 against 860 us)
+    if (const char* e = getenv("SVB_CORR_ROWS_THREADS")) rows_threads = atoi(e);
     if (split) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
         int per_sm = 0;
-        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr1, 256, smem_rsplit));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr1, rows_threads, smem_rsplit));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the split row kernels", N);
         cap_rsplit = (long long)per_sm * sms;
         const long long items = chains * N;
-        kr1<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), 256, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
+        kr1<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                            log2n1_rows, W, 1.0, o);
     } else {
         k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
@@ -547,8 +650,8 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     SVB_CUDA_TRY(cudaGetLastError());
     if (split) {
         const int log2n1 = log2n - kSplitLog2N2, n1 = 1 << log2n1;
-        const size_t smem_outer = ((size_t)n1 * kSplitCols + n1 / 2 + n1) * sizeof(double2);
-        const size_t smem_inner = ((size_t)kSplitN2 * kSplitCols + kSplitN2 / 2 + kSplitN2) * sizeof(double2);
+        const size_t smem_outer = ((size_t)n1 * kSplitCols + n1 / 2 + n1 + kSplitN2) * sizeof(double2);
+        const size_t smem_inner = ((size_t)kSplitN2 * kSplitCols + 2 * kSplitN2) * sizeof(double2);
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_inner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inner));
@@ -570,7 +673,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     }
     if (split) {
         const long long items = chains * N;
-        kr2<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), 256, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
+        kr2<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                            log2n1_rows, W, 1.0 / (V * V), o);
     } else {
         correlation_rows_inverse_kernel<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(chains, N, log2n, R,

@@ -15,6 +15,7 @@ lib = sys.argv[4] if len(sys.argv) > 4 else 'supervillain_b200/libsvb200.so'
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
 line_of = {}
+matched = []
 for f in os.listdir(tmp):
     if not f.endswith('sm_100a.cubin'):
         continue
@@ -23,7 +24,15 @@ for f in os.listdir(tmp):
     for l in out.split('\n'):
         m = re.match(r'\s*\.section\s+\.text\.(\S+),', l)
         if m:
-            active = pat in m.group(1)
+            # ONE function only: a pattern that matches several instantiations of a kernel would mix their line tables
+            # (addresses are offsets within a function) -- the first match is taken, the others are reported
+            hit = pat in m.group(1)
+            if hit and matched and m.group(1) != matched[0]:
+                print(f'# note: pattern also matches {m.group(1)[:100]} (ignored: give a longer pattern to select it)')
+                hit = False
+            if hit and not matched:
+                matched.append(m.group(1))
+            active = hit
             continue
         if not active:
             continue
