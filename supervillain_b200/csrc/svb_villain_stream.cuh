@@ -809,10 +809,12 @@ __global__ void __launch_bounds__(256, 3) villain_tile_pass_kernel(const __grid_
     __syncthreads();
     pdl_prologue();
     auto issue = [&](long long t, int stage) {
-        const long long chain = t / tiles_per_chain;
-        const int tile = (int)(t - chain * tiles_per_chain);
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int R = ty * kTileRows, C = tx * kTileCols;
+        // (32-bit arithmetic: the tiles of a call are fewer than 2^32 -- a 64-bit division by one thread cost this kernel 6 % of
+        // its issue slots, every other thread of the warp sitting it out)
+        const unsigned tu = (unsigned)t, tpc = (unsigned)tiles_per_chain;
+        const unsigned chain = tu / tpc, tile = tu - chain * tpc;
+        const unsigned ty = tile / (unsigned)tiles_x, tx = tile - ty * (unsigned)tiles_x;
+        const int R = (int)ty * kTileRows, C = (int)tx * kTileCols;
         tile_coord[stage][0] = (int)chain; tile_coord[stage][1] = R; tile_coord[stage][2] = C;
         unsigned char* st = tile_smem + stage * kTileStageBytes;
         mbar_expect_tx(&bar[stage], (uint32_t)(kTilePhiBytes + 2 * kTileNBytes));
@@ -1102,6 +1104,7 @@ static int launch_villain_tile_passes(const VillainArgs& a, double* obs_in, doub
     const int rc = villain_tile_maps(a, map_phi, map_n);
     if (rc) return rc;
     const long long tiles = (long long)(a.N / kTileCols) * (a.N / kTileRows) * a.chains;
+    if (tiles + 2LL * per_sm * info.sm_count > 0xffffffffLL) return fail(SVB_E_SHAPE, "the tile pass kernel indexes its tiles with 32 bits (%lld)", tiles);
     long long grid = (long long)per_sm * info.sm_count;
     if (grid > tiles) grid = tiles;
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
