@@ -973,13 +973,20 @@ static int villain_tile_maps(const VillainArgs& a, CUtensorMap& map_phi, CUtenso
 constexpr int kDn2Rows = 32, kDn2BoxRows = kDn2Rows + 1, kDn2BoxCols = kTileCols + 4;
 constexpr int kDn2BoxBytes = kDn2BoxRows * kDn2BoxCols * 4;                            // 17424
 constexpr int kDn2BoxSlot = (kDn2BoxBytes + 127) / 128 * 128;
-constexpr int kDn2Stages = 3, kDn2StageBytes = 2 * kDn2BoxSlot;
+#ifndef SVB_DN2_STAGES
+/* two CTAs of 256 threads per SM with three stages each (config-5 step 161.4 us); one CTA per SM with six stages, five tiles
+ * in flight: 164.2 us with 256 threads, 164.7 us with 512 */
+#define SVB_DN2_STAGES 3
+#define SVB_DN2_THREADS 256
+#define SVB_DN2_MINB 2
+#endif
+constexpr int kDn2Stages = SVB_DN2_STAGES, kDn2StageBytes = 2 * kDn2BoxSlot, kDn2Threads = SVB_DN2_THREADS, kDn2Warps = kDn2Threads / 32;
 constexpr int kDn2SmemBytes = kDn2Stages * kDn2StageBytes + 64;
 
-__global__ void __launch_bounds__(256, 2) villain_tile_dn2_kernel(const __grid_constant__ CUtensorMap map_n, const int32_t* __restrict__ n,
+__global__ void __launch_bounds__(kDn2Threads, SVB_DN2_MINB) villain_tile_dn2_kernel(const __grid_constant__ CUtensorMap map_n, const int32_t* __restrict__ n,
                                                                   long long chains, int N, double* __restrict__ state_out) {
     extern __shared__ __align__(128) unsigned char dn2_smem[];
-    const int tid = threadIdx.x, w8 = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
     uint64_t* bar = reinterpret_cast<uint64_t*>(dn2_smem + kDn2Stages * kDn2StageBytes);
     const int tiles_x = N / kTileCols, tiles_y = N / kDn2Rows, tiles_per_chain = tiles_x * tiles_y;
     const long long tiles = (long long)tiles_per_chain * chains;
@@ -1031,10 +1038,10 @@ __global__ void __launch_bounds__(256, 2) villain_tile_dn2_kernel(const __grid_c
             if (right && tid >= 128 && tid < 128 + kDn2Rows) N0[(tid - 128) * kDn2BoxCols + kTileCols] = gn0[(long long)(R + tid - 128) * N];   // column N = 0
             __syncthreads();
         }
-        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]); a thread: rows w8 + 8 h, four columns
+        // (dn)[x] = (n1[x+e0] - n1[x]) - (n0[x+e1] - n0[x]); a thread: rows warp + kDn2Warps h, four columns
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int i = w8 + 8 * h;
+        for (int h = 0; h < kDn2Rows / kDn2Warps; ++h) {
+            const int i = wrp + kDn2Warps * h;
             const int4 m0 = *reinterpret_cast<const int4*>(N0 + i * kDn2BoxCols + 4 * lane);
             const int hr = N0[i * kDn2BoxCols + 4 * lane + 4];
             const int4 m1 = *reinterpret_cast<const int4*>(N1 + i * kDn2BoxCols + 4 * lane);
@@ -1068,7 +1075,7 @@ static int launch_villain_tile_dn2(const int32_t* n, long long chains, int N, do
     if (per_sm == 0) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tile_dn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDn2SmemBytes));
         SVB_CUDA_TRY(cudaFuncSetAttribute(villain_tile_dn2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, villain_tile_dn2_kernel, 256, kDn2SmemBytes));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, villain_tile_dn2_kernel, kDn2Threads, kDn2SmemBytes));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "the (dn)^2 tile kernel does not fit an SM");
         if (info.device < 64) per_sm_cache[info.device] = per_sm;
     }
@@ -1083,7 +1090,7 @@ static int launch_villain_tile_dn2(const int32_t* n, long long chains, int N, do
     const long long tiles = (long long)(N / kTileCols) * (N / kDn2Rows) * chains;
     long long grid = (long long)per_sm * info.sm_count;
     if (grid > tiles) grid = tiles;
-    SVB_CUDA_TRY(launch_pdl(villain_tile_dn2_kernel, (unsigned)grid, 256, (size_t)kDn2SmemBytes, stream, map_n, n, chains, N, state_out));
+    SVB_CUDA_TRY(launch_pdl(villain_tile_dn2_kernel, (unsigned)grid, (unsigned)kDn2Threads, (size_t)kDn2SmemBytes, stream, map_n, n, chains, N, state_out));
     return 0;
 }
 
