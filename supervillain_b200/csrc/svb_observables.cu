@@ -71,85 +71,179 @@ __global__ void __launch_bounds__(256) correlation_kernel(const real* __restrict
     }
 }
 
+// 64-point transforms (the two-step transforms of the big lattices below, and both dimensions of an L = 64 lattice) as TWO radix-8 passes with the butterflies of a pass in
+// registers: a radix-2 stage costs about 18 instructions per element and a shared-memory round trip, three of them in registers
+// cost a third of that.  Position p = 8 a + b.  Decimation in frequency: DFT8 over a (stride 8) for every b, twiddle
+// W_64^{a b}, DFT8 over b -- position p then holds frequency (p >> 3) + 8 (p & 7) (digit reversal in base 8, fft64_freq).
+// Decimation in time takes that order back to the natural one: DFT8 over b, the same twiddle, DFT8 over a.
+__device__ __forceinline__ int fft64_freq(int p) { return ((p & 7) << 3) | (p >> 3); }
+__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(const double2 a, const double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(const double2 a, const double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(const double2 z) { return make_double2(z.y, -z.x); }                 // z (-i)
+// X[k] = sum_n x[n] e^{-2 pi i n k / 8}, natural order in and out
+__device__ __forceinline__ void dft8(double2 (&x)[8]) {
+    constexpr double S = 0.70710678118654752440;
+    const double2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
+    const double2 b0 = csub(x[0], x[4]), t1 = csub(x[1], x[5]), t2 = csub(x[2], x[6]), t3 = csub(x[3], x[7]);
+    const double2 b1 = make_double2((t1.x + t1.y) * S, (t1.y - t1.x) * S);                                      // w
+    const double2 b2 = mul_mi(t2);                                                                              // w^2 = -i
+    const double2 b3 = make_double2((t3.y - t3.x) * S, -(t3.x + t3.y) * S);                                     // w^3
+    const double2 c0 = cadd(a0, a2), c1 = cadd(a1, a3), d0 = csub(a0, a2), d1 = mul_mi(csub(a1, a3));
+    const double2 e0 = cadd(b0, b2), e1 = cadd(b1, b3), f0 = csub(b0, b2), f1 = mul_mi(csub(b1, b3));
+    x[0] = cadd(c0, c1); x[2] = cadd(d0, d1); x[4] = csub(c0, c1); x[6] = csub(d0, d1);
+    x[1] = cadd(e0, e1); x[3] = cadd(f0, f1); x[5] = csub(e0, e1); x[7] = csub(f0, f1);
+}
+// X[k] = sum_n x[n] e^{-2 pi i n k / 4}, natural order in and out
+__device__ __forceinline__ void dft4(double2 (&x)[4]) {
+    const double2 c0 = cadd(x[0], x[2]), c1 = cadd(x[1], x[3]), d0 = csub(x[0], x[2]), d1 = mul_mi(csub(x[1], x[3]));
+    x[0] = cadd(c0, c1); x[1] = cadd(d0, d1); x[2] = csub(c0, c1); x[3] = csub(d0, d1);
+}
+template <int R> __device__ __forceinline__ void dft_r(double2 (&x)[R]);
+template <> __device__ __forceinline__ void dft_r<8>(double2 (&x)[8]) { dft8(x); }
+template <> __device__ __forceinline__ void dft_r<4>(double2 (&x)[4]) { dft4(x); }
+
+// Transforms of length RA RB (64 = 8 x 8, 32 = 8 x 4, 16 = 4 x 4) of 2^lanes_log2 independent lines as two passes with the
+// butterflies of a pass in registers: position p = RB a + b; DFT_RA over a (stride RB), twiddle W^{a b}, DFT_RB over b
+// (decimation in frequency), or the two passes in the opposite order (decimation in time: takes the mixed order back to
+// the natural one).  Element (line, position) at d[line * lane_stride + position * pos_stride]; wn[t] = e^{-2 pi i t / (RA RB)}.
+// Consecutive threads take consecutive lines.
+// `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
+// DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
+struct NoScale {};
+template <bool DIF, int RA, int RB, class Scale = NoScale>
+__device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
+                                       const double2* __restrict__ wn, Scale scale = Scale()) {
+    constexpr bool SCALED = !std::is_same<Scale, NoScale>::value;
+    const int lmask = (1 << lanes_log2) - 1;
+    auto pass_a = [&](bool first) {                               // RA-point transforms over a, one per (line, b)
+        for (int i = threadIdx.x; i < (RB << lanes_log2); i += blockDim.x) {
+            const int g = i >> lanes_log2, lane = i & lmask;
+            double2* base = d + lane * lane_stride + g * pos_stride;
+            const int step = RB * pos_stride;
+            double2 x[RA];
+#pragma unroll
+            for (int j = 0; j < RA; ++j) x[j] = base[j * step];
+            dft_r<RA>(x);
+            if (first && g != 0) {                                // (first only in a DIF transform; a scale never applies here)
+#pragma unroll
+                for (int k = 1; k < RA; ++k) x[k] = cmul(x[k], wn[g * k]);
+            }
+#pragma unroll
+            for (int k = 0; k < RA; ++k) base[k * step] = x[k];
+        }
+        __syncthreads();
+    };
+    auto pass_b = [&](bool first) {                               // RB-point transforms over b, one per (line, a)
+        for (int i = threadIdx.x; i < (RA << lanes_log2); i += blockDim.x) {
+            const int g = i >> lanes_log2, lane = i & lmask;
+            double2* base = d + lane * lane_stride + RB * g * pos_stride;
+            double2 x[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) x[j] = base[j * pos_stride];
+            if constexpr (SCALED && !DIF) {
+                if (first) {
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) x[j] = cmul(x[j], scale(lane, RB * g + j));
+                }
+            }
+            dft_r<RB>(x);
+            if (first && g != 0) {
+#pragma unroll
+                for (int k = 1; k < RB; ++k) x[k] = cmul(x[k], wn[g * k]);
+            }
+            if constexpr (SCALED && DIF) {
+                if (!first) {
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) x[k] = cmul(x[k], scale(lane, RB * g + k));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RB; ++k) base[k * pos_stride] = x[k];
+        }
+        __syncthreads();
+    };
+    if (DIF) { pass_a(true); pass_b(false); } else { pass_b(true); pass_a(false); }
+}
+template <bool DIF, class Scale = NoScale>
+__device__ __forceinline__ void fft64(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
+                                      const double2* __restrict__ w64, Scale scale = Scale()) {
+    fft_rr<DIF, 8, 8, Scale>(d, pos_stride, lane_stride, lanes_log2, w64, scale);
+}
+template <int NN>
+__device__ __forceinline__ void fft_rr_twiddles(double2* wn) {
+    for (int k = threadIdx.x; k < NN; k += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)k / (double)NN, &sn, &cs);
+        wn[k] = make_double2(cs, sn);
+    }
+}
+__device__ __forceinline__ void fft64_twiddles(double2* w64) {
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)k / 64.0, &sn, &cs);
+        w64[k] = make_double2(cs, sn);
+    }
+}
+// the frequency that position p of an n1-point transform of the split holds: radix-8 passes at n1 = 64, radix-2 stages otherwise
+__device__ __forceinline__ int split_freq(int p, int log2n1) {
+    return log2n1 == 6 ? fft64_freq(p) : (int)(__brev((unsigned)p) >> (32 - log2n1));
+}
+
 // ------------------------------------------------------------------------------------------
 // The same correlators by FFT for power-of-two lattices that fit shared memory (N = 16, 32, 64), the reference's own route
 // (compact.py:465-536):  sum_x conj(s[x]) s[x - r] = N^-2 DFT[ |DFT s|^2 ](r), so C = N^-4 fft2(|fft2 s|^2).
-// Two radix-2 transforms per dimension out of shared memory: decimation in frequency (natural order in, bit-reversed out),
-// the pointwise |.|^2 in bit-reversed order, then decimation in time (bit-reversed in, natural out) -- no permutation pass.
+// Two transforms per dimension out of shared memory: decimation in frequency (natural order in, mixed order out), the
+// pointwise |.|^2 in that order, then decimation in time (mixed order in, natural out) -- no permutation pass.
 // O(N^2 log N) per chain instead of O(N^4): 8192 chains of 32^2 take 6.4 ms by direct summation.
 // ------------------------------------------------------------------------------------------
-template <int NT, bool ROWS, bool DIF>
-__device__ __forceinline__ void fft_pass(double* __restrict__ re, double* __restrict__ im, const double* __restrict__ twr,
-                                         const double* __restrict__ twi) {
-    constexpr int N = NT, HALF = N / 2;
-    for (int st = 0; (1 << st) < N; ++st) {
-        const int half = DIF ? (HALF >> st) : (1 << st);
-        const int tw_step = HALF / half;                          // twiddle e^{-2 pi i j / (2 half)} = tw[j * tw_step]
-        for (int b = threadIdx.x; b < N * HALF; b += blockDim.x) {
-            int line, bb;
-            if (ROWS) { line = b / HALF; bb = b - line * HALF; }   // lanes walk along a row
-            else { bb = b / N; line = b - bb * N; }               // lanes walk across columns: contiguous addresses
-            const int group = bb / half, j = bb - group * half;
-            const int i0 = group * 2 * half + j, i1 = i0 + half;
-            const int a = ROWS ? line * N + i0 : i0 * N + line;
-            const int c = ROWS ? line * N + i1 : i1 * N + line;
-            const double wr = twr[j * tw_step], wi = twi[j * tw_step];
-            const double ar = re[a], ai = im[a], cr = re[c], ci = im[c];
-            if (DIF) {
-                const double dr = ar - cr, di = ai - ci;
-                re[a] = ar + cr; im[a] = ai + ci;
-                re[c] = dr * wr - di * wi; im[c] = dr * wi + di * wr;
-            } else {
-                const double tr = cr * wr - ci * wi, ti = cr * wi + ci * wr;
-                re[a] = ar + tr; im[a] = ai + ti;
-                re[c] = ar - tr; im[c] = ai - ti;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 template <typename real, int KIND, int NT>
 __global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __restrict__ field, long long chains, int W,
                                                               double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int N = NT, V = N * N;
-    double* sre = reinterpret_cast<double*>(smem_raw);
-    double* sim = sre + V;
-    double* twr = sim + V;
-    double* twi = twr + N / 2;
-    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) sincospi(-2.0 * (double)k / (double)N, &twi[k], &twr[k]);
+    static_assert(NT == 64 || NT == 32 || NT == 16, "the radix passes of fft_rr cover 16, 32 and 64");
     const double scale = 1.0 / ((double)V * (double)V);
-    for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
-        const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
-        __syncthreads();
-        for (int i = threadIdx.x; i < V; i += blockDim.x) {
-            if (KIND == SVB_CORR_WINDING) {
-                const int x0 = i / N, x1 = i - x0 * N;
-                const int i0 = ((x0 + 1) & (N - 1)) * N + x1, i1 = x0 * N + ((x1 + 1) & (N - 1));
-                sre[i] = (double)(((long long)g[V + i0] - (long long)g[V + i]) - ((long long)g[i1] - (long long)g[i]));
-                sim[i] = 0.0;
-            } else {
-                double s, c;
-                const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[i]) / (double)W : (double)g[i];
-                sincos(ang, &s, &c);
-                sre[i] = c;
-                sim[i] = s;
+    {
+        // both dimensions as two register-resident radix passes each (fft_rr: 64 = 8 x 8, 32 = 8 x 4, 16 = 4 x 4) on a tile padded
+        // to N + 1 columns: L = 64 x 1024 chains 175 -> 74 us against the radix-2 stages below
+        constexpr int RS = N + 1, L2 = NT == 64 ? 6 : NT == 32 ? 5 : 4, RA = NT == 16 ? 4 : 8, RB = NT == 64 ? 8 : 4;
+        double2* d = reinterpret_cast<double2*>(smem_raw);             // [N][N + 1]
+        double2* wn = d + N * RS;
+        fft_rr_twiddles<NT>(wn);
+        for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
+            const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+            __syncthreads();
+            for (int i = threadIdx.x; i < V; i += blockDim.x) {
+                const int x0 = i >> L2, x1 = i & (N - 1);
+                if (KIND == SVB_CORR_WINDING) {
+                    const int i0 = ((x0 + 1) & (N - 1)) * N + x1, i1 = x0 * N + ((x1 + 1) & (N - 1));
+                    d[x0 * RS + x1] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + i]) - ((long long)g[i1] - (long long)g[i])), 0.0);
+                } else {
+                    double sn, cs;
+                    const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[i]) / (double)W : (double)g[i];
+                    sincos(ang, &sn, &cs);
+                    d[x0 * RS + x1] = make_double2(cs, sn);
+                }
+            }
+            __syncthreads();
+            fft_rr<true, RA, RB>(d, 1, RS, L2, wn);                     // along x1, a thread per row and group
+            fft_rr<true, RA, RB>(d, RS, 1, L2, wn);                     // along x0, a thread per column and group
+            for (int i = threadIdx.x; i < V; i += blockDim.x) {
+                double2* q = d + (i >> L2) * RS + (i & (N - 1));
+                const double2 v = *q;
+                *q = make_double2(v.x * v.x + v.y * v.y, 0.0);
+            }
+            __syncthreads();
+            fft_rr<false, RA, RB>(d, RS, 1, L2, wn);
+            fft_rr<false, RA, RB>(d, 1, RS, L2, wn);
+            for (int i = threadIdx.x; i < V; i += blockDim.x) {
+                const double2 v = d[(i >> L2) * RS + (i & (N - 1))];
+                *reinterpret_cast<double2*>(out + (chain * V + i) * 2) = make_double2(v.x * scale, v.y * scale);
             }
         }
-        __syncthreads();
-        fft_pass<NT, true, true>(sre, sim, twr, twi);
-        fft_pass<NT, false, true>(sre, sim, twr, twi);
-        for (int i = threadIdx.x; i < V; i += blockDim.x) {
-            const double a = sre[i], b = sim[i];
-            sre[i] = a * a + b * b;
-            sim[i] = 0.0;
-        }
-        __syncthreads();
-        fft_pass<NT, false, false>(sre, sim, twr, twi);
-        fft_pass<NT, true, false>(sre, sim, twr, twi);
-        for (int i = threadIdx.x; i < V; i += blockDim.x)
-            *reinterpret_cast<double2*>(out + (chain * V + i) * 2) = make_double2(sre[i] * scale, sim[i] * scale);
     }
 }
 
@@ -337,87 +431,6 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
         }
         __syncthreads();
     }
-}
-
-// The 64-point transforms of the split (every one of them at N = 4096) as TWO radix-8 passes with the butterflies of a pass in
-// registers: a radix-2 stage costs about 18 instructions per element and a shared-memory round trip, three of them in registers
-// cost a third of that.  Position p = 8 a + b.  Decimation in frequency: DFT8 over a (stride 8) for every b, twiddle
-// W_64^{a b}, DFT8 over b -- position p then holds frequency (p >> 3) + 8 (p & 7) (digit reversal in base 8, fft64_freq).
-// Decimation in time takes that order back to the natural one: DFT8 over b, the same twiddle, DFT8 over a.
-__device__ __forceinline__ int fft64_freq(int p) { return ((p & 7) << 3) | (p >> 3); }
-__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cadd(const double2 a, const double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(const double2 a, const double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 mul_mi(const double2 z) { return make_double2(z.y, -z.x); }                 // z (-i)
-// X[k] = sum_n x[n] e^{-2 pi i n k / 8}, natural order in and out
-__device__ __forceinline__ void dft8(double2 (&x)[8]) {
-    constexpr double S = 0.70710678118654752440;
-    const double2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
-    const double2 b0 = csub(x[0], x[4]), t1 = csub(x[1], x[5]), t2 = csub(x[2], x[6]), t3 = csub(x[3], x[7]);
-    const double2 b1 = make_double2((t1.x + t1.y) * S, (t1.y - t1.x) * S);                                      // w
-    const double2 b2 = mul_mi(t2);                                                                              // w^2 = -i
-    const double2 b3 = make_double2((t3.y - t3.x) * S, -(t3.x + t3.y) * S);                                     // w^3
-    const double2 c0 = cadd(a0, a2), c1 = cadd(a1, a3), d0 = csub(a0, a2), d1 = mul_mi(csub(a1, a3));
-    const double2 e0 = cadd(b0, b2), e1 = cadd(b1, b3), f0 = csub(b0, b2), f1 = mul_mi(csub(b1, b3));
-    x[0] = cadd(c0, c1); x[2] = cadd(d0, d1); x[4] = csub(c0, c1); x[6] = csub(d0, d1);
-    x[1] = cadd(e0, e1); x[3] = cadd(f0, f1); x[5] = csub(e0, e1); x[7] = csub(f0, f1);
-}
-// 64-point transforms of 2^lanes_log2 independent lines: element (line, position) at d[line * lane_stride + position * pos_stride];
-// w64[t] = e^{-2 pi i t / 64}.  Consecutive threads take consecutive lines.
-// `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
-// DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
-struct NoScale {};
-template <bool DIF, class Scale = NoScale>
-__device__ __forceinline__ void fft64(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
-                                      const double2* __restrict__ w64, Scale scale = Scale()) {
-    constexpr bool SCALED = !std::is_same<Scale, NoScale>::value;
-    const int items = 8 << lanes_log2, lmask = (1 << lanes_log2) - 1;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool strided = DIF ? pass == 0 : pass == 1;       // DFT8 over a (positions 8 j + g) or over b (positions 8 g + j)
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {
-            const int g = i >> lanes_log2, lane = i & lmask;
-            const int p0 = strided ? g : 8 * g, dp = strided ? 8 : 1;
-            double2* base = d + lane * lane_stride + p0 * pos_stride;
-            const int step = dp * pos_stride;
-            double2 x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = base[j * step];
-            if constexpr (SCALED && !DIF) {
-                if (pass == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] = cmul(x[j], scale(lane, p0 + j * dp));
-                }
-            }
-            dft8(x);
-            if (pass == 0 && g != 0) {
-#pragma unroll
-                for (int k = 1; k < 8; ++k) x[k] = cmul(x[k], w64[g * k]);
-            }
-            if constexpr (SCALED && DIF) {
-                if (pass == 1) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) x[k] = cmul(x[k], scale(lane, p0 + k * dp));
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) base[k * step] = x[k];
-        }
-        __syncthreads();
-    }
-}
-__device__ __forceinline__ void fft64_twiddles(double2* w64) {
-    for (int k = threadIdx.x; k < 64; k += blockDim.x) {
-        double sn, cs;
-        sincospi(-2.0 * (double)k / 64.0, &sn, &cs);
-        w64[k] = make_double2(cs, sn);
-    }
-}
-// the frequency that position p of an n1-point transform of the split holds: radix-8 passes at n1 = 64, radix-2 stages otherwise
-__device__ __forceinline__ int split_freq(int p, int log2n1) {
-    return log2n1 == 6 ? fft64_freq(p) : (int)(__brev((unsigned)p) >> (32 - log2n1));
 }
 
 // The ROW transforms of the same lattices, split the same way inside a row held in shared memory: position r = 64 r1 + r2 of
@@ -686,7 +699,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
 template <typename real, int KIND, int NT>
 static int launch_correlation_fft(const void* field, long long chains, int W, double* out, int sms, cudaStream_t st) {
     auto kern = correlation_fft_kernel<real, KIND, NT>;
-    const size_t smem = (size_t)(2 * NT * NT + NT) * sizeof(double);
+    const size_t smem = (size_t)(NT * (NT + 1) + NT) * sizeof(double2);      // the padded tile and the N twiddles (>= the radix-2 layout)
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
