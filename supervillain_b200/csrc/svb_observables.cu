@@ -632,10 +632,10 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const long long row_items = chains * (N / R), col_items = chains * (N / C);
     const long long cap_rows = (long long)per_sm_rows * sms, cap_cols = (long long)per_sm_cols * sms;
     double2* o = reinterpret_cast<double2*>(out);
-    // whole lines in shared memory while at least eight columns fit a CTA; beyond (N >= 2048) every transform in two steps,
+    // whole lines in shared memory up to N = 512; beyond, every transform in two steps,
     // r = 64 r1 + r2 (SVB_CORR_SPLIT_MIN_N lowers the threshold, for tests of the split at sizes that can be checked element by
     // element)
-    int split_min = 2048;
+    int split_min = 1024;                                          // 8.4 M sites: 629 against 745 us at N = 1024, 669 against 594 us at N = 512
     if (const char* e = getenv("SVB_CORR_SPLIT_MIN_N")) split_min = atoi(e);
     const bool split = N >= split_min && N >= 2 * kSplitN2;
     const double V = (double)N * (double)N;

@@ -198,7 +198,7 @@ def test_fft_correlators_match_the_reference_formula(N):
 
 @pytest.mark.parametrize('N', [128, 256, 1024])
 def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
-    """The column transforms of the biggest lattices (N >= 2048) run in two steps, r = 64 r1 + r2 (correlation_split_*_kernel).
+    """The transforms of the biggest lattices (N >= 1024) run in two steps, r = 64 r1 + r2 (correlation_split_*_kernel).
     With the threshold lowered the same kernels serve sizes that can be compared element by element with the restated
     Lattice.correlation (compact.py:465-536): n1 = N / 64 = 2, 4 and 16 rows per outer transform, 1e-12."""
     monkeypatch.setenv('SVB_CORR_SPLIT_MIN_N', '128')
