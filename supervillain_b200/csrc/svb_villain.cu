@@ -1625,6 +1625,7 @@ static int launch_villain_resid(const VillainArgs& a, cudaStream_t stream, const
 #include "svb_villain_filtered.cuh"
 #include "svb_villain_stream.cuh"
 #include "svb_villain_cluster.cuh"
+#include "svb_villain_strips.cuh"
 #include "svb_villain_link.cuh"
 #ifndef SVB_CLUSTER_TPB
 #define SVB_CLUSTER_TPB 512
@@ -1816,7 +1817,9 @@ static int dispatch_villain(const VillainArgs& a, int rng_mode, int arith_mode, 
     if (path != SVB_PATH_GLOBAL && a.N == 128 && sizeof(real) == 8 && rng_mode != SVB_RNG_INJECTED &&
         (arith_mode != SVB_ARITH_STRICT || a.filtered_strict) && !a.accept_mask && !a.dS_out && (!a.exact_mode || a.filtered_strict) &&
         !a.wide && ((uintptr_t)a.phi % 16 == 0) && ((uintptr_t)a.n % 16 == 0)) {
-        // one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
+        // single sparse sweeps: one chain per CTA, phi and n streamed through a ring of strips (svb_villain_strips.cuh); everything
+        // else: one chain per cluster of four CTAs, a 32-row strip each (svb_villain_cluster.cuh)
+        if (arith_mode != SVB_ARITH_STRICT && villain_strips_serves(a)) return launch_villain_strips(a, stream, info);
         return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, stream, info);
     }
 #endif
@@ -1910,7 +1913,9 @@ extern "C" int svb_villain_sweep_overlapped(void* phi, int32_t* n, int64_t chain
         case 16: return launch_villain_filtered<16, 16, 1>(a, st, info);
         case 32: return launch_villain_filtered<32, SVB_FILT_MINB32, SVB_FILT_STAGES>(a, st, info);
         case 64: return launch_villain_filtered<64, 2, 1>(a, st, info);
-        default: return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, st, info);
+        default:
+            if (villain_strips_serves(a)) return launch_villain_strips(a, st, info);
+            return launch_villain_cluster<128, SVB_CLUSTER_CL, SVB_CLUSTER_TPB, SVB_CLUSTER_STAGES>(a, st, info);
     }
 }
 
