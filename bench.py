@@ -58,7 +58,7 @@ SHAPES = {
                kernel='worldline_smem_table_kernel<N=64>',
                workload='config3: Worldline (m,v) L=64 kappa=0.5 W=1, 1024 chains/GPU (8192 over 8 GPUs), PlaquetteUpdate move in checkerboard order + observables'),
     'c4': dict(kind='villain', L=128, chains=8192, bytes=32, rotate=1, thermalise=20, cap=100, kappas_per_gpu=8,
-               kernel='villain_cluster_kernel<N=128, cluster of 4 x 512 threads>',
+               kernel='villain_strips_kernel<N=128, one chain per CTA of 512 threads, phi and n streamed through a ring of 8-row strips>',
                workload='config4: Villain L=128 kappa scan, 8 kappa x 1024 chains/GPU (64 kappa in [0.3,1.2] over 8 GPUs), NeighborhoodUpdate sweep + observables'),
     'c5': dict(kind='villain', L=4096, chains=1, bytes=32, rotate=1, thermalise=20, cap=200,
                kernel='villain_tile_pass_kernel (TMA tensor-staged 16 x 128 tiles, one launch per colour, in place)',

@@ -12,22 +12,44 @@
 // no cluster barriers (the top stall of the cluster kernel) and no distributed shared memory, the arithmetic and the thread
 // geometry of villain_smem_filtered_kernel unchanged (a thread owns rows r, r + 8, ... of one column slot; pairs of rows share a
 // Philox block), block barriers only.  The strips of the NEXT chain that fit the ring land during the colour passes.
+//
+// Measured (config-4 shard of bench.py, 8192 chains, one sweep + record per launch, overlapped launches): 959 - 995 us against
+// 1283 - 1347 us for the cluster kernel (0.66 - 0.68 of the HBM roofline against 0.49 - 0.51); without a record 883 us (0.74).
+// 143 thread-instructions per site-update (the cluster kernel: 227), issue slots 47 % busy with 16 warps per SM; a tenth of the
+// instructions are warps spinning on a strip's mbarrier: the ring keeps 70 KiB in flight per SM, and the build -- memory --
+// and the passes -- arithmetic -- of a chain do not overlap.  Tried on top: 1024 threads per CTA at 64 registers (HALVES = 2:
+// 1079 against 1048 us), an L2 prefetch of the rest of the next chain during the passes (975 against 961 us).  What the knobs
+// below are worth: all eight pairs of a pass unrolled and four strips of the build in flight per thread 1048 -> 961 us.
 #pragma once
 
 constexpr int kStripRows = 8, kStripRing = 4;
+#ifndef SVB_STRIPS_HALVES
+#define SVB_STRIPS_HALVES 1
+#endif
+#ifndef SVB_STRIPS_UNROLL_P
+#define SVB_STRIPS_UNROLL_P 8      /* pairs of rows of a colour pass in flight per thread */
+#endif
+#ifndef SVB_STRIPS_UNROLL_B
+#define SVB_STRIPS_UNROLL_B 4      /* strips of the residual build in flight per thread */
+#endif
+constexpr int kStripsUnrollP = SVB_STRIPS_UNROLL_P, kStripsUnrollB = SVB_STRIPS_UNROLL_B;
 
-template <int NT, bool OVERLAP, bool UNIT>
-__global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc) {
+// HALVES = 2: twice the threads -- the strips with an odd place in the load order and the upper half of the pairs of rows belong
+// to threads 4 N .. 8 N - 1 -- for 32 warps per SM at 64 registers instead of 16 at up to 128.
+template <int NT, bool OVERLAP, bool UNIT, int HALVES>
+__global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(const __grid_constant__ VillainArgs a, const __grid_constant__ FilterConsts fc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, T = 4 * NT, NW = T / 32;
-    constexpr int PER = VH / T;                                  // sites per thread per colour (rows row8 + 8 q) = strips per chain
-    static_assert(PER == N / kStripRows && PER % kStripRing == 0 && PER % 2 == 0, "villain_strips_kernel: unsupported geometry");
+    constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, TQ = 4 * NT, T = TQ * HALVES, NW = T / 32;
+    constexpr int PER = VH / TQ;                                 // rows row8 + 8 q of a column slot = strips per chain
+    static_assert(PER == N / kStripRows && PER % kStripRing == 0 && PER % (2 * HALVES) == 0 && (HALVES == 1 || HALVES == 2),
+                  "villain_strips_kernel: unsupported geometry");
     constexpr uint32_t bytes_phi = (kStripRows + 1) * N * sizeof(double);        // rows 8 q .. 8 q + 8
     constexpr uint32_t bytes_n0 = kStripRows * N * sizeof(int32_t);              // rows 8 q .. 8 q + 7
     constexpr uint32_t bytes_n1 = (kStripRows + 1) * N * sizeof(int32_t);        // rows 8 q .. 8 q + 8
     constexpr uint32_t strip_bytes = bytes_phi + bytes_n0 + bytes_n1;
     static_assert(strip_bytes % 128 == 0, "strips are 128-byte aligned");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tq = tid % TQ, half = tid / TQ;
     float* rc0 = reinterpret_cast<float*>(smem_raw + kStripRing * strip_bytes);   // [colour][VH]: residual of link (0, x)
     float* rc1 = rc0 + V;                                                         // [colour][VH]: residual of link (1, x)
     double* red_state = reinterpret_cast<double*>(rc1 + V);                       // [NW][4] per-warp partial sums
@@ -40,7 +62,7 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
     if (tid == 0) {
         for (int b = 0; b < kStripRing; ++b) {
             mbar_init(&full[b], 1);
-            mbar_init(&empty[b], NW);
+            mbar_init(&empty[b], NW / HALVES);
         }
         fence_mbar_init();
     }
@@ -61,7 +83,7 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
     const double two_I_scaled = (2.0 * a.interval_phi) * 2.3283064365386963e-10;          // (2 I) 2^-32, exact scaling
 
     // per-thread geometry: rows row8 + 8 q of the compact column k
-    const int row8 = tid / HN, k = tid - row8 * HN;
+    const int row8 = tq / HN, k = tq - row8 * HN;
     const int cc = row8 & 1;
     const int wrap0 = (row8 == 0) ? VH : 0;                       // backward-0 neighbour of row 0 is row N - 1
 
@@ -87,9 +109,13 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
             asm volatile("fence.proxy.async;" ::: "memory");
         }
     };
-    // (thread 0) the loads of strip q of `chain` into ring slot q % ring: rows 8 q .. 8 q + 8 (the row after the last one is row 0)
-    auto issue_strip = [&](long long chain, int q) {
-        const int b = q % kStripRing, r0 = kStripRows * q;
+    // strips are loaded in the order s = 0, 1, ...: strip s holds rows 8 q(s) .. 8 q(s) + 8 and is read by the threads of half
+    // s % HALVES
+    auto strip_q = [&](int s_) { return HALVES == 1 ? s_ : (s_ >> 1) + (PER / 2) * (s_ & 1); };
+    // (one thread) the loads of strip s of `chain` into ring slot s % ring (the row after the last one is row 0)
+    auto issue_strip = [&](long long chain, int s_) {
+        const int q = strip_q(s_);
+        const int b = s_ % kStripRing, r0 = kStripRows * q;
         unsigned char* st = smem_raw + (size_t)b * strip_bytes;
         const double* gp = reinterpret_cast<const double*>(a.phi) + chain * V;
         const int32_t* g0 = a.n + chain * 2 * V;
@@ -110,7 +136,7 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
     long long chain = blockIdx.x;
     if (tid == 0 && chain < a.chains) {
         wait_chain(chain, peek_epoch(chain));
-        for (int q = 0; q < kStripRing; ++q) issue_strip(chain, q);
+        for (int s_ = 0; s_ < kStripRing; ++s_) issue_strip(chain, s_);
     }
 
     int it = 0;
@@ -125,33 +151,34 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
         int32_t* gn0 = a.n + chain * 2 * V;
         int32_t* gn1 = gn0 + V;
         uint32_t seen_next = 0;
-        if (tid == 0 && next < a.chains) seen_next = peek_epoch(next);               // lands during the residual build
+        if (tq == 0 && next < a.chains) seen_next = peek_epoch(next);                // lands during the residual build
 
         int n_acc = 0;
         float sum_A = 0.0f;
         // ---- r = d(phi) - 2 pi n   (neighborhood.py:91) in fp64, stored rounded to fp32, strip by strip ----
         {
-            float* w0e = rc0 + cc * VH + tid;
-            float* w1e = rc1 + cc * VH + tid;
-            float* w0o = rc0 + (cc ^ 1) * VH + tid;
-            float* w1o = rc1 + (cc ^ 1) * VH + tid;
+            float* w0e = rc0 + cc * VH + tq;
+            float* w1e = rc1 + cc * VH + tq;
+            float* w0o = rc0 + (cc ^ 1) * VH + tq;
+            float* w1o = rc1 + (cc ^ 1) * VH + tq;
             double action = 0.0;
             int w0 = 0, w1 = 0;
             long long dn2 = 0;
-#pragma unroll 1
-            for (int q = 0; q < PER; ++q) {
-                const int b = q % kStripRing;
-                const uint32_t parity = (uint32_t)((it * (PER / kStripRing) + q / kStripRing) & 1);
+#pragma unroll kStripsUnrollB
+            for (int s_ = half; s_ < PER; s_ += HALVES) {
+                const int q = strip_q(s_);
+                const int b = s_ % kStripRing;
+                const uint32_t parity = (uint32_t)((it * (PER / kStripRing) + s_ / kStripRing) & 1);
                 const unsigned char* st = smem_raw + (size_t)b * strip_bytes;
                 const double* sp = reinterpret_cast<const double*>(st) + row8 * N;
                 const int32_t* s0 = reinterpret_cast<const int32_t*>(st + bytes_phi) + row8 * N;
                 const int32_t* s1 = reinterpret_cast<const int32_t*>(st + bytes_phi + bytes_n0) + row8 * N;
                 mbar_wait(&full[b], parity);
                 const PairResiduals pr = villain_pair_residuals(sp + 2 * k, sp + N + 2 * k, sp + ((2 * k + 2) & (N - 1)), s0 + 2 * k, s1 + 2 * k);
-                w0e[T * q] = (float)pr.r0e;
-                w1e[T * q] = (float)pr.r1e;
-                w0o[T * q] = (float)pr.r0o;
-                w1o[T * q] = (float)pr.r1o;
+                w0e[TQ * q] = (float)pr.r0e;
+                w1e[TQ * q] = (float)pr.r1e;
+                w0o[TQ * q] = (float)pr.r0o;
+                w1o[TQ * q] = (float)pr.r1o;
                 if (obs_of_input) {                                  // the observables of the arriving state ride along
                     action = fma(pr.r0e, pr.r0e, action);
                     action = fma(pr.r0o, pr.r0o, action);
@@ -164,18 +191,18 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
                     w0 += pr.a0.x + pr.a0.y;
                     w1 += pr.a1.x + pr.a1.y;
                 }
-                // the warp has read the strip; when every warp has, thread 0 refills the slot -- with a later strip of this chain
-                // or, towards the end, with the first strips of the next one (they land during the colour passes)
+                // the warp has read the strip; when every warp of the half has, its first thread refills the slot -- with a later
+                // strip of this chain or, towards the end, with the first strips of the next one (they land during the colour passes)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[b]);
-                if (tid == 0) {
+                if (tq == 0) {
                     mbar_wait(&empty[b], parity);
-                    const int qn = q + kStripRing;
-                    if (qn < PER) {
-                        issue_strip(chain, qn);
+                    const int sn = s_ + kStripRing;
+                    if (sn < PER) {
+                        issue_strip(chain, sn);
                     } else if (next < a.chains) {
-                        if (qn == PER) wait_chain(next, seen_next);
-                        issue_strip(next, qn - PER);
+                        if (sn < PER + HALVES) wait_chain(next, seen_next);          // the first strip of the next chain this thread loads
+                        issue_strip(next, sn - PER);
                     }
                 }
             }
@@ -191,13 +218,14 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
             const int par = (row8 + c) & 1;                    // column parity of this thread's sites of colour c
             const int x1 = 2 * k + par;
             const int ob1 = par ? 0 : ((k == 0) ? (1 - HN) : 1);          // compact index of x - e1 is j - ob1
-            float* R0own = rc0 + c * VH + tid;
-            float* R1own = rc1 + c * VH + tid;
-            float* R0b = rc0 + (c ^ 1) * VH + tid - HN;        // backward link (0, x - e0): row above, same compact column
+            float* R0own = rc0 + c * VH + tq;
+            float* R1own = rc1 + c * VH + tq;
+            float* R0b = rc0 + (c ^ 1) * VH + tq - HN;         // backward link (0, x - e0): row above, same compact column
             float* R0b_q0 = R0b + wrap0;
-            float* R1b = rc1 + (c ^ 1) * VH + tid - ob1;       // backward link (1, x - e1)
-#pragma unroll 4
-            for (int p = 0; p < PER / 2; ++p) {
+            float* R1b = rc1 + (c ^ 1) * VH + tq - ob1;        // backward link (1, x - e1)
+#pragma unroll kStripsUnrollP
+            for (int pl = 0; pl < PER / 2 / HALVES; ++pl) {
+                const int p = pl + half * (PER / 2 / HALVES);      // the pair of rows (row8 + 16 p, row8 + 16 p + 8)
                 const uint32_t c0 = (uint32_t)((row8 + 16 * p) * N + x1);                 // villain_pair_counter
                 const Philox4 bits = philox_site_keys(a, gc, gs, c0);
                 const int qA = 2 * p, qB = 2 * p + 1;
@@ -223,8 +251,8 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
                 U = __fadd2_rn(U, make_float2(-0.99999994f, -0.99999994f));
                 const float2 dphi = __ffma2_rn(make_float2(fc.two_I, fc.two_I), U, make_float2(-fc.I, -fc.I));
                 const float2 base_f = __ffma2_rn(dphi, make_float2(-1.0f, -1.0f), cIn2), base_b = __fadd2_rn(cIn2, dphi);
-                const float2 r_f0 = make_float2(R0own[T * qA], R0own[T * qB]), r_f1 = make_float2(R1own[T * qA], R1own[T * qB]);
-                const float2 r_b0 = make_float2(r0bA[T * qA], R0b[T * qB]), r_b1 = make_float2(R1b[T * qA], R1b[T * qB]);
+                const float2 r_f0 = make_float2(R0own[TQ * qA], R0own[TQ * qB]), r_f1 = make_float2(R1own[TQ * qA], R1own[TQ * qB]);
+                const float2 r_b0 = make_float2(r0bA[TQ * qA], R0b[TQ * qB]), r_b1 = make_float2(R1b[TQ * qA], R1b[TQ * qB]);
                 // dr = d(dphi) - 2 pi dn   (neighborhood.py:110), dn = W (digit - interval_n)
                 float2 dr_f0, dr_b0, dr_f1, dr_b1;
                 if (UNIT) {
@@ -311,10 +339,10 @@ __global__ void __launch_bounds__(4 * NT, 1) villain_strips_kernel(const __grid_
                             atomicAdd(gn0 + ((x0 - 1) & (N - 1)) * N + x1, W * dig[1] + mWI);
                             atomicAdd(gn1 + ic, W * dig[2] + mWI);
                             atomicAdd(gn1 + x0 * N + ((x1 - 1) & (N - 1)), W * dig[3] + mWI);
-                            R0own[T * q] = h ? n_f0.y : n_f0.x;
-                            r0b[T * q] = h ? n_b0.y : n_b0.x;
-                            R1own[T * q] = h ? n_f1.y : n_f1.x;
-                            R1b[T * q] = h ? n_b1.y : n_b1.x;
+                            R0own[TQ * q] = h ? n_f0.y : n_f0.x;
+                            r0b[TQ * q] = h ? n_b0.y : n_b0.x;
+                            R1own[TQ * q] = h ? n_f1.y : n_f1.x;
+                            R1b[TQ * q] = h ? n_b1.y : n_b1.x;
                         }
                     }
                 }
@@ -350,18 +378,24 @@ static bool villain_strips_serves(const VillainArgs& a) {
 static int launch_villain_strips(const VillainArgs& a, cudaStream_t stream, const DeviceInfo& info) {
     constexpr int NT = 128;
     const bool overlap = a.epochs != nullptr, unit = a.W == 1 && a.interval_n == 1;
-    auto kern = overlap ? (unit ? villain_strips_kernel<NT, true, true> : villain_strips_kernel<NT, true, false>)
-                        : (unit ? villain_strips_kernel<NT, false, true> : villain_strips_kernel<NT, false, false>);
+    int halves = SVB_STRIPS_HALVES;
+    if (const char* e = getenv("SVB_STRIPS_HALVES")) halves = atoi(e) == 2 ? 2 : 1;
+    auto kern1 = overlap ? (unit ? villain_strips_kernel<NT, true, true, 1> : villain_strips_kernel<NT, true, false, 1>)
+                         : (unit ? villain_strips_kernel<NT, false, true, 1> : villain_strips_kernel<NT, false, false, 1>);
+    auto kern2 = overlap ? (unit ? villain_strips_kernel<NT, true, true, 2> : villain_strips_kernel<NT, true, false, 2>)
+                         : (unit ? villain_strips_kernel<NT, false, true, 2> : villain_strips_kernel<NT, false, false, 2>);
+    auto kern = halves == 2 ? kern2 : kern1;
+    const int threads = 4 * NT * halves;
     constexpr size_t strip = (size_t)(kStripRows + 1) * NT * 8 + (size_t)kStripRows * NT * 4 + (size_t)(kStripRows + 1) * NT * 4;
-    const size_t smem = kStripRing * strip + 2 * (size_t)NT * NT * sizeof(float) + 6 * (4 * NT / 32) * sizeof(double) + 2 * kStripRing * 8 +
+    const size_t smem = kStripRing * strip + 2 * (size_t)NT * NT * sizeof(float) + 6 * (threads / 32) * sizeof(double) + 2 * kStripRing * 8 +
                         81 * sizeof(float4);
-    static int ready[4][64];
-    const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0);
+    static int ready[8][64];
+    const int variant = (overlap ? 1 : 0) + (unit ? 2 : 0) + (halves == 2 ? 4 : 0);
     if (info.device >= 64 || !ready[variant][info.device]) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int per_sm = 0;
-        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 4 * NT, smem));
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "the strips kernel does not fit an SM");
         if (info.device < 64) ready[variant][info.device] = 1;
     }
@@ -370,7 +404,7 @@ static int launch_villain_strips(const VillainArgs& a, cudaStream_t stream, cons
     const FilterConsts fc = make_filter_consts(a.interval_phi, a.W, a.interval_n);
     if (overlap) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(4 * NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -378,7 +412,7 @@ static int launch_villain_strips(const VillainArgs& a, cudaStream_t stream, cons
         SVB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, fc));
         return 0;
     }
-    kern<<<(unsigned)grid, 4 * NT, smem, stream>>>(a, fc);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(a, fc);
     SVB_CUDA_TRY(cudaGetLastError());
     return 0;
 }
