@@ -22,7 +22,10 @@
 // below are worth: all eight pairs of a pass unrolled and four strips of the build in flight per thread 1048 -> 961 us.
 #pragma once
 
-constexpr int kStripRows = 8, kStripRing = 4;
+#ifndef SVB_STRIPS_RING
+#define SVB_STRIPS_RING 4
+#endif
+constexpr int kStripRows = 8, kStripRing = SVB_STRIPS_RING;
 #ifndef SVB_STRIPS_HALVES
 #define SVB_STRIPS_HALVES 1
 #endif
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int N = NT, V = N * N, HN = N / 2, VH = V / 2, TQ = 4 * NT, T = TQ * HALVES, NW = T / 32;
     constexpr int PER = VH / TQ;                                 // rows row8 + 8 q of a column slot = strips per chain
-    static_assert(PER == N / kStripRows && PER % kStripRing == 0 && PER % (2 * HALVES) == 0 && (HALVES == 1 || HALVES == 2),
+    static_assert(PER == N / kStripRows && kStripRing <= PER && PER % (2 * HALVES) == 0 && (HALVES == 1 || HALVES == 2),
                   "villain_strips_kernel: unsupported geometry");
     constexpr uint32_t bytes_phi = (kStripRows + 1) * N * sizeof(double);        // rows 8 q .. 8 q + 8
     constexpr uint32_t bytes_n0 = kStripRows * N * sizeof(int32_t);              // rows 8 q .. 8 q + 7
@@ -113,9 +116,9 @@ __global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(cons
     // s % HALVES
     auto strip_q = [&](int s_) { return HALVES == 1 ? s_ : (s_ >> 1) + (PER / 2) * (s_ & 1); };
     // (one thread) the loads of strip s of `chain` into ring slot s % ring (the row after the last one is row 0)
-    auto issue_strip = [&](long long chain, int s_) {
+    auto issue_strip = [&](long long chain, int s_, int slot) {
         const int q = strip_q(s_);
-        const int b = s_ % kStripRing, r0 = kStripRows * q;
+        const int b = slot, r0 = kStripRows * q;
         unsigned char* st = smem_raw + (size_t)b * strip_bytes;
         const double* gp = reinterpret_cast<const double*>(a.phi) + chain * V;
         const int32_t* g0 = a.n + chain * 2 * V;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(cons
     long long chain = blockIdx.x;
     if (tid == 0 && chain < a.chains) {
         wait_chain(chain, peek_epoch(chain));
-        for (int s_ = 0; s_ < kStripRing; ++s_) issue_strip(chain, s_);
+        for (int s_ = 0; s_ < kStripRing; ++s_) issue_strip(chain, s_, s_);
     }
 
     int it = 0;
@@ -167,8 +170,10 @@ __global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(cons
 #pragma unroll kStripsUnrollB
             for (int s_ = half; s_ < PER; s_ += HALVES) {
                 const int q = strip_q(s_);
-                const int b = s_ % kStripRing;
-                const uint32_t parity = (uint32_t)((it * (PER / kStripRing) + s_ / kStripRing) & 1);
+                // the g-th strip this CTA reads lives in slot g % ring, in the slot's (g / ring)-th use
+                const unsigned g = (unsigned)it * PER + (unsigned)s_;
+                const int b = (int)(g % kStripRing);
+                const uint32_t parity = (g / kStripRing) & 1u;
                 const unsigned char* st = smem_raw + (size_t)b * strip_bytes;
                 const double* sp = reinterpret_cast<const double*>(st) + row8 * N;
                 const int32_t* s0 = reinterpret_cast<const int32_t*>(st + bytes_phi) + row8 * N;
@@ -199,10 +204,10 @@ __global__ void __launch_bounds__(4 * NT * HALVES, 1) villain_strips_kernel(cons
                     mbar_wait(&empty[b], parity);
                     const int sn = s_ + kStripRing;
                     if (sn < PER) {
-                        issue_strip(chain, sn);
+                        issue_strip(chain, sn, b);
                     } else if (next < a.chains) {
                         if (sn < PER + HALVES) wait_chain(next, seen_next);          // the first strip of the next chain this thread loads
-                        issue_strip(next, sn - PER);
+                        issue_strip(next, sn - PER, b);
                     }
                 }
             }
