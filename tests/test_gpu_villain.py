@@ -416,6 +416,38 @@ def test_sparse_launches_equal_dense_launches(N, chains):
     assert torch.allclose(rec_in[1:K, :, 0], rec[:K - 1, :, 0], rtol=1e-13, atol=0)         # the action (summation order)
 
 
+@pytest.mark.parametrize('chains,W,interval_n', [(150, 1, 1), (37, 2, 1), (301, 1, 0)])
+def test_strips_kernel_equals_cluster_kernel(chains, W, interval_n, monkeypatch):
+    """L = 128: single sparse sweeps run with one chain per CTA, phi and n streamed through a ring of strips
+    (villain_strips_kernel); SVB_VILLAIN_KERNEL128=cluster sends the same launches to the cluster kernel.  Same fields, same
+    records, launch after launch -- ordinary and overlapped launches, kappa per chain, more chains than CTAs."""
+    N, kappa, K = 128, 0.6, 4
+    S = svb.Villain(svb.Lattice2D(N), kappa, W=W)
+    kc = torch.linspace(0.3, 1.2, chains, dtype=torch.float64, device='cuda')
+    phi, n = svb.BatchedEnsemble(S, chains)._start('hot', 9)
+    n *= W
+    results = {}
+    for kernel in ('strips', 'cluster'):
+        monkeypatch.setenv('SVB_VILLAIN_KERNEL128', kernel)
+        a_phi, a_n, b_phi, b_n = phi.clone(), n.clone(), phi.clone(), n.clone()
+        rec = torch.zeros((K + 1, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+        plain = torch.zeros((K, chains, VOBS_COUNT), dtype=torch.float64, device='cuda')
+        st = ops.VillainOverlappedSweeps(a_phi, a_n, kappa, W=W, interval_n=interval_n, seed=6, chain0=3, kappa_chain=kc)
+        for k in range(K):
+            st.step(k, 1, obs=rec[k + 1], obs_in=rec[k])
+            ops.villain_sweep(b_phi, b_n, kappa, W=W, interval_n=interval_n, seed=6, sweep0=k, chain0=3, kappa_chain=kc)
+        torch.cuda.synchronize()
+        assert torch.equal(a_phi, b_phi) and torch.equal(a_n, b_n), kernel
+        results[kernel] = (a_phi, a_n, rec)
+    s_phi, s_n, s_rec = results['strips']
+    c_phi, c_n, c_rec = results['cluster']
+    assert torch.equal(s_phi, c_phi) and torch.equal(s_n, c_n)
+    assert not torch.equal(s_phi, phi)
+    assert torch.equal(s_rec[:, :, 1:5], c_rec[:, :, 1:5])                              # sum dn^2, wrapping, accepted: integers
+    assert torch.allclose(s_rec[:, :, 0], c_rec[:, :, 0], rtol=1e-13, atol=0)           # the action (summation order)
+    assert torch.allclose(s_rec[:, :, 5], c_rec[:, :, 5], rtol=1e-6, atol=0)            # the fp32 acceptance monitor
+
+
 def test_overlapped_launches_reject_what_they_do_not_serve():
     S = svb.Villain(svb.Lattice2D(48), 0.5)
     phi, n = svb.BatchedEnsemble(S, 4)._start('cold', 0)
