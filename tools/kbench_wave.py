@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Wavefront steps (svb_villain_sweep_wavefront) against colour-pass steps (svb_villain_sweep_inplace) and, at L = 128, the
-cluster kernel: CUDA-event time per single-sweep step with the obs_in record protocol.
+overlapped launches of svb_villain_sweep_overlapped (kind 'cluster': the strips kernel, or the cluster kernel under
+SVB_VILLAIN_KERNEL128=cluster): CUDA-event time per single-sweep step with the obs_in record protocol.
     KB_SHAPES='4096x1,128x8192'  KB_LAGS='0,8,16,32'  (0 = the launcher's choice)"""
 import os, sys
 import torch
