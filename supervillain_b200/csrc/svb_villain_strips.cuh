@@ -13,13 +13,14 @@
 // geometry of villain_smem_filtered_kernel unchanged (a thread owns rows r, r + 8, ... of one column slot; pairs of rows share a
 // Philox block), block barriers only.  The strips of the NEXT chain that fit the ring land during the colour passes.
 //
-// Measured (config-4 shard of bench.py, 8192 chains, one sweep + record per launch, overlapped launches): 959 - 995 us against
-// 1283 - 1347 us for the cluster kernel (0.66 - 0.68 of the HBM roofline against 0.49 - 0.51); without a record 883 us (0.74).
+// Measured (config-4 shard of bench.py, 8192 chains, one sweep + record per launch, overlapped launches): 892 - 911 us against
+// 1283 - 1347 us for the cluster kernel (0.72 - 0.74 of the HBM roofline against 0.49 - 0.51); without a record 847 us (0.78).
 // 143 thread-instructions per site-update (the cluster kernel: 227), issue slots 47 % busy with 16 warps per SM; a tenth of the
 // instructions are warps spinning on a strip's mbarrier: the ring keeps 70 KiB in flight per SM, and the build -- memory --
 // and the passes -- arithmetic -- of a chain do not overlap.  Tried on top: 1024 threads per CTA at 64 registers (HALVES = 2:
 // 1079 against 1048 us), an L2 prefetch of the rest of the next chain during the passes (975 against 961 us).  What the knobs
-// below are worth: all eight pairs of a pass unrolled and four strips of the build in flight per thread 1048 -> 961 us.
+// below are worth: all eight pairs of a pass in flight per thread 1048 -> 1029 us; the build unrolled 4, 8, 16 strips deep 1008 /
+// 961, 931, 911 us.
 #pragma once
 
 #ifndef SVB_STRIPS_RING
@@ -33,7 +34,7 @@ constexpr int kStripRows = 8, kStripRing = SVB_STRIPS_RING;
 #define SVB_STRIPS_UNROLL_P 8      /* pairs of rows of a colour pass in flight per thread */
 #endif
 #ifndef SVB_STRIPS_UNROLL_B
-#define SVB_STRIPS_UNROLL_B 4      /* strips of the residual build in flight per thread */
+#define SVB_STRIPS_UNROLL_B 16      /* strips of the residual build in flight per thread */
 #endif
 constexpr int kStripsUnrollP = SVB_STRIPS_UNROLL_P, kStripsUnrollB = SVB_STRIPS_UNROLL_B;
 
