@@ -113,10 +113,13 @@ template <> __device__ __forceinline__ void dft_r<4>(double2 (&x)[4]) { dft4(x);
 // `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
 // DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
 struct NoScale {};
-template <bool DIF, int RA, int RB, class Scale = NoScale>
+// `oscale(line, position)` (optional, DIT only): a factor for every element of the OUTPUT of a decimation-in-time transform.
+template <bool DIF, int RA, int RB, class Scale = NoScale, class OutScale = NoScale>
 __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
-                                       const double2* __restrict__ wn, Scale scale = Scale()) {
+                                       const double2* __restrict__ wn, Scale scale = Scale(), OutScale oscale = OutScale()) {
     constexpr bool SCALED = !std::is_same<Scale, NoScale>::value;
+    constexpr bool OSCALED = !std::is_same<OutScale, NoScale>::value;
+    static_assert(!(OSCALED && DIF), "an output factor is for decimation-in-time transforms");
     const int lmask = (1 << lanes_log2) - 1;
     auto pass_a = [&](bool first) {                               // RA-point transforms over a, one per (line, b)
         for (int i = threadIdx.x; i < (RB << lanes_log2); i += blockDim.x) {
@@ -130,6 +133,12 @@ __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, 
             if (first && g != 0) {                                // (first only in a DIF transform; a scale never applies here)
 #pragma unroll
                 for (int k = 1; k < RA; ++k) x[k] = cmul(x[k], wn[g * k]);
+            }
+            if constexpr (OSCALED) {
+                if (!first) {
+#pragma unroll
+                    for (int k = 0; k < RA; ++k) x[k] = cmul(x[k], oscale(lane, g + RB * k));
+                }
             }
 #pragma unroll
             for (int k = 0; k < RA; ++k) base[k * step] = x[k];
@@ -167,10 +176,10 @@ __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, 
     };
     if (DIF) { pass_a(true); pass_b(false); } else { pass_b(true); pass_a(false); }
 }
-template <bool DIF, class Scale = NoScale>
+template <bool DIF, class Scale = NoScale, class OutScale = NoScale>
 __device__ __forceinline__ void fft64(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
-                                      const double2* __restrict__ w64, Scale scale = Scale()) {
-    fft_rr<DIF, 8, 8, Scale>(d, pos_stride, lane_stride, lanes_log2, w64, scale);
+                                      const double2* __restrict__ w64, Scale scale = Scale(), OutScale oscale = OutScale()) {
+    fft_rr<DIF, 8, 8, Scale, OutScale>(d, pos_stride, lane_stride, lanes_log2, w64, scale, oscale);
 }
 template <int NN>
 __device__ __forceinline__ void fft_rr_twiddles(double2* wn) {
@@ -187,9 +196,30 @@ __device__ __forceinline__ void fft64_twiddles(double2* w64) {
         w64[k] = make_double2(cs, sn);
     }
 }
-// the frequency that position p of an n1-point transform of the split holds: radix-8 passes at n1 = 64, radix-2 stages otherwise
+// the frequency that position p of an n1-point transform of the split holds: two radix passes at n1 = 64, 32, 16 (position
+// RB k_a + k_b holds k_a + RA k_b), radix-2 stages (bit reversal) below
 __device__ __forceinline__ int split_freq(int p, int log2n1) {
-    return log2n1 == 6 ? fft64_freq(p) : (int)(__brev((unsigned)p) >> (32 - log2n1));
+    switch (log2n1) {
+        case 6: return fft64_freq(p);
+        case 5: return (p >> 2) + 8 * (p & 3);
+        case 4: return (p >> 2) + 4 * (p & 3);
+        default: return (int)(__brev((unsigned)p) >> (32 - log2n1));
+    }
+}
+// the n1-point transforms of the split with radix passes (n1 = 64: 8 x 8, 32: 8 x 4, 16: 4 x 4); wn[t] = e^{-2 pi i t / n1}, t < n1
+template <bool DIF, class Scale = NoScale, class OutScale = NoScale>
+__device__ __forceinline__ void fft_n1(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2, int log2n1,
+                                       const double2* __restrict__ wn, Scale scale = Scale(), OutScale oscale = OutScale()) {
+    if (log2n1 == 6) fft_rr<DIF, 8, 8, Scale, OutScale>(d, pos_stride, lane_stride, lanes_log2, wn, scale, oscale);
+    else if (log2n1 == 5) fft_rr<DIF, 8, 4, Scale, OutScale>(d, pos_stride, lane_stride, lanes_log2, wn, scale, oscale);
+    else fft_rr<DIF, 4, 4, Scale, OutScale>(d, pos_stride, lane_stride, lanes_log2, wn, scale, oscale);
+}
+__device__ __forceinline__ void fft_n1_twiddles(double2* wn, int n1) {
+    for (int k = threadIdx.x; k < n1; k += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)k / (double)n1, &sn, &cs);
+        wn[k] = make_double2(cs, sn);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -446,19 +476,36 @@ __global__ void __launch_bounds__(512) correlation_rows_split_kernel(const real*
     const int n1 = 1 << log2n1;
     constexpr int RS = kSplitN2 + 1;                                    // row stride of the tile: lines a bank group apart
     double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][64 (+1)]: the row
-    double2* tw1 = d + (size_t)n1 * RS;                                 // n1 / 2 twiddles of the n1-point transform
-    double2* w64 = tw1 + (n1 > 1 ? n1 / 2 : 1);                         // W_64^t, t < 64
+    double2* tw1 = d + (size_t)n1 * RS;                                 // twiddles of the n1-point transform: W_n1^t, t < n1 (radix passes,
+                                                                        // n1 >= 16) or t < n1 / 2 (radix-2 stages)
+    double2* w64 = tw1 + n1;                                            // W_64^t, t < 64
     double2* th = w64 + kSplitN2;                                       // W_N^{64 a}, a < 64
     double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
-    fft_twiddles(tw1, n1);
+    if (log2n1 >= 4) fft_n1_twiddles(tw1, n1); else fft_twiddles(tw1, n1);
     fft64_twiddles(w64);
     for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
         double sn, cs;
         sincospi(-2.0 * (double)((i * kSplitN2) & (N - 1)) / (double)N, &sn, &cs);
         th[i] = make_double2(cs, sn);
         sincospi(-2.0 * (double)i / (double)N, &sn, &cs);
-        tl[i] = make_double2(cs, sn);
+        tl[i] = make_double2(cs * scale, sn * scale);                   // every element meets W_N^t exactly once: the scaling rides along
     }
+    // the row travels between global memory and the padded tile as bulk copies (TMA), a line of 64 elements each, issued by
+    // warp 0: nothing of it passes through registers, and the next row is on its way while this one is being written back
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    constexpr uint32_t kLineBytes = kSplitN2 * sizeof(double2);
+    auto load_row = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)N * (uint32_t)sizeof(double2));
+        __syncwarp();
+        for (int r1 = lane; r1 < n1; r1 += 32) bulk_g2s(d + r1 * RS, src + r1 * kSplitN2, kLineBytes, &ld_bar);
+    };
+    auto store_row = [&](double2* dst) {
+        for (int r1 = lane; r1 < n1; r1 += 32) bulk_s2g(dst + r1 * kSplitN2, d + r1 * RS, kLineBytes);
+        bulk_commit();
+    };
     const long long V = (long long)N * N, items = chains * N;
     auto pad = [&](int i) { return i + (i >> kSplitLog2N2); };          // element i = 64 r1 + r2 of the row in the padded tile
     auto twiddle = [&](int i) {                                         // d[p][r2] *= W_N^{r2 k1(p)}
@@ -469,12 +516,12 @@ __global__ void __launch_bounds__(512) correlation_rows_split_kernel(const real*
     };
     // the n1-point transforms down the tile (one per r2) together with the twiddle W_N^{r2 k1(p)} between the two steps
     auto tw_of = [&](int r2, int p) {
-        const int t = r2 * fft64_freq(p);
+        const int t = r2 * split_freq(p, log2n1);
         return cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
     };
     auto outer = [&](bool dif) {
-        if (log2n1 == 6) {
-            if (dif) fft64<true>(d, RS, 1, kSplitLog2N2, w64, tw_of); else fft64<false>(d, RS, 1, kSplitLog2N2, w64, tw_of);
+        if (log2n1 >= 4) {
+            if (dif) fft_n1<true>(d, RS, 1, kSplitLog2N2, log2n1, tw1, tw_of); else fft_n1<false>(d, RS, 1, kSplitLog2N2, log2n1, tw1, tw_of);
         } else if (dif) {
             fft_tile_rows<true, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
             for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
@@ -485,90 +532,148 @@ __global__ void __launch_bounds__(512) correlation_rows_split_kernel(const real*
             fft_tile_rows<false, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
         }
     };
+    __syncthreads();
+    if (!FIRST && warp == 0 && blockIdx.x < items) load_row(out + (long long)blockIdx.x * N);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const long long chain = item / N;
+        const long long chain = item / N, next = item + gridDim.x;
         const int x0 = (int)(item - chain * N);
         double2* o = out + chain * V + (long long)x0 * N;
-        __syncthreads();
         if (FIRST) {
             const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
-            for (int x1 = threadIdx.x; x1 < N; x1 += blockDim.x) {
-                const long long at = (long long)x0 * N + x1;
-                if (KIND == SVB_CORR_WINDING) {
+            if (KIND != SVB_CORR_WINDING && threadIdx.x == 0 && next < items)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(field + next * N), "r"((uint32_t)N * (uint32_t)sizeof(real)) : "memory");
+            if (warp == 0) bulk_wait_read0();                            // the previous row has left the tile
+            __syncthreads();
+            if (KIND == SVB_CORR_WINDING) {
+                for (int x1 = threadIdx.x; x1 < N; x1 += blockDim.x) {
+                    const long long at = (long long)x0 * N + x1;
                     const long long i0 = (long long)((x0 + 1) & (N - 1)) * N + x1, i1 = (long long)x0 * N + ((x1 + 1) & (N - 1));
                     d[pad(x1)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
-                } else {
-                    double sn, cs;
-                    const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[at]) / (double)W : (double)g[at];
-                    sincos(ang, &sn, &cs);
-                    d[pad(x1)] = make_double2(cs, sn);
+                }
+            } else {
+                constexpr int kBatch = 8;                                // loads in flight per thread ahead of the sincos
+                const real* row = g + (long long)x0 * N;
+                for (int xb = threadIdx.x; xb < N; xb += kBatch * blockDim.x) {
+                    real v[kBatch];
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        const int x1 = xb + j * blockDim.x;
+                        v[j] = x1 < N ? row[x1] : (real)0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        const int x1 = xb + j * blockDim.x;
+                        if (x1 < N) {
+                            double sn, cs;
+                            const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)v[j]) / (double)W : (double)v[j];
+                            sincos(ang, &sn, &cs);
+                            d[pad(x1)] = make_double2(cs, sn);
+                        }
+                    }
                 }
             }
             __syncthreads();
             outer(true);
             fft64<true>(d, 1, RS, log2n1, w64);                         // 64 contiguous elements per line, a thread per line and group
-            for (int i = threadIdx.x; i < N; i += blockDim.x) o[i] = d[pad(i)];
-        } else {
-            for (int i = threadIdx.x; i < N; i += blockDim.x) d[pad(i)] = o[i];
+            fence_proxy_async();
             __syncthreads();
+            if (warp == 0) store_row(o);
+        } else {
+            if (threadIdx.x == 0 && next < items)                        // (its copy into the tile is issued once this row has left)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(out + next * N), "r"((uint32_t)N * (uint32_t)sizeof(double2)) : "memory");
+            mbar_wait(&ld_bar, ld_parity);
+            ld_parity ^= 1u;
             fft64<false>(d, 1, RS, log2n1, w64);
             outer(false);
-            for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const double2 v = d[pad(i)];
-                o[i] = make_double2(v.x * scale, v.y * scale);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                store_row(o);
+                if (next < items) {
+                    bulk_wait_read0();                                   // ... and only then may the next row land in the tile
+                    load_row(out + next * N);
+                }
             }
         }
     }
+    if (warp == 0) bulk_wait0();
 }
 
 // visits A (FIRST: DIF over r1, then W_N^{r2 bitrev(p)}) and A' (!FIRST: DIT over k1): a tile = (chain, r2, 32 columns)
 template <bool FIRST>
-__global__ void __launch_bounds__(256) correlation_split_outer_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) correlation_split_outer_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n1 = 1 << log2n1;
     double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][32]
-    double2* tw = d + (size_t)n1 * kSplitCols;                          // n1 / 2 twiddles of the n1-point transform
-    double2* tq = tw + n1 / 2;                                          // n1 twiddles W_N^{r2 k1(p)}
-    double2* w64 = tq + n1;                                             // W_64^t, t < 64
-    fft_twiddles(tw, n1);
-    fft64_twiddles(w64);
+    double2* tw = d + (size_t)n1 * kSplitCols;                          // W_n1^t, t < n1 (radix passes, n1 >= 16) or t < n1 / 2 (radix-2 stages)
+    double2* tq = tw + n1;                                              // n1 twiddles W_N^{r2 k1(p)}
+    if (log2n1 >= 4) fft_n1_twiddles(tw, n1); else fft_twiddles(tw, n1);
     const long long V = (long long)N * N;
     const int col_blocks = N / kSplitCols;
     const long long items = chains * kSplitN2 * col_blocks;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    // tiles travel as bulk copies (TMA), a row of 32 columns (512 bytes) each, issued by warp 0; the next tile is requested
+    // the moment this one has left shared memory
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    constexpr uint32_t kRowBytes = kSplitCols * sizeof(double2);
+    const long long row_step = (long long)kSplitN2 * N;
+    auto tile_of = [&](long long item, int& r2) {
         const long long chain = item / (kSplitN2 * col_blocks);
         const int rem = (int)(item - chain * (kSplitN2 * col_blocks));
-        const int r2 = rem / col_blocks, c0 = (rem - r2 * col_blocks) * kSplitCols;
-        double2* o = out + chain * V + (long long)r2 * N + c0;
-        __syncthreads();
+        r2 = rem / col_blocks;
+        return out + chain * V + (long long)r2 * N + (rem - r2 * col_blocks) * kSplitCols;
+    };
+    auto load_tile = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)n1 * kRowBytes);
+        __syncwarp();
+        for (int r1 = lane; r1 < n1; r1 += 32) bulk_g2s(d + r1 * kSplitCols, src + r1 * row_step, kRowBytes, &ld_bar);
+    };
+    __syncthreads();
+    int r2 = 0;
+    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x, r2));
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long next = item + gridDim.x;
+        double2* o = tile_of(item, r2);
         if (FIRST)
-            for (int p = threadIdx.x; p < n1; p += blockDim.x) {
+            for (int p = threadIdx.x; p < n1; p += blockDim.x) {        // (the previous tile's last pass ended in a barrier)
                 const int k1 = split_freq(p, log2n1);
                 double sn, cs;
                 sincospi(-2.0 * (double)((r2 * k1) & (N - 1)) / (double)N, &sn, &cs);
                 tq[p] = make_double2(cs, sn);
             }
-        for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) {
-            const int r1 = i >> kSplitLog2Cols, c = i & (kSplitCols - 1);
-            d[i] = o[(long long)r1 * kSplitN2 * N + c];
-        }
-        __syncthreads();
-        if (log2n1 == 6) fft64<FIRST>(d, kSplitCols, 1, kSplitLog2Cols, w64);
-        else fft_tile_rows<FIRST>(d, n1, log2n1, tw);
-        for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) {
-            const int r1 = i >> kSplitLog2Cols, c = i & (kSplitCols - 1);
-            double2 v = d[i];
+        mbar_wait(&ld_bar, ld_parity);
+        ld_parity ^= 1u;
+        if (log2n1 >= 4) {
+            if constexpr (FIRST) fft_n1<true>(d, kSplitCols, 1, kSplitLog2Cols, log2n1, tw, [&](int, int p) { return tq[p]; });
+            else fft_n1<false>(d, kSplitCols, 1, kSplitLog2Cols, log2n1, tw);
+        } else {
+            if (FIRST) __syncthreads();                                 // tq
+            fft_tile_rows<FIRST>(d, n1, log2n1, tw);
             if (FIRST) {
-                const double2 w = tq[r1];
-                v = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+                for (int i = threadIdx.x; i < n1 * kSplitCols; i += blockDim.x) d[i] = cmul(d[i], tq[i >> kSplitLog2Cols]);
+                __syncthreads();
             }
-            o[(long long)r1 * kSplitN2 * N + c] = v;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            for (int r1 = lane; r1 < n1; r1 += 32) bulk_s2g(o + r1 * row_step, d + r1 * kSplitCols, kRowBytes);
+            bulk_commit();
+            if (next < items) {
+                int r2n;
+                const double2* src = tile_of(next, r2n);
+                bulk_wait_read0();
+                load_tile(src);
+            }
         }
     }
+    if (warp == 0) bulk_wait0();
 }
 
 // visit B: a tile = (chain, p, 32 columns) = 64 consecutive rows: DIF over r2, |.|^2, DIT over k2, W_N^{bitrev(p) r2'}
-__global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64][32]
     double2* w64 = d + (size_t)kSplitN2 * kSplitCols;                   // W_64^t, t < 64
@@ -577,33 +682,57 @@ __global__ void __launch_bounds__(256) correlation_split_inner_kernel(long long 
     const long long V = (long long)N * N;
     const int n1 = 1 << log2n1, col_blocks = N / kSplitCols;
     const long long items = chains * n1 * col_blocks;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    constexpr uint32_t kRowBytes = kSplitCols * sizeof(double2);
+    auto tile_of = [&](long long item, int& p) {
         const long long chain = item / (n1 * col_blocks);
         const int rem = (int)(item - chain * (n1 * col_blocks));
-        const int p = rem / col_blocks, c0 = (rem - p * col_blocks) * kSplitCols;
+        p = rem / col_blocks;
+        return out + chain * V + (long long)p * kSplitN2 * N + (rem - p * col_blocks) * kSplitCols;
+    };
+    auto load_tile = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)kSplitN2 * kRowBytes);
+        __syncwarp();
+        for (int r = lane; r < kSplitN2; r += 32) bulk_g2s(d + r * kSplitCols, src + (long long)r * N, kRowBytes, &ld_bar);
+    };
+    __syncthreads();
+    int p = 0;
+    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x, p));
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long next = item + gridDim.x;
+        double2* o = tile_of(item, p);
         const int k1 = split_freq(p, log2n1);
-        double2* o = out + chain * V + (long long)p * kSplitN2 * N + c0;
-        __syncthreads();
-        for (int r = threadIdx.x; r < kSplitN2; r += blockDim.x) {
+        for (int r = threadIdx.x; r < kSplitN2; r += blockDim.x) {       // (the previous tile's last pass ended in a barrier)
             double sn, cs;
             sincospi(-2.0 * (double)((k1 * r) & (N - 1)) / (double)N, &sn, &cs);
             tq[r] = make_double2(cs, sn);
         }
-        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) d[i] = o[(long long)(i >> kSplitLog2Cols) * N + (i & (kSplitCols - 1))];
-        __syncthreads();
+        mbar_wait(&ld_bar, ld_parity);
+        ld_parity ^= 1u;
         fft64<true>(d, kSplitCols, 1, kSplitLog2Cols, w64);
         for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
             const double2 v = d[i];
             d[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
         }
         __syncthreads();
-        fft64<false>(d, kSplitCols, 1, kSplitLog2Cols, w64);
-        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
-            const int r = i >> kSplitLog2Cols;
-            const double2 v = d[i], w = tq[r];
-            o[(long long)r * N + (i & (kSplitCols - 1))] = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+        fft64<false>(d, kSplitCols, 1, kSplitLog2Cols, w64, NoScale(), [&](int, int r) { return tq[r]; });
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            for (int r = lane; r < kSplitN2; r += 32) bulk_s2g(o + (long long)r * N, d + r * kSplitCols, kRowBytes);
+            bulk_commit();
+            if (next < items) {
+                int pn;
+                const double2* src = tile_of(next, pn);
+                bulk_wait_read0();
+                load_tile(src);
+            }
         }
     }
+    if (warp == 0) bulk_wait0();
 }
 
 }  // namespace svb
@@ -640,7 +769,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const bool split = N >= split_min && N >= 2 * kSplitN2;
     const double V = (double)N * (double)N;
     const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
-    const size_t smem_rsplit = ((size_t)n1_rows * (kSplitN2 + 1) + (n1_rows > 1 ? n1_rows / 2 : 1) + 3 * kSplitN2) * sizeof(double2);
+    const size_t smem_rsplit = ((size_t)n1_rows * (kSplitN2 + 1) + n1_rows + 3 * kSplitN2) * sizeof(double2);
     auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
     auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
     long long cap_rsplit = 0;
@@ -663,7 +792,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     SVB_CUDA_TRY(cudaGetLastError());
     if (split) {
         const int log2n1 = log2n - kSplitLog2N2, n1 = 1 << log2n1;
-        const size_t smem_outer = ((size_t)n1 * kSplitCols + n1 / 2 + n1 + kSplitN2) * sizeof(double2);
+        const size_t smem_outer = ((size_t)n1 * kSplitCols + 2 * n1) * sizeof(double2);
         const size_t smem_inner = ((size_t)kSplitN2 * kSplitCols + 2 * kSplitN2) * sizeof(double2);
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_split_outer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));

@@ -196,11 +196,12 @@ def test_fft_correlators_match_the_reference_formula(N):
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize('N', [128, 256, 1024])
+@pytest.mark.parametrize('N', [128, 256, 512, 1024, 2048])
 def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
     """The transforms of the biggest lattices (N >= 1024) run in two steps, r = 64 r1 + r2 (correlation_split_*_kernel).
     With the threshold lowered the same kernels serve sizes that can be compared element by element with the restated
-    Lattice.correlation (compact.py:465-536): n1 = N / 64 = 2, 4 and 16 rows per outer transform, 1e-12."""
+    Lattice.correlation (compact.py:465-536): n1 = N / 64 = 2, 4, 8 rows per outer transform (radix-2 stages) and 16, 32 (two
+    radix passes, as the 64 of L = 4096), 1e-12."""
     monkeypatch.setenv('SVB_CORR_SPLIT_MIN_N', '128')
     rng = np.random.default_rng(N + 1)
     chains = 3 if N <= 256 else 1

@@ -627,7 +627,7 @@ def test_swapping_tiled_sweeps_equal_the_in_place_ones(N, path, sweeps_per_step)
     assert torch.equal(E.fields[0], phi) and torch.equal(E.fields[1], n)
 
 
-@pytest.mark.parametrize('kind', ['villain', 'worldline'])
+@pytest.mark.parametrize('kind', ['villain', 'villain128', 'worldline'])
 def test_overlapped_launch_protocol_soak(kind):
     """compute-sanitizer cannot run on this pool, so the epoch protocol of the overlapped launches is soaked instead: 2000
     back-to-back steps on each of TWO interleaved chain sets whose chain count (5000, 3000) is far above the grid (1184
@@ -635,8 +635,12 @@ def test_overlapped_launch_protocol_soak(kind):
     epoch would load a chain before its previous store landed; the final fields and the accepted totals must equal those
     of 2000 ordinary (fully serialised) launches bit for bit."""
     K, kappa, seed = 2000, 0.5, 31
-    if kind == 'villain':
-        N = 32
+    if kind.startswith('villain'):
+        # N = 128 is the strips kernel (one chain per CTA of a 148-CTA grid, the next chain's first strips requested while
+        # the last passes of this one still run): 400 steps of 700 and 300 chains
+        N = 128 if kind == 'villain128' else 32
+        if N == 128:
+            K = 400
         S = svb.Villain(svb.Lattice2D(N), kappa)
         make = lambda a, b, c0: ops.VillainOverlappedSweeps(a, b, kappa, seed=seed, chain0=c0)
         plain = lambda a, b, c0, k, obs: ops.villain_sweep(a, b, kappa, seed=seed, sweep0=k, chain0=c0, obs=obs)
@@ -647,7 +651,7 @@ def test_overlapped_launch_protocol_soak(kind):
         make = lambda a, b, c0: ops.WorldlineOverlappedSweeps(a, b, kappa, seed=seed, chain0=c0)
         plain = lambda a, b, c0, k, obs: ops.worldline_sweep(a, b, kappa, seed=seed, sweep0=k, chain0=c0, obs=obs)
         nobs = 7
-    counts = (5000, 3000) if kind == 'villain' else (1500, 700)
+    counts = {'villain': (5000, 3000), 'villain128': (700, 300), 'worldline': (1500, 700)}[kind]
     sets = [svb.BatchedEnsemble(S, c)._start('hot', 50 + i) for i, c in enumerate(counts)]
     refs = [(a.clone(), b.clone()) for a, b in sets]
     steppers = [make(a, b, 1000 * i) for i, (a, b) in enumerate(sets)]
@@ -657,7 +661,7 @@ def test_overlapped_launch_protocol_soak(kind):
     scratch = [torch.zeros((c, nobs), dtype=torch.float64, device='cuda') for c in counts]
     for k in range(K):
         for i, st in enumerate(steppers):
-            if kind == 'villain':
+            if kind.startswith('villain'):
                 st.step(k, 1, obs=recs[i][k], obs_in=recs[i][k - 1] if k else scratch[i])
             else:
                 st.step(k, 1, obs=recs[i][k])

@@ -6,6 +6,13 @@ from supervillain_b200 import ops
 N = int(os.environ.get('KB_L', 4096))
 phi = torch.rand((1, 1, N, N), dtype=torch.float64, device='cuda')
 out = torch.empty((1, N, N, 2), dtype=torch.float64, device='cuda')
-for _ in range(int(os.environ.get('KB_STEPS', 3))):
-    ops.villain_spin_spin(phi, out=out)
+steps = int(os.environ.get('KB_STEPS', 3))
+ops.villain_spin_spin(phi, out=out)
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
+t0.record()
+for _ in range(steps):
+    ops.villain_spin_spin(phi, out=out)
+t1.record()
+torch.cuda.synchronize()
+print(f'L={N} spin_spin {1e3 * t0.elapsed_time(t1) / steps:.1f} us per call ({steps} calls, lib {os.environ.get("SVB200_LIB", "default")})')
