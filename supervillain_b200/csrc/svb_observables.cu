@@ -113,11 +113,14 @@ template <> __device__ __forceinline__ void dft_r<4>(double2 (&x)[4]) { dft4(x);
 // `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
 // DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
 struct NoScale {};
+struct Norm2 {};                                                      // as the Scale of a DIF transform: every output element x -> |x|^2
 // `oscale(line, position)` (optional, DIT only): a factor for every element of the OUTPUT of a decimation-in-time transform.
 template <bool DIF, int RA, int RB, class Scale = NoScale, class OutScale = NoScale>
 __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, int lane_stride, int lanes_log2,
                                        const double2* __restrict__ wn, Scale scale = Scale(), OutScale oscale = OutScale()) {
-    constexpr bool SCALED = !std::is_same<Scale, NoScale>::value;
+    constexpr bool NORM2 = std::is_same<Scale, Norm2>::value;
+    constexpr bool SCALED = !std::is_same<Scale, NoScale>::value && !NORM2;
+    static_assert(!(NORM2 && !DIF), "|.|^2 is taken on the output of a decimation-in-frequency transform");
     constexpr bool OSCALED = !std::is_same<OutScale, NoScale>::value;
     static_assert(!(OSCALED && DIF), "an output factor is for decimation-in-time transforms");
     const int lmask = (1 << lanes_log2) - 1;
@@ -167,6 +170,12 @@ __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, 
                 if (!first) {
 #pragma unroll
                     for (int k = 0; k < RB; ++k) x[k] = cmul(x[k], scale(lane, RB * g + k));
+                }
+            }
+            if constexpr (NORM2) {
+                if (!first) {
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) x[k] = make_double2(x[k].x * x[k].x + x[k].y * x[k].y, 0.0);
                 }
             }
 #pragma unroll
@@ -243,8 +252,10 @@ __global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __rest
         double2* d = reinterpret_cast<double2*>(smem_raw);             // [N][N + 1]
         double2* wn = d + N * RS;
         fft_rr_twiddles<NT>(wn);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
             const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+            if (warp == 0) bulk_wait_read0();                           // the previous chain's result has left the tile
             __syncthreads();
             for (int i = threadIdx.x; i < V; i += blockDim.x) {
                 const int x0 = i >> L2, x1 = i & (N - 1);
@@ -260,20 +271,19 @@ __global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __rest
             }
             __syncthreads();
             fft_rr<true, RA, RB>(d, 1, RS, L2, wn);                     // along x1, a thread per row and group
-            fft_rr<true, RA, RB>(d, RS, 1, L2, wn);                     // along x0, a thread per column and group
-            for (int i = threadIdx.x; i < V; i += blockDim.x) {
-                double2* q = d + (i >> L2) * RS + (i & (N - 1));
-                const double2 v = *q;
-                *q = make_double2(v.x * v.x + v.y * v.y, 0.0);
-            }
-            __syncthreads();
+            fft_rr<true, RA, RB>(d, RS, 1, L2, wn, Norm2());            // along x0, a thread per column and group; |.|^2 on the way out
             fft_rr<false, RA, RB>(d, RS, 1, L2, wn);
-            fft_rr<false, RA, RB>(d, 1, RS, L2, wn);
-            for (int i = threadIdx.x; i < V; i += blockDim.x) {
-                const double2 v = d[(i >> L2) * RS + (i & (N - 1))];
-                *reinterpret_cast<double2*>(out + (chain * V + i) * 2) = make_double2(v.x * scale, v.y * scale);
+            fft_rr<false, RA, RB>(d, 1, RS, L2, wn, NoScale(), [&](int, int) { return make_double2(scale, 0.0); });
+            // the result leaves as bulk copies (TMA), a row each, while the next chain's field is being read
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                double2* o = reinterpret_cast<double2*>(out) + chain * V;
+                for (int r = lane; r < N; r += 32) bulk_s2g(o + r * N, d + r * RS, (uint32_t)(N * sizeof(double2)));
+                bulk_commit();
             }
         }
+        if (warp == 0) bulk_wait0();
     }
 }
 
@@ -712,12 +722,7 @@ __global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long lo
         }
         mbar_wait(&ld_bar, ld_parity);
         ld_parity ^= 1u;
-        fft64<true>(d, kSplitCols, 1, kSplitLog2Cols, w64);
-        for (int i = threadIdx.x; i < kSplitN2 * kSplitCols; i += blockDim.x) {
-            const double2 v = d[i];
-            d[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
-        }
-        __syncthreads();
+        fft64<true>(d, kSplitCols, 1, kSplitLog2Cols, w64, Norm2());    // ... |.|^2 on the way out of its second pass
         fft64<false>(d, kSplitCols, 1, kSplitLog2Cols, w64, NoScale(), [&](int, int r) { return tq[r]; });
         fence_proxy_async();
         __syncthreads();
@@ -830,11 +835,15 @@ static int launch_correlation_fft(const void* field, long long chains, int W, do
     auto kern = correlation_fft_kernel<real, KIND, NT>;
     const size_t smem = (size_t)(NT * (NT + 1) + NT) * sizeof(double2);      // the padded tile and the N twiddles (>= the radix-2 layout)
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a thread per radix-8 butterfly of a pass (N^2 / 8 of them): more threads than that idle through half of the passes
+    int threads = NT == 64 ? 256 : NT == 32 ? 128 : 64;
+    if (const char* e = getenv("SVB_CORR_FFT_THREADS")) threads = atoi(e);
+    if (threads < 32 || threads > 256 || threads % 32) return fail(SVB_E_PARAM, "SVB_CORR_FFT_THREADS=%d", threads);
     int per_sm = 0;
-    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long cap = (long long)per_sm * sms;
-    kern<<<(unsigned)(chains < cap ? chains : cap), 256, smem, st>>>(reinterpret_cast<const real*>(field), chains, W, out);
+    kern<<<(unsigned)(chains < cap ? chains : cap), threads, smem, st>>>(reinterpret_cast<const real*>(field), chains, W, out);
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }
