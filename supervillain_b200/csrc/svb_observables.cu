@@ -112,6 +112,10 @@ template <> __device__ __forceinline__ void dft_r<4>(double2 (&x)[4]) { dft4(x);
 // Consecutive threads take consecutive lines.
 // `scale(line, position)` (optional): a factor for every element, applied to the OUTPUT of a DIF transform and to the INPUT of a
 // DIT one -- the twiddle between the two steps of the split rides along instead of costing a pass over shared memory.
+#ifndef SVB_FFT_UNROLL
+#define SVB_FFT_UNROLL 1
+#endif
+constexpr int kFftUnroll = SVB_FFT_UNROLL;                            // butterflies of a pass in flight per thread
 struct NoScale {};
 struct Norm2 {};                                                      // as the Scale of a DIF transform: every output element x -> |x|^2
 // `oscale(line, position)` (optional, DIT only): a factor for every element of the OUTPUT of a decimation-in-time transform.
@@ -125,6 +129,7 @@ __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, 
     static_assert(!(OSCALED && DIF), "an output factor is for decimation-in-time transforms");
     const int lmask = (1 << lanes_log2) - 1;
     auto pass_a = [&](bool first) {                               // RA-point transforms over a, one per (line, b)
+#pragma unroll kFftUnroll
         for (int i = threadIdx.x; i < (RB << lanes_log2); i += blockDim.x) {
             const int g = i >> lanes_log2, lane = i & lmask;
             double2* base = d + lane * lane_stride + g * pos_stride;
@@ -149,6 +154,7 @@ __device__ __forceinline__ void fft_rr(double2* __restrict__ d, int pos_stride, 
         __syncthreads();
     };
     auto pass_b = [&](bool first) {                               // RB-point transforms over b, one per (line, a)
+#pragma unroll kFftUnroll
         for (int i = threadIdx.x; i < (RA << lanes_log2); i += blockDim.x) {
             const int g = i >> lanes_log2, lane = i & lmask;
             double2* base = d + lane * lane_stride + RB * g * pos_stride;
@@ -480,7 +486,7 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
 // W_N^t = W_N^{64 (t >> 6)} W_N^{t & 63}.  FIRST: s from the field, A, twiddle, B, written in the mixed order (p, q) <-> k =
 // bitrev(p) + n1 bitrev(q) that every later pass works in; !FIRST: B', twiddle, A', scaling -- natural order out.
 template <typename real, int KIND, bool FIRST>
-__global__ void __launch_bounds__(512) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
+__global__ void __launch_bounds__(256, 3) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
                                                                      double scale, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n1 = 1 << log2n1;
@@ -778,8 +784,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
     auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
     long long cap_rsplit = 0;
-    int rows_threads = 256;                                       // (512, an item of a radix-8 pass per thread at N = 4096: 1039 against 860 us)
-    if (const char* e = getenv("SVB_CORR_ROWS_THREADS")) rows_threads = atoi(e);
+    const int rows_threads = 256;                                 // (512, an item of a radix-8 pass per thread at N = 4096: 1039 against 860 us)
     if (split) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
