@@ -8,6 +8,7 @@
 // non-power-of-two lattices (exact to rounding), a shared-memory FFT for N = 16, 32, 64, and a three-launch FFT for
 // power-of-two lattices up to N = 4096.
 
+#include <cstring>
 #include <type_traits>
 #include "svb_common.cuh"
 
@@ -483,21 +484,59 @@ __device__ __forceinline__ void fft_tile_rows(double2* __restrict__ d, int n, in
 // the row is element (r1, r2) of an n1 x 64 tile, so step A is a transform down the tile's rows (a thread per column:
 // conflict-free, twiddles broadcast) and step B one of 64 contiguous elements per line (a warp per line).  The 4096-point
 // transform with strided twiddles it replaces ran at a seventh of this.  W_N^{t}, t = r2 k1 < 4096, comes from two tables of 64:
-// W_N^t = W_N^{64 (t >> 6)} W_N^{t & 63}.  FIRST: s from the field, A, twiddle, B, written in the mixed order (p, q) <-> k =
-// bitrev(p) + n1 bitrev(q) that every later pass works in; !FIRST: B', twiddle, A', scaling -- natural order out.
+// W_N^t = W_N^{64 (t >> 6)} W_N^{t & 63}.  FIRST: s from the field, A, twiddle, B, written in the mixed order that every
+// later pass works in; !FIRST: B', twiddle, A', scaling -- natural order out.
+// An item is R = 2^log2r consecutive rows (R N = 4096 elements for N <= 512, one row beyond): n1 R lines of 64.  Step A is two
+// radix passes for n1 >= 16 (R = 1) and ONE pass of n1-point transforms in registers for n1 <= 8 (natural order in and out).
+template <int N1>
+__device__ __forceinline__ void dft_small(double2 (&x)[N1]) {
+    if constexpr (N1 == 2) { const double2 a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
+    else if constexpr (N1 == 4) dft4(x);
+    else if constexpr (N1 == 8) dft8(x);
+}
+// n1-point transforms over elements `stride` apart, one per work item: item i starts at d[start(i)], tw(i, k) multiplies
+// output k of a decimation-in-frequency transform / input k of a decimation-in-time one
+template <int N1, bool DIF, class Start, class Tw>
+__device__ __forceinline__ void small_dft_pass(double2* __restrict__ d, int items, int stride, Start start, Tw tw) {
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        double2* base = d + start(i);
+        double2 x[N1];
+#pragma unroll
+        for (int j = 0; j < N1; ++j) x[j] = base[j * stride];
+        if constexpr (!DIF && !std::is_same<Tw, NoScale>::value) {
+#pragma unroll
+            for (int j = 0; j < N1; ++j) x[j] = cmul(x[j], tw(i, j));
+        }
+        dft_small<N1>(x);
+        if constexpr (DIF && !std::is_same<Tw, NoScale>::value) {
+#pragma unroll
+            for (int k = 0; k < N1; ++k) x[k] = cmul(x[k], tw(i, k));
+        }
+#pragma unroll
+        for (int k = 0; k < N1; ++k) base[k * stride] = x[k];
+    }
+    __syncthreads();
+}
+template <bool DIF, class Start, class Tw>
+__device__ __forceinline__ void small_dft_pass_n1(int log2n1, double2* __restrict__ d, int items, int stride, Start start, Tw tw) {
+    if (log2n1 == 1) small_dft_pass<2, DIF>(d, items, stride, start, tw);
+    else if (log2n1 == 2) small_dft_pass<4, DIF>(d, items, stride, start, tw);
+    else small_dft_pass<8, DIF>(d, items, stride, start, tw);
+}
+
 template <typename real, int KIND, bool FIRST>
-__global__ void __launch_bounds__(256, 3) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
-                                                                     double scale, double2* __restrict__ out) {
+__global__ void __launch_bounds__(256, 3) correlation_rows_split_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int log2r,
+                                                                        int W, double scale, double2* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n1 = 1 << log2n1;
+    const int n1 = 1 << log2n1, lines = n1 << log2r, log2lines = log2n1 + log2r;
+    const int E = N << log2r;                                           // elements of an item
     constexpr int RS = kSplitN2 + 1;                                    // row stride of the tile: lines a bank group apart
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][64 (+1)]: the row
-    double2* tw1 = d + (size_t)n1 * RS;                                 // twiddles of the n1-point transform: W_n1^t, t < n1 (radix passes,
-                                                                        // n1 >= 16) or t < n1 / 2 (radix-2 stages)
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [lines][64 (+1)]: the rows
+    double2* tw1 = d + (size_t)lines * RS;                              // W_n1^t, t < n1 (radix passes, n1 >= 16)
     double2* w64 = tw1 + n1;                                            // W_64^t, t < 64
     double2* th = w64 + kSplitN2;                                       // W_N^{64 a}, a < 64
     double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
-    if (log2n1 >= 4) fft_n1_twiddles(tw1, n1); else fft_twiddles(tw1, n1);
+    if (log2n1 >= 4) fft_n1_twiddles(tw1, n1);
     fft64_twiddles(w64);
     for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
         double sn, cs;
@@ -506,108 +545,101 @@ __global__ void __launch_bounds__(256, 3) correlation_rows_split_kernel(const re
         sincospi(-2.0 * (double)i / (double)N, &sn, &cs);
         tl[i] = make_double2(cs * scale, sn * scale);                   // every element meets W_N^t exactly once: the scaling rides along
     }
-    // the row travels between global memory and the padded tile as bulk copies (TMA), a line of 64 elements each, issued by
-    // warp 0: nothing of it passes through registers, and the next row is on its way while this one is being written back
+    // the rows travel between global memory and the padded tile as bulk copies (TMA), a line of 64 elements each, issued by
+    // warp 0: nothing of them passes through registers, and the next item is on its way while this one is being written back
     __shared__ __align__(8) uint64_t ld_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
     constexpr uint32_t kLineBytes = kSplitN2 * sizeof(double2);
-    auto load_row = [&](const double2* src) {
-        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)N * (uint32_t)sizeof(double2));
+    auto load_rows = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)E * (uint32_t)sizeof(double2));
         __syncwarp();
-        for (int r1 = lane; r1 < n1; r1 += 32) bulk_g2s(d + r1 * RS, src + r1 * kSplitN2, kLineBytes, &ld_bar);
+        for (int l = lane; l < lines; l += 32) bulk_g2s(d + l * RS, src + l * kSplitN2, kLineBytes, &ld_bar);
     };
-    auto store_row = [&](double2* dst) {
-        for (int r1 = lane; r1 < n1; r1 += 32) bulk_s2g(dst + r1 * kSplitN2, d + r1 * RS, kLineBytes);
+    auto store_rows = [&](double2* dst) {
+        for (int l = lane; l < lines; l += 32) bulk_s2g(dst + l * kSplitN2, d + l * RS, kLineBytes);
         bulk_commit();
     };
-    const long long V = (long long)N * N, items = chains * N;
-    auto pad = [&](int i) { return i + (i >> kSplitLog2N2); };          // element i = 64 r1 + r2 of the row in the padded tile
-    auto twiddle = [&](int i) {                                         // d[p][r2] *= W_N^{r2 k1(p)}
-        const int p = i >> kSplitLog2N2, r2 = i & (kSplitN2 - 1);
-        const int t = r2 * split_freq(p, log2n1);
-        const double2 w = cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
-        d[pad(i)] = cmul(d[pad(i)], w);
-    };
-    // the n1-point transforms down the tile (one per r2) together with the twiddle W_N^{r2 k1(p)} between the two steps
-    auto tw_of = [&](int r2, int p) {
-        const int t = r2 * split_freq(p, log2n1);
+    const long long V = (long long)N * N, items = (chains * N) >> log2r;
+    const int items_per_chain = N >> log2r;
+    auto pad = [&](int i) { return i + (i >> kSplitLog2N2); };          // element i of the item (64 per line) in the padded tile
+    // W_N^{r2 k1}; with radix passes position p holds k1 = split_freq(p)
+    auto tw_nat = [&](int r2, int k1) {
+        const int t = r2 * k1;
         return cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
     };
-    auto outer = [&](bool dif) {
-        if (log2n1 >= 4) {
-            if (dif) fft_n1<true>(d, RS, 1, kSplitLog2N2, log2n1, tw1, tw_of); else fft_n1<false>(d, RS, 1, kSplitLog2N2, log2n1, tw1, tw_of);
-        } else if (dif) {
-            fft_tile_rows<true, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
-            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
-            __syncthreads();
-        } else {
-            for (int i = threadIdx.x; i < N; i += blockDim.x) twiddle(i);
-            __syncthreads();
-            fft_tile_rows<false, kSplitLog2N2>(d, n1, log2n1, tw1, RS);
-        }
+    auto tw_of = [&](int r2, int p) { return tw_nat(r2, split_freq(p, log2n1)); };
+    // the n1-point transforms down the tile (one per row and r2) together with the twiddle between the two steps
+    auto outer = [&](auto dif_tag) {
+        constexpr bool DIF = decltype(dif_tag)::value;
+        if (log2n1 >= 4) fft_n1<DIF>(d, RS, 1, kSplitLog2N2, log2n1, tw1, tw_of);
+        else
+            small_dft_pass_n1<DIF>(log2n1, d, kSplitN2 << log2r, RS,
+                                   [&](int i) { return (i >> kSplitLog2N2) * n1 * RS + (i & (kSplitN2 - 1)); },
+                                   [&](int i, int k) { return tw_nat(i & (kSplitN2 - 1), k); });
     };
     __syncthreads();
-    if (!FIRST && warp == 0 && blockIdx.x < items) load_row(out + (long long)blockIdx.x * N);
+    if (!FIRST && warp == 0 && blockIdx.x < items) load_rows(out + (long long)blockIdx.x * E);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const long long chain = item / N, next = item + gridDim.x;
-        const int x0 = (int)(item - chain * N);
-        double2* o = out + chain * V + (long long)x0 * N;
+        const long long chain = item / items_per_chain, next = item + gridDim.x;
+        const int x0 = (int)(item - chain * items_per_chain) << log2r;  // the first row of the item
+        double2* o = out + item * E;
         if (FIRST) {
             const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
             if (KIND != SVB_CORR_WINDING && threadIdx.x == 0 && next < items)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(field + next * N), "r"((uint32_t)N * (uint32_t)sizeof(real)) : "memory");
-            if (warp == 0) bulk_wait_read0();                            // the previous row has left the tile
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(field + next * E), "r"((uint32_t)E * (uint32_t)sizeof(real)) : "memory");
+            if (warp == 0) bulk_wait_read0();                            // the previous item has left the tile
             __syncthreads();
             if (KIND == SVB_CORR_WINDING) {
-                for (int x1 = threadIdx.x; x1 < N; x1 += blockDim.x) {
-                    const long long at = (long long)x0 * N + x1;
-                    const long long i0 = (long long)((x0 + 1) & (N - 1)) * N + x1, i1 = (long long)x0 * N + ((x1 + 1) & (N - 1));
-                    d[pad(x1)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
+                for (int e = threadIdx.x; e < E; e += blockDim.x) {
+                    const int r = x0 + (e >> (log2n1 + kSplitLog2N2)), x1 = e & (N - 1);
+                    const long long at = (long long)r * N + x1;
+                    const long long i0 = (long long)((r + 1) & (N - 1)) * N + x1, i1 = (long long)r * N + ((x1 + 1) & (N - 1));
+                    d[pad(e)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
                 }
             } else {
                 constexpr int kBatch = 8;                                // loads in flight per thread ahead of the sincos
-                const real* row = g + (long long)x0 * N;
-                for (int xb = threadIdx.x; xb < N; xb += kBatch * blockDim.x) {
+                const real* rows = g + (long long)x0 * N;
+                for (int eb = threadIdx.x; eb < E; eb += kBatch * blockDim.x) {
                     real v[kBatch];
 #pragma unroll
                     for (int j = 0; j < kBatch; ++j) {
-                        const int x1 = xb + j * blockDim.x;
-                        v[j] = x1 < N ? row[x1] : (real)0;
+                        const int e = eb + j * blockDim.x;
+                        v[j] = e < E ? rows[e] : (real)0;
                     }
 #pragma unroll
                     for (int j = 0; j < kBatch; ++j) {
-                        const int x1 = xb + j * blockDim.x;
-                        if (x1 < N) {
+                        const int e = eb + j * blockDim.x;
+                        if (e < E) {
                             double sn, cs;
                             const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)v[j]) / (double)W : (double)v[j];
                             sincos(ang, &sn, &cs);
-                            d[pad(x1)] = make_double2(cs, sn);
+                            d[pad(e)] = make_double2(cs, sn);
                         }
                     }
                 }
             }
             __syncthreads();
-            outer(true);
-            fft64<true>(d, 1, RS, log2n1, w64);                         // 64 contiguous elements per line, a thread per line and group
+            outer(std::true_type());
+            fft64<true>(d, 1, RS, log2lines, w64);                      // 64 contiguous elements per line, a thread per line and group
             fence_proxy_async();
             __syncthreads();
-            if (warp == 0) store_row(o);
+            if (warp == 0) store_rows(o);
         } else {
-            if (threadIdx.x == 0 && next < items)                        // (its copy into the tile is issued once this row has left)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(out + next * N), "r"((uint32_t)N * (uint32_t)sizeof(double2)) : "memory");
+            if (threadIdx.x == 0 && next < items)                        // (its copy into the tile is issued once this item has left)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(out + next * E), "r"((uint32_t)E * (uint32_t)sizeof(double2)) : "memory");
             mbar_wait(&ld_bar, ld_parity);
             ld_parity ^= 1u;
-            fft64<false>(d, 1, RS, log2n1, w64);
-            outer(false);
+            fft64<false>(d, 1, RS, log2lines, w64);
+            outer(std::false_type());
             fence_proxy_async();
             __syncthreads();
             if (warp == 0) {
-                store_row(o);
+                store_rows(o);
                 if (next < items) {
-                    bulk_wait_read0();                                   // ... and only then may the next row land in the tile
-                    load_row(out + next * N);
+                    bulk_wait_read0();                                   // ... and only then may the next item land in the tile
+                    load_rows(out + next * E);
                 }
             }
         }
@@ -746,6 +778,64 @@ __global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long lo
     if (warp == 0) bulk_wait0();
 }
 
+// The columns of 128 <= N <= 512 in ONE visit: a tile = (chain, CW = 4096 / N columns) holds whole columns, 4096 elements.
+// Row r = 64 r1 + r2 of the tile lives in slot (r2, r1) of a 64 x 64 array whose line index is L = r1 CW + c, so that the steps
+// of the split are: A, n1-point transforms in registers over r1 (elements CW apart) and W_N^{r2 k1}; B, 64-point transforms
+// over r2 for all 64 lines at once (two radix-8 passes, |.|^2 on the way out), the same back (W_N^{k1 r2'} on the way out);
+// A', n1-point transforms over k1.  Rows travel as bulk copies (TMA) of CW elements, straight into and out of their slots.
+__global__ void __launch_bounds__(256, 3) correlation_columns_fused_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int log2cw = kSplitLog2N2 - log2n1, CW = 1 << log2cw;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64 r2][64 lines]
+    double2* w64 = d + kSplitN2 * kSplitN2;                             // W_64^t, t < 64
+    double2* tN = w64 + kSplitN2;                                       // W_N^t, t < N
+    fft64_twiddles(w64);
+    fft_n1_twiddles(tN, N);
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    const long long V = (long long)N * N;
+    const int col_blocks = N >> log2cw;
+    const long long items = chains * col_blocks;
+    const uint32_t row_bytes = (uint32_t)CW * (uint32_t)sizeof(double2);
+    auto tile_of = [&](long long item) {
+        const long long chain = item / col_blocks;
+        return out + chain * V + ((item - chain * col_blocks) << log2cw);
+    };
+    auto slot = [&](int r) { return (((r & (kSplitN2 - 1)) << log2n1) + (r >> kSplitLog2N2)) << log2cw; };
+    auto load_tile = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)(kSplitN2 * kSplitN2 * sizeof(double2)));
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) bulk_g2s(d + slot(r), src + (long long)r * N, row_bytes, &ld_bar);
+    };
+    auto start = [&](int i) { return ((i >> log2cw) << kSplitLog2N2) + (i & (CW - 1)); };      // (r2, c): line c of slot row r2
+    __syncthreads();
+    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x));
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long next = item + gridDim.x;
+        double2* o = tile_of(item);
+        mbar_wait(&ld_bar, ld_parity);
+        ld_parity ^= 1u;
+        small_dft_pass_n1<true>(log2n1, d, kSplitN2 << log2cw, CW, start, [&](int i, int k) { return tN[(i >> log2cw) * k]; });
+        fft64<true>(d, kSplitN2, 1, kSplitLog2N2, w64, Norm2());
+        fft64<false>(d, kSplitN2, 1, kSplitLog2N2, w64, NoScale(), [&](int L, int q) { return tN[(L >> log2cw) * q]; });
+        small_dft_pass_n1<false>(log2n1, d, kSplitN2 << log2cw, CW, start, NoScale());
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            for (int r = lane; r < N; r += 32) bulk_s2g(o + (long long)r * N, d + slot(r), row_bytes);
+            bulk_commit();
+            if (next < items) {
+                const double2* src = tile_of(next);
+                bulk_wait_read0();
+                load_tile(src);
+            }
+        }
+    }
+    if (warp == 0) bulk_wait0();
+}
+
 }  // namespace svb
 
 using namespace svb;
@@ -777,10 +867,16 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     // element)
     int split_min = 1024;                                          // 8.4 M sites: 629 against 745 us at N = 1024, 669 against 594 us at N = 512
     if (const char* e = getenv("SVB_CORR_SPLIT_MIN_N")) split_min = atoi(e);
-    const bool split = N >= split_min && N >= 2 * kSplitN2;
+    // 128 <= N <= 512: the row kernels of the split with 4096 / N rows per item and ONE column kernel (whole columns of a
+    // 4096 / N-column tile in shared memory): three launches, every element read and written once by each
+    // (SVB_CORR_ROUTE=legacy: the radix-2 kernels they replace; SVB_CORR_SPLIT_MIN_N set: the five-launch split or legacy)
+    const char* route = getenv("SVB_CORR_ROUTE");
+    const bool mid = N <= 512 && !getenv("SVB_CORR_SPLIT_MIN_N") && !(route && !strcmp(route, "legacy"));
+    const bool split = mid || (N >= split_min && N >= 2 * kSplitN2);
     const double V = (double)N * (double)N;
     const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
-    const size_t smem_rsplit = ((size_t)n1_rows * (kSplitN2 + 1) + n1_rows + 3 * kSplitN2) * sizeof(double2);
+    const int log2r = mid ? 12 - log2n : 0, lines_rows = n1_rows << log2r;
+    const size_t smem_rsplit = ((size_t)lines_rows * (kSplitN2 + 1) + n1_rows + 3 * kSplitN2) * sizeof(double2);
     auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
     auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
     long long cap_rsplit = 0;
@@ -792,15 +888,24 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kr1, rows_threads, smem_rsplit));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the split row kernels", N);
         cap_rsplit = (long long)per_sm * sms;
-        const long long items = chains * N;
+        const long long items = (chains * N) >> log2r;
         kr1<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
-                                                                                           log2n1_rows, W, 1.0, o);
+                                                                                           log2n1_rows, log2r, W, 1.0, o);
     } else {
         k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                              log2n, W, R, o);
     }
     SVB_CUDA_TRY(cudaGetLastError());
-    if (split) {
+    if (mid) {
+        const size_t smem_fused = ((size_t)kSplitN2 * kSplitN2 + kSplitN2 + N) * sizeof(double2);
+        SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_columns_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
+        int per_sm = 0;
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, correlation_columns_fused_kernel, 256, smem_fused));
+        if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the fused column kernel", N);
+        const long long items = chains * (N >> (kSplitLog2N2 - (log2n - kSplitLog2N2))), cap = (long long)per_sm * sms;
+        correlation_columns_fused_kernel<<<(unsigned)(items < cap ? items : cap), 256, smem_fused, st>>>(chains, N, log2n - kSplitLog2N2, o);
+        SVB_CUDA_TRY(cudaGetLastError());
+    } else if (split) {
         const int log2n1 = log2n - kSplitLog2N2, n1 = 1 << log2n1;
         const size_t smem_outer = ((size_t)n1 * kSplitCols + 2 * n1) * sizeof(double2);
         const size_t smem_inner = ((size_t)kSplitN2 * kSplitCols + 2 * kSplitN2) * sizeof(double2);
@@ -824,9 +929,9 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         SVB_CUDA_TRY(cudaGetLastError());
     }
     if (split) {
-        const long long items = chains * N;
+        const long long items = (chains * N) >> log2r;
         kr2<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
-                                                                                           log2n1_rows, W, 1.0 / (V * V), o);
+                                                                                           log2n1_rows, log2r, W, 1.0 / (V * V), o);
     } else {
         correlation_rows_inverse_kernel<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(chains, N, log2n, R,
                                                                                                                          1.0 / (V * V), o);

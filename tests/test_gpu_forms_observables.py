@@ -219,6 +219,36 @@ def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
     np.testing.assert_allclose(Cs, whole, rtol=0, atol=1e-13)
 
 
+@pytest.mark.parametrize('N,chains', [(128, 5), (256, 3), (512, 2)])
+def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypatch):
+    """128 <= N <= 512 (config 4's lattices): the row kernels of the split with 4096 / N rows per item and the fused
+    column kernel (correlation_columns_fused_kernel), all three kinds, against the restated Lattice.correlation
+    (compact.py:465-536) to 1e-12 and against the radix-2 kernels they replace (SVB_CORR_ROUTE=legacy)."""
+    monkeypatch.delenv('SVB_CORR_SPLIT_MIN_N', raising=False)
+    monkeypatch.delenv('SVB_CORR_ROUTE', raising=False)
+    rng = np.random.default_rng(N + 7)
+    phi = rng.uniform(-7, 7, (chains, 1, N, N))
+    n = rng.integers(-3, 4, (chains, 2, N, N))
+    v = rng.integers(-4, 5, (chains, 1, N, N))
+    tphi, tn, tv = torch.from_numpy(phi).cuda(), torch.from_numpy(n).to(torch.int32).cuda(), torch.from_numpy(v).to(torch.int32).cuda()
+    Cs = ops.villain_spin_spin(tphi).cpu().numpy()
+    Cs32 = ops.villain_spin_spin(tphi.to(torch.float32)).cpu().numpy()
+    Cw = ops.correlation('winding', tn).cpu().numpy()
+    Cv = ops.correlation('vortex', tv, W=3).cpu().numpy()
+    monkeypatch.setenv('SVB_CORR_ROUTE', 'legacy')
+    legacy = ops.villain_spin_spin(tphi).cpu().numpy()
+    np.testing.assert_allclose(Cs, legacy, rtol=0, atol=1e-13)
+    for c in range(chains):
+        s = np.exp(1j * phi[c, 0])
+        np.testing.assert_allclose(Cs[c], lat.correlation(s, s), rtol=0, atol=1e-12)
+        s32 = np.exp(1j * phi[c, 0].astype(np.float32).astype(np.float64))
+        np.testing.assert_allclose(Cs32[c], lat.correlation(s32, s32), rtol=0, atol=1e-12)
+        dn = lat.d1(n[c])[0].astype(np.float64)
+        np.testing.assert_allclose(Cw[c], lat.correlation(dn, dn), rtol=0, atol=1e-12 * max(1.0, np.abs(dn).max() ** 2))
+        e = np.exp(2j * np.pi * v[c, 0] / 3)
+        np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
+
+
 def test_fft_correlator_of_a_config5_lattice_properties():
     """L = 4096 (config 5), too large to compare element by element in a test: size-independent properties of
     Lattice.correlation instead -- C[0] = mean |s|^2 = 1 for a spin field, C[-r] = conj(C[r]), sum_r C[r] = N^2 |mean s|^2 ...
