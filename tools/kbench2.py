@@ -110,7 +110,7 @@ if 'forms' in which:
         phi = torch.rand((CH, 1, N, N), dtype=torch.float64, device='cuda')
         out = torch.empty((CH, N, N, 2), dtype=torch.float64, device='cuda')
         # three launches: field in (8 B), rows out (16), columns in + out (32), rows in + out (32) per site
-        report(f'spin_spin correlator L={N} x {CH} (three-launch FFT)', CH * N * N, 88, timeit(lambda: ops.villain_spin_spin(phi, out=out), n=3, reps=2))
+        report(f'spin_spin correlator L={N} x {CH} ({"three" if N <= 512 else "five"}-launch FFT)', CH * N * N, 88, timeit(lambda: ops.villain_spin_spin(phi, out=out), n=3, reps=2))
 if 'dec' in which:
     N, CH = 32, 4096                                     # config-2 shape: the decoupled Villain updates and the Hammer sequence
     S = svb.Villain(svb.Lattice2D(N), 0.5)
