@@ -102,7 +102,37 @@ __device__ __forceinline__ void dft4(double2 (&x)[4]) {
     const double2 c0 = cadd(x[0], x[2]), c1 = cadd(x[1], x[3]), d0 = csub(x[0], x[2]), d1 = mul_mi(csub(x[1], x[3]));
     x[0] = cadd(c0, c1); x[1] = cadd(d0, d1); x[2] = csub(c0, c1); x[3] = csub(d0, d1);
 }
+// X[k] = sum_n x[n] e^{-2 pi i n k / 16}, natural order in and out: n = 4 a + b, DFT4 over a, W_16^{a' b}, DFT4 over b, k = a' + 4 b'
+__device__ __forceinline__ void dft16(double2 (&x)[16]) {
+    constexpr double C1 = 0.92387953251128675613, S1 = 0.38268343236508977173, S = 0.70710678118654752440;
+    double2 y[4][4];                                                  // y[a'][b]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double2 t[4] = {x[b], x[4 + b], x[8 + b], x[12 + b]};
+        dft4(t);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) y[a][b] = t[a];
+    }
+    // W_16^{a' b}: exponents 1, 2, 3 (a' = 1), 2, 4, 6 (a' = 2), 3, 6, 9 (a' = 3)
+    y[1][1] = cmul(y[1][1], make_double2(C1, -S1));
+    y[1][2] = make_double2((y[1][2].x + y[1][2].y) * S, (y[1][2].y - y[1][2].x) * S);
+    y[1][3] = cmul(y[1][3], make_double2(S1, -C1));
+    y[2][1] = make_double2((y[2][1].x + y[2][1].y) * S, (y[2][1].y - y[2][1].x) * S);
+    y[2][2] = mul_mi(y[2][2]);
+    y[2][3] = make_double2((y[2][3].y - y[2][3].x) * S, -(y[2][3].x + y[2][3].y) * S);
+    y[3][1] = cmul(y[3][1], make_double2(S1, -C1));
+    y[3][2] = make_double2((y[3][2].y - y[3][2].x) * S, -(y[3][2].x + y[3][2].y) * S);
+    y[3][3] = cmul(y[3][3], make_double2(-C1, S1));
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double2 t[4] = {y[a][0], y[a][1], y[a][2], y[a][3]};
+        dft4(t);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[a + 4 * b] = t[b];
+    }
+}
 template <int R> __device__ __forceinline__ void dft_r(double2 (&x)[R]);
+template <> __device__ __forceinline__ void dft_r<16>(double2 (&x)[16]) { dft16(x); }
 template <> __device__ __forceinline__ void dft_r<8>(double2 (&x)[8]) { dft8(x); }
 template <> __device__ __forceinline__ void dft_r<4>(double2 (&x)[4]) { dft4(x); }
 
@@ -493,6 +523,7 @@ __device__ __forceinline__ void dft_small(double2 (&x)[N1]) {
     if constexpr (N1 == 2) { const double2 a = x[0], b = x[1]; x[0] = cadd(a, b); x[1] = csub(a, b); }
     else if constexpr (N1 == 4) dft4(x);
     else if constexpr (N1 == 8) dft8(x);
+    else if constexpr (N1 == 16) dft16(x);
 }
 // n1-point transforms over elements `stride` apart, one per work item: item i starts at d[start(i)], tw(i, k) multiplies
 // output k of a decimation-in-frequency transform / input k of a decimation-in-time one
@@ -521,7 +552,8 @@ template <bool DIF, class Start, class Tw>
 __device__ __forceinline__ void small_dft_pass_n1(int log2n1, double2* __restrict__ d, int items, int stride, Start start, Tw tw) {
     if (log2n1 == 1) small_dft_pass<2, DIF>(d, items, stride, start, tw);
     else if (log2n1 == 2) small_dft_pass<4, DIF>(d, items, stride, start, tw);
-    else small_dft_pass<8, DIF>(d, items, stride, start, tw);
+    else if (log2n1 == 3) small_dft_pass<8, DIF>(d, items, stride, start, tw);
+    else small_dft_pass<16, DIF>(d, items, stride, start, tw);
 }
 
 template <typename real, int KIND, bool FIRST>
@@ -836,9 +868,208 @@ __global__ void __launch_bounds__(256, 3) correlation_columns_fused_kernel(long 
     if (warp == 0) bulk_wait0();
 }
 
+// ------------------------------------------------------------------------------------------
+// The same two kernels with radix-16 butterflies: lines of LL = RA RB = 256 (16 x 16; 128 = 16 x 8 at N = 128) elements
+// instead of 64, so a row of N = n1 LL elements is an n1-point register pass (n1 = N / LL <= 16, none at n1 = 1) and TWO radix
+// passes -- three visits of shared memory where the kernels above make three (N <= 512) or four (N >= 1024), at twice the
+// registers per thread and two CTAs per SM.  An item is always 4096 elements (4096 / N rows, 4096 / LL lines).
+// ------------------------------------------------------------------------------------------
+template <typename real, int KIND, bool FIRST, int RA, int RB>
+__global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real* __restrict__ field, long long chains, int N, int log2n1, int W,
+                                                                      double scale, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7, RS = LL + 1, E = 4096, lines = E / LL, LOG2LINES = 12 - LOG2LL;
+    static_assert(LL == 256 || LL == 128, "lines of 256 or 128 elements");
+    const int n1 = 1 << log2n1, log2n = log2n1 + LOG2LL;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [lines][LL (+1)]
+    double2* wl = d + (size_t)lines * RS;                               // W_LL^t, t < LL
+    double2* th = wl + LL;                                              // W_N^{64 a}, a < 64
+    double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
+    fft_n1_twiddles(wl, LL);
+    for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)((i * kSplitN2) & (N - 1)) / (double)N, &sn, &cs);
+        th[i] = make_double2(cs, sn);
+        sincospi(-2.0 * (double)i / (double)N, &sn, &cs);
+        tl[i] = make_double2(cs, sn);
+    }
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    constexpr uint32_t kLineBytes = LL * sizeof(double2);
+    auto load_rows = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)E * (uint32_t)sizeof(double2));
+        __syncwarp();
+        for (int l = lane; l < lines; l += 32) bulk_g2s(d + l * RS, src + l * LL, kLineBytes, &ld_bar);
+    };
+    auto store_rows = [&](double2* dst) {
+        for (int l = lane; l < lines; l += 32) bulk_s2g(dst + l * LL, d + l * RS, kLineBytes);
+        bulk_commit();
+    };
+    const long long V = (long long)N * N, items = (chains * V) >> 12;
+    const int items_per_chain = (int)(V >> 12), log2r = 12 - log2n;
+    auto pad = [&](int i) { return i + (i >> LOG2LL); };
+    auto start = [&](int i) { return (i >> LOG2LL) * n1 * RS + (i & (LL - 1)); };        // (row, r2): line row n1, element r2
+    auto tw = [&](int i, int k1) {                                      // W_N^{r2 k1}
+        const int t = (i & (LL - 1)) * k1;
+        return cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
+    };
+    __syncthreads();
+    if (!FIRST && warp == 0 && blockIdx.x < items) load_rows(out + (long long)blockIdx.x * E);
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long chain = item / items_per_chain, next = item + gridDim.x;
+        const int x0 = (int)(item - chain * items_per_chain) << log2r;
+        double2* o = out + item * E;
+        if (FIRST) {
+            const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+            if (KIND != SVB_CORR_WINDING && threadIdx.x == 0 && next < items)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(field + next * E), "r"((uint32_t)E * (uint32_t)sizeof(real)) : "memory");
+            if (warp == 0) bulk_wait_read0();
+            __syncthreads();
+            if (KIND == SVB_CORR_WINDING) {
+                for (int e = threadIdx.x; e < E; e += blockDim.x) {
+                    const int r = x0 + (e >> log2n), x1 = e & (N - 1);
+                    const long long at = (long long)r * N + x1;
+                    const long long i0 = (long long)((r + 1) & (N - 1)) * N + x1, i1 = (long long)r * N + ((x1 + 1) & (N - 1));
+                    d[pad(e)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
+                }
+            } else {
+                constexpr int kBatch = 8;
+                const real* rows = g + (long long)x0 * N;
+                for (int eb = threadIdx.x; eb < E; eb += kBatch * blockDim.x) {
+                    real v[kBatch];
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) v[j] = rows[eb + j * blockDim.x];        // (E is a multiple of 8 x 256)
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        double sn, cs;
+                        const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)v[j]) / (double)W : (double)v[j];
+                        sincos(ang, &sn, &cs);
+                        d[pad(eb + j * blockDim.x)] = make_double2(cs, sn);
+                    }
+                }
+            }
+            __syncthreads();
+            if (log2n1 > 0) small_dft_pass_n1<true>(log2n1, d, E >> log2n1, RS, start, tw);
+            fft_rr<true, RA, RB>(d, 1, RS, LOG2LINES, wl);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) store_rows(o);
+        } else {
+            if (threadIdx.x == 0 && next < items)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(out + next * E), "r"((uint32_t)E * (uint32_t)sizeof(double2)) : "memory");
+            mbar_wait(&ld_bar, ld_parity);
+            ld_parity ^= 1u;
+            fft_rr<false, RA, RB>(d, 1, RS, LOG2LINES, wl, [&](int, int) { return make_double2(scale, 0.0); });
+            if (log2n1 > 0) small_dft_pass_n1<false>(log2n1, d, E >> log2n1, RS, start, tw);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                store_rows(o);
+                if (next < items) {
+                    bulk_wait_read0();
+                    load_rows(out + next * E);
+                }
+            }
+        }
+    }
+    if (warp == 0) bulk_wait0();
+}
+
+// columns of 128 <= N <= 512, whole columns of a 4096 / N-column tile: row r = LL r1 + r2 in slot (r2, r1) of an LL x lines array
+template <int RA, int RB>
+__global__ void __launch_bounds__(256, 2) correlation_columns_r16_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7, E = 4096, lines = E / LL, LOG2LINES = 12 - LOG2LL;
+    const int log2cw = LOG2LINES - log2n1, CW = 1 << log2cw;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [LL r2][lines]
+    double2* wl = d + E;                                                // W_LL^t, t < LL
+    double2* tN = wl + LL;                                              // W_N^t, t < N
+    fft_n1_twiddles(wl, LL);
+    fft_n1_twiddles(tN, N);
+    __shared__ __align__(8) uint64_t ld_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
+    uint32_t ld_parity = 0;
+    const long long V = (long long)N * N;
+    const int col_blocks = N >> log2cw;
+    const long long items = chains * col_blocks;
+    const uint32_t row_bytes = (uint32_t)CW * (uint32_t)sizeof(double2);
+    auto tile_of = [&](long long item) {
+        const long long chain = item / col_blocks;
+        return out + chain * V + ((item - chain * col_blocks) << log2cw);
+    };
+    auto slot = [&](int r) { return ((r & (LL - 1)) << LOG2LINES) + ((r >> LOG2LL) << log2cw); };
+    auto load_tile = [&](const double2* src) {
+        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)(E * sizeof(double2)));
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) bulk_g2s(d + slot(r), src + (long long)r * N, row_bytes, &ld_bar);
+    };
+    auto start = [&](int i) { return ((i >> log2cw) << LOG2LINES) + (i & (CW - 1)); };         // (r2, c)
+    __syncthreads();
+    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x));
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long next = item + gridDim.x;
+        double2* o = tile_of(item);
+        mbar_wait(&ld_bar, ld_parity);
+        ld_parity ^= 1u;
+        if (log2n1 > 0) {
+            small_dft_pass_n1<true>(log2n1, d, LL << log2cw, CW, start, [&](int i, int k) { return tN[(i >> log2cw) * k]; });
+            fft_rr<true, RA, RB>(d, lines, 1, LOG2LINES, wl, Norm2());
+            fft_rr<false, RA, RB>(d, lines, 1, LOG2LINES, wl, NoScale(), [&](int L, int q) { return tN[(L >> log2cw) * q]; });
+            small_dft_pass_n1<false>(log2n1, d, LL << log2cw, CW, start, NoScale());
+        } else {
+            fft_rr<true, RA, RB>(d, lines, 1, LOG2LINES, wl, Norm2());
+            fft_rr<false, RA, RB>(d, lines, 1, LOG2LINES, wl);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) {
+            for (int r = lane; r < N; r += 32) bulk_s2g(o + (long long)r * N, d + slot(r), row_bytes);
+            bulk_commit();
+            if (next < items) {
+                const double2* src = tile_of(next);
+                bulk_wait_read0();
+                load_tile(src);
+            }
+        }
+    }
+    if (warp == 0) bulk_wait0();
+}
+
 }  // namespace svb
 
 using namespace svb;
+
+template <typename real, int KIND, bool FIRST, int RA, int RB>
+static int launch_rows_r16(const void* field, long long chains, int N, int log2n, int W, double scale, double2* o, int sms, cudaStream_t st) {
+    constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7;
+    auto kern = correlation_rows_r16_kernel<real, KIND, FIRST, RA, RB>;
+    const size_t smem = ((size_t)(4096 / LL) * (LL + 1) + LL + 2 * kSplitN2) * sizeof(double2);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the radix-16 row kernel", N);
+    const long long items = (chains * N * N) >> 12, cap = (long long)per_sm * sms;
+    kern<<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(reinterpret_cast<const real*>(field), chains, N, log2n - LOG2LL, W, scale, o);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
+template <int RA, int RB>
+static int launch_columns_r16(long long chains, int N, int log2n, double2* o, int sms, cudaStream_t st) {
+    constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7;
+    auto kern = correlation_columns_r16_kernel<RA, RB>;
+    const size_t smem = ((size_t)4096 + LL + N) * sizeof(double2);
+    SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the radix-16 column kernel", N);
+    const long long items = (chains * N * N) >> 12, cap = (long long)per_sm * sms;
+    kern<<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(chains, N, log2n - LOG2LL, o);
+    SVB_CUDA_TRY(cudaGetLastError());
+    return SVB_OK;
+}
 
 template <typename real, int KIND>
 static int launch_correlation_fft_large(const void* field, long long chains, int N, int W, double* out, int sms, cudaStream_t st) {
@@ -877,11 +1108,24 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
     const int log2r = mid ? 12 - log2n : 0, lines_rows = n1_rows << log2r;
     const size_t smem_rsplit = ((size_t)lines_rows * (kSplitN2 + 1) + n1_rows + 3 * kSplitN2) * sizeof(double2);
+    // radix-16 kernels (lines of 256 or 128 elements: a visit of shared memory fewer): the rows of every split route -- per
+    // launch at 8.4 M sites 48-62 against 61-72 us (N = 128, 256), 57-72 against 62-75 us (N = 512), 125 + 158 against
+    // 137 + 164 us at N = 4096 -- and the columns of N = 128 (96 against 102 us; 144 against 130 us at N = 256, 263 against
+    // 202 us at N = 512, where a tile row is 128 bytes and the n1-point pass costs more than it saves).  SVB_CORR_R16=0: the
+    // radix-8 kernels throughout, =2: radix-16 columns for every N <= 512
+    int r16 = 1;
+    if (const char* e = getenv("SVB_CORR_R16")) r16 = atoi(e);
+    const bool rows16 = split && r16 > 0, cols16 = mid && rows16 && (N == 128 || r16 > 1);
+    if (rows16) {
+        const int rc = N == 128 ? launch_rows_r16<real, KIND, true, 16, 8>(field, chains, N, log2n, W, 1.0, o, sms, st)
+                                : launch_rows_r16<real, KIND, true, 16, 16>(field, chains, N, log2n, W, 1.0, o, sms, st);
+        if (rc != SVB_OK) return rc;
+    }
     auto kr1 = correlation_rows_split_kernel<real, KIND, true>;
     auto kr2 = correlation_rows_split_kernel<real, KIND, false>;
     long long cap_rsplit = 0;
     const int rows_threads = 256;                                 // (512, an item of a radix-8 pass per thread at N = 4096: 1039 against 860 us)
-    if (split) {
+    if (split && !rows16) {
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
         SVB_CUDA_TRY(cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rsplit));
         int per_sm = 0;
@@ -891,12 +1135,15 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         const long long items = (chains * N) >> log2r;
         kr1<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                            log2n1_rows, log2r, W, 1.0, o);
-    } else {
+    } else if (!split) {
         k1<<<(unsigned)(row_items < cap_rows ? row_items : cap_rows), 256, smem_rows, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                              log2n, W, R, o);
     }
     SVB_CUDA_TRY(cudaGetLastError());
-    if (mid) {
+    if (cols16) {
+        const int rc = N == 128 ? launch_columns_r16<16, 8>(chains, N, log2n, o, sms, st) : launch_columns_r16<16, 16>(chains, N, log2n, o, sms, st);
+        if (rc != SVB_OK) return rc;
+    } else if (mid) {
         const size_t smem_fused = ((size_t)kSplitN2 * kSplitN2 + kSplitN2 + N) * sizeof(double2);
         SVB_CUDA_TRY(cudaFuncSetAttribute(correlation_columns_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fused));
         int per_sm = 0;
@@ -928,7 +1175,10 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         correlation_columns_kernel<<<(unsigned)(col_items < cap_cols ? col_items : cap_cols), 256, smem_cols, st>>>(chains, N, log2n, C, log2c, o);
         SVB_CUDA_TRY(cudaGetLastError());
     }
-    if (split) {
+    if (rows16) {
+        return N == 128 ? launch_rows_r16<real, KIND, false, 16, 8>(field, chains, N, log2n, W, 1.0 / (V * V), o, sms, st)
+                        : launch_rows_r16<real, KIND, false, 16, 16>(field, chains, N, log2n, W, 1.0 / (V * V), o, sms, st);
+    } else if (split) {
         const long long items = (chains * N) >> log2r;
         kr2<<<(unsigned)(items < cap_rsplit ? items : cap_rsplit), rows_threads, smem_rsplit, st>>>(reinterpret_cast<const real*>(field), chains, N,
                                                                                            log2n1_rows, log2r, W, 1.0 / (V * V), o);

@@ -209,6 +209,10 @@ def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
     n = rng.integers(-3, 4, (chains, 2, N, N))
     Cs = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
     Cw = ops.correlation('winding', torch.from_numpy(n).to(torch.int32).cuda()).cpu().numpy()
+    monkeypatch.setenv('SVB_CORR_R16', '0')               # the radix-8 row kernels (the default rows are radix-16)
+    Cs8 = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    np.testing.assert_allclose(Cs8, Cs, rtol=0, atol=1e-13)
+    monkeypatch.delenv('SVB_CORR_R16')
     monkeypatch.setenv('SVB_CORR_SPLIT_MIN_N', '1000000')
     whole = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
     for c in range(chains):
@@ -238,6 +242,13 @@ def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypa
     monkeypatch.setenv('SVB_CORR_ROUTE', 'legacy')
     legacy = ops.villain_spin_spin(tphi).cpu().numpy()
     np.testing.assert_allclose(Cs, legacy, rtol=0, atol=1e-13)
+    monkeypatch.delenv('SVB_CORR_ROUTE')
+    # the radix-8 kernels throughout (0) and the radix-16 column kernel at every size (2): the same result
+    for r16 in ('0', '2'):
+        monkeypatch.setenv('SVB_CORR_R16', r16)
+        np.testing.assert_allclose(ops.villain_spin_spin(tphi).cpu().numpy(), Cs, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(ops.correlation('winding', tn).cpu().numpy(), Cw, rtol=0, atol=1e-12)
+    monkeypatch.delenv('SVB_CORR_R16')
     for c in range(chains):
         s = np.exp(1j * phi[c, 0])
         np.testing.assert_allclose(Cs[c], lat.correlation(s, s), rtol=0, atol=1e-12)
@@ -249,14 +260,20 @@ def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypa
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
 
 
-def test_fft_correlator_of_a_config5_lattice_properties():
+def test_fft_correlator_of_a_config5_lattice_properties(monkeypatch):
     """L = 4096 (config 5), too large to compare element by element in a test: size-independent properties of
     Lattice.correlation instead -- C[0] = mean |s|^2 = 1 for a spin field, C[-r] = conj(C[r]), sum_r C[r] = N^2 |mean s|^2 ...
-    and a plane wave s = exp(i k.x), whose correlator is exp(-i k.r) exactly."""
+    and a plane wave s = exp(i k.x), whose correlator is exp(-i k.r) exactly.  The radix-8 row kernels (SVB_CORR_R16=0)
+    and the default radix-16 ones agree to 1e-13."""
     N = 4096
     rng = np.random.default_rng(5)
     phi = rng.uniform(-np.pi, np.pi, (1, 1, N, N))
+    monkeypatch.setenv('SVB_CORR_R16', '0')
+    C8 = ops.villain_spin_spin(torch.from_numpy(phi).cuda())[0]
+    monkeypatch.delenv('SVB_CORR_R16')
     C = ops.villain_spin_spin(torch.from_numpy(phi).cuda())[0]
+    assert float((C - C8).abs().max()) < 1e-13
+    del C8
     s = torch.from_numpy(np.exp(1j * phi[0, 0])).cuda()
     assert abs(complex(C[0, 0]) - 1.0) < 1e-12
     flipped = torch.roll(torch.flip(C, (0, 1)), (1, 1), (0, 1))
