@@ -260,6 +260,21 @@ def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypa
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('N', [32, 128, 256])
+def test_spin_correlator_for_large_angles(N):
+    """phi is never wrapped by the reference's updates, so a long run can reach angles of any magnitude: the spin field
+    exp(i phi) of the FFT kernels (the small-lattice kernel, radix-16 lines of 128 and of 256) against numpy's exponential for
+    |phi| up to 1e12, 1e-12 on the correlator.  (A table-driven sincos, 30 instructions for the library's 85, passed this
+    test too and bought 1 % at L = 4096 and nothing on the small lattices: not kept.)"""
+    rng = np.random.default_rng(N)
+    scales = (1.0, 1.0e2, 9.9e4, 3.0e6, 1.0e12)
+    phi = np.stack([rng.uniform(-sc, sc, (1, N, N)) for sc in scales])
+    C = ops.villain_spin_spin(torch.from_numpy(phi).cuda()).cpu().numpy()
+    for c in range(len(scales)):
+        s = np.exp(1j * phi[c, 0])
+        np.testing.assert_allclose(C[c], lat.correlation(s, s), rtol=0, atol=1e-12, err_msg=f'scale {scales[c]}')
+
+
 def test_fft_correlator_of_a_config5_lattice_properties(monkeypatch):
     """L = 4096 (config 5), too large to compare element by element in a test: size-independent properties of
     Lattice.correlation instead -- C[0] = mean |s|^2 = 1 for a spin field, C[-r] = conj(C[r]), sum_r C[r] = N^2 |mean s|^2 ...
