@@ -8,6 +8,7 @@
 // non-power-of-two lattices (exact to rounding), a shared-memory FFT for N = 16, 32, 64, and a three-launch FFT for
 // power-of-two lattices up to N = 4096.
 
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
 #include <cstring>
 #include <type_traits>
 #include "svb_common.cuh"
@@ -477,6 +478,21 @@ __global__ void __launch_bounds__(256) correlation_rows_inverse_kernel(long long
 // ------------------------------------------------------------------------------------------
 constexpr int kSplitCols = 32, kSplitLog2Cols = 5, kSplitN2 = 64, kSplitLog2N2 = 6;
 
+// Column tiles are rows of 128 .. 512 bytes a row of the lattice (or 64 of them) apart: as 1-D bulk copies a tile is 64 .. 512
+// operations each way, and the copy engine of an SM retires one in about 10 ns -- 70 us of a 115 us kernel at N = 4096.  A
+// 3-D tensor map (the array as doubles: (2 column, ...)) moves a tile with ONE operation each way.
+__device__ __forceinline__ void box_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void box_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
 // FFT of length n along the ROWS of a tile d[row][kSplitCols] (a thread per column and butterfly: conflict-free); tw = the
 // n / 2 twiddles of the length-n transform
 template <bool DIF, int LOG2W = kSplitLog2Cols>
@@ -681,41 +697,35 @@ __global__ void __launch_bounds__(256, 3) correlation_rows_split_kernel(const re
 
 // visits A (FIRST: DIF over r1, then W_N^{r2 bitrev(p)}) and A' (!FIRST: DIT over k1): a tile = (chain, r2, 32 columns)
 template <bool FIRST>
-__global__ void __launch_bounds__(256, 4) correlation_split_outer_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(256, 4) correlation_split_outer_kernel(const __grid_constant__ CUtensorMap map, long long chains, int N, int log2n1) {
+    extern __shared__ __align__(128) unsigned char box_smem[];
     const int n1 = 1 << log2n1;
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [n1][32]
+    double2* d = reinterpret_cast<double2*>(box_smem);                 // [n1][32]: one box (2 x 32 doubles, 1, n1) of the map
     double2* tw = d + (size_t)n1 * kSplitCols;                          // W_n1^t, t < n1 (radix passes, n1 >= 16) or t < n1 / 2 (radix-2 stages)
     double2* tq = tw + n1;                                              // n1 twiddles W_N^{r2 k1(p)}
     if (log2n1 >= 4) fft_n1_twiddles(tw, n1); else fft_twiddles(tw, n1);
     const long long V = (long long)N * N;
     const int col_blocks = N / kSplitCols;
     const long long items = chains * kSplitN2 * col_blocks;
-    // tiles travel as bulk copies (TMA), a row of 32 columns (512 bytes) each, issued by warp 0; the next tile is requested
+    // a tile travels as one box of the tensor map (columns, r2, chain n1 + r1), issued by one thread; the next tile is requested
     // the moment this one has left shared memory
     __shared__ __align__(8) uint64_t ld_bar;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
-    constexpr uint32_t kRowBytes = kSplitCols * sizeof(double2);
-    const long long row_step = (long long)kSplitN2 * N;
-    auto tile_of = [&](long long item, int& r2) {
+    auto load_tile = [&](long long item) {                              // thread 0
         const long long chain = item / (kSplitN2 * col_blocks);
         const int rem = (int)(item - chain * (kSplitN2 * col_blocks));
-        r2 = rem / col_blocks;
-        return out + chain * V + (long long)r2 * N + (rem - r2 * col_blocks) * kSplitCols;
-    };
-    auto load_tile = [&](const double2* src) {
-        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)n1 * kRowBytes);
-        __syncwarp();
-        for (int r1 = lane; r1 < n1; r1 += 32) bulk_g2s(d + r1 * kSplitCols, src + r1 * row_step, kRowBytes, &ld_bar);
+        const int r2 = rem / col_blocks, c0 = (rem - r2 * col_blocks) * kSplitCols;
+        mbar_expect_tx(&ld_bar, (uint32_t)(n1 * kSplitCols * sizeof(double2)));
+        box_load_3d(d, &map, 2 * c0, r2, (int)(chain * n1), &ld_bar);
     };
     __syncthreads();
-    int r2 = 0;
-    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x, r2));
+    if (threadIdx.x == 0 && blockIdx.x < items) load_tile(blockIdx.x);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long next = item + gridDim.x;
-        double2* o = tile_of(item, r2);
+        const long long chain = item / (kSplitN2 * col_blocks);
+        const int rem = (int)(item - chain * (kSplitN2 * col_blocks));
+        const int r2 = rem / col_blocks, c0 = (rem - r2 * col_blocks) * kSplitCols;
         if (FIRST)
             for (int p = threadIdx.x; p < n1; p += blockDim.x) {        // (the previous tile's last pass ended in a barrier)
                 const int k1 = split_freq(p, log2n1);
@@ -738,24 +748,22 @@ __global__ void __launch_bounds__(256, 4) correlation_split_outer_kernel(long lo
         }
         fence_proxy_async();
         __syncthreads();
-        if (warp == 0) {
-            for (int r1 = lane; r1 < n1; r1 += 32) bulk_s2g(o + r1 * row_step, d + r1 * kSplitCols, kRowBytes);
+        if (threadIdx.x == 0) {
+            box_store_3d(&map, 2 * c0, r2, (int)(chain * n1), d);
             bulk_commit();
             if (next < items) {
-                int r2n;
-                const double2* src = tile_of(next, r2n);
                 bulk_wait_read0();
-                load_tile(src);
+                load_tile(next);
             }
         }
     }
-    if (warp == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait0();
 }
 
 // visit B: a tile = (chain, p, 32 columns) = 64 consecutive rows: DIF over r2, |.|^2, DIT over k2, W_N^{bitrev(p) r2'}
-__global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64][32]
+__global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(const __grid_constant__ CUtensorMap map, long long chains, int N, int log2n1) {
+    extern __shared__ __align__(128) unsigned char box_smem[];
+    double2* d = reinterpret_cast<double2*>(box_smem);                 // [64][32]: one box (2 x 32 doubles, 64, 1) of the map
     double2* w64 = d + (size_t)kSplitN2 * kSplitCols;                   // W_64^t, t < 64
     double2* tq = w64 + kSplitN2;                                       // 64 twiddles W_N^{k1 r2'}
     fft64_twiddles(w64);
@@ -763,27 +771,22 @@ __global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long lo
     const int n1 = 1 << log2n1, col_blocks = N / kSplitCols;
     const long long items = chains * n1 * col_blocks;
     __shared__ __align__(8) uint64_t ld_bar;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
-    constexpr uint32_t kRowBytes = kSplitCols * sizeof(double2);
-    auto tile_of = [&](long long item, int& p) {
+    auto load_tile = [&](long long item) {                              // thread 0
         const long long chain = item / (n1 * col_blocks);
         const int rem = (int)(item - chain * (n1 * col_blocks));
-        p = rem / col_blocks;
-        return out + chain * V + (long long)p * kSplitN2 * N + (rem - p * col_blocks) * kSplitCols;
-    };
-    auto load_tile = [&](const double2* src) {
-        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)kSplitN2 * kRowBytes);
-        __syncwarp();
-        for (int r = lane; r < kSplitN2; r += 32) bulk_g2s(d + r * kSplitCols, src + (long long)r * N, kRowBytes, &ld_bar);
+        const int p = rem / col_blocks, c0 = (rem - p * col_blocks) * kSplitCols;
+        mbar_expect_tx(&ld_bar, (uint32_t)(kSplitN2 * kSplitCols * sizeof(double2)));
+        box_load_3d(d, &map, 2 * c0, 0, (int)(chain * n1) + p, &ld_bar);
     };
     __syncthreads();
-    int p = 0;
-    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x, p));
+    if (threadIdx.x == 0 && blockIdx.x < items) load_tile(blockIdx.x);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long next = item + gridDim.x;
-        double2* o = tile_of(item, p);
+        const long long chain = item / (n1 * col_blocks);
+        const int rem = (int)(item - chain * (n1 * col_blocks));
+        const int p = rem / col_blocks, c0 = (rem - p * col_blocks) * kSplitCols;
         const int k1 = split_freq(p, log2n1);
         for (int r = threadIdx.x; r < kSplitN2; r += blockDim.x) {       // (the previous tile's last pass ended in a barrier)
             double sn, cs;
@@ -796,18 +799,16 @@ __global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long lo
         fft64<false>(d, kSplitCols, 1, kSplitLog2Cols, w64, NoScale(), [&](int, int r) { return tq[r]; });
         fence_proxy_async();
         __syncthreads();
-        if (warp == 0) {
-            for (int r = lane; r < kSplitN2; r += 32) bulk_s2g(o + (long long)r * N, d + r * kSplitCols, kRowBytes);
+        if (threadIdx.x == 0) {
+            box_store_3d(&map, 2 * c0, 0, (int)(chain * n1) + p, d);
             bulk_commit();
             if (next < items) {
-                int pn;
-                const double2* src = tile_of(next, pn);
                 bulk_wait_read0();
-                load_tile(src);
+                load_tile(next);
             }
         }
     }
-    if (warp == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait0();
 }
 
 // The columns of 128 <= N <= 512 in ONE visit: a tile = (chain, CW = 4096 / N columns) holds whole columns, 4096 elements.
@@ -815,38 +816,29 @@ __global__ void __launch_bounds__(256, 4) correlation_split_inner_kernel(long lo
 // of the split are: A, n1-point transforms in registers over r1 (elements CW apart) and W_N^{r2 k1}; B, 64-point transforms
 // over r2 for all 64 lines at once (two radix-8 passes, |.|^2 on the way out), the same back (W_N^{k1 r2'} on the way out);
 // A', n1-point transforms over k1.  Rows travel as bulk copies (TMA) of CW elements, straight into and out of their slots.
-__global__ void __launch_bounds__(256, 3) correlation_columns_fused_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int log2cw = kSplitLog2N2 - log2n1, CW = 1 << log2cw;
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [64 r2][64 lines]
+__global__ void __launch_bounds__(256, 3) correlation_columns_fused_kernel(const __grid_constant__ CUtensorMap map, long long chains, int N, int log2n1) {
+    extern __shared__ __align__(128) unsigned char box_smem[];
+    const int log2cw = kSplitLog2N2 - log2n1, CW = 1 << log2cw, n1 = 1 << log2n1;
+    double2* d = reinterpret_cast<double2*>(box_smem);                 // [64 r2][64 lines]: one box (2 CW doubles, n1, 64) of the map
     double2* w64 = d + kSplitN2 * kSplitN2;                             // W_64^t, t < 64
     double2* tN = w64 + kSplitN2;                                       // W_N^t, t < N
     fft64_twiddles(w64);
     fft_n1_twiddles(tN, N);
     __shared__ __align__(8) uint64_t ld_bar;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
-    const long long V = (long long)N * N;
     const int col_blocks = N >> log2cw;
     const long long items = chains * col_blocks;
-    const uint32_t row_bytes = (uint32_t)CW * (uint32_t)sizeof(double2);
-    auto tile_of = [&](long long item) {
+    auto load_tile = [&](long long item) {                              // thread 0: the map's dimensions are (column, chain n1 + r1, r2)
         const long long chain = item / col_blocks;
-        return out + chain * V + ((item - chain * col_blocks) << log2cw);
-    };
-    auto slot = [&](int r) { return (((r & (kSplitN2 - 1)) << log2n1) + (r >> kSplitLog2N2)) << log2cw; };
-    auto load_tile = [&](const double2* src) {
-        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)(kSplitN2 * kSplitN2 * sizeof(double2)));
-        __syncwarp();
-        for (int r = lane; r < N; r += 32) bulk_g2s(d + slot(r), src + (long long)r * N, row_bytes, &ld_bar);
+        mbar_expect_tx(&ld_bar, (uint32_t)(kSplitN2 * kSplitN2 * sizeof(double2)));
+        box_load_3d(d, &map, (int)(item - chain * col_blocks) << (log2cw + 1), (int)(chain * n1), 0, &ld_bar);
     };
     auto start = [&](int i) { return ((i >> log2cw) << kSplitLog2N2) + (i & (CW - 1)); };      // (r2, c): line c of slot row r2
     __syncthreads();
-    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x));
+    if (threadIdx.x == 0 && blockIdx.x < items) load_tile(blockIdx.x);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long next = item + gridDim.x;
-        double2* o = tile_of(item);
         mbar_wait(&ld_bar, ld_parity);
         ld_parity ^= 1u;
         small_dft_pass_n1<true>(log2n1, d, kSplitN2 << log2cw, CW, start, [&](int i, int k) { return tN[(i >> log2cw) * k]; });
@@ -855,17 +847,17 @@ __global__ void __launch_bounds__(256, 3) correlation_columns_fused_kernel(long 
         small_dft_pass_n1<false>(log2n1, d, kSplitN2 << log2cw, CW, start, NoScale());
         fence_proxy_async();
         __syncthreads();
-        if (warp == 0) {
-            for (int r = lane; r < N; r += 32) bulk_s2g(o + (long long)r * N, d + slot(r), row_bytes);
+        if (threadIdx.x == 0) {
+            const long long chain = item / col_blocks;
+            box_store_3d(&map, (int)(item - chain * col_blocks) << (log2cw + 1), (int)(chain * n1), 0, d);
             bulk_commit();
             if (next < items) {
-                const double2* src = tile_of(next);
                 bulk_wait_read0();
-                load_tile(src);
+                load_tile(next);
             }
         }
     }
-    if (warp == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait0();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -979,39 +971,30 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
 
 // columns of 128 <= N <= 512, whole columns of a 4096 / N-column tile: row r = LL r1 + r2 in slot (r2, r1) of an LL x lines array
 template <int RA, int RB>
-__global__ void __launch_bounds__(256, 2) correlation_columns_r16_kernel(long long chains, int N, int log2n1, double2* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(256, 2) correlation_columns_r16_kernel(const __grid_constant__ CUtensorMap map, long long chains, int N, int log2n1) {
+    extern __shared__ __align__(128) unsigned char box_smem[];
     constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7, E = 4096, lines = E / LL, LOG2LINES = 12 - LOG2LL;
-    const int log2cw = LOG2LINES - log2n1, CW = 1 << log2cw;
-    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [LL r2][lines]
+    const int log2cw = LOG2LINES - log2n1, CW = 1 << log2cw, n1 = 1 << log2n1;
+    double2* d = reinterpret_cast<double2*>(box_smem);                 // [LL r2][lines]: one box (2 CW doubles, n1, LL) of the map
     double2* wl = d + E;                                                // W_LL^t, t < LL
     double2* tN = wl + LL;                                              // W_N^t, t < N
     fft_n1_twiddles(wl, LL);
     fft_n1_twiddles(tN, N);
     __shared__ __align__(8) uint64_t ld_bar;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
-    const long long V = (long long)N * N;
     const int col_blocks = N >> log2cw;
     const long long items = chains * col_blocks;
-    const uint32_t row_bytes = (uint32_t)CW * (uint32_t)sizeof(double2);
-    auto tile_of = [&](long long item) {
+    auto load_tile = [&](long long item) {                              // thread 0: the map's dimensions are (column, chain n1 + r1, r2)
         const long long chain = item / col_blocks;
-        return out + chain * V + ((item - chain * col_blocks) << log2cw);
-    };
-    auto slot = [&](int r) { return ((r & (LL - 1)) << LOG2LINES) + ((r >> LOG2LL) << log2cw); };
-    auto load_tile = [&](const double2* src) {
-        if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)(E * sizeof(double2)));
-        __syncwarp();
-        for (int r = lane; r < N; r += 32) bulk_g2s(d + slot(r), src + (long long)r * N, row_bytes, &ld_bar);
+        mbar_expect_tx(&ld_bar, (uint32_t)(E * sizeof(double2)));
+        box_load_3d(d, &map, (int)(item - chain * col_blocks) << (log2cw + 1), (int)(chain * n1), 0, &ld_bar);
     };
     auto start = [&](int i) { return ((i >> log2cw) << LOG2LINES) + (i & (CW - 1)); };         // (r2, c)
     __syncthreads();
-    if (warp == 0 && blockIdx.x < items) load_tile(tile_of(blockIdx.x));
+    if (threadIdx.x == 0 && blockIdx.x < items) load_tile(blockIdx.x);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long next = item + gridDim.x;
-        double2* o = tile_of(item);
         mbar_wait(&ld_bar, ld_parity);
         ld_parity ^= 1u;
         if (log2n1 > 0) {
@@ -1025,22 +1008,46 @@ __global__ void __launch_bounds__(256, 2) correlation_columns_r16_kernel(long lo
         }
         fence_proxy_async();
         __syncthreads();
-        if (warp == 0) {
-            for (int r = lane; r < N; r += 32) bulk_s2g(o + (long long)r * N, d + slot(r), row_bytes);
+        if (threadIdx.x == 0) {
+            const long long chain = item / col_blocks;
+            box_store_3d(&map, (int)(item - chain * col_blocks) << (log2cw + 1), (int)(chain * n1), 0, d);
             bulk_commit();
             if (next < items) {
-                const double2* src = tile_of(next);
                 bulk_wait_read0();
-                load_tile(src);
+                load_tile(next);
             }
         }
     }
-    if (warp == 0) bulk_wait0();
+    if (threadIdx.x == 0) bulk_wait0();
 }
 
 }  // namespace svb
 
 using namespace svb;
+
+// tensor map over the complex array `base` taken as doubles: dims[0] = 2 N (contiguous), two more dimensions with byte strides
+typedef CUresult (*corr_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int corr_tensor_map(CUtensorMap& map, void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t s1, cuuint64_t s2,
+                           cuuint32_t b0, cuuint32_t b1, cuuint32_t b2) {
+    static corr_map_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        SVB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &status));
+        if (status != cudaDriverEntryPointSuccess || !fn) return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<corr_map_encode_fn>(fn);
+    }
+    const cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {s1, s2};
+    const cuuint32_t box[3] = {b0, b1, b2}, ones[3] = {1, 1, 1};
+    const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(SVB_E_UNSUPPORTED, "cuTensorMapEncodeTiled(correlator tiles: dims %llu %llu %llu, box %u %u %u) failed: %d", (unsigned long long)d0,
+                    (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2, (int)r);
+    return SVB_OK;
+}
 
 template <typename real, int KIND, bool FIRST, int RA, int RB>
 static int launch_rows_r16(const void* field, long long chains, int N, int log2n, int W, double scale, double2* o, int sms, cudaStream_t st) {
@@ -1066,7 +1073,13 @@ static int launch_columns_r16(long long chains, int N, int log2n, double2* o, in
     SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
     if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the radix-16 column kernel", N);
     const long long items = (chains * N * N) >> 12, cap = (long long)per_sm * sms;
-    kern<<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(chains, N, log2n - LOG2LL, o);
+    // (column, chain n1 + r1, r2): a box of all r2 and r1 lands as [r2][r1][column], the layout the passes work in
+    const int n1 = N / LL;
+    CUtensorMap map;
+    const int rc = corr_tensor_map(map, o, 2 * (cuuint64_t)N, (cuuint64_t)n1 * chains, LL, (cuuint64_t)LL * N * sizeof(double2), (cuuint64_t)N * sizeof(double2),
+                                   2 * (4096 / N), n1, LL);
+    if (rc != SVB_OK) return rc;
+    kern<<<(unsigned)(items < cap ? items : cap), 256, smem, st>>>(map, chains, N, log2n - LOG2LL);
     SVB_CUDA_TRY(cudaGetLastError());
     return SVB_OK;
 }
@@ -1150,7 +1163,12 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, correlation_columns_fused_kernel, 256, smem_fused));
         if (per_sm < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the fused column kernel", N);
         const long long items = chains * (N >> (kSplitLog2N2 - (log2n - kSplitLog2N2))), cap = (long long)per_sm * sms;
-        correlation_columns_fused_kernel<<<(unsigned)(items < cap ? items : cap), 256, smem_fused, st>>>(chains, N, log2n - kSplitLog2N2, o);
+        const int n1 = N / kSplitN2;
+        CUtensorMap map;                                           // (column, chain n1 + r1, r2) -> [r2][r1][column]
+        const int rc = corr_tensor_map(map, o, 2 * (cuuint64_t)N, (cuuint64_t)n1 * chains, kSplitN2, (cuuint64_t)kSplitN2 * N * sizeof(double2),
+                                       (cuuint64_t)N * sizeof(double2), 2 * (4096 / N), n1, kSplitN2);
+        if (rc != SVB_OK) return rc;
+        correlation_columns_fused_kernel<<<(unsigned)(items < cap ? items : cap), 256, smem_fused, st>>>(map, chains, N, log2n - kSplitLog2N2);
         SVB_CUDA_TRY(cudaGetLastError());
     } else if (split) {
         const int log2n1 = log2n - kSplitLog2N2, n1 = 1 << log2n1;
@@ -1165,11 +1183,19 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
         if (per_sm_outer < 1 || per_sm_inner < 1) return fail(SVB_E_UNSUPPORTED, "svb_correlation: N=%d does not fit the split column kernels", N);
         const long long outer_items = chains * kSplitN2 * (N / kSplitCols), inner_items = chains * n1 * (N / kSplitCols);
         const long long cap_outer = (long long)per_sm_outer * sms, cap_inner = (long long)per_sm_inner * sms;
-        correlation_split_outer_kernel<true><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(chains, N, log2n1, o);
+        // (column, r2, chain n1 + r1): an outer tile is the box (32 columns, one r2, all r1), an inner tile (32 columns, all r2, one r1)
+        CUtensorMap map_outer, map_inner;
+        int rc = corr_tensor_map(map_outer, o, 2 * (cuuint64_t)N, kSplitN2, (cuuint64_t)n1 * chains, (cuuint64_t)N * sizeof(double2),
+                                 (cuuint64_t)kSplitN2 * N * sizeof(double2), 2 * kSplitCols, 1, n1);
+        if (rc != SVB_OK) return rc;
+        rc = corr_tensor_map(map_inner, o, 2 * (cuuint64_t)N, kSplitN2, (cuuint64_t)n1 * chains, (cuuint64_t)N * sizeof(double2),
+                             (cuuint64_t)kSplitN2 * N * sizeof(double2), 2 * kSplitCols, kSplitN2, 1);
+        if (rc != SVB_OK) return rc;
+        correlation_split_outer_kernel<true><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(map_outer, chains, N, log2n1);
         SVB_CUDA_TRY(cudaGetLastError());
-        correlation_split_inner_kernel<<<(unsigned)(inner_items < cap_inner ? inner_items : cap_inner), 256, smem_inner, st>>>(chains, N, log2n1, o);
+        correlation_split_inner_kernel<<<(unsigned)(inner_items < cap_inner ? inner_items : cap_inner), 256, smem_inner, st>>>(map_inner, chains, N, log2n1);
         SVB_CUDA_TRY(cudaGetLastError());
-        correlation_split_outer_kernel<false><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(chains, N, log2n1, o);
+        correlation_split_outer_kernel<false><<<(unsigned)(outer_items < cap_outer ? outer_items : cap_outer), 256, smem_outer, st>>>(map_outer, chains, N, log2n1);
         SVB_CUDA_TRY(cudaGetLastError());
     } else {
         correlation_columns_kernel<<<(unsigned)(col_items < cap_cols ? col_items : cap_cols), 256, smem_cols, st>>>(chains, N, log2n, C, log2c, o);
