@@ -1115,7 +1115,12 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     // 4096 / N-column tile in shared memory): three launches, every element read and written once by each
     // (SVB_CORR_ROUTE=legacy: the radix-2 kernels they replace; SVB_CORR_SPLIT_MIN_N set: the five-launch split or legacy)
     const char* route = getenv("SVB_CORR_ROUTE");
-    const bool mid = N <= 512 && !getenv("SVB_CORR_SPLIT_MIN_N") && !(route && !strcmp(route, "legacy"));
+    int mid_max = 2048;                                            // (8.4 M sites: 240 against 350 us at N = 1024, 276 against 322 us at N = 2048)
+    if (const char* e = getenv("SVB_CORR_MID_MAX_N")) mid_max = atoi(e);
+    int r16 = 1;
+    if (const char* e = getenv("SVB_CORR_R16")) r16 = atoi(e);
+    if (r16 <= 0 && mid_max > 512) mid_max = 512;                  // (the 64-line kernels take several rows per item only for n1 <= 8)
+    const bool mid = N <= mid_max && !getenv("SVB_CORR_SPLIT_MIN_N") && !(route && !strcmp(route, "legacy"));
     const bool split = mid || (N >= split_min && N >= 2 * kSplitN2);
     const double V = (double)N * (double)N;
     const int log2n1_rows = log2n - kSplitLog2N2, n1_rows = split ? (1 << log2n1_rows) : 1;
@@ -1123,12 +1128,10 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     const size_t smem_rsplit = ((size_t)lines_rows * (kSplitN2 + 1) + n1_rows + 3 * kSplitN2) * sizeof(double2);
     // radix-16 kernels (lines of 256 or 128 elements: a visit of shared memory fewer): the rows of every split route -- per
     // launch at 8.4 M sites 48-62 against 61-72 us (N = 128, 256), 57-72 against 62-75 us (N = 512), 125 + 158 against
-    // 137 + 164 us at N = 4096 -- and the columns of N = 128 (96 against 102 us; 144 against 130 us at N = 256, 263 against
-    // 202 us at N = 512, where a tile row is 128 bytes and the n1-point pass costs more than it saves).  SVB_CORR_R16=0: the
-    // radix-8 kernels throughout, =2: radix-16 columns for every N <= 512
-    int r16 = 1;
-    if (const char* e = getenv("SVB_CORR_R16")) r16 = atoi(e);
-    const bool rows16 = split && r16 > 0, cols16 = mid && rows16 && (N == 128 || r16 > 1);
+    // 137 + 164 us at N = 4096 -- and the columns of the fused route except N = 512 (with tensor-map tiles, per correlator:
+    // 194 against 204 us at N = 256, 229 against 222 us at N = 512; N = 2048 has n1 = 32, beyond the 64-line kernel's register
+    // pass).  SVB_CORR_R16=0: the radix-8 kernels throughout (fused columns up to N = 512), =2: radix-16 columns at N = 512 too
+    const bool rows16 = split && r16 > 0, cols16 = mid && rows16 && (N != 512 || r16 > 1);
     if (rows16) {
         const int rc = N == 128 ? launch_rows_r16<real, KIND, true, 16, 8>(field, chains, N, log2n, W, 1.0, o, sms, st)
                                 : launch_rows_r16<real, KIND, true, 16, 16>(field, chains, N, log2n, W, 1.0, o, sms, st);

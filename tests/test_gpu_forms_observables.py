@@ -223,7 +223,7 @@ def test_split_column_transforms_match_the_reference_formula(N, monkeypatch):
     np.testing.assert_allclose(Cs, whole, rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize('N,chains', [(128, 5), (256, 3), (512, 2)])
+@pytest.mark.parametrize('N,chains', [(128, 5), (256, 3), (512, 2), (1024, 2), (2048, 1)])
 def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypatch):
     """128 <= N <= 512 (config 4's lattices): the row kernels of the split with 4096 / N rows per item and the fused
     column kernel (correlation_columns_fused_kernel), all three kinds, against the restated Lattice.correlation
