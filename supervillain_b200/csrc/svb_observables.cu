@@ -877,6 +877,8 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
     double2* wl = d + (size_t)lines * RS;                               // W_LL^t, t < LL
     double2* th = wl + LL;                                              // W_N^{64 a}, a < 64
     double2* tl = th + kSplitN2;                                        // W_N^b, b < 64
+    real* stage = reinterpret_cast<real*>(tl + kSplitN2);               // FIRST, spin fields: the NEXT item's 4096 field values (TMA)
+    constexpr bool STAGED = FIRST && KIND != SVB_CORR_WINDING;
     fft_n1_twiddles(wl, LL);
     for (int i = threadIdx.x; i < kSplitN2; i += blockDim.x) {
         double sn, cs;
@@ -890,6 +892,10 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
     if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); fence_mbar_init(); }
     uint32_t ld_parity = 0;
     constexpr uint32_t kLineBytes = LL * sizeof(double2);
+    auto load_field = [&](long long item) {                             // thread 0: an item's field values are contiguous
+        mbar_expect_tx(&ld_bar, (uint32_t)(E * sizeof(real)));
+        bulk_g2s(stage, field + item * E, (uint32_t)(E * sizeof(real)), &ld_bar);
+    };
     auto load_rows = [&](const double2* src) {
         if (lane == 0) mbar_expect_tx(&ld_bar, (uint32_t)E * (uint32_t)sizeof(double2));
         __syncwarp();
@@ -909,14 +915,13 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
     };
     __syncthreads();
     if (!FIRST && warp == 0 && blockIdx.x < items) load_rows(out + (long long)blockIdx.x * E);
+    if (STAGED && threadIdx.x == 0 && blockIdx.x < items) load_field(blockIdx.x);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long chain = item / items_per_chain, next = item + gridDim.x;
         const int x0 = (int)(item - chain * items_per_chain) << log2r;
         double2* o = out + item * E;
         if (FIRST) {
             const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
-            if (KIND != SVB_CORR_WINDING && threadIdx.x == 0 && next < items)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(field + next * E), "r"((uint32_t)E * (uint32_t)sizeof(real)) : "memory");
             if (warp == 0) bulk_wait_read0();
             __syncthreads();
             if (KIND == SVB_CORR_WINDING) {
@@ -927,22 +932,20 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
                     d[pad(e)] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + at]) - ((long long)g[i1] - (long long)g[at])), 0.0);
                 }
             } else {
-                constexpr int kBatch = 8;
-                const real* rows = g + (long long)x0 * N;
-                for (int eb = threadIdx.x; eb < E; eb += kBatch * blockDim.x) {
-                    real v[kBatch];
-#pragma unroll
-                    for (int j = 0; j < kBatch; ++j) v[j] = rows[eb + j * blockDim.x];        // (E is a multiple of 8 x 256)
-#pragma unroll
-                    for (int j = 0; j < kBatch; ++j) {
-                        double sn, cs;
-                        const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)v[j]) / (double)W : (double)v[j];
-                        sincos(ang, &sn, &cs);
-                        d[pad(eb + j * blockDim.x)] = make_double2(cs, sn);
-                    }
+                // the field values arrived by TMA while the previous item was being transformed; the next item's are requested
+                // as soon as these have been read
+                mbar_wait(&ld_bar, ld_parity);
+                ld_parity ^= 1u;
+                for (int e = threadIdx.x; e < E; e += blockDim.x) {
+                    double sn, cs;
+                    const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)stage[e]) / (double)W : (double)stage[e];
+                    sincos(ang, &sn, &cs);
+                    d[pad(e)] = make_double2(cs, sn);
                 }
+                fence_proxy_async();
             }
             __syncthreads();
+            if (STAGED && threadIdx.x == 0 && next < items) load_field(next);
             if (log2n1 > 0) small_dft_pass_n1<true>(log2n1, d, E >> log2n1, RS, start, tw);
             fft_rr<true, RA, RB>(d, 1, RS, LOG2LINES, wl);
             fence_proxy_async();
@@ -1053,7 +1056,8 @@ template <typename real, int KIND, bool FIRST, int RA, int RB>
 static int launch_rows_r16(const void* field, long long chains, int N, int log2n, int W, double scale, double2* o, int sms, cudaStream_t st) {
     constexpr int LL = RA * RB, LOG2LL = LL == 256 ? 8 : 7;
     auto kern = correlation_rows_r16_kernel<real, KIND, FIRST, RA, RB>;
-    const size_t smem = ((size_t)(4096 / LL) * (LL + 1) + LL + 2 * kSplitN2) * sizeof(double2);
+    const size_t smem = ((size_t)(4096 / LL) * (LL + 1) + LL + 2 * kSplitN2) * sizeof(double2) +
+                        (FIRST && KIND != SVB_CORR_WINDING ? 4096 * sizeof(real) : 0);      // + the staged field values of the next item
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -1119,6 +1123,7 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
     if (const char* e = getenv("SVB_CORR_MID_MAX_N")) mid_max = atoi(e);
     int r16 = 1;
     if (const char* e = getenv("SVB_CORR_R16")) r16 = atoi(e);
+    if ((uintptr_t)field % 16) r16 = 0;                            // (the radix-16 row kernel stages the field by bulk copies)
     if (r16 <= 0 && mid_max > 512) mid_max = 512;                  // (the 64-line kernels take several rows per item only for n1 <= 8)
     const bool mid = N <= mid_max && !getenv("SVB_CORR_SPLIT_MIN_N") && !(route && !strcmp(route, "legacy"));
     const bool split = mid || (N >= split_min && N >= 2 * kSplitN2);
