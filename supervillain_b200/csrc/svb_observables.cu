@@ -542,7 +542,28 @@ __device__ __forceinline__ void dft_small(double2 (&x)[N1]) {
     else if constexpr (N1 == 16) dft16(x);
 }
 // n1-point transforms over elements `stride` apart, one per work item: item i starts at d[start(i)], tw(i, k) multiplies
-// output k of a decimation-in-frequency transform / input k of a decimation-in-time one
+// output k of a decimation-in-frequency transform / input k of a decimation-in-time one.  PowerTw{w}: the factors of item i
+// are the powers w(i)^k, built by repeated multiplication (k <= 15: within 2e-15) -- one look-up per item instead of one or two
+// per element, which was a quarter of the row kernels' shared-memory traffic.
+template <class F> struct PowerTw { F base; };
+template <class F> __device__ __forceinline__ PowerTw<F> power_tw(F f) { return PowerTw<F>{f}; }
+template <class T> struct is_power_tw : std::false_type {};
+template <class F> struct is_power_tw<PowerTw<F>> : std::true_type {};
+template <int N1, class Tw>
+__device__ __forceinline__ void small_dft_twiddle(double2 (&x)[N1], int i, Tw& tw) {
+    if constexpr (is_power_tw<Tw>::value) {
+        const double2 w1 = tw.base(i);
+        double2 wk = w1;
+#pragma unroll
+        for (int k = 1; k < N1; ++k) {
+            x[k] = cmul(x[k], wk);
+            if (k + 1 < N1) wk = cmul(wk, w1);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N1; ++k) x[k] = cmul(x[k], tw(i, k));
+    }
+}
 template <int N1, bool DIF, class Start, class Tw>
 __device__ __forceinline__ void small_dft_pass(double2* __restrict__ d, int items, int stride, Start start, Tw tw) {
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -550,15 +571,9 @@ __device__ __forceinline__ void small_dft_pass(double2* __restrict__ d, int item
         double2 x[N1];
 #pragma unroll
         for (int j = 0; j < N1; ++j) x[j] = base[j * stride];
-        if constexpr (!DIF && !std::is_same<Tw, NoScale>::value) {
-#pragma unroll
-            for (int j = 0; j < N1; ++j) x[j] = cmul(x[j], tw(i, j));
-        }
+        if constexpr (!DIF && !std::is_same<Tw, NoScale>::value) small_dft_twiddle<N1>(x, i, tw);
         dft_small<N1>(x);
-        if constexpr (DIF && !std::is_same<Tw, NoScale>::value) {
-#pragma unroll
-            for (int k = 0; k < N1; ++k) x[k] = cmul(x[k], tw(i, k));
-        }
+        if constexpr (DIF && !std::is_same<Tw, NoScale>::value) small_dft_twiddle<N1>(x, i, tw);
 #pragma unroll
         for (int k = 0; k < N1; ++k) base[k * stride] = x[k];
     }
@@ -909,10 +924,10 @@ __global__ void __launch_bounds__(256, 2) correlation_rows_r16_kernel(const real
     const int items_per_chain = (int)(V >> 12), log2r = 12 - log2n;
     auto pad = [&](int i) { return i + (i >> LOG2LL); };
     auto start = [&](int i) { return (i >> LOG2LL) * n1 * RS + (i & (LL - 1)); };        // (row, r2): line row n1, element r2
-    auto tw = [&](int i, int k1) {                                      // W_N^{r2 k1}
-        const int t = (i & (LL - 1)) * k1;
+    auto tw = power_tw([&](int i) {                                     // W_N^{r2 k1} = (W_N^{r2})^{k1}
+        const int t = i & (LL - 1);
         return cmul(th[t >> kSplitLog2N2], tl[t & (kSplitN2 - 1)]);
-    };
+    });
     __syncthreads();
     if (!FIRST && warp == 0 && blockIdx.x < items) load_rows(out + (long long)blockIdx.x * E);
     if (STAGED && threadIdx.x == 0 && blockIdx.x < items) load_field(blockIdx.x);
@@ -1001,7 +1016,7 @@ __global__ void __launch_bounds__(256, 2) correlation_columns_r16_kernel(const _
         mbar_wait(&ld_bar, ld_parity);
         ld_parity ^= 1u;
         if (log2n1 > 0) {
-            small_dft_pass_n1<true>(log2n1, d, LL << log2cw, CW, start, [&](int i, int k) { return tN[(i >> log2cw) * k]; });
+            small_dft_pass_n1<true>(log2n1, d, LL << log2cw, CW, start, power_tw([&](int i) { return tN[i >> log2cw]; }));
             fft_rr<true, RA, RB>(d, lines, 1, LOG2LINES, wl, Norm2());
             fft_rr<false, RA, RB>(d, lines, 1, LOG2LINES, wl, NoScale(), [&](int L, int q) { return tN[(L >> log2cw) * q]; });
             small_dft_pass_n1<false>(log2n1, d, LL << log2cw, CW, start, NoScale());
