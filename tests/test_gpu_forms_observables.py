@@ -260,6 +260,27 @@ def test_mid_lattice_correlators_match_the_reference_formula(N, chains, monkeypa
         np.testing.assert_allclose(Cv[c], lat.correlation(e, e), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('N,chains', [(128, 333), (256, 90), (512, 21)])
+def test_mid_lattice_correlators_many_items_per_cta(N, chains, monkeypatch):
+    """More work items than resident CTAs (2 per SM x 148): every CTA of the TMA-fed kernels goes round its loop several
+    times -- the next tile requested when the store of this one has read shared memory, the staged field of the next item,
+    the mbarrier parities -- and an odd chain count leaves some CTAs one item short.  All three kinds against the
+    radix-2 kernels (SVB_CORR_ROUTE=legacy), which share none of that machinery, and a few chains against numpy."""
+    monkeypatch.delenv('SVB_CORR_SPLIT_MIN_N', raising=False)
+    rng = np.random.default_rng(N)
+    tphi = torch.from_numpy(rng.uniform(-7, 7, (chains, 1, N, N))).cuda()
+    tn = torch.from_numpy(rng.integers(-3, 4, (chains, 2, N, N))).to(torch.int32).cuda()
+    tv = torch.from_numpy(rng.integers(-4, 5, (chains, 1, N, N))).to(torch.int32).cuda()
+    got = [ops.villain_spin_spin(tphi), ops.correlation('winding', tn), ops.correlation('vortex', tv, W=5)]
+    monkeypatch.setenv('SVB_CORR_ROUTE', 'legacy')
+    ref = [ops.villain_spin_spin(tphi), ops.correlation('winding', tn), ops.correlation('vortex', tv, W=5)]
+    for g, r, tol in zip(got, ref, (1e-13, 1e-11, 1e-13)):
+        assert float((g - r).abs().max()) < tol
+    for c in (0, chains // 2, chains - 1):
+        s = np.exp(1j * tphi[c, 0].cpu().numpy())
+        np.testing.assert_allclose(got[0][c].cpu().numpy(), lat.correlation(s, s), rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize('N', [32, 128, 256])
 def test_spin_correlator_for_large_angles(N):
     """phi is never wrapped by the reference's updates, so a long run can reach angles of any magnitude: the spin field
