@@ -326,6 +326,103 @@ __global__ void __launch_bounds__(256) correlation_fft_kernel(const real* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// L = 32 (config 2's lattices) with a WARP per chain and a whole line of 32 elements per thread: three visits of shared
+// memory instead of eight -- rows; columns, |.|^2 and the columns of the second transform without leaving the registers;
+// rows -- and no block-wide barrier anywhere.  dft32 = 8 x 4 in registers with compile-time twiddles.
+// Measured SLOWER than correlation_fft_kernel<32> (122 against 102 us for 8192 chains: 150 registers leave 13 warps per SM to
+// hide the latencies of 32 sincos and of the fp64 butterflies), so it is opt-in (SVB_CORR_FFT32_WARP=1) and kept as an
+// independent implementation the tests compare with.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 w32(int m) {                       // e^{-2 pi i m / 32}, m < 32 (folded after unrolling)
+    constexpr double C[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                             0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0};
+    const int q = m >> 3, r = m & 7;
+    const double c = C[r], sn = C[8 - r];
+    return q == 0 ? make_double2(c, -sn) : q == 1 ? make_double2(-sn, -c) : q == 2 ? make_double2(-c, sn) : make_double2(sn, c);
+}
+// natural order in (n = 4 a + b); position p = 4 k_a + k_b of the result holds frequency k_a + 8 k_b
+__device__ __forceinline__ void dft32(double2 (&x)[32]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double2 t[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) t[a] = x[4 * a + b];
+        dft8(t);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) x[4 * a + b] = (a * b == 0) ? t[a] : cmul(t[a], w32(a * b));
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        double2 t[4] = {x[4 * a], x[4 * a + 1], x[4 * a + 2], x[4 * a + 3]};
+        dft4(t);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[4 * a + b] = t[b];
+    }
+}
+__host__ __device__ constexpr int dft32_freq(int p) { return (p >> 2) + 8 * (p & 3); }
+
+template <typename real, int KIND>
+__global__ void __launch_bounds__(32) correlation_fft32_warp_kernel(const real* __restrict__ field, long long chains, int W,
+                                                                    double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = 32, V = N * N, RS = N + 1;
+    double2* d = reinterpret_cast<double2*>(smem_raw);                 // [32][33]
+    const int lane = threadIdx.x;
+    const double scale = 1.0 / ((double)V * (double)V);
+    for (long long chain = blockIdx.x; chain < chains; chain += gridDim.x) {
+        const real* g = field + chain * (KIND == SVB_CORR_WINDING ? 2 : 1) * V;
+        bulk_wait_read0();                                              // this lane's row of the previous result has left the tile
+        __syncwarp();
+#pragma unroll 4
+        for (int x0 = 0; x0 < N; ++x0) {
+            const int i = x0 * N + lane;
+            if (KIND == SVB_CORR_WINDING) {
+                const int i0 = ((x0 + 1) & (N - 1)) * N + lane, i1 = x0 * N + ((lane + 1) & (N - 1));
+                d[x0 * RS + lane] = make_double2((double)(((long long)g[V + i0] - (long long)g[V + i]) - ((long long)g[i1] - (long long)g[i])), 0.0);
+            } else {
+                double sn, cs;
+                const double ang = (KIND == SVB_CORR_VORTEX) ? (SVB_TWO_PI * (double)g[i]) / (double)W : (double)g[i];
+                sincos(ang, &sn, &cs);
+                d[x0 * RS + lane] = make_double2(cs, sn);
+            }
+        }
+        __syncwarp();
+        double2 x[32];
+        // along x1: this lane's row
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = d[lane * RS + j];
+        dft32(x);
+#pragma unroll
+        for (int p = 0; p < N; ++p) d[lane * RS + dft32_freq(p)] = x[p];
+        __syncwarp();
+        // along x0: this lane's column; |.|^2; the second transform along the same axis straight away
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = d[j * RS + lane];
+        dft32(x);
+        {
+            double2 y[32];
+#pragma unroll
+            for (int p = 0; p < N; ++p) y[dft32_freq(p)] = make_double2(x[p].x * x[p].x + x[p].y * x[p].y, 0.0);
+            dft32(y);
+#pragma unroll
+            for (int p = 0; p < N; ++p) d[dft32_freq(p) * RS + lane] = y[p];
+        }
+        __syncwarp();
+        // along k1 -> r1: this lane's row of the result
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = d[lane * RS + j];
+        dft32(x);
+#pragma unroll
+        for (int p = 0; p < N; ++p) d[lane * RS + dft32_freq(p)] = make_double2(x[p].x * scale, x[p].y * scale);
+        fence_proxy_async();
+        __syncwarp();
+        bulk_s2g(reinterpret_cast<double2*>(out) + chain * V + lane * N, d + lane * RS, (uint32_t)(N * sizeof(double2)));
+        bulk_commit();
+    }
+    bulk_wait0();
+}
+
+// ------------------------------------------------------------------------------------------
 // Power-of-two lattices beyond shared memory (128 <= N <= 4096: configs 4 and 5) -- the same transform in three launches
 // that use `out` (chains, N, N) complex128 itself as the workspace:
 //   1. rows:    s from the field, decimation-in-frequency FFT of R rows per CTA, written in bit-reversed column order;
@@ -1241,6 +1338,22 @@ static int launch_correlation_fft_large(const void* field, long long chains, int
 
 template <typename real, int KIND, int NT>
 static int launch_correlation_fft(const void* field, long long chains, int W, double* out, int sms, cudaStream_t st) {
+    int warp32 = 0;                                                // SVB_CORR_FFT32_WARP=1: L = 32 with a warp per chain and a line per thread -- three visits of
+                                                                   // shared memory instead of eight, but 150 registers and 13 warps per SM: 122 against 102 us
+                                                                   // for 8192 chains, so the CTA kernel stays the default
+    if (const char* e = getenv("SVB_CORR_FFT32_WARP")) warp32 = atoi(e);
+    if (NT == 32 && warp32) {
+        auto kw = correlation_fft32_warp_kernel<real, KIND>;
+        const size_t smem_w = (size_t)32 * 33 * sizeof(double2);
+        SVB_CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        int per_sm = 0;
+        SVB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kw, 32, smem_w));
+        if (per_sm < 1) per_sm = 1;
+        const long long cap = (long long)per_sm * sms;
+        kw<<<(unsigned)(chains < cap ? chains : cap), 32, smem_w, st>>>(reinterpret_cast<const real*>(field), chains, W, out);
+        SVB_CUDA_TRY(cudaGetLastError());
+        return SVB_OK;
+    }
     auto kern = correlation_fft_kernel<real, KIND, NT>;
     const size_t smem = (size_t)(NT * (NT + 1) + NT) * sizeof(double2);      // the padded tile and the N twiddles (>= the radix-2 layout)
     SVB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

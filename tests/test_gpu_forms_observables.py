@@ -281,6 +281,28 @@ def test_mid_lattice_correlators_many_items_per_cta(N, chains, monkeypatch):
         np.testing.assert_allclose(got[0][c].cpu().numpy(), lat.correlation(s, s), rtol=0, atol=1e-12)
 
 
+def test_warp_per_chain_l32_correlator_equals_the_cta_kernel(monkeypatch):
+    """L = 32: correlation_fft32_warp_kernel (a warp per chain, 32-point transforms in registers; opt-in with
+    SVB_CORR_FFT32_WARP=1, it measured slower) against the default correlation_fft_kernel<32> for all kinds and against
+    numpy, with more chains than resident warps and an odd count: two independent implementations of the same transform."""
+    N, chains = 32, 5003
+    rng = np.random.default_rng(32)
+    tphi = torch.from_numpy(rng.uniform(-7, 7, (chains, 1, N, N))).cuda()
+    tn = torch.from_numpy(rng.integers(-3, 4, (chains, 2, N, N))).to(torch.int32).cuda()
+    tv = torch.from_numpy(rng.integers(-4, 5, (chains, 1, N, N))).to(torch.int32).cuda()
+    monkeypatch.setenv('SVB_CORR_FFT32_WARP', '1')
+    got = [ops.villain_spin_spin(tphi), ops.villain_spin_spin(tphi.to(torch.float32)), ops.correlation('winding', tn), ops.correlation('vortex', tv, W=5)]
+    monkeypatch.setenv('SVB_CORR_FFT32_WARP', '0')
+    ref = [ops.villain_spin_spin(tphi), ops.villain_spin_spin(tphi.to(torch.float32)), ops.correlation('winding', tn), ops.correlation('vortex', tv, W=5)]
+    for g, r, tol in zip(got, ref, (1e-13, 1e-13, 1e-11, 1e-13)):
+        assert float((g - r).abs().max()) < tol
+    for c in (0, 2500, chains - 1):
+        s = np.exp(1j * tphi[c, 0].cpu().numpy())
+        np.testing.assert_allclose(got[0][c].cpu().numpy(), lat.correlation(s, s), rtol=0, atol=1e-12)
+        dn = lat.d1(tn[c].cpu().numpy().astype(np.int64))[0].astype(np.float64)
+        np.testing.assert_allclose(got[2][c].cpu().numpy(), lat.correlation(dn, dn), rtol=0, atol=1e-11)
+
+
 @pytest.mark.parametrize('N', [32, 128, 256])
 def test_spin_correlator_for_large_angles(N):
     """phi is never wrapped by the reference's updates, so a long run can reach angles of any magnitude: the spin field
